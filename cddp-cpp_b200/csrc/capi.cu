@@ -1,0 +1,718 @@
+// C ABI of the B200 batched CLDDP engine (include/cddp_b200.h): handle, HBM buffers, the host
+// side of the per-iteration launch sequence.  No solver arithmetic happens on the host: the host
+// only launches fixed-shape kernels and polls a running-instance counter
+// (CDDPSolverBase::solve outer loop, src/cddp_core/cddp_solver_base.cpp:74-154, lives on the
+// device as a per-instance state machine — see backward.cu / forward.cu).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+using namespace cddp_b200;
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+int cuda_fail(cudaError_t e, const char *what) {
+  g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorMemoryAllocation) ? CDDP_B200_ERR_OUT_OF_MEMORY : CDDP_B200_ERR_CUDA;
+}
+
+#define CU(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+int build_alphas(const cddp_b200_options &o, double *alphas, int cap) {
+  // detail::buildLineSearchAlphas, src/cddp_core/cddp_context_utils.cpp:37-57
+  int cnt = 0;
+  double a = o.ls_initial_step_size;
+  for (int i = 0; i < o.ls_max_iterations && cnt < cap; ++i) {
+    alphas[cnt++] = a;
+    a *= o.ls_step_reduction_factor;
+    if (a < o.ls_min_step_size && i < o.ls_max_iterations - 1) {
+      if (cnt < cap) alphas[cnt++] = o.ls_min_step_size;
+      break;
+    }
+  }
+  if (cnt == 0) alphas[cnt++] = o.ls_initial_step_size;
+  return cnt;
+}
+
+int count_alphas(const cddp_b200_options &o) {
+  double tmp[256];
+  return build_alphas(o, tmp, 256);
+}
+
+}  // namespace
+
+struct cddp_b200_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Constants c{};
+  DeviceState d{};
+  std::vector<void *> allocs;
+  double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
+  int *h_running = nullptr;  // pinned
+  bool initialized = false;
+  bool have_instances = false;
+  bool timing_enabled = false;
+  cddp_b200_timing timing{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch for host-pointer setters / getters
+  double *scratch = nullptr;
+  size_t scratch_bytes = 0;
+
+  template <typename T>
+  int alloc(T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return 0;
+  }
+  int ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return 0;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr;
+    scratch_bytes = 0;
+    cudaError_t e = cudaMalloc((void **)&scratch, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    scratch_bytes = bytes;
+    return 0;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int now = -1;
+    if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+  }
+};
+
+int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch) {
+  if (!p || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (batch < 1 || p->horizon < 1 || !(p->dt > 0.0)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (p->n < 1 || p->n > CDDP_B200_MAX_N || p->m < 1 || p->m > CDDP_B200_MAX_M) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!p->Q || !p->R || !p->Qf) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (p->has_control_box && (!p->lb || !p->ub)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (p->integrator < CDDP_B200_EULER || p->integrator > CDDP_B200_RK4) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  switch (p->model) {
+    case CDDP_B200_MODEL_PENDULUM: if (p->n != 2 || p->m != 1) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    case CDDP_B200_MODEL_CARTPOLE: if (p->n != 4 || p->m != 1) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    case CDDP_B200_MODEL_UNICYCLE: if (p->n != 3 || p->m != 2) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    case CDDP_B200_MODEL_QUADROTOR: if (p->n != 13 || p->m != 4) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    case CDDP_B200_MODEL_LTI: if (!p->lti_A || !p->lti_B) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    default: return CDDP_B200_ERR_UNSUPPORTED_MODEL;
+  }
+  if (o->max_iterations < 0 || o->ls_max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  return 0;
+}
+
+void set_options(cddp_b200_solver *s, const cddp_b200_options &o) {
+  s->c.opt = o;
+  s->c.num_alphas = build_alphas(o, s->c.alphas, CDDP_B200_MAX_ALPHAS);
+  s->d.num_alphas = s->c.num_alphas;
+}
+
+struct KernelTimer {
+  cddp_b200_solver *s;
+  double *acc;
+  bool on;
+  KernelTimer(cddp_b200_solver *s_, double *acc_) : s(s_), acc(acc_), on(s_->timing_enabled) {
+    if (on) cudaEventRecord(s->ev0, s->stream);
+  }
+  void stop() {
+    if (!on) return;
+    cudaEventRecord(s->ev1, s->stream);
+    cudaEventSynchronize(s->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    *acc += ms;
+  }
+};
+
+int do_linearize(cddp_b200_solver *s, bool force) {
+  KernelTimer t(s, &s->timing.linearize_ms);
+  CU(launch_linearize(s->c, s->d, force, s->stream));
+  t.stop();
+  s->timing.linearize_launches++;
+  return 0;
+}
+int do_backward(cddp_b200_solver *s, int mode) {
+  KernelTimer t(s, &s->timing.backward_ms);
+  CU(launch_backward(s->c, s->d, mode, s->stream));
+  t.stop();
+  s->timing.backward_launches++;
+  return 0;
+}
+int do_forward(cddp_b200_solver *s, int mode) {
+  KernelTimer t(s, &s->timing.forward_ms);
+  CU(launch_forward(s->c, s->d, mode, s->stream));
+  t.stop();
+  s->timing.forward_launches++;
+  return 0;
+}
+
+int one_iteration(cddp_b200_solver *s) {
+  int r;
+  if ((r = do_linearize(s, false))) return r;
+  if ((r = do_backward(s, BW_ITERATE))) return r;
+  if ((r = do_forward(s, FW_ITERATE))) return r;
+  return 0;
+}
+
+int read_running(cddp_b200_solver *s, int *running) {
+  CU(launch_count_running(s->d, s->stream));
+  s->timing.other_launches++;
+  CU(cudaMemcpyAsync(s->h_running, s->d.num_running, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  *running = *s->h_running;
+  return 0;
+}
+
+int upload(cddp_b200_solver *s, double *dst, const double *src, size_t count, bool device_src) {
+  if (!src) {
+    CU(cudaMemsetAsync(dst, 0, count * sizeof(double), s->stream));
+    return 0;
+  }
+  CU(cudaMemcpyAsync(dst, src, count * sizeof(double), device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     s->stream));
+  return 0;
+}
+
+int set_instances_impl(cddp_b200_solver *s, const double *x0, const double *xref, const double *ref_traj,
+                       const double *X0, const double *U0, bool dev) {
+  if (!s || !x0 || !xref) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
+  const DeviceState &d = s->d;
+  const size_t B = d.B, n = d.n, m = d.m, N = d.N;
+  int r;
+  if ((r = upload(s, d.x0, x0, B * n, dev))) return r;
+  if ((r = upload(s, d.xref, xref, B * n, dev))) return r;
+  if (ref_traj) {
+    if (!s->d.ref_traj) {
+      double *p = nullptr;
+      if ((r = s->alloc(&p, B * (N + 1) * n))) return r;
+      s->d.ref_traj = p;
+    }
+    if ((r = upload(s, s->d.ref_traj, ref_traj, B * (N + 1) * n, dev))) return r;
+  } else {
+    s->d.ref_traj = nullptr;  // (buffer, if any, stays owned by allocs)
+  }
+  CU(cudaMemsetAsync(d.cur, 0, B * sizeof(int), s->stream));
+  if ((r = upload(s, d.X[0], X0, B * (N + 1) * n, dev))) return r;
+  if ((r = upload(s, d.U[0], U0, B * N * m, dev))) return r;
+  s->have_instances = true;
+  s->initialized = false;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cddp_b200_abi_version(void) { return CDDP_B200_ABI_VERSION; }
+
+const char *cddp_b200_error_string(int err) {
+  switch (err) {
+    case CDDP_B200_OK: return "ok";
+    case CDDP_B200_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case CDDP_B200_ERR_UNSUPPORTED_MODEL:
+      return "unsupported model: the dynamics have no device implementation (there is no CPU fallback)";
+    case CDDP_B200_ERR_CUDA: return "CUDA error (see cddp_b200_last_cuda_error)";
+    case CDDP_B200_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case CDDP_B200_ERR_STATE: return "invalid call order";
+    default: return "unknown error";
+  }
+}
+
+const char *cddp_b200_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+const char *cddp_b200_status_string(int status) {
+  switch (status) {
+    case CDDP_B200_STATUS_OPTIMAL: return "OptimalSolutionFound";
+    case CDDP_B200_STATUS_ACCEPTABLE: return "AcceptableSolutionFound";
+    case CDDP_B200_STATUS_MAX_ITERATIONS: return "MaxIterationsReached";
+    case CDDP_B200_STATUS_REG_LIMIT: return "RegularizationLimitReached_NotConverged";
+    case CDDP_B200_STATUS_MAX_CPU_TIME: return "MaxCpuTimeReached";
+    default: return "Running";
+  }
+}
+
+int cddp_b200_device_count(int *count) {
+  if (!count) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *count = 0;
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+void cddp_b200_default_options(cddp_b200_options *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->tolerance = 1e-5;
+  o->acceptable_tolerance = 1e-6;
+  o->max_iterations = 1;
+  o->max_cpu_time = 0.0;
+  o->termination_scaling_max_factor = 100.0;
+  o->ls_max_iterations = 11;
+  o->ls_initial_step_size = 1.0;
+  o->ls_min_step_size = 1e-8;
+  o->ls_step_reduction_factor = 0.5;
+  o->reg_initial_value = 1e-6;
+  o->reg_update_factor = 10.0;
+  o->reg_max_value = 1e7;
+  o->reg_min_value = 1e-10;
+  o->qp_max_iterations = 100;
+  o->qp_min_gradient_norm = 1e-8;
+  o->qp_min_relative_improvement = 1e-8;
+  o->qp_step_decrease_factor = 0.6;
+  o->qp_min_step_size = 1e-22;
+  o->qp_armijo_constant = 0.1;
+  o->armijo_constant = 1e-4;
+}
+
+int cddp_b200_build_alphas(const cddp_b200_options *opts, double *alphas, int capacity, int *count) {
+  if (!opts || !alphas || !count || capacity < 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *count = build_alphas(*opts, alphas, capacity);
+  return 0;
+}
+
+int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, int device,
+                     cddp_b200_solver **out) {
+  if (!out) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int r = validate(p, o, batch);
+  if (r) return r;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return cuda_fail(cudaErrorInvalidDevice, "device index");
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
+  cddp_b200_solver *s = new (std::nothrow) cddp_b200_solver();
+  if (!s) return CDDP_B200_ERR_OUT_OF_MEMORY;
+  s->device = device;
+  const int n = p->n, m = p->m, N = p->horizon;
+  const size_t B = batch;
+  Constants &c = s->c;
+  DeviceState &d = s->d;
+  c.model = p->model; c.n = n; c.m = m; c.N = N; c.integrator = p->integrator; c.has_box = p->has_control_box ? 1 : 0;
+  c.dt = p->dt;
+  std::memcpy(c.mp.p, p->model_params, sizeof(c.mp.p));
+  c.mp.n = n; c.mp.m = m;
+  for (int i = 0; i < CDDP_B200_MAX_M; ++i) {
+    c.lb[i] = (p->has_control_box && i < m) ? p->lb[i] : -INFINITY;
+    c.ub[i] = (p->has_control_box && i < m) ? p->ub[i] : INFINITY;
+  }
+  d.B = batch; d.n = n; d.m = m; d.N = N; d.rec_stride = record_stride(n, m);
+  set_options(s, *o);
+
+#define AL(ptr, cnt)                       \
+  do {                                     \
+    if ((r = s->alloc(&(ptr), (cnt)))) {   \
+      cddp_b200_destroy(s);                \
+      return r;                            \
+    }                                      \
+  } while (0)
+  // batch-shared constants: l_xx = 2 Q dt, l_uu = 2 R dt, phi_xx = 2 Qf (objective.cpp:38-39,130-154)
+  std::vector<double> hQ((size_t)n * n), hR((size_t)m * m), hQf((size_t)n * n);
+  for (int i = 0; i < n * n; ++i) { hQ[i] = 2.0 * (p->Q[i] * p->dt); hQf[i] = 2.0 * p->Qf[i]; }
+  for (int i = 0; i < m * m; ++i) hR[i] = 2.0 * (p->R[i] * p->dt);
+  AL(s->dQdt2, (size_t)n * n); AL(s->dRdt2, (size_t)m * m); AL(s->dQf2, (size_t)n * n);
+  cudaError_t e;
+  e = cudaMemcpy(s->dQdt2, hQ.data(), hQ.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(s->dRdt2, hR.data(), hR.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(s->dQf2, hQf.data(), hQf.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && p->model == CDDP_B200_MODEL_LTI) {
+    AL(s->dltiA, (size_t)n * n); AL(s->dltiB, (size_t)n * m);
+    e = cudaMemcpy(s->dltiA, p->lti_A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->dltiB, p->lti_B, (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { cddp_b200_destroy(s); return cuda_fail(e, "cudaMemcpy(constants)"); }
+  c.Qdt2 = s->dQdt2; c.Rdt2 = s->dRdt2; c.Qf2 = s->dQf2;
+  c.mp.lti_A = s->dltiA; c.mp.lti_B = s->dltiB;
+
+  AL(d.X[0], B * (N + 1) * n); AL(d.X[1], B * (N + 1) * n);
+  AL(d.U[0], B * N * m); AL(d.U[1], B * N * m);
+  AL(d.rec, B * N * d.rec_stride);
+  AL(d.vterm, B * n);
+  AL(d.K, B * N * m * n); AL(d.kff, B * N * m);
+  AL(d.x0, B * n); AL(d.xref, B * n);
+  d.ref_traj = nullptr;
+  AL(d.cur, B); AL(d.status, B); AL(d.iter, B); AL(d.lin_valid, B); AL(d.bw_ok, B); AL(d.accepted, B);
+  AL(d.reg, B); AL(d.cost, B); AL(d.alpha, B); AL(d.inf_du, B); AL(d.dV, 2 * B);
+  AL(d.ls_cost, B * CDDP_B200_MAX_ALPHAS);
+  AL(d.Vx0, B * n); AL(d.Vxx0, B * n * n);
+  AL(d.num_running, 1);
+  d.history = nullptr; d.history_len = nullptr; d.history_cap = 0;
+#undef AL
+  e = cudaMemset(d.rec, 0, B * N * d.rec_stride * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(d.cur, 0, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d.status, 0, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d.K, 0, B * N * m * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(d.kff, 0, B * N * m * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(d.ls_cost, 0, B * CDDP_B200_MAX_ALPHAS * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_running, sizeof(int));
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e != cudaSuccess) { cddp_b200_destroy(s); return cuda_fail(e, "solver setup"); }
+  *out = s;
+  return 0;
+}
+
+int cddp_b200_destroy(cddp_b200_solver *s) {
+  if (!s) return 0;
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  for (void *p : s->allocs) cudaFree(p);
+  if (s->scratch) cudaFree(s->scratch);
+  if (s->h_running) cudaFreeHost(s->h_running);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+  return 0;
+}
+
+int cddp_b200_set_stream(cddp_b200_solver *s, void *stream) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->stream = static_cast<cudaStream_t>(stream);
+  return 0;
+}
+
+int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *o) {
+  if (!s || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS || o->max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (s->d.history && o->max_iterations + 1 > s->d.history_cap) return CDDP_B200_ERR_STATE;
+  set_options(s, *o);
+  return 0;
+}
+
+int cddp_b200_set_instances(cddp_b200_solver *s, const double *x0, const double *xref, const double *ref_traj,
+                            const double *X0, const double *U0) {
+  return set_instances_impl(s, x0, xref, ref_traj, X0, U0, false);
+}
+
+int cddp_b200_set_instances_device(cddp_b200_solver *s, const double *x0, const double *xref, const double *ref_traj,
+                                   const double *X0, const double *U0) {
+  return set_instances_impl(s, x0, xref, ref_traj, X0, U0, true);
+}
+
+int cddp_b200_initialize(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->have_instances) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  CU(launch_initialize(s->c, s->d, s->stream));
+  s->timing.other_launches++;
+  s->initialized = true;
+  return 0;
+}
+
+int cddp_b200_linearize(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->initialized) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  return do_linearize(s, true);
+}
+
+int cddp_b200_backward_pass(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->initialized) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  return do_backward(s, BW_SINGLE);
+}
+
+int cddp_b200_forward_pass(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->initialized) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  return do_forward(s, FW_EVALUATE);
+}
+
+int cddp_b200_iterate(cddp_b200_solver *s, int iterations) {
+  if (!s || iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->initialized) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  for (int i = 0; i < iterations; ++i) {
+    int r = one_iteration(s);
+    if (r) return r;
+  }
+  return 0;
+}
+
+int cddp_b200_solve(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->have_instances) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  int r = cddp_b200_initialize(s);
+  if (r) return r;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int max_it = s->c.opt.max_iterations;
+  int final_status = CDDP_B200_STATUS_MAX_ITERATIONS;
+  // poll the running counter with a widening stride: cheap for short solves, rare for long ones
+  int next_poll = 4;
+  for (int it = 0; it < max_it; ++it) {
+    if (s->c.opt.max_cpu_time > 0.0) {  // cddp_solver_base.cpp:77-90 (wall clock, checked per batched iteration)
+      CU(cudaStreamSynchronize(s->stream));
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el > s->c.opt.max_cpu_time) {
+        final_status = CDDP_B200_STATUS_MAX_CPU_TIME;
+        break;
+      }
+    }
+    if ((r = one_iteration(s))) return r;
+    if (it + 1 == next_poll && it + 1 < max_it) {
+      int running = 0;
+      if ((r = read_running(s, &running))) return r;
+      if (running == 0) break;
+      next_poll += (next_poll < 16) ? 4 : 8;
+    }
+  }
+  CU(launch_finalize(s->c, s->d, final_status, s->stream));
+  s->timing.other_launches++;
+  return 0;
+}
+
+int cddp_b200_num_running(cddp_b200_solver *s, int *running) {
+  if (!s || !running) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  return read_running(s, running);
+}
+
+int cddp_b200_synchronize(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static int download(cddp_b200_solver *s, void *dst, const void *src, size_t bytes) {
+  if (!dst) return 0;
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+  return 0;
+}
+
+int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                           int *iterations_completed, int *status, double *final_step_length,
+                           double *final_regularization, double *inf_du) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  const size_t B = d.B, n = d.n, m = d.m, N = d.N;
+  int r;
+  if (X || U) {
+    const size_t nx = B * (N + 1) * n, nu = B * N * m;
+    if ((r = s->ensure_scratch((nx + nu) * sizeof(double)))) return r;
+    CU(launch_gather_current(s->c, d, X ? s->scratch : nullptr, U ? s->scratch + nx : nullptr, 0, s->stream));
+    s->timing.other_launches++;
+    if ((r = download(s, X, s->scratch, nx * sizeof(double)))) return r;
+    if ((r = download(s, U, s->scratch + nx, nu * sizeof(double)))) return r;
+  }
+  if ((r = download(s, K, d.K, B * N * m * n * sizeof(double)))) return r;
+  if ((r = download(s, final_objective, d.cost, B * sizeof(double)))) return r;
+  if ((r = download(s, iterations_completed, d.iter, B * sizeof(int)))) return r;
+  if ((r = download(s, status, d.status, B * sizeof(int)))) return r;
+  if ((r = download(s, final_step_length, d.alpha, B * sizeof(double)))) return r;
+  if ((r = download(s, final_regularization, d.reg, B * sizeof(double)))) return r;
+  if ((r = download(s, inf_du, d.inf_du, B * sizeof(double)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_enable_history(cddp_b200_solver *s, int enable) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  if (!enable) {
+    s->d.history = nullptr;
+    return 0;
+  }
+  const int cap = s->c.opt.max_iterations + 1;
+  if (!s->d.history_len || cap > s->d.history_cap) {
+    double *h = nullptr;
+    int *l = nullptr;
+    int r;
+    if ((r = s->alloc(&h, (size_t)s->d.B * cap * 4))) return r;
+    if ((r = s->alloc(&l, (size_t)s->d.B))) return r;
+    s->d.history = h;
+    s->d.history_len = l;
+    s->d.history_cap = cap;
+    CU(cudaMemset(l, 0, (size_t)s->d.B * sizeof(int)));
+  }
+  return 0;
+}
+
+int cddp_b200_get_history(cddp_b200_solver *s, double *history, int *lens) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->d.history) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  int r;
+  if ((r = download(s, history, s->d.history, (size_t)s->d.B * s->d.history_cap * 4 * sizeof(double)))) return r;
+  if ((r = download(s, lens, s->d.history_len, (size_t)s->d.B * sizeof(int)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_get_feedforward(cddp_b200_solver *s, double *k) {
+  if (!s || !k) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  int r = download(s, k, s->d.kff, (size_t)s->d.B * s->d.N * s->d.m * sizeof(double));
+  if (r) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_set_gains(cddp_b200_solver *s, const double *K, const double *k) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  if (K) CU(cudaMemcpyAsync(d.K, K, (size_t)d.B * d.N * d.m * d.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (k) CU(cudaMemcpyAsync(d.kff, k, (size_t)d.B * d.N * d.m * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_set_regularization(cddp_b200_solver *s, const double *reg) {
+  if (!s || !reg) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  CU(cudaMemcpyAsync(s->d.reg, reg, (size_t)s->d.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_set_cost(cddp_b200_solver *s, const double *cost) {
+  if (!s || !cost) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  CU(cudaMemcpyAsync(s->d.cost, cost, (size_t)s->d.B * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_get_linearization(cddp_b200_solver *s, double *A, double *Bm) {
+  if (!s || !A || !Bm) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  const size_t na = (size_t)d.B * d.N * d.n * d.n, nb = (size_t)d.B * d.N * d.n * d.m;
+  int r;
+  if ((r = s->ensure_scratch((na + nb) * sizeof(double)))) return r;
+  CU(launch_unpack_linearization(s->c, d, s->scratch, s->scratch + na, s->stream));
+  s->timing.other_launches++;
+  if ((r = download(s, A, s->scratch, na * sizeof(double)))) return r;
+  if ((r = download(s, Bm, s->scratch + na, nb * sizeof(double)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_set_linearization(cddp_b200_solver *s, const double *A, const double *Bm) {
+  if (!s || !A || !Bm) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  const size_t na = (size_t)d.B * d.N * d.n * d.n, nb = (size_t)d.B * d.N * d.n * d.m;
+  int r;
+  if ((r = s->ensure_scratch((na + nb) * sizeof(double)))) return r;
+  CU(cudaMemcpyAsync(s->scratch, A, na * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->scratch + na, Bm, nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(launch_pack_linearization(s->c, d, s->scratch, s->scratch + na, s->stream));
+  s->timing.other_launches++;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_get_sweep(cddp_b200_solver *s, double *dV, int *ok, double *inf_du, double *Vx0, double *Vxx0) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  int r;
+  if ((r = download(s, dV, d.dV, (size_t)d.B * 2 * sizeof(double)))) return r;
+  if ((r = download(s, ok, d.bw_ok, (size_t)d.B * sizeof(int)))) return r;
+  if ((r = download(s, inf_du, d.inf_du, (size_t)d.B * sizeof(double)))) return r;
+  if ((r = download(s, Vx0, d.Vx0, (size_t)d.B * d.n * sizeof(double)))) return r;
+  if ((r = download(s, Vxx0, d.Vxx0, (size_t)d.B * d.n * d.n * sizeof(double)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_get_forward(cddp_b200_solver *s, double *costs, int *accepted, double *Xnew, double *Unew) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  const size_t B = d.B, n = d.n, m = d.m, N = d.N;
+  int r;
+  if (costs) {
+    std::vector<double> tmp(B * CDDP_B200_MAX_ALPHAS);
+    if ((r = download(s, tmp.data(), d.ls_cost, tmp.size() * sizeof(double)))) return r;
+    CU(cudaStreamSynchronize(s->stream));
+    for (size_t b = 0; b < B; ++b)
+      for (int a = 0; a < s->c.num_alphas; ++a) costs[b * s->c.num_alphas + a] = tmp[b * CDDP_B200_MAX_ALPHAS + a];
+  }
+  if ((r = download(s, accepted, d.accepted, B * sizeof(int)))) return r;
+  if (Xnew || Unew) {
+    const size_t nx = B * (N + 1) * n, nu = B * N * m;
+    if ((r = s->ensure_scratch((nx + nu) * sizeof(double)))) return r;
+    CU(launch_gather_current(s->c, d, Xnew ? s->scratch : nullptr, Unew ? s->scratch + nx : nullptr, 1, s->stream));
+    s->timing.other_launches++;
+    if ((r = download(s, Xnew, s->scratch, nx * sizeof(double)))) return r;
+    if ((r = download(s, Unew, s->scratch + nx, nu * sizeof(double)))) return r;
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_reset_timing(cddp_b200_solver *s) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->timing = cddp_b200_timing{};
+  return 0;
+}
+
+int cddp_b200_get_timing(cddp_b200_solver *s, cddp_b200_timing *t) {
+  if (!s || !t) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *t = s->timing;
+  return 0;
+}
+
+int cddp_b200_enable_timing(cddp_b200_solver *s, int enable) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->timing_enabled = enable != 0;
+  return 0;
+}
+
+int cddp_b200_backward_algorithmic_bytes(cddp_b200_solver *s, double *bytes) {
+  if (!s || !bytes) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  const double n = s->d.n, m = s->d.m;
+  *bytes = 8.0 * (n * n + 2 * n * m + n + 3 * m) * (double)s->d.N * (double)s->d.B;
+  return 0;
+}
+
+int cddp_b200_solve_host(const cddp_b200_problem *problem, const cddp_b200_options *opts, int batch, int device,
+                         const double *x0, const double *xref, const double *ref_traj, double *X, double *U, double *K,
+                         double *final_objective, int *iterations_completed, int *status, double *final_step_length,
+                         double *final_regularization, double *inf_du) {
+  cddp_b200_solver *s = nullptr;
+  int r = cddp_b200_create(problem, opts, batch, device, &s);
+  if (r) return r;
+  r = cddp_b200_set_instances(s, x0, xref, ref_traj, X, U);
+  if (!r) r = cddp_b200_solve(s);
+  if (!r)
+    r = cddp_b200_get_solution(s, X, U, K, final_objective, iterations_completed, status, final_step_length,
+                               final_regularization, inf_du);
+  cddp_b200_destroy(s);
+  return r;
+}
+
+}  // extern "C"

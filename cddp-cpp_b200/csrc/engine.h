@@ -1,0 +1,92 @@
+// Internal (non-ABI) definitions shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/cddp_b200.h"
+#include "models.cuh"
+
+namespace cddp_b200 {
+
+// ---- HBM layout (see DESIGN.md "Data layout") ----
+// All per-instance arrays are batch-outermost and contiguous per instance so that one warp streams
+// one trajectory.
+//
+//  X[2]     : [B][N+1][n]   double-buffered nominal / candidate state trajectory (cur[b] selects)
+//  U[2]     : [B][N][m]
+//  rec      : [B][N][rec_stride]  per-timestep linearisation record consumed by the backward sweep:
+//               A (n*n) | B (n*m) | lx (n) | lu (m) | u (m) | pad to an even count (16-byte multiple
+//               so that one cp.async.bulk moves one record)
+//  vterm    : [B][n]        terminal gradient V_x(N) = 2 Qf (x_N - ref)
+//  K        : [B][N][m][n]  feedback gains K_u_
+//  kff      : [B][N][m]     feed-forward k_u_ (updated in place: doubles as BoxQP warm start)
+struct DeviceState {
+  int B, n, m, N;
+  int rec_stride;  // doubles per record
+  int num_alphas;
+  double *X[2];
+  double *U[2];
+  double *rec;
+  double *vterm;
+  double *K;
+  double *kff;
+  double *x0;        // [B][n]
+  double *xref;      // [B][n]
+  double *ref_traj;  // [B][N+1][n] or nullptr
+  // per-instance scalars
+  int *cur;        // which X/U buffer holds the nominal trajectory
+  int *status;     // CDDP_B200_STATUS_*
+  int *iter;       // iterations_completed
+  int *lin_valid;  // rec matches the nominal trajectory
+  int *bw_ok;      // last backward sweep succeeded
+  int *accepted;   // index of the accepted alpha in the last line search (-1 none)
+  double *reg;     // regularization_
+  double *cost;    // cost_
+  double *alpha;   // alpha_pr_
+  double *inf_du;  // inf_du_
+  double *dV;      // [B][2]
+  double *ls_cost; // [B][CDDP_B200_MAX_ALPHAS] cost of every line-search candidate
+  double *Vx0;     // [B][n]   value gradient at t=0 after the last sweep (white-box)
+  double *Vxx0;    // [B][n][n]
+  double *history; // [B][max_iterations+1][4] or nullptr
+  int *history_len;
+  int history_cap;
+  int *num_running;  // device counter
+};
+
+// batch-shared constants, passed by value to kernels (fits the 4 KB parameter space comfortably)
+struct Constants {
+  int model, n, m, N, integrator, has_box;
+  double dt;
+  ModelParams mp;
+  const double *Qdt2;  // device [n][n] = 2*Q*dt  (l_xx, objective.cpp:130-134)
+  const double *Rdt2;  // device [m][m] = 2*R*dt  (l_uu)
+  const double *Qf2;   // device [n][n] = 2*Qf    (phi_xx)
+  double lb[CDDP_B200_MAX_M], ub[CDDP_B200_MAX_M];
+  double alphas[CDDP_B200_MAX_ALPHAS];
+  int num_alphas;
+  cddp_b200_options opt;
+};
+
+inline int record_stride(int n, int m) {
+  int c = n * n + n * m + n + 2 * m;
+  return (c + 1) & ~1;
+}
+
+enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };
+enum ForwardMode { FW_EVALUATE = 0 /* do not apply */, FW_ITERATE = 1 };
+
+// kernel launchers (one per translation unit)
+cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st);
+cudaError_t launch_initialize(const Constants &c, const DeviceState &d, cudaStream_t st);
+cudaError_t launch_backward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
+cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
+cudaError_t launch_finalize(const Constants &c, const DeviceState &d, int final_status, cudaStream_t st);
+cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st);
+cudaError_t launch_unpack_linearization(const Constants &c, const DeviceState &d, double *A, double *Bm,
+                                        cudaStream_t st);
+cudaError_t launch_pack_linearization(const Constants &c, const DeviceState &d, const double *A, const double *Bm,
+                                      cudaStream_t st);
+cudaError_t launch_gather_current(const Constants &c, const DeviceState &d, double *X, double *U, int which,
+                                  cudaStream_t st);
+
+}  // namespace cddp_b200

@@ -1,0 +1,302 @@
+// Linearisation + bookkeeping kernels.
+//
+//  linearize : for every (instance, t) build the backward-sweep record
+//                A = I + dt*Fx, B = dt*Fu                       (clddp_solver.cpp:113-118)
+//                lx = 2 Q_ (x - ref_t), lu = 2 R_ u             (objective.cpp:100-120; Q_=Q*dt, R_=R*dt)
+//              and the terminal gradient V_x(N) = 2 Qf (x_N - ref) (objective.cpp:122-126).
+//  initialize: initializeProblemIfNecessary + CLDDPSolver::initialize cold start
+//              (cddp_core.cpp:272-306, clddp_solver.cpp:68-74, cddp_solver_base.cpp:416-424).
+#include "engine.h"
+
+namespace cddp_b200 {
+
+namespace {
+
+__device__ __forceinline__ const double *ref_ptr(const DeviceState &d, int b, int t) {
+  // objective.cpp:84-88: per-index reference if a reference trajectory was given
+  return d.ref_traj ? d.ref_traj + ((size_t)b * (d.N + 1) + t) * d.n : d.xref + (size_t)b * d.n;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState d, int force) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = d.N + 1;
+  if (gid >= (long long)d.B * per) return;
+  const int b = (int)(gid / per), t = (int)(gid % per);
+  if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;
+  const int cur = d.cur[b];
+  const double *xp = d.X[cur] + ((size_t)b * (d.N + 1) + t) * NS;
+  double x[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = xp[i];
+  if (t == d.N) {
+    const double *ref = d.xref + (size_t)b * NS;  // terminal cost always uses reference_state_ (objective.cpp:96)
+    double e[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
+    for (int i = 0; i < NS; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) s += c.Qf2[i * NS + j] * e[j];
+      d.vterm[(size_t)b * NS + i] = s;
+    }
+    return;
+  }
+  const double *up = d.U[cur] + ((size_t)b * d.N + t) * NC;
+  double u[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) u[i] = up[i];
+  double Fx[NS * NS], Fu[NS * NC];
+  Model<MODEL>::jac(c.mp, x, u, Fx, Fu);
+  double *r = d.rec + ((size_t)b * d.N + t) * d.rec_stride;
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) r[i * NS + j] = c.dt * Fx[i * NS + j] + (i == j ? 1.0 : 0.0);
+  r += NS * NS;
+#pragma unroll
+  for (int i = 0; i < NS * NC; ++i) r[i] = c.dt * Fu[i];
+  r += NS * NC;
+  const double *ref = ref_ptr(d, b, t);
+  double e[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
+  for (int i = 0; i < NS; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
+    r[i] = s;
+  }
+  r += NS;
+  for (int i = 0; i < NC; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
+    r[i] = s;
+  }
+  r += NC;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) r[i] = u[i];
+}
+
+// LTI: runtime dimensions; Fx = (A_d - I)/dt, Fu = B_d/dt (lti_system.cpp:78-92) then the solver's
+// A = I + dt*Fx, B = dt*Fu — reproduced literally so that roundoff matches the reference's path.
+__global__ void __launch_bounds__(128) linearize_lti_kernel(Constants c, DeviceState d, int force) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = d.N + 1, n = d.n, m = d.m;
+  if (gid >= (long long)d.B * per) return;
+  const int b = (int)(gid / per), t = (int)(gid % per);
+  if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;
+  const int cur = d.cur[b];
+  const double *x = d.X[cur] + ((size_t)b * (d.N + 1) + t) * n;
+  if (t == d.N) {
+    const double *ref = d.xref + (size_t)b * n;
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += c.Qf2[i * n + j] * (x[j] - ref[j]);
+      d.vterm[(size_t)b * n + i] = s;
+    }
+    return;
+  }
+  const double *u = d.U[cur] + ((size_t)b * d.N + t) * m;
+  double *r = d.rec + ((size_t)b * d.N + t) * d.rec_stride;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      const double fx = (c.mp.lti_A[i * n + j] - (i == j ? 1.0 : 0.0)) / c.dt;
+      r[i * n + j] = c.dt * fx + (i == j ? 1.0 : 0.0);
+    }
+  r += n * n;
+  for (int i = 0; i < n * m; ++i) r[i] = c.dt * (c.mp.lti_B[i] / c.dt);
+  r += n * m;
+  const double *ref = ref_ptr(d, b, t);
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += c.Qdt2[i * n + j] * (x[j] - ref[j]);
+    r[i] = s;
+  }
+  r += n;
+  for (int i = 0; i < m; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < m; ++j) s += c.Rdt2[i * m + j] * u[j];
+    r[i] = s;
+  }
+  r += m;
+  for (int i = 0; i < m; ++i) r[i] = u[i];
+}
+
+// One warp per instance: X[0] = x0, zero gains, initial cost of the GIVEN trajectory (no re-rollout,
+// clddp_solver.cpp:72-74), reset per-instance solver state.
+__global__ void __launch_bounds__(128) initialize_kernel(Constants c, DeviceState d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d.B) return;
+  const int b = warp, n = d.n, m = d.m, N = d.N;
+  const int cur = d.cur[b];
+  double *X = d.X[cur] + (size_t)b * (N + 1) * n;
+  const double *U = d.U[cur] + (size_t)b * N * m;
+  for (int i = lane; i < n; i += 32) X[i] = d.x0[(size_t)b * n + i];  // cddp_core.cpp:294
+  __syncwarp();
+  for (size_t i = lane; i < (size_t)N * m * n; i += 32) d.K[(size_t)b * N * m * n + i] = 0.0;
+  for (size_t i = lane; i < (size_t)N * m; i += 32) d.kff[(size_t)b * N * m + i] = 0.0;
+  // running cost: (e^T Q_) e + (u^T R_) u with Q_ = Q*dt (Qdt2 = 2*Q_), objective.cpp:80-92
+  double J = 0.0;
+  for (int t = lane; t <= N; t += 32) {
+    const double *x = X + (size_t)t * n;
+    if (t == N) {
+      const double *ref = d.xref + (size_t)b * n;
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qf2[i * n + j]);
+        s += r * (x[j] - ref[j]);
+      }
+      J += s;
+    } else {
+      const double *ref = ref_ptr(d, b, t);
+      const double *u = U + (size_t)t * m;
+      double sx = 0.0, su = 0.0;
+      for (int j = 0; j < n; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * n + j]);
+        sx += r * (x[j] - ref[j]);
+      }
+      for (int j = 0; j < m; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < m; ++i) r += u[i] * (0.5 * c.Rdt2[i * m + j]);
+        su += r * u[j];
+      }
+      J += sx + su;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
+  if (lane == 0) {
+    d.cost[b] = J;
+    d.reg[b] = c.opt.reg_initial_value;
+    d.alpha[b] = c.opt.ls_initial_step_size;
+    d.inf_du[b] = __longlong_as_double(0x7ff0000000000000LL);
+    d.status[b] = CDDP_B200_STATUS_RUNNING;
+    d.iter[b] = 0;
+    d.lin_valid[b] = 0;
+    d.bw_ok[b] = 0;
+    d.accepted[b] = -1;
+    d.dV[2 * b] = 0.0;
+    d.dV[2 * b + 1] = 0.0;
+    if (d.history) {
+      double *h = d.history + (size_t)b * d.history_cap * 4;
+      h[0] = J;
+      h[1] = c.opt.ls_initial_step_size;
+      h[2] = __longlong_as_double(0x7ff0000000000000LL);
+      h[3] = c.opt.reg_initial_value;
+      d.history_len[b] = 1;
+    }
+  }
+}
+
+__global__ void finalize_kernel(DeviceState d, int final_status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  if (d.status[b] == CDDP_B200_STATUS_RUNNING) d.status[b] = final_status;
+}
+
+__global__ void count_running_kernel(DeviceState d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool run = b < d.B && d.status[b] == CDDP_B200_STATUS_RUNNING;
+  const unsigned mask = __ballot_sync(0xffffffffu, run);
+  if ((threadIdx.x & 31) == 0 && mask) atomicAdd(d.num_running, __popc(mask));
+}
+
+__global__ void unpack_lin_kernel(DeviceState d, double *A, double *Bm) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)d.B * d.N) return;
+  const int n = d.n, m = d.m;
+  const double *r = d.rec + (size_t)gid * d.rec_stride;
+  for (int i = 0; i < n * n; ++i) A[(size_t)gid * n * n + i] = r[i];
+  for (int i = 0; i < n * m; ++i) Bm[(size_t)gid * n * m + i] = r[n * n + i];
+}
+
+__global__ void pack_lin_kernel(DeviceState d, const double *A, const double *Bm) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)d.B * d.N) return;
+  const int n = d.n, m = d.m;
+  double *r = d.rec + (size_t)gid * d.rec_stride;
+  for (int i = 0; i < n * n; ++i) r[i] = A[(size_t)gid * n * n + i];
+  for (int i = 0; i < n * m; ++i) r[n * n + i] = Bm[(size_t)gid * n * m + i];
+}
+
+// copy the nominal (which=0) or candidate (which=1) trajectory of every instance to contiguous output
+__global__ void gather_current_kernel(DeviceState d, double *X, double *U, int which) {
+  const int b = blockIdx.x;
+  const int buf = d.cur[b] ^ which;
+  const size_t nx = (size_t)(d.N + 1) * d.n, nu = (size_t)d.N * d.m;
+  if (X)
+    for (size_t i = threadIdx.x; i < nx; i += blockDim.x) X[b * nx + i] = d.X[buf][b * nx + i];
+  if (U)
+    for (size_t i = threadIdx.x; i < nu; i += blockDim.x) U[b * nu + i] = d.U[buf][b * nu + i];
+}
+
+}  // namespace
+
+cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st) {
+  const long long total = (long long)d.B * (d.N + 1);
+  const int threads = 128;
+  const int blocks = (int)((total + threads - 1) / threads);
+  switch (c.model) {
+    case CDDP_B200_MODEL_PENDULUM:
+      linearize_kernel<CDDP_B200_MODEL_PENDULUM><<<blocks, threads, 0, st>>>(c, d, force);
+      break;
+    case CDDP_B200_MODEL_CARTPOLE:
+      linearize_kernel<CDDP_B200_MODEL_CARTPOLE><<<blocks, threads, 0, st>>>(c, d, force);
+      break;
+    case CDDP_B200_MODEL_UNICYCLE:
+      linearize_kernel<CDDP_B200_MODEL_UNICYCLE><<<blocks, threads, 0, st>>>(c, d, force);
+      break;
+    case CDDP_B200_MODEL_QUADROTOR:
+      linearize_kernel<CDDP_B200_MODEL_QUADROTOR><<<blocks, threads, 0, st>>>(c, d, force);
+      break;
+    case CDDP_B200_MODEL_LTI: linearize_lti_kernel<<<blocks, threads, 0, st>>>(c, d, force); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_initialize(const Constants &c, const DeviceState &d, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (d.B * 32 + threads - 1) / threads;
+  initialize_kernel<<<blocks, threads, 0, st>>>(c, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const Constants &, const DeviceState &d, int final_status, cudaStream_t st) {
+  finalize_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d, final_status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d.num_running, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  count_running_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_linearization(const Constants &, const DeviceState &d, double *A, double *Bm,
+                                        cudaStream_t st) {
+  const long long total = (long long)d.B * d.N;
+  unpack_lin_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(d, A, Bm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_linearization(const Constants &, const DeviceState &d, const double *A, const double *Bm,
+                                      cudaStream_t st) {
+  const long long total = (long long)d.B * d.N;
+  pack_lin_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(d, A, Bm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_current(const Constants &, const DeviceState &d, double *X, double *U, int which,
+                                  cudaStream_t st) {
+  gather_current_kernel<<<d.B, 128, 0, st>>>(d, X, U, which);
+  return cudaGetLastError();
+}
+
+}  // namespace cddp_b200

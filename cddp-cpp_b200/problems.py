@@ -1,0 +1,252 @@
+"""Workload definitions: BASELINE.json's configs made concrete plus the extra
+reference fixtures the parity tests use.  Pure numpy, deterministic (seeded); consumed by tests/,
+bench.py and __graft_entry__.smoke().  Nothing here touches the GPU or the oracle.
+
+Every config cites the reference file it is taken from (relative to astomodynamics/cddp-cpp @ f71fa80)
+and lists its deviations from that file.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+SEED_BASE = 20260101  # default_rng(seed = 20260101 + config_id)
+
+
+def _diag(vals):
+    return np.diag(np.asarray(vals, dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# Minimal numpy dynamics, used ONLY to build initial trajectories (e.g. the hover rollout of the
+# quadrotor example, examples/cddp_quadrotor_point.cpp:87-95).  Not a solver component.
+# ---------------------------------------------------------------------------------------------
+def _quadrotor_f(params, x, u):
+    mass, I, L = params[0], np.asarray(params[1:10]).reshape(3, 3), params[10]
+    q = x[3:7].copy()
+    nq = math.sqrt(float(q @ q))
+    q = q / nq if nq > 1e-6 else np.array([1.0, 0.0, 0.0, 0.0])
+    qw, qx, qy, qz = q
+    w = x[10:13]
+    xd = np.zeros(13)
+    xd[0:3] = x[7:10]
+    xd[3] = -0.5 * (qx * w[0] + qy * w[1] + qz * w[2])
+    xd[4] = 0.5 * (qw * w[0] + qy * w[2] - qz * w[1])
+    xd[5] = 0.5 * (qw * w[1] - qx * w[2] + qz * w[0])
+    xd[6] = 0.5 * (qw * w[2] + qx * w[1] - qy * w[0])
+    thrust = u[0] + u[1] + u[2] + u[3]
+    tau = np.array([L * (u[0] - u[2]), L * (u[1] - u[3]), 0.1 * (u[0] - u[1] + u[2] - u[3])])
+    r3 = np.array([2 * (qx * qz + qy * qw), 2 * (qy * qz - qx * qw), 1 - 2 * (qx * qx + qy * qy)])
+    xd[7:10] = (1.0 / mass) * (r3 * thrust) - np.array([0.0, 0.0, 9.81])
+    xd[10:13] = np.linalg.inv(I) @ (tau - np.cross(w, I @ w))
+    return xd
+
+
+def _rk4(f, x, u, dt):
+    k1 = f(x, u)
+    k2 = f(x + 0.5 * dt * k1, u)
+    k3 = f(x + 0.5 * dt * k2, u)
+    k4 = f(x + dt * k3, u)
+    return x + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+
+
+def quadrotor_rollout(params, dt, x0, U):
+    X = np.zeros((U.shape[0] + 1, 13))
+    X[0] = x0
+    f = lambda x, u: _quadrotor_f(params, x, u)  # noqa: E731
+    for t in range(U.shape[0]):
+        X[t + 1] = _rk4(f, X[t], U[t], dt)
+    return X
+
+
+# ---------------------------------------------------------------------------------------------
+# option dictionaries (keys are cddp_b200_options field names; unspecified = reference default)
+# ---------------------------------------------------------------------------------------------
+def make_config(name: str, batch: int | None = None, horizon: int | None = None, seed_offset: int = 0) -> dict:
+    """Returns {"spec", "options", "x0", "xref", "X0", "U0", "ref_traj", "name", "config_id", "notes"}."""
+    builders = {
+        "pendulum": _cfg_pendulum, "cartpole": _cfg_cartpole, "quadrotor": _cfg_quadrotor,
+        "unicycle": _cfg_unicycle, "lti": _cfg_lti, "quadrotor_fig8": _cfg_quadrotor_fig8,
+    }
+    if name not in builders:
+        raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
+    return builders[name](batch, horizon, seed_offset)
+
+
+def _cfg_pendulum(batch, horizon, seed_offset):
+    """BASELINE config #1.  tests/cddp_core/test_clddp_solver.cpp:28-118 (CLDDPTest.SolvePendulum).
+    Deviations: none for batch 1 (instance 0 is the unperturbed fixture); further instances perturb x0."""
+    B = batch or 1
+    N = horizon or 500
+    dt = 0.05
+    rng = np.random.default_rng(SEED_BASE + 1 + seed_offset)
+    spec = dict(model="pendulum", n=2, m=1, horizon=N, dt=dt, integrator="euler", params=[1.0, 1.0, 0.0],
+                Q=np.zeros((2, 2)), R=0.1 * np.eye(1), Qf=100.0 * np.eye(2), lb=[-10.0], ub=[10.0])
+    options = dict(max_iterations=100, tolerance=1e-3, acceptable_tolerance=1e-4, reg_initial_value=1e-6)
+    x0 = np.tile(np.array([math.pi, 0.0]), (B, 1))
+    if B > 1:
+        x0[1:] += 0.05 * rng.standard_normal((B - 1, 2))
+    xref = np.zeros((B, 2))
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    U0 = np.zeros((B, N, 1))
+    return dict(name="pendulum", config_id=1, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="pendulum swing-up n=2 m=1 N=500, CLDDP + box +-10 (test_clddp_solver.cpp:28-118)")
+
+
+def _cfg_cartpole(batch, horizon, seed_offset):
+    """BASELINE config #2.  examples/cddp_cartpole.cpp:27-68.
+    Deviations: the example adds a +-5 box and runs IPDDP; BASELINE asks for the
+    unconstrained iLQR (CLDDP inverse branch, clddp_solver.cpp:142-145).  x0 perturbed, sigma=0.05."""
+    B = batch or 1024
+    N = horizon or 100
+    dt = 0.05
+    rng = np.random.default_rng(SEED_BASE + 2 + seed_offset)
+    spec = dict(model="cartpole", n=4, m=1, horizon=N, dt=dt, integrator="rk4", params=[1.0, 0.2, 0.5, 9.81, 0.0],
+                Q=np.zeros((4, 4)), R=0.1 * np.eye(1), Qf=100.0 * np.eye(4), lb=None, ub=None)
+    options = dict(max_iterations=80, tolerance=1e-6, acceptable_tolerance=1e-5, reg_initial_value=1e-5)
+    x0 = np.zeros((B, 4))
+    x0[1:] += 0.05 * rng.standard_normal((B - 1, 4))
+    xref = np.tile(np.array([0.0, math.pi, 0.0, 0.0]), (B, 1))
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    U0 = np.zeros((B, N, 1))
+    return dict(name="cartpole", config_id=2, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="cartpole swing-up n=4 m=1 N=100, unconstrained iLQR (examples/cddp_cartpole.cpp:27-68 minus the box)")
+
+
+QUADROTOR_PARAMS = [1.0, 0.01, 0, 0, 0, 0.01, 0, 0, 0, 0.02, 0.2]  # mass, inertia(9), arm_length
+
+
+def _cfg_quadrotor(batch, horizon, seed_offset):
+    """BASELINE config #3 (the headline).  examples/cddp_quadrotor_point.cpp:23-98.
+    Deviations: the example is N=120 and runs IPDDP; BASELINE asks for N=100 and the
+    control-box CLDDP (boxQP) path.  Start position perturbed sigma=0.1, goal position sigma_g=0.5."""
+    B = batch or 4096
+    N = horizon or 100
+    dt = 0.02
+    rng = np.random.default_rng(SEED_BASE + 3 + seed_offset)
+    Q = np.zeros((13, 13))
+    Q[4, 4] = Q[5, 5] = Q[6, 6] = 0.1
+    R = 0.1 * np.eye(4)
+    Qf = _diag([500, 500, 500, 1, 1, 1, 1, 10, 10, 10, 0, 0, 0])
+    spec = dict(model="quadrotor", n=13, m=4, horizon=N, dt=dt, integrator="rk4", params=QUADROTOR_PARAMS,
+                Q=Q, R=R, Qf=Qf, lb=[0.0] * 4, ub=[5.0] * 4)
+    options = dict(max_iterations=120, ls_max_iterations=15, reg_initial_value=1e-4)
+    x0 = np.zeros((B, 13))
+    x0[:, 3] = 1.0
+    xref = np.zeros((B, 13))
+    xref[:, 0], xref[:, 2], xref[:, 3] = 3.0, 2.0, 1.0
+    if B > 1:
+        x0[1:, 0:3] += 0.1 * rng.standard_normal((B - 1, 3))
+        xref[1:, 0:3] += 0.5 * rng.standard_normal((B - 1, 3))
+    hover = 1.0 * 9.81 / 4.0
+    U0 = np.full((B, N, 4), hover)
+    # hover rollout (cddp_quadrotor_point.cpp:87-95).  From rest at identity attitude it is stationary
+    # up to roundoff, so roll out instance 0 once and translate it for the others.
+    Xr = quadrotor_rollout(QUADROTOR_PARAMS, dt, x0[0], U0[0])
+    X0 = np.repeat(Xr[None, :, :], B, axis=0)
+    X0[:, :, 0:3] += (x0[:, None, 0:3] - x0[0, None, 0:3])
+    return dict(name="quadrotor", config_id=3, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="quadrotor point-to-point n=13 m=4 N=100, control box 0..5 (boxQP), CLDDP "
+                      "(examples/cddp_quadrotor_point.cpp:23-98 with N=100, CLDDP instead of IPDDP)")
+
+
+def _cfg_unicycle(batch, horizon, seed_offset):
+    """tests/cddp_core/test_clddp_solver.cpp:231-290 (CLDDPTest.SolveUnicycle).
+    Note the reference quirk: setInitialTrajectory(X=0) overwrites initial_state_ with X[0] = 0
+    (cddp_core.cpp:139-141), so the fixture really starts from the origin.  Deviation: the test sets
+    enable_parallel=true (min-cost selection); here the default sequential rule is used unless the
+    caller sets options['enable_parallel']=1."""
+    B = batch or 1
+    N = horizon or 100
+    dt = 0.03
+    rng = np.random.default_rng(SEED_BASE + 6 + seed_offset)
+    spec = dict(model="unicycle", n=3, m=2, horizon=N, dt=dt, integrator="euler", params=[],
+                Q=np.zeros((3, 3)), R=0.5 * np.eye(2), Qf=0.5 * _diag([50.0, 50.0, 10.0]),
+                lb=[-1.0, -math.pi], ub=[1.0, math.pi])
+    options = dict(max_iterations=20, tolerance=1e-2)
+    x0 = np.zeros((B, 3))
+    xref = np.tile(np.array([2.0, 2.0, math.pi / 2.0]), (B, 1))
+    if B > 1:
+        xref[1:] += 0.2 * rng.standard_normal((B - 1, 3))
+    X0 = np.zeros((B, N + 1, 3))
+    U0 = np.zeros((B, N, 2))
+    return dict(name="unicycle", config_id=6, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="unicycle n=3 m=2 N=100 box CLDDP (test_clddp_solver.cpp:231-290)")
+
+
+def _cfg_lti(batch, horizon, seed_offset):
+    """LQ problem on LTISystem (src/dynamics_model/lti_system.cpp:71-92): the one model whose
+    linearisation equals its rollout, so CLDDP converges in one accepted step and the gains are the
+    textbook finite-horizon LQR gains (closed-form known answer).  Not a reference fixture."""
+    B = batch or 4
+    N = horizon or 50
+    dt = 0.1
+    rng = np.random.default_rng(SEED_BASE + 7 + seed_offset)
+    n, m = 4, 2
+    S = rng.standard_normal((n, n))
+    S = 0.5 * (S - S.T)
+    # A_d = expm(dt*S) via a short Taylor series (S skew-symmetric => well conditioned)
+    Ad = np.eye(n)
+    term = np.eye(n)
+    for i in range(1, 20):
+        term = term @ (dt * S) / i
+        Ad = Ad + term
+    Bd = dt * rng.standard_normal((n, m))
+    spec = dict(model="lti", n=n, m=m, horizon=N, dt=dt, integrator="euler", params=[], lti_A=Ad, lti_B=Bd,
+                Q=np.eye(n), R=0.5 * np.eye(m), Qf=10.0 * np.eye(n), lb=None, ub=None)
+    options = dict(max_iterations=10, tolerance=1e-8, acceptable_tolerance=1e-12, reg_initial_value=1e-10,
+                   reg_min_value=1e-12)
+    x0 = rng.standard_normal((B, n))
+    xref = np.zeros((B, n))
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    U0 = np.zeros((B, N, m))
+    return dict(name="lti", config_id=7, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="LTI LQ known-answer problem n=4 m=2")
+
+
+def _cfg_quadrotor_fig8(batch, horizon, seed_offset):
+    """Figure-8 tracking with a per-timestep reference trajectory, patterned on
+    tests/cddp_core/test_clddp_solver.cpp:570-710 (CLDDPTest.SolveQuadrotor: box 0..4, reference_states).
+    Shortened horizon by default so the oracle finishes in seconds."""
+    B = batch or 2
+    N = horizon or 100
+    dt = 0.02
+    rng = np.random.default_rng(SEED_BASE + 8 + seed_offset)
+    Q = np.zeros((13, 13))
+    Q[0, 0] = Q[1, 1] = Q[2, 2] = 1.0
+    R = 0.01 * np.eye(4)
+    Qf = _diag([10, 10, 10, 0, 0, 0, 0, 1, 1, 1, 0, 0, 0])
+    spec = dict(model="quadrotor", n=13, m=4, horizon=N, dt=dt, integrator="rk4", params=QUADROTOR_PARAMS,
+                Q=Q, R=R, Qf=Qf, lb=[0.0] * 4, ub=[4.0] * 4)
+    options = dict(max_iterations=30, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-4)
+    tt = np.arange(N + 1) * dt
+    T = N * dt
+    ang = 2 * math.pi * tt / T
+    ref = np.zeros((B, N + 1, 13))
+    for b in range(B):
+        amp = 1.0 + (0.2 * rng.standard_normal() if b else 0.0)
+        ref[b, :, 0] = amp * np.sin(ang)
+        ref[b, :, 1] = amp * np.sin(ang) * np.cos(ang)
+        ref[b, :, 2] = 1.0
+        ref[b, :, 3] = 1.0
+    x0 = np.zeros((B, 13))
+    x0[:, 2], x0[:, 3] = 1.0, 1.0
+    xref = ref[:, -1, :].copy()
+    hover = 9.81 / 4.0
+    U0 = np.full((B, N, 4), hover)
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    return dict(name="quadrotor_fig8", config_id=8, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0,
+                ref_traj=ref, notes="quadrotor figure-8 tracking with reference_states (test_clddp_solver.cpp:570-710 pattern)")
+
+
+def shard(cfg: dict, rank: int, world: int) -> dict:
+    """Contiguous batch shard for one rank: B_g = ceil(B / G)."""
+    B = cfg["x0"].shape[0]
+    per = (B + world - 1) // world
+    lo, hi = min(rank * per, B), min((rank + 1) * per, B)
+    out = dict(cfg)
+    for key in ("x0", "xref", "X0", "U0", "ref_traj"):
+        out[key] = None if cfg[key] is None else cfg[key][lo:hi]
+    out["shard"] = (lo, hi)
+    return out

@@ -1,0 +1,243 @@
+/*
+ * include/cddp_b200.h — C ABI of the B200-native batched CLDDP/iLQR engine.
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates: a DDP
+ * iteration of cddp-cpp's CLDDP solver (backward Riccati sweep + forward rollout / line search),
+ * batched over independent problem instances.  Everything below is plain C: pointers, sizes and
+ * PODs — no C++/torch types.  The C++ shim that mirrors the reference API (cddp::CDDP,
+ * ISolverAlgorithm, DynamicalSystem, ...) lives in cddp-cpp_b200/host/ and calls only these
+ * entry points; INTEGRATION.md shows the binding a cddp-cpp maintainer would add.
+ *
+ * Citations are file:line in astomodynamics/cddp-cpp @ f71fa80 (v0.5.2).  The reference has no
+ * FFI and no batch API; each entry point names the reference interface it
+ * replaces for a batch of B instances.
+ *
+ * Conventions: row-major doubles; batch outermost.  x0,xref: [B][n]; ref_traj: [B][N+1][n];
+ * X: [B][N+1][n]; U: [B][N][m]; K: [B][N][m][n]; k: [B][N][m].  Every function returns 0 on
+ * success or a CDDP_B200_ERR_* code; cddp_b200_error_string() describes it.  Solve OUTCOMES are
+ * never errors — they come back as per-instance status codes that map to the reference's
+ * status_message strings (cddp_solver_base.cpp:69,82,162; clddp_solver.cpp:209,270,274).
+ * There is no CPU fallback: if no CUDA device is usable every entry point that computes fails
+ * with CDDP_B200_ERR_CUDA.
+ */
+#ifndef CDDP_B200_H
+#define CDDP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CDDP_B200_API __attribute__((visibility("default")))
+#else
+#define CDDP_B200_API
+#endif
+
+#define CDDP_B200_ABI_VERSION 1
+#define CDDP_B200_MAX_N 16      /* state dimension cap of the in-kernel dense blocks */
+#define CDDP_B200_MAX_M 8       /* control dimension cap */
+#define CDDP_B200_MAX_ALPHAS 32 /* line-search candidates evaluated in parallel (one lane each) */
+
+/* error codes */
+enum {
+  CDDP_B200_OK = 0,
+  CDDP_B200_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad dimension, unsupported option */
+  CDDP_B200_ERR_UNSUPPORTED_MODEL = 2, /* host-only DynamicalSystem: no device dynamics (no CPU fallback) */
+  CDDP_B200_ERR_CUDA = 3,              /* CUDA runtime error / no device; see cddp_b200_last_cuda_error */
+  CDDP_B200_ERR_OUT_OF_MEMORY = 4,
+  CDDP_B200_ERR_STATE = 5              /* call order violated (e.g. backward before linearize) */
+};
+
+/* Device-resident dynamics models (src/dynamics_model/<name>.cpp).  model_params layout:
+ *   PENDULUM  : length, mass, damping                                   (pendulum.cpp:24-27)
+ *   CARTPOLE  : cart_mass, pole_mass, pole_length, gravity, damping     (cartpole.cpp:27-36)
+ *   UNICYCLE  : (none)                                                  (unicycle.cpp:24-26)
+ *   QUADROTOR : mass, inertia 3x3 row-major (9), arm_length             (quadrotor.cpp:25-31)
+ *   LTI       : (none) — discrete A_d, B_d passed in lti_A, lti_B       (lti_system.cpp:71-92)
+ */
+enum {
+  CDDP_B200_MODEL_PENDULUM = 0,
+  CDDP_B200_MODEL_CARTPOLE = 1,
+  CDDP_B200_MODEL_UNICYCLE = 2,
+  CDDP_B200_MODEL_QUADROTOR = 3,
+  CDDP_B200_MODEL_LTI = 4
+};
+
+/* DynamicalSystem integration_type (dynamical_system.cpp:67-83) */
+enum { CDDP_B200_EULER = 0, CDDP_B200_HEUN = 1, CDDP_B200_RK3 = 2, CDDP_B200_RK4 = 3 };
+
+/* per-instance outcome -> CDDPSolution::status_message */
+enum {
+  CDDP_B200_STATUS_RUNNING = 0,        /* "Running" (only before/within a solve) */
+  CDDP_B200_STATUS_OPTIMAL = 1,        /* "OptimalSolutionFound" */
+  CDDP_B200_STATUS_ACCEPTABLE = 2,     /* "AcceptableSolutionFound" */
+  CDDP_B200_STATUS_MAX_ITERATIONS = 3, /* "MaxIterationsReached" */
+  CDDP_B200_STATUS_REG_LIMIT = 4,      /* "RegularizationLimitReached_NotConverged" */
+  CDDP_B200_STATUS_MAX_CPU_TIME = 5    /* "MaxCpuTimeReached" */
+};
+
+/* The subset of cddp::CDDPOptions the CLDDP path reads (include/cddp-cpp/cddp_core/options.hpp:
+ * :41-50 line search, :58-66 regularization, :93-105 filter.armijo_constant, :208-251 main;
+ * boxqp.hpp:30-41 BoxQPOptions).  Defaults from cddp_b200_default_options() equal the
+ * reference's member initialisers. */
+typedef struct {
+  double tolerance;                      /* 1e-5 */
+  double acceptable_tolerance;           /* 1e-6 */
+  int max_iterations;                    /* 1 */
+  int enable_parallel;                   /* 0: first accepted alpha wins (default, cddp_solver_base.cpp:255-263);
+                                            1: lowest cost among accepted alphas (enable_parallel=true, :264-285) */
+  double max_cpu_time;                   /* seconds, 0 = unlimited (checked between batched iterations) */
+  double termination_scaling_max_factor; /* 100 */
+  int ls_max_iterations;                 /* line_search.max_iterations 11 */
+  int reserved1;
+  double ls_initial_step_size;           /* 1 */
+  double ls_min_step_size;               /* 1e-8 */
+  double ls_step_reduction_factor;       /* 0.5 */
+  double reg_initial_value;              /* regularization.initial_value 1e-6 */
+  double reg_update_factor;              /* 10 */
+  double reg_max_value;                  /* 1e7 */
+  double reg_min_value;                  /* 1e-10 */
+  int qp_max_iterations;                 /* box_qp.max_iterations 100 */
+  int reserved2;
+  double qp_min_gradient_norm;           /* 1e-8 */
+  double qp_min_relative_improvement;    /* 1e-8 */
+  double qp_step_decrease_factor;        /* 0.6 */
+  double qp_min_step_size;               /* 1e-22 */
+  double qp_armijo_constant;             /* 0.1 */
+  double armijo_constant;                /* filter.armijo_constant 1e-4 (clddp_solver.cpp:256) */
+} cddp_b200_options;
+
+/* Batch-shared problem definition = what a cddp::CDDP object holds besides per-instance data:
+ * system (model id + parameters), QuadraticObjective weights (objective.cpp:30-64; Q and R are
+ * passed UNscaled, the engine applies the reference's Q*dt, R*dt), horizon, timestep, and the
+ * optional ControlConstraint bounds (constraint.hpp:144-251; looked up by the literal name
+ * "ControlConstraint", clddp_solver.cpp:85-86). */
+typedef struct {
+  int model;
+  int n;       /* state_dim */
+  int m;       /* control_dim */
+  int horizon; /* N */
+  double dt;   /* timestep */
+  int integrator;
+  int has_control_box;
+  double model_params[16];
+  const double *lti_A; /* [n][n] (LTI only, else NULL) */
+  const double *lti_B; /* [n][m] */
+  const double *Q;     /* [n][n] */
+  const double *R;     /* [m][m] */
+  const double *Qf;    /* [n][n] */
+  const double *lb;    /* [m] rawLowerBound (NULL if !has_control_box) */
+  const double *ub;    /* [m] rawUpperBound */
+} cddp_b200_problem;
+
+/* CUDA-event timings accumulated since the last cddp_b200_reset_timing(); one launch of each
+ * kernel per batched DDP iteration. */
+typedef struct {
+  double linearize_ms;
+  double backward_ms;
+  double forward_ms;
+  long long linearize_launches;
+  long long backward_launches;
+  long long forward_launches;
+  long long other_launches; /* init / cost / bookkeeping kernels */
+} cddp_b200_timing;
+
+typedef struct cddp_b200_solver cddp_b200_solver; /* opaque: owns all device buffers */
+
+/* ---- library ---- */
+CDDP_B200_API int cddp_b200_abi_version(void);
+CDDP_B200_API const char *cddp_b200_error_string(int err);
+CDDP_B200_API const char *cddp_b200_last_cuda_error(void);
+CDDP_B200_API const char *cddp_b200_status_string(int status);
+CDDP_B200_API int cddp_b200_device_count(int *count);
+
+/* CDDPOptions() defaults (options.hpp) and detail::buildLineSearchAlphas
+ * (cddp_context_utils.cpp:37-57).  Returns the number of alphas via *count. */
+CDDP_B200_API void cddp_b200_default_options(cddp_b200_options *opts);
+CDDP_B200_API int cddp_b200_build_alphas(const cddp_b200_options *opts, double *alphas, int capacity, int *count);
+
+/* ---- lifetime: replaces constructing B cddp::CDDP objects (cddp_core.cpp:37-61) plus
+ * addPathConstraint("ControlConstraint", ...) (cddp_core.cpp:148-153) ---- */
+CDDP_B200_API int cddp_b200_create(const cddp_b200_problem *problem, const cddp_b200_options *opts, int batch, int device,
+                     cddp_b200_solver **out);
+CDDP_B200_API int cddp_b200_destroy(cddp_b200_solver *s);
+/* kernels are launched on this cudaStream_t (default: the legacy default stream) */
+CDDP_B200_API int cddp_b200_set_stream(cddp_b200_solver *s, void *cuda_stream);
+/* CDDP::setOptions (cddp_core.cpp:109-113): rebuilds the alpha schedule */
+CDDP_B200_API int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *opts);
+
+/* ---- per-instance data: CDDP::setInitialState / setReferenceState(s) / setInitialTrajectory
+ * (cddp_core.cpp:68-100,127-142).  Host pointers; copied H2D on the solver's stream.
+ * ref_traj may be NULL (single reference state, objective.cpp:84-88).  X0 may be NULL: the state
+ * trajectory is then zero except X[0] = x0 (ensureTrajectoryShape, cddp_context_utils.cpp:97-107).
+ * U0 may be NULL (zeros). ---- */
+CDDP_B200_API int cddp_b200_set_instances(cddp_b200_solver *s, const double *x0, const double *xref, const double *ref_traj,
+                            const double *X0, const double *U0);
+/* same, device pointers (device-to-device; used to time the path with inputs resident in HBM) */
+CDDP_B200_API int cddp_b200_set_instances_device(cddp_b200_solver *s, const double *x0, const double *xref, const double *ref_traj,
+                                   const double *X0, const double *U0);
+
+/* ---- solver steps (the reference's template-method hooks, one call = whole batch) ---- */
+/* initializeProblemIfNecessary (cddp_core.cpp:272-306) + CLDDPSolver::initialize cold start
+ * (clddp_solver.cpp:28-75): X[0]=x0, gains zeroed, cost from the given X,U, reg=initial. */
+CDDP_B200_API int cddp_b200_initialize(cddp_b200_solver *s);
+/* A_t = I + dt*Fx, B_t = dt*Fu and cost gradients for every t (clddp_solver.cpp:113-122) */
+CDDP_B200_API int cddp_b200_linearize(cddp_b200_solver *s);
+/* one CLDDPSolver::backwardPass per instance at its current regularization, no retry
+ * (clddp_solver.cpp:79-204); per-instance success flag readable via cddp_b200_get_sweep */
+CDDP_B200_API int cddp_b200_backward_pass(cddp_b200_solver *s);
+/* CDDPSolverBase::performForwardPass, sequential semantics = first accepted alpha
+ * (cddp_solver_base.cpp:248-263) with every alpha rolled out in parallel; does not apply */
+CDDP_B200_API int cddp_b200_forward_pass(cddp_b200_solver *s);
+/* `iterations` passes of the CDDPSolverBase::solve loop body (cddp_solver_base.cpp:74-154) for
+ * every instance still running: backward with regularization retry, early convergence test,
+ * line search, accept / reject, regularization schedule, convergence test. */
+CDDP_B200_API int cddp_b200_iterate(cddp_b200_solver *s, int iterations);
+/* CDDP::solve("CLDDP") (cddp_core.cpp:235-270): initialize + iterate until every instance has
+ * stopped or max_iterations; instances still running are marked MaxIterationsReached. */
+CDDP_B200_API int cddp_b200_solve(cddp_b200_solver *s);
+CDDP_B200_API int cddp_b200_num_running(cddp_b200_solver *s, int *running);
+CDDP_B200_API int cddp_b200_synchronize(cddp_b200_solver *s);
+
+/* ---- results: CDDPSolution fields (cddp_core.hpp:54-103) per instance.  Any pointer may be
+ * NULL.  Synchronises the stream. ---- */
+CDDP_B200_API int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                           int *iterations_completed, int *status, double *final_step_length,
+                           double *final_regularization, double *inf_du);
+/* optional History (cddp_core.hpp:77-102) when recorded: [B][max_iterations+1][4] =
+ * {objective, step_length_primal, dual_infeasibility, regularization}; lens [B] */
+CDDP_B200_API int cddp_b200_enable_history(cddp_b200_solver *s, int enable);
+CDDP_B200_API int cddp_b200_get_history(cddp_b200_solver *s, double *history, int *lens);
+
+/* ---- white-box access for parity tests (the reference's tests use a friend shim the same way,
+ * tests/cddp_core/test_ipddp_solver.cpp:30-134) ---- */
+CDDP_B200_API int cddp_b200_get_feedforward(cddp_b200_solver *s, double *k);                  /* k_u_ */
+CDDP_B200_API int cddp_b200_set_gains(cddp_b200_solver *s, const double *K, const double *k); /* warm start k_u_/K_u_ */
+CDDP_B200_API int cddp_b200_set_regularization(cddp_b200_solver *s, const double *reg);       /* [B] */
+CDDP_B200_API int cddp_b200_set_cost(cddp_b200_solver *s, const double *cost);                /* [B] cost_ */
+CDDP_B200_API int cddp_b200_get_linearization(cddp_b200_solver *s, double *A, double *B);     /* [B][N][n][n], [B][N][n][m] */
+CDDP_B200_API int cddp_b200_set_linearization(cddp_b200_solver *s, const double *A, const double *B);
+/* after backward_pass: dV [B][2], ok [B], inf_du [B], Vx0 [B][n], Vxx0 [B][n][n] (value function at t=0) */
+CDDP_B200_API int cddp_b200_get_sweep(cddp_b200_solver *s, double *dV, int *ok, double *inf_du, double *Vx0, double *Vxx0);
+/* after forward_pass: costs [B][num_alphas], accepted alpha index [B] (-1 = none), candidate X,U of
+ * the accepted alpha (unchanged nominal if none) */
+CDDP_B200_API int cddp_b200_get_forward(cddp_b200_solver *s, double *costs, int *accepted, double *Xnew, double *Unew);
+
+/* ---- measurement ---- */
+CDDP_B200_API int cddp_b200_reset_timing(cddp_b200_solver *s);
+CDDP_B200_API int cddp_b200_get_timing(cddp_b200_solver *s, cddp_b200_timing *t);
+CDDP_B200_API int cddp_b200_enable_timing(cddp_b200_solver *s, int enable);
+/* algorithmic HBM bytes of one backward sweep of the whole batch: 8*(n^2+2nm+n+3m)*N*B */
+CDDP_B200_API int cddp_b200_backward_algorithmic_bytes(cddp_b200_solver *s, double *bytes);
+
+/* ---- one-shot convenience: the call a user of the batched API makes.  Host buffers in, host
+ * buffers out; H2D and D2H copies are inside.  X,U are in/out. ---- */
+CDDP_B200_API int cddp_b200_solve_host(const cddp_b200_problem *problem, const cddp_b200_options *opts, int batch, int device,
+                         const double *x0, const double *xref, const double *ref_traj, double *X, double *U, double *K,
+                         double *final_objective, int *iterations_completed, int *status, double *final_step_length,
+                         double *final_regularization, double *inf_du);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDDP_B200_H */

@@ -1,0 +1,1259 @@
+/*
+ * oracle/cddp_oracle.cpp — CPU restatement of the reference CLDDP hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see cddp_oracle.h).  PARITY STATUS: "parity unpinned" — the
+ * reference needs Eigen 3.4.0 + autodiff v1.1.2 (network FetchContent) and cannot be built here;
+ * this file restates the algorithm from the cited reference lines and the published algorithms
+ * of the Eigen routines the reference calls (PartialPivLU inverse, pivoted LDLT, eigenvalue PD test).
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ */
+#include "cddp_oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr int MAXN = ORACLE_MAX_N;
+constexpr int MAXM = ORACLE_MAX_M;
+constexpr int MAXD = MAXN + MAXM;
+
+/* ------------------------------------------------------------------------------------------
+ * Forward-mode dual number: stands in for autodiff::dual2nd + autodiff::jacobian
+ * (dynamical_system.cpp:102-133, quadrotor.cpp:116-140).  First derivatives only — CLDDP never
+ * consults Hessians (clddp_solver.cpp has no use_ilqr branch).
+ * ---------------------------------------------------------------------------------------- */
+struct Dual {
+  double v;
+  double d[MAXD];
+  int nd;
+};
+
+inline Dual dconst(double c, int nd) {
+  Dual r;
+  r.v = c;
+  r.nd = nd;
+  for (int i = 0; i < nd; ++i) r.d[i] = 0.0;
+  return r;
+}
+inline Dual operator+(const Dual &a, const Dual &b) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = a.v + b.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = a.d[i] + b.d[i];
+  return r;
+}
+inline Dual operator-(const Dual &a, const Dual &b) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = a.v - b.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = a.d[i] - b.d[i];
+  return r;
+}
+inline Dual operator-(const Dual &a) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = -a.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = -a.d[i];
+  return r;
+}
+inline Dual operator*(const Dual &a, const Dual &b) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = a.v * b.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+  return r;
+}
+inline Dual operator/(const Dual &a, const Dual &b) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = a.v / b.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v;
+  return r;
+}
+inline Dual operator+(const Dual &a, double c) { Dual r = a; r.v += c; return r; }
+inline Dual operator+(double c, const Dual &a) { return a + c; }
+inline Dual operator-(const Dual &a, double c) { Dual r = a; r.v -= c; return r; }
+inline Dual operator-(double c, const Dual &a) { return (-a) + c; }
+inline Dual operator*(const Dual &a, double c) {
+  Dual r = a;
+  r.v *= c;
+  for (int i = 0; i < a.nd; ++i) r.d[i] *= c;
+  return r;
+}
+inline Dual operator*(double c, const Dual &a) { return a * c; }
+inline Dual operator/(const Dual &a, double c) { return a * (1.0 / c); }
+inline Dual sqrt(const Dual &a) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = std::sqrt(a.v);
+  for (int i = 0; i < a.nd; ++i) r.d[i] = a.d[i] / (2.0 * r.v);
+  return r;
+}
+inline Dual sin(const Dual &a) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = std::sin(a.v);
+  const double c = std::cos(a.v);
+  for (int i = 0; i < a.nd; ++i) r.d[i] = c * a.d[i];
+  return r;
+}
+inline Dual cos(const Dual &a) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = std::cos(a.v);
+  const double s = -std::sin(a.v);
+  for (int i = 0; i < a.nd; ++i) r.d[i] = s * a.d[i];
+  return r;
+}
+inline double val(double a) { return a; }
+inline double val(const Dual &a) { return a.v; }
+using std::cos;
+using std::sin;
+using std::sqrt;
+
+/* ------------------------------------------------------------------------------------------
+ * Model dynamics, templated on the scalar so the same text serves f and its AD Jacobian.
+ * `jac` selects the *Autodiff variant of the reference where the two differ (cartpole damping,
+ * cartpole.cpp:90; pendulum gravity sign, pendulum.cpp:97 — the latter is never used by CLDDP
+ * because Pendulum overrides the Jacobians analytically, pendulum.cpp:45-66).
+ * ---------------------------------------------------------------------------------------- */
+
+/* quadrotor.cpp:33-96 (double) and :162-221 (dual).  params: mass, Ixx,Ixy,Ixz,Iyx,...,Izz (9), arm_length */
+template <typename T>
+void quadrotor_f(const double *P, const T *x, const T *u, T *xd) {
+  const double mass = P[0];
+  const double *I = P + 1; /* row-major 3x3 */
+  const double L = P[10];
+  const double gravity = 9.81; /* quadrotor.hpp gravity_ */
+  xd[0] = x[7];
+  xd[1] = x[8];
+  xd[2] = x[9];
+  T qw = x[3], qx = x[4], qy = x[5], qz = x[6];
+  T norm = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+  if (val(norm) > 1e-6) { /* quadrotor.cpp:45-55 */
+    qw = qw / norm;
+    qx = qx / norm;
+    qy = qy / norm;
+    qz = qz / norm;
+  } else {
+    qw = qw * 0.0 + 1.0;
+    qx = qx * 0.0;
+    qy = qy * 0.0;
+    qz = qz * 0.0;
+  }
+  T wx = x[10], wy = x[11], wz = x[12];
+  xd[3] = -0.5 * (qx * wx + qy * wy + qz * wz); /* :65-68 */
+  xd[4] = 0.5 * (qw * wx + qy * wz - qz * wy);
+  xd[5] = 0.5 * (qw * wy - qx * wz + qz * wx);
+  xd[6] = 0.5 * (qw * wz + qx * wy - qy * wx);
+  T f1 = u[0], f2 = u[1], f3 = u[2], f4 = u[3];
+  T thrust = f1 + f2 + f3 + f4; /* :75-81 */
+  T tau_x = L * (f1 - f3);
+  T tau_y = L * (f2 - f4);
+  T tau_z = 0.1 * (f1 - f2 + f3 - f4);
+  /* rotation matrix third column (thrust along body z), :99-113 */
+  T R02 = 2.0 * (qx * qz + qy * qw);
+  T R12 = 2.0 * (qy * qz - qx * qw);
+  T R22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+  const double im = 1.0 / mass;
+  xd[7] = im * (R02 * thrust); /* :86-88 */
+  xd[8] = im * (R12 * thrust);
+  xd[9] = im * (R22 * thrust) - gravity;
+  /* angular_acc = I^{-1} (tau - w x (I w)), :90-93; 3x3 cofactor inverse (Eigen fixed-size inverse) */
+  T Iw0 = I[0] * wx + I[1] * wy + I[2] * wz;
+  T Iw1 = I[3] * wx + I[4] * wy + I[5] * wz;
+  T Iw2 = I[6] * wx + I[7] * wy + I[8] * wz;
+  T r0 = tau_x - (wy * Iw2 - wz * Iw1);
+  T r1 = tau_y - (wz * Iw0 - wx * Iw2);
+  T r2 = tau_z - (wx * Iw1 - wy * Iw0);
+  const double c00 = I[4] * I[8] - I[5] * I[7], c01 = I[2] * I[7] - I[1] * I[8], c02 = I[1] * I[5] - I[2] * I[4];
+  const double c10 = I[5] * I[6] - I[3] * I[8], c11 = I[0] * I[8] - I[2] * I[6], c12 = I[2] * I[3] - I[0] * I[5];
+  const double c20 = I[3] * I[7] - I[4] * I[6], c21 = I[1] * I[6] - I[0] * I[7], c22 = I[0] * I[4] - I[1] * I[3];
+  const double det = I[0] * c00 + I[1] * c10 + I[2] * c20;
+  const double id = 1.0 / det;
+  xd[10] = (c00 * id) * r0 + (c01 * id) * r1 + (c02 * id) * r2;
+  xd[11] = (c10 * id) * r0 + (c11 * id) * r1 + (c12 * id) * r2;
+  xd[12] = (c20 * id) * r0 + (c21 * id) * r1 + (c22 * id) * r2;
+}
+
+/* cartpole.cpp:38-62 (double) and :64-93 (dual, adds -damping*theta_dot).
+ * params: cart_mass, pole_mass, pole_length, gravity, damping */
+template <typename T>
+void cartpole_f(const double *P, const T *x, const T *u, T *xd, bool jac) {
+  const double mc = P[0], mp = P[1], l = P[2], g = P[3], damping = P[4];
+  T theta = x[1], x_dot = x[2], theta_dot = x[3], force = u[0];
+  T s = sin(theta), c = cos(theta);
+  const double total_mass = mc + mp;
+  T den = mc + mp * s * s;
+  xd[0] = x_dot;
+  xd[1] = theta_dot;
+  xd[2] = (force + mp * s * (l * theta_dot * theta_dot + g * c)) / den;
+  T num = -force * c - mp * l * theta_dot * theta_dot * c * s - total_mass * g * s;
+  if (jac) num = num - damping * theta_dot; /* cartpole.cpp:90 */
+  xd[3] = num / (l * den);
+}
+
+/* pendulum.cpp:29-43.  params: length, mass, damping */
+void pendulum_f(const double *P, const double *x, const double *u, double *xd) {
+  const double length = P[0], mass = P[1], damping = P[2], gravity = 9.81;
+  const double inertia = mass * length * length;
+  xd[0] = x[1];
+  xd[1] = (u[0] - damping * x[1] + mass * gravity * length * std::sin(x[0])) / inertia;
+}
+
+/* unicycle.cpp:28-41 */
+void unicycle_f(const double *x, const double *u, double *xd) {
+  xd[0] = u[0] * std::cos(x[2]);
+  xd[1] = u[0] * std::sin(x[2]);
+  xd[2] = u[1];
+}
+
+void lti_step(const oracle_problem *p, const double *x, const double *u, double *xn) {
+  /* lti_system.cpp:71-76 */
+  const int n = p->n, m = p->m;
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += p->lti_A[i * n + j] * x[j];
+    double s2 = 0.0;
+    for (int j = 0; j < m; ++j) s2 += p->lti_B[i * m + j] * u[j];
+    xn[i] = s + s2;
+  }
+}
+
+void continuous_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xd);
+
+/* dynamical_system.cpp:28-83 */
+void discrete_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xn) {
+  const int n = p->n;
+  const double dt = p->dt;
+  if (p->model == ORACLE_LTI) {
+    lti_step(p, x, u, xn);
+    return;
+  }
+  double k1[MAXN], k2[MAXN], k3[MAXN], k4[MAXN], tmp[MAXN];
+  switch (p->integrator) {
+    case ORACLE_EULER:
+      continuous_dynamics(p, x, u, t, k1);
+      for (int i = 0; i < n; ++i) xn[i] = x[i] + dt * k1[i];
+      break;
+    case ORACLE_HEUN:
+      continuous_dynamics(p, x, u, t, k1);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] + dt * k1[i];
+      continuous_dynamics(p, tmp, u, t + dt, k2);
+      for (int i = 0; i < n; ++i) xn[i] = x[i] + 0.5 * dt * (k1[i] + k2[i]);
+      break;
+    case ORACLE_RK3:
+      continuous_dynamics(p, x, u, t, k1);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] + 0.5 * dt * k1[i];
+      continuous_dynamics(p, tmp, u, t + 0.5 * dt, k2);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] - dt * k1[i] + 2 * dt * k2[i];
+      continuous_dynamics(p, tmp, u, t + dt, k3);
+      for (int i = 0; i < n; ++i) xn[i] = x[i] + (dt / 6) * (k1[i] + 4 * k2[i] + k3[i]);
+      break;
+    default: /* rk4 */
+      continuous_dynamics(p, x, u, t, k1);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] + 0.5 * dt * k1[i];
+      continuous_dynamics(p, tmp, u, t + 0.5 * dt, k2);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] + 0.5 * dt * k2[i];
+      continuous_dynamics(p, tmp, u, t + 0.5 * dt, k3);
+      for (int i = 0; i < n; ++i) tmp[i] = x[i] + dt * k3[i];
+      continuous_dynamics(p, tmp, u, t + dt, k4);
+      for (int i = 0; i < n; ++i) xn[i] = x[i] + (dt / 6) * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+      break;
+  }
+}
+
+void continuous_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xd) {
+  switch (p->model) {
+    case ORACLE_PENDULUM: pendulum_f(p->model_params, x, u, xd); break;
+    case ORACLE_CARTPOLE: cartpole_f<double>(p->model_params, x, u, xd, false); break;
+    case ORACLE_UNICYCLE: unicycle_f(x, u, xd); break;
+    case ORACLE_QUADROTOR: quadrotor_f<double>(p->model_params, x, u, xd); break;
+    case ORACLE_LTI: {
+      /* base-class fallback dynamical_system.cpp:85-98: (x_next - x)/dt */
+      double xn[MAXN];
+      lti_step(p, x, u, xn);
+      for (int i = 0; i < p->n; ++i) xd[i] = (xn[i] - x[i]) / p->dt;
+      break;
+    }
+    default:
+      for (int i = 0; i < p->n; ++i) xd[i] = 0.0;
+  }
+  (void)t;
+}
+
+/* getJacobians: continuous-time Fx (n x n), Fu (n x m). */
+void jacobians(const oracle_problem *p, const double *x, const double *u, double t, double *Fx, double *Fu) {
+  const int n = p->n, m = p->m;
+  std::fill(Fx, Fx + n * n, 0.0);
+  std::fill(Fu, Fu + n * m, 0.0);
+  const double *P = p->model_params;
+  switch (p->model) {
+    case ORACLE_PENDULUM: { /* pendulum.cpp:45-66 */
+      const double length = P[0], mass = P[1], damping = P[2], gravity = 9.81;
+      Fx[0 * 2 + 1] = 1.0;
+      Fx[1 * 2 + 0] = (gravity / length) * std::cos(x[0]);
+      Fx[1 * 2 + 1] = -damping / (mass * length * length);
+      Fu[1] = 1.0 / (mass * length * length);
+      break;
+    }
+    case ORACLE_UNICYCLE: { /* unicycle.cpp:43-66 */
+      Fx[0 * 3 + 2] = -u[0] * std::sin(x[2]);
+      Fx[1 * 3 + 2] = u[0] * std::cos(x[2]);
+      Fu[0 * 2 + 0] = std::cos(x[2]);
+      Fu[1 * 2 + 0] = std::sin(x[2]);
+      Fu[2 * 2 + 1] = 1.0;
+      break;
+    }
+    case ORACLE_LTI: { /* lti_system.cpp:78-92 */
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Fx[i * n + j] = (p->lti_A[i * n + j] - (i == j ? 1.0 : 0.0)) / p->dt;
+      for (int i = 0; i < n * m; ++i) Fu[i] = p->lti_B[i] / p->dt;
+      break;
+    }
+    case ORACLE_CARTPOLE:
+    case ORACLE_QUADROTOR: { /* autodiff::jacobian: cartpole.cpp:95-103, quadrotor.cpp:116-140 */
+      const int nd = n + m;
+      Dual xs[MAXN], us[MAXM], xd[MAXN];
+      for (int i = 0; i < n; ++i) {
+        xs[i] = dconst(x[i], nd);
+        xs[i].d[i] = 1.0;
+      }
+      for (int j = 0; j < m; ++j) {
+        us[j] = dconst(u[j], nd);
+        us[j].d[n + j] = 1.0;
+      }
+      for (int i = 0; i < n; ++i) xd[i] = dconst(0.0, nd);
+      if (p->model == ORACLE_CARTPOLE)
+        cartpole_f<Dual>(P, xs, us, xd, true);
+      else
+        quadrotor_f<Dual>(P, xs, us, xd);
+      for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) Fx[i * n + j] = xd[i].d[j];
+        for (int j = 0; j < m; ++j) Fu[i * m + j] = xd[i].d[n + j];
+      }
+      break;
+    }
+    default: break;
+  }
+  (void)t;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * QuadraticObjective (objective.cpp:30-154): Q_ = Q*dt, R_ = R*dt, no 1/2 factors.
+ * ---------------------------------------------------------------------------------------- */
+double running_cost(const oracle_problem *p, const double *x, const double *u, const double *ref) {
+  const int n = p->n, m = p->m;
+  const double dt = p->dt;
+  double e[MAXN];
+  for (int i = 0; i < n; ++i) e[i] = x[i] - ref[i];
+  /* (e^T Q_) e  — left-to-right as Eigen evaluates the product chain (objective.cpp:89-90) */
+  double sx = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r += e[i] * (p->Q[i * n + j] * dt);
+    sx += r * e[j];
+  }
+  double su = 0.0;
+  for (int j = 0; j < m; ++j) {
+    double r = 0.0;
+    for (int i = 0; i < m; ++i) r += u[i] * (p->R[i * m + j] * dt);
+    su += r * u[j];
+  }
+  return sx + su;
+}
+
+double terminal_cost(const oracle_problem *p, const double *x, const double *ref) { /* objective.cpp:94-98 */
+  const int n = p->n;
+  double e[MAXN];
+  for (int i = 0; i < n; ++i) e[i] = x[i] - ref[i];
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r += e[i] * p->Qf[i * n + j];
+    s += r * e[j];
+  }
+  return s;
+}
+
+inline const double *ref_at(const oracle_problem *p, const double *xref, const double *ref_traj, int t) {
+  /* objective.cpp:84-88: reference_states_[index] if a trajectory was given else reference_state_ */
+  return ref_traj ? ref_traj + (size_t)t * p->n : xref;
+}
+
+/* cddp_solver_base.cpp:416-424 */
+double trajectory_cost(const oracle_problem *p, const double *X, const double *U, const double *xref,
+                       const double *ref_traj) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  double J = 0.0;
+  for (int t = 0; t < N; ++t) J += running_cost(p, X + (size_t)t * n, U + (size_t)t * m, ref_at(p, xref, ref_traj, t));
+  J += terminal_cost(p, X + (size_t)N * n, xref);
+  return J;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Small dense numerics standing in for the Eigen 3.4.0 routines the reference calls.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Eigen::EigenSolver(M).eigenvalues().real().minCoeff() for a (numerically) symmetric M
+ * (clddp_solver.cpp:133-134): cyclic Jacobi on the symmetric part. */
+double min_eigenvalue_sym(const double *M, int n) {
+  double a[MAXM * MAXM];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i * n + j] = 0.5 * (M[i * n + j] + M[j * n + i]);
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
+    if (off < 1e-300) break;
+    for (int p_ = 0; p_ < n; ++p_)
+      for (int q = p_ + 1; q < n; ++q) {
+        const double apq = a[p_ * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * n + q] - a[p_ * n + p_]) / (2.0 * apq);
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = a[k * n + p_], akq = a[k * n + q];
+          a[k * n + p_] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = a[p_ * n + k], aqk = a[q * n + k];
+          a[p_ * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+      }
+  }
+  double mn = a[0];
+  for (int i = 1; i < n; ++i) mn = std::min(mn, a[i * n + i]);
+  return mn;
+}
+
+/* MatrixXd::inverse() for a dynamic matrix = PartialPivLU().inverse() (clddp_solver.cpp:143). */
+void inverse_lu(const double *M, int n, double *Inv) {
+  double a[MAXM * MAXM];
+  int perm[MAXM];
+  std::memcpy(a, M, sizeof(double) * n * n);
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = std::fabs(a[k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(a[i * n + k]) > best) {
+        best = std::fabs(a[i * n + k]);
+        piv = i;
+      }
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) std::swap(a[k * n + j], a[piv * n + j]);
+      std::swap(perm[k], perm[piv]);
+    }
+    for (int i = k + 1; i < n; ++i) {
+      a[i * n + k] /= a[k * n + k];
+      for (int j = k + 1; j < n; ++j) a[i * n + j] -= a[i * n + k] * a[k * n + j];
+    }
+  }
+  for (int c = 0; c < n; ++c) {
+    double y[MAXM];
+    for (int i = 0; i < n; ++i) {
+      double s = (perm[i] == c) ? 1.0 : 0.0;
+      for (int j = 0; j < i; ++j) s -= a[i * n + j] * y[j];
+      y[i] = s;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = y[i];
+      for (int j = i + 1; j < n; ++j) s -= a[i * n + j] * y[j];
+      y[i] = s / a[i * n + i];
+    }
+    for (int i = 0; i < n; ++i) Inv[i * n + c] = y[i];
+  }
+}
+
+/* Eigen::LDLT<MatrixXd> (lower, diagonal pivoting) — the published algorithm of Eigen 3.4.0
+ * LDLT.h ldlt_inplace<Lower>::unblocked + solve (boxqp.hpp:62, boxqp.cpp:105,147,
+ * clddp_solver.cpp:174). */
+struct LDLT {
+  int n = 0;
+  double a[MAXM * MAXM]; /* L strictly below the diagonal, D on the diagonal */
+  int tr[MAXM];          /* transpositions */
+  bool ok = true;
+
+  void compute(const double *M, int n_) {
+    n = n_;
+    ok = true;
+    std::memcpy(a, M, sizeof(double) * n * n);
+    bool found_zero_pivot = false;
+    for (int k = 0; k < n; ++k) {
+      int big = k;
+      double best = std::fabs(a[k * n + k]);
+      for (int i = k + 1; i < n; ++i)
+        if (std::fabs(a[i * n + i]) > best) {
+          best = std::fabs(a[i * n + i]);
+          big = i;
+        }
+      tr[k] = big;
+      if (big != k) {
+        /* symmetric row/column interchange on the lower triangle */
+        const int s = n - big - 1;
+        for (int j = 0; j < k; ++j) std::swap(a[k * n + j], a[big * n + j]);
+        for (int i = 0; i < s; ++i) std::swap(a[(big + 1 + i) * n + k], a[(big + 1 + i) * n + big]);
+        std::swap(a[k * n + k], a[big * n + big]);
+        for (int i = k + 1; i < big; ++i) std::swap(a[i * n + k], a[big * n + i]);
+      }
+      const int rs = n - k - 1;
+      if (k > 0) {
+        double temp[MAXM];
+        for (int j = 0; j < k; ++j) temp[j] = a[j * n + j] * a[k * n + j];
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += a[k * n + j] * temp[j];
+        a[k * n + k] -= s;
+        for (int i = 0; i < rs; ++i) {
+          double s2 = 0.0;
+          for (int j = 0; j < k; ++j) s2 += a[(k + 1 + i) * n + j] * temp[j];
+          a[(k + 1 + i) * n + k] -= s2;
+        }
+      }
+      const double akk = a[k * n + k];
+      const bool pivot_is_valid = std::fabs(akk) > 0.0;
+      if (k == 0 && !pivot_is_valid) {
+        for (int j = 0; j < n; ++j) tr[j] = j;
+        return;
+      }
+      if (rs > 0 && pivot_is_valid) {
+        for (int i = 0; i < rs; ++i) a[(k + 1 + i) * n + k] /= akk;
+      } else if (rs > 0) {
+        for (int i = 0; i < rs; ++i)
+          if (a[(k + 1 + i) * n + k] != 0.0) ok = false;
+      }
+      if (found_zero_pivot && pivot_is_valid)
+        ok = false;
+      else if (!pivot_is_valid)
+        found_zero_pivot = true;
+    }
+  }
+
+  void solve_inplace(double *b) const {
+    for (int k = 0; k < n; ++k)
+      if (tr[k] != k) std::swap(b[k], b[tr[k]]);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < i; ++j) b[i] -= a[i * n + j] * b[j];
+    const double tol = std::numeric_limits<double>::min();
+    for (int i = 0; i < n; ++i) {
+      if (std::fabs(a[i * n + i]) > tol)
+        b[i] /= a[i * n + i];
+      else
+        b[i] = 0.0;
+    }
+    for (int i = n - 1; i >= 0; --i)
+      for (int j = i + 1; j < n; ++j) b[i] -= a[j * n + i] * b[j];
+    for (int k = n - 1; k >= 0; --k)
+      if (tr[k] != k) std::swap(b[k], b[tr[k]]);
+  }
+};
+
+/* ------------------------------------------------------------------------------------------
+ * BoxQPSolver (boxqp.cpp:25-250)
+ * ---------------------------------------------------------------------------------------- */
+struct BoxQPOut {
+  double x[MAXM];
+  int free_mask[MAXM];
+  int status;
+  int iterations;
+  int factorizations;
+  double final_value;
+  double final_grad_norm;
+  LDLT Hfree;
+  int nfree_factor; /* size of the factor currently held */
+};
+
+inline double qp_value(const double *x, const double *H, const double *g, int n) { /* boxqp.cpp:235-239 */
+  double Hx[MAXM];
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += H[i * n + j] * x[j];
+    Hx[i] = s;
+  }
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < n; ++i) {
+    a += x[i] * Hx[i];
+    b += g[i] * x[i];
+  }
+  return 0.5 * a + b;
+}
+
+void boxqp_solve(const oracle_options *o, int n, const double *H, const double *g, const double *lower,
+                 const double *upper, const double *x0, BoxQPOut *r) {
+  r->status = ORACLE_QP_MAX_ITER_EXCEEDED;
+  r->iterations = 0;
+  r->factorizations = 0;
+  r->final_grad_norm = 0.0;
+  r->nfree_factor = 0;
+  r->Hfree.n = 0;
+  /* initializeX, boxqp.cpp:184-205 */
+  if (x0) {
+    for (int i = 0; i < n; ++i) r->x[i] = std::min(std::max(x0[i], lower[i]), upper[i]);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      if (std::isfinite(lower[i]) && std::isfinite(upper[i]))
+        r->x[i] = 0.5 * (lower[i] + upper[i]);
+      else if (std::isfinite(lower[i]))
+        r->x[i] = lower[i];
+      else if (std::isfinite(upper[i]))
+        r->x[i] = upper[i];
+      else
+        r->x[i] = 0.0;
+    }
+  }
+  int clamped[MAXM], old_clamped[MAXM];
+  for (int i = 0; i < n; ++i) {
+    clamped[i] = 0;
+    r->free_mask[i] = 1;
+  }
+  double value = qp_value(r->x, H, g, n);
+  double old_value = std::numeric_limits<double>::infinity();
+
+  for (int iter = 0; iter < o->qp_max_iterations; ++iter) {
+    r->iterations = iter + 1;
+    if (iter > 0 && std::fabs(old_value - value) < o->qp_min_relative_improvement * std::fabs(old_value)) {
+      r->status = ORACLE_QP_SUCCESS; /* :52-57 */
+      break;
+    }
+    old_value = value;
+    double grad[MAXM];
+    for (int i = 0; i < n; ++i) { /* :61 */
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += H[i * n + j] * r->x[j];
+      grad[i] = g[i] + s;
+    }
+    int nclamped = 0;
+    for (int i = 0; i < n; ++i) { /* :64-73 */
+      old_clamped[i] = clamped[i];
+      clamped[i] = ((r->x[i] == lower[i] && grad[i] > 0) || (r->x[i] == upper[i] && grad[i] < 0)) ? 1 : 0;
+      r->free_mask[i] = 1 - clamped[i];
+      nclamped += clamped[i];
+    }
+    if (nclamped == n) { /* :76-79 */
+      r->status = ORACLE_QP_ALL_CLAMPED;
+      break;
+    }
+    bool any_different = false;
+    for (int i = 0; i < n; ++i)
+      if (old_clamped[i] != clamped[i]) any_different = true;
+    int free_idx[MAXM], nf = 0;
+    for (int i = 0; i < n; ++i)
+      if (!clamped[i]) free_idx[nf++] = i;
+    if (iter == 0 || any_different) { /* :89-111 */
+      double Hf[MAXM * MAXM];
+      for (int i = 0; i < nf; ++i)
+        for (int j = 0; j < nf; ++j) Hf[i * nf + j] = H[free_idx[i] * n + free_idx[j]];
+      r->Hfree.compute(Hf, nf);
+      r->nfree_factor = nf;
+      if (!r->Hfree.ok) {
+        r->status = ORACLE_QP_HESSIAN_NOT_PD;
+        break;
+      }
+      r->factorizations++;
+    }
+    double gn = 0.0; /* :114-125 */
+    for (int i = 0; i < n; ++i)
+      if (!clamped[i]) gn += grad[i] * grad[i];
+    gn = std::sqrt(gn);
+    r->final_grad_norm = gn;
+    if (gn < o->qp_min_gradient_norm) {
+      r->status = ORACLE_QP_SUCCESS;
+      break;
+    }
+    double search[MAXM], gc[MAXM]; /* :128-152 */
+    for (int i = 0; i < n; ++i) {
+      search[i] = 0.0;
+      gc[i] = g[i];
+    }
+    for (int i = 0; i < n; ++i)
+      if (clamped[i])
+        for (int j = 0; j < n; ++j) gc[j] += H[j * n + i] * r->x[i];
+    double gf[MAXM];
+    for (int i = 0; i < nf; ++i) gf[i] = gc[free_idx[i]];
+    r->Hfree.solve_inplace(gf);
+    for (int i = 0; i < nf; ++i) search[free_idx[i]] = -gf[i] - r->x[free_idx[i]];
+    double sdotg = 0.0; /* :155-159 */
+    for (int i = 0; i < n; ++i) sdotg += search[i] * grad[i];
+    if (sdotg >= 0) {
+      r->status = ORACLE_QP_NO_DESCENT;
+      break;
+    }
+    /* lineSearch, :207-233 */
+    double step = 1.0;
+    bool ls_ok = false;
+    double xn[MAXM];
+    while (step > o->qp_min_step_size) {
+      for (int i = 0; i < n; ++i) xn[i] = std::min(std::max(r->x[i] + step * search[i], lower[i]), upper[i]);
+      const double vn = qp_value(xn, H, g, n);
+      if ((vn - value) <= o->qp_armijo_constant * step * sdotg) {
+        ls_ok = true;
+        break;
+      }
+      step *= o->qp_step_decrease_factor;
+    }
+    if (!ls_ok) {
+      r->status = ORACLE_QP_MAX_LS_EXCEEDED;
+      break;
+    }
+    for (int i = 0; i < n; ++i) r->x[i] = xn[i];
+    value = qp_value(r->x, H, g, n); /* :170-172 */
+  }
+  r->final_value = value;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CLDDPSolver::backwardPass (clddp_solver.cpp:79-204) on stacked A,B (or computed on the fly).
+ * ---------------------------------------------------------------------------------------- */
+int backward_pass(const oracle_problem *p, const oracle_options *o, const double *Astack, const double *Bstack,
+                  const double *X, const double *U, const double *xref, const double *ref_traj, double reg, double *K,
+                  double *k, double *dV, double *inf_du, double *Vx_dbg, double *Vxx_dbg, int *fail_t) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  const double dt = p->dt;
+  double Vx[MAXN], Vxx[MAXN * MAXN];
+  /* terminal derivatives, objective.cpp:122-126,151-154 */
+  {
+    const double *xN = X + (size_t)N * n;
+    double e[MAXN];
+    for (int i = 0; i < n; ++i) e[i] = xN[i] - xref[i];
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += (2.0 * p->Qf[i * n + j]) * e[j];
+      Vx[i] = s;
+      for (int j = 0; j < n; ++j) Vxx[i * n + j] = 2.0 * p->Qf[i * n + j];
+    }
+  }
+  if (Vx_dbg) std::memcpy(Vx_dbg + (size_t)N * n, Vx, sizeof(double) * n);
+  if (Vxx_dbg) std::memcpy(Vxx_dbg + (size_t)N * n * n, Vxx, sizeof(double) * n * n);
+  dV[0] = dV[1] = 0.0;
+  double norm_Vx = 0.0;
+  for (int i = 0; i < n; ++i) norm_Vx += std::fabs(Vx[i]);
+  double Qu_error = 0.0;
+  if (fail_t) *fail_t = -1;
+
+  double A[MAXN * MAXN], B[MAXN * MAXM], Fx[MAXN * MAXN], Fu[MAXN * MAXM];
+  double Qx[MAXN], Qu[MAXM], Qxx[MAXN * MAXN], Qux[MAXM * MAXN], Quu[MAXM * MAXM], Quu_reg[MAXM * MAXM];
+  double VA[MAXN * MAXN], VB[MAXN * MAXM];
+  double kk[MAXM], KK[MAXM * MAXN];
+
+  for (int t = N - 1; t >= 0; --t) {
+    const double *x = X + (size_t)t * n;
+    const double *u = U + (size_t)t * m;
+    if (Astack) {
+      std::memcpy(A, Astack + (size_t)t * n * n, sizeof(double) * n * n);
+      std::memcpy(B, Bstack + (size_t)t * n * m, sizeof(double) * n * m);
+    } else {
+      jacobians(p, x, u, t * dt, Fx, Fu); /* :113-118 */
+      for (int i = 0; i < n * n; ++i) A[i] = dt * Fx[i];
+      for (int i = 0; i < n; ++i) A[i * n + i] += 1.0;
+      for (int i = 0; i < n * m; ++i) B[i] = dt * Fu[i];
+    }
+    /* cost derivatives (objective.cpp:100-149): l_x = 2 Q_ e, l_u = 2 R_ u, l_xx = 2 Q_, l_uu = 2 R_, l_ux = 0 */
+    const double *ref = ref_at(p, xref, ref_traj, t);
+    double e[MAXN];
+    for (int i = 0; i < n; ++i) e[i] = x[i] - ref[i];
+    for (int i = 0; i < n; ++i) { /* Q_x = l_x + A^T V_x (:124) */
+      double lx = 0.0;
+      for (int j = 0; j < n; ++j) lx += (2.0 * (p->Q[i * n + j] * dt)) * e[j];
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += A[j * n + i] * Vx[j];
+      Qx[i] = lx + s;
+    }
+    for (int i = 0; i < m; ++i) { /* Q_u = l_u + B^T V_x (:125) */
+      double lu = 0.0;
+      for (int j = 0; j < m; ++j) lu += (2.0 * (p->R[i * m + j] * dt)) * u[j];
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += B[j * m + i] * Vx[j];
+      Qu[i] = lu + s;
+    }
+    for (int i = 0; i < n; ++i) /* V_xx A, V_xx B */
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += Vxx[i * n + l] * A[l * n + j];
+        VA[i * n + j] = s;
+      }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < m; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += Vxx[i * n + l] * B[l * m + j];
+        VB[i * m + j] = s;
+      }
+    for (int i = 0; i < n; ++i) /* Q_xx = l_xx + A^T V_xx A (:126) */
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += A[l * n + i] * VA[l * n + j];
+        Qxx[i * n + j] = 2.0 * (p->Q[i * n + j] * dt) + s;
+      }
+    for (int i = 0; i < m; ++i) /* Q_ux = l_ux + B^T V_xx A (:127) */
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += B[l * m + i] * VA[l * n + j];
+        Qux[i * n + j] = s;
+      }
+    for (int i = 0; i < m; ++i) /* Q_uu = l_uu + B^T V_xx B (:128) */
+      for (int j = 0; j < m; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += B[l * m + i] * VB[l * m + j];
+        Quu[i * m + j] = 2.0 * (p->R[i * m + j] * dt) + s;
+      }
+    std::memcpy(Quu_reg, Quu, sizeof(double) * m * m); /* :130-131 */
+    for (int i = 0; i < m; ++i) Quu_reg[i * m + i] += reg;
+
+    if (!(min_eigenvalue_sym(Quu_reg, m) > 0.0)) { /* :133-140 (NaN also fails) */
+      if (fail_t) *fail_t = t;
+      return 0;
+    }
+
+    if (!p->has_control_box) { /* :142-145 */
+      double H[MAXM * MAXM];
+      inverse_lu(Quu_reg, m, H);
+      for (int i = 0; i < m; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < m; ++j) s += H[i * m + j] * Qu[j];
+        kk[i] = -s;
+        for (int c = 0; c < n; ++c) {
+          double s2 = 0.0;
+          for (int j = 0; j < m; ++j) s2 += H[i * m + j] * Qux[j * n + c];
+          KK[i * n + c] = -s2;
+        }
+      }
+    } else { /* :147-178 */
+      double lb[MAXM], ub[MAXM];
+      for (int i = 0; i < m; ++i) {
+        lb[i] = p->lb[i] - u[i];
+        ub[i] = p->ub[i] - u[i];
+      }
+      BoxQPOut qp;
+      boxqp_solve(o, m, Quu_reg, Qu, lb, ub, k + (size_t)t * m, &qp);
+      if (qp.status == ORACLE_QP_HESSIAN_NOT_PD || qp.status == ORACLE_QP_NO_DESCENT) {
+        if (fail_t) *fail_t = t;
+        return 0;
+      }
+      for (int i = 0; i < m; ++i) kk[i] = qp.x[i];
+      std::fill(KK, KK + m * n, 0.0);
+      int free_idx[MAXM], nf = 0;
+      for (int i = 0; i < m; ++i)
+        if (qp.free_mask[i]) free_idx[nf++] = i;
+      if (nf > 0) {
+        /* K_free = -Hfree.solve(Q_ux[free,:]) (:174).  Every exit of BoxQPSolver::solve that leaves
+         * a non-empty free set leaves the factor of exactly that set (the set only changes together
+         * with a refactorisation, boxqp.cpp:81-111; the relative-improvement exit at :52-57 runs
+         * before the set is touched).  The size guard below only protects the restatement. */
+        if (qp.nfree_factor != nf) {
+          double Hf[MAXM * MAXM];
+          for (int i = 0; i < nf; ++i)
+            for (int j = 0; j < nf; ++j) Hf[i * nf + j] = Quu_reg[free_idx[i] * m + free_idx[j]];
+          qp.Hfree.compute(Hf, nf);
+        }
+        for (int c = 0; c < n; ++c) {
+          double col[MAXM];
+          for (int i = 0; i < nf; ++i) col[i] = Qux[free_idx[i] * n + c];
+          qp.Hfree.solve_inplace(col);
+          for (int i = 0; i < nf; ++i) KK[free_idx[i] * n + c] = -col[i];
+        }
+      }
+    }
+    std::memcpy(k + (size_t)t * m, kk, sizeof(double) * m); /* :181-182 */
+    std::memcpy(K + (size_t)t * m * n, KK, sizeof(double) * m * n);
+
+    /* dV (:184-186), unregularised Q_uu */
+    double Quuk[MAXM];
+    for (int i = 0; i < m; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += Quu[i * m + j] * kk[j];
+      Quuk[i] = s;
+    }
+    double d0 = 0.0, d1 = 0.0;
+    for (int i = 0; i < m; ++i) {
+      d0 += Qu[i] * kk[i];
+      d1 += kk[i] * Quuk[i];
+    }
+    dV[0] += d0;
+    dV[1] += 0.5 * d1;
+
+    /* V_x = Q_x + K^T Q_uu k + Q_ux^T k + K^T Q_u (:188-189) */
+    double nVx[MAXN];
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int j = 0; j < m; ++j) {
+        a += KK[j * n + i] * Quuk[j];
+        b += Qux[j * n + i] * kk[j];
+        c += KK[j * n + i] * Qu[j];
+      }
+      nVx[i] = Qx[i] + a + b + c;
+    }
+    /* V_xx = Q_xx + K^T Q_uu K + Q_ux^T K + K^T Q_ux, then symmetrise (:190-192) */
+    double QuuK[MAXM * MAXN];
+    for (int i = 0; i < m; ++i)
+      for (int c = 0; c < n; ++c) {
+        double s = 0.0;
+        for (int j = 0; j < m; ++j) s += Quu[i * m + j] * KK[j * n + c];
+        QuuK[i * n + c] = s;
+      }
+    double nV[MAXN * MAXN];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int l = 0; l < m; ++l) {
+          a += KK[l * n + i] * QuuK[l * n + j];
+          b += Qux[l * n + i] * KK[l * n + j];
+          c += KK[l * n + i] * Qux[l * n + j];
+        }
+        nV[i * n + j] = Qxx[i * n + j] + a + b + c;
+      }
+    for (int i = 0; i < n; ++i) {
+      Vx[i] = nVx[i];
+      for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * (nV[i * n + j] + nV[j * n + i]);
+    }
+    if (Vx_dbg) std::memcpy(Vx_dbg + (size_t)t * n, Vx, sizeof(double) * n);
+    if (Vxx_dbg) std::memcpy(Vxx_dbg + (size_t)t * n * n, Vxx, sizeof(double) * n * n);
+    double l1 = 0.0, linf = 0.0; /* :194-195 */
+    for (int i = 0; i < n; ++i) l1 += std::fabs(Vx[i]);
+    for (int i = 0; i < m; ++i) linf = std::max(linf, std::fabs(Qu[i]));
+    norm_Vx += l1;
+    Qu_error = std::max(Qu_error, linf);
+  }
+  double sf = o->termination_scaling_max_factor; /* :197-201 */
+  sf = std::max(sf, norm_Vx / (double)(N * n)) / sf;
+  *inf_du = Qu_error / sf;
+  return 1;
+}
+
+/* CLDDPSolver::forwardPass (clddp_solver.cpp:215-262) */
+int forward_pass(const oracle_problem *p, const oracle_options *o, const double *x0, const double *X, const double *U,
+                 const double *xref, const double *ref_traj, const double *K, const double *k, const double *dV,
+                 double cost, double alpha, double *Xn, double *Un, double *Jn) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  std::memcpy(Xn, x0, sizeof(double) * n); /* :224 */
+  double J = 0.0;
+  for (int t = 0; t < N; ++t) {
+    const double *x = Xn + (size_t)t * n;
+    double dx[MAXN];
+    for (int i = 0; i < n; ++i) dx[i] = x[i] - X[(size_t)t * n + i];
+    double *u = Un + (size_t)t * m;
+    for (int i = 0; i < m; ++i) { /* :232-233 */
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += K[((size_t)t * m + i) * n + j] * dx[j];
+      u[i] = U[(size_t)t * m + i] + alpha * k[(size_t)t * m + i] + s;
+    }
+    if (p->has_control_box) /* :235-238, constraint.hpp:225-228 */
+      for (int i = 0; i < m; ++i) u[i] = std::min(std::max(u[i], p->lb[i]), p->ub[i]);
+    J += running_cost(p, x, u, ref_at(p, xref, ref_traj, t)); /* :240-241 */
+    discrete_dynamics(p, x, u, t * p->dt, Xn + (size_t)(t + 1) * n);
+  }
+  J += terminal_cost(p, Xn + (size_t)N * n, xref);
+  const double dJ = cost - J; /* :249-257 */
+  const double expected = -alpha * (dV[0] + 0.5 * alpha * dV[1]);
+  const double ratio = expected > 0.0 ? dJ / expected : std::copysign(1.0, dJ);
+  *Jn = J;
+  return ratio > o->armijo_constant ? 1 : 0;
+}
+
+int build_alphas(const oracle_options *o, double *alphas) { /* cddp_context_utils.cpp:37-57 */
+  int cnt = 0;
+  double a = o->ls_initial_step_size;
+  for (int i = 0; i < o->ls_max_iterations && cnt < ORACLE_MAX_ALPHAS - 1; ++i) {
+    alphas[cnt++] = a;
+    a *= o->ls_step_reduction_factor;
+    if (a < o->ls_min_step_size && i < o->ls_max_iterations - 1) {
+      alphas[cnt++] = o->ls_min_step_size;
+      break;
+    }
+  }
+  if (cnt == 0) alphas[cnt++] = o->ls_initial_step_size;
+  return cnt;
+}
+
+/* CDDP::solve("CLDDP"): cddp_core.cpp:235-306 + clddp_solver.cpp:28-75 + cddp_solver_base.cpp:29-186 */
+void solve_one(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
+               const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
+               double *history) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  /* initializeProblemIfNecessary (cddp_core.cpp:272-306): X_[0] = initial_state_, reg = initial */
+  std::memcpy(X, x0, sizeof(double) * n);
+  double reg = o->reg_initial_value;
+  double alpha_pr = o->ls_initial_step_size;
+  /* CLDDPSolver::initialize cold start (clddp_solver.cpp:68-74) */
+  std::fill(K, K + (size_t)N * m * n, 0.0);
+  std::fill(k, k + (size_t)N * m, 0.0);
+  double cost = trajectory_cost(p, X, U, xref, ref_traj);
+  double inf_du = std::numeric_limits<double>::infinity();
+  double dV[2] = {0.0, 0.0};
+  std::vector<double> Xn((size_t)(N + 1) * n), Un((size_t)N * m);
+  int hl = 0;
+  auto record = [&]() {
+    if (history) {
+      history[hl * 4 + 0] = cost;
+      history[hl * 4 + 1] = alpha_pr;
+      history[hl * 4 + 2] = inf_du;
+      history[hl * 4 + 3] = reg;
+      ++hl;
+    }
+  };
+  record();
+  const auto start = std::chrono::high_resolution_clock::now();
+  int iter = 0;
+  int status = ORACLE_MAX_ITERATIONS;
+  bool converged = false;
+  while (iter < o->max_iterations) {
+    ++iter;
+    if (o->max_cpu_time > 0) { /* cddp_solver_base.cpp:77-90 */
+      auto el = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - start);
+      if (el.count() > o->max_cpu_time * 1000) {
+        status = ORACLE_MAX_CPU_TIME;
+        break;
+      }
+    }
+    bool backward_ok = false; /* :93-111 */
+    while (!backward_ok) {
+      backward_ok = backward_pass(p, o, nullptr, nullptr, X, U, xref, ref_traj, reg, K, k, dV, &inf_du, nullptr,
+                                  nullptr, nullptr) != 0;
+      if (!backward_ok) {
+        reg = std::min(reg * o->reg_update_factor, o->reg_max_value); /* cddp_core.cpp:308-314 */
+        if (reg >= o->reg_max_value) {
+          status = ORACLE_REG_LIMIT;
+          break;
+        }
+      }
+    }
+    if (!backward_ok) break;
+    if (inf_du < o->tolerance) { /* clddp_solver.cpp:206-213 */
+      status = ORACLE_OPTIMAL;
+      converged = true;
+      record();
+      break;
+    }
+    bool fp_success = false; /* cddp_solver_base.cpp:255-263: first success wins */
+    double Jn = 0.0, a_acc = 0.0;
+    if (!o->enable_parallel) {
+      for (int ai = 0; ai < na; ++ai) {
+        if (forward_pass(p, o, x0, X, U, xref, ref_traj, K, k, dV, cost, alphas[ai], Xn.data(), Un.data(), &Jn)) {
+          fp_success = true;
+          a_acc = alphas[ai];
+          break;
+        }
+      }
+    } else { /* enable_parallel: lowest merit among successes, :264-285 */
+      std::vector<double> Xt((size_t)(N + 1) * n), Ut((size_t)N * m);
+      double best = std::numeric_limits<double>::infinity();
+      for (int ai = 0; ai < na; ++ai) {
+        double Jt = 0.0;
+        if (forward_pass(p, o, x0, X, U, xref, ref_traj, K, k, dV, cost, alphas[ai], Xt.data(), Ut.data(), &Jt) &&
+            Jt < best) {
+          best = Jt;
+          fp_success = true;
+          a_acc = alphas[ai];
+          Jn = Jt;
+          Xn = Xt;
+          Un = Ut;
+        }
+      }
+    }
+    if (fp_success) { /* :129-139 */
+      const double dJ = cost - Jn;
+      std::memcpy(X, Xn.data(), sizeof(double) * (N + 1) * n);
+      std::memcpy(U, Un.data(), sizeof(double) * N * m);
+      cost = Jn;
+      alpha_pr = a_acc;
+      record();
+      reg = std::max(reg / o->reg_update_factor, o->reg_min_value); /* cddp_core.cpp:316-322 */
+      if (inf_du < o->tolerance) { /* clddp_solver.cpp:264-277 */
+        status = ORACLE_OPTIMAL;
+        converged = true;
+      } else if (dJ > 0.0 && dJ < o->acceptable_tolerance) {
+        status = ORACLE_ACCEPTABLE;
+        converged = true;
+      }
+    } else { /* cddp_solver_base.cpp:206-218 */
+      reg = std::min(reg * o->reg_update_factor, o->reg_max_value);
+      if (reg >= o->reg_max_value) {
+        status = ORACLE_REG_LIMIT;
+        break;
+      }
+    }
+    if (converged) break;
+  }
+  res->final_objective = cost;
+  res->final_step_length = alpha_pr;
+  res->final_regularization = reg;
+  res->inf_du = inf_du;
+  res->iterations = iter;
+  res->status = status;
+  res->history_len = hl;
+  res->reserved = 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+void oracle_default_options(oracle_options *o) { /* options.hpp:41-66,93-105,208-251; boxqp.hpp:30-41 */
+  std::memset(o, 0, sizeof(*o));
+  o->tolerance = 1e-5;
+  o->acceptable_tolerance = 1e-6;
+  o->max_iterations = 1;
+  o->max_cpu_time = 0.0;
+  o->termination_scaling_max_factor = 100.0;
+  o->ls_max_iterations = 11;
+  o->ls_initial_step_size = 1.0;
+  o->ls_min_step_size = 1e-8;
+  o->ls_step_reduction_factor = 0.5;
+  o->reg_initial_value = 1e-6;
+  o->reg_update_factor = 10.0;
+  o->reg_max_value = 1e7;
+  o->reg_min_value = 1e-10;
+  o->qp_max_iterations = 100;
+  o->qp_min_gradient_norm = 1e-8;
+  o->qp_min_relative_improvement = 1e-8;
+  o->qp_step_decrease_factor = 0.6;
+  o->qp_min_step_size = 1e-22;
+  o->qp_armijo_constant = 0.1;
+  o->armijo_constant = 1e-4;
+}
+
+int oracle_build_alphas(const oracle_options *o, double *alphas) { return build_alphas(o, alphas); }
+
+void oracle_continuous_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xdot) {
+  continuous_dynamics(p, x, u, t, xdot);
+}
+void oracle_discrete_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xnext) {
+  discrete_dynamics(p, x, u, t, xnext);
+}
+void oracle_jacobians(const oracle_problem *p, const double *x, const double *u, double t, double *Fx, double *Fu) {
+  jacobians(p, x, u, t, Fx, Fu);
+}
+double oracle_running_cost(const oracle_problem *p, const double *x, const double *u, const double *ref) {
+  return running_cost(p, x, u, ref);
+}
+double oracle_terminal_cost(const oracle_problem *p, const double *x, const double *ref) {
+  return terminal_cost(p, x, ref);
+}
+double oracle_trajectory_cost(const oracle_problem *p, const double *X, const double *U, const double *xref,
+                              const double *ref_traj) {
+  return trajectory_cost(p, X, U, xref, ref_traj);
+}
+
+int oracle_boxqp(const oracle_options *o, int n, const double *H, const double *g, const double *lower,
+                 const double *upper, const double *x0, double *x, int *free_mask, int *iterations,
+                 int *factorizations, double *final_value, double *final_grad_norm, int ncols, const double *Kfree_rhs,
+                 double *Kfree_out) {
+  BoxQPOut r;
+  boxqp_solve(o, n, H, g, lower, upper, x0, &r);
+  for (int i = 0; i < n; ++i) {
+    x[i] = r.x[i];
+    free_mask[i] = r.free_mask[i];
+  }
+  if (iterations) *iterations = r.iterations;
+  if (factorizations) *factorizations = r.factorizations;
+  if (final_value) *final_value = r.final_value;
+  if (final_grad_norm) *final_grad_norm = r.final_grad_norm;
+  if (Kfree_rhs && Kfree_out && ncols > 0) {
+    int free_idx[MAXM], nf = 0;
+    for (int i = 0; i < n; ++i)
+      if (r.free_mask[i]) free_idx[nf++] = i;
+    std::fill(Kfree_out, Kfree_out + n * ncols, 0.0);
+    if (nf > 0) {
+      double Hf[MAXM * MAXM];
+      for (int i = 0; i < nf; ++i)
+        for (int j = 0; j < nf; ++j) Hf[i * nf + j] = H[free_idx[i] * n + free_idx[j]];
+      LDLT f;
+      f.compute(Hf, nf);
+      for (int c = 0; c < ncols; ++c) {
+        double col[MAXM];
+        for (int i = 0; i < nf; ++i) col[i] = Kfree_rhs[free_idx[i] * ncols + c];
+        f.solve_inplace(col);
+        for (int i = 0; i < nf; ++i) Kfree_out[free_idx[i] * ncols + c] = col[i];
+      }
+    }
+  }
+  return r.status;
+}
+
+int oracle_backward_pass(const oracle_problem *p, const oracle_options *o, const double *X, const double *U,
+                         const double *xref, const double *ref_traj, double reg, double *K, double *k, double *dV,
+                         double *inf_du, double *Vx_dbg, double *Vxx_dbg, int *fail_t) {
+  return backward_pass(p, o, nullptr, nullptr, X, U, xref, ref_traj, reg, K, k, dV, inf_du, Vx_dbg, Vxx_dbg, fail_t);
+}
+
+int oracle_backward_pass_AB(const oracle_problem *p, const oracle_options *o, const double *A, const double *B,
+                            const double *X, const double *U, const double *xref, const double *ref_traj, double reg,
+                            double *K, double *k, double *dV, double *inf_du, double *Vx_dbg, double *Vxx_dbg,
+                            int *fail_t) {
+  return backward_pass(p, o, A, B, X, U, xref, ref_traj, reg, K, k, dV, inf_du, Vx_dbg, Vxx_dbg, fail_t);
+}
+
+void oracle_linearize(const oracle_problem *p, const double *X, const double *U, double *A, double *B) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  double Fx[MAXN * MAXN], Fu[MAXN * MAXM];
+  for (int t = 0; t < N; ++t) {
+    jacobians(p, X + (size_t)t * n, U + (size_t)t * m, t * p->dt, Fx, Fu);
+    double *At = A + (size_t)t * n * n, *Bt = B + (size_t)t * n * m;
+    for (int i = 0; i < n * n; ++i) At[i] = p->dt * Fx[i];
+    for (int i = 0; i < n; ++i) At[i * n + i] += 1.0;
+    for (int i = 0; i < n * m; ++i) Bt[i] = p->dt * Fu[i];
+  }
+}
+
+int oracle_forward_pass(const oracle_problem *p, const oracle_options *o, const double *x0, const double *X,
+                        const double *U, const double *xref, const double *ref_traj, const double *K, const double *k,
+                        const double *dV, double cost, double alpha, double *Xn, double *Un, double *Jn) {
+  return forward_pass(p, o, x0, X, U, xref, ref_traj, K, k, dV, cost, alpha, Xn, Un, Jn);
+}
+
+void oracle_solve(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
+                  const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
+                  double *history) {
+  solve_one(p, o, x0, xref, ref_traj, X, U, K, k, res, history);
+}
+
+void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                        const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                        oracle_result *res) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
+  auto work = [&](int tid) {
+    const int lo = (int)((long long)batch * tid / nthreads), hi = (int)((long long)batch * (tid + 1) / nthreads);
+    for (int b = lo; b < hi; ++b) {
+      solve_one(p, o, x0 + (size_t)b * n, xref + (size_t)b * n,
+                ref_traj ? ref_traj + (size_t)b * (N + 1) * n : nullptr, X + (size_t)b * (N + 1) * n,
+                U + (size_t)b * N * m, K + (size_t)b * N * m * n, k + (size_t)b * N * m, res + b, nullptr);
+    }
+  };
+  if (nthreads == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+  for (auto &t : th) t.join();
+}
+
+int oracle_hardware_threads(void) {
+  unsigned h = std::thread::hardware_concurrency();
+  return h ? (int)h : 1;
+}
+
+const char *oracle_status_string(int status) {
+  switch (status) {
+    case ORACLE_OPTIMAL: return "OptimalSolutionFound";
+    case ORACLE_ACCEPTABLE: return "AcceptableSolutionFound";
+    case ORACLE_MAX_ITERATIONS: return "MaxIterationsReached";
+    case ORACLE_REG_LIMIT: return "RegularizationLimitReached_NotConverged";
+    case ORACLE_MAX_CPU_TIME: return "MaxCpuTimeReached";
+    default: return "Running";
+  }
+}
+
+} /* extern "C" */

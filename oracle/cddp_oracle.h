@@ -1,0 +1,162 @@
+/*
+ * oracle/cddp_oracle.h — C API of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C++17 CPU restatement of the reference's
+ * CLDDP hot path (astomodynamics/cddp-cpp @ f71fa80, v0.5.2).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product (cddp-cpp_b200/) never includes, links or calls anything in this directory.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference cannot be compiled in this image
+ * (Eigen 3.4.0 and autodiff v1.1.2 are fetched by CMake FetchContent, CMakeLists.txt:65-97,
+ * :120-125; no network), and the reference's own tests pin no gains / trajectories / costs on
+ * this path.  The oracle is therefore pinned by (i) the closed-form
+ * known-answer tests the reference does hold (test_objective.cpp, test_constraint.cpp,
+ * test_finite_difference.cpp, test_quadrotor.cpp hover + Jacobian-vs-FD), (ii) an independent
+ * numpy restatement (oracle/np_oracle.py) that must agree with it, and (iii) LQR closed forms.
+ *
+ * All matrices are row-major doubles.  Trajectories are [t][dim].
+ */
+#ifndef CDDP_ORACLE_H
+#define CDDP_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORACLE_MAX_N 16
+#define ORACLE_MAX_M 8
+#define ORACLE_MAX_ALPHAS 64
+
+/* model ids (src/dynamics_model/<name>.cpp) */
+enum { ORACLE_PENDULUM = 0, ORACLE_CARTPOLE = 1, ORACLE_UNICYCLE = 2, ORACLE_QUADROTOR = 3, ORACLE_LTI = 4 };
+/* integrators (src/cddp_core/dynamical_system.cpp:28-83) */
+enum { ORACLE_EULER = 0, ORACLE_HEUN = 1, ORACLE_RK3 = 2, ORACLE_RK4 = 3 };
+/* BoxQP status (include/cddp-cpp/cddp_core/boxqp.hpp:47-55) */
+enum {
+  ORACLE_QP_HESSIAN_NOT_PD = -1, ORACLE_QP_NO_DESCENT = 0, ORACLE_QP_MAX_ITER_EXCEEDED = 1,
+  ORACLE_QP_MAX_LS_EXCEEDED = 2, ORACLE_QP_NO_BOUNDS = 3, ORACLE_QP_SUCCESS = 4, ORACLE_QP_ALL_CLAMPED = 5
+};
+/* solve status -> reference status_message strings (cddp_solver_base.cpp:69,82,162; clddp_solver.cpp:209,270,274) */
+enum {
+  ORACLE_RUNNING = 0, ORACLE_OPTIMAL = 1, ORACLE_ACCEPTABLE = 2, ORACLE_MAX_ITERATIONS = 3,
+  ORACLE_REG_LIMIT = 4, ORACLE_MAX_CPU_TIME = 5
+};
+
+/* Field-for-field the same layout as cddp_b200_options (include/cddp_b200.h) so that the tests
+ * can feed the oracle and the product from one ctypes Structure.  Defaults: options.hpp:41-66,
+ * :93-105, :208-251; boxqp.hpp:30-41. */
+typedef struct {
+  double tolerance;                       /* 1e-5 */
+  double acceptable_tolerance;            /* 1e-6 */
+  int max_iterations;                     /* 1 */
+  int enable_parallel;                    /* 0 */
+  double max_cpu_time;                    /* 0 = unlimited */
+  double termination_scaling_max_factor;  /* 100 */
+  int ls_max_iterations;                  /* 11 */
+  int reserved1;
+  double ls_initial_step_size;            /* 1 */
+  double ls_min_step_size;                /* 1e-8 */
+  double ls_step_reduction_factor;        /* 0.5 */
+  double reg_initial_value;               /* 1e-6 */
+  double reg_update_factor;               /* 10 */
+  double reg_max_value;                   /* 1e7 */
+  double reg_min_value;                   /* 1e-10 */
+  int qp_max_iterations;                  /* 100 */
+  int reserved2;
+  double qp_min_gradient_norm;            /* 1e-8 */
+  double qp_min_relative_improvement;     /* 1e-8 */
+  double qp_step_decrease_factor;         /* 0.6 */
+  double qp_min_step_size;                /* 1e-22 */
+  double qp_armijo_constant;              /* 0.1 */
+  double armijo_constant;                 /* filter.armijo_constant 1e-4 */
+} oracle_options;
+
+/* Batch-shared problem description; same layout as cddp_b200_problem. */
+typedef struct {
+  int model;
+  int n;
+  int m;
+  int horizon;
+  double dt;
+  int integrator;
+  int has_control_box;
+  double model_params[16];
+  const double *lti_A; /* n x n discrete A_d (LTI only) */
+  const double *lti_B; /* n x m discrete B_d (LTI only) */
+  const double *Q;     /* n x n, UNscaled: the objective multiplies by dt (objective.cpp:38-39) */
+  const double *R;     /* m x m, UNscaled */
+  const double *Qf;    /* n x n */
+  const double *lb;    /* m, ControlConstraint raw lower bound (constraint.hpp:222) */
+  const double *ub;    /* m */
+} oracle_problem;
+
+void oracle_default_options(oracle_options *o);
+int oracle_build_alphas(const oracle_options *o, double *alphas /* [ORACLE_MAX_ALPHAS] */);
+
+/* L2 plugin surface restated: dynamics, integrators, Jacobians, objective */
+void oracle_continuous_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xdot);
+void oracle_discrete_dynamics(const oracle_problem *p, const double *x, const double *u, double t, double *xnext);
+void oracle_jacobians(const oracle_problem *p, const double *x, const double *u, double t, double *Fx, double *Fu);
+double oracle_running_cost(const oracle_problem *p, const double *x, const double *u, const double *ref);
+double oracle_terminal_cost(const oracle_problem *p, const double *x, const double *ref);
+double oracle_trajectory_cost(const oracle_problem *p, const double *X, const double *U, const double *xref,
+                              const double *ref_traj);
+
+/* BoxQPSolver::solve (boxqp.cpp:25-182).  Kfree_rhs/Kfree_out (optional, n x ncols): on return
+ * Kfree_out[free rows] = Hfree.solve(Kfree_rhs[free rows]) with the factor the solver ended with. */
+int oracle_boxqp(const oracle_options *o, int n, const double *H, const double *g, const double *lower,
+                 const double *upper, const double *x0 /* may be NULL */, double *x, int *free_mask, int *iterations,
+                 int *factorizations, double *final_value, double *final_grad_norm, int ncols, const double *Kfree_rhs,
+                 double *Kfree_out);
+
+/* CLDDPSolver::backwardPass (clddp_solver.cpp:79-204).  k is in/out (warm start + result).
+ * Vx_dbg [N+1][n], Vxx_dbg [N+1][n*n] optional.  Returns 1 on success, 0 on failure;
+ * fail_t (optional) receives the failing timestep. */
+int oracle_backward_pass(const oracle_problem *p, const oracle_options *o, const double *X, const double *U,
+                         const double *xref, const double *ref_traj, double reg, double *K, double *k, double *dV,
+                         double *inf_du, double *Vx_dbg, double *Vxx_dbg, int *fail_t);
+
+/* Same sweep on caller-supplied stacked discrete Jacobians A[t] (n x n), B[t] (n x m). */
+int oracle_backward_pass_AB(const oracle_problem *p, const oracle_options *o, const double *A, const double *B,
+                            const double *X, const double *U, const double *xref, const double *ref_traj, double reg,
+                            double *K, double *k, double *dV, double *inf_du, double *Vx_dbg, double *Vxx_dbg,
+                            int *fail_t);
+
+/* clddp_solver.cpp:113-118: A = I + dt*Fx, B = dt*Fu for every t. */
+void oracle_linearize(const oracle_problem *p, const double *X, const double *U, double *A, double *B);
+
+/* CLDDPSolver::forwardPass (clddp_solver.cpp:215-262). Returns success flag. */
+int oracle_forward_pass(const oracle_problem *p, const oracle_options *o, const double *x0, const double *X,
+                        const double *U, const double *xref, const double *ref_traj, const double *K, const double *k,
+                        const double *dV, double cost, double alpha, double *Xn, double *Un, double *Jn);
+
+/* CDDP::solve("CLDDP") for one instance (cddp_core.cpp:235-270 + cddp_solver_base.cpp:29-186).
+ * X,U in/out.  history (optional) [max_iterations+1][4] = {objective, alpha, inf_du, reg}. */
+typedef struct {
+  double final_objective;
+  double final_step_length;
+  double final_regularization;
+  double inf_du;
+  int iterations;
+  int status;
+  int history_len;
+  int reserved;
+} oracle_result;
+
+void oracle_solve(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
+                  const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
+                  double *history);
+
+/* Batch over independent instances, statically partitioned over nthreads std::threads.
+ * x0 [B][n], xref [B][n], ref_traj [B][N+1][n] or NULL, X [B][N+1][n], U [B][N][m], K [B][N][m][n], k [B][N][m]. */
+void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                        const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                        oracle_result *res);
+
+int oracle_hardware_threads(void);
+const char *oracle_status_string(int status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,259 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+The problem/option dictionaries are the ones cddp-cpp_b200/problems.py produces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4}
+INTEGRATORS = {"euler": 0, "heun": 1, "rk3": 2, "rk4": 3}
+STATUS_STRINGS = {0: "Running", 1: "OptimalSolutionFound", 2: "AcceptableSolutionFound", 3: "MaxIterationsReached",
+                  4: "RegularizationLimitReached_NotConverged", 5: "MaxCpuTimeReached"}
+QP_STATUS = {-1: "HESSIAN_NOT_PD", 0: "NO_DESCENT", 1: "MAX_ITER_EXCEEDED", 2: "MAX_LS_EXCEEDED", 3: "NO_BOUNDS",
+             4: "SUCCESS", 5: "ALL_CLAMPED"}
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("tolerance", C.c_double), ("acceptable_tolerance", C.c_double), ("max_iterations", C.c_int),
+        ("enable_parallel", C.c_int), ("max_cpu_time", C.c_double), ("termination_scaling_max_factor", C.c_double),
+        ("ls_max_iterations", C.c_int), ("reserved1", C.c_int), ("ls_initial_step_size", C.c_double),
+        ("ls_min_step_size", C.c_double), ("ls_step_reduction_factor", C.c_double), ("reg_initial_value", C.c_double),
+        ("reg_update_factor", C.c_double), ("reg_max_value", C.c_double), ("reg_min_value", C.c_double),
+        ("qp_max_iterations", C.c_int), ("reserved2", C.c_int), ("qp_min_gradient_norm", C.c_double),
+        ("qp_min_relative_improvement", C.c_double), ("qp_step_decrease_factor", C.c_double),
+        ("qp_min_step_size", C.c_double), ("qp_armijo_constant", C.c_double), ("armijo_constant", C.c_double),
+    ]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("model", C.c_int), ("n", C.c_int), ("m", C.c_int), ("horizon", C.c_int), ("dt", C.c_double),
+        ("integrator", C.c_int), ("has_control_box", C.c_int), ("model_params", C.c_double * 16),
+        ("lti_A", C.POINTER(C.c_double)), ("lti_B", C.POINTER(C.c_double)), ("Q", C.POINTER(C.c_double)),
+        ("R", C.POINTER(C.c_double)), ("Qf", C.POINTER(C.c_double)), ("lb", C.POINTER(C.c_double)),
+        ("ub", C.POINTER(C.c_double)),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [("final_objective", C.c_double), ("final_step_length", C.c_double),
+                ("final_regularization", C.c_double), ("inf_du", C.c_double), ("iterations", C.c_int),
+                ("status", C.c_int), ("history_len", C.c_int), ("reserved", C.c_int)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    lib.oracle_running_cost.restype = C.c_double
+    lib.oracle_terminal_cost.restype = C.c_double
+    lib.oracle_trajectory_cost.restype = C.c_double
+    lib.oracle_status_string.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def make_options(**overrides) -> Options:
+    o = Options()
+    load().oracle_default_options(C.byref(o))
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+class OracleProblem:
+    def __init__(self, spec: dict):
+        self.spec = spec
+        n, m = int(spec["n"]), int(spec["m"])
+        self.n, self.m, self.N = n, m, int(spec["horizon"])
+        self._keep = {}
+        p = Problem()
+        model = spec["model"]
+        p.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
+        p.n, p.m, p.horizon, p.dt = n, m, self.N, float(spec["dt"])
+        integ = spec.get("integrator", "rk4")
+        p.integrator = INTEGRATORS[integ] if isinstance(integ, str) else int(integ)
+        p.has_control_box = 1 if spec.get("lb") is not None else 0
+        params = list(spec.get("params", []))
+        for i in range(16):
+            p.model_params[i] = float(params[i]) if i < len(params) else 0.0
+        dp = C.POINTER(C.c_double)
+        for key in ("lti_A", "lti_B", "Q", "R", "Qf", "lb", "ub"):
+            v = spec.get(key)
+            if v is None:
+                setattr(p, key, None)
+            else:
+                arr = _f64(v)
+                self._keep[key] = arr
+                setattr(p, key, arr.ctypes.data_as(dp))
+        self.struct = p
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def build_alphas(opts: Options) -> np.ndarray:
+    buf = np.zeros(64)
+    cnt = load().oracle_build_alphas(C.byref(opts), _p(buf))
+    return buf[:cnt].copy()
+
+
+def continuous_dynamics(P: OracleProblem, x, u, t=0.0):
+    x, u = _f64(x), _f64(u)
+    out = np.zeros(P.n)
+    load().oracle_continuous_dynamics(P.ref, _p(x), _p(u), C.c_double(t), _p(out))
+    return out
+
+
+def discrete_dynamics(P: OracleProblem, x, u, t=0.0):
+    x, u = _f64(x), _f64(u)
+    out = np.zeros(P.n)
+    load().oracle_discrete_dynamics(P.ref, _p(x), _p(u), C.c_double(t), _p(out))
+    return out
+
+
+def jacobians(P: OracleProblem, x, u, t=0.0):
+    x, u = _f64(x), _f64(u)
+    Fx, Fu = np.zeros((P.n, P.n)), np.zeros((P.n, P.m))
+    load().oracle_jacobians(P.ref, _p(x), _p(u), C.c_double(t), _p(Fx), _p(Fu))
+    return Fx, Fu
+
+
+def running_cost(P, x, u, ref):
+    x, u, ref = _f64(x), _f64(u), _f64(ref)
+    return load().oracle_running_cost(P.ref, _p(x), _p(u), _p(ref))
+
+
+def terminal_cost(P, x, ref):
+    x, ref = _f64(x), _f64(ref)
+    return load().oracle_terminal_cost(P.ref, _p(x), _p(ref))
+
+
+def trajectory_cost(P, X, U, xref, ref_traj=None):
+    X, U, xref = _f64(X), _f64(U), _f64(xref)
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    return load().oracle_trajectory_cost(P.ref, _p(X), _p(U), _p(xref), _p(rt))
+
+
+def boxqp(opts: Options, H, g, lower, upper, x0=None, rhs=None):
+    H, g, lower, upper = _f64(H), _f64(g), _f64(lower), _f64(upper)
+    n = g.shape[0]
+    x0a = _f64(x0) if x0 is not None else None
+    x = np.zeros(n)
+    free = np.zeros(n, dtype=np.int32)
+    it, fac = C.c_int(0), C.c_int(0)
+    fv, gn = C.c_double(0), C.c_double(0)
+    ncols = 0
+    rhs_a = out = None
+    if rhs is not None:
+        rhs_a = _f64(rhs)
+        ncols = rhs_a.shape[1]
+        out = np.zeros((n, ncols))
+    st = load().oracle_boxqp(C.byref(opts), n, _p(H), _p(g), _p(lower), _p(upper), _p(x0a), _p(x), _p(free),
+                             C.byref(it), C.byref(fac), C.byref(fv), C.byref(gn), ncols, _p(rhs_a), _p(out))
+    return dict(status=st, x=x, free=free, iterations=it.value, factorizations=fac.value, value=fv.value,
+                grad_norm=gn.value, solve=out)
+
+
+def linearize(P, X, U):
+    X, U = _f64(X), _f64(U)
+    A, B = np.zeros((P.N, P.n, P.n)), np.zeros((P.N, P.n, P.m))
+    load().oracle_linearize(P.ref, _p(X), _p(U), _p(A), _p(B))
+    return A, B
+
+
+def backward_pass(P, opts, X, U, xref, reg, k_prev=None, ref_traj=None, A=None, B=None, debug=False):
+    X, U, xref = _f64(X), _f64(U), _f64(xref)
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K = np.zeros((P.N, P.m, P.n))
+    k = np.zeros((P.N, P.m)) if k_prev is None else _f64(k_prev).copy()
+    dV = np.zeros(2)
+    inf_du = C.c_double(0)
+    fail_t = C.c_int(-1)
+    Vx = np.zeros((P.N + 1, P.n)) if debug else None
+    Vxx = np.zeros((P.N + 1, P.n, P.n)) if debug else None
+    if A is not None:
+        A, B = _f64(A), _f64(B)
+        ok = load().oracle_backward_pass_AB(P.ref, C.byref(opts), _p(A), _p(B), _p(X), _p(U), _p(xref), _p(rt),
+                                            C.c_double(reg), _p(K), _p(k), _p(dV), C.byref(inf_du), _p(Vx), _p(Vxx),
+                                            C.byref(fail_t))
+    else:
+        ok = load().oracle_backward_pass(P.ref, C.byref(opts), _p(X), _p(U), _p(xref), _p(rt), C.c_double(reg), _p(K),
+                                         _p(k), _p(dV), C.byref(inf_du), _p(Vx), _p(Vxx), C.byref(fail_t))
+    return dict(ok=bool(ok), K=K, k=k, dV=dV, inf_du=inf_du.value, fail_t=fail_t.value, Vx=Vx, Vxx=Vxx)
+
+
+def forward_pass(P, opts, x0, X, U, xref, K, k, dV, cost, alpha, ref_traj=None):
+    x0, X, U, xref, K, k, dV = map(_f64, (x0, X, U, xref, K, k, dV))
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    Xn, Un = np.zeros_like(X), np.zeros_like(U)
+    Jn = C.c_double(0)
+    ok = load().oracle_forward_pass(P.ref, C.byref(opts), _p(x0), _p(X), _p(U), _p(xref), _p(rt), _p(K), _p(k), _p(dV),
+                                    C.c_double(cost), C.c_double(alpha), _p(Xn), _p(Un), C.byref(Jn))
+    return dict(success=bool(ok), X=Xn, U=Un, cost=Jn.value)
+
+
+def solve(P, opts, x0, xref, X0, U0, ref_traj=None, history=False):
+    x0, xref = _f64(x0), _f64(xref)
+    X, U = _f64(X0).copy(), _f64(U0).copy()
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K, k = np.zeros((P.N, P.m, P.n)), np.zeros((P.N, P.m))
+    res = Result()
+    hist = np.zeros((opts.max_iterations + 1, 4)) if history else None
+    load().oracle_solve(P.ref, C.byref(opts), _p(x0), _p(xref), _p(rt), _p(X), _p(U), _p(K), _p(k), C.byref(res), _p(hist))
+    out = dict(X=X, U=U, K=K, k=k, cost=res.final_objective, alpha=res.final_step_length,
+               reg=res.final_regularization, inf_du=res.inf_du, iterations=res.iterations, status=res.status)
+    if history:
+        out["history"] = hist[: res.history_len].copy()
+    return out
+
+
+def solve_batch(P, opts, x0, xref, X0, U0, ref_traj=None, nthreads=1):
+    x0, xref = _f64(x0), _f64(xref)
+    B = x0.shape[0]
+    X, U = _f64(X0).copy(), _f64(U0).copy()
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K, k = np.zeros((B, P.N, P.m, P.n)), np.zeros((B, P.N, P.m))
+    res = (Result * B)()
+    load().oracle_solve_batch(P.ref, C.byref(opts), B, int(nthreads), _p(x0), _p(xref), _p(rt), _p(X), _p(U), _p(K),
+                              _p(k), res)
+    return dict(X=X, U=U, K=K, k=k, cost=np.array([r.final_objective for r in res]),
+                alpha=np.array([r.final_step_length for r in res]), reg=np.array([r.final_regularization for r in res]),
+                inf_du=np.array([r.inf_du for r in res]), iterations=np.array([r.iterations for r in res], dtype=np.int32),
+                status=np.array([r.status for r in res], dtype=np.int32))
+
+
+def hardware_threads() -> int:
+    return int(load().oracle_hardware_threads())
