@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the B200 batched CLDDP engine (contract in the task brief).
+
+Metric (BASELINE.json): "DDP iterations/sec, quadrotor n=13 m=4 N=100, batch sweep at 1/2/4/8 GPU".
+Unit of work: one INSTANCE-ITERATION = one backward Riccati sweep + one forward line search for one
+problem instance.  One bench "step" = one batched DDP iteration = the three kernels
+(linearise, backward sweep, forward rollout/line search) over the rank's whole batch.
+
+  value        = instance-iterations/s, whole job, inputs resident in HBM when the timed region starts
+  e2e.value    = same metric through the C-ABI the way a user calls it: pinned HOST buffers in,
+                 `iters_per_call` DDP iterations, HOST buffers out — H2D + D2H inside the timed region
+  roofline     = backward-sweep kernel: algorithmic HBM bytes 8(n^2+2nm+n+3m)*N*B per launch divided
+                 by its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline = the CPU oracle (restatement of the reference algorithm; the reference itself cannot
+                 be built here: Eigen/autodiff unavailable) on a bounded sample, all host threads
+
+Convergence exits are disabled in the throughput legs (tolerance = acceptable_tolerance = 0) so every
+instance performs every iteration; converge-to-tolerance parity is covered by tests/ (pytest -m gpu).
+
+`--impl reference` times the CPU oracle on the same workload/metric (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DDP iterations/sec (instance-iterations: backward sweep + forward line search per problem instance)"
+UNIT = "instance-iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="quadrotor")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's batch)")
+    ap.add_argument("--iters-per-call", type=int, default=10, help="DDP iterations per e2e solve call")
+    ap.add_argument("--e2e-calls", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if t0 is not None and not (t0 - 0.15 <= ts <= t1 + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def throughput_options(cfg, max_iterations):
+    o = dict(cfg["options"])
+    o.update(tolerance=0.0, acceptable_tolerance=0.0, max_iterations=max_iterations)
+    return o
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement of the reference algorithm, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as ob
+    problems = importlib.import_module("cddp-cpp_b200.problems")
+    threads = ob.hardware_threads()
+    sample = args.cpu_sample or max(threads * 4, 32)
+    iters = args.iters_per_call
+    cfg = problems.make_config(args.config, batch=sample)
+    P = ob.OracleProblem(cfg["spec"])
+    oo = ob.make_options(**throughput_options(cfg, iters))
+    times, done = [], 0
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = ob.solve_batch(P, oo, cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"], cfg["ref_traj"], nthreads=threads)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+            done += int(r["iterations"].sum())
+    total = sum(times)
+    value = done / total
+    spec = cfg["spec"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["notes"], "n": spec["n"], "m": spec["m"], "horizon": spec["horizon"],
+                   "sample_instances": sample, "iterations_per_step": iters,
+                   "note": "CPU restatement of the reference algorithm (oracle/); the reference itself cannot be built "
+                           "here (Eigen 3.4 / autodiff are network FetchContent deps)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} instances x {iters} DDP iterations per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cddp = importlib.import_module("cddp-cpp_b200")
+    problems = importlib.import_module("cddp-cpp_b200.problems")
+    peaks, peak_src = measured_peaks()
+
+    # ---- workload: BASELINE config #3 per GPU (weak scaling: the batch shards with no exchange) ----
+    base = problems.make_config(args.config, batch=1)
+    per_gpu = args.batch or {"quadrotor": 4096, "cartpole": 1024, "pendulum": 1}.get(args.config, 1024)
+    cfg = problems.make_config(args.config, batch=per_gpu, seed_offset=1000 * rank)
+    spec = cfg["spec"]
+    n, m, N, B = spec["n"], spec["m"], spec["horizon"], per_gpu
+    K, W = args.steps, args.warmup
+    opts = cddp.default_options(**throughput_options(cfg, max(W + K, args.iters_per_call)))
+    solver = cddp.BatchedCLDDP(spec, opts, B, device=local_rank)
+    stream = torch.cuda.current_stream()
+    solver.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident throughput ----
+    dev = {k: torch.from_numpy(np.ascontiguousarray(cfg[k])).cuda() for k in ("x0", "xref", "X0", "U0")}
+    rt = torch.from_numpy(np.ascontiguousarray(cfg["ref_traj"])).cuda() if cfg["ref_traj"] is not None else None
+    solver.set_instances_device(dev["x0"].data_ptr(), dev["xref"].data_ptr(), dev["X0"].data_ptr(), dev["U0"].data_ptr(),
+                                rt.data_ptr() if rt is not None else None)
+    solver.initialize()
+    for _ in range(W):
+        solver.iterate(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(K):
+        solver.iterate(1)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    sc = solver.get_scalars()
+    iters_done = int(sc["iterations"].sum())
+    assert iters_done == B * (W + K), f"every instance must perform every iteration ({iters_done} != {B * (W + K)})"
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # the path's single collective: all-gather of per-instance results (cost, iterations, status)
+        mine = torch.from_numpy(np.stack([sc["cost"], sc["iterations"].astype(np.float64), sc["status"].astype(np.float64)], 1)).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        all_cost = torch.cat(gathered)[:, 0]
+        finite = bool(torch.isfinite(all_cost).all().item())
+    else:
+        finite = bool(np.isfinite(sc["cost"]).all())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- leg 2: per-kernel CUDA-event timing of the same iterations (roofline for the backward sweep) ----
+    solver.set_instances_device(dev["x0"].data_ptr(), dev["xref"].data_ptr(), dev["X0"].data_ptr(), dev["U0"].data_ptr(),
+                                rt.data_ptr() if rt is not None else None)
+    solver.initialize()
+    for _ in range(W):
+        solver.iterate(1)
+    solver.enable_timing(True)
+    solver.reset_timing()
+    for _ in range(K):
+        solver.iterate(1)
+    tm = solver.get_timing()
+    solver.enable_timing(False)
+    bw_ms = tm.backward_ms / max(tm.backward_launches, 1)
+    alg_bytes = solver.backward_algorithmic_bytes()
+    achieved = alg_bytes / (bw_ms * 1e-3) / 1e9
+    peak = float(peaks["hbm_gbs"])
+    roofline = {"kernel": "backward_sweep", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": bw_ms,
+                "kernel_ms_per_iteration": {"linearize": tm.linearize_ms / max(tm.linearize_launches, 1), "backward": bw_ms,
+                                            "forward": tm.forward_ms / max(tm.forward_launches, 1)}}
+    traffic_file = os.path.join(ROOT, "profiles", "backward_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B and tj.get("config") == args.config:
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+
+    # ---- leg 3: end to end through the C ABI with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        ipc = args.iters_per_call
+        solver.set_options(cddp.default_options(**throughput_options(cfg, ipc)))
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        hin = {k: pin(cfg[k]) for k in ("x0", "xref", "X0", "U0")}
+        hrt = pin(cfg["ref_traj"]) if cfg["ref_traj"] is not None else None
+        hout = {"X": torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory(),
+                "U": torch.empty((B, N, m), dtype=torch.float64).pin_memory(),
+                "K": torch.empty((B, N, m, n), dtype=torch.float64).pin_memory(),
+                "cost": torch.empty(B, dtype=torch.float64).pin_memory(),
+                "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
+                "status": torch.empty(B, dtype=torch.int32).pin_memory()}
+        h2d = sum(v.numel() * v.element_size() for v in hin.values()) + (hrt.numel() * 8 if hrt is not None else 0)
+        d2h = sum(v.numel() * v.element_size() for v in hout.values())
+        lib, h = solver.lib, solver.handle
+
+        def one_call():
+            cddp._check(lib.cddp_b200_set_instances(h, hin["x0"].data_ptr(), hin["xref"].data_ptr(),
+                                                    hrt.data_ptr() if hrt is not None else None,
+                                                    hin["X0"].data_ptr(), hin["U0"].data_ptr()))
+            cddp._check(lib.cddp_b200_solve(h))
+            cddp._check(lib.cddp_b200_get_solution(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr(),
+                                                   hout["cost"].data_ptr(), hout["iters"].data_ptr(),
+                                                   hout["status"].data_ptr(), None, None, None))
+
+        one_call()
+        barrier()
+        t0 = time.perf_counter()
+        calls = max(args.e2e_calls, 1)
+        for _ in range(calls):
+            one_call()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        done = int(hout["iters"].sum().item())
+        assert done == B * ipc
+        e2e = {"value": world * B * ipc * calls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "iterations_per_call": ipc, "calls": calls, "ms_per_call": 1e3 * dt / calls,
+               "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution (pinned host buffers)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_binding as ob
+        threads = ob.hardware_threads()
+        sample = args.cpu_sample or max(threads * 16, 64)
+        ccfg = problems.make_config(args.config, batch=sample)
+        P = ob.OracleProblem(ccfg["spec"])
+        it_cpu = W + K
+        oo = ob.make_options(**throughput_options(ccfg, it_cpu))
+        t0 = time.perf_counter()
+        r = ob.solve_batch(P, oo, ccfg["x0"], ccfg["xref"], ccfg["X0"], ccfg["U0"], ccfg["ref_traj"], nthreads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} instances x {it_cpu} DDP iterations of the same workload, {dt:.1f}s wall, std::thread static partition",
+               "note": "CPU restatement of the reference algorithm (Eigen/autodiff unavailable, reference not buildable here)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["notes"], "n": n, "m": m, "horizon": N, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one all-gather of per-instance results",
+                       "step": "one batched DDP iteration (linearise + backward sweep + forward line search, all alphas in parallel)",
+                       "convergence_exits": "disabled (tolerance=0) so every instance does every iteration",
+                       "l2": "no flush needed: per-iteration working set (linearisation records %.0f MB + gains %.0f MB) "
+                             "exceeds the 126 MB L2" % (8e-6 * B * N * (n * n + n * m + n + 2 * m), 8e-6 * B * N * m * n),
+                       "line_search_alphas": solver.num_alphas},
+            "batched_iterations_per_s": K / (ms * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
+            "clocks": clocks, "all_costs_finite": finite,
+        }
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
