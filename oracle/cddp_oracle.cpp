@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int MAXN = ORACLE_MAX_N;
-constexpr int MAXM = ORACLE_MAX_M;
+constexpr int MAXM = 16; /* capacity (>= ORACLE_MAX_M): the reference BoxQP fixture of test_boxqp.cpp:125-220 is 15x15 */
 constexpr int MAXD = MAXN + MAXM;
 
 /* ------------------------------------------------------------------------------------------

