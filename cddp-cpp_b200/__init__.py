@@ -106,7 +106,8 @@ ABI_SYMBOLS = [
     "cddp_b200_get_feedforward", "cddp_b200_set_gains", "cddp_b200_set_regularization", "cddp_b200_set_cost",
     "cddp_b200_get_linearization", "cddp_b200_set_linearization", "cddp_b200_get_sweep", "cddp_b200_get_forward",
     "cddp_b200_reset_timing", "cddp_b200_get_timing", "cddp_b200_enable_timing",
-    "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host",
+    "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host", "cddp_b200_set_record_layout",
+    "cddp_b200_get_record_layout",
 ]
 
 
@@ -145,6 +146,8 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_destroy.argtypes = [vp]
     lib.cddp_b200_set_stream.argtypes = [vp, vp]
     lib.cddp_b200_set_options.argtypes = [vp, C.POINTER(Options)]
+    lib.cddp_b200_set_record_layout.argtypes = [vp, C.c_int]
+    lib.cddp_b200_get_record_layout.argtypes = [vp, ip, ip]
     lib.cddp_b200_set_instances.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.cddp_b200_set_instances_device.argtypes = [vp, vp, vp, vp, vp, vp]
     for name in ("initialize", "linearize", "backward_pass", "forward_pass", "solve", "synchronize", "reset_timing"):
@@ -288,6 +291,16 @@ class BatchedCLDDP:
         _check(self.lib.cddp_b200_set_options(self.handle, C.byref(opts)))
         self.opts = opts
         self.num_alphas = len(build_alphas(opts))
+
+    def set_record_layout(self, layout):
+        """'dense' (stacked n*n+n*m Jacobians) or 'structured' (the model's structural non-zeros only)."""
+        code = {"dense": 0, "structured": 1}[layout] if isinstance(layout, str) else int(layout)
+        _check(self.lib.cddp_b200_set_record_layout(self.handle, code))
+
+    def get_record_layout(self):
+        lay, nb = C.c_int(0), C.c_int(0)
+        _check(self.lib.cddp_b200_get_record_layout(self.handle, C.byref(lay), C.byref(nb)))
+        return ("dense", "structured")[lay.value], nb.value
 
     def set_instances(self, x0, xref, X0=None, U0=None, ref_traj=None):
         B, n, m, N = self.B, self.n, self.m, self.N

@@ -1,10 +1,549 @@
-// Register-tiled specialisations of the backward sweep (see DESIGN.md "Backward sweep kernel").
-// Until a specialisation exists for a shape, the generic kernel in backward.cu handles it.
+// Batched CLDDP backward Riccati sweep, v2: sub-warp-per-trajectory, row-per-lane, warp-specialised.
+//
+// Reference behaviour followed: CLDDPSolver::backwardPass, src/cddp_core/clddp_solver.cpp:79-204, and the
+// regularisation-retry loop of CDDPSolverBase::solve, src/cddp_core/cddp_solver_base.cpp:93-111 (same
+// statements as backward.cu, which stays as the runtime-dimension fallback).
+//
+// Work decomposition (DESIGN.md "Backward sweep kernel"):
+//   * One trajectory is owned by a GROUP of G = 4/8/16 lanes (smallest power of two > n).  Lane r < n holds
+//     ROW r of V_xx in registers; lane r == n holds V_x^T as an extra row, so that  [V_xx; V_x^T] * [A|B]
+//     yields P_A = V_xx A, P_B = V_xx B and the vector parts A^T V_x, B^T V_x in ONE pass of identical
+//     instructions.  A warp therefore sweeps 32/G trajectories at once and 13 (+1) of every 16 lanes of
+//     each DFMA do useful work (the v1 kernel left 19 of 32 lanes idle in its rank-13 products).
+//   * Q_xx = l_xx + P_A^T A and Q_xu = P_A^T B use the symmetry of V_xx: lane r needs COLUMN r of P_A
+//     (one shared-memory transpose) and the record entries by broadcast.  With a compile-time sparsity
+//     pattern of A = I + dt*Fx (records.cuh) the unrolled loops skip every structural zero.
+//   * The control-space subproblem (PD test, BoxQP, inverse of the free block) is scalar work per
+//     trajectory.  Doing it redundantly in every lane (v1) costs more FP64 issue slots than the matrix
+//     work, so a dedicated QP WARP solves the subproblems of all T trajectories of the CTA, one trajectory
+//     per LANE, between two CTA barriers; the other CTAs resident on the SM cover its latency.
+//   * Records are staged global->shared by TMA bulk copies (cp.async.bulk + mbarrier), double-buffered
+//     one timestep ahead, issued by one lane per trajectory.
+#include <cstdint>
+#include <type_traits>
+
+#include "boxqp_small.cuh"
 #include "engine.h"
+#include "records.cuh"
 
 namespace cddp_b200 {
 
-cudaError_t launch_backward_fast(const Constants &, const DeviceState &, int, cudaStream_t, bool *handled) {
+namespace {
+
+template <int B_, int E_, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (B_ < E_) {
+    f(std::integral_constant<int, B_>{});
+    static_for<B_ + 1, E_>(f);
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+constexpr int group_size(int ns) { return ns + 1 <= 4 ? 4 : (ns + 1 <= 8 ? 8 : 16); }
+
+enum { CTRL_OK = 1, CTRL_RESTART = 2, CTRL_FAIL = 3 };
+
+template <int NS, int NC, class PAT, int W>
+struct SweepCfg {
+  using L = RecordLayout<NS, NC, PAT>;
+  static constexpr int G = group_size(NS);
+  static constexpr int TPW = 32 / G;  // trajectories per warp
+  static constexpr int T = W * TPW;   // trajectories per CTA (one QP-warp lane each)
+  static constexpr int RS = L::stride;
+  // per-trajectory shared-memory block (offsets in doubles)
+  static constexpr int oRec = 0;                          // [2][RS] double-buffered record
+  static constexpr int oPA = oRec + 2 * RS;               // [NS+1][NS]  P_A rows (+ row NS = V_x^T A); reused for the V' transpose
+  static constexpr int oPB = oPA + (NS + 1) * NS;         // [NS+1][NC]
+  static constexpr int oKt = oPB + (NS + 1) * NC;         // [NC][NS] K
+  static constexpr int oMt = oKt + NC * NS;               // [NC][NS] M = Q_uu K + Q_ux
+  static constexpr int oVx = oMt + NC * NS;               // [NS] current V_x
+  static constexpr int oQuu = oVx + NS;                   // [NC][NC] unregularised Q_uu      (matrix lanes -> QP lane)
+  static constexpr int oQu = oQuu + NC * NC;              // [NC]
+  static constexpr int oU = oQu + NC;                     // [NC] nominal control u_t
+  static constexpr int oKprev = oU + NC;                  // [NC] BoxQP warm start k_u_[t]
+  static constexpr int oKk = oKprev + NC;                 // [NC] k                           (QP lane -> matrix lanes)
+  static constexpr int oHinv = oKk + NC;                  // [NC][NC] inverse of the free block of Q_uu_reg, clamped rows/cols 0
+  static constexpr int oW = oHinv + NC * NC;              // [NC] Q_uu k + Q_u
+  static constexpr int oCtrl = oW + NC;                   // int state
+  static constexpr int oBar = oCtrl + 1;                  // 2 x uint64 mbarrier
+  static constexpr int raw = oBar + 2;
+  static constexpr int ST = raw + ((2 - raw % 4) + 4) % 4;  // == 2 (mod 4): even (16-byte aligned records) and the
+                                                            // blocks of neighbouring trajectories start in different banks
+  static constexpr int constDoubles = ((NS * NS + NC * NC) + 1) & ~1;
+  static constexpr size_t smemBytes = sizeof(double) * (size_t)(constDoubles + T * ST);
+  static constexpr int threads = (W + 1) * 32;
+};
+
+template <int NS, int NC, class PAT, int W, int MINB>
+__global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
+  using Cfg = SweepCfg<NS, NC, PAT, W>;
+  using L = typename Cfg::L;
+  constexpr int G = Cfg::G, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
+  extern __shared__ __align__(16) double smem[];
+  double *sQ = smem;            // l_xx = 2 Q dt
+  double *sR = sQ + NS * NS;    // l_uu = 2 R dt
+  double *traj0 = smem + Cfg::constDoubles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = d.N;
+  for (int i = threadIdx.x; i < NS * NS; i += blockDim.x) sQ[i] = c.Qdt2[i];
+  for (int i = threadIdx.x; i < NC * NC; i += blockDim.x) sR[i] = c.Rdt2[i];
+
+  if (warp < W) {
+    // =========================================================== matrix warps
+    const int hw = lane / G, r = lane % G;
+    const int q = warp * TPW + hw;
+    const int b = blockIdx.x * T + q;
+    double *S = traj0 + q * ST;
+    const int rr = r < NS ? r : NS - 1;  // lanes >= NS duplicate row NS-1 in column-type work (results unused)
+    const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+    const int bb = alive ? b : 0;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(S + Cfg::oBar);
+    if (r == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const double *grec = d.rec + (size_t)bb * N * RS;
+    double *gK = d.K + (size_t)bb * N * NC * NS;
+    double *gk = d.kff + (size_t)bb * N * NC;
+    const double *vterm = d.vterm + (size_t)bb * NS;
+
+    double V[NS];  // lane r < NS: row r of V_xx; lane NS: V_x^T
+    uint32_t par0 = 0u, par1 = 0u;        // mbarrier phase parity of each record buffer
+    bool pend0 = false, pend1 = false;    // a bulk copy into the buffer is in flight
+    int t = N - 1, buf = 0;
+    bool run = alive;
+
+    auto issue = [&](int tt, int x) {
+      if (r == 0) {
+        mbar_expect_tx(&bar[x], RS * 8);
+        bulk_g2s(S + Cfg::oRec + x * RS, grec + (size_t)tt * RS, RS * 8, &bar[x]);
+      }
+      if (x) pend1 = true; else pend0 = true;
+    };
+    auto wait_buf = [&](int x) {
+      mbar_wait(&bar[x], x ? par1 : par0);
+      if (x) { par1 ^= 1u; pend1 = false; } else { par0 ^= 1u; pend0 = false; }
+    };
+    auto init_sweep = [&]() {  // V_xx = 2 Qf, V_x = 2 Qf (x_N - ref)  (clddp_solver.cpp:89-92)
+      static_for<0, NS>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        V[j] = (r < NS) ? c.Qf2[rr * NS + j] : vterm[j];
+      });
+      if (r < NS) S[Cfg::oVx + r] = vterm[r];
+      t = N - 1;
+      buf = 0;
+    };
+
+    __syncthreads();  // mbarriers initialised, sQ/sR loaded
+    if (run) {
+      init_sweep();
+      issue(N - 1, 0);
+    }
+    const double qd = sQ[rr * NS + rr];
+
+    while (true) {
+      const bool wrun = __any_sync(0xffffffffu, run);
+      double Qxx[NS], Qxu[NC], Qx = 0.0;
+      if (wrun) {
+        // ------------------------------------------------------------ phase A
+        double kprev = 0.0;
+        if (run && r < NC) kprev = gk[(size_t)t * NC + r];  // warm start k_u_[t] (clddp_solver.cpp:149)
+        if (run) {
+          wait_buf(buf);
+          if (t > 0) issue(t - 1, buf ^ 1);  // next record, one step ahead
+        }
+        const double *rc = S + Cfg::oRec + buf * RS;
+        {
+          // [P_A | P_B](row r) = V(row r) * [A | B]                     (:124-128, first factor)
+          double P[NS + NC];
+#pragma unroll
+          for (int j = 0; j < NS + NC; ++j) P[j] = 0.0;
+          static_for<0, NS>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            static_for<0, NS>([&](auto jc) {
+              constexpr int j = decltype(jc)::value;
+              if constexpr (PAT::a(l, j)) P[j] = fma(V[l], rc[L::idxA(l, j)], P[j]);
+            });
+            if constexpr (PAT::brow(l)) {
+              static_for<0, NC>([&](auto ac) {
+                constexpr int a = decltype(ac)::value;
+                P[NS + a] = fma(V[l], rc[L::idxB(l, a)], P[NS + a]);
+              });
+            }
+          });
+          if (r <= NS) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = P[j];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) S[Cfg::oPB + r * NC + a] = P[NS + a];
+          }
+        }
+        __syncwarp();
+        // Q_uu = l_uu + B^T P_B, one entry per lane; Q_u = l_u + B^T V_x; hand-off to the QP lane
+        for (int e = r; e < NC * NC; e += G) {
+          const int a = e / NC, bcol = e - a * NC;
+          double acc = sR[e];
+          static_for<0, NS>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            if constexpr (PAT::brow(l)) acc = fma(rc[L::idxB(l, 0) + a], S[Cfg::oPB + l * NC + bcol], acc);
+          });
+          if (run) S[Cfg::oQuu + e] = acc;
+        }
+        if (run && r < NC) {
+          S[Cfg::oQu + r] = rc[L::offLu + r] + S[Cfg::oPB + NS * NC + r];
+          S[Cfg::oU + r] = rc[L::offU + r];
+          S[Cfg::oKprev + r] = kprev;
+        }
+      }
+      if (!__syncthreads_or(run ? 1 : 0)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
+      if (wrun) {
+        // ------------------------------------------------------------ phase A2 (overlaps the QP warp's work)
+        const double *rc = S + Cfg::oRec + buf * RS;
+        // Q_xx(row r) = l_xx + (P_A^T A)(row r);  Q_xu(row r) = (P_A^T B)(row r)   (V_xx symmetric)
+        double col[NS];
+#pragma unroll
+        for (int l = 0; l < NS; ++l) col[l] = S[Cfg::oPA + l * NS + rr];
+        if (c.q_diag) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) Qxx[j] = (j == rr) ? qd : 0.0;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) Qxx[j] = sQ[rr * NS + j];
+        }
+#pragma unroll
+        for (int a = 0; a < NC; ++a) Qxu[a] = 0.0;
+        static_for<0, NS>([&](auto lc) {
+          constexpr int l = decltype(lc)::value;
+          static_for<0, NS>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (PAT::a(l, j)) Qxx[j] = fma(col[l], rc[L::idxA(l, j)], Qxx[j]);
+          });
+          if constexpr (PAT::brow(l)) {
+            static_for<0, NC>([&](auto ac) {
+              constexpr int a = decltype(ac)::value;
+              Qxu[a] = fma(col[l], rc[L::idxB(l, a)], Qxu[a]);
+            });
+          }
+        });
+        Qx = rc[L::offLx + rr] + S[Cfg::oPA + NS * NS + rr];  // Q_x = l_x + A^T V_x
+      }
+      __syncthreads();                            // barrier 2: k, H^-1, state visible to the matrix warps
+      if (wrun) {
+        // ------------------------------------------------------------ phase C
+        const int st = run ? *reinterpret_cast<volatile int *>(S + Cfg::oCtrl) : 0;
+        const bool okh = run && st == CTRL_OK;
+        double Kc[NC], Mc[NC];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {  // K(:, r) = -H_free^-1 Q_ux(free, r), clamped rows 0   (:142-178)
+          double s = 0.0;
+#pragma unroll
+          for (int bcol = 0; bcol < NC; ++bcol) s = fma(S[Cfg::oHinv + a * NC + bcol], Qxu[bcol], s);
+          Kc[a] = -s;
+        }
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {  // M(:, r) = Q_uu K(:, r) + Q_ux(:, r)   (unregularised Q_uu)
+          double s = Qxu[a];
+#pragma unroll
+          for (int bcol = 0; bcol < NC; ++bcol) s = fma(S[Cfg::oQuu + a * NC + bcol], Kc[bcol], s);
+          Mc[a] = s;
+        }
+        if (okh && r < NS) {
+#pragma unroll
+          for (int a = 0; a < NC; ++a) {
+            gK[((size_t)t * NC + a) * NS + r] = Kc[a];  // K_u_[t] (:182)
+            S[Cfg::oKt + a * NS + r] = Kc[a];
+            S[Cfg::oMt + a * NS + r] = Mc[a];
+          }
+        }
+        if (okh && r < NC) gk[(size_t)t * NC + r] = S[Cfg::oKk + r];  // k_u_[t] (:181)
+        __syncwarp();
+        double Vn[NS], vxn = Qx;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) Vn[j] = Qxx[j];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {  // V_xx' = Q_xx + K^T M + Q_ux^T K ; V_x' = Q_x + K^T (Q_uu k + Q_u) + Q_ux^T k  (:188-191)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            Vn[j] = fma(Kc[a], S[Cfg::oMt + a * NS + j], Vn[j]);
+            Vn[j] = fma(Qxu[a], S[Cfg::oKt + a * NS + j], Vn[j]);
+          }
+          vxn = fma(Kc[a], S[Cfg::oW + a], vxn);
+          vxn = fma(Qxu[a], S[Cfg::oKk + a], vxn);
+        }
+        if (okh && r < NS) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = Vn[j];
+          S[Cfg::oVx + r] = vxn;
+        }
+        __syncwarp();
+        if (okh) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); lane NS takes the new V_x^T
+            V[j] = (r < NS) ? 0.5 * (Vn[j] + S[Cfg::oPA + j * NS + rr]) : S[Cfg::oVx + j];
+          --t;
+          buf ^= 1;
+          if (t < 0) {  // sweep finished: white-box value function at t = 0
+            run = false;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+              if (r < NS) d.Vxx0[((size_t)b * NS + r) * NS + j] = V[j];
+              if (r == NS) d.Vx0[(size_t)b * NS + j] = V[j];
+            }
+          }
+        } else if (run) {
+          if (pend0) wait_buf(0);  // drain the speculative prefetch
+          if (pend1) wait_buf(1);
+          if (st == CTRL_RESTART) {     // backward failure: sweep again at the increased regularisation
+            init_sweep();
+            issue(N - 1, 0);
+          } else {
+            run = false;
+          }
+        }
+        __syncwarp();  // all reads of the transpose buffer done before the next step overwrites it
+      }
+    }
+  } else {
+    // =========================================================== QP warp: lane q <-> trajectory q
+    constexpr int MC = NC;
+    const int q = lane;
+    const int b = blockIdx.x * T + q;
+    const bool alive = q < T && b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+    const double *S = traj0 + (q < T ? q : T - 1) * ST;
+    double *Sw = traj0 + (q < T ? q : T - 1) * ST;
+    __syncthreads();
+    double reg = alive ? d.reg[b] : 0.0;
+    if (alive && mode == BW_ITERATE) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
+    double dV0 = 0.0, dV1 = 0.0, Qu_err = 0.0, norm_Vx = 0.0;
+    int qt = N - 1, status = CDDP_B200_STATUS_RUNNING;
+    bool run = alive, ok = false;
+    constexpr unsigned all = (1u << NC) - 1u;
+    while (true) {
+      if (!__syncthreads_or(run ? 1 : 0)) break;
+      if (run) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) norm_Vx += fabs(S[Cfg::oVx + j]);  // ||V_x||_1 of the value function entering step t (:107,:194)
+        double H[MC * MC], g[MC], kk[MC];
+#pragma unroll
+        for (int a = 0; a < MC; ++a) {
+          g[a] = S[Cfg::oQu + a];
+#pragma unroll
+          for (int bcol = a; bcol < MC; ++bcol) {  // symmetric storage from the upper triangle
+            const double h = S[Cfg::oQuu + a * MC + bcol] + (a == bcol ? reg : 0.0);  // Q_uu_reg (:130-131)
+            H[a * MC + bcol] = h;
+            H[bcol * MC + a] = h;
+          }
+        }
+        unsigned free_mask = all;
+        bool good;
+        if constexpr (MC <= 4) {
+          // closed-form inverse + Sylvester PD test (boxqp_small.cuh)
+          double Hinv[MC * MC];
+          good = SmallQP<MC>::masked_inverse(H, all, Hinv);  // PD test (:133-140)
+          if (good) {
+            if (c.has_box) {  // (:147-159)
+              double lo[MC], hi[MC];
+#pragma unroll
+              for (int a = 0; a < MC; ++a) {
+                const double un = S[Cfg::oU + a];
+                lo[a] = c.lb[a] - un;
+                hi[a] = c.ub[a] - un;
+                kk[a] = S[Cfg::oKprev + a];
+              }
+              const int qs = SmallQP<MC>::solve(c.opt, H, g, lo, hi, kk, free_mask, Hinv);
+              good = !(qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT);
+              if (good && c.opt.qp_max_iterations <= 0) SmallQP<MC>::masked_inverse(H, free_mask, Hinv);
+              if (free_mask == 0u) {
+#pragma unroll
+                for (int e = 0; e < MC * MC; ++e) Hinv[e] = 0.0;  // ALL_CLAMPED: K = 0 (:163)
+              }
+            } else {  // k = -H^-1 Q_u (:142-144)
+#pragma unroll
+              for (int a = 0; a < MC; ++a) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int bcol = 0; bcol < MC; ++bcol) sacc = fma(Hinv[a * MC + bcol], g[bcol], sacc);
+                kk[a] = -sacc;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < MC * MC; ++e) Sw[Cfg::oHinv + e] = Hinv[e];
+          }
+        } else {
+          double Lf[MC * MC];
+          good = SmallMat<MC>::masked_cholesky(NC, H, all, Lf);  // PD test (:133-140)
+          if (good) {
+            if (c.has_box) {
+              double lo[MC], hi[MC];
+#pragma unroll
+              for (int a = 0; a < MC; ++a) {
+                const double un = S[Cfg::oU + a];
+                lo[a] = c.lb[a] - un;
+                hi[a] = c.ub[a] - un;
+                kk[a] = S[Cfg::oKprev + a];
+              }
+              const int qs = SmallMat<MC>::boxqp(c.opt, NC, H, g, lo, hi, kk, free_mask, Lf);
+              good = !(qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT);
+              if (good && c.opt.qp_max_iterations <= 0) SmallMat<MC>::masked_cholesky(NC, H, free_mask, Lf);
+            } else {
+#pragma unroll
+              for (int a = 0; a < MC; ++a) kk[a] = 0.0;
+            }
+          }
+          if (good) {
+            // inverse of the free block (clamped rows/columns zero): K = -Hinv Q_ux  (:142-145, :161-178)
+#pragma unroll
+            for (int col = 0; col < MC; ++col) {
+              double e[MC];
+#pragma unroll
+              for (int a = 0; a < MC; ++a) e[a] = (a == col) ? 1.0 : 0.0;
+              const bool fc = (free_mask >> col) & 1u;
+              if (fc) SmallMat<MC>::chol_solve(NC, Lf, e);
+#pragma unroll
+              for (int a = 0; a < MC; ++a) {
+                const double hv = (fc && ((free_mask >> a) & 1u)) ? e[a] : 0.0;
+                Sw[Cfg::oHinv + a * MC + col] = hv;
+                if (!c.has_box) kk[a] = fma(-hv, g[col], kk[a]);  // k = -H^-1 Q_u (:144)
+              }
+            }
+          }
+        }
+        if (good) {
+          double d0 = 0.0, d1 = 0.0, linf = 0.0;
+#pragma unroll
+          for (int a = 0; a < MC; ++a) {  // dV += (Q_u.k, 0.5 k^T Q_uu k), unregularised Q_uu (:184-186)
+            double s = 0.0;
+#pragma unroll
+            for (int bcol = 0; bcol < MC; ++bcol) s = fma(S[Cfg::oQuu + a * MC + bcol], kk[bcol], s);
+            d0 = fma(g[a], kk[a], d0);
+            d1 = fma(kk[a], s, d1);
+            linf = fmax(linf, fabs(g[a]));
+            Sw[Cfg::oW + a] = s + g[a];
+            Sw[Cfg::oKk + a] = kk[a];
+          }
+          dV0 += d0;
+          dV1 += 0.5 * d1;
+          Qu_err = fmax(Qu_err, linf);  // (:195)
+          *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_OK;
+          if (--qt < 0) {
+            run = false;
+            ok = true;
+          }
+        } else if (mode == BW_SINGLE) {
+          *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_FAIL;
+          run = false;
+        } else {
+          // increaseRegularization + limit test (cddp_solver_base.cpp:95-109, cddp_core.cpp:308-326)
+          reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+          if (reg >= c.opt.reg_max_value) {
+            status = CDDP_B200_STATUS_REG_LIMIT;
+            *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_FAIL;
+            run = false;
+          } else {
+            *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_RESTART;
+            dV0 = dV1 = Qu_err = norm_Vx = 0.0;
+            qt = N - 1;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (alive) {
+      double inf_du = 0.0;
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) norm_Vx += fabs(S[Cfg::oVx + j]);  // V_x at t = 0
+        double sf = c.opt.termination_scaling_max_factor;               // (:197-201)
+        sf = fmax(sf, norm_Vx / (double)(N * NS)) / sf;
+        inf_du = Qu_err / sf;
+        d.dV[2 * b] = dV0;
+        d.dV[2 * b + 1] = dV1;
+        d.inf_du[b] = inf_du;
+      }
+      d.bw_ok[b] = ok ? 1 : 0;
+      d.lin_valid[b] = 1;
+      if (mode == BW_ITERATE) {
+        d.reg[b] = reg;
+        if (ok && inf_du < c.opt.tolerance) {  // checkEarlyConvergence, clddp_solver.cpp:206-213
+          status = CDDP_B200_STATUS_OPTIMAL;
+          if (d.history) {  // recordIterationHistory, cddp_solver_base.cpp:116-118
+            const int hl = d.history_len[b];
+            if (hl < d.history_cap) {
+              double *h = d.history + ((size_t)b * d.history_cap + hl) * 4;
+              h[0] = d.cost[b];
+              h[1] = d.alpha[b];
+              h[2] = inf_du;
+              h[3] = reg;
+              d.history_len[b] = hl + 1;
+            }
+          }
+        }
+        if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+      }
+    }
+  }
+}
+
+template <int NS, int NC, class PAT, int W, int MINB>
+cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
+  using Cfg = SweepCfg<NS, NC, PAT, W>;
+  static_assert(Cfg::T <= 32, "one QP-warp lane per trajectory");
+  static_assert(NS + 1 <= Cfg::G, "V_x rides as an extra row");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::smemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int blocks = (d.B + Cfg::T - 1) / Cfg::T;
+  sweep_kernel<NS, NC, PAT, W, MINB><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int mode, cudaStream_t st, bool *handled) {
+  *handled = true;
+  const int n = d.n, m = d.m;
+  if (d.layout == RECORDS_STRUCTURED) {
+    if (c.model == CDDP_B200_MODEL_QUADROTOR) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 2>(c, d, mode, st);
+    if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
+    if (c.model == CDDP_B200_MODEL_UNICYCLE) return launch_sweep<3, 2, ModelPattern<CDDP_B200_MODEL_UNICYCLE>, 4, 4>(c, d, mode, st);
+  } else {
+    if (n == 2 && m == 1) return launch_sweep<2, 1, DensePattern, 4, 4>(c, d, mode, st);
+    if (n == 3 && m == 2) return launch_sweep<3, 2, DensePattern, 4, 4>(c, d, mode, st);
+    if (n == 4 && m == 1) return launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
+    if (n == 4 && m == 2) return launch_sweep<4, 2, DensePattern, 7, 2>(c, d, mode, st);
+    if (n == 6 && m == 3) return launch_sweep<6, 3, DensePattern, 7, 2>(c, d, mode, st);
+    if (n == 13 && m == 4) return launch_sweep<13, 4, DensePattern, 7, 2>(c, d, mode, st);
+    if (n == 14 && m == 7) return launch_sweep<14, 7, DensePattern, 7, 1>(c, d, mode, st);
+  }
   *handled = false;
   return cudaSuccess;
 }

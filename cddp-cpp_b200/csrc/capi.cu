@@ -60,6 +60,8 @@ struct cddp_b200_solver {
   DeviceState d{};
   std::vector<void *> allocs;
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
+  int *didxA = nullptr, *didxB = nullptr;
+  double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;
   bool have_instances = false;
@@ -130,6 +132,38 @@ void set_options(cddp_b200_solver *s, const cddp_b200_options &o) {
   s->c.opt = o;
   s->c.num_alphas = build_alphas(o, s->c.alphas, CDDP_B200_MAX_ALPHAS);
   s->d.num_alphas = s->c.num_alphas;
+}
+
+// Selects the record layout (records.cuh): allocates the record buffer of that layout on first use and
+// uploads the index tables the generic pack/unpack kernels use.
+int apply_layout(cddp_b200_solver *s, int layout) {
+  DeviceState &d = s->d;
+  if (layout == RECORDS_STRUCTURED && !model_has_structured_layout(s->c.model)) layout = RECORDS_DENSE;
+  RecordMap map;
+  fill_record_map_for(map, s->c.model, d.n, d.m, layout == RECORDS_STRUCTURED);
+  if (!s->rec_by_layout[layout]) {
+    double *p = nullptr;
+    const size_t cnt = (size_t)d.B * d.N * map.stride;
+    int r = s->alloc(&p, cnt);
+    if (r) return r;
+    CU(cudaMemsetAsync(p, 0, cnt * sizeof(double), s->stream));
+    s->rec_by_layout[layout] = p;
+  }
+  if (!s->didxA) {
+    int r;
+    if ((r = s->alloc(&s->didxA, (size_t)CDDP_B200_MAX_N * CDDP_B200_MAX_N))) return r;
+    if ((r = s->alloc(&s->didxB, (size_t)CDDP_B200_MAX_N * CDDP_B200_MAX_M))) return r;
+  }
+  CU(cudaMemcpyAsync(s->didxA, map.idxA, sizeof(map.idxA), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->didxB, map.idxB, sizeof(map.idxB), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // `map` is a stack object
+  d.rec = s->rec_by_layout[layout];
+  d.rec_stride = map.stride;
+  d.layout = layout;
+  d.idxA = s->didxA;
+  d.idxB = s->didxB;
+  d.offLx = map.offLx; d.offLu = map.offLu; d.offU = map.offU;
+  return 0;
 }
 
 struct KernelTimer {
@@ -322,7 +356,11 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
     c.lb[i] = (p->has_control_box && i < m) ? p->lb[i] : -INFINITY;
     c.ub[i] = (p->has_control_box && i < m) ? p->ub[i] : INFINITY;
   }
-  d.B = batch; d.n = n; d.m = m; d.N = N; d.rec_stride = record_stride(n, m);
+  d.B = batch; d.n = n; d.m = m; d.N = N;
+  c.q_diag = 1;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (i != j && p->Q[i * n + j] != 0.0) c.q_diag = 0;
   set_options(s, *o);
 
 #define AL(ptr, cnt)                       \
@@ -352,7 +390,10 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
 
   AL(d.X[0], B * (N + 1) * n); AL(d.X[1], B * (N + 1) * n);
   AL(d.U[0], B * N * m); AL(d.U[1], B * N * m);
-  AL(d.rec, B * N * d.rec_stride);
+  if ((r = apply_layout(s, RECORDS_STRUCTURED))) {  // falls back to dense for models without a pattern
+    cddp_b200_destroy(s);
+    return r;
+  }
   AL(d.vterm, B * n);
   AL(d.K, B * N * m * n); AL(d.kff, B * N * m);
   AL(d.x0, B * n); AL(d.xref, B * n);
@@ -364,8 +405,7 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
   AL(d.num_running, 1);
   d.history = nullptr; d.history_len = nullptr; d.history_cap = 0;
 #undef AL
-  e = cudaMemset(d.rec, 0, B * N * d.rec_stride * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemset(d.cur, 0, B * sizeof(int));
+  e = cudaMemset(d.cur, 0, B * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d.status, 0, B * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d.K, 0, B * N * m * n * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(d.kff, 0, B * N * m * sizeof(double));
@@ -402,6 +442,26 @@ int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *o) {
   if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS || o->max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (s->d.history && o->max_iterations + 1 > s->d.history_cap) return CDDP_B200_ERR_STATE;
   set_options(s, *o);
+  return 0;
+}
+
+int cddp_b200_set_record_layout(cddp_b200_solver *s, int layout) {
+  if (!s || (layout != CDDP_B200_RECORDS_DENSE && layout != CDDP_B200_RECORDS_STRUCTURED)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const bool had = s->initialized;
+  int r = apply_layout(s, layout);
+  if (r) return r;
+  if (had) {  // re-derive the records of the current nominal trajectory in the new layout
+    CU(launch_linearize(s->c, s->d, true, s->stream));
+    s->timing.other_launches++;
+  }
+  return 0;
+}
+
+int cddp_b200_get_record_layout(cddp_b200_solver *s, int *layout, int *record_bytes) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (layout) *layout = s->d.layout;
+  if (record_bytes) *record_bytes = s->d.rec_stride * (int)sizeof(double);
   return 0;
 }
 
@@ -625,6 +685,10 @@ int cddp_b200_set_linearization(cddp_b200_solver *s, const double *A, const doub
   const DeviceState &d = s->d;
   const size_t na = (size_t)d.B * d.N * d.n * d.n, nb = (size_t)d.B * d.N * d.n * d.m;
   int r;
+  if (d.layout != RECORDS_DENSE) {
+    // caller-supplied Jacobians are dense by definition: carry the cost terms over to dense records
+    if ((r = cddp_b200_set_record_layout(s, CDDP_B200_RECORDS_DENSE))) return r;
+  }
   if ((r = s->ensure_scratch((na + nb) * sizeof(double)))) return r;
   CU(cudaMemcpyAsync(s->scratch, A, na * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->scratch + na, Bm, nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));

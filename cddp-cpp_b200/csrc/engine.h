@@ -4,6 +4,7 @@
 
 #include "../../include/cddp_b200.h"
 #include "models.cuh"
+#include "records.cuh"
 
 namespace cddp_b200 {
 
@@ -13,15 +14,20 @@ namespace cddp_b200 {
 //
 //  X[2]     : [B][N+1][n]   double-buffered nominal / candidate state trajectory (cur[b] selects)
 //  U[2]     : [B][N][m]
-//  rec      : [B][N][rec_stride]  per-timestep linearisation record consumed by the backward sweep:
-//               A (n*n) | B (n*m) | lx (n) | lu (m) | u (m) | pad to an even count (16-byte multiple
-//               so that one cp.async.bulk moves one record)
+//  rec      : [B][N][rec_stride]  per-timestep linearisation record consumed by the backward sweep
+//               (records.cuh): A entries | B rows | lx (n) | lu (m) | u (m) | pad to an even count
+//               (16-byte multiple so that one cp.async.bulk moves one record).  `layout` says whether
+//               A,B are stored densely or only at the model's structural non-zeros.
 //  vterm    : [B][n]        terminal gradient V_x(N) = 2 Qf (x_N - ref)
 //  K        : [B][N][m][n]  feedback gains K_u_
 //  kff      : [B][N][m]     feed-forward k_u_ (updated in place: doubles as BoxQP warm start)
 struct DeviceState {
   int B, n, m, N;
   int rec_stride;  // doubles per record
+  int layout;      // RECORDS_DENSE / RECORDS_STRUCTURED
+  const int *idxA; // device [n*n] record index of A(l,j), -1 = structural zero   (generic pack/unpack kernels)
+  const int *idxB; // device [n*m]
+  int offLx, offLu, offU;
   int num_alphas;
   double *X[2];
   double *U[2];
@@ -56,6 +62,7 @@ struct DeviceState {
 // batch-shared constants, passed by value to kernels (fits the 4 KB parameter space comfortably)
 struct Constants {
   int model, n, m, N, integrator, has_box;
+  int q_diag;  // Q is diagonal (l_xx touches only the diagonal of Q_xx)
   double dt;
   ModelParams mp;
   const double *Qdt2;  // device [n][n] = 2*Q*dt  (l_xx, objective.cpp:130-134)
@@ -67,10 +74,7 @@ struct Constants {
   cddp_b200_options opt;
 };
 
-inline int record_stride(int n, int m) {
-  int c = n * n + n * m + n + 2 * m;
-  return (c + 1) & ~1;
-}
+enum RecordLayoutKind { RECORDS_DENSE = 0, RECORDS_STRUCTURED = 1 };
 
 enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };
 enum ForwardMode { FW_EVALUATE = 0 /* do not apply */, FW_ITERATE = 1 };

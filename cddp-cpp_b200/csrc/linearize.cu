@@ -6,6 +6,8 @@
 //              and the terminal gradient V_x(N) = 2 Qf (x_N - ref) (objective.cpp:122-126).
 //  initialize: initializeProblemIfNecessary + CLDDPSolver::initialize cold start
 //              (cddp_core.cpp:272-306, clddp_solver.cpp:68-74, cddp_solver_base.cpp:416-424).
+#include <type_traits>
+
 #include "engine.h"
 
 namespace cddp_b200 {
@@ -17,9 +19,20 @@ __device__ __forceinline__ const double *ref_ptr(const DeviceState &d, int b, in
   return d.ref_traj ? d.ref_traj + ((size_t)b * (d.N + 1) + t) * d.n : d.xref + (size_t)b * d.n;
 }
 
-template <int MODEL>
+template <int B_, int E_, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (B_ < E_) {
+    f(std::integral_constant<int, B_>{});
+    static_for<B_ + 1, E_>(f);
+  }
+}
+
+// One thread per (instance, t).  PAT = DensePattern (RECORDS_DENSE) or ModelPattern<MODEL> (RECORDS_STRUCTURED):
+// only entries inside the pattern are stored; the analytic Jacobians are identically zero outside it.
+template <int MODEL, class PAT>
 __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState d, int force) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  using L = RecordLayout<NS, NC, PAT>;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = d.N + 1;
   if (gid >= (long long)d.B * per) return;
@@ -49,15 +62,20 @@ __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState
   for (int i = 0; i < NC; ++i) u[i] = up[i];
   double Fx[NS * NS], Fu[NS * NC];
   Model<MODEL>::jac(c.mp, x, u, Fx, Fu);
-  double *r = d.rec + ((size_t)b * d.N + t) * d.rec_stride;
-#pragma unroll
-  for (int i = 0; i < NS; ++i)
-#pragma unroll
-    for (int j = 0; j < NS; ++j) r[i * NS + j] = c.dt * Fx[i * NS + j] + (i == j ? 1.0 : 0.0);
-  r += NS * NS;
-#pragma unroll
-  for (int i = 0; i < NS * NC; ++i) r[i] = c.dt * Fu[i];
-  r += NS * NC;
+  double *r = d.rec + ((size_t)b * d.N + t) * L::stride;
+  static_for<0, NS>([&](auto lc) {
+    constexpr int l = decltype(lc)::value;
+    static_for<0, NS>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      if constexpr (PAT::a(l, j)) r[L::idxA(l, j)] = c.dt * Fx[l * NS + j] + (l == j ? 1.0 : 0.0);
+    });
+    if constexpr (PAT::brow(l)) {
+      static_for<0, NC>([&](auto ac) {
+        constexpr int a = decltype(ac)::value;
+        r[L::idxB(l, a)] = c.dt * Fu[l * NC + a];
+      });
+    }
+  });
   const double *ref = ref_ptr(d, b, t);
   double e[NS];
 #pragma unroll
@@ -66,18 +84,16 @@ __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
-    r[i] = s;
+    r[L::offLx + i] = s;
   }
-  r += NS;
   for (int i = 0; i < NC; ++i) {
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
-    r[i] = s;
+    r[L::offLu + i] = s;
   }
-  r += NC;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) r[i] = u[i];
+  for (int i = 0; i < NC; ++i) r[L::offU + i] = u[i];
 }
 
 // LTI: runtime dimensions; Fx = (A_d - I)/dt, Fu = B_d/dt (lti_system.cpp:78-92) then the solver's
@@ -211,17 +227,20 @@ __global__ void unpack_lin_kernel(DeviceState d, double *A, double *Bm) {
   if (gid >= (long long)d.B * d.N) return;
   const int n = d.n, m = d.m;
   const double *r = d.rec + (size_t)gid * d.rec_stride;
-  for (int i = 0; i < n * n; ++i) A[(size_t)gid * n * n + i] = r[i];
-  for (int i = 0; i < n * m; ++i) Bm[(size_t)gid * n * m + i] = r[n * n + i];
+  for (int i = 0; i < n * n; ++i) A[(size_t)gid * n * n + i] = d.idxA[i] >= 0 ? r[d.idxA[i]] : 0.0;
+  for (int i = 0; i < n * m; ++i) Bm[(size_t)gid * n * m + i] = d.idxB[i] >= 0 ? r[d.idxB[i]] : 0.0;
 }
 
+// dense layout only (capi switches the solver to RECORDS_DENSE before packing caller-supplied Jacobians)
 __global__ void pack_lin_kernel(DeviceState d, const double *A, const double *Bm) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)d.B * d.N) return;
   const int n = d.n, m = d.m;
   double *r = d.rec + (size_t)gid * d.rec_stride;
-  for (int i = 0; i < n * n; ++i) r[i] = A[(size_t)gid * n * n + i];
-  for (int i = 0; i < n * m; ++i) r[n * n + i] = Bm[(size_t)gid * n * m + i];
+  for (int i = 0; i < n * n; ++i)
+    if (d.idxA[i] >= 0) r[d.idxA[i]] = A[(size_t)gid * n * n + i];
+  for (int i = 0; i < n * m; ++i)
+    if (d.idxB[i] >= 0) r[d.idxB[i]] = Bm[(size_t)gid * n * m + i];
 }
 
 // copy the nominal (which=0) or candidate (which=1) trajectory of every instance to contiguous output
@@ -237,26 +256,31 @@ __global__ void gather_current_kernel(DeviceState d, double *X, double *U, int w
 
 }  // namespace
 
-cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st) {
+cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t stream) {
   const long long total = (long long)d.B * (d.N + 1);
   const int threads = 128;
   const int blocks = (int)((total + threads - 1) / threads);
+  const bool st = d.layout == RECORDS_STRUCTURED;
+#define LIN(MODEL, PAT) linearize_kernel<MODEL, PAT><<<blocks, threads, 0, st_>>>(c, d, force)
+  cudaStream_t st_ = stream;
   switch (c.model) {
-    case CDDP_B200_MODEL_PENDULUM:
-      linearize_kernel<CDDP_B200_MODEL_PENDULUM><<<blocks, threads, 0, st>>>(c, d, force);
-      break;
+    case CDDP_B200_MODEL_PENDULUM: LIN(CDDP_B200_MODEL_PENDULUM, DensePattern); break;
     case CDDP_B200_MODEL_CARTPOLE:
-      linearize_kernel<CDDP_B200_MODEL_CARTPOLE><<<blocks, threads, 0, st>>>(c, d, force);
+      if (st) LIN(CDDP_B200_MODEL_CARTPOLE, ModelPattern<CDDP_B200_MODEL_CARTPOLE>);
+      else LIN(CDDP_B200_MODEL_CARTPOLE, DensePattern);
       break;
     case CDDP_B200_MODEL_UNICYCLE:
-      linearize_kernel<CDDP_B200_MODEL_UNICYCLE><<<blocks, threads, 0, st>>>(c, d, force);
+      if (st) LIN(CDDP_B200_MODEL_UNICYCLE, ModelPattern<CDDP_B200_MODEL_UNICYCLE>);
+      else LIN(CDDP_B200_MODEL_UNICYCLE, DensePattern);
       break;
     case CDDP_B200_MODEL_QUADROTOR:
-      linearize_kernel<CDDP_B200_MODEL_QUADROTOR><<<blocks, threads, 0, st>>>(c, d, force);
+      if (st) LIN(CDDP_B200_MODEL_QUADROTOR, ModelPattern<CDDP_B200_MODEL_QUADROTOR>);
+      else LIN(CDDP_B200_MODEL_QUADROTOR, DensePattern);
       break;
-    case CDDP_B200_MODEL_LTI: linearize_lti_kernel<<<blocks, threads, 0, st>>>(c, d, force); break;
+    case CDDP_B200_MODEL_LTI: linearize_lti_kernel<<<blocks, threads, 0, st_>>>(c, d, force); break;
     default: return cudaErrorInvalidValue;
   }
+#undef LIN
   return cudaGetLastError();
 }
 

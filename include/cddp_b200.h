@@ -166,6 +166,15 @@ CDDP_B200_API int cddp_b200_set_stream(cddp_b200_solver *s, void *cuda_stream);
 /* CDDP::setOptions (cddp_core.cpp:109-113): rebuilds the alpha schedule */
 CDDP_B200_API int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *opts);
 
+/* HBM layout of the per-timestep linearisation records the backward sweep streams (no reference
+ * counterpart: the reference recomputes A = I + dt*Fx, B = dt*Fu inside the loop, clddp_solver.cpp:113-118).
+ * DENSE = stacked n*n + n*m Jacobians (any model; required for cddp_b200_set_linearization, which
+ * switches to it).  STRUCTURED = only the structural non-zeros of the built-in model's Jacobians
+ * (default when the model has a pattern; the sweep kernel unrolls over the pattern). */
+enum { CDDP_B200_RECORDS_DENSE = 0, CDDP_B200_RECORDS_STRUCTURED = 1 };
+CDDP_B200_API int cddp_b200_set_record_layout(cddp_b200_solver *s, int layout);
+CDDP_B200_API int cddp_b200_get_record_layout(cddp_b200_solver *s, int *layout, int *record_bytes);
+
 /* ---- per-instance data: CDDP::setInitialState / setReferenceState(s) / setInitialTrajectory
  * (cddp_core.cpp:68-100,127-142).  Host pointers; copied H2D on the solver's stream.
  * ref_traj may be NULL (single reference state, objective.cpp:84-88).  X0 may be NULL: the state

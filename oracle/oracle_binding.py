@@ -74,6 +74,28 @@ def load():
     return lib
 
 
+class variant:
+    """Context manager: route calls to liboracle_fma.so (same algorithm, fp contraction on)."""
+
+    def __enter__(self):
+        global _lib
+        self.prev = load()
+        path = os.path.join(_HERE, "liboracle_fma.so")
+        if not os.path.exists(path):
+            build()
+        lib = C.CDLL(path)
+        lib.oracle_running_cost.restype = C.c_double
+        lib.oracle_terminal_cost.restype = C.c_double
+        lib.oracle_trajectory_cost.restype = C.c_double
+        lib.oracle_status_string.restype = C.c_char_p
+        _lib = lib
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self.prev
+
+
 def _f64(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
 
