@@ -61,6 +61,7 @@ struct cddp_b200_solver {
   std::vector<void *> allocs;
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
   int *didxA = nullptr, *didxB = nullptr;
+  int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;
@@ -350,7 +351,9 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
   DeviceState &d = s->d;
   c.model = p->model; c.n = n; c.m = m; c.N = N; c.integrator = p->integrator; c.has_box = p->has_control_box ? 1 : 0;
   c.dt = p->dt;
-  std::memcpy(c.mp.p, p->model_params, sizeof(c.mp.p));
+  std::memset(c.mp.p, 0, sizeof(c.mp.p));
+  std::memcpy(c.mp.p, p->model_params, sizeof(p->model_params));
+  if (p->model == CDDP_B200_MODEL_QUADROTOR) Model<CDDP_B200_MODEL_QUADROTOR>::prepare(c.mp);
   c.mp.n = n; c.mp.m = m;
   for (int i = 0; i < CDDP_B200_MAX_M; ++i) {
     c.lb[i] = (p->has_control_box && i < m) ? p->lb[i] : -INFINITY;
@@ -361,6 +364,13 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j)
       if (i != j && p->Q[i * n + j] != 0.0) c.q_diag = 0;
+  c.cost_diag = c.q_diag;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (i != j && p->Qf[i * n + j] != 0.0) c.cost_diag = 0;
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j)
+      if (i != j && p->R[i * m + j] != 0.0) c.cost_diag = 0;
   set_options(s, *o);
 
 #define AL(ptr, cnt)                       \
@@ -402,6 +412,8 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
   AL(d.reg, B); AL(d.cost, B); AL(d.alpha, B); AL(d.inf_du, B); AL(d.dV, 2 * B);
   AL(d.ls_cost, B * CDDP_B200_MAX_ALPHAS);
   AL(d.Vx0, B * n); AL(d.Vxx0, B * n * n);
+  s->ckpt_lg = s->c.num_alphas > 16 ? 32 : 16;
+  AL(d.ckpt, B * s->ckpt_lg * s->ckpt_lg * n);
   AL(d.num_running, 1);
   d.history = nullptr; d.history_len = nullptr; d.history_cap = 0;
 #undef AL
@@ -441,6 +453,14 @@ int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *o) {
   if (!s || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS || o->max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (s->d.history && o->max_iterations + 1 > s->d.history_cap) return CDDP_B200_ERR_STATE;
+  if (count_alphas(*o) > 16 && s->ckpt_lg < 32) {  // more than 16 alphas: one trajectory per warp, bigger scratch
+    DeviceGuard g(s->device);
+    double *p = nullptr;
+    int r = s->alloc(&p, (size_t)s->d.B * 32 * 32 * s->d.n);
+    if (r) return r;
+    s->d.ckpt = p;
+    s->ckpt_lg = 32;
+  }
   set_options(s, *o);
   return 0;
 }

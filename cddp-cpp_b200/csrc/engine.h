@@ -53,6 +53,7 @@ struct DeviceState {
   double *ls_cost; // [B][CDDP_B200_MAX_ALPHAS] cost of every line-search candidate
   double *Vx0;     // [B][n]   value gradient at t=0 after the last sweep (white-box)
   double *Vxx0;    // [B][n][n]
+  double *ckpt;    // [B][LG][LG][n] line-search scratch: state of every alpha at the start of every segment
   double *history; // [B][max_iterations+1][4] or nullptr
   int *history_len;
   int history_cap;
@@ -62,7 +63,8 @@ struct DeviceState {
 // batch-shared constants, passed by value to kernels (fits the 4 KB parameter space comfortably)
 struct Constants {
   int model, n, m, N, integrator, has_box;
-  int q_diag;  // Q is diagonal (l_xx touches only the diagonal of Q_xx)
+  int q_diag;     // Q is diagonal (l_xx touches only the diagonal of Q_xx)
+  int cost_diag;  // Q, R and Qf are all diagonal
   double dt;
   ModelParams mp;
   const double *Qdt2;  // device [n][n] = 2*Q*dt  (l_xx, objective.cpp:130-134)

@@ -19,8 +19,11 @@
 
 namespace cddp_b200 {
 
+// p[0..15] = cddp_b200_problem.model_params; p[16..] = derived constants filled by prepare_model_params()
+// (quadrotor: p[16..24] = inertia^-1 row-major, p[25] = 1/mass — the reference recomputes inertia_.inverse() in
+// every dynamics call, quadrotor.cpp:92).
 struct ModelParams {
-  double p[16];
+  double p[32];
   const double *lti_A;  // device, [n][n]
   const double *lti_B;  // device, [n][m]
   int n, m;
@@ -132,30 +135,39 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
   struct Inertia {
     double I[9], Iinv[9];
   };
-  __device__ __forceinline__ static void inertia(const ModelParams &P, Inertia &J) {
+  __host__ __device__ __forceinline__ static void inertia(const ModelParams &P, Inertia &J) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) J.I[i] = P.p[1 + i];
-    const double *I = J.I;
+    for (int i = 0; i < 9; ++i) {
+      J.I[i] = P.p[1 + i];
+      J.Iinv[i] = P.p[16 + i];
+    }
+  }
+  // host-side: 3x3 inverse by cofactors, stored in p[16..24]; p[25] = 1/mass
+  __host__ static void prepare(ModelParams &P) {
+    const double *I = P.p + 1;
     const double c00 = I[4] * I[8] - I[5] * I[7], c01 = I[2] * I[7] - I[1] * I[8], c02 = I[1] * I[5] - I[2] * I[4];
     const double c10 = I[5] * I[6] - I[3] * I[8], c11 = I[0] * I[8] - I[2] * I[6], c12 = I[2] * I[3] - I[0] * I[5];
     const double c20 = I[3] * I[7] - I[4] * I[6], c21 = I[1] * I[6] - I[0] * I[7], c22 = I[0] * I[4] - I[1] * I[3];
     const double id = 1.0 / (I[0] * c00 + I[1] * c10 + I[2] * c20);
-    J.Iinv[0] = c00 * id; J.Iinv[1] = c01 * id; J.Iinv[2] = c02 * id;
-    J.Iinv[3] = c10 * id; J.Iinv[4] = c11 * id; J.Iinv[5] = c12 * id;
-    J.Iinv[6] = c20 * id; J.Iinv[7] = c21 * id; J.Iinv[8] = c22 * id;
+    double *o = P.p + 16;
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+    o[3] = c10 * id; o[4] = c11 * id; o[5] = c12 * id;
+    o[6] = c20 * id; o[7] = c21 * id; o[8] = c22 * id;
+    P.p[25] = 1.0 / P.p[0];
   }
 
   __device__ __forceinline__ static void f(const ModelParams &P, const double *x, const double *u, double *xd) {
-    const double mass = P.p[0], L = P.p[10], gravity = 9.81;
+    const double L = P.p[10], gravity = 9.81;
     Inertia J;
     inertia(P, J);
     xd[0] = x[7];
     xd[1] = x[8];
     xd[2] = x[9];
     double qw = x[3], qx = x[4], qy = x[5], qz = x[6];
-    const double norm = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
-    if (norm > 1e-6) {
-      qw /= norm; qx /= norm; qy /= norm; qz /= norm;
+    const double n2 = qw * qw + qx * qx + qy * qy + qz * qz;
+    if (n2 > 1e-12) {  // ||q|| > 1e-6 (quadrotor.cpp:45-55); q/||q|| as q * rsqrt(|q|^2): one reciprocal-sqrt, no divisions
+      const double inv = rsqrt(n2);
+      qw *= inv; qx *= inv; qy *= inv; qz *= inv;
     } else {
       qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0;
     }
@@ -166,7 +178,7 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
     xd[6] = 0.5 * (qw * wz + qx * wy - qy * wx);
     const double thrust = u[0] + u[1] + u[2] + u[3];
     const double tx = L * (u[0] - u[2]), ty = L * (u[1] - u[3]), tz = 0.1 * (u[0] - u[1] + u[2] - u[3]);
-    const double im = 1.0 / mass;
+    const double im = P.p[25];
     xd[7] = im * (2.0 * (qx * qz + qy * qw) * thrust);
     xd[8] = im * (2.0 * (qy * qz - qx * qw) * thrust);
     xd[9] = im * ((1.0 - 2.0 * (qx * qx + qy * qy)) * thrust) - gravity;
