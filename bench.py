@@ -210,6 +210,7 @@ def main():
     for _ in range(W):
         solver.iterate(1)
     barrier()
+    solver.reset_timing()  # launch counters only (event timing stays off in this leg)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -223,6 +224,8 @@ def main():
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
+    tl = solver.get_timing()
+    gpu_launches = int(tl.linearize_launches + tl.backward_launches + tl.forward_launches + tl.other_launches)
     clocks = sampler.stop(t_wall0, t_wall1)
     sc = solver.get_scalars()
     iters_done = int(sc["iterations"].sum())
@@ -231,14 +234,12 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        # the path's single collective: all-gather of per-instance results (cost, iterations, status)
-        mine = torch.from_numpy(np.stack([sc["cost"], sc["iterations"].astype(np.float64), sc["status"].astype(np.float64)], 1)).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        all_cost = torch.cat(gathered)[:, 0]
-        finite = bool(torch.isfinite(all_cost).all().item())
-    else:
-        finite = bool(np.isfinite(sc["cost"]).all())
+    # the path's single collective: all-gather of per-instance results (cost, iterations, status) over NCCL
+    sharding = importlib.import_module("cddp-cpp_b200.sharding")
+    all_cost, all_iters, _ = sharding.gather_results(sc["cost"], sc["iterations"], sc["status"], B * world,
+                                                     device=torch.device("cuda", local_rank) if world > 1 else None)
+    finite = bool(np.isfinite(all_cost).all())
+    assert int(all_iters.sum()) == world * B * (W + K)
     value = world * B * K / (ms * 1e-3)
 
     # ---- leg 2: per-kernel CUDA-event timing of the same iterations (roofline for the backward sweep) ----
@@ -324,7 +325,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_binding as ob
         threads = ob.hardware_threads()
-        sample = args.cpu_sample or max(threads * 16, 64)
+        sample = args.cpu_sample or B  # the same batch the GPU ran (~10 s of host work at cfg 3)
         ccfg = problems.make_config(args.config, batch=sample)
         P = ob.OracleProblem(ccfg["spec"])
         it_cpu = W + K
@@ -341,14 +342,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["notes"], "n": n, "m": m, "horizon": N, "batch_per_gpu": B, "global_batch": B * world,
+                       "record_layout": "%s (%d B/record)" % solver.get_record_layout(),
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one all-gather of per-instance results",
                        "step": "one batched DDP iteration (linearise + backward sweep + forward line search, all alphas in parallel)",
                        "convergence_exits": "disabled (tolerance=0) so every instance does every iteration",
-                       "l2": "no flush needed: per-iteration working set (linearisation records %.0f MB + gains %.0f MB) "
-                             "exceeds the 126 MB L2" % (8e-6 * B * N * (n * n + n * m + n + 2 * m), 8e-6 * B * N * m * n),
+                       "l2": "no flush needed: per-iteration working set (linearisation records %.0f MB + gains %.0f MB + "
+                             "trajectories %.0f MB) exceeds the 126 MB L2"
+                             % (1e-6 * B * N * solver.get_record_layout()[1], 8e-6 * B * N * m * n, 2 * 8e-6 * B * N * (n + m)),
                        "line_search_alphas": solver.num_alphas},
             "batched_iterations_per_s": K / (ms * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": clocks, "all_costs_finite": finite,
         }
         print(json.dumps(line), flush=True)
