@@ -74,22 +74,26 @@ struct SweepCfg {
   static constexpr int TPW = 32 / G;  // trajectories per warp
   static constexpr int T = W * TPW;   // trajectories per CTA (one QP-warp lane each)
   static constexpr int RS = L::stride;
-  // per-trajectory shared-memory block (offsets in doubles)
+  // per-trajectory shared-memory block (offsets in doubles).  Every field starts on an even offset (16 bytes): nvcc
+  // merges stores/loads of neighbouring doubles into 128-bit accesses and has been seen (compute-sanitizer, pendulum
+  // instantiation) to do so across two 1-element fields at an ODD offset, which faults; with even field starts every
+  // merged pair is 16-byte aligned.
+  static constexpr int ev(int x) { return (x + 1) & ~1; }
   static constexpr int oRec = 0;                          // [2][RS] double-buffered record
   static constexpr int oPA = oRec + 2 * RS;               // [NS+1][NS]  P_A rows (+ row NS = V_x^T A); reused for the V' transpose
-  static constexpr int oPB = oPA + (NS + 1) * NS;         // [NS+1][NC]
-  static constexpr int oKt = oPB + (NS + 1) * NC;         // [NC][NS] K
-  static constexpr int oMt = oKt + NC * NS;               // [NC][NS] M = Q_uu K + Q_ux
-  static constexpr int oVx = oMt + NC * NS;               // [NS] current V_x
-  static constexpr int oQuu = oVx + NS;                   // [NC][NC] unregularised Q_uu      (matrix lanes -> QP lane)
-  static constexpr int oQu = oQuu + NC * NC;              // [NC]
-  static constexpr int oU = oQu + NC;                     // [NC] nominal control u_t
-  static constexpr int oKprev = oU + NC;                  // [NC] BoxQP warm start k_u_[t]
-  static constexpr int oKk = oKprev + NC;                 // [NC] k                           (QP lane -> matrix lanes)
-  static constexpr int oHinv = oKk + NC;                  // [NC][NC] inverse of the free block of Q_uu_reg, clamped rows/cols 0
-  static constexpr int oW = oHinv + NC * NC;              // [NC] Q_uu k + Q_u
-  static constexpr int oCtrl = oW + NC;                   // int state
-  static constexpr int oBar = oCtrl + 1;                  // 2 x uint64 mbarrier
+  static constexpr int oPB = oPA + ev((NS + 1) * NS);     // [NS+1][NC]
+  static constexpr int oQux = oPB + ev((NS + 1) * NC);    // [NC][NS] Q_ux
+  static constexpr int oVx = oQux + ev(NC * NS);          // [NS] scratch for the new V_x
+  static constexpr int oQuu = oVx + ev(NS);               // [NC][NC] unregularised Q_uu      (matrix lanes -> QP lane)
+  static constexpr int oQu = oQuu + ev(NC * NC);          // [NC]
+  static constexpr int oU = oQu + ev(NC);                 // [NC] nominal control u_t
+  static constexpr int oKprev = oU + ev(NC);              // [NC] BoxQP warm start k_u_[t]
+  static constexpr int oKk = oKprev + ev(NC);             // [NC] k                           (QP lane -> matrix lanes)
+  static constexpr int oHinv = oKk + ev(NC);              // [NC][NC] Ht = inverse of the free block of Q_uu_reg, clamped rows/cols 0
+  static constexpr int oW = oHinv + ev(NC * NC);          // [NC] w = Q_uu k + Q_u
+  static constexpr int oNrm = oW + ev(NC);                // sum_t ||V_x||_1 (matrix lane NS -> QP lane, at the end of the sweep)
+  static constexpr int oCtrl = oNrm + 2;                  // int state
+  static constexpr int oBar = oCtrl + 2;                  // 2 x uint64 mbarrier
   static constexpr int raw = oBar + 2;
   static constexpr int ST = raw + ((2 - raw % 4) + 4) % 4;  // == 2 (mod 4): even (16-byte aligned records) and the
                                                             // blocks of neighbouring trajectories start in different banks
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     const int q = warp * TPW + hw;
     const int b = blockIdx.x * T + q;
     double *S = traj0 + q * ST;
+    const volatile double *Sv = S;  // for broadcast reads (see phase A1)
     const int rr = r < NS ? r : NS - 1;  // lanes >= NS duplicate row NS-1 in column-type work (results unused)
     const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
     const int bb = alive ? b : 0;
@@ -149,14 +154,15 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       mbar_wait(&bar[x], x ? par1 : par0);
       if (x) { par1 ^= 1u; pend1 = false; } else { par0 ^= 1u; pend0 = false; }
     };
+    double nrm = 0.0;  // lane NS: sum over the sweep of ||V_x||_1 (clddp_solver.cpp:107,:194)
     auto init_sweep = [&]() {  // V_xx = 2 Qf, V_x = 2 Qf (x_N - ref)  (clddp_solver.cpp:89-92)
       static_for<0, NS>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         V[j] = (r < NS) ? c.Qf2[rr * NS + j] : vterm[j];
       });
-      if (r < NS) S[Cfg::oVx + r] = vterm[r];
       t = N - 1;
       buf = 0;
+      nrm = 0.0;
     };
 
     __syncthreads();  // mbarriers initialised, sQ/sR loaded
@@ -170,47 +176,44 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       const bool wrun = __any_sync(0xffffffffu, run);
       double Qxx[NS], Qxu[NC], Qx = 0.0;
       if (wrun) {
-        // ------------------------------------------------------------ phase A
+        // ------------------------------------------------------------ phase A1 (critical path): what the QP needs
         double kprev = 0.0;
         if (run && r < NC) kprev = gk[(size_t)t * NC + r];  // warm start k_u_[t] (clddp_solver.cpp:149)
         if (run) {
           wait_buf(buf);
           if (t > 0) issue(t - 1, buf ^ 1);  // next record, one step ahead
         }
-        const double *rc = S + Cfg::oRec + buf * RS;
+        // BROADCAST operand reads go through a volatile pointer on purpose: nvcc would merge neighbouring doubles into
+        // LDS.128, and a broadcast LDS.128 costs 2 shared-memory cycles per warp against <=0.5 for LDS.64 (measured,
+        // tools/microbench/lds_broadcast.cu) — 2x more per byte, and shared-memory issue is what bounds this kernel.
+        const volatile double *rc = S + Cfg::oRec + buf * RS;
         {
-          // [P_A | P_B](row r) = V(row r) * [A | B]                     (:124-128, first factor)
-          double P[NS + NC];
+          // P_B(row r) = V(row r) * B ; lane NS: (B^T V_x)^T
+          double PBr[NC];
 #pragma unroll
-          for (int j = 0; j < NS + NC; ++j) P[j] = 0.0;
+          for (int a = 0; a < NC; ++a) PBr[a] = 0.0;
           static_for<0, NS>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
-            static_for<0, NS>([&](auto jc) {
-              constexpr int j = decltype(jc)::value;
-              if constexpr (PAT::a(l, j)) P[j] = fma(V[l], rc[L::idxA(l, j)], P[j]);
-            });
             if constexpr (PAT::brow(l)) {
               static_for<0, NC>([&](auto ac) {
                 constexpr int a = decltype(ac)::value;
-                P[NS + a] = fma(V[l], rc[L::idxB(l, a)], P[NS + a]);
+                PBr[a] = fma(V[l], rc[L::idxB(l, a)], PBr[a]);
               });
             }
           });
           if (r <= NS) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = P[j];
-#pragma unroll
-            for (int a = 0; a < NC; ++a) S[Cfg::oPB + r * NC + a] = P[NS + a];
+            for (int a = 0; a < NC; ++a) S[Cfg::oPB + r * NC + a] = PBr[a];
           }
         }
         __syncwarp();
-        // Q_uu = l_uu + B^T P_B, one entry per lane; Q_u = l_u + B^T V_x; hand-off to the QP lane
+        // Q_uu = l_uu + B^T P_B, one entry per lane; Q_u = l_u + B^T V_x; hand-off to the QP lane   (:125,:128)
         for (int e = r; e < NC * NC; e += G) {
           const int a = e / NC, bcol = e - a * NC;
           double acc = sR[e];
           static_for<0, NS>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
-            if constexpr (PAT::brow(l)) acc = fma(rc[L::idxB(l, 0) + a], S[Cfg::oPB + l * NC + bcol], acc);
+            if constexpr (PAT::brow(l)) acc = fma(rc[L::idxB(l, 0) + a], Sv[Cfg::oPB + l * NC + bcol], acc);
           });
           if (run) S[Cfg::oQuu + e] = acc;
         }
@@ -222,8 +225,30 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       }
       if (!__syncthreads_or(run ? 1 : 0)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
       if (wrun) {
-        // ------------------------------------------------------------ phase A2 (overlaps the QP warp's work)
-        const double *rc = S + Cfg::oRec + buf * RS;
+        // ------------------------------------------------------------ phase A2 (in the shadow of the QP warp)
+        const volatile double *rc = S + Cfg::oRec + buf * RS;
+        {
+          // P_A(row r) = V(row r) * A ; lane NS: (A^T V_x)^T                                  (:124,:126-127)
+          double PAr[NS];
+#pragma unroll
+          for (int j = 0; j < NS; ++j) PAr[j] = 0.0;
+          static_for<0, NS>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            static_for<0, NS>([&](auto jc) {
+              constexpr int j = decltype(jc)::value;
+              if constexpr (PAT::a(l, j)) PAr[j] = fma(V[l], rc[L::idxA(l, j)], PAr[j]);
+            });
+          });
+          if (r <= NS) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = PAr[j];
+          }
+          double l1 = 0.0;  // ||V_x||_1 of the value function entering this step (lane NS holds V_x)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) l1 += fabs(V[j]);
+          nrm += l1;
+        }
+        __syncwarp();
         // Q_xx(row r) = l_xx + (P_A^T A)(row r);  Q_xu(row r) = (P_A^T B)(row r)   (V_xx symmetric)
         double col[NS];
 #pragma unroll
@@ -251,49 +276,65 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
           }
         });
         Qx = rc[L::offLx + rr] + S[Cfg::oPA + NS * NS + rr];  // Q_x = l_x + A^T V_x
+        if (r < NS) {
+#pragma unroll
+          for (int a = 0; a < NC; ++a) S[Cfg::oQux + a * NS + r] = Qxu[a];
+        }
       }
-      __syncthreads();                            // barrier 2: k, H^-1, state visible to the matrix warps
+      __syncthreads();  // barrier 2: k, Ht, w, state visible to the matrix warps (and Q_ux to the other lanes)
       if (wrun) {
-        // ------------------------------------------------------------ phase C
+        // ------------------------------------------------------------ phase C (critical path): value update
         const int st = run ? *reinterpret_cast<volatile int *>(S + Cfg::oCtrl) : 0;
         const bool okh = run && st == CTRL_OK;
-        double Kc[NC], Mc[NC];
+        // With K = -Ht Q_ux (Ht symmetric, zero in clamped rows/columns):
+        //   V_xx' = Q_xx + K^T Q_uu K + Q_ux^T K + K^T Q_ux = Q_xx + Q_ux^T T,   T(:, r) = 2 K(:, r) - Ht Q_uu K(:, r)
+        //   V_x'  = Q_x + K^T (Q_uu k + Q_u) + Q_ux^T k      = Q_x + Q_ux^T (k - Ht w),  w = Q_uu k + Q_u      (:188-191)
+        // Each lane forms its own column of K and T from three m x m mat-vecs (no shared-memory round trip on the
+        // critical path); the only broadcast stream left is Q_ux (m x n), staged during the QP's shadow.
+        double Kc[NC], z[NC], QK[NC], T[NC];
+        {
+          double Ht[NC * NC];
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {  // K(:, r) = -H_free^-1 Q_ux(free, r), clamped rows 0   (:142-178)
-          double s = 0.0;
+          for (int e = 0; e < NC * NC; ++e) Ht[e] = Sv[Cfg::oHinv + e];
 #pragma unroll
-          for (int bcol = 0; bcol < NC; ++bcol) s = fma(S[Cfg::oHinv + a * NC + bcol], Qxu[bcol], s);
-          Kc[a] = -s;
-        }
+          for (int a = 0; a < NC; ++a) {  // K(:, r) = -Ht Q_ux(:, r)   (:142-178) ;  z = k - Ht w
+            double sK = 0.0, sz = 0.0;
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {  // M(:, r) = Q_uu K(:, r) + Q_ux(:, r)   (unregularised Q_uu)
-          double s = Qxu[a];
+            for (int bcol = 0; bcol < NC; ++bcol) {
+              sK = fma(Ht[a * NC + bcol], Qxu[bcol], sK);
+              sz = fma(Ht[a * NC + bcol], Sv[Cfg::oW + bcol], sz);
+            }
+            Kc[a] = -sK;
+            z[a] = Sv[Cfg::oKk + a] - sz;
+          }
 #pragma unroll
-          for (int bcol = 0; bcol < NC; ++bcol) s = fma(S[Cfg::oQuu + a * NC + bcol], Kc[bcol], s);
-          Mc[a] = s;
+          for (int a = 0; a < NC; ++a) {  // Q_uu K(:, r)   (unregularised Q_uu)
+            double sq = 0.0;
+#pragma unroll
+            for (int bcol = 0; bcol < NC; ++bcol) sq = fma(Sv[Cfg::oQuu + a * NC + bcol], Kc[bcol], sq);
+            QK[a] = sq;
+          }
+#pragma unroll
+          for (int a = 0; a < NC; ++a) {
+            double sT = 2.0 * Kc[a];
+#pragma unroll
+            for (int bcol = 0; bcol < NC; ++bcol) sT = fma(-Ht[a * NC + bcol], QK[bcol], sT);
+            T[a] = sT;
+          }
         }
         if (okh && r < NS) {
 #pragma unroll
-          for (int a = 0; a < NC; ++a) {
-            gK[((size_t)t * NC + a) * NS + r] = Kc[a];  // K_u_[t] (:182)
-            S[Cfg::oKt + a * NS + r] = Kc[a];
-            S[Cfg::oMt + a * NS + r] = Mc[a];
-          }
+          for (int a = 0; a < NC; ++a) gK[((size_t)t * NC + a) * NS + r] = Kc[a];  // K_u_[t] (:182)
         }
         if (okh && r < NC) gk[(size_t)t * NC + r] = S[Cfg::oKk + r];  // k_u_[t] (:181)
-        __syncwarp();
         double Vn[NS], vxn = Qx;
 #pragma unroll
         for (int j = 0; j < NS; ++j) Vn[j] = Qxx[j];
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {  // V_xx' = Q_xx + K^T M + Q_ux^T K ; V_x' = Q_x + K^T (Q_uu k + Q_u) + Q_ux^T k  (:188-191)
+        for (int a = 0; a < NC; ++a) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            Vn[j] = fma(Kc[a], S[Cfg::oMt + a * NS + j], Vn[j]);
-            Vn[j] = fma(Qxu[a], S[Cfg::oKt + a * NS + j], Vn[j]);
-          }
-          vxn = fma(Kc[a], S[Cfg::oW + a], vxn);
-          vxn = fma(Qxu[a], S[Cfg::oKk + a], vxn);
+          for (int j = 0; j < NS; ++j) Vn[j] = fma(T[a], Sv[Cfg::oQux + a * NS + j], Vn[j]);
+          vxn = fma(Qxu[a], z[a], vxn);
         }
         if (okh && r < NS) {
 #pragma unroll
@@ -304,16 +345,19 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         if (okh) {
 #pragma unroll
           for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); lane NS takes the new V_x^T
-            V[j] = (r < NS) ? 0.5 * (Vn[j] + S[Cfg::oPA + j * NS + rr]) : S[Cfg::oVx + j];
+            V[j] = (r < NS) ? 0.5 * (Vn[j] + S[Cfg::oPA + j * NS + rr]) : Sv[Cfg::oVx + j];
           --t;
           buf ^= 1;
-          if (t < 0) {  // sweep finished: white-box value function at t = 0
+          if (t < 0) {  // sweep finished: white-box value function at t = 0, and the V_x(0) term of the norm
             run = false;
+            double l1 = 0.0;
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
+              l1 += fabs(V[j]);
               if (r < NS) d.Vxx0[((size_t)b * NS + r) * NS + j] = V[j];
               if (r == NS) d.Vx0[(size_t)b * NS + j] = V[j];
             }
+            if (r == NS) S[Cfg::oNrm] = nrm + l1;
           }
         } else if (run) {
           if (pend0) wait_buf(0);  // drain the speculative prefetch
@@ -339,16 +383,14 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     __syncthreads();
     double reg = alive ? d.reg[b] : 0.0;
     if (alive && mode == BW_ITERATE) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
-    double dV0 = 0.0, dV1 = 0.0, Qu_err = 0.0, norm_Vx = 0.0;
+    double dV0 = 0.0, dV1 = 0.0, Qu_err = 0.0;
     int qt = N - 1, status = CDDP_B200_STATUS_RUNNING;
     bool run = alive, ok = false;
     constexpr unsigned all = (1u << NC) - 1u;
     while (true) {
       if (!__syncthreads_or(run ? 1 : 0)) break;
       if (run) {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) norm_Vx += fabs(S[Cfg::oVx + j]);  // ||V_x||_1 of the value function entering step t (:107,:194)
-        double H[MC * MC], g[MC], kk[MC];
+        double H[MC * MC], g[MC], kk[MC], Hk[MC];
 #pragma unroll
         for (int a = 0; a < MC; ++a) {
           g[a] = S[Cfg::oQu + a];
@@ -364,9 +406,9 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         if constexpr (MC <= 4) {
           // closed-form inverse + Sylvester PD test (boxqp_small.cuh)
           double Hinv[MC * MC];
-          good = SmallQP<MC>::masked_inverse(H, all, Hinv);  // PD test (:133-140)
-          if (good) {
-            if (c.has_box) {  // (:147-159)
+          if (c.has_box) {  // (:147-159)
+            good = SymPD<MC>::run(H);  // PD test (:133-140)
+            if (good) {
               double lo[MC], hi[MC];
 #pragma unroll
               for (int a = 0; a < MC; ++a) {
@@ -375,22 +417,29 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
                 hi[a] = c.ub[a] - un;
                 kk[a] = S[Cfg::oKprev + a];
               }
-              const int qs = SmallQP<MC>::solve(c.opt, H, g, lo, hi, kk, free_mask, Hinv);
+              const int qs = SmallQP<MC>::solve(c.opt, H, g, lo, hi, kk, free_mask, Hinv, Hk);
               good = !(qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT);
-              if (good && c.opt.qp_max_iterations <= 0) SmallQP<MC>::masked_inverse(H, free_mask, Hinv);
-              if (free_mask == 0u) {
-#pragma unroll
-                for (int e = 0; e < MC * MC; ++e) Hinv[e] = 0.0;  // ALL_CLAMPED: K = 0 (:163)
-              }
-            } else {  // k = -H^-1 Q_u (:142-144)
-#pragma unroll
-              for (int a = 0; a < MC; ++a) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int bcol = 0; bcol < MC; ++bcol) sacc = fma(Hinv[a * MC + bcol], g[bcol], sacc);
-                kk[a] = -sacc;
-              }
+              if (good && c.opt.qp_max_iterations <= 0) SmallQP<MC>::masked_inverse_raw(H, free_mask, Hinv);
+              SmallQP<MC>::zero_clamped(free_mask, Hinv);  // ALL_CLAMPED: free_mask == 0 -> K = 0 (:163)
             }
+          } else {  // k = -H^-1 Q_u (:142-144)
+            good = SymInverse<MC>::run(H, Hinv);
+#pragma unroll
+            for (int a = 0; a < MC; ++a) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int bcol = 0; bcol < MC; ++bcol) sacc = fma(Hinv[a * MC + bcol], g[bcol], sacc);
+              kk[a] = -sacc;
+            }
+#pragma unroll
+            for (int a = 0; a < MC; ++a) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int bcol = 0; bcol < MC; ++bcol) sacc = fma(H[a * MC + bcol], kk[bcol], sacc);
+              Hk[a] = sacc;
+            }
+          }
+          if (good) {
 #pragma unroll
             for (int e = 0; e < MC * MC; ++e) Sw[Cfg::oHinv + e] = Hinv[e];
           }
@@ -431,19 +480,24 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
                 if (!c.has_box) kk[a] = fma(-hv, g[col], kk[a]);  // k = -H^-1 Q_u (:144)
               }
             }
+#pragma unroll
+            for (int a = 0; a < MC; ++a) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int bcol = 0; bcol < MC; ++bcol) sacc = fma(H[a * MC + bcol], kk[bcol], sacc);
+              Hk[a] = sacc;
+            }
           }
         }
         if (good) {
           double d0 = 0.0, d1 = 0.0, linf = 0.0;
 #pragma unroll
           for (int a = 0; a < MC; ++a) {  // dV += (Q_u.k, 0.5 k^T Q_uu k), unregularised Q_uu (:184-186)
-            double s = 0.0;
-#pragma unroll
-            for (int bcol = 0; bcol < MC; ++bcol) s = fma(S[Cfg::oQuu + a * MC + bcol], kk[bcol], s);
+            const double sq = fma(-reg, kk[a], Hk[a]);  // (Q_uu k)_a = (Q_uu_reg k)_a - reg k_a
             d0 = fma(g[a], kk[a], d0);
-            d1 = fma(kk[a], s, d1);
+            d1 = fma(kk[a], sq, d1);
             linf = fmax(linf, fabs(g[a]));
-            Sw[Cfg::oW + a] = s + g[a];
+            Sw[Cfg::oW + a] = sq + g[a];
             Sw[Cfg::oKk + a] = kk[a];
           }
           dV0 += d0;
@@ -466,7 +520,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
             run = false;
           } else {
             *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_RESTART;
-            dV0 = dV1 = Qu_err = norm_Vx = 0.0;
+            dV0 = dV1 = Qu_err = 0.0;
             qt = N - 1;
           }
         }
@@ -476,8 +530,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     if (alive) {
       double inf_du = 0.0;
       if (ok) {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) norm_Vx += fabs(S[Cfg::oVx + j]);  // V_x at t = 0
+        const double norm_Vx = S[Cfg::oNrm];  // accumulated by the lane that holds V_x
         double sf = c.opt.termination_scaling_max_factor;               // (:197-201)
         sf = fmax(sf, norm_Vx / (double)(N * NS)) / sf;
         inf_du = Qu_err / sf;

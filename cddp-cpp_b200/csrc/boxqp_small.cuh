@@ -111,11 +111,53 @@ struct SymInverse<4> {
   }
 };
 
+// Sylvester's criterion on the FULL matrix only (no inverse): the PD test of clddp_solver.cpp:133-140.
+template <int M>
+struct SymPD;
+template <>
+struct SymPD<1> {
+  __device__ __forceinline__ static bool run(const double *a) { return a[0] > 0.0; }
+};
+template <>
+struct SymPD<2> {
+  __device__ __forceinline__ static bool run(const double *a) { return (a[0] > 0.0) && (a[0] * a[3] - a[1] * a[1] > 0.0); }
+};
+template <>
+struct SymPD<3> {
+  __device__ __forceinline__ static bool run(const double *a) {
+    const double c00 = a[4] * a[8] - a[5] * a[5], c01 = a[2] * a[5] - a[1] * a[8], c02 = a[1] * a[5] - a[2] * a[4];
+    return (a[0] > 0.0) && (a[0] * a[4] - a[1] * a[1] > 0.0) && (a[0] * c00 + a[1] * c01 + a[2] * c02 > 0.0);
+  }
+};
+template <>
+struct SymPD<4> {
+  __device__ __forceinline__ static bool run(const double *a) {
+#define A_(i, j) a[(i) * 4 + (j)]
+    const double s0 = A_(0, 0) * A_(1, 1) - A_(0, 1) * A_(0, 1);
+    const double s1 = A_(0, 0) * A_(1, 2) - A_(0, 1) * A_(0, 2);
+    const double s2 = A_(0, 0) * A_(1, 3) - A_(0, 1) * A_(0, 3);
+    const double s3 = A_(0, 1) * A_(1, 2) - A_(1, 1) * A_(0, 2);
+    const double s4 = A_(0, 1) * A_(1, 3) - A_(1, 1) * A_(0, 3);
+    const double s5 = A_(0, 2) * A_(1, 3) - A_(1, 2) * A_(0, 3);
+    const double c5 = A_(2, 2) * A_(3, 3) - A_(2, 3) * A_(2, 3);
+    const double c4 = A_(1, 2) * A_(3, 3) - A_(1, 3) * A_(2, 3);
+    const double c3 = A_(1, 2) * A_(2, 3) - A_(1, 3) * A_(2, 2);
+    const double c2 = A_(0, 2) * A_(3, 3) - A_(0, 3) * A_(2, 3);
+    const double c1 = A_(0, 2) * A_(2, 3) - A_(0, 3) * A_(2, 2);
+    const double c0 = A_(0, 2) * A_(1, 3) - A_(0, 3) * A_(1, 2);
+    const double det = (s0 * c5 - s1 * c4) + (s2 * c3 + s3 * c2) + (s5 * c0 - s4 * c1);
+    const double n33 = A_(0, 2) * s3 - A_(1, 2) * s1 + A_(2, 2) * s0;
+#undef A_
+    return (a[0] > 0.0) && (s0 > 0.0) && (n33 > 0.0) && (det > 0.0);
+  }
+};
+
 template <int M>
 struct SmallQP {
-  // inverse of the masked matrix; rows/columns of clamped indices are returned as ZERO (so that
-  // Hinv * rhs needs no further masking).  H must be symmetric-stored.
-  __device__ __forceinline__ static bool masked_inverse(const double *H, unsigned free_mask, double *Hinv) {
+  // inverse of the masked matrix (clamped rows/columns replaced by identity).  The result is block diagonal: its
+  // free block is the inverse of the free block of H; clamped rows/columns come back as identity rows — callers
+  // mask their right-hand sides / results instead of paying 2*M*M selects here.  H must be symmetric-stored.
+  __device__ __forceinline__ static bool masked_inverse_raw(const double *H, unsigned free_mask, double *Inv) {
     double Hm[M * M];
 #pragma unroll
     for (int i = 0; i < M; ++i)
@@ -124,43 +166,52 @@ struct SmallQP {
         const bool f = ((free_mask >> i) & 1u) && ((free_mask >> j) & 1u);
         Hm[i * M + j] = f ? H[i * M + j] : (i == j ? 1.0 : 0.0);
       }
-    double Inv[M * M];
-    const bool pd = SymInverse<M>::run(Hm, Inv);
+    return SymInverse<M>::run(Hm, Inv);
+  }
+  // same, with clamped rows/columns zeroed (the form K = -Hinv Q_ux wants)
+  __device__ __forceinline__ static bool masked_inverse(const double *H, unsigned free_mask, double *Hinv) {
+    const bool pd = masked_inverse_raw(H, free_mask, Hinv);
+    zero_clamped(free_mask, Hinv);
+    return pd;
+  }
+  __device__ __forceinline__ static void zero_clamped(unsigned free_mask, double *Hinv) {
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         const bool f = ((free_mask >> i) & 1u) && ((free_mask >> j) & 1u);
-        Hinv[i * M + j] = f ? Inv[i * M + j] : 0.0;
+        Hinv[i * M + j] = f ? Hinv[i * M + j] : 0.0;
       }
-    return pd;
   }
 
-  __device__ __forceinline__ static double value(const double *H, const double *g, const double *x) {
-    double a = 0.0, bb = 0.0;
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      double hx = 0.0;
-#pragma unroll
-      for (int j = 0; j < M; ++j) hx += H[i * M + j] * x[j];
-      a += x[i] * hx;
-      bb += g[i] * x[i];
-    }
-    return 0.5 * a + bb;
-  }
-
-  // BoxQPSolver::solve.  x: in = warm start, out = solution.  On return free_mask / Hinv describe the
-  // free set of the LAST factorisation (boxqp.cpp:89-111), Hinv zero in clamped rows/columns; for
-  // QP_ALL_CLAMPED free_mask == 0 and Hinv is left untouched (the caller uses K = 0).
+  // BoxQPSolver::solve.  x: in = warm start, out = solution.  On return free_mask / Hinv describe the free set of
+  // the LAST factorisation (boxqp.cpp:89-111): Hinv is the raw masked inverse (use zero_clamped before forming K);
+  // for QP_ALL_CLAMPED free_mask == 0 and Hinv is whatever was last computed (the caller uses K = 0, clddp_solver.cpp:163).
+  // H x is carried between iterations: the product evaluated for the Armijo test of the accepted candidate IS the
+  // one the next iteration's gradient needs (same arithmetic as recomputing it, boxqp.cpp:61 / :170-172).  On return
+  // Hx = H x for the returned x.
   __device__ static int solve(const cddp_b200_options &o, const double *H, const double *g, const double *lo,
-                              const double *hi, double *x, unsigned &free_mask, double *Hinv) {
+                              const double *hi, double *x, unsigned &free_mask, double *Hinv, double *Hx) {
     constexpr unsigned all = (1u << M) - 1u;
     int status = QP_MAX_ITER_EXCEEDED;
 #pragma unroll
     for (int i = 0; i < M; ++i) x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+    auto matvec_value = [&](const double *z, double *Hz) {  // 0.5 z^T H z + g^T z  (boxqp.cpp:235-239)
+      double a = 0.0, bb = 0.0;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) s += H[i * M + j] * z[j];
+        Hz[i] = s;
+        a += z[i] * s;
+        bb += g[i] * z[i];
+      }
+      return 0.5 * a + bb;
+    };
     unsigned clamped = 0u;
     free_mask = all;
-    double value_ = value(H, g, x);
+    double value_ = matvec_value(x, Hx);
     double old_value = __longlong_as_double(0x7ff0000000000000LL);
     const double gtol2 = o.qp_min_gradient_norm * o.qp_min_gradient_norm;
     for (int iter = 0; iter < o.qp_max_iterations; ++iter) {
@@ -171,12 +222,7 @@ struct SmallQP {
       old_value = value_;
       double grad[M];
 #pragma unroll
-      for (int i = 0; i < M; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) s += H[i * M + j] * x[j];
-        grad[i] = g[i] + s;
-      }
+      for (int i = 0; i < M; ++i) grad[i] = g[i] + Hx[i];
       const unsigned old_clamped = clamped;
       clamped = 0u;
 #pragma unroll
@@ -188,7 +234,7 @@ struct SmallQP {
         break;
       }
       if (iter == 0 || clamped != old_clamped) {
-        if (!masked_inverse(H, free_mask, Hinv)) {
+        if (!masked_inverse_raw(H, free_mask, Hinv)) {
           status = QP_HESSIAN_NOT_PD;
           break;
         }
@@ -208,7 +254,7 @@ struct SmallQP {
 #pragma unroll
         for (int i = 0; i < M; ++i)
           if ((clamped >> i) & 1u) s += H[j * M + i] * x[i];
-        rhs[j] = s;
+        rhs[j] = ((free_mask >> j) & 1u) ? s : 0.0;  // masked rhs: the identity rows of the raw inverse then contribute nothing
       }
       double search[M];
       double sdotg = 0.0;
@@ -216,7 +262,7 @@ struct SmallQP {
       for (int i = 0; i < M; ++i) {
         double y = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) y += Hinv[i * M + j] * rhs[j];  // clamped rows/columns of Hinv are zero
+        for (int j = 0; j < M; ++j) y += Hinv[i * M + j] * rhs[j];
         search[i] = ((free_mask >> i) & 1u) ? (-y - x[i]) : 0.0;
         sdotg += search[i] * grad[i];
       }
@@ -226,11 +272,11 @@ struct SmallQP {
       }
       double step = 1.0, vn = 0.0;
       bool ls_ok = false;
-      double xn[M];
+      double xn[M], Hxn[M];
       while (step > o.qp_min_step_size) {
 #pragma unroll
         for (int i = 0; i < M; ++i) xn[i] = fmin(fmax(x[i] + step * search[i], lo[i]), hi[i]);
-        vn = value(H, g, xn);
+        vn = matvec_value(xn, Hxn);
         if ((vn - value_) <= o.qp_armijo_constant * step * sdotg) {
           ls_ok = true;
           break;
@@ -242,8 +288,11 @@ struct SmallQP {
         break;
       }
 #pragma unroll
-      for (int i = 0; i < M; ++i) x[i] = xn[i];
-      value_ = vn;  // evaluateObjective(x) of the accepted candidate: identical arithmetic (boxqp.cpp:170-172)
+      for (int i = 0; i < M; ++i) {
+        x[i] = xn[i];
+        Hx[i] = Hxn[i];
+      }
+      value_ = vn;
     }
     return status;
   }
