@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--config", default="quadrotor")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's batch)")
     ap.add_argument("--iters-per-call", type=int, default=10, help="DDP iterations per e2e solve call")
-    ap.add_argument("--e2e-calls", type=int, default=3)
+    ap.add_argument("--e2e-calls", type=int, default=6)
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -274,50 +274,91 @@ def main():
         except Exception:
             pass
 
-    # ---- leg 3: end to end through the C ABI with pinned host buffers ----
+    # ---- leg 3: end to end through the C ABI with pinned HOST buffers, the way a serving loop calls it ----
+    # Every call uploads its inputs (x0, xref, X0, U0) host->device and downloads its full solution (X, U, K, cost,
+    # iterations, status) device->host inside the timed region.  Two solver handles on two CUDA streams are used
+    # alternately (double buffering across calls: call k+1's upload + solve overlaps call k's download), each with
+    # its own pinned buffers; "serial" is the same measurement on ONE handle with a blocking call sequence.
     e2e = None
     if not args.no_e2e:
         ipc = args.iters_per_call
-        solver.set_options(cddp.default_options(**throughput_options(cfg, ipc)))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-        hin = {k: pin(cfg[k]) for k in ("x0", "xref", "X0", "U0")}
-        hrt = pin(cfg["ref_traj"]) if cfg["ref_traj"] is not None else None
-        hout = {"X": torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory(),
-                "U": torch.empty((B, N, m), dtype=torch.float64).pin_memory(),
-                "K": torch.empty((B, N, m, n), dtype=torch.float64).pin_memory(),
-                "cost": torch.empty(B, dtype=torch.float64).pin_memory(),
-                "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
-                "status": torch.empty(B, dtype=torch.int32).pin_memory()}
-        h2d = sum(v.numel() * v.element_size() for v in hin.values()) + (hrt.numel() * 8 if hrt is not None else 0)
-        d2h = sum(v.numel() * v.element_size() for v in hout.values())
-        lib, h = solver.lib, solver.handle
+        lib = solver.lib
 
-        def one_call():
-            cddp._check(lib.cddp_b200_set_instances(h, hin["x0"].data_ptr(), hin["xref"].data_ptr(),
-                                                    hrt.data_ptr() if hrt is not None else None,
-                                                    hin["X0"].data_ptr(), hin["U0"].data_ptr()))
-            cddp._check(lib.cddp_b200_solve(h))
-            cddp._check(lib.cddp_b200_get_solution(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr(),
-                                                   hout["cost"].data_ptr(), hout["iters"].data_ptr(),
-                                                   hout["status"].data_ptr(), None, None, None))
+        class Lane:
+            def __init__(self, slv, strm):
+                self.s, self.stream = slv, strm
+                slv.set_stream(strm.cuda_stream)
+                slv.set_options(cddp.default_options(**throughput_options(cfg, ipc)))
+                self.hin = {k: pin(cfg[k]) for k in ("x0", "xref", "X0", "U0")}
+                self.hrt = pin(cfg["ref_traj"]) if cfg["ref_traj"] is not None else None
+                self.hout = {"X": torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory(),
+                             "U": torch.empty((B, N, m), dtype=torch.float64).pin_memory(),
+                             "K": torch.empty((B, N, m, n), dtype=torch.float64).pin_memory(),
+                             "cost": torch.empty(B, dtype=torch.float64).pin_memory(),
+                             "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
+                             "status": torch.empty(B, dtype=torch.int32).pin_memory()}
 
-        one_call()
+            def enqueue(self, blocking):
+                h, hin, hout = self.s.handle, self.hin, self.hout
+                cddp._check(lib.cddp_b200_set_instances(h, hin["x0"].data_ptr(), hin["xref"].data_ptr(),
+                                                        self.hrt.data_ptr() if self.hrt is not None else None,
+                                                        hin["X0"].data_ptr(), hin["U0"].data_ptr()))
+                cddp._check(lib.cddp_b200_solve(h))
+                get = lib.cddp_b200_get_solution if blocking else lib.cddp_b200_get_solution_async
+                cddp._check(get(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr(), hout["cost"].data_ptr(),
+                                hout["iters"].data_ptr(), hout["status"].data_ptr(), None, None, None))
+
+            def wait(self):
+                self.s.synchronize()
+                assert int(self.hout["iters"].sum().item()) == B * ipc
+                assert bool(torch.isfinite(self.hout["cost"]).all().item())
+
+        lane0 = Lane(solver, torch.cuda.Stream())
+        h2d = sum(v.numel() * v.element_size() for v in lane0.hin.values()) + (lane0.hrt.numel() * 8 if lane0.hrt is not None else 0)
+        d2h = sum(v.numel() * v.element_size() for v in lane0.hout.values())
+        calls = max(args.e2e_calls, 2)
+        # (a) serial: one handle, blocking calls
+        lane0.enqueue(True)
         barrier()
         t0 = time.perf_counter()
-        calls = max(args.e2e_calls, 1)
         for _ in range(calls):
-            one_call()
+            lane0.enqueue(True)
+        barrier()
+        dt_serial = time.perf_counter() - t0
+        # (b) pipelined: two handles, asynchronous calls
+        solver2 = cddp.BatchedCLDDP(spec, cddp.default_options(**throughput_options(cfg, ipc)), B, device=local_rank)
+        lane1 = Lane(solver2, torch.cuda.Stream())
+        lanes = [lane0, lane1]
+        for ln in lanes:
+            ln.s.set_poll_interval(0)
+            ln.enqueue(False)
+            ln.wait()
+        barrier()
+        t0 = time.perf_counter()
+        inflight = [False, False]
+        for k in range(calls):
+            i = k & 1
+            if inflight[i]:
+                lanes[i].wait()
+            lanes[i].enqueue(False)
+            inflight[i] = True
+        for i in (0, 1):
+            if inflight[i]:
+                lanes[i].wait()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt, dt_serial], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        done = int(hout["iters"].sum().item())
-        assert done == B * ipc
+            dt, dt_serial = float(t[0].item()), float(t[1].item())
         e2e = {"value": world * B * ipc * calls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "iterations_per_call": ipc, "calls": calls, "ms_per_call": 1e3 * dt / calls,
-               "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution (pinned host buffers)"}
+               "serial_value": world * B * ipc * calls / dt_serial, "serial_ms_per_call": 1e3 * dt_serial / calls,
+               "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution[_async] on pinned host buffers; "
+                      "value = two handles double-buffered on two CUDA streams, serial_value = one handle, blocking calls"}
+        solver2.close()
+        solver.set_stream(stream.cuda_stream)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
     cpu = None

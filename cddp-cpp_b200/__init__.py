@@ -107,7 +107,7 @@ ABI_SYMBOLS = [
     "cddp_b200_get_linearization", "cddp_b200_set_linearization", "cddp_b200_get_sweep", "cddp_b200_get_forward",
     "cddp_b200_reset_timing", "cddp_b200_get_timing", "cddp_b200_enable_timing",
     "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host", "cddp_b200_set_record_layout",
-    "cddp_b200_get_record_layout",
+    "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_get_solution_async",
 ]
 
 
@@ -155,6 +155,8 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_iterate.argtypes = [vp, C.c_int]
     lib.cddp_b200_num_running.argtypes = [vp, ip]
     lib.cddp_b200_get_solution.argtypes = [vp] + [vp] * 9
+    lib.cddp_b200_get_solution_async.argtypes = [vp] + [vp] * 9
+    lib.cddp_b200_set_poll_interval.argtypes = [vp, C.c_int]
     lib.cddp_b200_enable_history.argtypes = [vp, C.c_int]
     lib.cddp_b200_get_history.argtypes = [vp, vp, vp]
     lib.cddp_b200_get_feedforward.argtypes = [vp, vp]
@@ -301,6 +303,9 @@ class BatchedCLDDP:
         lay, nb = C.c_int(0), C.c_int(0)
         _check(self.lib.cddp_b200_get_record_layout(self.handle, C.byref(lay), C.byref(nb)))
         return ("dense", "structured")[lay.value], nb.value
+
+    def set_poll_interval(self, interval: int):
+        _check(self.lib.cddp_b200_set_poll_interval(self.handle, int(interval)))
 
     def set_instances(self, x0, xref, X0=None, U0=None, ref_traj=None):
         B, n, m, N = self.B, self.n, self.m, self.N

@@ -62,6 +62,7 @@ struct cddp_b200_solver {
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
   int *didxA = nullptr, *didxB = nullptr;
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
+  int poll_interval = -1;  // -1: widening stride (default); 0: never poll (fully asynchronous solve); k > 0: every k iterations
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;
@@ -546,8 +547,10 @@ int cddp_b200_solve(cddp_b200_solver *s) {
   const auto t0 = std::chrono::steady_clock::now();
   const int max_it = s->c.opt.max_iterations;
   int final_status = CDDP_B200_STATUS_MAX_ITERATIONS;
-  // poll the running counter with a widening stride: cheap for short solves, rare for long ones
-  int next_poll = 4;
+  // poll the running counter with a widening stride: cheap for short solves, rare for long ones.  With
+  // poll_interval == 0 the solve is enqueued without any host synchronisation (finished instances are masked on
+  // the device, so running the remaining launches is correct, just not free).
+  int next_poll = s->poll_interval > 0 ? s->poll_interval : 4;
   for (int it = 0; it < max_it; ++it) {
     if (s->c.opt.max_cpu_time > 0.0) {  // cddp_solver_base.cpp:77-90 (wall clock, checked per batched iteration)
       CU(cudaStreamSynchronize(s->stream));
@@ -558,11 +561,11 @@ int cddp_b200_solve(cddp_b200_solver *s) {
       }
     }
     if ((r = one_iteration(s))) return r;
-    if (it + 1 == next_poll && it + 1 < max_it) {
+    if (s->poll_interval != 0 && it + 1 == next_poll && it + 1 < max_it) {
       int running = 0;
       if ((r = read_running(s, &running))) return r;
       if (running == 0) break;
-      next_poll += (next_poll < 16) ? 4 : 8;
+      next_poll += s->poll_interval > 0 ? s->poll_interval : ((next_poll < 16) ? 4 : 8);
     }
   }
   CU(launch_finalize(s->c, s->d, final_status, s->stream));
@@ -589,9 +592,9 @@ static int download(cddp_b200_solver *s, void *dst, const void *src, size_t byte
   return 0;
 }
 
-int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
-                           int *iterations_completed, int *status, double *final_step_length,
-                           double *final_regularization, double *inf_du) {
+static int get_solution_impl(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                             int *iterations_completed, int *status, double *final_step_length, double *final_regularization,
+                             double *inf_du, bool sync) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
   DeviceGuard g(s->device);
   const DeviceState &d = s->d;
@@ -612,7 +615,27 @@ int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K,
   if ((r = download(s, final_step_length, d.alpha, B * sizeof(double)))) return r;
   if ((r = download(s, final_regularization, d.reg, B * sizeof(double)))) return r;
   if ((r = download(s, inf_du, d.inf_du, B * sizeof(double)))) return r;
-  CU(cudaStreamSynchronize(s->stream));
+  if (sync) CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                           int *iterations_completed, int *status, double *final_step_length,
+                           double *final_regularization, double *inf_du) {
+  return get_solution_impl(s, X, U, K, final_objective, iterations_completed, status, final_step_length, final_regularization,
+                           inf_du, true);
+}
+
+int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                                 int *iterations_completed, int *status, double *final_step_length,
+                                 double *final_regularization, double *inf_du) {
+  return get_solution_impl(s, X, U, K, final_objective, iterations_completed, status, final_step_length, final_regularization,
+                           inf_du, false);
+}
+
+int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval) {
+  if (!s || interval < -1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->poll_interval = interval;
   return 0;
 }
 

@@ -213,6 +213,17 @@ CDDP_B200_API int cddp_b200_synchronize(cddp_b200_solver *s);
 CDDP_B200_API int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
                            int *iterations_completed, int *status, double *final_step_length,
                            double *final_regularization, double *inf_du);
+/* Asynchronous serving (no reference counterpart; the reference's stated use is MPC, README.md:11): with
+ * cddp_b200_set_poll_interval(s, 0) cddp_b200_solve only ENQUEUES work on the solver's stream (no host
+ * synchronisation; instances that finish early are masked on the device), and cddp_b200_get_solution_async enqueues
+ * the device-to-host copies without waiting — call cddp_b200_synchronize before reading the host buffers.  Host
+ * buffers must be pinned and stay valid until then.  Two handles on two streams give a double-buffered pipeline in
+ * which call k+1's upload + solve overlaps call k's download.  interval -1 = default widening poll, k > 0 = poll the
+ * running-instance counter every k iterations. */
+CDDP_B200_API int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval);
+CDDP_B200_API int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
+                                 int *iterations_completed, int *status, double *final_step_length,
+                                 double *final_regularization, double *inf_du);
 /* optional History (cddp_core.hpp:77-102) when recorded: [B][max_iterations+1][4] =
  * {objective, step_length_primal, dual_infeasibility, regularization}; lens [B] */
 CDDP_B200_API int cddp_b200_enable_history(cddp_b200_solver *s, int enable);

@@ -302,3 +302,46 @@ def test_full_size_properties(cddp, ob, problems):
     np.testing.assert_array_equal(r2["iterations"], o["iterations"])
     s.close()
     s2.close()
+
+
+def test_async_double_buffered_calls_match_blocking(cddp, problems):
+    """cddp_b200_set_poll_interval(0) + cddp_b200_get_solution_async: two handles on two streams, calls interleaved
+    (the e2e serving pattern of bench.py) must return exactly what the blocking sequence returns."""
+    import torch
+    cfg = problems.make_config("quadrotor", batch=64, horizon=50)
+    opts = dict(cfg["options"], max_iterations=7)
+    ref_s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), 64)
+    ref_s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    ref_s.solve()
+    ref = ref_s.get_solution()
+    ref_s.close()
+    lanes = []
+    for _ in range(2):
+        s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), 64)
+        st = torch.cuda.Stream()
+        s.set_stream(st.cuda_stream)
+        s.set_poll_interval(0)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        hin = {k: pin(cfg[k]) for k in ("x0", "xref", "X0", "U0")}
+        out = {"X": torch.empty((64, 51, 13), dtype=torch.float64).pin_memory(), "U": torch.empty((64, 50, 4), dtype=torch.float64).pin_memory(),
+               "K": torch.empty((64, 50, 4, 13), dtype=torch.float64).pin_memory(), "cost": torch.empty(64, dtype=torch.float64).pin_memory(),
+               "it": torch.empty(64, dtype=torch.int32).pin_memory(), "st": torch.empty(64, dtype=torch.int32).pin_memory()}
+        lanes.append((s, st, hin, out))
+    lib = lanes[0][0].lib
+    for rep in range(3):
+        for s, st, hin, out in lanes:
+            s.synchronize()
+            for v in out.values():
+                v.zero_()
+            cddp._check(lib.cddp_b200_set_instances(s.handle, hin["x0"].data_ptr(), hin["xref"].data_ptr(), None, hin["X0"].data_ptr(), hin["U0"].data_ptr()))
+            cddp._check(lib.cddp_b200_solve(s.handle))
+            cddp._check(lib.cddp_b200_get_solution_async(s.handle, out["X"].data_ptr(), out["U"].data_ptr(), out["K"].data_ptr(), out["cost"].data_ptr(),
+                                                         out["it"].data_ptr(), out["st"].data_ptr(), None, None, None))
+    for s, st, hin, out in lanes:
+        s.synchronize()
+        np.testing.assert_array_equal(out["cost"].numpy(), ref["cost"])
+        np.testing.assert_array_equal(out["X"].numpy(), ref["X"])
+        np.testing.assert_array_equal(out["K"].numpy(), ref["K"])
+        np.testing.assert_array_equal(out["it"].numpy(), ref["iterations"])
+        np.testing.assert_array_equal(out["st"].numpy(), ref["status"])
+        s.close()
