@@ -63,7 +63,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
-constexpr int group_size(int ns) { return ns + 1 <= 4 ? 4 : (ns + 1 <= 8 ? 8 : 16); }
+// Lane-group geometry: a trajectory's n+1 rows (V_xx rows + the V_x^T row) are spread over G lanes with R rows per lane
+// (row = lane_in_group + G*slot).  n+1 <= 4: G=4,R=1; n+1 <= 8: G=8,R=1; else G=8,R=2.  Two rows per lane make every
+// broadcast operand feed two DFMAs and halve the number of warps needed per trajectory, so that a CTA of 7 matrix
+// warps (28 trajectories) + 1 QP warp fills an SM with 256 threads at up to 255 registers each.
+constexpr int group_size(int ns) { return ns + 1 <= 4 ? 4 : 8; }
+constexpr int rows_per_lane(int ns) { return ns + 1 <= 8 ? 1 : 2; }
 
 enum { CTRL_OK = 1, CTRL_RESTART = 2, CTRL_FAIL = 3 };
 
@@ -71,6 +76,7 @@ template <int NS, int NC, class PAT, int W>
 struct SweepCfg {
   using L = RecordLayout<NS, NC, PAT>;
   static constexpr int G = group_size(NS);
+  static constexpr int R = rows_per_lane(NS);
   static constexpr int TPW = 32 / G;  // trajectories per warp
   static constexpr int T = W * TPW;   // trajectories per CTA (one QP-warp lane each)
   static constexpr int RS = L::stride;
@@ -106,7 +112,7 @@ template <int NS, int NC, class PAT, int W, int MINB>
 __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
   using Cfg = SweepCfg<NS, NC, PAT, W>;
   using L = typename Cfg::L;
-  constexpr int G = Cfg::G, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
+  constexpr int G = Cfg::G, R = Cfg::R, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
   extern __shared__ __align__(16) double smem[];
   double *sQ = smem;            // l_xx = 2 Q dt
   double *sR = sQ + NS * NS;    // l_uu = 2 R dt
@@ -118,12 +124,23 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
 
   if (warp < W) {
     // =========================================================== matrix warps
-    const int hw = lane / G, r = lane % G;
+    const int hw = lane / G, r = lane % G;  // hw: which of the warp's TPW trajectories, r: lane within the group
     const int q = warp * TPW + hw;
     const int b = blockIdx.x * T + q;
     double *S = traj0 + q * ST;
     const volatile double *Sv = S;  // for broadcast reads (see phase A1)
-    const int rr = r < NS ? r : NS - 1;  // lanes >= NS duplicate row NS-1 in column-type work (results unused)
+    // rows owned by this lane: row[s] = r + G*s.  row < NS: a row of V_xx; row == NS: V_x^T; row > NS: idle slot
+    // (computes a duplicate of row NS-1 / of V_x, never stored)
+    int row[R], rr[R];
+    bool isrow[R], isvx[R], has[R];
+#pragma unroll
+    for (int sl = 0; sl < R; ++sl) {
+      row[sl] = r + G * sl;
+      rr[sl] = row[sl] < NS ? row[sl] : NS - 1;
+      isrow[sl] = row[sl] < NS;
+      isvx[sl] = row[sl] == NS;
+      has[sl] = row[sl] <= NS;
+    }
     const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
     const int bb = alive ? b : 0;
     uint64_t *bar = reinterpret_cast<uint64_t *>(S + Cfg::oBar);
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     double *gk = d.kff + (size_t)bb * N * NC;
     const double *vterm = d.vterm + (size_t)bb * NS;
 
-    double V[NS];  // lane r < NS: row r of V_xx; lane NS: V_x^T
+    double V[R][NS];  // per slot: a row of V_xx, or V_x^T
     uint32_t par0 = 0u, par1 = 0u;        // mbarrier phase parity of each record buffer
     bool pend0 = false, pend1 = false;    // a bulk copy into the buffer is in flight
     int t = N - 1, buf = 0;
@@ -154,12 +171,12 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       mbar_wait(&bar[x], x ? par1 : par0);
       if (x) { par1 ^= 1u; pend1 = false; } else { par0 ^= 1u; pend0 = false; }
     };
-    double nrm = 0.0;  // lane NS: sum over the sweep of ||V_x||_1 (clddp_solver.cpp:107,:194)
+    double nrm = 0.0;  // slot holding V_x: sum over the sweep of ||V_x||_1 (clddp_solver.cpp:107,:194)
     auto init_sweep = [&]() {  // V_xx = 2 Qf, V_x = 2 Qf (x_N - ref)  (clddp_solver.cpp:89-92)
-      static_for<0, NS>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        V[j] = (r < NS) ? c.Qf2[rr * NS + j] : vterm[j];
-      });
+#pragma unroll
+      for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) V[sl][j] = isrow[sl] ? c.Qf2[rr[sl] * NS + j] : vterm[j];
       t = N - 1;
       buf = 0;
       nrm = 0.0;
@@ -170,11 +187,13 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       init_sweep();
       issue(N - 1, 0);
     }
-    const double qd = sQ[rr * NS + rr];
+    double qd[R];
+#pragma unroll
+    for (int sl = 0; sl < R; ++sl) qd[sl] = sQ[rr[sl] * NS + rr[sl]];
 
     while (true) {
       const bool wrun = __any_sync(0xffffffffu, run);
-      double Qxx[NS], Qxu[NC], Qx = 0.0;
+      double Qxx[R][NS], Qxu[R][NC], Qx[R];
       if (wrun) {
         // ------------------------------------------------------------ phase A1 (critical path): what the QP needs
         double kprev = 0.0;
@@ -188,23 +207,29 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         // tools/microbench/lds_broadcast.cu) — 2x more per byte, and shared-memory issue is what bounds this kernel.
         const volatile double *rc = S + Cfg::oRec + buf * RS;
         {
-          // P_B(row r) = V(row r) * B ; lane NS: (B^T V_x)^T
-          double PBr[NC];
+          // P_B(row) = V(row) * B ; V_x slot: (B^T V_x)^T
+          double PBr[R][NC];
 #pragma unroll
-          for (int a = 0; a < NC; ++a) PBr[a] = 0.0;
+          for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+            for (int a = 0; a < NC; ++a) PBr[sl][a] = 0.0;
           static_for<0, NS>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
             if constexpr (PAT::brow(l)) {
               static_for<0, NC>([&](auto ac) {
                 constexpr int a = decltype(ac)::value;
-                PBr[a] = fma(V[l], rc[L::idxB(l, a)], PBr[a]);
+                const double bv = rc[L::idxB(l, a)];
+#pragma unroll
+                for (int sl = 0; sl < R; ++sl) PBr[sl][a] = fma(V[sl][l], bv, PBr[sl][a]);
               });
             }
           });
-          if (r <= NS) {
 #pragma unroll
-            for (int a = 0; a < NC; ++a) S[Cfg::oPB + r * NC + a] = PBr[a];
-          }
+          for (int sl = 0; sl < R; ++sl)
+            if (has[sl]) {
+#pragma unroll
+              for (int a = 0; a < NC; ++a) S[Cfg::oPB + row[sl] * NC + a] = PBr[sl][a];
+            }
         }
         __syncwarp();
         // Q_uu = l_uu + B^T P_B, one entry per lane; Q_u = l_u + B^T V_x; hand-off to the QP lane   (:125,:128)
@@ -228,57 +253,78 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         // ------------------------------------------------------------ phase A2 (in the shadow of the QP warp)
         const volatile double *rc = S + Cfg::oRec + buf * RS;
         {
-          // P_A(row r) = V(row r) * A ; lane NS: (A^T V_x)^T                                  (:124,:126-127)
-          double PAr[NS];
+          // P_A(row) = V(row) * A ; V_x slot: (A^T V_x)^T                                  (:124,:126-127)
+          double PAr[R][NS];
 #pragma unroll
-          for (int j = 0; j < NS; ++j) PAr[j] = 0.0;
+          for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) PAr[sl][j] = 0.0;
           static_for<0, NS>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
             static_for<0, NS>([&](auto jc) {
               constexpr int j = decltype(jc)::value;
-              if constexpr (PAT::a(l, j)) PAr[j] = fma(V[l], rc[L::idxA(l, j)], PAr[j]);
+              if constexpr (PAT::a(l, j)) {
+                const double av = rc[L::idxA(l, j)];
+#pragma unroll
+                for (int sl = 0; sl < R; ++sl) PAr[sl][j] = fma(V[sl][l], av, PAr[sl][j]);
+              }
             });
           });
-          if (r <= NS) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = PAr[j];
+          for (int sl = 0; sl < R; ++sl) {
+            if (has[sl]) {
+#pragma unroll
+              for (int j = 0; j < NS; ++j) S[Cfg::oPA + row[sl] * NS + j] = PAr[sl][j];
+            }
+            double l1 = 0.0;  // ||V_x||_1 of the value function entering this step
+#pragma unroll
+            for (int j = 0; j < NS; ++j) l1 += fabs(V[sl][j]);
+            nrm += isvx[sl] ? l1 : 0.0;
           }
-          double l1 = 0.0;  // ||V_x||_1 of the value function entering this step (lane NS holds V_x)
-#pragma unroll
-          for (int j = 0; j < NS; ++j) l1 += fabs(V[j]);
-          nrm += l1;
         }
         __syncwarp();
-        // Q_xx(row r) = l_xx + (P_A^T A)(row r);  Q_xu(row r) = (P_A^T B)(row r)   (V_xx symmetric)
-        double col[NS];
+        // Q_xx(row) = l_xx + (P_A^T A)(row);  Q_xu(row) = (P_A^T B)(row)   (V_xx symmetric)
+        double col[R][NS];
 #pragma unroll
-        for (int l = 0; l < NS; ++l) col[l] = S[Cfg::oPA + l * NS + rr];
-        if (c.q_diag) {
+        for (int sl = 0; sl < R; ++sl) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) Qxx[j] = (j == rr) ? qd : 0.0;
-        } else {
+          for (int l = 0; l < NS; ++l) col[sl][l] = S[Cfg::oPA + l * NS + rr[sl]];
+          if (c.q_diag) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) Qxx[j] = sQ[rr * NS + j];
+            for (int j = 0; j < NS; ++j) Qxx[sl][j] = (j == rr[sl]) ? qd[sl] : 0.0;
+          } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) Qxx[sl][j] = sQ[rr[sl] * NS + j];
+          }
+#pragma unroll
+          for (int a = 0; a < NC; ++a) Qxu[sl][a] = 0.0;
         }
-#pragma unroll
-        for (int a = 0; a < NC; ++a) Qxu[a] = 0.0;
         static_for<0, NS>([&](auto lc) {
           constexpr int l = decltype(lc)::value;
           static_for<0, NS>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            if constexpr (PAT::a(l, j)) Qxx[j] = fma(col[l], rc[L::idxA(l, j)], Qxx[j]);
+            if constexpr (PAT::a(l, j)) {
+              const double av = rc[L::idxA(l, j)];
+#pragma unroll
+              for (int sl = 0; sl < R; ++sl) Qxx[sl][j] = fma(col[sl][l], av, Qxx[sl][j]);
+            }
           });
           if constexpr (PAT::brow(l)) {
             static_for<0, NC>([&](auto ac) {
               constexpr int a = decltype(ac)::value;
-              Qxu[a] = fma(col[l], rc[L::idxB(l, a)], Qxu[a]);
+              const double bv = rc[L::idxB(l, a)];
+#pragma unroll
+              for (int sl = 0; sl < R; ++sl) Qxu[sl][a] = fma(col[sl][l], bv, Qxu[sl][a]);
             });
           }
         });
-        Qx = rc[L::offLx + rr] + S[Cfg::oPA + NS * NS + rr];  // Q_x = l_x + A^T V_x
-        if (r < NS) {
 #pragma unroll
-          for (int a = 0; a < NC; ++a) S[Cfg::oQux + a * NS + r] = Qxu[a];
+        for (int sl = 0; sl < R; ++sl) {
+          Qx[sl] = rc[L::offLx + rr[sl]] + S[Cfg::oPA + NS * NS + rr[sl]];  // Q_x = l_x + A^T V_x
+          if (isrow[sl]) {
+#pragma unroll
+            for (int a = 0; a < NC; ++a) S[Cfg::oQux + a * NS + row[sl]] = Qxu[sl][a];
+          }
         }
       }
       __syncthreads();  // barrier 2: k, Ht, w, state visible to the matrix warps (and Q_ux to the other lanes)
@@ -287,77 +333,105 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         const int st = run ? *reinterpret_cast<volatile int *>(S + Cfg::oCtrl) : 0;
         const bool okh = run && st == CTRL_OK;
         // With K = -Ht Q_ux (Ht symmetric, zero in clamped rows/columns):
-        //   V_xx' = Q_xx + K^T Q_uu K + Q_ux^T K + K^T Q_ux = Q_xx + Q_ux^T T,   T(:, r) = 2 K(:, r) - Ht Q_uu K(:, r)
+        //   V_xx' = Q_xx + K^T Q_uu K + Q_ux^T K + K^T Q_ux = Q_xx + Q_ux^T T,   T(:, i) = 2 K(:, i) - Ht Q_uu K(:, i)
         //   V_x'  = Q_x + K^T (Q_uu k + Q_u) + Q_ux^T k      = Q_x + Q_ux^T (k - Ht w),  w = Q_uu k + Q_u      (:188-191)
-        // Each lane forms its own column of K and T from three m x m mat-vecs (no shared-memory round trip on the
+        // Each slot forms its own column of K and T from three m x m mat-vecs (no shared-memory round trip on the
         // critical path); the only broadcast stream left is Q_ux (m x n), staged during the QP's shadow.
-        double Kc[NC], z[NC], QK[NC], T[NC];
+        double Kc[R][NC], z[NC], T[R][NC];
         {
-          double Ht[NC * NC];
+          double Ht[NC * NC], Qu_[NC * NC];
 #pragma unroll
-          for (int e = 0; e < NC * NC; ++e) Ht[e] = Sv[Cfg::oHinv + e];
+          for (int e = 0; e < NC * NC; ++e) {
+            Ht[e] = Sv[Cfg::oHinv + e];
+            Qu_[e] = Sv[Cfg::oQuu + e];
+          }
 #pragma unroll
-          for (int a = 0; a < NC; ++a) {  // K(:, r) = -Ht Q_ux(:, r)   (:142-178) ;  z = k - Ht w
-            double sK = 0.0, sz = 0.0;
+          for (int a = 0; a < NC; ++a) {  // z = k - Ht w
+            double sz = 0.0;
 #pragma unroll
-            for (int bcol = 0; bcol < NC; ++bcol) {
-              sK = fma(Ht[a * NC + bcol], Qxu[bcol], sK);
-              sz = fma(Ht[a * NC + bcol], Sv[Cfg::oW + bcol], sz);
-            }
-            Kc[a] = -sK;
+            for (int bcol = 0; bcol < NC; ++bcol) sz = fma(Ht[a * NC + bcol], Sv[Cfg::oW + bcol], sz);
             z[a] = Sv[Cfg::oKk + a] - sz;
           }
 #pragma unroll
-          for (int a = 0; a < NC; ++a) {  // Q_uu K(:, r)   (unregularised Q_uu)
-            double sq = 0.0;
+          for (int sl = 0; sl < R; ++sl) {
+            double QK[NC];
 #pragma unroll
-            for (int bcol = 0; bcol < NC; ++bcol) sq = fma(Sv[Cfg::oQuu + a * NC + bcol], Kc[bcol], sq);
-            QK[a] = sq;
-          }
+            for (int a = 0; a < NC; ++a) {  // K(:, i) = -Ht Q_ux(:, i)   (:142-178)
+              double sK = 0.0;
 #pragma unroll
-          for (int a = 0; a < NC; ++a) {
-            double sT = 2.0 * Kc[a];
+              for (int bcol = 0; bcol < NC; ++bcol) sK = fma(Ht[a * NC + bcol], Qxu[sl][bcol], sK);
+              Kc[sl][a] = -sK;
+            }
 #pragma unroll
-            for (int bcol = 0; bcol < NC; ++bcol) sT = fma(-Ht[a * NC + bcol], QK[bcol], sT);
-            T[a] = sT;
+            for (int a = 0; a < NC; ++a) {  // Q_uu K(:, i)   (unregularised Q_uu)
+              double sq = 0.0;
+#pragma unroll
+              for (int bcol = 0; bcol < NC; ++bcol) sq = fma(Qu_[a * NC + bcol], Kc[sl][bcol], sq);
+              QK[a] = sq;
+            }
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+              double sT = 2.0 * Kc[sl][a];
+#pragma unroll
+              for (int bcol = 0; bcol < NC; ++bcol) sT = fma(-Ht[a * NC + bcol], QK[bcol], sT);
+              T[sl][a] = sT;
+            }
           }
         }
-        if (okh && r < NS) {
 #pragma unroll
-          for (int a = 0; a < NC; ++a) gK[((size_t)t * NC + a) * NS + r] = Kc[a];  // K_u_[t] (:182)
-        }
+        for (int sl = 0; sl < R; ++sl)
+          if (okh && isrow[sl]) {
+#pragma unroll
+            for (int a = 0; a < NC; ++a) gK[((size_t)t * NC + a) * NS + row[sl]] = Kc[sl][a];  // K_u_[t] (:182)
+          }
         if (okh && r < NC) gk[(size_t)t * NC + r] = S[Cfg::oKk + r];  // k_u_[t] (:181)
-        double Vn[NS], vxn = Qx;
+        double Vn[R][NS], vxn[R];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) Vn[j] = Qxx[j];
+        for (int sl = 0; sl < R; ++sl) {
+          vxn[sl] = Qx[sl];
+#pragma unroll
+          for (int j = 0; j < NS; ++j) Vn[sl][j] = Qxx[sl][j];
+#pragma unroll
+          for (int a = 0; a < NC; ++a) vxn[sl] = fma(Qxu[sl][a], z[a], vxn[sl]);
+        }
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) Vn[j] = fma(T[a], Sv[Cfg::oQux + a * NS + j], Vn[j]);
-          vxn = fma(Qxu[a], z[a], vxn);
-        }
-        if (okh && r < NS) {
+          for (int j = 0; j < NS; ++j) {
+            const double qv = Sv[Cfg::oQux + a * NS + j];
 #pragma unroll
-          for (int j = 0; j < NS; ++j) S[Cfg::oPA + r * NS + j] = Vn[j];
-          S[Cfg::oVx + r] = vxn;
+            for (int sl = 0; sl < R; ++sl) Vn[sl][j] = fma(T[sl][a], qv, Vn[sl][j]);
+          }
         }
+#pragma unroll
+        for (int sl = 0; sl < R; ++sl)
+          if (okh && isrow[sl]) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) S[Cfg::oPA + row[sl] * NS + j] = Vn[sl][j];
+            S[Cfg::oVx + row[sl]] = vxn[sl];
+          }
         __syncwarp();
         if (okh) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); lane NS takes the new V_x^T
-            V[j] = (r < NS) ? 0.5 * (Vn[j] + S[Cfg::oPA + j * NS + rr]) : Sv[Cfg::oVx + j];
+          for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+            for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); the V_x slot takes the new V_x^T
+              V[sl][j] = isrow[sl] ? 0.5 * (Vn[sl][j] + S[Cfg::oPA + j * NS + rr[sl]]) : Sv[Cfg::oVx + j];
           --t;
           buf ^= 1;
           if (t < 0) {  // sweep finished: white-box value function at t = 0, and the V_x(0) term of the norm
             run = false;
-            double l1 = 0.0;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-              l1 += fabs(V[j]);
-              if (r < NS) d.Vxx0[((size_t)b * NS + r) * NS + j] = V[j];
-              if (r == NS) d.Vx0[(size_t)b * NS + j] = V[j];
+            for (int sl = 0; sl < R; ++sl) {
+              double l1 = 0.0;
+#pragma unroll
+              for (int j = 0; j < NS; ++j) {
+                l1 += fabs(V[sl][j]);
+                if (isrow[sl]) d.Vxx0[((size_t)b * NS + row[sl]) * NS + j] = V[sl][j];
+                if (isvx[sl]) d.Vx0[(size_t)b * NS + j] = V[sl][j];
+              }
+              if (isvx[sl]) S[Cfg::oNrm] = nrm + l1;
             }
-            if (r == NS) S[Cfg::oNrm] = nrm + l1;
           }
         } else if (run) {
           if (pend0) wait_buf(0);  // drain the speculative prefetch
@@ -566,7 +640,7 @@ template <int NS, int NC, class PAT, int W, int MINB>
 cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
   using Cfg = SweepCfg<NS, NC, PAT, W>;
   static_assert(Cfg::T <= 32, "one QP-warp lane per trajectory");
-  static_assert(NS + 1 <= Cfg::G, "V_x rides as an extra row");
+  static_assert(NS + 1 <= Cfg::G * Cfg::R, "V_x rides as an extra row");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -585,7 +659,7 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
   *handled = true;
   const int n = d.n, m = d.m;
   if (d.layout == RECORDS_STRUCTURED) {
-    if (c.model == CDDP_B200_MODEL_QUADROTOR) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 2>(c, d, mode, st);
+    if (c.model == CDDP_B200_MODEL_QUADROTOR) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
     if (c.model == CDDP_B200_MODEL_UNICYCLE) return launch_sweep<3, 2, ModelPattern<CDDP_B200_MODEL_UNICYCLE>, 4, 4>(c, d, mode, st);
   } else {
@@ -594,8 +668,8 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
     if (n == 4 && m == 1) return launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 4 && m == 2) return launch_sweep<4, 2, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 6 && m == 3) return launch_sweep<6, 3, DensePattern, 7, 2>(c, d, mode, st);
-    if (n == 13 && m == 4) return launch_sweep<13, 4, DensePattern, 7, 2>(c, d, mode, st);
-    if (n == 14 && m == 7) return launch_sweep<14, 7, DensePattern, 7, 1>(c, d, mode, st);
+    if (n == 13 && m == 4) return launch_sweep<13, 4, DensePattern, 7, 1>(c, d, mode, st);
+    if (n == 14 && m == 7) return launch_sweep<14, 7, DensePattern, 5, 1>(c, d, mode, st);
   }
   *handled = false;
   return cudaSuccess;
