@@ -345,3 +345,56 @@ def test_async_double_buffered_calls_match_blocking(cddp, problems):
         np.testing.assert_array_equal(out["it"].numpy(), ref["iterations"])
         np.testing.assert_array_equal(out["st"].numpy(), ref["status"])
         s.close()
+
+
+@pytest.mark.parametrize("integrator", ["euler", "heun", "rk3", "rk4"])
+def test_integrators_and_dense_costs(cddp, ob, problems, integrator):
+    """Every integrator of dynamical_system.cpp:28-83 in the rollout, with NON-diagonal Q, R, Qf (the dense cost path
+    of the line-search kernel and the non-diagonal l_xx path of the sweep)."""
+    rng = np.random.default_rng(11)
+    cfg = problems.make_config("quadrotor", batch=4, horizon=30)
+    n, m = 13, 4
+    Mq, Mr, Mf = rng.standard_normal((n, n)), rng.standard_normal((m, m)), rng.standard_normal((n, n))
+    spec = dict(cfg["spec"], integrator=integrator, Q=0.01 * (Mq @ Mq.T), R=0.05 * (Mr @ Mr.T) + 0.05 * np.eye(m),
+                Qf=cfg["spec"]["Qf"] + 0.5 * (Mf @ Mf.T))
+    opts = dict(cfg["options"], max_iterations=6)
+    s = cddp.BatchedCLDDP(spec, cddp.default_options(**opts), 4)
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    s.solve()
+    r = s.get_solution()
+    o = ob.solve_batch(ob.OracleProblem(spec), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    np.testing.assert_array_equal(r["iterations"], o["iterations"])
+    np.testing.assert_array_equal(r["status"], o["status"])
+    assert np.max(np.abs(r["cost"] - o["cost"]) / np.abs(o["cost"])) < COST_TOL
+    assert rel_err(r["X"], o["X"]) < 1e-6 and rel_err(r["K"], o["K"]) < 1e-5
+    s.close()
+
+
+def test_more_than_16_alphas_and_layout_equivalence(cddp, ob, problems):
+    """> 16 line-search candidates switch the rollout kernel to one trajectory per warp (32 lanes); the dense and the
+    structured record layouts must give the same solve (to roundoff: different summation order only)."""
+    cfg = problems.make_config("quadrotor", batch=9, horizon=40)
+    opts = dict(cfg["options"], max_iterations=8, ls_max_iterations=24, ls_step_reduction_factor=0.7)
+    assert len(cddp.build_alphas(cddp.default_options(**opts))) == 24
+    res = {}
+    for layout in ("structured", "dense"):
+        s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), 9)
+        s.set_record_layout(layout)
+        assert s.get_record_layout()[0] == layout
+        s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        s.solve()
+        res[layout] = s.get_solution()
+        s.close()
+    o = ob.solve_batch(ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    for layout in res:
+        np.testing.assert_array_equal(res[layout]["iterations"], o["iterations"])
+        np.testing.assert_array_equal(res[layout]["alpha"], o["alpha"])
+        assert np.max(np.abs(res[layout]["cost"] - o["cost"]) / np.abs(o["cost"])) < COST_TOL
+    assert rel_err(res["dense"]["X"], res["structured"]["X"]) < 1e-8
+    # set_options after create: 11 -> 24 alphas re-sizes the line-search scratch
+    s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**dict(opts, ls_max_iterations=11, ls_step_reduction_factor=0.5)), 9)
+    s.set_options(cddp.default_options(**opts))
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    s.solve()
+    np.testing.assert_array_equal(s.get_solution()["cost"], res["structured"]["cost"])
+    s.close()
