@@ -108,6 +108,7 @@ ABI_SYMBOLS = [
     "cddp_b200_reset_timing", "cddp_b200_get_timing", "cddp_b200_enable_timing",
     "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host", "cddp_b200_set_record_layout",
     "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_get_solution_async",
+    "cddp_b200_mpc_advance", "cddp_b200_get_first_controls_async",
 ]
 
 
@@ -157,6 +158,8 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_get_solution.argtypes = [vp] + [vp] * 9
     lib.cddp_b200_get_solution_async.argtypes = [vp] + [vp] * 9
     lib.cddp_b200_set_poll_interval.argtypes = [vp, C.c_int]
+    lib.cddp_b200_mpc_advance.argtypes = [vp, C.c_int, vp, vp]
+    lib.cddp_b200_get_first_controls_async.argtypes = [vp, vp, vp, vp]
     lib.cddp_b200_enable_history.argtypes = [vp, C.c_int]
     lib.cddp_b200_get_history.argtypes = [vp, vp, vp]
     lib.cddp_b200_get_feedforward.argtypes = [vp, vp]
@@ -303,6 +306,19 @@ class BatchedCLDDP:
         lay, nb = C.c_int(0), C.c_int(0)
         _check(self.lib.cddp_b200_get_record_layout(self.handle, C.byref(lay), C.byref(nb)))
         return ("dense", "structured")[lay.value], nb.value
+
+    def mpc_advance(self, steps: int, x0_new=None, xref_new=None):
+        a = _f64(x0_new, (self.B, self.n)) if x0_new is not None else None
+        b = _f64(xref_new, (self.B, self.n)) if xref_new is not None else None
+        self._keep_mpc = (a, b)
+        _check(self.lib.cddp_b200_mpc_advance(self.handle, int(steps), _ptr(a), _ptr(b)))
+        _check(self.lib.cddp_b200_synchronize(self.handle))
+
+    def get_first_controls(self):
+        u0, cost, st = np.empty((self.B, self.m)), np.empty(self.B), np.empty(self.B, dtype=np.int32)
+        _check(self.lib.cddp_b200_get_first_controls_async(self.handle, _ptr(u0), _ptr(cost), _ptr(st)))
+        _check(self.lib.cddp_b200_synchronize(self.handle))
+        return u0, cost, st
 
     def set_poll_interval(self, interval: int):
         _check(self.lib.cddp_b200_set_poll_interval(self.handle, int(interval)))

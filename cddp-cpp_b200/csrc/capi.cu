@@ -633,6 +633,35 @@ int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, doub
                            inf_du, false);
 }
 
+int cddp_b200_mpc_advance(cddp_b200_solver *s, int steps, const double *x0_new, const double *xref_new) {
+  if (!s || steps < 0 || steps > s->d.N) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->have_instances) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  if (steps > 0) {
+    CU(launch_shift(d, steps, s->stream));
+    s->timing.other_launches++;
+  }
+  if (x0_new) CU(cudaMemcpyAsync(d.x0, x0_new, (size_t)d.B * d.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (xref_new) CU(cudaMemcpyAsync(d.xref, xref_new, (size_t)d.B * d.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  s->initialized = false;
+  return 0;
+}
+
+int cddp_b200_get_first_controls_async(cddp_b200_solver *s, double *u0, double *final_objective, int *status) {
+  if (!s || !u0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const DeviceState &d = s->d;
+  int r;
+  if ((r = s->ensure_scratch((size_t)d.B * d.m * sizeof(double)))) return r;
+  CU(launch_first_controls(d, s->scratch, s->stream));
+  s->timing.other_launches++;
+  if ((r = download(s, u0, s->scratch, (size_t)d.B * d.m * sizeof(double)))) return r;
+  if ((r = download(s, final_objective, d.cost, (size_t)d.B * sizeof(double)))) return r;
+  if ((r = download(s, status, d.status, (size_t)d.B * sizeof(int)))) return r;
+  return 0;
+}
+
 int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval) {
   if (!s || interval < -1) return CDDP_B200_ERR_INVALID_ARGUMENT;
   s->poll_interval = interval;

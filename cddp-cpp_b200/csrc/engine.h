@@ -88,6 +88,8 @@ cudaError_t launch_backward(const Constants &c, const DeviceState &d, int mode, 
 cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
 cudaError_t launch_finalize(const Constants &c, const DeviceState &d, int final_status, cudaStream_t st);
 cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st);
+cudaError_t launch_shift(const DeviceState &d, int k, cudaStream_t st);
+cudaError_t launch_first_controls(const DeviceState &d, double *u0, cudaStream_t st);
 cudaError_t launch_unpack_linearization(const Constants &c, const DeviceState &d, double *A, double *Bm,
                                         cudaStream_t st);
 cudaError_t launch_pack_linearization(const Constants &c, const DeviceState &d, const double *A, const double *Bm,

@@ -274,7 +274,49 @@ __global__ void gather_current_kernel(DeviceState d, double *X, double *U, int w
     for (size_t i = threadIdx.x; i < nu; i += blockDim.x) U[b * nu + i] = d.U[buf][b * nu + i];
 }
 
+// Receding-horizon shift of the nominal trajectory (MPC warm start): X[t] <- X[t+k], U[t] <- U[t+k]; the tail repeats the
+// last control and the last state.  Written into the candidate buffer, then the buffers are swapped.
+__global__ void shift_kernel(DeviceState d, int k) {
+  const int b = blockIdx.x;
+  const int n = d.n, m = d.m, N = d.N;
+  const int cur = d.cur[b];
+  const double *Xs = d.X[cur] + (size_t)b * (N + 1) * n;
+  const double *Us = d.U[cur] + (size_t)b * N * m;
+  double *Xd = d.X[cur ^ 1] + (size_t)b * (N + 1) * n;
+  double *Ud = d.U[cur ^ 1] + (size_t)b * N * m;
+  for (int i = threadIdx.x; i < (N + 1) * n; i += blockDim.x) {
+    const int t = i / n, j = i - t * n;
+    Xd[i] = Xs[(size_t)min(t + k, N) * n + j];
+  }
+  for (int i = threadIdx.x; i < N * m; i += blockDim.x) {
+    const int t = i / m, j = i - t * m;
+    Ud[i] = Us[(size_t)min(t + k, N - 1) * m + j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    d.cur[b] = cur ^ 1;
+    d.lin_valid[b] = 0;
+  }
+}
+
+__global__ void first_controls_kernel(DeviceState d, double *u0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.B * d.m) return;
+  const int b = i / d.m, j = i - b * d.m;
+  u0[i] = d.U[d.cur[b]][(size_t)b * d.N * d.m + j];
+}
+
 }  // namespace
+
+cudaError_t launch_shift(const DeviceState &d, int k, cudaStream_t st) {
+  shift_kernel<<<d.B, 128, 0, st>>>(d, k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_first_controls(const DeviceState &d, double *u0, cudaStream_t st) {
+  first_controls_kernel<<<(d.B * d.m + 127) / 128, 128, 0, st>>>(d, u0);
+  return cudaGetLastError();
+}
 
 template <int MODEL, class PAT>
 cudaError_t launch_linearize_model(const Constants &c, const DeviceState &d, bool force, cudaStream_t stream) {

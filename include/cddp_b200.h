@@ -224,6 +224,16 @@ CDDP_B200_API int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval)
 CDDP_B200_API int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
                                  int *iterations_completed, int *status, double *final_step_length,
                                  double *final_regularization, double *inf_du);
+/* Receding-horizon (MPC) loop on a persistent handle — the reference's stated use case (README.md:11), where it
+ * re-creates the solver and re-sends everything on every CDDP::solve (cddp_core.cpp:241) with options.warm_start
+ * keeping X_/U_ (cddp_core.cpp:287-292).  cddp_b200_mpc_advance shifts every instance's nominal trajectory left by
+ * `steps` (X[t] <- X[t+steps], U[t] <- U[t+steps], tail = last state / last control) ON THE DEVICE and uploads only
+ * the new measured initial states x0_new [B][n] (and optionally new references); the next cddp_b200_solve then starts
+ * from the shifted trajectory with X[0] = x0_new, zero gains and the initial regularisation, exactly like a
+ * warm-started CDDP::solve.  cddp_b200_get_first_controls_async returns U[0] [B][m] (+ cost, status), the only
+ * thing an MPC loop needs back; it does not synchronise. */
+CDDP_B200_API int cddp_b200_mpc_advance(cddp_b200_solver *s, int steps, const double *x0_new, const double *xref_new);
+CDDP_B200_API int cddp_b200_get_first_controls_async(cddp_b200_solver *s, double *u0, double *final_objective, int *status);
 /* optional History (cddp_core.hpp:77-102) when recorded: [B][max_iterations+1][4] =
  * {objective, step_length_primal, dual_infeasibility, regularization}; lens [B] */
 CDDP_B200_API int cddp_b200_enable_history(cddp_b200_solver *s, int enable);

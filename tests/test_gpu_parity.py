@@ -398,3 +398,28 @@ def test_more_than_16_alphas_and_layout_equivalence(cddp, ob, problems):
     s.solve()
     np.testing.assert_array_equal(s.get_solution()["cost"], res["structured"]["cost"])
     s.close()
+
+
+def test_mpc_receding_horizon_loop(cddp, ob, problems):
+    """Persistent-handle MPC loop: solve, apply u0, shift the trajectory on the device, upload only the new x0, solve
+    again.  Each cycle must equal the oracle solving the same shifted, warm-started problem from scratch."""
+    B, N = 6, 40
+    cfg = problems.make_config("quadrotor", batch=B, horizon=N)
+    opts = dict(cfg["options"], max_iterations=5)
+    s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), B)
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+    x0, X, U = cfg["x0"].copy(), cfg["X0"].copy(), cfg["U0"].copy()
+    for cycle in range(3):
+        s.solve()
+        u0, cost, st = s.get_first_controls()
+        o = ob.solve_batch(P, oo, x0, cfg["xref"], X, U)
+        assert np.max(np.abs(cost - o["cost"]) / np.abs(o["cost"])) < COST_TOL, cycle
+        assert rel_err(u0, o["U"][:, 0]) < 1e-6
+        np.testing.assert_array_equal(st, o["status"])
+        # plant step with the applied control (+ a small disturbance), then shift by one step
+        x0 = np.stack([ob.discrete_dynamics(P, o["X"][b, 0], o["U"][b, 0]) for b in range(B)]) + 1e-3 * (cycle + 1)
+        X = np.concatenate([o["X"][:, 1:], o["X"][:, -1:]], axis=1)
+        U = np.concatenate([o["U"][:, 1:], o["U"][:, -1:]], axis=1)
+        s.mpc_advance(1, x0)
+    s.close()
