@@ -172,6 +172,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       if (x) { par1 ^= 1u; pend1 = false; } else { par0 ^= 1u; pend0 = false; }
     };
     double nrm = 0.0;  // slot holding V_x: sum over the sweep of ||V_x||_1 (clddp_solver.cpp:107,:194)
+    double kprev = 0.0;  // lanes r < NC: BoxQP warm start of the step about to be processed
     auto init_sweep = [&]() {  // V_xx = 2 Qf, V_x = 2 Qf (x_N - ref)  (clddp_solver.cpp:89-92)
 #pragma unroll
       for (int sl = 0; sl < R; ++sl)
@@ -180,12 +181,18 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       t = N - 1;
       buf = 0;
       nrm = 0.0;
+      kprev = (r < NC) ? gk[(size_t)(N - 1) * NC + r] : 0.0;
     };
 
     __syncthreads();  // mbarriers initialised, sQ/sR loaded
+    auto start_staging = [&]() {  // records N-1 (waited here: phase A1 reads it at once) and N-2 (one step ahead)
+      issue(N - 1, 0);
+      if (N > 1) issue(N - 2, 1);
+      wait_buf(0);
+    };
     if (run) {
       init_sweep();
-      issue(N - 1, 0);
+      start_staging();
     }
     double qd[R];
 #pragma unroll
@@ -196,12 +203,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       double Qxx[R][NS], Qxu[R][NC], Qx[R];
       if (wrun) {
         // ------------------------------------------------------------ phase A1 (critical path): what the QP needs
-        double kprev = 0.0;
-        if (run && r < NC) kprev = gk[(size_t)t * NC + r];  // warm start k_u_[t] (clddp_solver.cpp:149)
-        if (run) {
-          wait_buf(buf);
-          if (t > 0) issue(t - 1, buf ^ 1);  // next record, one step ahead
-        }
+        // (the record of this step was waited for in the previous step's shadow phase)
         // BROADCAST operand reads go through a volatile pointer on purpose: nvcc would merge neighbouring doubles into
         // LDS.128, and a broadcast LDS.128 costs 2 shared-memory cycles per warp against <=0.5 for LDS.64 (measured,
         // tools/microbench/lds_broadcast.cu) — 2x more per byte, and shared-memory issue is what bounds this kernel.
@@ -233,14 +235,18 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         }
         __syncwarp();
         // Q_uu = l_uu + B^T P_B, one entry per lane; Q_u = l_u + B^T V_x; hand-off to the QP lane   (:125,:128)
-        for (int e = r; e < NC * NC; e += G) {
-          const int a = e / NC, bcol = e - a * NC;
-          double acc = sR[e];
-          static_for<0, NS>([&](auto lc) {
-            constexpr int l = decltype(lc)::value;
-            if constexpr (PAT::brow(l)) acc = fma(rc[L::idxB(l, 0) + a], Sv[Cfg::oPB + l * NC + bcol], acc);
-          });
-          if (run) S[Cfg::oQuu + e] = acc;
+#pragma unroll
+        for (int ke = 0; ke < (NC * NC + G - 1) / G; ++ke) {
+          const int e = r + ke * G;
+          if (e < NC * NC) {
+            const int a = e / NC, bcol = e - a * NC;
+            double acc = sR[e];
+            static_for<0, NS>([&](auto lc) {
+              constexpr int l = decltype(lc)::value;
+              if constexpr (PAT::brow(l)) acc = fma(rc[L::idxB(l, 0) + a], Sv[Cfg::oPB + l * NC + bcol], acc);
+            });
+            if (run) S[Cfg::oQuu + e] = acc;
+          }
         }
         if (run && r < NC) {
           S[Cfg::oQu + r] = rc[L::offLu + r] + S[Cfg::oPB + NS * NC + r];
@@ -251,6 +257,12 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       if (!__syncthreads_or(run ? 1 : 0)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
       if (wrun) {
         // ------------------------------------------------------------ phase A2 (in the shadow of the QP warp)
+        // BoxQP warm start of the NEXT step, k_u_[t-1] (clddp_solver.cpp:149): an HBM-latency load, issued here so
+        // that it is off the critical path (phase A1 used to stall on it)
+        if (run && r < NC && t > 0) kprev = gk[(size_t)(t - 1) * NC + r];
+        // TMA staging, also in the shadow: record t-1 (other buffer) was issued one step ago -> wait for it now.
+        // Record t-2 is issued into THIS step's buffer once phase A2 has finished reading it (end of this block).
+        if (run && t > 0) wait_buf(buf ^ 1);
         const volatile double *rc = S + Cfg::oRec + buf * RS;
         {
           // P_A(row) = V(row) * A ; V_x slot: (A^T V_x)^T                                  (:124,:126-127)
@@ -326,6 +338,8 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
             for (int a = 0; a < NC; ++a) S[Cfg::oQux + a * NS + row[sl]] = Qxu[sl][a];
           }
         }
+        __syncwarp();  // every lane of the group is done reading this step's record
+        if (run && t > 1) issue(t - 2, buf);
       }
       __syncthreads();  // barrier 2: k, Ht, w, state visible to the matrix warps (and Q_ux to the other lanes)
       if (wrun) {
@@ -378,13 +392,6 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
             }
           }
         }
-#pragma unroll
-        for (int sl = 0; sl < R; ++sl)
-          if (okh && isrow[sl]) {
-#pragma unroll
-            for (int a = 0; a < NC; ++a) gK[((size_t)t * NC + a) * NS + row[sl]] = Kc[sl][a];  // K_u_[t] (:182)
-          }
-        if (okh && r < NC) gk[(size_t)t * NC + r] = S[Cfg::oKk + r];  // k_u_[t] (:181)
         double Vn[R][NS], vxn[R];
 #pragma unroll
         for (int sl = 0; sl < R; ++sl) {
@@ -417,6 +424,15 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
 #pragma unroll
             for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); the V_x slot takes the new V_x^T
               V[sl][j] = isrow[sl] ? 0.5 * (Vn[sl][j] + S[Cfg::oPA + j * NS + rr[sl]]) : Sv[Cfg::oVx + j];
+          // gains to HBM last: a store keeps its address/data registers busy until the LSU has read them, which
+          // stalled the value update when the stores sat in front of it
+#pragma unroll
+          for (int sl = 0; sl < R; ++sl)
+            if (isrow[sl]) {
+#pragma unroll
+              for (int a = 0; a < NC; ++a) gK[((size_t)t * NC + a) * NS + row[sl]] = Kc[sl][a];  // K_u_[t] (:182)
+            }
+          if (r < NC) gk[(size_t)t * NC + r] = S[Cfg::oKk + r];  // k_u_[t] (:181)
           --t;
           buf ^= 1;
           if (t < 0) {  // sweep finished: white-box value function at t = 0, and the V_x(0) term of the norm
@@ -438,7 +454,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
           if (pend1) wait_buf(1);
           if (st == CTRL_RESTART) {     // backward failure: sweep again at the increased regularisation
             init_sweep();
-            issue(N - 1, 0);
+            start_staging();
           } else {
             run = false;
           }
