@@ -20,7 +20,11 @@ namespace cddp_b200 {
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
+// Two warps per CTA and at most 146 registers: 7 CTAs = 14 warps = 28 trajectories per SM, so that the headline batch
+// (4096 trajectories = 27.7 per SM) is ONE wave.  With 4-warp CTAs at 168 registers only 12 warps fitted and the launch
+// ran 1.15 waves (ncu launch__waves_per_multiprocessor), i.e. a second, nearly empty pass of the whole rollout.
+constexpr int kWarpsPerCta = 2;
+constexpr int kMinCtasPerSm = 7;
 
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
@@ -114,7 +118,7 @@ __device__ __forceinline__ double quad_form(const double *M, const double *e) {
 //           the saved states, and write the candidate trajectory (1/LG of a rollout in latency instead of
 //           a full sequential replay).
 template <int MODEL, int LG, bool DIAG>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) forward_kernel(Constants c, DeviceState d, int mode) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kernel(Constants c, DeviceState d, int mode) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
   constexpr int STEP = NS + 2 * NC + NC * NS;  // x_nom | u_nom | k | K
   constexpr int STEPP = (STEP + 1) & ~1;
