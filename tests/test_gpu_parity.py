@@ -423,3 +423,50 @@ def test_mpc_receding_horizon_loop(cddp, ob, problems):
         U = np.concatenate([o["U"][:, 1:], o["U"][:, -1:]], axis=1)
         s.mpc_advance(1, x0)
     s.close()
+
+
+@pytest.mark.parametrize("name", ["quadrotor", "cartpole", "unicycle", "pendulum"])
+def test_random_trajectories_per_step_parity(cddp, ob, problems, name):
+    """Random (dynamically inconsistent) nominal trajectories far from the nominal fixtures: linearisation, sweep with
+    a warm-started BoxQP at several regularisations (including ones that make the sweep fail and restart), and the
+    line search, instance by instance against the oracle."""
+    rng = np.random.default_rng({"quadrotor": 31, "cartpole": 32, "unicycle": 33, "pendulum": 34}[name])
+    B, N = 12, 25
+    cfg = problems.make_config(name, batch=B, horizon=N)
+    n, m = cfg["spec"]["n"], cfg["spec"]["m"]
+    X0 = cfg["X0"] + 0.3 * rng.standard_normal((B, N + 1, n))
+    lo = -1.0 if cfg["spec"].get("lb") is None else np.asarray(cfg["spec"]["lb"])
+    hi = 1.0 if cfg["spec"].get("ub") is None else np.asarray(cfg["spec"]["ub"])
+    U0 = rng.uniform(lo, hi, size=(B, N, m))
+    x0 = X0[:, 0].copy()
+    opts = dict(cfg["options"], max_iterations=3)
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+    for reg in (1e-6, 1e-2, 10.0):
+        s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), B)
+        s.set_instances(x0, cfg["xref"], X0, U0)
+        s.initialize()
+        s.set_regularization(reg)
+        kprev = 0.05 * rng.standard_normal((B, N, m))
+        s.set_gains(k=kprev)
+        s.linearize()
+        s.backward_pass()
+        sw, K, k = s.get_sweep(), s.get_solution()["K"], s.get_feedforward()
+        s.forward_pass()
+        fw = s.get_forward()
+        c0 = s.get_scalars()["cost"]
+        for b in range(B):
+            r = ob.backward_pass(P, oo, X0[b], U0[b], cfg["xref"][b], reg, k_prev=kprev[b], debug=True)
+            assert bool(sw["ok"][b]) == r["ok"], (name, reg, b)
+            if not r["ok"]:
+                continue
+            assert rel_err(K[b], r["K"]) < 1e-8 and rel_err(k[b], r["k"]) < 1e-8, (name, reg, b)
+            assert rel_err(sw["dV"][b], r["dV"]) < 1e-8 and rel_err(sw["Vxx0"][b], r["Vxx"][0]) < 1e-8
+            first = -1
+            for ai, a in enumerate(ob.build_alphas(oo)):
+                f = ob.forward_pass(P, oo, x0[b], X0[b], U0[b], cfg["xref"][b], r["K"], r["k"], r["dV"], c0[b], a)
+                if np.isfinite(f["cost"]):
+                    assert abs(fw["costs"][b, ai] - f["cost"]) < 1e-7 * abs(f["cost"])
+                if f["success"] and first < 0:
+                    first = ai
+            assert fw["accepted"][b] == first
+        s.close()
