@@ -265,6 +265,46 @@ class ControlConstraint : public Constraint {  // constraint.hpp:144-251 (BoxCon
   Eigen::VectorXd lower_bound_, upper_bound_;
 };
 
+// Terminal constraints (terminal_constraint.hpp:29-158).  CLDDP never reads them (clddp_solver.cpp looks up
+// "ControlConstraint" only); they are mirrored so that CDDP::addTerminalConstraint and the dual-dimension bookkeeping
+// behave as in the reference (test_cddp_core.cpp:637-676).
+class TerminalConstraint : public Constraint {
+ public:
+  explicit TerminalConstraint(const std::string &name) : Constraint(name) {}
+};
+class TerminalEqualityConstraint : public TerminalConstraint {  // x_N - target = 0
+ public:
+  explicit TerminalEqualityConstraint(const Eigen::VectorXd &target_state, const std::string &name = "TerminalEqualityConstraint")
+      : TerminalConstraint(name), target_state_(target_state) {}
+  int getDualDim() const override { return (int)target_state_.size(); }
+  Eigen::VectorXd evaluate(const Eigen::VectorXd &final_state, const Eigen::VectorXd &, int = 0) const override {
+    if (final_state.size() != target_state_.size())
+      throw std::invalid_argument("TerminalEqualityConstraint: final_state dimension mismatch.");
+    return final_state - target_state_;
+  }
+  Eigen::VectorXd getLowerBound() const override { return Eigen::VectorXd::Zero(target_state_.size()); }
+  Eigen::VectorXd getUpperBound() const override { return Eigen::VectorXd::Zero(target_state_.size()); }
+  const Eigen::VectorXd &getTargetState() const { return target_state_; }
+
+ private:
+  Eigen::VectorXd target_state_;
+};
+class TerminalInequalityConstraint : public TerminalConstraint {  // A x_N - b <= 0
+ public:
+  TerminalInequalityConstraint(const Eigen::MatrixXd &A, const Eigen::VectorXd &b, const std::string &name = "TerminalInequalityConstraint")
+      : TerminalConstraint(name), A_(A), b_(b) {}
+  int getDualDim() const override { return (int)b_.size(); }
+  Eigen::VectorXd evaluate(const Eigen::VectorXd &final_state, const Eigen::VectorXd &, int = 0) const override {
+    return (A_ * final_state) - b_;
+  }
+  Eigen::VectorXd getLowerBound() const override;
+  Eigen::VectorXd getUpperBound() const override { return Eigen::VectorXd::Zero(b_.size()); }
+
+ private:
+  Eigen::MatrixXd A_;
+  Eigen::VectorXd b_;
+};
+
 // ------------------------------------------------------------------------------------------------ solution / solver / facade
 struct CDDPSolution {  // cddp_core.hpp:54-103
   std::string solver_name;
@@ -317,6 +357,7 @@ class CDDP {  // cddp_core.hpp:212-442, cddp_core.cpp
   int getTotalDualDim() const { return total_dual_dim_; }
   const CDDPOptions &getOptions() const { return options_; }
   const std::map<std::string, std::unique_ptr<Constraint>> &getConstraintSet() const { return path_constraint_set_; }
+  const std::map<std::string, std::unique_ptr<Constraint>> &getTerminalConstraintSet() const { return terminal_constraint_set_; }
   bool hasSystem() const { return (bool)system_; }
   bool hasObjective() const { return (bool)objective_; }
 
@@ -331,11 +372,20 @@ class CDDP {  // cddp_core.hpp:212-442, cddp_core.cpp
   void setInitialTrajectory(const std::vector<Eigen::VectorXd> &X, const std::vector<Eigen::VectorXd> &U);
   void addPathConstraint(std::string constraint_name, std::unique_ptr<Constraint> constraint);
   bool removePathConstraint(const std::string &constraint_name);
+  void addTerminalConstraint(std::string constraint_name, std::unique_ptr<Constraint> constraint);
+  bool removeTerminalConstraint(const std::string &constraint_name);
 
   template <typename T>
   T *getConstraint(const std::string &name) const {  // exact name AND dynamic type (clddp_solver.cpp:85-86)
     auto it = path_constraint_set_.find(name);
     if (it == path_constraint_set_.end()) return nullptr;
+    return dynamic_cast<T *>(it->second.get());
+  }
+
+  template <typename T>
+  T *getTerminalConstraint(const std::string &name) const {
+    auto it = terminal_constraint_set_.find(name);
+    if (it == terminal_constraint_set_.end()) return nullptr;
     return dynamic_cast<T *>(it->second.get());
   }
 
@@ -370,6 +420,7 @@ class CDDP {  // cddp_core.hpp:212-442, cddp_core.cpp
   std::unique_ptr<DynamicalSystem> system_;
   std::unique_ptr<Objective> objective_;
   std::map<std::string, std::unique_ptr<Constraint>> path_constraint_set_;
+  std::map<std::string, std::unique_ptr<Constraint>> terminal_constraint_set_;
   Eigen::VectorXd initial_state_, reference_state_;
   std::vector<Eigen::VectorXd> reference_states_;
   int horizon_;

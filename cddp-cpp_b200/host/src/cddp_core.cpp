@@ -389,6 +389,27 @@ bool CDDP::removePathConstraint(const std::string &name) {
   return true;
 }
 
+void CDDP::addTerminalConstraint(std::string name, std::unique_ptr<Constraint> constraint) {
+  if (!constraint) throw std::runtime_error("Cannot add null constraint.");
+  const int dual = constraint->getDualDim();
+  auto it = terminal_constraint_set_.find(name);
+  if (it != terminal_constraint_set_.end()) total_dual_dim_ -= it->second->getDualDim();
+  terminal_constraint_set_[name] = std::move(constraint);
+  total_dual_dim_ += dual;
+  initialized_ = false;
+}
+bool CDDP::removeTerminalConstraint(const std::string &name) {
+  auto it = terminal_constraint_set_.find(name);
+  if (it == terminal_constraint_set_.end()) return false;
+  total_dual_dim_ -= it->second->getDualDim();
+  terminal_constraint_set_.erase(it);
+  initialized_ = false;
+  return true;
+}
+Eigen::VectorXd TerminalInequalityConstraint::getLowerBound() const {
+  return Eigen::VectorXd::Constant(b_.size(), -std::numeric_limits<double>::infinity());
+}
+
 static const char *solverTypeToString(SolverType t) {
   switch (t) {
     case SolverType::CLDDP: return "CLDDP";

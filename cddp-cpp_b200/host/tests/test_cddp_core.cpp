@@ -136,6 +136,22 @@ void DualDimBookkeepingAndNullConstraint() {
   CHECK(c->getTotalDualDim() == 2 * control_dim);
   CHECK(c->getConstraint<ControlConstraint>("ControlConstraint") != nullptr);
   CHECK(c->getConstraint<ControlConstraint>("SomethingElse") == nullptr);
+  // terminal constraints share the dual-dimension bookkeeping (test_cddp_core.cpp:637-676)
+  c->addTerminalConstraint("RepeatedTerminalConstraint", std::make_unique<TerminalEqualityConstraint>(vec({2, 2, 0})));
+  CHECK(c->getTotalDualDim() == 2 * control_dim + state_dim);
+  Eigen::MatrixXd A1(1, state_dim);
+  A1(0, 0) = 1.0;
+  c->addTerminalConstraint("RepeatedTerminalConstraint", std::make_unique<TerminalInequalityConstraint>(A1, vec({2.5})));
+  CHECK(c->getTotalDualDim() == 2 * control_dim + 1);
+  CHECK(c->getTerminalConstraint<TerminalInequalityConstraint>("RepeatedTerminalConstraint") != nullptr);
+  CHECK(c->getTerminalConstraint<TerminalEqualityConstraint>("RepeatedTerminalConstraint") == nullptr);
+  CHECK(c->getTerminalConstraintSet().size() == 1);
+  CHECK_NEAR(c->getTerminalConstraint<TerminalInequalityConstraint>("RepeatedTerminalConstraint")->evaluate(vec({3, 0, 0}), vec({0, 0}))[0], 0.5, 1e-15);
+  CHECK(c->removeTerminalConstraint("RepeatedTerminalConstraint"));
+  CHECK(!c->removeTerminalConstraint("RepeatedTerminalConstraint"));
+  CHECK(c->getTotalDualDim() == 2 * control_dim);
+  TerminalEqualityConstraint te(vec({1, 2, 3}));
+  CHECK((te.evaluate(vec({1.5, 2, 2}), vec({0, 0})) - vec({0.5, 0, -1})).norm() < 1e-15 && te.getName() == "TerminalEqualityConstraint");
   CHECK(c->removePathConstraint("ControlConstraint"));
   CHECK(!c->removePathConstraint("ControlConstraint"));
   CHECK(c->getTotalDualDim() == 0);
