@@ -1094,6 +1094,790 @@ void solve_one(const oracle_problem *p, const oracle_options *o, const double *x
   res->reserved = 0;
 }
 
+
+/* ==========================================================================================
+ * IPDDP (src/cddp_core/ipddp_solver.cpp) — cold start (options.warm_start = false), use_ilqr = true
+ * (the default, options.hpp:223: no dynamics-Hessian terms), path INEQUALITY constraints of the types
+ * ControlConstraint / StateConstraint (constraint.hpp:144-251), LinearConstraint (:253-318) and
+ * BallConstraint (:320-440); no terminal constraints (branches 1 and 3 of IPDDPSolver::backwardPass:
+ * :1055-1118 unconstrained, :1355-1569 path constraints).  The costate bookkeeping (Lambda_, k_lambda_,
+ * K_lambda_) only feeds an allFinite() test in the reference (:1612-1618, :1665-1671) and is not carried.
+ * ======================================================================================== */
+constexpr int MAXDUAL = 64; /* total dual dimension capacity */
+constexpr double kSlackInteriorOffset = 1e-4; /* ipddp_solver.cpp:35-38 */
+constexpr double EPS_SLACK = 1e-10;
+constexpr double MAX_BARRIER_RATIO = 1e6;
+
+inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (hi < v ? hi : v); } /* std::clamp */
+inline double clip_pos(double num, double den) { return clampd(num / den, 0.0, MAX_BARRIER_RATIO); }      /* :222-225 */
+inline double clip_signed(double num, double den) { return clampd(num / den, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO); } /* :227-231 */
+
+int constraint_dim(const oracle_problem *p, const oracle_constraint &c) {
+  switch (c.type) {
+    case ORACLE_CON_CONTROL_BOX: return 2 * p->m; /* constraint.hpp:156 */
+    case ORACLE_CON_STATE_BOX: return 2 * p->n;
+    case ORACLE_CON_BALL: return 1;               /* :324 */
+    default: return c.rows;                       /* LinearConstraint :261 */
+  }
+}
+int total_dual_dim(const oracle_problem *p, const oracle_constraint *cs, int nc) { /* ipddp_solver.cpp:2134-2143 */
+  int d = 0;
+  for (int i = 0; i < nc; ++i) d += constraint_dim(p, cs[i]);
+  return d;
+}
+
+/* g = constraint.evaluate(x,u) - constraint.getUpperBound() for the stacked set, in the caller's order (the
+ * reference iterates a std::map keyed by constraint name, i.e. alphabetical order) (:2273-2278) */
+void eval_constraints(const oracle_problem *p, const oracle_constraint *cs, int nc, const double *x, const double *u,
+                      double *g) {
+  int o = 0;
+  for (int c = 0; c < nc; ++c) {
+    const oracle_constraint &C = cs[c];
+    if (C.type == ORACLE_CON_CONTROL_BOX || C.type == ORACLE_CON_STATE_BOX) { /* constraint.hpp:156-180 */
+      const int k = C.type == ORACLE_CON_CONTROL_BOX ? p->m : p->n;
+      const double *v = C.type == ORACLE_CON_CONTROL_BOX ? u : x;
+      for (int i = 0; i < k; ++i) {
+        g[o + i] = (-v[i]) * C.scale - (-C.p0[i] * C.scale);
+        g[o + k + i] = v[i] * C.scale - C.p1[i] * C.scale;
+      }
+      o += 2 * k;
+    } else if (C.type == ORACLE_CON_BALL) { /* :326-343 */
+      double sq = 0.0;
+      for (int i = 0; i < C.rows; ++i) sq += (x[i] - C.p0[i]) * (x[i] - C.p0[i]);
+      g[o] = -(C.scale * sq) - (-(C.p1[0] * C.p1[0]) * C.scale);
+      o += 1;
+    } else { /* LinearConstraint: A x - b (scale_factor is NOT applied by evaluate, :263-268) */
+      for (int r = 0; r < C.rows; ++r) {
+        double s = 0.0;
+        for (int j = 0; j < p->n; ++j) s += C.p0[r * p->n + j] * x[j];
+        g[o + r] = s - C.p1[r];
+      }
+      o += C.rows;
+    }
+  }
+}
+
+/* getStateJacobian / getControlJacobian of the stacked set: Gx [d][n], Gu [d][m] */
+void constraint_jacobians(const oracle_problem *p, const oracle_constraint *cs, int nc, const double *x, double *Gx,
+                          double *Gu) {
+  const int n = p->n, m = p->m;
+  int o = 0;
+  for (int c = 0; c < nc; ++c) {
+    const oracle_constraint &C = cs[c];
+    const int dim = constraint_dim(p, C);
+    for (int r = 0; r < dim; ++r) {
+      for (int j = 0; j < n; ++j) Gx[(o + r) * n + j] = 0.0;
+      for (int j = 0; j < m; ++j) Gu[(o + r) * m + j] = 0.0;
+    }
+    if (C.type == ORACLE_CON_CONTROL_BOX) { /* constraint.hpp:201-217 */
+      for (int i = 0; i < m; ++i) {
+        Gu[(o + i) * m + i] = -1.0 * C.scale;
+        Gu[(o + m + i) * m + i] = 1.0 * C.scale;
+      }
+    } else if (C.type == ORACLE_CON_STATE_BOX) { /* :183-199 */
+      for (int i = 0; i < n; ++i) {
+        Gx[(o + i) * n + i] = -1.0 * C.scale;
+        Gx[(o + n + i) * n + i] = 1.0 * C.scale;
+      }
+    } else if (C.type == ORACLE_CON_BALL) { /* :360-373 */
+      for (int i = 0; i < C.rows; ++i) Gx[o * n + i] = -2.0 * C.scale * (x[i] - C.p0[i]);
+    } else { /* :278-284 */
+      for (int r = 0; r < C.rows; ++r)
+        for (int j = 0; j < n; ++j) Gx[(o + r) * n + j] = C.p0[r * n + j];
+    }
+    o += dim;
+  }
+}
+
+struct FilterPt { double merit, theta; };
+inline bool dominates(const FilterPt &a, const FilterPt &b) { return a.merit <= b.merit && a.theta <= b.theta; } /* cddp_core.hpp:171-174 */
+bool accept_filter_entry(std::vector<FilterPt> &f, double merit, double theta) { /* interior_point_utils.cpp:81-97 */
+  const FilterPt cand{merit, theta};
+  for (const auto &q : f)
+    if (dominates(q, cand)) return false;
+  f.erase(std::remove_if(f.begin(), f.end(), [&](const FilterPt &q) { return dominates(cand, q); }), f.end());
+  f.push_back(cand);
+  return true;
+}
+void prune_filter(std::vector<FilterPt> &f) { /* interior_point_utils.cpp:116-141 */
+  if (f.empty()) return;
+  FilterPt bv = f[0], bm = f[0];
+  for (const auto &q : f) { /* std::min_element: first minimal element */
+    if (q.theta < bv.theta) bv = q;
+    if (q.merit < bm.merit) bm = q;
+  }
+  f.clear();
+  f.push_back(bv);
+  if (std::fabs(bm.theta - bv.theta) > 1e-12 || std::fabs(bm.merit - bv.merit) > 1e-12) f.push_back(bm);
+}
+
+struct IpState {
+  int n, m, N, d, nc;
+  const oracle_problem *p;
+  const oracle_options *o;
+  const oracle_ipddp_options *io;
+  const oracle_constraint *cs;
+  const double *x0, *xref, *ref_traj;
+  std::vector<double> X, U, Y, S, G;                     /* nominal trajectory, duals, slacks, constraint values */
+  std::vector<double> ku, Ku, ky, Ky, ks, Ks, dS, dY;   /* gains and linearised steps */
+  std::vector<double> A, B;                              /* F_x_, F_u_ (cddp_solver_base.cpp:319-345) */
+  double mu = 0, cost = 0, merit = 0, phi = 0, theta = 0, filter_theta = 0;
+  double inf_pr = 0, inf_du = 0, inf_comp = 0, step_norm = 0, reg = 0, alpha_pr = 1, alpha_du = 1;
+  double dV[2] = {0, 0};
+  std::vector<FilterPt> filter;
+};
+
+double ip_theta(const IpState &s, const double *G, const double *S) { /* computeTheta :2778-2848 */
+  const bool l2 = s.io->theta_norm_l2 != 0;
+  double total = 0.0, max_entry = 0.0;
+  for (int c = 0, o = 0; c < s.nc; ++c) { /* per constraint, per t, as the reference's map-of-trajectories loops */
+    const int dim = constraint_dim(s.p, s.cs[c]);
+    for (int t = 0; t < s.N; ++t) {
+      double acc = 0.0, mx = 0.0;
+      for (int i = 0; i < dim; ++i) {
+        const double r = G[(size_t)t * s.d + o + i] + S[(size_t)t * s.d + o + i];
+        acc += l2 ? r * r : std::fabs(r);
+        mx = std::max(mx, std::fabs(r));
+      }
+      total += acc;
+      max_entry = std::max(max_entry, mx);
+    }
+    o += dim;
+  }
+  const double th = l2 ? std::sqrt(total) : total;
+  return std::max(th, max_entry);
+}
+double ip_merit(const IpState &s, const double *S, double cost) { /* computeBarrierMerit :2850-2880 */
+  double merit = cost;
+  for (int c = 0, o = 0; c < s.nc; ++c) {
+    const int dim = constraint_dim(s.p, s.cs[c]);
+    for (int t = 0; t < s.N; ++t) {
+      double acc = 0.0;
+      for (int i = 0; i < dim; ++i) acc += std::log(std::max(S[(size_t)t * s.d + o + i], EPS_SLACK));
+      merit -= s.mu * acc;
+    }
+    o += dim;
+  }
+  return merit;
+}
+void ip_primal_comp(const IpState &s, const double *G, const double *S, const double *Y, double mu, double *inf_pr,
+                    double *inf_comp) { /* computePrimalAndComplementarity :2882-2937 */
+  double ip = 0.0, ic = 0.0;
+  for (size_t i = 0; i < (size_t)s.N * s.d; ++i) {
+    ip = std::max(ip, std::fabs(G[i] + S[i]));
+    ic = std::max(ic, std::fabs(Y[i] * S[i] - mu));
+  }
+  *inf_pr = ip;
+  *inf_comp = ic;
+}
+void ip_reset_filter(IpState &s) { /* resetBarrierFilter :2484-2517 */
+  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp);
+  s.merit = ip_merit(s, s.S.data(), s.cost);
+  s.phi = s.merit;
+  s.filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data()), 1e-8);
+  s.theta = std::max(s.filter_theta, std::max(s.io->theta_0_floor, 1e-8));
+  s.filter.clear();
+}
+
+void ip_initialize(IpState &s, const double *U0) { /* IPDDPSolver::initialize cold start :818-913 */
+  const int n = s.n, m = s.m, N = s.N, d = s.d;
+  s.X.assign((size_t)(N + 1) * n, 0.0);
+  s.U.assign((size_t)N * m, 0.0);
+  if (U0) std::memcpy(s.U.data(), U0, sizeof(double) * N * m);
+  s.ku.assign((size_t)N * m, 0.0);
+  s.Ku.assign((size_t)N * m * n, 0.0);
+  s.Y.assign((size_t)N * d, 0.0); s.S.assign((size_t)N * d, 0.0); s.G.assign((size_t)N * d, 0.0);
+  s.ky.assign((size_t)N * d, 0.0); s.Ky.assign((size_t)N * d * n, 0.0);
+  s.ks.assign((size_t)N * d, 0.0); s.Ks.assign((size_t)N * d * n, 0.0);
+  s.dS.assign((size_t)N * d, 0.0); s.dY.assign((size_t)N * d, 0.0);
+  s.A.assign((size_t)N * n * n, 0.0); s.B.assign((size_t)N * n * m, 0.0);
+  std::memcpy(s.X.data(), s.x0, sizeof(double) * n);
+  for (int t = 0; t < N; ++t) /* :876-882 rollout of the given controls */
+    discrete_dynamics(s.p, &s.X[(size_t)t * n], &s.U[(size_t)t * m], t * s.p->dt, &s.X[(size_t)(t + 1) * n]);
+  s.mu = s.nc == 0 ? std::max(s.o->tolerance / 10.0, s.io->mu_min_value) : s.io->mu_initial; /* :884-887 */
+  s.reg = s.o->reg_initial_value;
+  s.step_norm = 0.0;
+  s.alpha_pr = 1.0;
+  s.alpha_du = 1.0;
+  /* evaluateTrajectory (:2252-2296) + initializeDualSlackVariables (:2428-2482) */
+  for (int t = 0; t < N; ++t) {
+    double *g = &s.G[(size_t)t * d];
+    eval_constraints(s.p, s.cs, s.nc, &s.X[(size_t)t * n], &s.U[(size_t)t * m], g);
+    for (int i = 0; i < d; ++i) {
+      const double si = std::max(s.io->slack_var_init_scale, -g[i] + kSlackInteriorOffset);
+      s.S[(size_t)t * d + i] = si;
+      s.Y[(size_t)t * d + i] = (s.mu * s.io->dual_var_init_scale) / std::max(si, EPS_SLACK);
+    }
+  }
+  s.cost = trajectory_cost(s.p, s.X.data(), s.U.data(), s.xref, s.ref_traj);
+  ip_reset_filter(s);
+  s.inf_du = 0.0;
+  s.dV[0] = s.dV[1] = 0.0;
+}
+
+/* IPDDPSolver::backwardPass (:960-1569), branches 1 and 3 */
+bool ip_backward(IpState &s) {
+  const int n = s.n, m = s.m, N = s.N, d = s.d;
+  const oracle_problem *p = s.p;
+  const double dt = p->dt;
+  /* precomputeDynamicsDerivatives: F_x = dt*Fx with +1 on the diagonal, F_u = dt*Fu (cddp_solver_base.cpp:340-344) */
+  {
+    double Fx[MAXN * MAXN], Fu[MAXN * MAXM];
+    for (int t = 0; t < N; ++t) {
+      jacobians(p, &s.X[(size_t)t * n], &s.U[(size_t)t * m], t * dt, Fx, Fu);
+      double *A = &s.A[(size_t)t * n * n], *B = &s.B[(size_t)t * n * m];
+      for (int i = 0; i < n * n; ++i) A[i] = dt * Fx[i];
+      for (int i = 0; i < n; ++i) A[i * n + i] += 1.0;
+      for (int i = 0; i < n * m; ++i) B[i] = dt * Fu[i];
+    }
+  }
+  double Vx[MAXN], Vxx[MAXN * MAXN];
+  {
+    const double *xN = &s.X[(size_t)N * n];
+    double e[MAXN];
+    for (int i = 0; i < n; ++i) e[i] = xN[i] - s.xref[i];
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < n; ++j) acc += (2.0 * p->Qf[i * n + j]) * e[j];
+      Vx[i] = acc;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * (2.0 * p->Qf[i * n + j] + 2.0 * p->Qf[j * n + i]); /* :990 */
+  }
+  s.dV[0] = s.dV[1] = 0.0;
+  double inf_du = 0.0, inf_pr = 0.0, inf_comp = 0.0, step_norm = 0.0;
+  std::vector<double> Gx((size_t)std::max(d, 1) * n), Gu((size_t)std::max(d, 1) * m);
+  double Qx[MAXN], Qu[MAXM], Qxx[MAXN * MAXN], Qux[MAXM * MAXN], Quu[MAXM * MAXM], Qr[MAXM * MAXM];
+  double VA[MAXN * MAXN], VB[MAXN * MAXM];
+  double YS[MAXDUAL], rhat[MAXDUAL], Sir[MAXDUAL], prim[MAXDUAL], comp[MAXDUAL], ssafe[MAXDUAL];
+  LDLT ldlt;
+  for (int t = N - 1; t >= 0; --t) {
+    const double *x = &s.X[(size_t)t * n], *u = &s.U[(size_t)t * m];
+    const double *A = &s.A[(size_t)t * n * n], *B = &s.B[(size_t)t * n * m];
+    const double *y = d ? &s.Y[(size_t)t * d] : nullptr, *sl = d ? &s.S[(size_t)t * d] : nullptr;
+    const double *g = d ? &s.G[(size_t)t * d] : nullptr;
+    if (d) constraint_jacobians(p, s.cs, s.nc, x, Gx.data(), Gu.data()); /* precomputeConstraintGradients :2145-2250 */
+    const double *ref = ref_at(p, s.xref, s.ref_traj, t);
+    double e[MAXN];
+    for (int i = 0; i < n; ++i) e[i] = x[i] - ref[i];
+    for (int i = 0; i < n; ++i) { /* Q_x = l_x + Q_yx^T y + A^T V_x (:1393) */
+      double lx = 0.0;
+      for (int j = 0; j < n; ++j) lx += (2.0 * (p->Q[i * n + j] * dt)) * e[j];
+      double gy = 0.0;
+      for (int r = 0; r < d; ++r) gy += Gx[r * n + i] * y[r];
+      double av = 0.0;
+      for (int j = 0; j < n; ++j) av += A[j * n + i] * Vx[j];
+      Qx[i] = d ? (lx + gy) + av : lx + av;
+    }
+    for (int i = 0; i < m; ++i) { /* Q_u = l_u + Q_yu^T y + B^T V_x (:1394) */
+      double lu = 0.0;
+      for (int j = 0; j < m; ++j) lu += (2.0 * (p->R[i * m + j] * dt)) * u[j];
+      double gy = 0.0;
+      for (int r = 0; r < d; ++r) gy += Gu[r * m + i] * y[r];
+      double bv = 0.0;
+      for (int j = 0; j < n; ++j) bv += B[j * m + i] * Vx[j];
+      Qu[i] = d ? (lu + gy) + bv : lu + bv;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += Vxx[i * n + l] * A[l * n + j];
+        VA[i * n + j] = acc;
+      }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < m; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += Vxx[i * n + l] * B[l * m + j];
+        VB[i * m + j] = acc;
+      }
+    for (int i = 0; i < n; ++i) /* Q_xx = l_xx + A^T V_xx A (:1395) */
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += A[l * n + i] * VA[l * n + j];
+        Qxx[i * n + j] = 2.0 * (p->Q[i * n + j] * dt) + acc;
+      }
+    for (int i = 0; i < m; ++i) /* Q_ux = l_ux + B^T V_xx A (:1396), l_ux = 0 */
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += B[l * m + i] * VA[l * n + j];
+        Qux[i * n + j] = acc;
+      }
+    for (int i = 0; i < m; ++i) /* Q_uu = l_uu + B^T V_xx B (:1397) */
+      for (int j = 0; j < m; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += B[l * m + i] * VB[l * m + j];
+        Quu[i * m + j] = 2.0 * (p->R[i * m + j] * dt) + acc;
+      }
+    for (int i = 0; i < d; ++i) { /* :1413-1425 */
+      ssafe[i] = std::max(sl[i], std::max(s.mu * 1e-3, EPS_SLACK));
+      YS[i] = clip_pos(y[i], ssafe[i]);
+      prim[i] = g[i] + sl[i];
+      comp[i] = y[i] * sl[i] - s.mu;
+      rhat[i] = y[i] * prim[i] - comp[i];
+      Sir[i] = clip_signed(rhat[i], ssafe[i]); /* :1437-1443 */
+    }
+    for (int i = 0; i < m; ++i) /* Q_uu_reg = sym(Q_uu) + Q_yu^T YSinv Q_yu + reg I (:1427-1429; branch 1: :1083-1084) */
+      for (int j = 0; j < m; ++j) {
+        double acc = 0.0;
+        for (int r = 0; r < d; ++r) acc += Gu[r * m + i] * (YS[r] * Gu[r * m + j]);
+        Qr[i * m + j] = 0.5 * (Quu[i * m + j] + Quu[j * m + i]) + acc;
+      }
+    for (int i = 0; i < m; ++i) Qr[i * m + i] += s.reg;
+    ldlt.compute(Qr, m);
+    if (!ldlt.ok) return false; /* :1431-1435 */
+    double rhs0[MAXM], rhsK[MAXM * MAXN];
+    for (int i = 0; i < m; ++i) { /* bigRHS (:1444-1447) */
+      double acc = 0.0;
+      for (int r = 0; r < d; ++r) acc += Gu[r * m + i] * Sir[r];
+      rhs0[i] = d ? Qu[i] + acc : Qu[i];
+      for (int j = 0; j < n; ++j) {
+        double a2 = 0.0;
+        for (int r = 0; r < d; ++r) a2 += Gu[r * m + i] * (YS[r] * Gx[r * n + j]);
+        rhsK[i * n + j] = d ? Qux[i * n + j] + a2 : Qux[i * n + j];
+      }
+    }
+    double *ku = &s.ku[(size_t)t * m], *Ku = &s.Ku[(size_t)t * m * n];
+    {
+      double col[MAXM];
+      for (int i = 0; i < m; ++i) col[i] = rhs0[i];
+      ldlt.solve_inplace(col);
+      for (int i = 0; i < m; ++i) ku[i] = -col[i];
+      for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) col[i] = rhsK[i * n + j];
+        ldlt.solve_inplace(col);
+        for (int i = 0; i < m; ++i) Ku[i * n + j] = -col[i];
+      }
+    }
+    if (d) { /* :1463-1491 */
+      double *ky = &s.ky[(size_t)t * d], *Ky = &s.Ky[(size_t)t * d * n];
+      double *ks = &s.ks[(size_t)t * d], *Ks = &s.Ks[(size_t)t * d * n];
+      for (int r = 0; r < d; ++r) {
+        double temp = 0.0;
+        for (int i = 0; i < m; ++i) temp += Gu[r * m + i] * ku[i];
+        ky[r] = clip_signed(rhat[r] + y[r] * temp, ssafe[r]);
+        ks[r] = -prim[r] - temp;
+        for (int j = 0; j < n; ++j) {
+          double gk = 0.0;
+          for (int i = 0; i < m; ++i) gk += Gu[r * m + i] * Ku[i * n + j];
+          const double q = Gx[r * n + j] + gk;
+          Ky[r * n + j] = clampd(YS[r] * q, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+          Ks[r * n + j] = -Gx[r * n + j] - gk;
+        }
+      }
+      /* condensed Q-terms (:1493-1497) */
+      for (int i = 0; i < m; ++i) Qu[i] = rhs0[i];
+      for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int r = 0; r < d; ++r) acc += Gx[r * n + i] * Sir[r];
+        Qx[i] += acc;
+      }
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double acc = 0.0;
+          for (int r = 0; r < d; ++r) acc += Gx[r * n + i] * (YS[r] * Gx[r * n + j]);
+          Qxx[i * n + j] += acc;
+        }
+      for (int i = 0; i < m; ++i) {
+        for (int j = 0; j < n; ++j) Qux[i * n + j] = rhsK[i * n + j];
+        for (int j = 0; j < m; ++j) {
+          double acc = 0.0;
+          for (int r = 0; r < d; ++r) acc += Gu[r * m + i] * (YS[r] * Gu[r * m + j]);
+          Quu[i * m + j] += acc;
+        }
+      }
+    } else { /* branch 1 (:1083-1084): the regularised, symmetrised Q_uu is what enters V and dV */
+      for (int i = 0; i < m * m; ++i) Quu[i] = Qr[i];
+    }
+    double Quuk[MAXM];
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += Quu[i * m + j] * ku[j];
+      Quuk[i] = acc;
+    }
+    double d0 = 0.0, d1 = 0.0;
+    for (int i = 0; i < m; ++i) { /* :1499-1500 */
+      d0 += ku[i] * Qu[i];
+      d1 += ku[i] * Quuk[i];
+    }
+    s.dV[0] += d0;
+    s.dV[1] += 0.5 * d1;
+    double Vxn[MAXN], Vxxn[MAXN * MAXN], QuuK[MAXM * MAXN];
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < m; ++l) acc += Quu[i * m + l] * Ku[l * n + j];
+        QuuK[i * n + j] = acc;
+      }
+    for (int i = 0; i < n; ++i) { /* V_x = Q_x + K^T Q_u + Q_ux^T k + K^T Q_uu k (:1502-1503) */
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int l = 0; l < m; ++l) {
+        a1 += Ku[l * n + i] * Qu[l];
+        a2 += Qux[l * n + i] * ku[l];
+        a3 += Ku[l * n + i] * Quuk[l];
+      }
+      Vxn[i] = ((Qx[i] + a1) + a2) + a3;
+    }
+    for (int i = 0; i < n; ++i) /* V_xx = Q_xx + K^T Q_ux + Q_ux^T K + K^T Q_uu K (:1504-1505) */
+      for (int j = 0; j < n; ++j) {
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int l = 0; l < m; ++l) {
+          a1 += Ku[l * n + i] * Qux[l * n + j];
+          a2 += Qux[l * n + i] * Ku[l * n + j];
+          a3 += Ku[l * n + i] * QuuK[l * n + j];
+        }
+        Vxxn[i * n + j] = ((Qxx[i * n + j] + a1) + a2) + a3;
+      }
+    for (int i = 0; i < n; ++i) {
+      Vx[i] = Vxn[i];
+      for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * (Vxxn[i * n + j] + Vxxn[j * n + i]);
+    }
+    for (int i = 0; i < m; ++i) { /* :1510-1513 */
+      inf_du = std::max(inf_du, std::fabs(Qu[i]));
+      step_norm = std::max(step_norm, std::fabs(ku[i]));
+    }
+    for (int i = 0; i < d; ++i) {
+      inf_pr = std::max(inf_pr, std::fabs(prim[i]));
+      inf_comp = std::max(inf_comp, std::fabs(comp[i]));
+    }
+  }
+  if (d) { /* rolloutLinearPolicy from dx0 = 0 (:368-392) and the linearised slack/dual steps (:1516-1538) */
+    double dx[MAXN], dxn[MAXN], du[MAXM];
+    for (int i = 0; i < n; ++i) dx[i] = 0.0;
+    for (int t = 0; t < N; ++t) {
+      const double *A = &s.A[(size_t)t * n * n], *B = &s.B[(size_t)t * n * m];
+      for (int r = 0; r < d; ++r) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) {
+          a1 += s.Ks[((size_t)t * d + r) * n + j] * dx[j];
+          a2 += s.Ky[((size_t)t * d + r) * n + j] * dx[j];
+        }
+        s.dS[(size_t)t * d + r] = s.ks[(size_t)t * d + r] + a1;
+        s.dY[(size_t)t * d + r] = clampd(s.ky[(size_t)t * d + r] + a2, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+      }
+      for (int i = 0; i < m; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < n; ++j) acc += s.Ku[((size_t)t * m + i) * n + j] * dx[j];
+        du[i] = s.ku[(size_t)t * m + i] + acc;
+      }
+      for (int i = 0; i < n; ++i) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) a1 += A[i * n + j] * dx[j];
+        for (int j = 0; j < m; ++j) a2 += B[i * m + j] * du[j];
+        dxn[i] = (a1 + a2) + 0.0;
+      }
+      for (int i = 0; i < n; ++i) dx[i] = dxn[i];
+    }
+    s.inf_pr = inf_pr;
+    s.inf_comp = inf_comp;
+  } else {
+    s.inf_pr = 0.0; /* :1113-1116 */
+    s.inf_comp = 0.0;
+  }
+  s.inf_du = inf_du;
+  s.step_norm = step_norm;
+  return true;
+}
+
+struct IpTrial {
+  bool success = false;
+  double cost = 0, merit = 0, theta = 0, inf_pr = 0, inf_comp = 0, alpha_pr = 0, alpha_du = 0;
+  std::vector<double> X, U, Y, S, G;
+};
+
+/* IPDDPSolver::forwardPass (:1571-1876) */
+void ip_forward(const IpState &s, double alpha, IpTrial &r) {
+  const int n = s.n, m = s.m, N = s.N, d = s.d;
+  const oracle_problem *p = s.p;
+  r.success = false;
+  /* computeMaxStepSizes (:2939-2988) */
+  const double tau_b = std::max(s.io->min_fraction_to_boundary, 1.0 - s.mu);
+  double apm = 1.0, adm = 1.0;
+  for (int c = 0, o = 0; c < s.nc; ++c) {
+    const int dim = constraint_dim(p, s.cs[c]);
+    for (int t = 0; t < N; ++t)
+      for (int i = 0; i < dim; ++i) {
+        const size_t q = (size_t)t * d + o + i;
+        if (s.dS[q] < 0.0) apm = std::min(apm, -tau_b * s.S[q] / s.dS[q]);
+        if (s.dY[q] < 0.0) adm = std::min(adm, -tau_b * s.Y[q] / s.dY[q]);
+      }
+    o += dim;
+  }
+  apm = clampd(apm, 0.0, 1.0);
+  adm = clampd(adm, 0.0, 1.0);
+  const double tau = s.nc == 0 ? 1.0 : std::max(s.io->min_fraction_to_boundary, 1.0 - s.mu); /* :1585-1588 */
+  const double alpha_pr = std::min(alpha, apm), alpha_du = std::min(alpha, adm);
+  r.alpha_pr = alpha_pr;
+  r.alpha_du = alpha_du;
+  r.X.assign((size_t)(N + 1) * n, 0.0);
+  r.U.assign((size_t)N * m, 0.0);
+  r.Y = s.Y;
+  r.S = s.S;
+  r.G.assign((size_t)N * d, 0.0);
+  std::memcpy(r.X.data(), s.x0, sizeof(double) * n);
+  auto finite_vec = [](const double *v, int k) {
+    for (int i = 0; i < k; ++i)
+      if (!std::isfinite(v[i])) return false;
+    return true;
+  };
+  for (int t = 0; t < N; ++t) {
+    double dx[MAXN];
+    const double *xt = &r.X[(size_t)t * n];
+    for (int i = 0; i < n; ++i) dx[i] = xt[i] - s.X[(size_t)t * n + i];
+    for (int c = 0, o = 0; c < s.nc; ++c) { /* :1620-1647, per constraint */
+      const int dim = constraint_dim(p, s.cs[c]);
+      double sn[MAXDUAL], yn[MAXDUAL];
+      for (int i = 0; i < dim; ++i) {
+        const size_t q = (size_t)t * d + o + i;
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) {
+          a1 += s.Ks[q * n + j] * dx[j];
+          a2 += s.Ky[q * n + j] * dx[j];
+        }
+        sn[i] = (s.S[q] + alpha_pr * s.ks[q]) + a1;
+        yn[i] = (s.Y[q] + alpha_du * s.ky[q]) + a2;
+      }
+      for (int i = 0; i < dim; ++i) {
+        const size_t q = (size_t)t * d + o + i;
+        if (sn[i] < (1.0 - tau) * s.S[q] || yn[i] < (1.0 - tau) * s.Y[q]) return;
+      }
+      if (!finite_vec(sn, dim) || !finite_vec(yn, dim)) return;
+      for (int i = 0; i < dim; ++i) {
+        r.S[(size_t)t * d + o + i] = sn[i];
+        r.Y[(size_t)t * d + o + i] = yn[i];
+      }
+      o += dim;
+    }
+    double *ut = &r.U[(size_t)t * m];
+    for (int i = 0; i < m; ++i) { /* :1650-1651 (no clamp) */
+      double acc = 0.0;
+      for (int j = 0; j < n; ++j) acc += s.Ku[((size_t)t * m + i) * n + j] * dx[j];
+      ut[i] = (s.U[(size_t)t * m + i] + alpha_pr * s.ku[(size_t)t * m + i]) + acc;
+    }
+    discrete_dynamics(p, xt, ut, t * p->dt, &r.X[(size_t)(t + 1) * n]);
+    if (!finite_vec(&r.X[(size_t)(t + 1) * n], n) || !finite_vec(ut, m)) return;
+  }
+  double cost_new = 0.0; /* :1735-1751 */
+  for (int t = 0; t < N; ++t) {
+    cost_new += running_cost(p, &r.X[(size_t)t * n], &r.U[(size_t)t * m], ref_at(p, s.xref, s.ref_traj, t));
+    if (d) eval_constraints(p, s.cs, s.nc, &r.X[(size_t)t * n], &r.U[(size_t)t * m], &r.G[(size_t)t * d]);
+  }
+  cost_new += terminal_cost(p, &r.X[(size_t)N * n], s.xref);
+  const double phi_new = ip_merit(s, r.S.data(), cost_new);
+  const double theta_new = ip_theta(s, r.G.data(), r.S.data());
+  double ipn = 0.0, icn = 0.0;
+  ip_primal_comp(s, r.G.data(), r.S.data(), r.Y.data(), s.mu, &ipn, &icn);
+  if (!std::isfinite(phi_new) || !std::isfinite(theta_new) || !std::isfinite(ipn) || !std::isfinite(icn)) return;
+  bool accept = false;
+  if (s.nc == 0) { /* :1787-1794: hard-coded 1e-6 */
+    const double dJ = s.cost - cost_new;
+    const double expected = -alpha_pr * (s.dV[0] + 0.5 * alpha_pr * s.dV[1]);
+    const double ratio = expected > 0.0 ? dJ / expected : std::copysign(1.0, dJ);
+    accept = ratio > 1e-6;
+  } else { /* :1796-1839 */
+    const double expected_improvement = alpha_pr * s.dV[0];
+    const double cv_old = s.filter.empty() ? 0.0 : s.filter.back().theta;
+    const double high_ref = s.filter.empty() ? s.filter_theta : cv_old;
+    const double merit_old = s.merit;
+    if (theta_new > s.io->max_violation_threshold) {
+      if (theta_new < (1 - s.io->violation_acceptance_threshold) * high_ref) accept = true;
+    } else if (std::max(theta_new, cv_old) < s.io->min_violation_for_armijo_check && expected_improvement < 0) {
+      if (phi_new < merit_old + s.o->armijo_constant * expected_improvement) accept = true;
+    } else {
+      if (phi_new < merit_old - s.io->merit_acceptance_threshold * theta_new ||
+          theta_new < (1 - s.io->violation_acceptance_threshold) * cv_old)
+        accept = true;
+    }
+  }
+  if (!accept) return;
+  r.success = true;
+  r.cost = cost_new;
+  r.merit = phi_new;
+  r.theta = theta_new;
+  r.inf_pr = ipn;
+  r.inf_comp = icn;
+}
+
+void ip_update_barrier(IpState &s) { /* updateBarrierParameters(context, true) (:2548-2660) */
+  const bool no_barrier = s.nc == 0;
+  const double scaled_inf_du = s.inf_du; /* computeScaledDualInfeasibility, check_state_stationarity = false (:2725-2733) */
+  const double mu_old = s.mu;
+  if (no_barrier) {
+    s.mu = mu_old;
+  } else if (s.io->barrier_strategy == ORACLE_BARRIER_ADAPTIVE) {
+    const double kkt = std::max(std::max(s.inf_pr, scaled_inf_du), s.inf_comp);
+    const double threshold = std::max(s.io->mu_update_factor * s.mu, 2.0 * s.mu);
+    if (kkt <= threshold) {
+      double factor = s.io->mu_update_factor;
+      if (s.mu > 1e-20) {
+        const double ratio = kkt / std::max(s.mu, 1e-20);
+        if (ratio < 0.01) factor = 0.1 * s.io->mu_update_factor;
+        else if (ratio < 0.1) factor = 0.3 * s.io->mu_update_factor;
+        else if (ratio < 0.5) factor = 0.6 * s.io->mu_update_factor;
+      }
+      const double linear = factor * s.mu;
+      const double superlinear = std::pow(s.mu, s.io->mu_update_power);
+      s.mu = std::max(std::min(linear, superlinear), std::max(s.io->mu_min_value, s.o->tolerance / 100.0));
+    }
+  } else {
+    const double kkt = std::max(std::max(s.inf_pr, scaled_inf_du * s.io->barrier_update_dual_weight), s.inf_comp);
+    if (kkt <= s.io->mu_kappa_epsilon * s.mu) {
+      const double linear = s.io->mu_update_factor * s.mu;
+      const double superlinear = std::pow(s.mu, s.io->mu_update_power);
+      s.mu = std::max(s.io->mu_min_value, std::min(linear, superlinear));
+    }
+  }
+  const double filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data()), 1e-8);
+  const bool reset_filter = (s.mu < mu_old) && (s.mu > 0.0);
+  if (reset_filter) {
+    s.filter.clear();
+  } else {
+    accept_filter_entry(s.filter, s.phi, filter_theta);
+    if ((int)s.filter.size() > s.io->max_filter_size) prune_filter(s.filter);
+  }
+  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp);
+  s.merit = ip_merit(s, s.S.data(), s.cost);
+  s.phi = s.merit;
+  s.filter_theta = filter_theta;
+  s.theta = std::max(filter_theta, std::max(s.io->theta_0_floor, 1e-8));
+}
+
+/* CDDP::solve("IPDDP"): CDDPSolverBase::solve (cddp_solver_base.cpp:29-186) with the IPDDP hooks */
+void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                     const oracle_constraint *cs, int nc, const double *x0, const double *xref, const double *ref_traj,
+                     double *X, double *U, double *K, double *Yout, double *Sout, oracle_ipddp_result *res,
+                     double *history) {
+  IpState s;
+  s.p = p; s.o = o; s.io = io; s.cs = cs; s.nc = nc;
+  s.n = p->n; s.m = p->m; s.N = p->horizon; s.d = total_dual_dim(p, cs, nc);
+  s.x0 = x0; s.xref = xref; s.ref_traj = ref_traj;
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  ip_initialize(s, U);
+  int hl = 0;
+  auto record = [&]() { /* recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp :2084-2088) */
+    if (!history) return;
+    double *h = history + (size_t)hl * ORACLE_IPDDP_HISTORY_COLS;
+    h[0] = s.cost; h[1] = s.merit; h[2] = s.alpha_pr; h[3] = s.alpha_du; h[4] = s.inf_du;
+    h[5] = s.inf_pr; h[6] = s.inf_comp; h[7] = s.reg; h[8] = s.mu;
+    ++hl;
+  };
+  record();
+  int iter = 0, status = ORACLE_MAX_ITERATIONS;
+  bool converged = false;
+  const bool no_barrier = nc == 0;
+  IpTrial trial;
+  while (iter < o->max_iterations) {
+    ++iter;
+    bool backward_ok = false;
+    while (!backward_ok) {
+      backward_ok = ip_backward(s);
+      if (!backward_ok) {
+        s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+        if (s.reg >= o->reg_max_value) {
+          status = ORACLE_REG_LIMIT;
+          break;
+        }
+      }
+    }
+    if (!backward_ok) break;
+    { /* checkEarlyConvergence (:925-958) */
+      bool early;
+      if (no_barrier) {
+        early = s.inf_pr < o->tolerance && s.inf_du < o->tolerance;
+      } else {
+        const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
+        early = s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol &&
+                std::fabs(s.alpha_pr) * s.step_norm < o->tolerance * 10.0;
+      }
+      if (early) {
+        status = ORACLE_OPTIMAL;
+        converged = true;
+        record();
+        break;
+      }
+    }
+    bool fp = false; /* performForwardPass, sequential (cddp_solver_base.cpp:255-263) */
+    for (int ai = 0; ai < na; ++ai) {
+      ip_forward(s, alphas[ai], trial);
+      if (trial.success) {
+        fp = true;
+        break;
+      }
+    }
+    if (fp) {
+      const double dJ = s.cost - trial.cost;
+      /* applyForwardPassResult (:1878-1951) */
+      s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
+      s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
+      s.Y = trial.Y; s.S = trial.S; s.G = trial.G;
+      s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
+      s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
+      ip_update_barrier(s);
+      record();
+      s.reg = std::max(s.reg / o->reg_update_factor, o->reg_min_value);
+      /* checkConvergence (:1953-2025) */
+      if (no_barrier) {
+        if (s.inf_pr < o->tolerance && s.inf_du < o->tolerance) {
+          status = ORACLE_OPTIMAL;
+          converged = true;
+        } else if (o->acceptable_tolerance > 0.0) {
+          const double sq = std::sqrt(o->acceptable_tolerance);
+          bool acc = s.inf_pr < sq && s.inf_du < sq && iter > 50;
+          if (dJ > 0.0) acc = acc || (dJ < o->acceptable_tolerance && iter > 50 && s.inf_pr < sq && s.inf_du < sq);
+          if (acc) {
+            status = ORACLE_ACCEPTABLE;
+            converged = true;
+          }
+        }
+      } else {
+        const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
+        if (s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol && s.step_norm < o->tolerance * 10.0) {
+          status = ORACLE_OPTIMAL;
+          converged = true;
+        } else if (o->acceptable_tolerance > 0.0) {
+          const double at = std::sqrt(o->acceptable_tolerance);
+          const double bat = std::max(io->mu_min_value * 100.0, o->tolerance / 10.0);
+          const bool kkt = s.inf_pr < at && s.inf_du < at && s.inf_comp < at;
+          const bool done = s.mu <= bat;
+          bool acc = kkt && done && iter > 10 && std::fabs(dJ) < o->acceptable_tolerance;
+          acc = acc || (kkt && done && iter >= 1 && s.step_norm < o->tolerance * 10.0 && s.inf_pr < 1e-4);
+          if (acc) {
+            status = ORACLE_ACCEPTABLE;
+            converged = true;
+          }
+        }
+      }
+    } else { /* handleForwardPassFailure (:2037-2082) */
+      s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+      if (s.reg >= o->reg_max_value) {
+        const double base = std::sqrt(std::max(o->acceptable_tolerance, o->tolerance));
+        const double at = no_barrier ? base : std::max(base, io->barrier_tol_mult * s.mu);
+        const bool acc = o->acceptable_tolerance > 0.0 && s.inf_pr < at && s.inf_du < at && (no_barrier || s.inf_comp < at);
+        status = acc ? ORACLE_ACCEPTABLE : ORACLE_REG_LIMIT;
+        break;
+      }
+    }
+    if (converged) break;
+  }
+  std::memcpy(X, s.X.data(), sizeof(double) * s.X.size());
+  std::memcpy(U, s.U.data(), sizeof(double) * s.U.size());
+  if (K) std::memcpy(K, s.Ku.data(), sizeof(double) * s.Ku.size());
+  if (Yout && s.d) std::memcpy(Yout, s.Y.data(), sizeof(double) * s.Y.size());
+  if (Sout && s.d) std::memcpy(Sout, s.S.data(), sizeof(double) * s.S.size());
+  res->final_objective = s.cost;
+  res->final_step_length = s.alpha_pr;
+  res->final_regularization = s.reg;
+  res->inf_du = s.inf_du;
+  res->inf_pr = s.inf_pr;
+  res->inf_comp = s.inf_comp;
+  res->mu = s.mu;
+  res->merit = s.merit;
+  res->iterations = iter;
+  res->status = status;
+  res->history_len = hl;
+  res->dual_dim = s.d;
+}
+
 } /* namespace */
 
 extern "C" {
@@ -1238,6 +2022,124 @@ void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int ba
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
   for (auto &t : th) t.join();
+}
+
+void oracle_ipddp_default_options(oracle_ipddp_options *io) { /* options.hpp:75-104,148-186 */
+  std::memset(io, 0, sizeof(*io));
+  io->dual_var_init_scale = 1e-1;
+  io->slack_var_init_scale = 1e-2;
+  io->barrier_tol_mult = 0.1;
+  io->barrier_update_dual_weight = 0.01;
+  io->mu_kappa_epsilon = 10.0;
+  io->theta_0_floor = 1.0;
+  io->mu_initial = 1.0;
+  io->mu_min_value = 1e-10;
+  io->mu_update_factor = 0.5;
+  io->mu_update_power = 1.2;
+  io->min_fraction_to_boundary = 0.99;
+  io->merit_acceptance_threshold = 1e-6;
+  io->violation_acceptance_threshold = 1e-6;
+  io->max_violation_threshold = 1e4;
+  io->min_violation_for_armijo_check = 1e-7;
+  io->theta_norm_l2 = 0;
+  io->max_filter_size = 5;
+  io->barrier_strategy = ORACLE_BARRIER_ADAPTIVE;
+}
+
+int oracle_total_dual_dim(const oracle_problem *p, const oracle_constraint *cs, int nc) { return total_dual_dim(p, cs, nc); }
+
+void oracle_eval_constraints(const oracle_problem *p, const oracle_constraint *cs, int nc, const double *x,
+                             const double *u, double *g, double *Gx, double *Gu) {
+  if (g) eval_constraints(p, cs, nc, x, u, g);
+  if (Gx && Gu) constraint_jacobians(p, cs, nc, x, Gx, Gu);
+}
+
+void oracle_ipddp_solve(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                        const oracle_constraint *cs, int nc, const double *x0, const double *xref,
+                        const double *ref_traj, double *X, double *U, double *K, double *Y, double *S,
+                        oracle_ipddp_result *res, double *history) {
+  ipddp_solve_one(p, o, io, cs, nc, x0, xref, ref_traj, X, U, K, Y, S, res, history);
+}
+
+void oracle_ipddp_solve_batch(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                              const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0,
+                              const double *xref, const double *ref_traj, double *X, double *U, double *K, double *Y,
+                              double *S, oracle_ipddp_result *res) {
+  const int n = p->n, m = p->m, N = p->horizon, d = total_dual_dim(p, cs, nc);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > batch) nthreads = batch;
+  auto work = [&](int tid) {
+    const int lo = (int)((long long)batch * tid / nthreads), hi = (int)((long long)batch * (tid + 1) / nthreads);
+    for (int b = lo; b < hi; ++b)
+      ipddp_solve_one(p, o, io, cs, nc, x0 + (size_t)b * n, xref + (size_t)b * n,
+                      ref_traj ? ref_traj + (size_t)b * (N + 1) * n : nullptr, X + (size_t)b * (N + 1) * n,
+                      U + (size_t)b * N * m, K ? K + (size_t)b * N * m * n : nullptr,
+                      Y ? Y + (size_t)b * N * d : nullptr, S ? S + (size_t)b * N * d : nullptr, res + b, nullptr);
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &t : th) t.join();
+}
+
+void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                        const oracle_constraint *cs, int nc, const double *x0, const double *xref,
+                        const double *ref_traj, const double *U0, int iters, double *X, double *U, double *Y, double *S,
+                        double *G, double *ku, double *Ku, double *ky, double *Ky, double *ks, double *Ks, double *dS,
+                        double *dY, double *scalars, double *trial_costs) {
+  IpState s;
+  s.p = p; s.o = o; s.io = io; s.cs = cs; s.nc = nc;
+  s.n = p->n; s.m = p->m; s.N = p->horizon; s.d = total_dual_dim(p, cs, nc);
+  s.x0 = x0; s.xref = xref; s.ref_traj = ref_traj;
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  ip_initialize(s, U0);
+  IpTrial trial;
+  bool ok = true;
+  for (int it = 0; it <= iters && ok; ++it) {
+    ok = ip_backward(s);
+    if (!ok || it == iters) break;
+    bool fp = false;
+    for (int ai = 0; ai < na; ++ai) {
+      ip_forward(s, alphas[ai], trial);
+      if (trial.success) { fp = true; break; }
+    }
+    if (fp) {
+      s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
+      s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
+      s.Y = trial.Y; s.S = trial.S; s.G = trial.G;
+      s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
+      s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
+      ip_update_barrier(s);
+      s.reg = std::max(s.reg / o->reg_update_factor, o->reg_min_value);
+    } else {
+      s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+    }
+  }
+  auto cp = [](double *dst, const std::vector<double> &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(double) * v.size()); };
+  cp(X, s.X); cp(U, s.U); cp(Y, s.Y); cp(S, s.S); cp(G, s.G); cp(ku, s.ku); cp(Ku, s.Ku);
+  cp(ky, s.ky); cp(Ky, s.Ky); cp(ks, s.ks); cp(Ks, s.Ks); cp(dS, s.dS); cp(dY, s.dY);
+  if (trial_costs) {
+    for (int ai = 0; ai < na; ++ai) {
+      ip_forward(s, alphas[ai], trial);
+      trial_costs[ai * 4 + 0] = trial.success ? 1.0 : 0.0;
+      trial_costs[ai * 4 + 1] = trial.cost;
+      trial_costs[ai * 4 + 2] = trial.merit;
+      trial_costs[ai * 4 + 3] = trial.theta;
+    }
+  }
+  if (scalars) {
+    const double tau_b = std::max(io->min_fraction_to_boundary, 1.0 - s.mu);
+    double apm = 1.0, adm = 1.0;
+    for (size_t q = 0; q < s.dS.size(); ++q) {
+      if (s.dS[q] < 0.0) apm = std::min(apm, -tau_b * s.S[q] / s.dS[q]);
+      if (s.dY[q] < 0.0) adm = std::min(adm, -tau_b * s.Y[q] / s.dY[q]);
+    }
+    scalars[0] = s.mu; scalars[1] = s.cost; scalars[2] = s.merit; scalars[3] = s.inf_pr; scalars[4] = s.inf_du;
+    scalars[5] = s.inf_comp; scalars[6] = s.step_norm; scalars[7] = s.reg; scalars[8] = s.dV[0]; scalars[9] = s.dV[1];
+    scalars[10] = clampd(apm, 0.0, 1.0); scalars[11] = clampd(adm, 0.0, 1.0); scalars[12] = s.filter_theta;
+    scalars[13] = s.theta; scalars[14] = (double)s.filter.size(); scalars[15] = ok ? 1.0 : 0.0;
+  }
 }
 
 int oracle_hardware_threads(void) {

@@ -153,6 +153,92 @@ void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int ba
                         const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
                         oracle_result *res);
 
+/* ---------------------------------------------------------------------------------------------
+ * IPDDP (src/cddp_core/ipddp_solver.cpp): cold start, use_ilqr = true, path inequality constraints, no
+ * terminal constraints.  Same parity status as above ("parity unpinned").
+ * ------------------------------------------------------------------------------------------- */
+/* path-constraint kinds (include/cddp-cpp/cddp_core/constraint.hpp) */
+enum { ORACLE_CON_CONTROL_BOX = 0, ORACLE_CON_STATE_BOX = 1, ORACLE_CON_BALL = 2, ORACLE_CON_LINEAR = 3 };
+enum { ORACLE_BARRIER_ADAPTIVE = 0, ORACLE_BARRIER_MONOTONIC = 1, ORACLE_BARRIER_IPOPT = 2 };
+#define ORACLE_IPDDP_HISTORY_COLS 9 /* objective, merit, alpha_pr, alpha_du, inf_du, inf_pr, inf_comp, reg, mu */
+
+/* One entry of the path-constraint set; pass the entries in the order the reference iterates them (a
+ * std::map keyed by constraint name: alphabetical).  Same layout as cddp_b200_constraint.
+ *   CONTROL_BOX / STATE_BOX: p0 = lower [m|n], p1 = upper [m|n]            (constraint.hpp:144-251)
+ *   BALL: rows = dim of the centre, p0 = centre [rows], p1 = &radius       (:320-440)
+ *   LINEAR: rows, p0 = A [rows][n], p1 = b [rows]; scale is ignored        (:253-318) */
+typedef struct {
+  int type;
+  int rows;
+  double scale; /* scale_factor */
+  const double *p0;
+  const double *p1;
+} oracle_constraint;
+
+/* options.hpp:75-104 (barrier, filter) and :148-186 (IPDDPAlgorithmOptions); same layout as cddp_b200_ipddp_options */
+typedef struct {
+  double dual_var_init_scale;            /* 1e-1 */
+  double slack_var_init_scale;           /* 1e-2 */
+  double barrier_tol_mult;               /* 0.1 */
+  double barrier_update_dual_weight;     /* 0.01 */
+  double mu_kappa_epsilon;               /* 10 */
+  double theta_0_floor;                  /* 1 */
+  double mu_initial;                     /* 1 */
+  double mu_min_value;                   /* 1e-10 */
+  double mu_update_factor;               /* 0.5 */
+  double mu_update_power;                /* 1.2 */
+  double min_fraction_to_boundary;       /* 0.99 */
+  double merit_acceptance_threshold;     /* filter 1e-6 */
+  double violation_acceptance_threshold; /* 1e-6 */
+  double max_violation_threshold;        /* 1e4 */
+  double min_violation_for_armijo_check; /* 1e-7 */
+  int theta_norm_l2;                     /* 0 = "l1" */
+  int max_filter_size;                   /* 5 */
+  int barrier_strategy;                  /* ADAPTIVE */
+  int reserved;
+} oracle_ipddp_options;
+
+typedef struct {
+  double final_objective;
+  double final_step_length; /* alpha_pr_ */
+  double final_regularization;
+  double inf_du;
+  double inf_pr;
+  double inf_comp;
+  double mu;
+  double merit;
+  int iterations;
+  int status;
+  int history_len;
+  int dual_dim;
+} oracle_ipddp_result;
+
+void oracle_ipddp_default_options(oracle_ipddp_options *io);
+int oracle_total_dual_dim(const oracle_problem *p, const oracle_constraint *cs, int nc);
+/* g(x,u) - upper [d], Gx [d][n], Gu [d][m] of the stacked constraint set */
+void oracle_eval_constraints(const oracle_problem *p, const oracle_constraint *cs, int nc, const double *x,
+                             const double *u, double *g, double *Gx, double *Gu);
+/* CDDP::solve("IPDDP") for one instance.  U in = initial controls (X is re-rolled out, :876-882), X,U out;
+ * K [N][m][n]; Y,S [N][d] (optional); history [max_iterations+1][ORACLE_IPDDP_HISTORY_COLS] (optional). */
+void oracle_ipddp_solve(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                        const oracle_constraint *cs, int nc, const double *x0, const double *xref,
+                        const double *ref_traj, double *X, double *U, double *K, double *Y, double *S,
+                        oracle_ipddp_result *res, double *history);
+void oracle_ipddp_solve_batch(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                              const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0,
+                              const double *xref, const double *ref_traj, double *X, double *U, double *K, double *Y,
+                              double *S, oracle_ipddp_result *res);
+/* white-box single steps for per-step parity: state in/out through flat arrays.
+ * oracle_ipddp_step runs initialize + `iters` full iterations and then ONE backward pass, returning every
+ * intermediate the CUDA path exposes. */
+void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                        const oracle_constraint *cs, int nc, const double *x0, const double *xref,
+                        const double *ref_traj, const double *U0, int iters, double *X, double *U, double *Y, double *S,
+                        double *G, double *ku, double *Ku, double *ky, double *Ky, double *ks, double *Ks, double *dS,
+                        double *dY, double *scalars /* [16]: mu, cost, merit, inf_pr, inf_du, inf_comp, step_norm, reg,
+                        dV0, dV1, alpha_pr_max, alpha_du_max, filter_theta, theta, filter_size, bw_ok */,
+                        double *trial_costs /* [num_alphas][4]: success, cost, merit, theta of every alpha */);
+
 int oracle_hardware_threads(void);
 const char *oracle_status_string(int status);
 

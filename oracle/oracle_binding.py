@@ -279,3 +279,153 @@ def solve_batch(P, opts, x0, xref, X0, U0, ref_traj=None, nthreads=1):
 
 def hardware_threads() -> int:
     return int(load().oracle_hardware_threads())
+
+
+# ------------------------------------------------------------------------------------------------
+# IPDDP (src/cddp_core/ipddp_solver.cpp): cold start, path inequality constraints
+# ------------------------------------------------------------------------------------------------
+CONSTRAINT_TYPES = {"control_box": 0, "state_box": 1, "ball": 2, "linear": 3}
+DEFAULT_CONSTRAINT_NAMES = {"control_box": "ControlConstraint", "state_box": "StateConstraint", "ball": "BallConstraint",
+                            "linear": "LinearConstraint"}
+IPDDP_HISTORY_COLS = 9
+
+
+class Constraint(C.Structure):
+    _fields_ = [("type", C.c_int), ("rows", C.c_int), ("scale", C.c_double), ("p0", C.POINTER(C.c_double)),
+                ("p1", C.POINTER(C.c_double))]
+
+
+class IpddpOptions(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "dual_var_init_scale", "slack_var_init_scale", "barrier_tol_mult", "barrier_update_dual_weight",
+        "mu_kappa_epsilon", "theta_0_floor", "mu_initial", "mu_min_value", "mu_update_factor", "mu_update_power",
+        "min_fraction_to_boundary", "merit_acceptance_threshold", "violation_acceptance_threshold",
+        "max_violation_threshold", "min_violation_for_armijo_check")] + [
+        ("theta_norm_l2", C.c_int), ("max_filter_size", C.c_int), ("barrier_strategy", C.c_int), ("reserved", C.c_int)]
+
+
+class IpddpResult(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("final_objective", "final_step_length", "final_regularization", "inf_du",
+                                          "inf_pr", "inf_comp", "mu", "merit")] + [
+        ("iterations", C.c_int), ("status", C.c_int), ("history_len", C.c_int), ("dual_dim", C.c_int)]
+
+
+def sort_constraints(constraints):
+    """The reference keeps path constraints in a std::map keyed by name and iterates it in key order
+    (cddp_core.hpp:420-423, ipddp_solver.cpp:1375-1390): sort the same way."""
+    return sorted(constraints, key=lambda c: c.get("name", DEFAULT_CONSTRAINT_NAMES[c["type"]]))
+
+
+class ConstraintSet:
+    """ctypes array of oracle_constraint / cddp_b200_constraint (identical layouts) built from a list of dicts:
+    {'type': 'control_box'|'state_box', 'lb': [...], 'ub': [...], 'scale': 1.0}
+    {'type': 'ball', 'center': [...], 'radius': r, 'scale': 1.0}   {'type': 'linear', 'A': [[...]], 'b': [...]}"""
+
+    def __init__(self, constraints, struct=Constraint):
+        cs = sort_constraints(list(constraints or []))
+        self.constraints = cs
+        self.nc = len(cs)
+        self._keep = []
+        arr = (struct * max(self.nc, 1))()
+        dp = C.POINTER(C.c_double)
+        for i, c in enumerate(cs):
+            t = c["type"]
+            arr[i].type = CONSTRAINT_TYPES[t]
+            arr[i].scale = float(c.get("scale", 1.0))
+            if t in ("control_box", "state_box"):
+                a0, a1 = _f64(c["lb"]), _f64(c["ub"])
+                arr[i].rows = a0.shape[0]
+            elif t == "ball":
+                a0, a1 = _f64(c["center"]), _f64([c["radius"]])
+                arr[i].rows = a0.shape[0]
+            else:
+                a0, a1 = _f64(c["A"]), _f64(c["b"])
+                arr[i].rows = a1.shape[0]
+            self._keep += [a0, a1]
+            arr[i].p0 = a0.ctypes.data_as(dp)
+            arr[i].p1 = a1.ctypes.data_as(dp)
+        self.array = arr
+
+    def dual_dim(self, n, m):
+        d = 0
+        for c in self.constraints:
+            d += {"control_box": 2 * m, "state_box": 2 * n, "ball": 1}.get(c["type"], len(np.atleast_1d(c.get("b", []))))
+        return d
+
+
+def make_ipddp_options(**overrides) -> IpddpOptions:
+    io = IpddpOptions()
+    load().oracle_ipddp_default_options(C.byref(io))
+    for k, v in overrides.items():
+        if not hasattr(io, k):
+            raise AttributeError(k)
+        setattr(io, k, v)
+    return io
+
+
+def eval_constraints(P, cset: ConstraintSet, x, u):
+    x, u = _f64(x), _f64(u)
+    d = cset.dual_dim(P.n, P.m)
+    g, Gx, Gu = np.zeros(d), np.zeros((d, P.n)), np.zeros((d, P.m))
+    load().oracle_eval_constraints(P.ref, cset.array, cset.nc, _p(x), _p(u), _p(g), _p(Gx), _p(Gu))
+    return g, Gx, Gu
+
+
+def ipddp_solve(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_traj=None, history=False):
+    x0, xref = _f64(x0), _f64(xref)
+    d = cset.dual_dim(P.n, P.m)
+    X, U = np.zeros((P.N + 1, P.n)), _f64(U0).copy()
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K = np.zeros((P.N, P.m, P.n))
+    Y, S = np.zeros((P.N, max(d, 1))), np.zeros((P.N, max(d, 1)))
+    res = IpddpResult()
+    hist = np.zeros((opts.max_iterations + 1, IPDDP_HISTORY_COLS)) if history else None
+    load().oracle_ipddp_solve(P.ref, C.byref(opts), C.byref(iopts), cset.array, cset.nc, _p(x0), _p(xref), _p(rt), _p(X),
+                              _p(U), _p(K), _p(Y), _p(S), C.byref(res), _p(hist))
+    out = dict(X=X, U=U, K=K, Y=Y[:, :d], S=S[:, :d], cost=res.final_objective, alpha=res.final_step_length,
+               reg=res.final_regularization, inf_du=res.inf_du, inf_pr=res.inf_pr, inf_comp=res.inf_comp, mu=res.mu,
+               merit=res.merit, iterations=res.iterations, status=res.status)
+    if history:
+        out["history"] = hist[: res.history_len].copy()
+    return out
+
+
+def ipddp_solve_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_traj=None, nthreads=1):
+    x0, xref = _f64(x0), _f64(xref)
+    B = x0.shape[0]
+    d = cset.dual_dim(P.n, P.m)
+    X, U = np.zeros((B, P.N + 1, P.n)), _f64(U0).copy()
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K = np.zeros((B, P.N, P.m, P.n))
+    Y, S = np.zeros((B, P.N, d)), np.zeros((B, P.N, d))
+    res = (IpddpResult * B)()
+    load().oracle_ipddp_solve_batch(P.ref, C.byref(opts), C.byref(iopts), cset.array, cset.nc, B, int(nthreads), _p(x0),
+                                    _p(xref), _p(rt), _p(X), _p(U), _p(K), _p(Y) if d else None, _p(S) if d else None, res)
+    f = lambda k, dt=np.float64: np.array([getattr(r, k) for r in res], dtype=dt)  # noqa: E731
+    return dict(X=X, U=U, K=K, Y=Y, S=S, cost=f("final_objective"), alpha=f("final_step_length"),
+                reg=f("final_regularization"), inf_du=f("inf_du"), inf_pr=f("inf_pr"), inf_comp=f("inf_comp"), mu=f("mu"),
+                merit=f("merit"), iterations=f("iterations", np.int32), status=f("status", np.int32))
+
+
+def ipddp_probe(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, iters, ref_traj=None):
+    """initialize + `iters` full iterations + ONE backward pass; returns every intermediate (white box)."""
+    x0, xref, U0 = _f64(x0), _f64(xref), _f64(U0)
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    N, n, m, d = P.N, P.n, P.m, cset.dual_dim(P.n, P.m)
+    dd = max(d, 1)
+    z = lambda *s: np.zeros(s)  # noqa: E731
+    out = dict(X=z(N + 1, n), U=z(N, m), Y=z(N, dd), S=z(N, dd), G=z(N, dd), ku=z(N, m), Ku=z(N, m, n), ky=z(N, dd),
+               Ky=z(N, dd, n), ks=z(N, dd), Ks=z(N, dd, n), dS=z(N, dd), dY=z(N, dd))
+    scal = np.zeros(16)
+    na = len(build_alphas(opts))
+    trial = np.zeros((na, 4))
+    load().oracle_ipddp_probe(P.ref, C.byref(opts), C.byref(iopts), cset.array, cset.nc, _p(x0), _p(xref), _p(rt), _p(U0),
+                              int(iters), *[_p(out[k]) for k in ("X", "U", "Y", "S", "G", "ku", "Ku", "ky", "Ky", "ks", "Ks",
+                                                                 "dS", "dY")], _p(scal), _p(trial))
+    names = ("mu", "cost", "merit", "inf_pr", "inf_du", "inf_comp", "step_norm", "reg", "dV0", "dV1", "alpha_pr_max",
+             "alpha_du_max", "filter_theta", "theta", "filter_size", "bw_ok")
+    out.update({k: scal[i] for i, k in enumerate(names)})
+    out["trial"] = trial
+    for k in ("Y", "S", "G", "ky", "Ky", "ks", "Ks", "dS", "dY"):
+        out[k] = out[k][:, :d]
+    return out
