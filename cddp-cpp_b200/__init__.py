@@ -83,6 +83,30 @@ class Problem(C.Structure):
     ]
 
 
+class Constraint(C.Structure):
+    """cddp_b200_constraint — one entry of the IPDDP path-constraint set."""
+
+    _fields_ = [("type", C.c_int), ("rows", C.c_int), ("scale", C.c_double), ("p0", C.POINTER(C.c_double)),
+                ("p1", C.POINTER(C.c_double))]
+
+
+class IpddpOptions(C.Structure):
+    """cddp_b200_ipddp_options — CDDPOptions::ipddp + ::filter (options.hpp:75-104, :148-186)."""
+
+    _fields_ = [(k, C.c_double) for k in (
+        "dual_var_init_scale", "slack_var_init_scale", "barrier_tol_mult", "barrier_update_dual_weight",
+        "mu_kappa_epsilon", "theta_0_floor", "mu_initial", "mu_min_value", "mu_update_factor", "mu_update_power",
+        "min_fraction_to_boundary", "merit_acceptance_threshold", "violation_acceptance_threshold",
+        "max_violation_threshold", "min_violation_for_armijo_check")] + [
+        ("theta_norm_l2", C.c_int), ("max_filter_size", C.c_int), ("barrier_strategy", C.c_int), ("reserved", C.c_int)]
+
+
+CONSTRAINT_TYPES = {"control_box": 0, "state_box": 1, "ball": 2, "linear": 3}
+DEFAULT_CONSTRAINT_NAMES = {"control_box": "ControlConstraint", "state_box": "StateConstraint", "ball": "BallConstraint",
+                            "linear": "LinearConstraint"}
+IPDDP_HISTORY_COLS = 9
+
+
 class Timing(C.Structure):
     _fields_ = [
         ("linearize_ms", C.c_double),
@@ -109,6 +133,9 @@ ABI_SYMBOLS = [
     "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host", "cddp_b200_set_record_layout",
     "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_get_solution_async",
     "cddp_b200_mpc_advance", "cddp_b200_get_first_controls_async",
+    "cddp_b200_ipddp_default_options", "cddp_b200_ipddp_create", "cddp_b200_ipddp_dual_dim",
+    "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
+    "cddp_b200_ipddp_get_history",
 ]
 
 
@@ -174,10 +201,19 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_enable_timing.argtypes = [vp, C.c_int]
     lib.cddp_b200_backward_algorithmic_bytes.argtypes = [vp, dp]
     lib.cddp_b200_solve_host.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int, C.c_int] + [vp] * 12
+    lib.cddp_b200_ipddp_default_options.restype = None
+    lib.cddp_b200_ipddp_default_options.argtypes = [C.POINTER(IpddpOptions)]
+    lib.cddp_b200_ipddp_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(IpddpOptions), vp, C.c_int,
+                                           C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cddp_b200_ipddp_dual_dim.argtypes = [vp, ip]
+    lib.cddp_b200_ipddp_get_solution.argtypes = [vp, vp, vp, vp, vp]
+    lib.cddp_b200_ipddp_get_gains.argtypes = [vp, vp, vp, vp, vp]
+    lib.cddp_b200_ipddp_get_line_search.argtypes = [vp, vp]
+    lib.cddp_b200_ipddp_get_history.argtypes = [vp, vp, vp]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("cddp_b200_error_string", "cddp_b200_last_cuda_error", "cddp_b200_status_string",
-                        "cddp_b200_default_options"):
+                        "cddp_b200_default_options", "cddp_b200_ipddp_default_options"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -456,6 +492,92 @@ class BatchedCLDDP:
         v = C.c_double(0.0)
         _check(self.lib.cddp_b200_backward_algorithmic_bytes(self.handle, C.byref(v)))
         return v.value
+
+
+def default_ipddp_options(**overrides) -> IpddpOptions:
+    io = IpddpOptions()
+    load_library().cddp_b200_ipddp_default_options(C.byref(io))
+    for k, v in overrides.items():
+        if not hasattr(io, k):
+            raise AttributeError(f"unknown IPDDP option {k}")
+        setattr(io, k, v)
+    return io
+
+
+class ConstraintSet:
+    """Array of cddp_b200_constraint from a list of dicts, sorted by constraint name like the reference's std::map
+    (cddp_core.hpp:420-423):  {'type': 'control_box'|'state_box', 'lb', 'ub', 'scale'} | {'type': 'ball', 'center',
+    'radius', 'scale'} | {'type': 'linear', 'A', 'b'}; optional 'name' overrides the class's default name."""
+
+    def __init__(self, constraints):
+        cs = sorted(list(constraints or []), key=lambda c: c.get("name", DEFAULT_CONSTRAINT_NAMES[c["type"]]))
+        self.constraints, self.nc, self._keep = cs, len(cs), []
+        arr = (Constraint * max(self.nc, 1))()
+        dp = C.POINTER(C.c_double)
+        for i, c in enumerate(cs):
+            t = c["type"]
+            arr[i].type = CONSTRAINT_TYPES[t]
+            arr[i].scale = float(c.get("scale", 1.0))
+            if t in ("control_box", "state_box"):
+                a0, a1 = _f64(c["lb"]), _f64(c["ub"])
+                arr[i].rows = a0.shape[0]
+            elif t == "ball":
+                a0, a1 = _f64(c["center"]), _f64([c["radius"]])
+                arr[i].rows = a0.shape[0]
+            else:
+                a0, a1 = _f64(c["A"]), _f64(c["b"])
+                arr[i].rows = a1.shape[0]
+            self._keep += [a0, a1]
+            arr[i].p0, arr[i].p1 = a0.ctypes.data_as(dp), a1.ctypes.data_as(dp)
+        self.array = arr
+
+
+class BatchedIPDDP(BatchedCLDDP):
+    """IPDDP handle (cddp_b200_ipddp_create): same driving entry points as BatchedCLDDP plus the interior-point results."""
+
+    def __init__(self, spec: dict, opts: Options, ipddp_opts: IpddpOptions, constraints, batch: int, device: int = 0):
+        self.lib = load_library()
+        self.pspec = ProblemSpec(dict(spec, lb=None, ub=None))
+        self.opts, self.ipddp_opts = opts, ipddp_opts
+        self.cset = constraints if isinstance(constraints, ConstraintSet) else ConstraintSet(constraints)
+        self.B, self.n, self.m, self.N = int(batch), self.pspec.n, self.pspec.m, self.pspec.N
+        self.handle = C.c_void_p()
+        _check(self.lib.cddp_b200_ipddp_create(C.byref(self.pspec.struct), C.byref(opts), C.byref(ipddp_opts), self.cset.array,
+                                               self.cset.nc, self.B, device, C.byref(self.handle)))
+        self.num_alphas = len(build_alphas(opts))
+        d = C.c_int(0)
+        _check(self.lib.cddp_b200_ipddp_dual_dim(self.handle, C.byref(d)))
+        self.d = d.value
+        self._keep = []
+
+    def get_ipddp_solution(self, trajectories: bool = True) -> dict:
+        B, N, d = self.B, self.N, self.d
+        out = {"Y": np.zeros((B, N, d)), "S": np.zeros((B, N, d)), "G": np.zeros((B, N, d))} if trajectories else {}
+        sc = np.empty((B, 8))
+        _check(self.lib.cddp_b200_ipddp_get_solution(self.handle, _ptr(out.get("Y")) if d else None,
+                                                     _ptr(out.get("S")) if d else None, _ptr(out.get("G")) if d else None,
+                                                     _ptr(sc)))
+        for i, k in enumerate(("mu", "merit", "inf_pr", "inf_comp", "step_norm", "alpha_du", "alpha_pr_max", "alpha_du_max")):
+            out[k] = sc[:, i].copy()
+        return out
+
+    def get_ipddp_gains(self) -> dict:
+        B, N, d, n = self.B, self.N, self.d, self.n
+        out = {"ky": np.zeros((B, N, d)), "Ky": np.zeros((B, N, d, n)), "ks": np.zeros((B, N, d)), "Ks": np.zeros((B, N, d, n))}
+        _check(self.lib.cddp_b200_ipddp_get_gains(self.handle, _ptr(out["ky"]), _ptr(out["Ky"]), _ptr(out["ks"]), _ptr(out["Ks"])))
+        return out
+
+    def get_line_search(self) -> np.ndarray:
+        t = np.empty((self.B, self.num_alphas, 4))
+        _check(self.lib.cddp_b200_ipddp_get_line_search(self.handle, _ptr(t)))
+        return t
+
+    def get_history(self):
+        cap = self.opts.max_iterations + 1
+        h = np.empty((self.B, cap, IPDDP_HISTORY_COLS))
+        lens = np.empty(self.B, dtype=np.int32)
+        _check(self.lib.cddp_b200_ipddp_get_history(self.handle, _ptr(h), _ptr(lens)))
+        return h, lens
 
 
 def solve_host(spec: dict, opts: Options, x0, xref, X0, U0, ref_traj=None, device: int = 0) -> dict:

@@ -61,6 +61,9 @@ struct cddp_b200_solver {
   std::vector<void *> allocs;
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
   int *didxA = nullptr, *didxB = nullptr;
+  int kind = 0;      // 0 = CLDDP, 1 = IPDDP
+  IpConstants ic{};  // IPDDP: flattened constraint rows + options
+  IpDevice ip{};     // IPDDP: duals, slacks, gains, per-instance barrier/filter state
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
   int poll_interval = -1;  // -1: widening stride (default); 0: never poll (fully asynchronous solve); k > 0: every k iterations
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
@@ -194,14 +197,16 @@ int do_linearize(cddp_b200_solver *s, bool force) {
 }
 int do_backward(cddp_b200_solver *s, int mode) {
   KernelTimer t(s, &s->timing.backward_ms);
-  CU(launch_backward(s->c, s->d, mode, s->stream));
+  if (s->kind == 1) CU(launch_ip_backward(s->c, s->d, s->ic, s->ip, mode, s->stream));
+  else CU(launch_backward(s->c, s->d, mode, s->stream));
   t.stop();
   s->timing.backward_launches++;
   return 0;
 }
 int do_forward(cddp_b200_solver *s, int mode) {
   KernelTimer t(s, &s->timing.forward_ms);
-  CU(launch_forward(s->c, s->d, mode, s->stream));
+  if (s->kind == 1) CU(launch_ip_forward(s->c, s->d, s->ic, s->ip, mode, s->stream));
+  else CU(launch_forward(s->c, s->d, mode, s->stream));
   t.stop();
   s->timing.forward_launches++;
   return 0;
@@ -468,6 +473,7 @@ int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *o) {
 
 int cddp_b200_set_record_layout(cddp_b200_solver *s, int layout) {
   if (!s || (layout != CDDP_B200_RECORDS_DENSE && layout != CDDP_B200_RECORDS_STRUCTURED)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (s->kind == 1 && layout != CDDP_B200_RECORDS_DENSE) return CDDP_B200_ERR_INVALID_ARGUMENT;  // the IPDDP sweep reads dense records
   DeviceGuard g(s->device);
   const bool had = s->initialized;
   int r = apply_layout(s, layout);
@@ -500,7 +506,8 @@ int cddp_b200_initialize(cddp_b200_solver *s) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (!s->have_instances) return CDDP_B200_ERR_STATE;
   DeviceGuard g(s->device);
-  CU(launch_initialize(s->c, s->d, s->stream));
+  if (s->kind == 1) CU(launch_ip_initialize(s->c, s->d, s->ic, s->ip, s->stream));
+  else CU(launch_initialize(s->c, s->d, s->stream));
   s->timing.other_launches++;
   s->initialized = true;
   return 0;
@@ -680,7 +687,7 @@ int cddp_b200_enable_history(cddp_b200_solver *s, int enable) {
     double *h = nullptr;
     int *l = nullptr;
     int r;
-    if ((r = s->alloc(&h, (size_t)s->d.B * cap * 4))) return r;
+    if ((r = s->alloc(&h, (size_t)s->d.B * cap * (s->kind == 1 ? IP_HISTORY_COLS : 4)))) return r;
     if ((r = s->alloc(&l, (size_t)s->d.B))) return r;
     s->d.history = h;
     s->d.history_len = l;
@@ -692,7 +699,7 @@ int cddp_b200_enable_history(cddp_b200_solver *s, int enable) {
 
 int cddp_b200_get_history(cddp_b200_solver *s, double *history, int *lens) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
-  if (!s->d.history) return CDDP_B200_ERR_STATE;
+  if (!s->d.history || s->kind == 1) return CDDP_B200_ERR_STATE;
   DeviceGuard g(s->device);
   int r;
   if ((r = download(s, history, s->d.history, (size_t)s->d.B * s->d.history_cap * 4 * sizeof(double)))) return r;
@@ -806,6 +813,229 @@ int cddp_b200_get_forward(cddp_b200_solver *s, double *costs, int *accepted, dou
     if ((r = download(s, Xnew, s->scratch, nx * sizeof(double)))) return r;
     if ((r = download(s, Unew, s->scratch + nx, nu * sizeof(double)))) return r;
   }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ IPDDP */
+void cddp_b200_ipddp_default_options(cddp_b200_ipddp_options *io) { /* options.hpp:75-104,148-186 */
+  if (!io) return;
+  std::memset(io, 0, sizeof(*io));
+  io->dual_var_init_scale = 1e-1;
+  io->slack_var_init_scale = 1e-2;
+  io->barrier_tol_mult = 0.1;
+  io->barrier_update_dual_weight = 0.01;
+  io->mu_kappa_epsilon = 10.0;
+  io->theta_0_floor = 1.0;
+  io->mu_initial = 1.0;
+  io->mu_min_value = 1e-10;
+  io->mu_update_factor = 0.5;
+  io->mu_update_power = 1.2;
+  io->min_fraction_to_boundary = 0.99;
+  io->merit_acceptance_threshold = 1e-6;
+  io->violation_acceptance_threshold = 1e-6;
+  io->max_violation_threshold = 1e4;
+  io->min_violation_for_armijo_check = 1e-7;
+  io->theta_norm_l2 = 0;
+  io->max_filter_size = 5;
+  io->barrier_strategy = CDDP_B200_BARRIER_ADAPTIVE;
+}
+
+int cddp_b200_ipddp_create(const cddp_b200_problem *p, const cddp_b200_options *o, const cddp_b200_ipddp_options *io,
+                           const cddp_b200_constraint *cs, int nc, int batch, int device, cddp_b200_solver **out) {
+  if (!out) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!p || !o || !io || nc < 0 || (nc > 0 && !cs)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (p->model == CDDP_B200_MODEL_LTI) return CDDP_B200_ERR_UNSUPPORTED_MODEL;
+  if (io->max_filter_size < 1 || io->max_filter_size >= IP_FILTER_CAP) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (count_alphas(*o) > 16) return CDDP_B200_ERR_INVALID_ARGUMENT;  // one lane per alpha, 16 lanes per trajectory
+  const int n = p->n, m = p->m;
+  // flatten the constraint set into rows
+  int D = 0;
+  for (int i = 0; i < nc; ++i) {
+    switch (cs[i].type) {
+      case CDDP_B200_CON_CONTROL_BOX: D += 2 * m; break;
+      case CDDP_B200_CON_STATE_BOX: D += 2 * n; break;
+      case CDDP_B200_CON_BALL:
+        if (cs[i].rows < 1 || cs[i].rows > n) return CDDP_B200_ERR_INVALID_ARGUMENT;
+        D += 1;
+        break;
+      case CDDP_B200_CON_LINEAR:
+        if (cs[i].rows < 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+        D += cs[i].rows;
+        break;
+      default: return CDDP_B200_ERR_INVALID_ARGUMENT;
+    }
+    if (!cs[i].p0 || !cs[i].p1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  }
+  if (D > IP_MAX_DUAL) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  cddp_b200_problem pc = *p;
+  pc.has_control_box = 0;  // IPDDP never clamps (ipddp_solver.cpp:1650-1651); a ControlConstraint is a constraint row pair
+  pc.lb = pc.ub = nullptr;
+  cddp_b200_solver *s = nullptr;
+  int r = cddp_b200_create(&pc, o, batch, device, &s);
+  if (r) return r;
+  DeviceGuard g(device);
+  s->kind = 1;
+  const int Dn = D > 0 ? D : 1;
+  std::vector<int> rt(Dn, 0), bd(Dn, 0);
+  std::vector<double> Gx((size_t)Dn * n, 0.0), Gu((size_t)Dn * m, 0.0), off(Dn, 0.0), sc(Dn, 1.0);
+  int row = 0;
+  for (int i = 0; i < nc; ++i) {
+    const cddp_b200_constraint &C = cs[i];
+    if (C.type == CDDP_B200_CON_CONTROL_BOX || C.type == CDDP_B200_CON_STATE_BOX) {  // constraint.hpp:144-217
+      const bool ctrl = C.type == CDDP_B200_CON_CONTROL_BOX;
+      const int k = ctrl ? m : n;
+      for (int j = 0; j < k; ++j) {
+        for (int half = 0; half < 2; ++half) {
+          const int rr = row + half * k + j;
+          rt[rr] = ctrl ? IP_ROW_CONTROL : IP_ROW_STATE;
+          sc[rr] = C.scale;
+          const double sgn = half ? 1.0 : -1.0;
+          if (ctrl) Gu[(size_t)rr * m + j] = sgn * C.scale;
+          else Gx[(size_t)rr * n + j] = sgn * C.scale;
+          off[rr] = half ? C.p1[j] * C.scale : -C.p0[j] * C.scale;  // ip_upper_bound_ (:156-159)
+        }
+      }
+      row += 2 * k;
+    } else if (C.type == CDDP_B200_CON_BALL) {  // constraint.hpp:320-373
+      rt[row] = IP_ROW_BALL;
+      bd[row] = C.rows;
+      sc[row] = C.scale;
+      off[row] = C.p1[0];
+      for (int j = 0; j < C.rows; ++j) Gx[(size_t)row * n + j] = C.p0[j];
+      row += 1;
+    } else {  // LinearConstraint (:253-284)
+      for (int q = 0; q < C.rows; ++q) {
+        rt[row + q] = IP_ROW_STATE;
+        sc[row + q] = C.scale;
+        off[row + q] = C.p1[q];
+        for (int j = 0; j < n; ++j) Gx[(size_t)(row + q) * n + j] = C.p0[(size_t)q * n + j];
+      }
+      row += C.rows;
+    }
+  }
+  int *drt = nullptr, *dbd = nullptr;
+  double *dGx = nullptr, *dGu = nullptr, *doff = nullptr, *dsc = nullptr;
+  IpDevice &ip = s->ip;
+  const size_t B = batch, N = p->horizon, Dd = Dn;
+#define AL(ptr, cnt)                     \
+  do {                                   \
+    if ((r = s->alloc(&(ptr), (cnt)))) { \
+      cddp_b200_destroy(s);              \
+      return r;                          \
+    }                                    \
+  } while (0)
+  AL(drt, Dd); AL(dbd, Dd); AL(dGx, Dd * n); AL(dGu, Dd * m); AL(doff, Dd); AL(dsc, Dd);
+  for (int q = 0; q < 2; ++q) { AL(ip.Y[q], B * N * Dd); AL(ip.S[q], B * N * Dd); AL(ip.G[q], B * N * Dd); }
+  AL(ip.ky, B * N * Dd); AL(ip.ks, B * N * Dd); AL(ip.Ky, B * N * Dd * n); AL(ip.Ks, B * N * Dd * n);
+  AL(ip.mu, B); AL(ip.merit, B); AL(ip.logsum, B); AL(ip.filter_theta, B); AL(ip.inf_pr, B); AL(ip.inf_comp, B);
+  AL(ip.step_norm, B); AL(ip.alpha_du, B); AL(ip.apm, B); AL(ip.adm, B);
+  AL(ip.filter, B * IP_FILTER_CAP * 2); AL(ip.filter_size, B); AL(ip.ls_stats, B * CDDP_B200_MAX_ALPHAS * 4);
+#undef AL
+  cudaError_t e = cudaMemcpy(drt, rt.data(), Dd * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dbd, bd.data(), Dd * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dGx, Gx.data(), Gx.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dGu, Gu.data(), Gu.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(doff, off.data(), Dd * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dsc, sc.data(), Dd * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(ip.filter_size, 0, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ip.ls_stats, 0, B * CDDP_B200_MAX_ALPHAS * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.ky, 0, B * N * Dd * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.ks, 0, B * N * Dd * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.Ky, 0, B * N * Dd * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.Ks, 0, B * N * Dd * n * sizeof(double));
+  if (e != cudaSuccess) { cddp_b200_destroy(s); return cuda_fail(e, "ipddp setup"); }
+  s->ic.d = D; s->ic.nc = nc;
+  s->ic.row_type = drt; s->ic.row_bdim = dbd; s->ic.Gx = dGx; s->ic.Gu = dGu; s->ic.off = doff; s->ic.scale = dsc;
+  s->ic.io = *io;
+  if ((r = apply_layout(s, RECORDS_DENSE))) { cddp_b200_destroy(s); return r; }
+  *out = s;
+  return 0;
+}
+
+int cddp_b200_ipddp_dual_dim(cddp_b200_solver *s, int *d) {
+  if (!s || !d) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  *d = s->kind == 1 ? s->ic.d : 0;
+  return 0;
+}
+
+namespace {
+// gather a [B][N][d(*n)] double-buffered array of the CURRENT nominal into contiguous scratch: done on the host side of
+// the copy by reading both buffers and selecting per instance (cur is tiny)
+int download_current(cddp_b200_solver *s, double *dst, double *const buf[2], size_t per_instance) {
+  if (!dst) return 0;
+  const size_t B = s->d.B;
+  std::vector<int> cur(B);
+  CU(cudaMemcpyAsync(cur.data(), s->d.cur, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (size_t b = 0; b < B; ++b)
+    CU(cudaMemcpyAsync(dst + b * per_instance, buf[cur[b]] + b * per_instance, per_instance * sizeof(double),
+                       cudaMemcpyDeviceToHost, s->stream));
+  return 0;
+}
+}  // namespace
+
+int cddp_b200_ipddp_get_solution(cddp_b200_solver *s, double *Y, double *S, double *G, double *scalars) {
+  if (!s || s->kind != 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const size_t B = s->d.B, per = (size_t)s->d.N * s->ic.d;
+  int r;
+  if (per) {
+    if ((r = download_current(s, Y, s->ip.Y, per))) return r;
+    if ((r = download_current(s, S, s->ip.S, per))) return r;
+    if ((r = download_current(s, G, s->ip.G, per))) return r;
+  }
+  if (scalars) {
+    std::vector<double> tmp(8 * B);
+    double *src[8] = {s->ip.mu, s->ip.merit, s->ip.inf_pr, s->ip.inf_comp, s->ip.step_norm, s->ip.alpha_du, s->ip.apm, s->ip.adm};
+    for (int k = 0; k < 8; ++k)
+      if ((r = download(s, tmp.data() + k * B, src[k], B * sizeof(double)))) return r;
+    CU(cudaStreamSynchronize(s->stream));
+    for (size_t b = 0; b < B; ++b)
+      for (int k = 0; k < 8; ++k) scalars[b * 8 + k] = tmp[k * B + b];
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_ipddp_get_gains(cddp_b200_solver *s, double *ky, double *Ky, double *ks, double *Ks) {
+  if (!s || s->kind != 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const size_t cnt = (size_t)s->d.B * s->d.N * s->ic.d;
+  int r;
+  if (cnt) {
+    if ((r = download(s, ky, s->ip.ky, cnt * sizeof(double)))) return r;
+    if ((r = download(s, ks, s->ip.ks, cnt * sizeof(double)))) return r;
+    if ((r = download(s, Ky, s->ip.Ky, cnt * s->d.n * sizeof(double)))) return r;
+    if ((r = download(s, Ks, s->ip.Ks, cnt * s->d.n * sizeof(double)))) return r;
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_ipddp_get_line_search(cddp_b200_solver *s, double *table) {
+  if (!s || s->kind != 1 || !table) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const size_t B = s->d.B;
+  std::vector<double> tmp(B * CDDP_B200_MAX_ALPHAS * 4);
+  int r;
+  if ((r = download(s, tmp.data(), s->ip.ls_stats, tmp.size() * sizeof(double)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
+  const int na = s->c.num_alphas;
+  for (size_t b = 0; b < B; ++b)
+    for (int a = 0; a < na; ++a)
+      for (int k = 0; k < 4; ++k) table[(b * na + a) * 4 + k] = tmp[(b * CDDP_B200_MAX_ALPHAS + a) * 4 + k];
+  return 0;
+}
+
+int cddp_b200_ipddp_get_history(cddp_b200_solver *s, double *history, int *lens) {
+  if (!s || s->kind != 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->d.history) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  int r;
+  if ((r = download(s, history, s->d.history, (size_t)s->d.B * s->d.history_cap * IP_HISTORY_COLS * sizeof(double)))) return r;
+  if ((r = download(s, lens, s->d.history_len, (size_t)s->d.B * sizeof(int)))) return r;
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }

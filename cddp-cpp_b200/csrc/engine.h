@@ -78,6 +78,37 @@ struct Constants {
 
 enum RecordLayoutKind { RECORDS_DENSE = 0, RECORDS_STRUCTURED = 1 };
 
+// ---- IPDDP (ipddp.cu) ----
+// The path-constraint set flattened to rows: g_r(x,u) = a_r . x - off_r (STATE rows: StateConstraint, LinearConstraint),
+// a_r . u - off_r (CONTROL rows: ControlConstraint) or -scale |x[0:bdim] - centre|^2 + scale radius^2 (BALL rows).
+enum { IP_ROW_STATE = 0, IP_ROW_CONTROL = 1, IP_ROW_BALL = 2 };
+constexpr int IP_FILTER_CAP = 8;
+constexpr int IP_HISTORY_COLS = 9;  // objective, merit, alpha_pr, alpha_du, inf_du, inf_pr, inf_comp, reg, mu
+constexpr int IP_MAX_DUAL = 48;
+
+struct IpConstants {
+  int d;   // total dual dimension (rows)
+  int nc;  // number of constraints in the set (0 = unconstrained branch)
+  const int *row_type;   // device [d]
+  const int *row_bdim;   // device [d]  ball: dimension of the centre
+  const double *Gx;      // device [d][n]  STATE rows: dg/dx; BALL rows: centre in the first bdim entries
+  const double *Gu;      // device [d][m]  CONTROL rows: dg/du
+  const double *off;     // device [d]  affine rows: upper bound; BALL rows: radius
+  const double *scale;   // device [d]
+  cddp_b200_ipddp_options io;
+};
+
+struct IpDevice {
+  double *Y[2], *S[2], *G[2];  // [B][N][d] duals, slacks, constraint values; double-buffered like X/U (cur[b] selects)
+  double *ky, *ks;             // [B][N][d]
+  double *Ky, *Ks;             // [B][N][d][n]
+  // per-instance scalars
+  double *mu, *merit, *logsum, *filter_theta, *inf_pr, *inf_comp, *step_norm, *alpha_du, *apm, *adm;
+  double *filter;    // [B][IP_FILTER_CAP][2] (merit, theta)
+  int *filter_size;  // [B]
+  double *ls_stats;  // [B][CDDP_B200_MAX_ALPHAS][4] success, cost, merit, theta of every line-search candidate
+};
+
 enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };
 enum ForwardMode { FW_EVALUATE = 0 /* do not apply */, FW_ITERATE = 1 };
 
@@ -94,6 +125,12 @@ cudaError_t launch_unpack_linearization(const Constants &c, const DeviceState &d
                                         cudaStream_t st);
 cudaError_t launch_pack_linearization(const Constants &c, const DeviceState &d, const double *A, const double *Bm,
                                       cudaStream_t st);
+cudaError_t launch_ip_initialize(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
+                                 cudaStream_t st);
+cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                               cudaStream_t st);
+cudaError_t launch_ip_forward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                              cudaStream_t st);
 cudaError_t launch_gather_current(const Constants &c, const DeviceState &d, double *X, double *U, int which,
                                   cudaStream_t st);
 

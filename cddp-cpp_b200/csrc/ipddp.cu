@@ -1,0 +1,1109 @@
+// Batched IPDDP (interior-point DDP) on the device: backward sweep with the primal-dual condensation of the path
+// inequality constraints, forward rollout with parallel line-search alphas and the filter acceptance test, barrier
+// update and convergence tests — one DDP iteration = linearize_kernel (linearize.cu, shared with CLDDP) +
+// ip_backward_kernel + ip_forward_kernel.
+//
+// Reference behaviour followed (astomodynamics/cddp-cpp @ f71fa80), options.warm_start = false, use_ilqr = true
+// (the defaults, options.hpp:223,230), path inequality constraints only (no terminal constraints):
+//   IPDDPSolver::initialize (cold start)              src/cddp_core/ipddp_solver.cpp:818-913
+//   evaluateTrajectory / initializeDualSlackVariables  :2252-2296, :2428-2482
+//   backwardPass, unconstrained branch                 :1055-1118
+//   backwardPass, path-constraint branch               :1355-1569 (+ rolloutLinearPolicy :368-392)
+//   computeMaxStepSizes                                :2939-2988
+//   forwardPass (+ filter acceptance)                  :1571-1876
+//   applyForwardPassResult / updateBarrierParameters   :1878-1951, :2548-2660
+//   checkEarlyConvergence / checkConvergence           :925-958, :1953-2025
+//   handleForwardPassFailure                           :2037-2082
+//   computeTheta / computeBarrierMerit / computePrimalAndComplementarity  :2778-2937
+//   filter helpers                                     src/cddp_core/interior_point_utils.cpp:81-141
+//   constraints                                        include/cddp-cpp/cddp_core/constraint.hpp:144-440
+//   outer loop                                         src/cddp_core/cddp_solver_base.cpp:29-186
+// The costate bookkeeping (Lambda_, k_lambda_, K_lambda_) only feeds an allFinite() test in the reference
+// (:1612-1618, :1665-1671) and is not carried.
+//
+// Deliberate numerical differences (DESIGN.md "Numerics"): the barrier merit and theta sums run over (t, row) in
+// time-major order (the reference sums constraint-major over a std::map of trajectories) and the merit after a
+// barrier update is formed as cost - mu * sum(log s) from the carried log-sum; both are reorderings of the same
+// sums.  Eigen::LDLT (diagonal pivoting) is followed literally (ldlt_small below), because unlike a Cholesky
+// factorisation it does not reject indefinite matrices and the reference relies on that (:1431-1435).
+#include "engine.h"
+
+namespace cddp_b200 {
+
+namespace {
+
+constexpr double kSlackInteriorOffset = 1e-4;  // ipddp_solver.cpp:35-38
+constexpr double EPS_SLACK = 1e-10;
+constexpr double MAX_BARRIER_RATIO = 1e6;
+
+__device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ double clip_pos(double num, double den) { return clampd(num / den, 0.0, MAX_BARRIER_RATIO); }
+__device__ __forceinline__ double clip_signed(double num, double den) {
+  return clampd(num / den, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+}
+__device__ __forceinline__ bool finite_d(double v) { return fabs(v) < pos_inf(); }
+
+__device__ __forceinline__ const double *ref_ptr(const DeviceState &d, int b, int t) {
+  return d.ref_traj ? d.ref_traj + ((size_t)b * (d.N + 1) + t) * d.n : d.xref + (size_t)b * d.n;
+}
+
+// g_r(x,u) = constraint.evaluate(x,u) - getUpperBound() for row r of the stacked set (ipddp_solver.cpp:2273-2278)
+__device__ __forceinline__ double con_value(const IpConstants &ic, int r, int n, int m, const double *x, const double *u) {
+  const int ty = ic.row_type[r];
+  if (ty == IP_ROW_BALL) {  // constraint.hpp:326-343
+    const int bd = ic.row_bdim[r];
+    const double sc = ic.scale[r], rad = ic.off[r];
+    double sq = 0.0;
+    for (int i = 0; i < bd; ++i) {
+      const double df = x[i] - ic.Gx[r * n + i];
+      sq += df * df;
+    }
+    return -(sc * sq) - (-(rad * rad) * sc);
+  }
+  double s = 0.0;
+  if (ty == IP_ROW_STATE) {
+    for (int j = 0; j < n; ++j) s += ic.Gx[r * n + j] * x[j];
+  } else {
+    for (int j = 0; j < m; ++j) s += ic.Gu[r * m + j] * u[j];
+  }
+  return s - ic.off[r];
+}
+
+// Eigen 3.4.0 LDLT (lower, diagonal pivoting), ldlt_inplace<Lower>::unblocked — executed by ONE lane on the m x m
+// matrix in shared memory.  a: in = matrix, out = L strictly below the diagonal and D on it; tr: transpositions.
+// Returns info() == Success.
+__device__ bool ldlt_small(double *a, int *tr, int n) {
+  bool ok = true, found_zero_pivot = false;
+  for (int k = 0; k < n; ++k) {
+    int big = k;
+    double best = fabs(a[k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(a[i * n + i]) > best) {
+        best = fabs(a[i * n + i]);
+        big = i;
+      }
+    tr[k] = big;
+    if (big != k) {
+      const int s = n - big - 1;
+      for (int j = 0; j < k; ++j) { const double t = a[k * n + j]; a[k * n + j] = a[big * n + j]; a[big * n + j] = t; }
+      for (int i = 0; i < s; ++i) {
+        const double t = a[(big + 1 + i) * n + k];
+        a[(big + 1 + i) * n + k] = a[(big + 1 + i) * n + big];
+        a[(big + 1 + i) * n + big] = t;
+      }
+      { const double t = a[k * n + k]; a[k * n + k] = a[big * n + big]; a[big * n + big] = t; }
+      for (int i = k + 1; i < big; ++i) { const double t = a[i * n + k]; a[i * n + k] = a[big * n + i]; a[big * n + i] = t; }
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      double temp[CDDP_B200_MAX_M];
+      for (int j = 0; j < k; ++j) temp[j] = a[j * n + j] * a[k * n + j];
+      double s = 0.0;
+      for (int j = 0; j < k; ++j) s += a[k * n + j] * temp[j];
+      a[k * n + k] -= s;
+      for (int i = 0; i < rs; ++i) {
+        double s2 = 0.0;
+        for (int j = 0; j < k; ++j) s2 += a[(k + 1 + i) * n + j] * temp[j];
+        a[(k + 1 + i) * n + k] -= s2;
+      }
+    }
+    const double akk = a[k * n + k];
+    const bool valid = fabs(akk) > 0.0;
+    if (k == 0 && !valid) {
+      for (int j = 0; j < n; ++j) tr[j] = j;
+      return ok;
+    }
+    if (rs > 0 && valid) {
+      for (int i = 0; i < rs; ++i) a[(k + 1 + i) * n + k] /= akk;
+    } else if (rs > 0) {
+      for (int i = 0; i < rs; ++i)
+        if (a[(k + 1 + i) * n + k] != 0.0) ok = false;
+    }
+    if (found_zero_pivot && valid) ok = false;
+    else if (!valid) found_zero_pivot = true;
+  }
+  return ok;
+}
+
+// LDLT::solve for one right-hand side held in b[0..n) with stride `st`
+__device__ void ldlt_solve(const double *a, const int *tr, int n, double *b, int st) {
+  for (int k = 0; k < n; ++k)
+    if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) b[i * st] -= a[i * n + j] * b[j * st];
+  const double tol = 2.2250738585072014e-308;  // numeric_limits<double>::min()
+  for (int i = 0; i < n; ++i) {
+    if (fabs(a[i * n + i]) > tol) b[i * st] /= a[i * n + i];
+    else b[i * st] = 0.0;
+  }
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = i + 1; j < n; ++j) b[i * st] -= a[j * n + i] * b[j * st];
+  for (int k = n - 1; k >= 0; --k)
+    if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
+}
+
+// ---------------------------------------------------------------------------------------------- filter
+__device__ __forceinline__ bool dominates(double m1, double t1, double m2, double t2) { return m1 <= m2 && t1 <= t2; }
+
+// detail::acceptFilterEntry (interior_point_utils.cpp:81-97); f = [cap][2] (merit, theta)
+__device__ void filter_accept(double *f, int &cnt, double merit, double theta) {
+  for (int i = 0; i < cnt; ++i)
+    if (dominates(f[2 * i], f[2 * i + 1], merit, theta)) return;
+  int w = 0;
+  for (int i = 0; i < cnt; ++i)
+    if (!dominates(merit, theta, f[2 * i], f[2 * i + 1])) {
+      f[2 * w] = f[2 * i];
+      f[2 * w + 1] = f[2 * i + 1];
+      ++w;
+    }
+  cnt = w;
+  if (cnt < IP_FILTER_CAP) {
+    f[2 * cnt] = merit;
+    f[2 * cnt + 1] = theta;
+    ++cnt;
+  }
+}
+// detail::pruneFilterToBestPoints (interior_point_utils.cpp:116-141)
+__device__ void filter_prune(double *f, int &cnt) {
+  if (cnt == 0) return;
+  double bvm = f[0], bvt = f[1], bmm = f[0], bmt = f[1];
+  for (int i = 0; i < cnt; ++i) {
+    if (f[2 * i + 1] < bvt) { bvm = f[2 * i]; bvt = f[2 * i + 1]; }
+    if (f[2 * i] < bmm) { bmm = f[2 * i]; bmt = f[2 * i + 1]; }
+  }
+  f[0] = bvm; f[1] = bvt;
+  cnt = 1;
+  if (fabs(bmt - bvt) > 1e-12 || fabs(bmm - bvm) > 1e-12) { f[2] = bmm; f[3] = bmt; cnt = 2; }
+}
+
+__device__ void ip_record_history(const DeviceState &d, const IpDevice &ip, int b) {
+  // recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp_solver.cpp:2084-2088)
+  if (!d.history) return;
+  const int hl = d.history_len[b];
+  if (hl >= d.history_cap) return;
+  double *h = d.history + ((size_t)b * d.history_cap + hl) * IP_HISTORY_COLS;
+  h[0] = d.cost[b]; h[1] = ip.merit[b]; h[2] = d.alpha[b]; h[3] = ip.alpha_du[b]; h[4] = d.inf_du[b];
+  h[5] = ip.inf_pr[b]; h[6] = ip.inf_comp[b]; h[7] = d.reg[b]; h[8] = ip.mu[b];
+  d.history_len[b] = hl + 1;
+}
+
+// ---------------------------------------------------------------------------------------------- initialize
+// One thread per instance: cold start (ipddp_solver.cpp:818-913).
+template <int MODEL>
+__global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const int N = d.N, D = ic.d;
+  const int cur = d.cur[b];
+  double *X = d.X[cur] + (size_t)b * (N + 1) * NS;
+  const double *U = d.U[cur] + (size_t)b * N * NC;
+  double *G = ip.G[cur] + (size_t)b * N * D, *S = ip.S[cur] + (size_t)b * N * D, *Y = ip.Y[cur] + (size_t)b * N * D;
+  const double mu = ic.nc == 0 ? fmax(c.opt.tolerance / 10.0, ic.io.mu_min_value) : ic.io.mu_initial;  // :884-887
+  double x[NS], xn[NS], u[NC];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+  double J = 0.0, logsum = 0.0, theta = 0.0, maxr = 0.0, maxys = -pos_inf(), minys = pos_inf();
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) X[(size_t)t * NS + i] = x[i];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) u[i] = U[(size_t)t * NC + i];
+    {  // running cost (objective.cpp:80-92)
+      const double *ref = ref_ptr(d, b, t);
+      double sx = 0.0, su = 0.0;
+      for (int j = 0; j < NS; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < NS; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * NS + j]);
+        sx += r * (x[j] - ref[j]);
+      }
+      for (int j = 0; j < NC; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < NC; ++i) r += u[i] * (0.5 * c.Rdt2[i * NC + j]);
+        su += r * u[j];
+      }
+      J += sx + su;
+    }
+    double acc = 0.0, lacc = 0.0;
+    for (int r = 0; r < D; ++r) {  // :2447-2466
+      const double g = con_value(ic, r, NS, NC, x, u);
+      const double s = fmax(ic.io.slack_var_init_scale, -g + kSlackInteriorOffset);
+      const double y = (mu * ic.io.dual_var_init_scale) / fmax(s, EPS_SLACK);
+      G[(size_t)t * D + r] = g;
+      S[(size_t)t * D + r] = s;
+      Y[(size_t)t * D + r] = y;
+      const double res = g + s;
+      acc += ic.io.theta_norm_l2 ? res * res : fabs(res);
+      maxr = fmax(maxr, fabs(res));
+      lacc += log(fmax(s, EPS_SLACK));
+      maxys = fmax(maxys, y * s);
+      minys = fmin(minys, y * s);
+    }
+    theta += acc;
+    logsum += lacc;
+    discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = xn[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i) X[(size_t)N * NS + i] = x[i];
+  {
+    const double *ref = d.xref + (size_t)b * NS;
+    double sx = 0.0;
+    for (int j = 0; j < NS; ++j) {
+      double r = 0.0;
+      for (int i = 0; i < NS; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qf2[i * NS + j]);
+      sx += r * (x[j] - ref[j]);
+    }
+    J += sx;
+  }
+  if (ic.io.theta_norm_l2) theta = sqrt(theta);
+  theta = fmax(theta, maxr);
+  d.cost[b] = J;
+  d.reg[b] = c.opt.reg_initial_value;
+  d.alpha[b] = 1.0;
+  ip.alpha_du[b] = 1.0;
+  ip.mu[b] = mu;
+  ip.step_norm[b] = 0.0;
+  ip.inf_pr[b] = maxr;  // resetBarrierFilter (:2484-2517)
+  ip.inf_comp[b] = D ? fmax(maxys - mu, mu - minys) : 0.0;
+  ip.merit[b] = J - mu * logsum;
+  ip.logsum[b] = logsum;
+  ip.filter_theta[b] = fmax(theta, 1e-8);
+  ip.filter_size[b] = 0;
+  ip.apm[b] = 1.0;
+  ip.adm[b] = 1.0;
+  d.inf_du[b] = 0.0;
+  d.dV[2 * b] = 0.0;
+  d.dV[2 * b + 1] = 0.0;
+  d.status[b] = CDDP_B200_STATUS_RUNNING;
+  d.iter[b] = 0;
+  d.lin_valid[b] = 0;
+  d.bw_ok[b] = 0;
+  d.accepted[b] = -1;
+  if (d.history) {
+    d.history_len[b] = 0;
+    ip_record_history(d, ip, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward sweep
+// A group of G lanes owns one trajectory; its dense blocks live in the group's slice of shared memory and the lanes
+// split the output entries of every product (runtime dimensions).  The m x m pivoted LDLT runs on one lane; the
+// 1 + n right-hand sides [Q_u | Q_ux] are solved one column per lane.
+constexpr int kBwThreads = 128;
+
+__host__ __device__ inline int ip_group_doubles(int n, int m, int D, int rs) {
+  int c = rs + n;                    // record, x
+  c += n * n + n;                    // V, vx
+  c += n * n + n * m;                // PA, PB
+  c += n * n + m * n + 2 * m * m;    // Qxx, Qux, Quu, Qr
+  c += n + m;                        // Qx, Qu
+  c += m * (n + 1);                  // RHS / kK
+  c += m * (n > m ? n : m);          // Q_uu K scratch (also stages the m x m condensed Q_uu)
+  c += D * n + D * m;                // Gx, Gu
+  c += 8 * D;                        // y, s, g, ssafe, YS, prim, rhat, Sir
+  c += 3 * n + 2 * m;                // dx, dxn, scratch
+  c += CDDP_B200_MAX_M;              // transpositions (ints, generously)
+  return (c + 1) & ~1;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
+                                                                 int mode) {
+  extern __shared__ double smem[];
+  const int n = d.n, m = d.m, N = d.N, rs = d.rec_stride, D = ic.d;
+  constexpr int GPC = kBwThreads / G;  // groups per CTA
+  double *sQ = smem;
+  double *sR = sQ + n * n;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) sQ[i] = c.Qdt2[i];
+  for (int i = threadIdx.x; i < m * m; i += blockDim.x) sR[i] = c.Rdt2[i];
+  __syncthreads();
+  const int grp = threadIdx.x / G, r = threadIdx.x % G;
+  const int b = blockIdx.x * GPC + grp;
+  const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+  const int bb = alive ? b : 0;
+  double *w = sR + m * m + ((n * n + m * m) & 1) + (size_t)grp * ip_group_doubles(n, m, D, rs);
+  double *rec = w;  w += rs;
+  double *xs = w;   w += n;
+  double *V = w;    w += n * n;
+  double *vx = w;   w += n;
+  double *PA = w;   w += n * n;
+  double *PB = w;   w += n * m;
+  double *Qxx = w;  w += n * n;
+  double *Qux = w;  w += m * n;
+  double *Quu = w;  w += m * m;
+  double *Qr = w;   w += m * m;
+  double *Qx = w;   w += n;
+  double *Qu = w;   w += m;
+  double *RHS = w;  w += m * (n + 1);  // [m][1+n]: column 0 -> k, columns 1..n -> K
+  double *QK = w;   w += m * (n > m ? n : m);
+  double *Gx = w;   w += D * n;
+  double *Gu = w;   w += D * m;
+  double *ys = w;   w += D;
+  double *ss = w;   w += D;
+  double *gs = w;   w += D;
+  double *ssafe = w; w += D;
+  double *YS = w;   w += D;
+  double *prim = w; w += D;
+  double *rhat = w; w += D;
+  double *Sir = w;  w += D;
+  double *dx = w;   w += n;
+  double *dxn = w;  w += n;
+  double *scr = w;  w += n + 2 * m;
+  int *tr = reinterpret_cast<int *>(w);
+
+  const int cur = d.cur[bb];
+  const double *grec = d.rec + (size_t)bb * N * rs;
+  const double *gX = d.X[cur] + (size_t)bb * (N + 1) * n;
+  const double *gY = ip.Y[cur] + (size_t)bb * N * D, *gS = ip.S[cur] + (size_t)bb * N * D, *gG = ip.G[cur] + (size_t)bb * N * D;
+  double *gK = d.K + (size_t)bb * N * m * n, *gk = d.kff + (size_t)bb * N * m;
+  double *gky = ip.ky + (size_t)bb * N * D, *gks = ip.ks + (size_t)bb * N * D;
+  double *gKy = ip.Ky + (size_t)bb * N * D * n, *gKs = ip.Ks + (size_t)bb * N * D * n;
+  const double *A = rec, *Bm = rec + n * n, *lx = rec + d.offLx, *lu = rec + d.offLu;
+  const int nc1 = n + 1;
+
+  const double mu = alive ? ip.mu[bb] : 1.0;
+  double reg = alive ? d.reg[bb] : 0.0;
+  if (alive && mode == BW_ITERATE && r == 0) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
+  int status = CDDP_B200_STATUS_RUNNING;
+  bool need = alive, ok = false;
+  double dV0 = 0.0, dV1 = 0.0, inf_du = 0.0, inf_pr = 0.0, inf_comp = 0.0, step_norm = 0.0;
+
+  while (__any_sync(0xffffffffu, need)) {
+    bool act = need;  // this group sweeps in this round
+    if (act) {
+      // V_xx = sym(2 Qf), V_x = 2 Qf (x_N - ref)   (:983-990)
+      for (int i = r; i < n * n; i += G) {
+        const int a = i / n, e = i - a * n;
+        V[i] = 0.5 * (c.Qf2[a * n + e] + c.Qf2[e * n + a]);
+      }
+      for (int i = r; i < n; i += G) vx[i] = d.vterm[(size_t)bb * n + i];
+    }
+    dV0 = dV1 = inf_du = inf_pr = inf_comp = step_norm = 0.0;
+    __syncwarp();
+    for (int t = N - 1; t >= 0; --t) {
+      if (act) {
+        for (int i = r; i < rs; i += G) rec[i] = grec[(size_t)t * rs + i];
+        for (int i = r; i < n; i += G) xs[i] = gX[(size_t)t * n + i];
+        for (int i = r; i < D; i += G) {
+          ys[i] = gY[(size_t)t * D + i];
+          ss[i] = gS[(size_t)t * D + i];
+          gs[i] = gG[(size_t)t * D + i];
+        }
+      }
+      __syncwarp();
+      if (act) {
+        // constraint Jacobians of this step (precomputeConstraintGradients :2145-2250) and the barrier terms (:1413-1443)
+        for (int i = r; i < D * n; i += G) {
+          const int row = i / n, j = i - row * n;
+          const int ty = ic.row_type[row];
+          double v = 0.0;
+          if (ty == IP_ROW_STATE) v = ic.Gx[i];
+          else if (ty == IP_ROW_BALL && j < ic.row_bdim[row]) v = -2.0 * ic.scale[row] * (xs[j] - ic.Gx[i]);
+          Gx[i] = v;
+        }
+        for (int i = r; i < D * m; i += G) Gu[i] = (ic.row_type[i / m] == IP_ROW_CONTROL) ? ic.Gu[i] : 0.0;
+        for (int i = r; i < D; i += G) {
+          const double sf = fmax(ss[i], fmax(mu * 1e-3, EPS_SLACK));
+          ssafe[i] = sf;
+          YS[i] = clip_pos(ys[i], sf);
+          const double pr = gs[i] + ss[i];
+          const double cp = ys[i] * ss[i] - mu;
+          prim[i] = pr;
+          const double rh = ys[i] * pr - cp;
+          rhat[i] = rh;
+          Sir[i] = clip_signed(rh, sf);
+        }
+        // P = V [A|B]
+        for (int idx = r; idx < n * (n + m); idx += G) {
+          const int i = idx / (n + m), j = idx - i * (n + m);
+          double s = 0.0;
+          if (j < n) {
+            for (int l = 0; l < n; ++l) s += V[i * n + l] * A[l * n + j];
+            PA[i * n + j] = s;
+          } else {
+            for (int l = 0; l < n; ++l) s += V[i * n + l] * Bm[l * m + (j - n)];
+            PB[i * m + (j - n)] = s;
+          }
+        }
+      }
+      __syncwarp();
+      if (act) {
+        // Q_x = l_x + Q_yx^T y + A^T V_x ; Q_u = l_u + Q_yu^T y + B^T V_x   (:1393-1394)
+        for (int j = r; j < n + m; j += G) {
+          if (j < n) {
+            double gy = 0.0, av = 0.0;
+            for (int q = 0; q < D; ++q) gy += Gx[q * n + j] * ys[q];
+            for (int l = 0; l < n; ++l) av += A[l * n + j] * vx[l];
+            Qx[j] = D ? (lx[j] + gy) + av : lx[j] + av;
+          } else {
+            const int a = j - n;
+            double gy = 0.0, bv = 0.0;
+            for (int q = 0; q < D; ++q) gy += Gu[q * m + a] * ys[q];
+            for (int l = 0; l < n; ++l) bv += Bm[l * m + a] * vx[l];
+            Qu[a] = D ? (lu[a] + gy) + bv : lu[a] + bv;
+          }
+        }
+        // Q_xx = l_xx + A^T P_A ; Q_ux = B^T P_A ; Q_uu = l_uu + B^T P_B   (:1395-1397)
+        for (int idx = r; idx < n * n + m * n + m * m; idx += G) {
+          double s = 0.0;
+          if (idx < n * n) {
+            const int i = idx / n, j = idx - i * n;
+            for (int l = 0; l < n; ++l) s += A[l * n + i] * PA[l * n + j];
+            Qxx[idx] = sQ[idx] + s;
+          } else if (idx < n * n + m * n) {
+            const int e = idx - n * n, i = e / n, j = e - i * n;
+            for (int l = 0; l < n; ++l) s += Bm[l * m + i] * PA[l * n + j];
+            Qux[e] = s;
+          } else {
+            const int e = idx - n * n - m * n, i = e / m, j = e - i * m;
+            for (int l = 0; l < n; ++l) s += Bm[l * m + i] * PB[l * m + j];
+            Quu[e] = sR[e] + s;
+          }
+        }
+      }
+      __syncwarp();
+      if (act) {
+        // Q_uu_reg = sym(Q_uu) + Q_yu^T YSinv Q_yu + reg I (:1427-1429; unconstrained :1083-1084) and
+        // bigRHS = [Q_u + Q_yu^T S^-1 rhat | Q_ux + Q_yu^T YSinv Q_yx]   (:1444-1447)
+        for (int idx = r; idx < m * m + m * nc1; idx += G) {
+          if (idx < m * m) {
+            const int i = idx / m, j = idx - i * m;
+            double acc = 0.0;
+            for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]);
+            Qr[idx] = 0.5 * (Quu[i * m + j] + Quu[j * m + i]) + acc + (i == j ? reg : 0.0);
+          } else {
+            const int e = idx - m * m, i = e / nc1, j = e - i * nc1;
+            double acc = 0.0;
+            if (j == 0) {
+              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * Sir[q];
+              RHS[e] = D ? Qu[i] + acc : Qu[i];
+            } else {
+              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gx[q * n + (j - 1)]);
+              RHS[e] = D ? Qux[i * n + (j - 1)] + acc : Qux[i * n + (j - 1)];
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // condensed Q terms that need the pre-solve RHS (:1493-1497), before RHS is overwritten by the solve
+      if (act) {
+        for (int idx = r; idx < m + m * n + n + n * n + m * m; idx += G) {
+          int e = idx;
+          if (e < m) {
+            Qu[e] = RHS[e * nc1];
+            continue;
+          }
+          e -= m;
+          if (e < m * n) {
+            const int i = e / n, j = e - i * n;
+            Qux[e] = RHS[i * nc1 + 1 + j];
+            continue;
+          }
+          e -= m * n;
+          if (e < n) {
+            double acc = 0.0;
+            for (int q = 0; q < D; ++q) acc += Gx[q * n + e] * Sir[q];
+            if (D) Qx[e] += acc;
+            continue;
+          }
+          e -= n;
+          if (e < n * n) {
+            const int i = e / n, j = e - i * n;
+            double acc = 0.0;
+            for (int q = 0; q < D; ++q) acc += Gx[q * n + i] * (YS[q] * Gx[q * n + j]);
+            if (D) Qxx[e] += acc;
+            continue;
+          }
+          e -= n * n;
+          {
+            const int i = e / m, j = e - i * m;
+            if (D) {
+              double acc = 0.0;
+              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]);
+              QK[e] = Quu[e] + acc;  // staged: Quu is still being read by other lanes' Qr (done above) — safe after sync
+            } else {
+              QK[e] = Qr[e];  // unconstrained branch: the symmetrised + regularised Q_uu enters V and dV (:1083-1084)
+            }
+          }
+        }
+      }
+      __syncwarp();
+      bool fail = false;
+      if (act) {
+        for (int i = r; i < m * m; i += G) Quu[i] = QK[i];
+        if (r == 0) {
+          const bool good = ldlt_small(Qr, tr, m);  // Eigen::LDLT(Q_uu_reg) (:1431)
+          tr[CDDP_B200_MAX_M] = good ? 1 : 0;
+        }
+      }
+      __syncwarp();
+      if (act) {
+        fail = tr[CDDP_B200_MAX_M] == 0;  // ldlt.info() != Success -> backward pass fails (:1432-1435)
+        if (!fail) {
+          for (int col = r; col < nc1; col += G) {  // kK = -ldlt.solve(bigRHS) (:1449)
+            ldlt_solve(Qr, tr, m, RHS + col, nc1);
+            for (int i = 0; i < m; ++i) RHS[i * nc1 + col] = -RHS[i * nc1 + col];
+          }
+        }
+      }
+      __syncwarp();
+      if (act && !fail) {
+        // gains to HBM (:1458-1459)
+        for (int i = r; i < m * nc1; i += G) {
+          const int a = i / nc1, j = i - a * nc1;
+          if (j == 0) gk[(size_t)t * m + a] = RHS[i];
+          else gK[((size_t)t * m + a) * n + (j - 1)] = RHS[i];
+        }
+        // k_y, K_y, k_s, K_s (:1461-1491)
+        for (int idx = r; idx < D * nc1; idx += G) {
+          const int q = idx / nc1, j = idx - q * nc1;
+          if (j == 0) {
+            double temp = 0.0;
+            for (int i = 0; i < m; ++i) temp += Gu[q * m + i] * RHS[i * nc1];
+            gky[(size_t)t * D + q] = clip_signed(rhat[q] + ys[q] * temp, ssafe[q]);
+            gks[(size_t)t * D + q] = -prim[q] - temp;
+          } else {
+            double gkk = 0.0;
+            for (int i = 0; i < m; ++i) gkk += Gu[q * m + i] * RHS[i * nc1 + j];
+            const double qq = Gx[q * n + (j - 1)] + gkk;
+            gKy[((size_t)t * D + q) * n + (j - 1)] = clampd(YS[q] * qq, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+            gKs[((size_t)t * D + q) * n + (j - 1)] = -Gx[q * n + (j - 1)] - gkk;
+          }
+        }
+        // Q_uu K, Q_uu k
+        for (int idx = r; idx < m * n + m; idx += G) {
+          if (idx < m * n) {
+            const int i = idx / n, j = idx - i * n;
+            double acc = 0.0;
+            for (int l = 0; l < m; ++l) acc += Quu[i * m + l] * RHS[l * nc1 + 1 + j];
+            QK[idx] = acc;
+          } else {
+            const int i = idx - m * n;
+            double acc = 0.0;
+            for (int l = 0; l < m; ++l) acc += Quu[i * m + l] * RHS[l * nc1];
+            scr[i] = acc;
+          }
+        }
+      }
+      __syncwarp();
+      if (act && !fail) {
+        // dV (:1499-1500), infeasibility measures (:1510-1513): every lane redundantly (tiny)
+        double d0 = 0.0, d1 = 0.0;
+        for (int i = 0; i < m; ++i) {
+          const double ki = RHS[i * nc1];
+          d0 += ki * Qu[i];
+          d1 += ki * scr[i];
+          inf_du = fmax(inf_du, fabs(Qu[i]));
+          step_norm = fmax(step_norm, fabs(ki));
+        }
+        dV0 += d0;
+        dV1 += 0.5 * d1;
+        for (int q = 0; q < D; ++q) {
+          inf_pr = fmax(inf_pr, fabs(prim[q]));
+          inf_comp = fmax(inf_comp, fabs(ys[q] * ss[q] - mu));
+        }
+        // V_x = Q_x + K^T Q_u + Q_ux^T k + K^T Q_uu k (:1502-1503) -> dxn (scratch) ; V_xx (:1504-1506) -> PA (scratch)
+        for (int idx = r; idx < n + n * n; idx += G) {
+          if (idx < n) {
+            const int i = idx;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int l = 0; l < m; ++l) {
+              const double Kli = RHS[l * nc1 + 1 + i];
+              a1 += Kli * Qu[l];
+              a2 += Qux[l * n + i] * RHS[l * nc1];
+              a3 += Kli * scr[l];
+            }
+            dxn[i] = ((Qx[i] + a1) + a2) + a3;
+          } else {
+            const int e = idx - n, i = e / n, j = e - i * n;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int l = 0; l < m; ++l) {
+              const double Kli = RHS[l * nc1 + 1 + i];
+              a1 += Kli * Qux[l * n + j];
+              a2 += Qux[l * n + i] * RHS[l * nc1 + 1 + j];
+              a3 += Kli * QK[l * n + j];
+            }
+            PA[e] = ((Qxx[e] + a1) + a2) + a3;
+          }
+        }
+      }
+      __syncwarp();
+      if (act && !fail) {
+        for (int i = r; i < n; i += G) vx[i] = dxn[i];
+        for (int e = r; e < n * n; e += G) {
+          const int i = e / n, j = e - i * n;
+          V[e] = 0.5 * (PA[i * n + j] + PA[j * n + i]);
+        }
+      }
+      if (act && fail) act = false;  // idle until the end of this sweep; `need` stays set -> retry
+      else if (act && t == 0) {
+        need = false;
+        ok = true;
+      }
+      __syncwarp();
+    }
+    if (need && alive) {  // this group's sweep failed
+      if (mode == BW_SINGLE) {
+        need = false;
+      } else {  // increaseRegularization + limit test (cddp_solver_base.cpp:95-109, cddp_core.cpp:308-326)
+        reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+        if (reg >= c.opt.reg_max_value) {
+          status = CDDP_B200_STATUS_REG_LIMIT;
+          need = false;
+        }
+      }
+    }
+  }
+
+  // linearised slack / dual steps and the fraction-to-boundary step caps: rolloutLinearPolicy from dx0 = 0 (:368-392),
+  // dS = k_s + K_s dX, dY = clamp(k_y + K_y dX) (:1516-1538), computeMaxStepSizes (:2939-2988)
+  double apm = 1.0, adm = 1.0;
+  const bool roll = ok && D > 0;
+  if (__any_sync(0xffffffffu, roll)) {
+    const double tau_b = fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);
+    if (roll)
+      for (int i = r; i < n; i += G) dx[i] = 0.0;
+    __syncwarp();
+    for (int t = 0; t < N; ++t) {
+      if (roll) {
+        for (int i = r; i < rs; i += G) rec[i] = grec[(size_t)t * rs + i];
+        for (int q = r; q < D; q += G) {
+          double a1 = 0.0, a2 = 0.0;
+          for (int j = 0; j < n; ++j) {
+            a1 += gKs[((size_t)t * D + q) * n + j] * dx[j];
+            a2 += gKy[((size_t)t * D + q) * n + j] * dx[j];
+          }
+          const double ds = gks[(size_t)t * D + q] + a1;
+          const double dy = clampd(gky[(size_t)t * D + q] + a2, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+          if (ds < 0.0) apm = fmin(apm, -tau_b * gS[(size_t)t * D + q] / ds);
+          if (dy < 0.0) adm = fmin(adm, -tau_b * gY[(size_t)t * D + q] / dy);
+        }
+        for (int i = r; i < m; i += G) {
+          double acc = 0.0;
+          for (int j = 0; j < n; ++j) acc += gK[((size_t)t * m + i) * n + j] * dx[j];
+          scr[i] = gk[(size_t)t * m + i] + acc;
+        }
+      }
+      __syncwarp();
+      if (roll)
+        for (int i = r; i < n; i += G) {
+          double a1 = 0.0, a2 = 0.0;
+          for (int j = 0; j < n; ++j) a1 += A[i * n + j] * dx[j];
+          for (int j = 0; j < m; ++j) a2 += Bm[i * m + j] * scr[j];
+          dxn[i] = (a1 + a2) + 0.0;
+        }
+      __syncwarp();
+      if (roll)
+        for (int i = r; i < n; i += G) dx[i] = dxn[i];
+      __syncwarp();
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      apm = fmin(apm, __shfl_xor_sync(0xffffffffu, apm, o));
+      adm = fmin(adm, __shfl_xor_sync(0xffffffffu, adm, o));
+    }
+    apm = clampd(apm, 0.0, 1.0);
+    adm = clampd(adm, 0.0, 1.0);
+  }
+
+  if (alive && r == 0) {
+    d.bw_ok[b] = ok ? 1 : 0;
+    d.lin_valid[b] = 1;
+    if (ok) {
+      d.dV[2 * b] = dV0;
+      d.dV[2 * b + 1] = dV1;
+      d.inf_du[b] = inf_du;
+      ip.step_norm[b] = step_norm;
+      ip.inf_pr[b] = D ? inf_pr : 0.0;  // (:1113-1116, :1565-1568)
+      ip.inf_comp[b] = D ? inf_comp : 0.0;
+      ip.apm[b] = apm;
+      ip.adm[b] = adm;
+    }
+    if (mode == BW_ITERATE) {
+      d.reg[b] = reg;
+      if (ok) {  // checkEarlyConvergence (:925-958)
+        bool early;
+        const double ipr = D ? inf_pr : 0.0, icp = D ? inf_comp : 0.0;
+        if (ic.nc == 0) {
+          early = ipr < c.opt.tolerance && inf_du < c.opt.tolerance;
+        } else {
+          const double tol = fmax(c.opt.tolerance, ic.io.barrier_tol_mult * mu);
+          early = ipr < tol && inf_du < tol && icp < tol && fabs(d.alpha[b]) * step_norm < c.opt.tolerance * 10.0;
+        }
+        if (early) {
+          status = CDDP_B200_STATUS_OPTIMAL;
+          ip_record_history(d, ip, b);
+        }
+      }
+      if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward pass
+constexpr int kFwThreads = 64;
+
+struct TrialStats {
+  double cost, logsum, theta, inf_pr, maxys, minys;
+  bool feasible;
+};
+
+// One rollout of IPDDPSolver::forwardPass (:1597-1751) for step sizes (alpha_pr, alpha_du).  WRITE: store the trial
+// trajectory, slacks, duals and constraint values into the candidate buffers.
+template <int MODEL, bool WRITE>
+__device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
+                                           int b, int cur, double alpha_pr, double alpha_du, double tau, double mu,
+                                           TrialStats &st) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  const int N = d.N, D = ic.d;
+  const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
+  const double *gK = d.K + (size_t)b * N * NC * NS, *gk = d.kff + (size_t)b * N * NC;
+  const double *S0 = ip.S[cur] + (size_t)b * N * D, *Y0 = ip.Y[cur] + (size_t)b * N * D;
+  const double *gks = ip.ks + (size_t)b * N * D, *gky = ip.ky + (size_t)b * N * D;
+  const double *gKs = ip.Ks + (size_t)b * N * D * NS, *gKy = ip.Ky + (size_t)b * N * D * NS;
+  double *Xc = d.X[cur ^ 1] + (size_t)b * (N + 1) * NS, *Uc = d.U[cur ^ 1] + (size_t)b * N * NC;
+  double *Sc = ip.S[cur ^ 1] + (size_t)b * N * D, *Yc = ip.Y[cur ^ 1] + (size_t)b * N * D, *Gc = ip.G[cur ^ 1] + (size_t)b * N * D;
+  const bool l2 = ic.io.theta_norm_l2 != 0;
+  double x[NS], xn[NS], u[NC], dxv[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+  st.cost = 0.0; st.logsum = 0.0; st.theta = 0.0; st.inf_pr = 0.0; st.maxys = -pos_inf(); st.minys = pos_inf();
+  st.feasible = true;
+  bool feas = true;
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - Xn[(size_t)t * NS + i];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {  // u' = u + alpha_pr k + K dx (no clamp) (:1650-1651)
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) acc += gK[((size_t)t * NC + i) * NS + j] * dxv[j];
+      u[i] = (Un[(size_t)t * NC + i] + alpha_pr * gk[(size_t)t * NC + i]) + acc;
+    }
+    double acc_t = 0.0, lacc = 0.0;
+    for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
+      const size_t e = (size_t)t * D + q;
+      double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        a1 += gKs[e * NS + j] * dxv[j];
+        a2 += gKy[e * NS + j] * dxv[j];
+      }
+      const double s0 = S0[e], y0 = Y0[e];
+      const double sn = (s0 + alpha_pr * gks[e]) + a1;
+      const double yn = (y0 + alpha_du * gky[e]) + a2;
+      if (sn < (1.0 - tau) * s0 || yn < (1.0 - tau) * y0) feas = false;
+      if (!finite_d(sn) || !finite_d(yn)) feas = false;
+      const double g = con_value(ic, q, NS, NC, x, u);  // (:1743-1748)
+      const double res = g + sn;
+      acc_t += l2 ? res * res : fabs(res);
+      st.inf_pr = fmax(st.inf_pr, fabs(res));
+      lacc += log(fmax(sn, EPS_SLACK));
+      st.maxys = fmax(st.maxys, yn * sn);
+      st.minys = fmin(st.minys, yn * sn);
+      if (WRITE) {
+        Sc[e] = sn;
+        Yc[e] = yn;
+        Gc[e] = g;
+      }
+    }
+    st.theta += acc_t;
+    st.logsum += lacc;
+    {  // running cost (:1741)
+      const double *ref = ref_ptr(d, b, t);
+      double sx = 0.0, su = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        double rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * NS + j]);
+        sx += rr * (x[j] - ref[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        double rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) rr += u[i] * (0.5 * c.Rdt2[i * NC + j]);
+        su += rr * u[j];
+      }
+      st.cost += sx + su;
+    }
+    if (WRITE) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) Xc[(size_t)t * NS + i] = x[i];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) Uc[(size_t)t * NC + i] = u[i];
+    }
+    discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);  // (:1652-1654)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      x[i] = xn[i];
+      if (!finite_d(xn[i])) feas = false;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (!finite_d(u[i])) feas = false;
+  }
+  {
+    const double *ref = d.xref + (size_t)b * NS;
+    double sx = 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double rr = 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qf2[i * NS + j]);
+      sx += rr * (x[j] - ref[j]);
+    }
+    st.cost += sx;
+  }
+  if (WRITE) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
+  }
+  if (l2) st.theta = sqrt(st.theta);
+  st.theta = fmax(st.theta, st.inf_pr);
+  st.feasible = feas;
+}
+
+// One lane per alpha, 16 lanes per trajectory.  pass 1: every lane rolls its alpha out and applies the acceptance test;
+// the first accepted alpha (sequential semantics, cddp_solver_base.cpp:255-263) is replayed once (pass 2, all lanes of
+// the group in lock-step, lane 0 writing the candidate buffers); lane 0 then runs the per-instance bookkeeping.
+template <int MODEL>
+__global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
+                                                                int mode) {
+  constexpr int LG = 16;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LG, al = lane % LG;
+  const int b = ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp;
+  const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+  if (!__any_sync(0xffffffffu, alive)) return;
+  const int bb = alive ? b : 0;
+  const int na = c.num_alphas, D = ic.d;
+  const int cur = d.cur[bb];
+  const double mu = ip.mu[bb];
+  const bool active = alive && al < na;
+  const double alpha = c.alphas[al < na ? al : na - 1];
+  const double tau = ic.nc == 0 ? 1.0 : fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);  // (:1585-1588)
+  const double alpha_pr = fmin(alpha, ip.apm[bb]), alpha_du = fmin(alpha, ip.adm[bb]);
+  TrialStats st;
+  ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st);
+  const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
+  const double phi_new = st.cost - mu * st.logsum;  // computeBarrierMerit (:2850-2880)
+  const double theta_new = st.theta;
+  const double inf_comp_new = D ? fmax(st.maxys - mu, mu - st.minys) : 0.0;
+  bool accept = false;
+  if (st.feasible && finite_d(phi_new) && finite_d(theta_new) && finite_d(st.inf_pr) && finite_d(inf_comp_new)) {
+    if (ic.nc == 0) {  // (:1787-1794)
+      const double dJ = cost_old - st.cost;
+      const double expected = -alpha_pr * (d.dV[2 * bb] + 0.5 * alpha_pr * d.dV[2 * bb + 1]);
+      const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
+      accept = ratio > 1e-6;
+    } else {  // filter acceptance (:1796-1839)
+      const double expected_improvement = alpha_pr * d.dV[2 * bb];
+      const int fs = ip.filter_size[bb];
+      const double cv_old = fs ? ip.filter[((size_t)bb * IP_FILTER_CAP + (fs - 1)) * 2 + 1] : 0.0;
+      const double high_ref = fs ? cv_old : ip.filter_theta[bb];
+      if (theta_new > ic.io.max_violation_threshold) {
+        accept = theta_new < (1 - ic.io.violation_acceptance_threshold) * high_ref;
+      } else if (fmax(theta_new, cv_old) < ic.io.min_violation_for_armijo_check && expected_improvement < 0) {
+        accept = phi_new < merit_old + c.opt.armijo_constant * expected_improvement;
+      } else {
+        accept = phi_new < merit_old - ic.io.merit_acceptance_threshold * theta_new ||
+                 theta_new < (1 - ic.io.violation_acceptance_threshold) * cv_old;
+      }
+    }
+  }
+  const bool success = active && accept;
+  unsigned ballot = __ballot_sync(0xffffffffu, success);
+  ballot = (ballot >> (grp * LG)) & 0xffffu;
+  const int first = ballot ? (__ffs(ballot) - 1) : -1;
+  if (alive && al < na) {
+    double *ls = ip.ls_stats + ((size_t)b * CDDP_B200_MAX_ALPHAS + al) * 4;
+    ls[0] = success ? 1.0 : 0.0;
+    ls[1] = st.cost;
+    ls[2] = phi_new;
+    ls[3] = theta_new;
+  }
+  const int src = grp * LG + (first >= 0 ? first : 0);
+  const double a_pr = __shfl_sync(0xffffffffu, alpha_pr, src), a_du = __shfl_sync(0xffffffffu, alpha_du, src);
+  const double cost_new = __shfl_sync(0xffffffffu, st.cost, src), logsum_new = __shfl_sync(0xffffffffu, st.logsum, src);
+  const double th_new = __shfl_sync(0xffffffffu, theta_new, src), ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
+  const double maxys = __shfl_sync(0xffffffffu, st.maxys, src), minys = __shfl_sync(0xffffffffu, st.minys, src);
+  const double phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
+  if (alive && first >= 0 && al == 0) {  // pass 2: write the accepted trial
+    TrialStats s2;
+    ip_rollout<MODEL, true>(c, d, ic, ip, b, cur, a_pr, a_du, tau, mu, s2);
+  }
+  if (!(alive && al == 0)) return;
+  d.accepted[b] = first;
+  if (mode != FW_ITERATE) return;
+  double reg = d.reg[b];
+  int status = CDDP_B200_STATUS_RUNNING;
+  const bool no_barrier = ic.nc == 0;
+  const double inf_du = d.inf_du[b];
+  if (first >= 0) {
+    const double dJ = cost_old - cost_new;  // cddp_solver_base.cpp:130
+    // applyForwardPassResult (:1878-1951)
+    d.cost[b] = cost_new;
+    d.alpha[b] = a_pr;
+    ip.alpha_du[b] = a_du;
+    d.cur[b] = cur ^ 1;
+    d.lin_valid[b] = 0;
+    double inf_pr = ipr_new;
+    double inf_comp = D ? fmax(maxys - mu, mu - minys) : 0.0;
+    const double phi = phi_acc;
+    // updateBarrierParameters(context, true) (:2548-2660)
+    double mu_new = mu;
+    if (!no_barrier) {
+      if (ic.io.barrier_strategy == CDDP_B200_BARRIER_ADAPTIVE) {
+        const double kkt = fmax(fmax(inf_pr, inf_du), inf_comp);
+        const double threshold = fmax(ic.io.mu_update_factor * mu, 2.0 * mu);
+        if (kkt <= threshold) {
+          double factor = ic.io.mu_update_factor;
+          if (mu > 1e-20) {
+            const double ratio = kkt / fmax(mu, 1e-20);
+            if (ratio < 0.01) factor = 0.1 * ic.io.mu_update_factor;
+            else if (ratio < 0.1) factor = 0.3 * ic.io.mu_update_factor;
+            else if (ratio < 0.5) factor = 0.6 * ic.io.mu_update_factor;
+          }
+          const double linear = factor * mu;
+          const double superlinear = pow(mu, ic.io.mu_update_power);
+          mu_new = fmax(fmin(linear, superlinear), fmax(ic.io.mu_min_value, c.opt.tolerance / 100.0));
+        }
+      } else {
+        const double kkt = fmax(fmax(inf_pr, inf_du * ic.io.barrier_update_dual_weight), inf_comp);
+        if (kkt <= ic.io.mu_kappa_epsilon * mu) {
+          const double linear = ic.io.mu_update_factor * mu;
+          const double superlinear = pow(mu, ic.io.mu_update_power);
+          mu_new = fmax(ic.io.mu_min_value, fmin(linear, superlinear));
+        }
+      }
+    }
+    const double filter_theta = fmax(th_new, 1e-8);
+    double *f = ip.filter + (size_t)b * IP_FILTER_CAP * 2;
+    int fs = ip.filter_size[b];
+    if ((mu_new < mu) && (mu_new > 0.0)) {
+      fs = 0;
+    } else {
+      filter_accept(f, fs, phi, filter_theta);
+      if (fs > ic.io.max_filter_size) filter_prune(f, fs);
+    }
+    ip.filter_size[b] = fs;
+    inf_comp = D ? fmax(maxys - mu_new, mu_new - minys) : 0.0;
+    ip.mu[b] = mu_new;
+    ip.inf_pr[b] = inf_pr;
+    ip.inf_comp[b] = inf_comp;
+    ip.merit[b] = cost_new - mu_new * logsum_new;
+    ip.logsum[b] = logsum_new;
+    ip.filter_theta[b] = filter_theta;
+    ip_record_history(d, ip, b);                                     // cddp_solver_base.cpp:133-135
+    reg = fmax(reg / c.opt.reg_update_factor, c.opt.reg_min_value);  // decreaseRegularization
+    const int iter = d.iter[b];
+    const double step_norm = ip.step_norm[b];
+    // checkConvergence (:1953-2025)
+    if (no_barrier) {
+      if (inf_pr < c.opt.tolerance && inf_du < c.opt.tolerance) {
+        status = CDDP_B200_STATUS_OPTIMAL;
+      } else if (c.opt.acceptable_tolerance > 0.0) {
+        const double sq = sqrt(c.opt.acceptable_tolerance);
+        bool acc = inf_pr < sq && inf_du < sq && iter > 50;
+        if (dJ > 0.0) acc = acc || (dJ < c.opt.acceptable_tolerance && iter > 50 && inf_pr < sq && inf_du < sq);
+        if (acc) status = CDDP_B200_STATUS_ACCEPTABLE;
+      }
+    } else {
+      const double tol = fmax(c.opt.tolerance, ic.io.barrier_tol_mult * mu_new);
+      if (inf_pr < tol && inf_du < tol && inf_comp < tol && step_norm < c.opt.tolerance * 10.0) {
+        status = CDDP_B200_STATUS_OPTIMAL;
+      } else if (c.opt.acceptable_tolerance > 0.0) {
+        const double at = sqrt(c.opt.acceptable_tolerance);
+        const double bat = fmax(ic.io.mu_min_value * 100.0, c.opt.tolerance / 10.0);
+        const bool kkt = inf_pr < at && inf_du < at && inf_comp < at;
+        const bool done = mu_new <= bat;
+        bool acc = kkt && done && iter > 10 && fabs(dJ) < c.opt.acceptable_tolerance;
+        acc = acc || (kkt && done && iter >= 1 && step_norm < c.opt.tolerance * 10.0 && inf_pr < 1e-4);
+        if (acc) status = CDDP_B200_STATUS_ACCEPTABLE;
+      }
+    }
+  } else {  // handleForwardPassFailure (:2037-2082)
+    reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+    if (reg >= c.opt.reg_max_value) {
+      const double base = sqrt(fmax(c.opt.acceptable_tolerance, c.opt.tolerance));
+      const double at = no_barrier ? base : fmax(base, ic.io.barrier_tol_mult * mu);
+      const bool acc = c.opt.acceptable_tolerance > 0.0 && ip.inf_pr[b] < at && inf_du < at &&
+                       (no_barrier || ip.inf_comp[b] < at);
+      status = acc ? CDDP_B200_STATUS_ACCEPTABLE : CDDP_B200_STATUS_REG_LIMIT;
+    }
+  }
+  d.reg[b] = reg;
+  if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+}
+
+template <int MODEL>
+cudaError_t launch_ip_forward_model(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                                    cudaStream_t st) {
+  const int per_cta = kFwThreads / 16;
+  ip_forward_kernel<MODEL><<<(d.B + per_cta - 1) / per_cta, kFwThreads, 0, st>>>(c, d, ic, ip, mode);
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t launch_ip_init_model(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
+                                 cudaStream_t st) {
+  ip_initialize_kernel<MODEL><<<(d.B + 63) / 64, 64, 0, st>>>(c, d, ic, ip);
+  return cudaGetLastError();
+}
+
+template <int G>
+cudaError_t launch_ip_backward_g(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                                 cudaStream_t st) {
+  const int n = d.n, m = d.m;
+  const int gpc = kBwThreads / G;
+  const size_t shm = sizeof(double) * ((size_t)n * n + m * m + ((n * n + m * m) & 1) +
+                                       (size_t)gpc * ip_group_doubles(n, m, ic.d, d.rec_stride));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ip_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (shm > 200 * 1024) return cudaErrorInvalidValue;
+  ip_backward_kernel<G><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_ip_initialize(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
+                                 cudaStream_t st) {
+  switch (c.model) {
+    case CDDP_B200_MODEL_PENDULUM: return launch_ip_init_model<CDDP_B200_MODEL_PENDULUM>(c, d, ic, ip, st);
+    case CDDP_B200_MODEL_CARTPOLE: return launch_ip_init_model<CDDP_B200_MODEL_CARTPOLE>(c, d, ic, ip, st);
+    case CDDP_B200_MODEL_UNICYCLE: return launch_ip_init_model<CDDP_B200_MODEL_UNICYCLE>(c, d, ic, ip, st);
+    case CDDP_B200_MODEL_QUADROTOR: return launch_ip_init_model<CDDP_B200_MODEL_QUADROTOR>(c, d, ic, ip, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                               cudaStream_t st) {
+  // lanes per trajectory: the widest per-step loop has n*(n+m) entries
+  if (d.n * (d.n + d.m) <= 24) return launch_ip_backward_g<8>(c, d, ic, ip, mode, st);
+  if (d.n * (d.n + d.m) <= 64) return launch_ip_backward_g<16>(c, d, ic, ip, mode, st);
+  return launch_ip_backward_g<32>(c, d, ic, ip, mode, st);
+}
+
+cudaError_t launch_ip_forward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                              cudaStream_t st) {
+  switch (c.model) {
+    case CDDP_B200_MODEL_PENDULUM: return launch_ip_forward_model<CDDP_B200_MODEL_PENDULUM>(c, d, ic, ip, mode, st);
+    case CDDP_B200_MODEL_CARTPOLE: return launch_ip_forward_model<CDDP_B200_MODEL_CARTPOLE>(c, d, ic, ip, mode, st);
+    case CDDP_B200_MODEL_UNICYCLE: return launch_ip_forward_model<CDDP_B200_MODEL_UNICYCLE>(c, d, ic, ip, mode, st);
+    case CDDP_B200_MODEL_QUADROTOR: return launch_ip_forward_model<CDDP_B200_MODEL_QUADROTOR>(c, d, ic, ip, mode, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace cddp_b200

@@ -68,6 +68,9 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
     builders = {
         "pendulum": _cfg_pendulum, "cartpole": _cfg_cartpole, "quadrotor": _cfg_quadrotor,
         "unicycle": _cfg_unicycle, "lti": _cfg_lti, "quadrotor_fig8": _cfg_quadrotor_fig8,
+        "unicycle_obstacle": _cfg_unicycle_obstacle, "cartpole_ipddp": _cfg_cartpole_ipddp,
+        "pendulum_ipddp": _cfg_pendulum_ipddp, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
+        "quadrotor_ipddp": _cfg_quadrotor_ipddp,
     }
     if name not in builders:
         raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
@@ -238,6 +241,98 @@ def _cfg_quadrotor_fig8(batch, horizon, seed_offset):
     X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
     return dict(name="quadrotor_fig8", config_id=8, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0,
                 ref_traj=ref, notes="quadrotor figure-8 tracking with reference_states (test_clddp_solver.cpp:570-710 pattern)")
+
+
+# ---------------------------------------------------------------------------------------------
+# IPDDP workloads ("solver": "ipddp"; "constraints" = the path-constraint set, "ipddp_options" = overrides of
+# CDDPOptions::ipddp).  X0 is None: IPDDP re-rolls the state trajectory out from U0 (ipddp_solver.cpp:876-882).
+# ---------------------------------------------------------------------------------------------
+def _cfg_unicycle_obstacle(batch, horizon, seed_offset):
+    """BASELINE config #4 (path-inequality part): unicycle obstacle avoidance with IPDDP, patterned on
+    examples/python_portfolio_lib.py:374-473 (ball r=0.4 at (1,1), control box +-(1.1, pi), R=0.05 I,
+    Qf=diag(100,100,50), dt=0.03, tol 1e-4) with N=200 as BASELINE.json words it.  Deviations: the
+    terminal-equality constraint of config #4 is not included (terminal constraints are out of scope of this
+    round); per-instance goals are perturbed."""
+    B = batch or 1
+    N = horizon or 200
+    dt = 0.03
+    rng = np.random.default_rng(SEED_BASE + 4 + seed_offset)
+    spec = dict(model="unicycle", n=3, m=2, horizon=N, dt=dt, integrator="euler", params=[],
+                Q=np.zeros((3, 3)), R=0.05 * np.eye(2), Qf=_diag([100.0, 100.0, 50.0]), lb=None, ub=None)
+    options = dict(max_iterations=150, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-6)
+    constraints = [dict(type="control_box", lb=[-1.1, -math.pi], ub=[1.1, math.pi]),
+                   dict(type="ball", center=[1.0, 1.0], radius=0.4)]
+    x0 = np.zeros((B, 3))
+    xref = np.tile(np.array([2.0, 2.0, math.pi / 2.0]), (B, 1))
+    if B > 1:
+        xref[1:, 0:2] += 0.15 * rng.standard_normal((B - 1, 2))
+        xref[1:, 2] += 0.1 * rng.standard_normal(B - 1)
+    U0 = np.zeros((B, N, 2))
+    return dict(name="unicycle_obstacle", config_id=4, solver="ipddp", spec=spec, options=options, constraints=constraints,
+                ipddp_options={}, x0=x0, xref=xref, X0=None, U0=U0, ref_traj=None,
+                notes="unicycle obstacle avoidance n=3 m=2 N=200, IPDDP, control box + ball (python_portfolio_lib.py:374-473)")
+
+
+def _cfg_unicycle_ipddp_free(batch, horizon, seed_offset):
+    """IPDDP with an empty constraint set (unconstrained branch, ipddp_solver.cpp:1055-1118)."""
+    cfg = _cfg_unicycle_obstacle(batch, horizon or 100, seed_offset)
+    cfg.update(name="unicycle_ipddp_free", config_id=14, constraints=[], notes="unicycle, IPDDP without constraints")
+    return cfg
+
+
+def _cfg_pendulum_ipddp(batch, horizon, seed_offset):
+    """examples/cddp_pendulum.cpp:27-67: Pendulum(dt=0.02, l=0.5, m=1, b=0.01) N=100, control box +-20, IPDDP."""
+    B = batch or 1
+    N = horizon or 100
+    dt = 0.02
+    rng = np.random.default_rng(SEED_BASE + 11 + seed_offset)
+    spec = dict(model="pendulum", n=2, m=1, horizon=N, dt=dt, integrator="euler", params=[0.5, 1.0, 0.01],
+                Q=np.zeros((2, 2)), R=0.1 * np.eye(1), Qf=100.0 * np.eye(2), lb=None, ub=None)
+    options = dict(max_iterations=100, tolerance=1e-5, acceptable_tolerance=1e-6, reg_initial_value=1e-6)
+    constraints = [dict(type="control_box", lb=[-20.0], ub=[20.0])]
+    x0 = np.tile(np.array([math.pi, 0.0]), (B, 1))
+    if B > 1:
+        x0[1:] += 0.05 * rng.standard_normal((B - 1, 2))
+    xref = np.zeros((B, 2))
+    U0 = np.zeros((B, N, 1))
+    return dict(name="pendulum_ipddp", config_id=11, solver="ipddp", spec=spec, options=options, constraints=constraints,
+                ipddp_options={}, x0=x0, xref=xref, X0=None, U0=U0, ref_traj=None,
+                notes="pendulum swing-up, IPDDP + control box +-20 (examples/cddp_pendulum.cpp:27-67)")
+
+
+def _cfg_cartpole_ipddp(batch, horizon, seed_offset):
+    """examples/cddp_cartpole.cpp:27-68: CartPole rk4, control box +-5, IPDDP; plus a state box on the cart position
+    (StateConstraint) and a linear constraint so that every constraint kind is exercised."""
+    B = batch or 1
+    N = horizon or 100
+    dt = 0.05
+    rng = np.random.default_rng(SEED_BASE + 12 + seed_offset)
+    spec = dict(model="cartpole", n=4, m=1, horizon=N, dt=dt, integrator="rk4", params=[1.0, 0.2, 0.5, 9.81, 0.0],
+                Q=np.zeros((4, 4)), R=0.1 * np.eye(1), Qf=100.0 * np.eye(4), lb=None, ub=None)
+    options = dict(max_iterations=120, tolerance=1e-5, acceptable_tolerance=1e-6, reg_initial_value=1e-5)
+    big = 1e3
+    constraints = [dict(type="control_box", lb=[-5.0], ub=[5.0]),
+                   dict(type="state_box", lb=[-2.0, -big, -big, -big], ub=[2.0, big, big, big]),
+                   dict(type="linear", A=[[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, -1.0, 0.0]], b=[6.0, 6.0])]
+    x0 = np.zeros((B, 4))
+    if B > 1:
+        x0[1:] += 0.05 * rng.standard_normal((B - 1, 4))
+    xref = np.tile(np.array([0.0, math.pi, 0.0, 0.0]), (B, 1))
+    U0 = np.zeros((B, N, 1))
+    return dict(name="cartpole_ipddp", config_id=12, solver="ipddp", spec=spec, options=options, constraints=constraints,
+                ipddp_options={}, x0=x0, xref=xref, X0=None, U0=U0, ref_traj=None,
+                notes="cartpole swing-up, IPDDP, control box +-5 + state box + linear (examples/cddp_cartpole.cpp:27-68)")
+
+
+def _cfg_quadrotor_ipddp(batch, horizon, seed_offset):
+    """examples/cddp_quadrotor_point.cpp:23-98 as written (IPDDP, control box 0..5) with a shorter default horizon."""
+    cfg = _cfg_quadrotor(batch or 2, horizon or 60, seed_offset)
+    spec = dict(cfg["spec"], lb=None, ub=None)
+    options = dict(max_iterations=80, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-4, ls_max_iterations=11)
+    cfg.update(name="quadrotor_ipddp", config_id=13, solver="ipddp", spec=spec, options=options, X0=None, ipddp_options={},
+               constraints=[dict(type="control_box", lb=[0.0] * 4, ub=[5.0] * 4)],
+               notes="quadrotor point-to-point, IPDDP + control box 0..5 (examples/cddp_quadrotor_point.cpp:23-98)")
+    return cfg
 
 
 def shard(cfg: dict, rank: int, world: int) -> dict:

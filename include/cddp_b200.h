@@ -130,6 +130,50 @@ typedef struct {
   const double *ub;    /* [m] rawUpperBound */
 } cddp_b200_problem;
 
+/* ---- IPDDP: interior-point DDP with path inequality constraints (src/cddp_core/ipddp_solver.cpp) ----
+ * One entry of the path-constraint set = one addPathConstraint(name, constraint) call (cddp_core.cpp:156-161).
+ * Pass the entries in the order the reference iterates them: its std::map is keyed by constraint NAME, so
+ * alphabetical ("BallConstraint" < "ControlConstraint" < "LinearConstraint" < "StateConstraint").
+ *   CONTROL_BOX / STATE_BOX: p0 = lower [m|n], p1 = upper [m|n]; dual dim 2m | 2n   (constraint.hpp:144-251)
+ *   BALL  : rows = dimension of the centre, p0 = centre [rows], p1 = &radius; dual dim 1  (constraint.hpp:320-440)
+ *   LINEAR: rows, p0 = A [rows][n], p1 = b [rows]; dual dim rows; scale ignored as in the reference (:253-318) */
+enum { CDDP_B200_CON_CONTROL_BOX = 0, CDDP_B200_CON_STATE_BOX = 1, CDDP_B200_CON_BALL = 2, CDDP_B200_CON_LINEAR = 3 };
+typedef struct {
+  int type;
+  int rows;
+  double scale; /* scale_factor */
+  const double *p0;
+  const double *p1;
+} cddp_b200_constraint;
+
+/* BarrierStrategy (options.hpp:28-33); MONOTONIC and IPOPT share one update rule in IPDDP (ipddp_solver.cpp:2601-2613) */
+enum { CDDP_B200_BARRIER_ADAPTIVE = 0, CDDP_B200_BARRIER_MONOTONIC = 1, CDDP_B200_BARRIER_IPOPT = 2 };
+
+/* cddp::CDDPOptions::ipddp + ::filter (options.hpp:75-104, :148-186); defaults from
+ * cddp_b200_ipddp_default_options() equal the reference's member initialisers.  filter.armijo_constant is
+ * cddp_b200_options::armijo_constant. */
+typedef struct {
+  double dual_var_init_scale;            /* 1e-1 */
+  double slack_var_init_scale;           /* 1e-2 */
+  double barrier_tol_mult;               /* 0.1 */
+  double barrier_update_dual_weight;     /* 0.01 */
+  double mu_kappa_epsilon;               /* 10 */
+  double theta_0_floor;                  /* 1 */
+  double mu_initial;                     /* barrier.mu_initial 1 */
+  double mu_min_value;                   /* 1e-10 */
+  double mu_update_factor;               /* 0.5 */
+  double mu_update_power;                /* 1.2 */
+  double min_fraction_to_boundary;       /* 0.99 */
+  double merit_acceptance_threshold;     /* filter 1e-6 */
+  double violation_acceptance_threshold; /* 1e-6 */
+  double max_violation_threshold;        /* 1e4 */
+  double min_violation_for_armijo_check; /* 1e-7 */
+  int theta_norm_l2;                     /* theta_norm: 0 = "l1" (default), 1 = "l2" */
+  int max_filter_size;                   /* 5 (at most 7) */
+  int barrier_strategy;                  /* CDDP_B200_BARRIER_ADAPTIVE */
+  int reserved;
+} cddp_b200_ipddp_options;
+
 /* CUDA-event timings accumulated since the last cddp_b200_reset_timing(); one launch of each
  * kernel per batched DDP iteration. */
 typedef struct {
@@ -252,6 +296,31 @@ CDDP_B200_API int cddp_b200_get_sweep(cddp_b200_solver *s, double *dV, int *ok, 
 /* after forward_pass: costs [B][num_alphas], accepted alpha index [B] (-1 = none), candidate X,U of
  * the accepted alpha (unchanged nominal if none) */
 CDDP_B200_API int cddp_b200_get_forward(cddp_b200_solver *s, double *costs, int *accepted, double *Xnew, double *Unew);
+
+/* ---- IPDDP handle: replaces B x { CDDP::addPathConstraint(...); CDDP::solve("IPDDP") } (cddp_core.cpp:156-161,
+ * :235-270; IPDDPSolver, src/cddp_core/ipddp_solver.cpp).  Scope: cold start (options.warm_start = false),
+ * use_ilqr = true, path inequality constraints of the four kinds above, no terminal constraints, built-in models
+ * except LTI; problem->has_control_box is ignored (a ControlConstraint is an entry of `constraints`).  The handle is
+ * driven by the same entry points as a CLDDP handle: cddp_b200_set_instances (X0 is ignored: IPDDP re-rolls the
+ * state trajectory out from the given controls, ipddp_solver.cpp:876-882), cddp_b200_initialize / _linearize /
+ * _backward_pass / _forward_pass / _iterate / _solve, cddp_b200_get_solution (inf_du = unscaled max |Q_u|). ---- */
+CDDP_B200_API void cddp_b200_ipddp_default_options(cddp_b200_ipddp_options *opts);
+CDDP_B200_API int cddp_b200_ipddp_create(const cddp_b200_problem *problem, const cddp_b200_options *opts,
+                                         const cddp_b200_ipddp_options *ipddp_opts, const cddp_b200_constraint *constraints,
+                                         int num_constraints, int batch, int device, cddp_b200_solver **out);
+/* total dual dimension d of the handle's constraint set (getTotalDualDim, ipddp_solver.cpp:2134-2143); 0 for CLDDP handles */
+CDDP_B200_API int cddp_b200_ipddp_dual_dim(cddp_b200_solver *s, int *d);
+/* CDDPSolution interior-point fields (cddp_core.hpp:54-103; populateSolverSpecificSolution, ipddp_solver.cpp:2090-2097) and
+ * the dual / slack / constraint-value trajectories Y, S, G [B][N][d].  scalars [B][8] = final_barrier_mu, merit,
+ * inf_pr, inf_comp, step_norm, alpha_du, alpha_pr_max, alpha_du_max.  Any pointer may be NULL. */
+CDDP_B200_API int cddp_b200_ipddp_get_solution(cddp_b200_solver *s, double *Y, double *S, double *G, double *scalars);
+/* white box: slack/dual gains of the last backward pass, k_y,k_s [B][N][d], K_y,K_s [B][N][d][n]; line-search table
+ * [B][num_alphas][4] = accepted?, cost, barrier merit, theta of every alpha of the last forward pass */
+CDDP_B200_API int cddp_b200_ipddp_get_gains(cddp_b200_solver *s, double *ky, double *Ky, double *ks, double *Ks);
+CDDP_B200_API int cddp_b200_ipddp_get_line_search(cddp_b200_solver *s, double *table);
+/* History with interior-point columns: [B][max_iterations+1][9] = objective, merit, alpha_pr, alpha_du, inf_du, inf_pr,
+ * inf_comp, regularization, barrier_mu (cddp_b200_enable_history must have been called); lens [B] */
+CDDP_B200_API int cddp_b200_ipddp_get_history(cddp_b200_solver *s, double *history, int *lens);
 
 /* ---- measurement ---- */
 CDDP_B200_API int cddp_b200_reset_timing(cddp_b200_solver *s);
