@@ -676,10 +676,10 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
             a1 += gKs[((size_t)t * D + q) * n + j] * dx[j];
             a2 += gKy[((size_t)t * D + q) * n + j] * dx[j];
           }
-          const double ds = gks[(size_t)t * D + q] + a1;
-          const double dy = clampd(gky[(size_t)t * D + q] + a2, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
-          if (ds < 0.0) apm = fmin(apm, -tau_b * gS[(size_t)t * D + q] / ds);
-          if (dy < 0.0) adm = fmin(adm, -tau_b * gY[(size_t)t * D + q] / dy);
+          const double ds = __dadd_rn(gks[(size_t)t * D + q], a1);
+          const double dy = clampd(__dadd_rn(gky[(size_t)t * D + q], a2), -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+          if (ds < 0.0) apm = fmin(apm, __ddiv_rn(__dmul_rn(-tau_b, gS[(size_t)t * D + q]), ds));
+          if (dy < 0.0) adm = fmin(adm, __ddiv_rn(__dmul_rn(-tau_b, gY[(size_t)t * D + q]), dy));
         }
         for (int i = r; i < m; i += G) {
           double acc = 0.0;
@@ -793,9 +793,12 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
         a2 += gKy[e * NS + j] * dxv[j];
       }
       const double s0 = S0[e], y0 = Y0[e];
-      const double sn = (s0 + alpha_pr * gks[e]) + a1;
-      const double yn = (y0 + alpha_du * gky[e]) + a2;
-      if (sn < (1.0 - tau) * s0 || yn < (1.0 - tau) * y0) feas = false;
+      // No FMA contraction here: with alpha_pr at its fraction-to-boundary cap and dx = 0 (t = 0) the test below compares
+      // s + alpha ds against (1 - tau) s, which are EQUAL in exact arithmetic — the reference's decision is then made by
+      // the rounding of exactly these two operations (:1623-1630), so they are reproduced operation by operation.
+      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, gks[e])), a1);
+      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, gky[e])), a2);
+      if (sn < __dmul_rn(1.0 - tau, s0) || yn < __dmul_rn(1.0 - tau, y0)) feas = false;
       if (!finite_d(sn) || !finite_d(yn)) feas = false;
       const double g = con_value(ic, q, NS, NC, x, u);  // (:1743-1748)
       const double res = g + sn;

@@ -1581,6 +1581,11 @@ bool ip_backward(IpState &s) {
 struct IpTrial {
   bool success = false;
   double cost = 0, merit = 0, theta = 0, inf_pr = 0, inf_comp = 0, alpha_pr = 0, alpha_du = 0;
+  /* Test instrumentation (not in the reference): relative margin by which this trial's accept/reject decision was
+   * taken.  With alpha_pr at its fraction-to-boundary cap the slack test at t = 0 compares two numbers that are equal
+   * in exact arithmetic, so the reference's own decision is then made by roundoff; tests use the smallest margin of a
+   * solve to tell roundoff-decided instances from robust ones. */
+  double margin = 0;
   std::vector<double> X, U, Y, S, G;
 };
 
@@ -1589,6 +1594,8 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
   const int n = s.n, m = s.m, N = s.N, d = s.d;
   const oracle_problem *p = s.p;
   r.success = false;
+  r.margin = 1.0;
+  double feas_margin = 1.0;
   /* computeMaxStepSizes (:2939-2988) */
   const double tau_b = std::max(s.io->min_fraction_to_boundary, 1.0 - s.mu);
   double apm = 1.0, adm = 1.0;
@@ -1638,7 +1645,16 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
       }
       for (int i = 0; i < dim; ++i) {
         const size_t q = (size_t)t * d + o + i;
-        if (sn[i] < (1.0 - tau) * s.S[q] || yn[i] < (1.0 - tau) * s.Y[q]) return;
+        const double smin = (1.0 - tau) * s.S[q], ymin = (1.0 - tau) * s.Y[q];
+        const double ms = std::fabs(sn[i] - smin) / std::max(std::fabs(smin), 1e-300);
+        const double my = std::fabs(yn[i] - ymin) / std::max(std::fabs(ymin), 1e-300);
+        if (sn[i] < smin || yn[i] < ymin) {
+          /* rejected: the decision is as robust as this violation (the scan below looks for a clearer one) */
+          double best = std::max(sn[i] < smin ? ms : 0.0, yn[i] < ymin ? my : 0.0);
+          r.margin = best;
+          return;
+        }
+        feas_margin = std::min(feas_margin, std::min(ms, my));
       }
       if (!finite_vec(sn, dim) || !finite_vec(yn, dim)) return;
       for (int i = 0; i < dim; ++i) {
@@ -1668,26 +1684,37 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
   ip_primal_comp(s, r.G.data(), r.S.data(), r.Y.data(), s.mu, &ipn, &icn);
   if (!std::isfinite(phi_new) || !std::isfinite(theta_new) || !std::isfinite(ipn) || !std::isfinite(icn)) return;
   bool accept = false;
+  double acc_margin = 1.0;
+  auto rm = [](double a, double b) { return std::fabs(a - b) / std::max(std::max(std::fabs(a), std::fabs(b)), 1e-300); };
   if (s.nc == 0) { /* :1787-1794: hard-coded 1e-6 */
     const double dJ = s.cost - cost_new;
     const double expected = -alpha_pr * (s.dV[0] + 0.5 * alpha_pr * s.dV[1]);
     const double ratio = expected > 0.0 ? dJ / expected : std::copysign(1.0, dJ);
     accept = ratio > 1e-6;
+    acc_margin = std::fabs(dJ) / std::max(std::fabs(s.cost), 1e-300);
   } else { /* :1796-1839 */
     const double expected_improvement = alpha_pr * s.dV[0];
     const double cv_old = s.filter.empty() ? 0.0 : s.filter.back().theta;
     const double high_ref = s.filter.empty() ? s.filter_theta : cv_old;
     const double merit_old = s.merit;
     if (theta_new > s.io->max_violation_threshold) {
-      if (theta_new < (1 - s.io->violation_acceptance_threshold) * high_ref) accept = true;
+      const double rhs = (1 - s.io->violation_acceptance_threshold) * high_ref;
+      if (theta_new < rhs) accept = true;
+      acc_margin = rm(theta_new, rhs);
     } else if (std::max(theta_new, cv_old) < s.io->min_violation_for_armijo_check && expected_improvement < 0) {
-      if (phi_new < merit_old + s.o->armijo_constant * expected_improvement) accept = true;
+      const double rhs = merit_old + s.o->armijo_constant * expected_improvement;
+      if (phi_new < rhs) accept = true;
+      acc_margin = rm(phi_new, rhs);
     } else {
-      if (phi_new < merit_old - s.io->merit_acceptance_threshold * theta_new ||
-          theta_new < (1 - s.io->violation_acceptance_threshold) * cv_old)
-        accept = true;
+      const double r1 = merit_old - s.io->merit_acceptance_threshold * theta_new;
+      const double r2 = (1 - s.io->violation_acceptance_threshold) * cv_old;
+      const bool c1 = phi_new < r1, c2 = theta_new < r2;
+      if (c1 || c2) accept = true;
+      const double m1 = rm(phi_new, r1), m2 = rm(theta_new, r2);
+      acc_margin = accept ? std::max(c1 ? m1 : 0.0, c2 ? m2 : 0.0) : std::min(m1, m2);
     }
   }
+  r.margin = accept ? std::min(feas_margin, acc_margin) : acc_margin;
   if (!accept) return;
   r.success = true;
   r.cost = cost_new;
@@ -1766,6 +1793,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
   bool converged = false;
   const bool no_barrier = nc == 0;
   IpTrial trial;
+  double min_margin = 1.0;
   while (iter < o->max_iterations) {
     ++iter;
     bool backward_ok = false;
@@ -1799,6 +1827,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
     bool fp = false; /* performForwardPass, sequential (cddp_solver_base.cpp:255-263) */
     for (int ai = 0; ai < na; ++ai) {
       ip_forward(s, alphas[ai], trial);
+      min_margin = std::min(min_margin, trial.margin);
       if (trial.success) {
         fp = true;
         break;
@@ -1872,6 +1901,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
   res->inf_comp = s.inf_comp;
   res->mu = s.mu;
   res->merit = s.merit;
+  res->decision_margin = min_margin;
   res->iterations = iter;
   res->status = status;
   res->history_len = hl;

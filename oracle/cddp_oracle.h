@@ -207,6 +207,7 @@ typedef struct {
   double inf_comp;
   double mu;
   double merit;
+  double decision_margin; /* test instrumentation: smallest relative margin of any line-search accept/reject decision */
   int iterations;
   int status;
   int history_len;

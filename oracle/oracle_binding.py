@@ -306,7 +306,7 @@ class IpddpOptions(C.Structure):
 
 class IpddpResult(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("final_objective", "final_step_length", "final_regularization", "inf_du",
-                                          "inf_pr", "inf_comp", "mu", "merit")] + [
+                                          "inf_pr", "inf_comp", "mu", "merit", "decision_margin")] + [
         ("iterations", C.c_int), ("status", C.c_int), ("history_len", C.c_int), ("dual_dim", C.c_int)]
 
 
@@ -384,7 +384,7 @@ def ipddp_solve(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_traj=None
                               _p(U), _p(K), _p(Y), _p(S), C.byref(res), _p(hist))
     out = dict(X=X, U=U, K=K, Y=Y[:, :d], S=S[:, :d], cost=res.final_objective, alpha=res.final_step_length,
                reg=res.final_regularization, inf_du=res.inf_du, inf_pr=res.inf_pr, inf_comp=res.inf_comp, mu=res.mu,
-               merit=res.merit, iterations=res.iterations, status=res.status)
+               merit=res.merit, decision_margin=res.decision_margin, iterations=res.iterations, status=res.status)
     if history:
         out["history"] = hist[: res.history_len].copy()
     return out
@@ -404,7 +404,8 @@ def ipddp_solve_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_tra
     f = lambda k, dt=np.float64: np.array([getattr(r, k) for r in res], dtype=dt)  # noqa: E731
     return dict(X=X, U=U, K=K, Y=Y, S=S, cost=f("final_objective"), alpha=f("final_step_length"),
                 reg=f("final_regularization"), inf_du=f("inf_du"), inf_pr=f("inf_pr"), inf_comp=f("inf_comp"), mu=f("mu"),
-                merit=f("merit"), iterations=f("iterations", np.int32), status=f("status", np.int32))
+                merit=f("merit"), decision_margin=f("decision_margin"), iterations=f("iterations", np.int32),
+                status=f("status", np.int32))
 
 
 def ipddp_probe(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, iters, ref_traj=None):

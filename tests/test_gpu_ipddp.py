@@ -1,0 +1,171 @@
+"""GPU parity tests of the batched IPDDP path (cddp-cpp_b200/csrc/ipddp.cu, through the C ABI cddp_b200_ipddp_*) against
+the CPU oracle on the same seeded inputs.  Tolerances: 1e-9 relative for one backward pass / one line search on identical
+inputs; 1e-6 relative final cost for whole solves.
+
+Whole-solve parity procedure.  IPDDP's line search contains a decision the reference itself takes by roundoff: with
+alpha_pr at its fraction-to-boundary cap and dx = 0 (t = 0), `s + alpha ds < (1 - tau) s` compares two numbers that are
+equal in exact arithmetic (ipddp_solver.cpp:1623-1630, :2939-2988).  The oracle reports the smallest relative margin of
+all line-search decisions of a solve (decision_margin, test instrumentation).  As for CLDDP (DESIGN.md "Parity procedure")
+a long non-converging solve can also amplify roundoff chaotically, which the pair of oracle builds (strict /
+fp-contraction on) detects.  Instances with margin > 1e-9 on which the two oracle builds agree to 1e-7 are ROBUST:
+the CUDA path must reproduce their iteration count, status and final cost (1e-6).  On the others the CUDA result must be
+a valid solve: finite, feasible in the interior-point sense, cost of the returned trajectory, barrier parameter within
+the solver's schedule."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-9
+COST_TOL = 1e-6
+ROBUST_MARGIN = 1e-9
+CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "cartpole_ipddp", "quadrotor_ipddp"]
+
+
+def make(cddp, cfg, B, **opt_over):
+    opts = dict(cfg["options"], **opt_over)
+    s = cddp.BatchedIPDDP(cfg["spec"], cddp.default_options(**opts), cddp.default_ipddp_options(**cfg.get("ipddp_options", {})),
+                          cfg["constraints"], B)
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], cfg["ref_traj"])
+    return s, opts
+
+
+def robust_mask(ob, P, oo, oi, cs, cfg, o):
+    with ob.variant():
+        o2 = ob.ipddp_solve_batch(P, oo, oi, cs, cfg["x0"], cfg["xref"], cfg["U0"], cfg["ref_traj"], nthreads=4)
+    return ((o["decision_margin"] > ROBUST_MARGIN) & (o2["decision_margin"] > ROBUST_MARGIN) &
+            (o["iterations"] == o2["iterations"]) & (np.abs(o["cost"] - o2["cost"]) <= 1e-7 * np.abs(o["cost"])))
+
+
+def oracle_of(ob, cfg, opts):
+    return (ob.OracleProblem(cfg["spec"]), ob.make_options(**opts), ob.make_ipddp_options(**cfg.get("ipddp_options", {})),
+            ob.ConstraintSet(cfg["constraints"]))
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("iters", [0, 2])
+def test_single_iteration_steps(cddp, ob, problems, name, iters):
+    """initialize (+ `iters` iterations) -> backward pass -> line search, each quantity against the oracle."""
+    B = 5
+    cfg = problems.make_config(name, batch=B, horizon=50)
+    s, opts = make(cddp, cfg, B)
+    P, oo, oi, cs = oracle_of(ob, cfg, opts)
+    s.initialize()
+    if iters:
+        s.iterate(iters)
+    s.linearize()
+    s.backward_pass()
+    s.forward_pass()
+    sol, ips, gains, sw, kff, ls = (s.get_solution(), s.get_ipddp_solution(), s.get_ipddp_gains(), s.get_sweep(),
+                                    s.get_feedforward(), s.get_line_search())
+    fw = s.get_forward()
+    for b in range(B):
+        r = ob.ipddp_probe(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], iters)
+        if iters and ob.ipddp_solve(P, ob.make_options(**dict(opts, max_iterations=iters)), oi, cs, cfg["x0"][b], cfg["xref"][b],
+                                    cfg["U0"][b])["decision_margin"] < ROBUST_MARGIN:
+            continue  # the first `iters` iterations already contain a roundoff-decided line search
+        for key, val in (("X", sol["X"][b]), ("U", sol["U"][b]), ("Y", ips["Y"][b]), ("S", ips["S"][b]), ("G", ips["G"][b])):
+            assert rel_err(val, r[key]) < STEP_TOL, (name, b, key)
+        assert sw["ok"][b] == 1 and r["bw_ok"] == 1.0
+        for key, val in (("ku", kff[b]), ("Ku", sol["K"][b]), ("ky", gains["ky"][b]), ("Ky", gains["Ky"][b]),
+                         ("ks", gains["ks"][b]), ("Ks", gains["Ks"][b])):
+            assert rel_err(val, r[key]) < STEP_TOL, (name, b, key)
+        for key, val in (("mu", ips["mu"][b]), ("cost", sol["cost"][b]), ("merit", ips["merit"][b]), ("inf_du", sol["inf_du"][b]),
+                         ("inf_comp", ips["inf_comp"][b]), ("step_norm", ips["step_norm"][b]), ("reg", sol["reg"][b]),
+                         ("dV0", sw["dV"][b, 0]), ("dV1", sw["dV"][b, 1]), ("alpha_pr_max", ips["alpha_pr_max"][b]),
+                         ("alpha_du_max", ips["alpha_du_max"][b])):
+            assert abs(val - r[key]) <= STEP_TOL * max(abs(r[key]), 1e-300), (name, b, key, val, r[key])
+        assert abs(ips["inf_pr"][b] - r["inf_pr"]) <= 1e-9 * abs(r["inf_pr"]) + 1e-13  # residuals of ~1e-15 carry no digits
+        acc_g, acc_c = ls[b][:, 0].astype(int), r["trial"][:, 0].astype(int)
+        first_c = int(np.argmax(acc_c)) if acc_c.any() else -1
+        assert fw["accepted"][b] == first_c, (name, b, acc_g, acc_c)
+        if first_c >= 0:  # the accepted alpha: cost, barrier merit, theta
+            assert abs(ls[b][first_c, 1] - r["trial"][first_c, 1]) <= 1e-8 * abs(r["trial"][first_c, 1])
+            assert abs(ls[b][first_c, 2] - r["trial"][first_c, 2]) <= 1e-8 * max(abs(r["trial"][first_c, 2]), abs(r["trial"][first_c, 1]))
+            assert abs(ls[b][first_c, 3] - r["trial"][first_c, 3]) <= 1e-8 * abs(r["trial"][first_c, 3]) + 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_whole_solve(cddp, ob, problems, name):
+    B = 12
+    cfg = problems.make_config(name, batch=B)
+    s, opts = make(cddp, cfg, B)
+    P, oo, oi, cs = oracle_of(ob, cfg, opts)
+    s.enable_history(True)
+    s.solve()
+    g, gi = s.get_solution(), s.get_ipddp_solution()
+    h, hl = s.get_history()
+    o = ob.ipddp_solve_batch(P, oo, oi, cs, cfg["x0"], cfg["xref"], cfg["U0"], cfg["ref_traj"], nthreads=4)
+    robust = robust_mask(ob, P, oo, oi, cs, cfg, o)
+    if name in ("unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp"):
+        assert robust.sum() >= B // 2, "workload expected to be mostly roundoff-robust"
+    for b in range(B):
+        assert np.isfinite(g["cost"][b]) and np.isfinite(g["X"][b]).all()
+        assert abs(ob.trajectory_cost(P, g["X"][b], g["U"][b], cfg["xref"][b]) - g["cost"][b]) <= 1e-10 * abs(g["cost"][b])
+        if cs.nc:
+            assert (gi["S"][b] > 0).all() and (gi["Y"][b] > 0).all()
+            G = np.array([ob.eval_constraints(P, cs, g["X"][b][t], g["U"][b][t])[0] for t in range(P.N)])
+            assert rel_err(gi["G"][b], G) < 1e-12
+            assert np.abs(G + gi["S"][b]).max() <= gi["inf_pr"][b] * (1 + 1e-9) + 1e-14
+            if g["status"][b] in (1, 2):
+                assert G.max() < 1e-3
+        assert np.all(np.diff(h[b, : hl[b], 8]) <= 0.0)
+        if robust[b]:
+            assert g["iterations"][b] == o["iterations"][b] and g["status"][b] == o["status"][b], (name, b)
+            assert abs(g["cost"][b] - o["cost"][b]) <= COST_TOL * abs(o["cost"][b]), (name, b)
+            assert abs(gi["mu"][b] - o["mu"][b]) <= 1e-9 * o["mu"][b]
+            assert rel_err(g["X"][b], o["X"][b]) < 1e-5 and rel_err(g["U"][b], o["U"][b]) < 1e-4
+    # per-iteration trace of the first robust instance: objective, merit, alpha_pr, alpha_du, inf_du, reg, mu
+    for b in np.flatnonzero(robust)[:1]:
+        r0 = ob.ipddp_solve(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], history=True)
+        assert hl[b] == len(r0["history"])
+        for col in (0, 1, 2, 3, 4, 7, 8):
+            assert rel_err(h[b, : hl[b], col], r0["history"][:, col]) < 1e-6, (name, b, col)
+    s.close()
+
+
+def test_full_size_config4_properties(cddp, ob, problems):
+    """BASELINE config #4's path-constraint workload at its per-GPU size (2048 instances / 4 GPUs = 512 per GPU; the
+    whole 2048 here), N = 200: every instance finite, returned trajectories satisfy the obstacle and box constraints,
+    batch independence (a slice solved alone is bitwise identical), oracle parity on a robust slice."""
+    B = 2048
+    cfg = problems.make_config("unicycle_obstacle", batch=B)
+    s, opts = make(cddp, cfg, B)
+    s.solve()
+    g, gi = s.get_solution(want_K=False), s.get_ipddp_solution(False)
+    assert np.isfinite(g["cost"]).all() and np.isfinite(g["X"]).all() and np.isfinite(g["U"]).all()
+    conv = np.isin(g["status"], (1, 2))
+    assert conv.mean() > 0.9
+    dist = np.hypot(g["X"][:, :-1, 0] - 1.0, g["X"][:, :-1, 1] - 1.0)
+    assert (dist[conv] > 0.4 - 1e-3).all(), "converged trajectories avoid the obstacle"
+    assert (np.abs(g["U"][conv, :, 0]) <= 1.1 + 1e-6).all() and (np.abs(g["U"][conv, :, 1]) <= np.pi + 1e-6).all()
+    s.close()
+    sl = slice(100, 140)
+    sub = dict(cfg, x0=cfg["x0"][sl], xref=cfg["xref"][sl], U0=cfg["U0"][sl])
+    s2, _ = make(cddp, sub, 40)
+    s2.solve()
+    g2 = s2.get_solution(want_K=False)
+    assert np.array_equal(g2["cost"], g["cost"][sl]) and np.array_equal(g2["X"], g["X"][sl])
+    s2.close()
+    P, oo, oi, cs = oracle_of(ob, cfg, opts)
+    o = ob.ipddp_solve_batch(P, oo, oi, cs, sub["x0"], sub["xref"], sub["U0"], nthreads=8)
+    robust = robust_mask(ob, P, oo, oi, cs, dict(sub, ref_traj=None), o)
+    assert robust.sum() >= 20
+    assert (g2["iterations"][robust] == o["iterations"][robust]).all()
+    assert (np.abs(g2["cost"][robust] - o["cost"][robust]) <= COST_TOL * np.abs(o["cost"][robust])).all()
+
+
+def test_errors_and_scope(cddp, problems):
+    """Setup errors are error codes (the C++ shim turns them into std::runtime_error): LTI is not supported by the IPDDP
+    handle, more than 16 line-search alphas, an unknown constraint kind."""
+    cfg = problems.make_config("unicycle_obstacle", batch=2, horizon=10)
+    with pytest.raises(cddp.CddpB200Error):
+        cddp.BatchedIPDDP(cfg["spec"], cddp.default_options(ls_max_iterations=20), cddp.default_ipddp_options(), cfg["constraints"], 2)
+    with pytest.raises(cddp.CddpB200Error):
+        cddp.BatchedIPDDP(cfg["spec"], cddp.default_options(), cddp.default_ipddp_options(max_filter_size=9), cfg["constraints"], 2)
+    lti = problems.make_config("lti", batch=2)
+    with pytest.raises(cddp.CddpB200Error):
+        cddp.BatchedIPDDP(lti["spec"], cddp.default_options(), cddp.default_ipddp_options(), [], 2)
