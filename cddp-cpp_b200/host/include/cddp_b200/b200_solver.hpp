@@ -20,8 +20,26 @@ class CLDDPSolver : public ISolverAlgorithm {
   int device_;
 };
 
+// Drop-in for cddp::IPDDPSolver (src/cddp_core/ipddp_solver.cpp): cold start, use_ilqr = true, path inequality
+// constraints of the kinds ControlConstraint / StateConstraint / LinearConstraint / BallConstraint, no terminal
+// constraints.  Anything else (terminal constraints, warm_start, use_ilqr = false, other constraint classes, LTISystem)
+// is a setup error: std::runtime_error, never a CPU fallback.
+class IPDDPSolver : public ISolverAlgorithm {
+ public:
+  explicit IPDDPSolver(int device = 0) : device_(device) {}
+  void initialize(CDDP &context) override;
+  CDDPSolution solve(CDDP &context) override;
+  std::string getSolverName() const override { return "IPDDP"; }
+
+ private:
+  int device_;
+};
+
+// Batched IPDDP facade: same contract as solveBatch; the constraint sets must be identical across the batch.
+std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, int device = 0);
+
 // Registers the B200 solver under "CLDDP" (shadows the name the reference's built-in uses — SolverPrecedence
-// semantics, tests/cddp_core/test_cddp_core.cpp:463-483) and under "CLDDP_B200".
+// semantics, tests/cddp_core/test_cddp_core.cpp:463-483) and under "CLDDP_B200"; likewise "IPDDP" / "IPDDP_B200".
 void registerSolvers(int device = 0);
 
 // Batched facade: B structurally identical problems (same model + parameters, objective weights, horizon, timestep,

@@ -66,6 +66,28 @@ struct SolverSpecificFilterOptions {  // options.hpp:93-105 (CLDDP reads armijo_
   double min_violation_for_armijo_check = 1e-7;
   double armijo_constant = 1e-4;
 };
+enum class BarrierStrategy { ADAPTIVE, MONOTONIC, IPOPT };  // options.hpp:28-33
+struct SolverSpecificBarrierOptions {  // options.hpp:75-87
+  double mu_initial = 1e-0;
+  double mu_min_value = 1e-10;
+  double mu_update_factor = 0.5;
+  double mu_update_power = 1.2;
+  double min_fraction_to_boundary = 0.99;
+  BarrierStrategy strategy = BarrierStrategy::ADAPTIVE;
+};
+struct IPDDPAlgorithmOptions {  // options.hpp:148-186 (the members the cold-start path-constraint path reads)
+  double dual_var_init_scale = 1e-1;
+  double slack_var_init_scale = 1e-2;
+  double barrier_tol_mult = 0.1;
+  double barrier_update_dual_weight = 0.01;
+  double mu_kappa_epsilon = 10.0;
+  bool check_state_stationarity = false;
+  std::string theta_norm = "l1";
+  int max_filter_size = 5;
+  double theta_0_floor = 1.0;
+  bool warmstart_repair = false;
+  SolverSpecificBarrierOptions barrier;
+};
 struct CDDPOptions {  // options.hpp:208-251
   double tolerance = 1e-5;
   double acceptable_tolerance = 1e-6;
@@ -85,6 +107,7 @@ struct CDDPOptions {  // options.hpp:208-251
   RegularizationOptions regularization;
   BoxQPOptions box_qp;
   SolverSpecificFilterOptions filter;
+  IPDDPAlgorithmOptions ipddp;
 };
 
 namespace detail {
@@ -263,6 +286,72 @@ class ControlConstraint : public Constraint {  // constraint.hpp:144-251 (BoxCon
 
  private:
   Eigen::VectorXd lower_bound_, upper_bound_;
+};
+
+class StateConstraint : public Constraint {  // constraint.hpp:144-251 (BoxConstraint<State>)
+ public:
+  StateConstraint(const Eigen::VectorXd &lower_bound, const Eigen::VectorXd &upper_bound, double scale_factor = 1.0)
+      : Constraint("StateConstraint"), lower_bound_(lower_bound), upper_bound_(upper_bound), scale_factor_(scale_factor) {}
+  int getDualDim() const override { return 2 * (int)upper_bound_.size(); }
+  Eigen::VectorXd evaluate(const Eigen::VectorXd &state, const Eigen::VectorXd &, int = 0) const override {  // [-x; x] * scale
+    const long k = state.size();
+    Eigen::VectorXd g(2 * k);
+    for (long i = 0; i < k; ++i) { g[i] = -state[i] * scale_factor_; g[k + i] = state[i] * scale_factor_; }
+    return g;
+  }
+  Eigen::VectorXd getLowerBound() const override { return Eigen::VectorXd::Constant(getDualDim(), -std::numeric_limits<double>::infinity()); }
+  Eigen::VectorXd getUpperBound() const override {  // [-lb; ub] * scale (:156-159)
+    const long k = upper_bound_.size();
+    Eigen::VectorXd g(2 * k);
+    for (long i = 0; i < k; ++i) { g[i] = -lower_bound_[i] * scale_factor_; g[k + i] = upper_bound_[i] * scale_factor_; }
+    return g;
+  }
+  const Eigen::VectorXd &rawLowerBound() const { return lower_bound_; }
+  const Eigen::VectorXd &rawUpperBound() const { return upper_bound_; }
+  double getScaleFactor() const { return scale_factor_; }
+
+ private:
+  Eigen::VectorXd lower_bound_, upper_bound_;
+  double scale_factor_;
+};
+
+class LinearConstraint : public Constraint {  // constraint.hpp:253-318: A x <= b (scale_factor is stored, never applied)
+ public:
+  LinearConstraint(const Eigen::MatrixXd &A, const Eigen::VectorXd &b, double scale_factor = 1.0)
+      : Constraint("LinearConstraint"), A_(A), b_(b), scale_factor_(scale_factor) {}
+  int getDualDim() const override { return (int)b_.size(); }
+  Eigen::VectorXd evaluate(const Eigen::VectorXd &state, const Eigen::VectorXd &, int = 0) const override { return A_ * state; }
+  Eigen::VectorXd getLowerBound() const override { return Eigen::VectorXd::Constant(b_.size(), -std::numeric_limits<double>::infinity()); }
+  Eigen::VectorXd getUpperBound() const override { return b_; }
+  const Eigen::MatrixXd &getA() const { return A_; }
+  double getScaleFactor() const { return scale_factor_; }
+
+ private:
+  Eigen::MatrixXd A_;
+  Eigen::VectorXd b_;
+  double scale_factor_;
+};
+
+class BallConstraint : public Constraint {  // constraint.hpp:320-440: -scale |x[0:dim] - center|^2 <= -scale r^2
+ public:
+  BallConstraint(double radius, const Eigen::VectorXd &center, double scale_factor = 1.0)
+      : Constraint("BallConstraint"), radius_(radius), center_(center), scale_factor_(scale_factor) {}
+  int getDualDim() const override { return 1; }
+  Eigen::VectorXd evaluate(const Eigen::VectorXd &state, const Eigen::VectorXd &, int = 0) const override {
+    double sq = 0.0;
+    for (long i = 0; i < center_.size(); ++i) sq += (state[i] - center_[i]) * (state[i] - center_[i]);
+    return Eigen::VectorXd::Constant(1, -(scale_factor_ * sq));
+  }
+  Eigen::VectorXd getLowerBound() const override { return Eigen::VectorXd::Constant(1, -std::numeric_limits<double>::infinity()); }
+  Eigen::VectorXd getUpperBound() const override { return Eigen::VectorXd::Constant(1, -(radius_ * radius_) * scale_factor_); }
+  const Eigen::VectorXd &getCenter() const { return center_; }
+  double getRadius() const { return radius_; }
+  double getScaleFactor() const { return scale_factor_; }
+
+ private:
+  double radius_;
+  Eigen::VectorXd center_;
+  double scale_factor_;
 };
 
 // Terminal constraints (terminal_constraint.hpp:29-158).  CLDDP never reads them (clddp_solver.cpp looks up

@@ -237,10 +237,231 @@ CDDPSolution CLDDPSolver::solve(CDDP &context) {
   return solveBatch(one, device_)[0];
 }
 
+// ------------------------------------------------------------------------------------------------ IPDDP
+namespace {
+
+struct ConDesc {  // one path constraint in C-ABI form, with its backing storage
+  int type = 0, rows = 0;
+  double scale = 1.0;
+  std::vector<double> p0, p1;
+  bool operator==(const ConDesc &o) const { return type == o.type && rows == o.rows && scale == o.scale && p0 == o.p0 && p1 == o.p1; }
+};
+
+struct IpShared {
+  cddp_b200_ipddp_options io{};
+  std::vector<ConDesc> cons;
+};
+
+void describe_ipddp(CDDP &ctx, IpShared &s) {
+  const CDDPOptions &o = ctx.getOptions();
+  if (o.warm_start) throw std::runtime_error("B200 IPDDP: options.warm_start is not supported by the device path");
+  if (!o.use_ilqr) throw std::runtime_error("B200 IPDDP: use_ilqr = false (second-order dynamics terms) is not supported by the device path");
+  if (!ctx.getTerminalConstraintSet().empty())
+    throw std::runtime_error("B200 IPDDP: terminal constraints are not supported by the device path");
+  if (o.ipddp.check_state_stationarity || o.ipddp.warmstart_repair)
+    throw std::runtime_error("B200 IPDDP: check_state_stationarity / warmstart_repair are not supported by the device path");
+  cddp_b200_ipddp_default_options(&s.io);
+  s.io.dual_var_init_scale = o.ipddp.dual_var_init_scale;
+  s.io.slack_var_init_scale = o.ipddp.slack_var_init_scale;
+  s.io.barrier_tol_mult = o.ipddp.barrier_tol_mult;
+  s.io.barrier_update_dual_weight = o.ipddp.barrier_update_dual_weight;
+  s.io.mu_kappa_epsilon = o.ipddp.mu_kappa_epsilon;
+  s.io.theta_0_floor = o.ipddp.theta_0_floor;
+  s.io.mu_initial = o.ipddp.barrier.mu_initial;
+  s.io.mu_min_value = o.ipddp.barrier.mu_min_value;
+  s.io.mu_update_factor = o.ipddp.barrier.mu_update_factor;
+  s.io.mu_update_power = o.ipddp.barrier.mu_update_power;
+  s.io.min_fraction_to_boundary = o.ipddp.barrier.min_fraction_to_boundary;
+  s.io.merit_acceptance_threshold = o.filter.merit_acceptance_threshold;
+  s.io.violation_acceptance_threshold = o.filter.violation_acceptance_threshold;
+  s.io.max_violation_threshold = o.filter.max_violation_threshold;
+  s.io.min_violation_for_armijo_check = o.filter.min_violation_for_armijo_check;
+  s.io.theta_norm_l2 = o.ipddp.theta_norm == "l2" ? 1 : 0;
+  s.io.max_filter_size = o.ipddp.max_filter_size;
+  s.io.barrier_strategy = o.ipddp.barrier.strategy == BarrierStrategy::ADAPTIVE ? CDDP_B200_BARRIER_ADAPTIVE
+                          : o.ipddp.barrier.strategy == BarrierStrategy::MONOTONIC ? CDDP_B200_BARRIER_MONOTONIC : CDDP_B200_BARRIER_IPOPT;
+  const int n = ctx.getStateDim();
+  // std::map iteration = the reference's constraint order (ipddp_solver.cpp:1375-1390)
+  for (const auto &kv : ctx.getConstraintSet()) {
+    ConDesc c;
+    const Constraint *base = kv.second.get();
+    if (auto *cc = dynamic_cast<const ControlConstraint *>(base)) {
+      c.type = CDDP_B200_CON_CONTROL_BOX;
+      c.rows = (int)cc->rawLowerBound().size();
+      c.p0.assign(cc->rawLowerBound().data(), cc->rawLowerBound().data() + c.rows);
+      c.p1.assign(cc->rawUpperBound().data(), cc->rawUpperBound().data() + c.rows);
+    } else if (auto *sc = dynamic_cast<const StateConstraint *>(base)) {
+      c.type = CDDP_B200_CON_STATE_BOX;
+      c.rows = (int)sc->rawLowerBound().size();
+      c.scale = sc->getScaleFactor();
+      c.p0.assign(sc->rawLowerBound().data(), sc->rawLowerBound().data() + c.rows);
+      c.p1.assign(sc->rawUpperBound().data(), sc->rawUpperBound().data() + c.rows);
+    } else if (auto *bc = dynamic_cast<const BallConstraint *>(base)) {
+      c.type = CDDP_B200_CON_BALL;
+      c.rows = (int)bc->getCenter().size();
+      c.scale = bc->getScaleFactor();
+      c.p0.assign(bc->getCenter().data(), bc->getCenter().data() + c.rows);
+      c.p1.assign(1, bc->getRadius());
+    } else if (auto *lc = dynamic_cast<const LinearConstraint *>(base)) {
+      c.type = CDDP_B200_CON_LINEAR;
+      c.rows = (int)lc->getUpperBound().size();
+      c.scale = lc->getScaleFactor();
+      if (lc->getA().cols() != n) throw std::runtime_error("B200 IPDDP: LinearConstraint A has the wrong number of columns");
+      flatten(lc->getA(), c.p0);
+      const Eigen::VectorXd b = lc->getUpperBound();
+      c.p1.assign(b.data(), b.data() + c.rows);
+    } else {
+      throw std::runtime_error("B200 IPDDP: path constraint '" + kv.first + "' has no device implementation (supported: ControlConstraint, "
+                               "StateConstraint, LinearConstraint, BallConstraint); there is no CPU fallback");
+    }
+    s.cons.push_back(std::move(c));
+  }
+}
+
+}  // namespace
+
+std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, int device) {
+  if (problems.empty()) return {};
+  const auto t_start = std::chrono::high_resolution_clock::now();
+  const int B = (int)problems.size();
+  Shared sh;
+  IpShared ish;
+  describe(*problems[0], sh);
+  describe_ipddp(*problems[0], ish);
+  if (sh.has_ref_traj) throw std::runtime_error("B200 IPDDP: per-timestep reference states are not supported by the device path");
+  for (int b = 1; b < B; ++b) {
+    Shared other;
+    IpShared iother;
+    describe(*problems[b], other);
+    describe_ipddp(*problems[b], iother);
+    if (!same_shared(sh, other) || std::memcmp(&ish.io, &iother.io, sizeof(ish.io)) != 0 || !(ish.cons == iother.cons))
+      throw std::runtime_error("B200 IPDDP: solveBatchIPDDP needs structurally identical problems (model, weights, horizon, timestep, "
+                               "options, constraint set); instance " + std::to_string(b) + " differs from instance 0");
+  }
+  sh.p.has_control_box = 0;  // a ControlConstraint is a row pair of the constraint set here, never a clamp
+  bind_pointers(sh);
+  std::vector<cddp_b200_constraint> cs(ish.cons.size());
+  for (size_t i = 0; i < cs.size(); ++i) {
+    cs[i].type = ish.cons[i].type;
+    cs[i].rows = ish.cons[i].rows;
+    cs[i].scale = ish.cons[i].scale;
+    cs[i].p0 = ish.cons[i].p0.data();
+    cs[i].p1 = ish.cons[i].p1.data();
+  }
+  const int n = sh.p.n, m = sh.p.m, N = sh.p.horizon;
+  std::vector<double> x0((size_t)B * n), xref((size_t)B * n), X((size_t)B * (N + 1) * n), U((size_t)B * N * m);
+  for (int b = 0; b < B; ++b) {
+    CDDP &c = *problems[b];
+    c.initializeProblemIfNecessary();
+    const Eigen::VectorXd ref = c.getObjective().getReferenceState();
+    if ((int)ref.size() != n) throw std::runtime_error("B200 IPDDP: reference state has the wrong dimension");
+    for (int i = 0; i < n; ++i) {
+      x0[(size_t)b * n + i] = c.getInitialState()[i];
+      xref[(size_t)b * n + i] = ref[i];
+    }
+    for (int t = 0; t < N; ++t)
+      for (int i = 0; i < m; ++i) U[((size_t)b * N + t) * m + i] = c.U_[(size_t)t][i];
+  }
+  std::vector<double> K((size_t)B * N * m * n), cost((size_t)B), alpha((size_t)B), reg((size_t)B), inf_du((size_t)B), sc((size_t)B * 8);
+  std::vector<int> iters((size_t)B), status((size_t)B);
+  const bool want_hist = problems[0]->getOptions().return_iteration_info;
+  std::vector<double> hist;
+  std::vector<int> hist_len;
+  cddp_b200_solver *h = nullptr;
+  check(cddp_b200_ipddp_create(&sh.p, &sh.o, &ish.io, cs.empty() ? nullptr : cs.data(), (int)cs.size(), B, device, &h), "ipddp_create");
+  struct Guard {
+    cddp_b200_solver *h;
+    ~Guard() { cddp_b200_destroy(h); }
+  } guard{h};
+  if (want_hist) check(cddp_b200_enable_history(h, 1), "enable_history");
+  check(cddp_b200_set_instances(h, x0.data(), xref.data(), nullptr, nullptr, U.data()), "set_instances");
+  check(cddp_b200_solve(h), "solve");
+  check(cddp_b200_get_solution(h, X.data(), U.data(), K.data(), cost.data(), iters.data(), status.data(), alpha.data(), reg.data(),
+                               inf_du.data()), "get_solution");
+  check(cddp_b200_ipddp_get_solution(h, nullptr, nullptr, nullptr, sc.data()), "ipddp_get_solution");
+  const int cap = sh.o.max_iterations + 1;
+  if (want_hist) {
+    hist.resize((size_t)B * cap * 9);
+    hist_len.resize((size_t)B);
+    check(cddp_b200_ipddp_get_history(h, hist.data(), hist_len.data()), "ipddp_get_history");
+  }
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();
+  std::vector<CDDPSolution> out((size_t)B);
+  for (int b = 0; b < B; ++b) {
+    CDDP &c = *problems[b];
+    CDDPSolution &s = out[(size_t)b];
+    const double *q = &sc[(size_t)b * 8];  // mu, merit, inf_pr, inf_comp, step_norm, alpha_du, alpha_pr_max, alpha_du_max
+    s.solver_name = "IPDDP";
+    s.status_message = cddp_b200_status_string(status[(size_t)b]);
+    s.iterations_completed = iters[(size_t)b];
+    s.solve_time_ms = ms;
+    s.final_objective = cost[(size_t)b];
+    s.final_step_length = alpha[(size_t)b];
+    s.final_regularization = reg[(size_t)b];
+    s.final_barrier_mu = q[0];  // populateSolverSpecificSolution (ipddp_solver.cpp:2090-2097)
+    s.final_primal_infeasibility = q[2];
+    s.final_dual_infeasibility = inf_du[(size_t)b];
+    s.final_complementary_infeasibility = q[3];
+    s.time_points.resize((size_t)N + 1);
+    s.state_trajectory.assign((size_t)N + 1, Eigen::VectorXd::Zero(n));
+    s.control_trajectory.assign((size_t)N, Eigen::VectorXd::Zero(m));
+    s.feedback_gains.assign((size_t)N, Eigen::MatrixXd::Zero(m, n));
+    for (int t = 0; t <= N; ++t) {
+      s.time_points[(size_t)t] = t * sh.p.dt;
+      for (int i = 0; i < n; ++i) s.state_trajectory[(size_t)t][i] = X[((size_t)b * (N + 1) + t) * n + i];
+    }
+    for (int t = 0; t < N; ++t)
+      for (int i = 0; i < m; ++i) {
+        s.control_trajectory[(size_t)t][i] = U[((size_t)b * N + t) * m + i];
+        for (int j = 0; j < n; ++j) s.feedback_gains[(size_t)t](i, j) = K[(((size_t)b * N + t) * m + i) * n + j];
+      }
+    if (want_hist)
+      for (int k = 0; k < hist_len[(size_t)b]; ++k) {
+        const double *row = &hist[((size_t)b * cap + k) * 9];
+        s.history.objective.push_back(row[0]);
+        s.history.merit_function.push_back(row[1]);
+        s.history.step_length_primal.push_back(row[2]);
+        s.history.step_length_dual.push_back(row[3]);
+        s.history.dual_infeasibility.push_back(row[4]);
+        s.history.primal_infeasibility.push_back(row[5]);
+        s.history.complementary_infeasibility.push_back(row[6]);
+        s.history.regularization.push_back(row[7]);
+        s.history.barrier_mu.push_back(row[8]);
+      }
+    c.X_ = s.state_trajectory;
+    c.U_ = s.control_trajectory;
+    c.cost_ = s.final_objective;
+    c.merit_function_ = q[1];
+    c.inf_pr_ = q[2];
+    c.inf_du_ = inf_du[(size_t)b];
+    c.inf_comp_ = q[3];
+    c.step_norm_ = q[4];
+    c.alpha_pr_ = s.final_step_length;
+    c.alpha_du_ = q[5];
+    c.regularization_ = s.final_regularization;
+  }
+  return out;
+}
+
+void IPDDPSolver::initialize(CDDP &context) {
+  Shared s;
+  IpShared is;
+  describe(context, s);
+  describe_ipddp(context, is);
+}
+
+CDDPSolution IPDDPSolver::solve(CDDP &context) {
+  std::vector<CDDP *> one{&context};
+  return solveBatchIPDDP(one, device_)[0];
+}
+
 void registerSolvers(int device) {
   auto factory = [device]() { return std::unique_ptr<ISolverAlgorithm>(new CLDDPSolver(device)); };
   CDDP::registerSolver("CLDDP", factory);
   CDDP::registerSolver("CLDDP_B200", factory);
+  auto ip_factory = [device]() { return std::unique_ptr<ISolverAlgorithm>(new IPDDPSolver(device)); };
+  CDDP::registerSolver("IPDDP", ip_factory);
+  CDDP::registerSolver("IPDDP_B200", ip_factory);
 }
 
 }  // namespace b200

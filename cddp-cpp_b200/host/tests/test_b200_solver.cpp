@@ -163,11 +163,94 @@ void SolveQuadrotorBatch() {
   }
   CHECK(threw);
 }
+
+// IPDDP through the registry, written like the reference's IPDDP tests (tests/cddp_core/test_ipddp_solver.cpp:552-620
+// SolveUnicycle: status in {Optimal, Acceptable}) on the obstacle-avoidance problem of examples/python_portfolio_lib.py:
+// 374-473 (ControlConstraint + BallConstraint), single solve and batched facade, with oracle parity.
+void SolveUnicycleObstacleIPDDP() {
+  const int N = 100, B = 6;
+  const double dt = 0.03;
+  CDDPOptions o;
+  o.max_iterations = 150; o.tolerance = 1e-4; o.acceptable_tolerance = 1e-6; o.regularization.initial_value = 1e-6; o.verbose = false;
+  o.return_iteration_info = true;
+  const Eigen::MatrixXd Q = Eigen::MatrixXd::Zero(3, 3), R = diag({0.05, 0.05}), Qf = diag({100, 100, 50});
+  std::vector<std::unique_ptr<CDDP>> owners;
+  std::vector<CDDP *> batch;
+  for (int b = 0; b < B; ++b) {
+    const auto x0 = vec({0.0, 0.0, 0.0}), goal = vec({2.0 + 0.03 * b, 2.0 - 0.02 * b, M_PI / 2.0});
+    auto c = std::make_unique<CDDP>(x0, goal, N, dt, std::make_unique<Unicycle>(dt, "euler"),
+                                    std::make_unique<QuadraticObjective>(Q, R, Qf, goal, std::vector<Eigen::VectorXd>(), dt), o);
+    // inserted in non-alphabetical order on purpose: the std::map orders them Ball < Control like the reference
+    c->addPathConstraint("ControlConstraint", std::make_unique<ControlConstraint>(vec({-1.1, -M_PI}), vec({1.1, M_PI})));
+    c->addPathConstraint("BallConstraint", std::make_unique<BallConstraint>(0.4, vec({1.0, 1.0})));
+    std::vector<Eigen::VectorXd> X((size_t)N + 1, x0), U((size_t)N, vec({0.0, 0.0}));
+    c->setInitialTrajectory(X, U);
+    batch.push_back(c.get());
+    owners.push_back(std::move(c));
+  }
+  CHECK(batch[0]->getTotalDualDim() == 5);
+  CDDPSolution s0 = batch[0]->solve(SolverType::IPDDP);
+  CHECK(s0.solver_name == "IPDDP");
+  CHECK(s0.status_message == "OptimalSolutionFound" || s0.status_message == "AcceptableSolutionFound");
+  CHECK(s0.final_barrier_mu > 0.0 && s0.final_barrier_mu < 1e-3);
+  CHECK(s0.final_primal_infeasibility < 1e-3 && s0.final_complementary_infeasibility < 1e-3);
+  CHECK(s0.history.barrier_mu.size() == s0.history.objective.size() && !s0.history.barrier_mu.empty());
+  CHECK(batch[0]->cost_ == s0.final_objective && batch[0]->inf_pr_ == s0.final_primal_infeasibility);
+  double mind = 1e9;
+  for (int t = 0; t <= N; ++t) mind = std::min(mind, std::hypot(s0.state_trajectory[(size_t)t][0] - 1.0, s0.state_trajectory[(size_t)t][1] - 1.0));
+  CHECK(mind > 0.4 - 1e-3);
+  // fresh problems for the batched call (solve() left instance 0 at its solution)
+  for (int b = 0; b < B; ++b) {
+    std::vector<Eigen::VectorXd> X((size_t)N + 1, batch[(size_t)b]->getInitialState()), U((size_t)N, vec({0.0, 0.0}));
+    batch[(size_t)b]->setInitialTrajectory(X, U);
+  }
+  std::vector<CDDPSolution> sols = b200::solveBatchIPDDP(batch);
+  CHECK(sols[0].iterations_completed == s0.iterations_completed && sols[0].final_objective == s0.final_objective);
+  // oracle parity
+  const double Qa[9] = {0}, Ra[4] = {0.05, 0, 0, 0.05}, Qfa[9] = {100, 0, 0, 0, 100, 0, 0, 0, 50};
+  oracle_problem p{};
+  p.model = ORACLE_UNICYCLE; p.n = 3; p.m = 2; p.horizon = N; p.dt = dt; p.integrator = ORACLE_EULER; p.Q = Qa; p.R = Ra; p.Qf = Qfa;
+  oracle_options oo;
+  oracle_default_options(&oo);
+  oo.max_iterations = 150; oo.tolerance = 1e-4; oo.acceptable_tolerance = 1e-6; oo.reg_initial_value = 1e-6;
+  oracle_ipddp_options oi;
+  oracle_ipddp_default_options(&oi);
+  const double center[2] = {1.0, 1.0}, radius[1] = {0.4}, lb[2] = {-1.1, -M_PI}, ub[2] = {1.1, M_PI};
+  oracle_constraint cs[2] = {{ORACLE_CON_BALL, 2, 1.0, center, radius}, {ORACLE_CON_CONTROL_BOX, 2, 1.0, lb, ub}};
+  double worst = 0.0;
+  int compared = 0;
+  for (int b = 0; b < B; ++b) {
+    std::vector<double> Xo((size_t)(N + 1) * 3), Uo((size_t)N * 2, 0.0), Ko((size_t)N * 6);
+    const double x0a[3] = {0, 0, 0}, xr[3] = {2.0 + 0.03 * b, 2.0 - 0.02 * b, M_PI / 2.0};
+    oracle_ipddp_result res;
+    oracle_ipddp_solve(&p, &oo, &oi, cs, 2, x0a, xr, nullptr, Xo.data(), Uo.data(), Ko.data(), nullptr, nullptr, &res, nullptr);
+    if (res.decision_margin < 1e-9) continue;  // roundoff-decided line search (tests/test_gpu_ipddp.py)
+    ++compared;
+    CHECK(res.iterations == sols[(size_t)b].iterations_completed);
+    CHECK(std::string(oracle_status_string(res.status)) == sols[(size_t)b].status_message);
+    worst = std::max(worst, std::fabs(res.final_objective - sols[(size_t)b].final_objective) / std::fabs(res.final_objective));
+    CHECK(std::fabs(res.mu - sols[(size_t)b].final_barrier_mu) <= 1e-9 * res.mu);
+  }
+  CHECK(compared >= B / 2);
+  CHECK(worst < 1e-6);
+  std::printf("  unicycle obstacle IPDDP: %d iterations, %s, J=%.9f, mu=%.3e, min distance %.4f; batch of %d: worst cost rel err vs oracle %.2e\n",
+              s0.iterations_completed, s0.status_message.c_str(), s0.final_objective, s0.final_barrier_mu, mind, B, worst);
+  // setup errors: terminal constraints / unsupported constraint classes are exceptions, never a CPU fallback
+  bool threw = false;
+  batch[0]->addTerminalConstraint("TerminalEqualityConstraint", std::make_unique<TerminalEqualityConstraint>(vec({2.0, 2.0, 0.0})));
+  try {
+    batch[0]->solve("IPDDP");
+  } catch (const std::runtime_error &) {
+    threw = true;
+  }
+  CHECK(threw);
+}
 }  // namespace
 
 int main() {
   b200::registerSolvers();
   RUN(SolvePendulum);
   RUN(SolveQuadrotorBatch);
+  RUN(SolveUnicycleObstacleIPDDP);
   return finish();
 }
