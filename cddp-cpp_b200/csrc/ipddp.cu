@@ -143,6 +143,13 @@ __device__ void ldlt_solve(const double *a, const int *tr, int n, double *b, int
     if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
 }
 
+// asynchronous global -> shared copies (LDGSTS): the next timestep's operands are fetched while the current one is
+// being processed, so that the chain of N dependent timesteps pays HBM/L2 latency once, not N times
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------- filter
 __device__ __forceinline__ bool dominates(double m1, double t1, double m2, double t2) { return m1 <= m2 && t1 <= t2; }
 
@@ -294,8 +301,14 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
 // 1 + n right-hand sides [Q_u | Q_ux] are solved one column per lane.
 constexpr int kBwThreads = 128;
 
+__host__ __device__ inline int ip_stage_doubles(int n, int m, int D, int rs) {
+  const int sweep = rs + n + 3 * D;                          // record | x | y | s | g of one timestep
+  const int roll = rs + 4 * D + 2 * D * n + m * n + m;       // record | k_s k_y S Y | K_s K_y | K | k (linear rollout)
+  const int b = sweep > roll ? sweep : roll;
+  return (b + 1) & ~1;
+}
 __host__ __device__ inline int ip_group_doubles(int n, int m, int D, int rs) {
-  int c = rs + n;                    // record, x
+  int c = 2 * ip_stage_doubles(n, m, D, rs);  // double-buffered staging block
   c += n * n + n;                    // V, vx
   c += n * n + n * m;                // PA, PB
   c += n * n + m * n + 2 * m * m;    // Qxx, Qux, Quu, Qr
@@ -303,30 +316,49 @@ __host__ __device__ inline int ip_group_doubles(int n, int m, int D, int rs) {
   c += m * (n + 1);                  // RHS / kK
   c += m * (n > m ? n : m);          // Q_uu K scratch (also stages the m x m condensed Q_uu)
   c += D * n + D * m;                // Gx, Gu
-  c += 8 * D;                        // y, s, g, ssafe, YS, prim, rhat, Sir
+  c += 5 * D;                        // ssafe, YS, prim, rhat, Sir
   c += 3 * n + 2 * m;                // dx, dxn, scratch
   c += CDDP_B200_MAX_M;              // transpositions (ints, generously)
   return (c + 1) & ~1;
 }
+__host__ __device__ inline int ip_table_doubles(int n, int m, int D) {  // constraint table staged in shared memory
+  return D * n + D * m + 2 * D + D;  // Gx | Gu | off | scale | (row_type, row_bdim) packed as ints in D doubles
+}
 
-template <int G>
+// NS, NC: compile-time state / control dimensions (0 = runtime): with constants the inner products unroll and the
+// index arithmetic (idx / n, idx % n) strength-reduces — about half of the generic kernel's instruction stream.
+template <int G, int NS, int NC>
 __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
                                                                  int mode) {
   extern __shared__ double smem[];
-  const int n = d.n, m = d.m, N = d.N, rs = d.rec_stride, D = ic.d;
+  const int n = NS ? NS : d.n, m = NC ? NC : d.m, N = d.N, rs = d.rec_stride, D = ic.d;
   constexpr int GPC = kBwThreads / G;  // groups per CTA
   double *sQ = smem;
   double *sR = sQ + n * n;
+  double *tGx = sR + m * m + ((n * n + m * m) & 1);  // constraint table (batch-shared)
+  double *tGu = tGx + D * n;
+  double *tOff = tGu + D * m;
+  double *tScale = tOff + D;
+  int *tType = reinterpret_cast<int *>(tScale + D);
+  int *tBdim = tType + D;
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) sQ[i] = c.Qdt2[i];
   for (int i = threadIdx.x; i < m * m; i += blockDim.x) sR[i] = c.Rdt2[i];
+  for (int i = threadIdx.x; i < D * n; i += blockDim.x) tGx[i] = ic.Gx[i];
+  for (int i = threadIdx.x; i < D * m; i += blockDim.x) tGu[i] = ic.Gu[i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    tOff[i] = ic.off[i];
+    tScale[i] = ic.scale[i];
+    tType[i] = ic.row_type[i];
+    tBdim[i] = ic.row_bdim[i];
+  }
   __syncthreads();
   const int grp = threadIdx.x / G, r = threadIdx.x % G;
   const int b = blockIdx.x * GPC + grp;
   const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   const int bb = alive ? b : 0;
-  double *w = sR + m * m + ((n * n + m * m) & 1) + (size_t)grp * ip_group_doubles(n, m, D, rs);
-  double *rec = w;  w += rs;
-  double *xs = w;   w += n;
+  const int blk = ip_stage_doubles(n, m, D, rs);
+  double *w = tGx + ((ip_table_doubles(n, m, D) + 1) & ~1) + (size_t)grp * ip_group_doubles(n, m, D, rs);
+  double *stg = w;  w += 2 * blk;
   double *V = w;    w += n * n;
   double *vx = w;   w += n;
   double *PA = w;   w += n * n;
@@ -341,9 +373,6 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   double *QK = w;   w += m * (n > m ? n : m);
   double *Gx = w;   w += D * n;
   double *Gu = w;   w += D * m;
-  double *ys = w;   w += D;
-  double *ss = w;   w += D;
-  double *gs = w;   w += D;
   double *ssafe = w; w += D;
   double *YS = w;   w += D;
   double *prim = w; w += D;
@@ -361,8 +390,18 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   double *gK = d.K + (size_t)bb * N * m * n, *gk = d.kff + (size_t)bb * N * m;
   double *gky = ip.ky + (size_t)bb * N * D, *gks = ip.ks + (size_t)bb * N * D;
   double *gKy = ip.Ky + (size_t)bb * N * D * n, *gKs = ip.Ks + (size_t)bb * N * D * n;
-  const double *A = rec, *Bm = rec + n * n, *lx = rec + d.offLx, *lu = rec + d.offLu;
   const int nc1 = n + 1;
+  // stage the operands of timestep tt into staging buffer `x`: record | x_t | y_t | s_t | g_t
+  auto issue_sweep = [&](int tt, int x) {
+    double *dst = stg + x * blk;
+    for (int i = r; i < rs; i += G) cp_async8(dst + i, grec + (size_t)tt * rs + i);
+    for (int i = r; i < n; i += G) cp_async8(dst + rs + i, gX + (size_t)tt * n + i);
+    for (int i = r; i < D; i += G) {
+      cp_async8(dst + rs + n + i, gY + (size_t)tt * D + i);
+      cp_async8(dst + rs + n + D + i, gS + (size_t)tt * D + i);
+      cp_async8(dst + rs + n + 2 * D + i, gG + (size_t)tt * D + i);
+    }
+  };
 
   const double mu = alive ? ip.mu[bb] : 1.0;
   double reg = alive ? d.reg[bb] : 0.0;
@@ -382,29 +421,25 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       for (int i = r; i < n; i += G) vx[i] = d.vterm[(size_t)bb * n + i];
     }
     dV0 = dV1 = inf_du = inf_pr = inf_comp = step_norm = 0.0;
+    if (act) issue_sweep(N - 1, 0);
+    cp_async_wait_all();
     __syncwarp();
     for (int t = N - 1; t >= 0; --t) {
-      if (act) {
-        for (int i = r; i < rs; i += G) rec[i] = grec[(size_t)t * rs + i];
-        for (int i = r; i < n; i += G) xs[i] = gX[(size_t)t * n + i];
-        for (int i = r; i < D; i += G) {
-          ys[i] = gY[(size_t)t * D + i];
-          ss[i] = gS[(size_t)t * D + i];
-          gs[i] = gG[(size_t)t * D + i];
-        }
-      }
-      __syncwarp();
+      const int bi = (N - 1 - t) & 1;
+      if (act && t > 0) issue_sweep(t - 1, bi ^ 1);  // consumed one step from now
+      const double *rec = stg + bi * blk, *xs = rec + rs, *ys = xs + n, *ss = ys + D, *gs = ss + D;
+      const double *A = rec, *Bm = rec + n * n, *lx = rec + d.offLx, *lu = rec + d.offLu;
       if (act) {
         // constraint Jacobians of this step (precomputeConstraintGradients :2145-2250) and the barrier terms (:1413-1443)
         for (int i = r; i < D * n; i += G) {
           const int row = i / n, j = i - row * n;
-          const int ty = ic.row_type[row];
+          const int ty = tType[row];
           double v = 0.0;
-          if (ty == IP_ROW_STATE) v = ic.Gx[i];
-          else if (ty == IP_ROW_BALL && j < ic.row_bdim[row]) v = -2.0 * ic.scale[row] * (xs[j] - ic.Gx[i]);
+          if (ty == IP_ROW_STATE) v = tGx[i];
+          else if (ty == IP_ROW_BALL && j < tBdim[row]) v = -2.0 * tScale[row] * (xs[j] - tGx[i]);
           Gx[i] = v;
         }
-        for (int i = r; i < D * m; i += G) Gu[i] = (ic.row_type[i / m] == IP_ROW_CONTROL) ? ic.Gu[i] : 0.0;
+        for (int i = r; i < D * m; i += G) Gu[i] = (tType[i / m] == IP_ROW_CONTROL) ? tGu[i] : 0.0;
         for (int i = r; i < D; i += G) {
           const double sf = fmax(ss[i], fmax(mu * 1e-3, EPS_SLACK));
           ssafe[i] = sf;
@@ -643,6 +678,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         need = false;
         ok = true;
       }
+      cp_async_wait_all();  // the next step's operands have landed
       __syncwarp();
     }
     if (need && alive) {  // this group's sweep failed
@@ -664,27 +700,51 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   const bool roll = ok && D > 0;
   if (__any_sync(0xffffffffu, roll)) {
     const double tau_b = fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);
-    if (roll)
+    // staging block of the rollout: record | k_s | k_y | S | Y | K_s | K_y | K | k of one timestep
+    const int oKs = rs, oKy = oKs + D, oS = oKy + D, oY = oS + D, oKS = oY + D, oKY = oKS + D * n, oK = oKY + D * n, ok_ = oK + m * n;
+    auto issue_roll = [&](int tt, int x) {
+      double *dst = stg + x * blk;
+      for (int i = r; i < rs; i += G) cp_async8(dst + i, grec + (size_t)tt * rs + i);
+      for (int i = r; i < D; i += G) {
+        cp_async8(dst + oKs + i, gks + (size_t)tt * D + i);
+        cp_async8(dst + oKy + i, gky + (size_t)tt * D + i);
+        cp_async8(dst + oS + i, gS + (size_t)tt * D + i);
+        cp_async8(dst + oY + i, gY + (size_t)tt * D + i);
+      }
+      for (int i = r; i < D * n; i += G) {
+        cp_async8(dst + oKS + i, gKs + (size_t)tt * D * n + i);
+        cp_async8(dst + oKY + i, gKy + (size_t)tt * D * n + i);
+      }
+      for (int i = r; i < m * n; i += G) cp_async8(dst + oK + i, gK + (size_t)tt * m * n + i);
+      for (int i = r; i < m; i += G) cp_async8(dst + ok_ + i, gk + (size_t)tt * m + i);
+    };
+    if (roll) {
       for (int i = r; i < n; i += G) dx[i] = 0.0;
+      issue_roll(0, 0);
+    }
+    cp_async_wait_all();
     __syncwarp();
     for (int t = 0; t < N; ++t) {
+      const int bi = t & 1;
+      if (roll && t + 1 < N) issue_roll(t + 1, bi ^ 1);
+      const double *st_ = stg + bi * blk;
+      const double *A = st_, *Bm = st_ + n * n;
       if (roll) {
-        for (int i = r; i < rs; i += G) rec[i] = grec[(size_t)t * rs + i];
         for (int q = r; q < D; q += G) {
           double a1 = 0.0, a2 = 0.0;
           for (int j = 0; j < n; ++j) {
-            a1 += gKs[((size_t)t * D + q) * n + j] * dx[j];
-            a2 += gKy[((size_t)t * D + q) * n + j] * dx[j];
+            a1 += st_[oKS + q * n + j] * dx[j];
+            a2 += st_[oKY + q * n + j] * dx[j];
           }
-          const double ds = __dadd_rn(gks[(size_t)t * D + q], a1);
-          const double dy = clampd(__dadd_rn(gky[(size_t)t * D + q], a2), -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
-          if (ds < 0.0) apm = fmin(apm, __ddiv_rn(__dmul_rn(-tau_b, gS[(size_t)t * D + q]), ds));
-          if (dy < 0.0) adm = fmin(adm, __ddiv_rn(__dmul_rn(-tau_b, gY[(size_t)t * D + q]), dy));
+          const double ds = __dadd_rn(st_[oKs + q], a1);
+          const double dy = clampd(__dadd_rn(st_[oKy + q], a2), -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+          if (ds < 0.0) apm = fmin(apm, __ddiv_rn(__dmul_rn(-tau_b, st_[oS + q]), ds));
+          if (dy < 0.0) adm = fmin(adm, __ddiv_rn(__dmul_rn(-tau_b, st_[oY + q]), dy));
         }
         for (int i = r; i < m; i += G) {
           double acc = 0.0;
-          for (int j = 0; j < n; ++j) acc += gK[((size_t)t * m + i) * n + j] * dx[j];
-          scr[i] = gk[(size_t)t * m + i] + acc;
+          for (int j = 0; j < n; ++j) acc += st_[oK + i * n + j] * dx[j];
+          scr[i] = st_[ok_ + i] + acc;
         }
       }
       __syncwarp();
@@ -698,6 +758,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       __syncwarp();
       if (roll)
         for (int i = r; i < n; i += G) dx[i] = dxn[i];
+      cp_async_wait_all();
       __syncwarp();
     }
 #pragma unroll
@@ -751,13 +812,20 @@ struct TrialStats {
   bool feasible;
 };
 
-// One rollout of IPDDPSolver::forwardPass (:1597-1751) for step sizes (alpha_pr, alpha_du).  WRITE: store the trial
+// One rollout of IPDDPSolver::forwardPass (:1597-1751) for step sizes (alpha_pr, alpha_du), executed by ALL lanes of a
+// 16-lane group in lock-step (one alpha per lane in pass 1, the accepted alpha replicated in pass 2).  The per-timestep
+// operands x_nom | u_nom | k | K | S | Y | k_s | k_y | K_s | K_y are shared by the group's lanes: they are staged through a
+// double-buffered shared-memory block with asynchronous copies one timestep ahead.  WRITE && wr: store the trial
 // trajectory, slacks, duals and constraint values into the candidate buffers.
+__host__ __device__ inline int ip_fw_step_doubles(int n, int m, int D) {
+  return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1;
+}
+
 template <int MODEL, bool WRITE>
 __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
                                            int b, int cur, double alpha_pr, double alpha_du, double tau, double mu,
-                                           TrialStats &st) {
-  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+                                           TrialStats &st, double *stage, int al, bool wr) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC, LG = 16;
   const int N = d.N, D = ic.d;
   const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
   const double *gK = d.K + (size_t)b * N * NC * NS, *gk = d.kff + (size_t)b * N * NC;
@@ -767,6 +835,31 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
   double *Xc = d.X[cur ^ 1] + (size_t)b * (N + 1) * NS, *Uc = d.U[cur ^ 1] + (size_t)b * N * NC;
   double *Sc = ip.S[cur ^ 1] + (size_t)b * N * D, *Yc = ip.Y[cur ^ 1] + (size_t)b * N * D, *Gc = ip.G[cur ^ 1] + (size_t)b * N * D;
   const bool l2 = ic.io.theta_norm_l2 != 0;
+  const int blk = ip_fw_step_doubles(NS, NC, D);
+  const int oU = NS, ok_ = oU + NC, oK = ok_ + NC, oS = oK + NC * NS, oY = oS + D, oks = oY + D, oky = oks + D, oKs = oky + D,
+            oKy = oKs + D * NS;
+  auto issue = [&](int tt, int x) {
+    double *dst = stage + x * blk;
+    for (int i = al; i < NS; i += LG) cp_async8(dst + i, Xn + (size_t)tt * NS + i);
+    for (int i = al; i < NC; i += LG) {
+      cp_async8(dst + oU + i, Un + (size_t)tt * NC + i);
+      cp_async8(dst + ok_ + i, gk + (size_t)tt * NC + i);
+    }
+    for (int i = al; i < NC * NS; i += LG) cp_async8(dst + oK + i, gK + (size_t)tt * NC * NS + i);
+    for (int i = al; i < D; i += LG) {
+      cp_async8(dst + oS + i, S0 + (size_t)tt * D + i);
+      cp_async8(dst + oY + i, Y0 + (size_t)tt * D + i);
+      cp_async8(dst + oks + i, gks + (size_t)tt * D + i);
+      cp_async8(dst + oky + i, gky + (size_t)tt * D + i);
+    }
+    for (int i = al; i < D * NS; i += LG) {
+      cp_async8(dst + oKs + i, gKs + (size_t)tt * D * NS + i);
+      cp_async8(dst + oKy + i, gKy + (size_t)tt * D * NS + i);
+    }
+  };
+  issue(0, 0);
+  cp_async_wait_all();
+  __syncwarp();
   double x[NS], xn[NS], u[NC], dxv[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
@@ -774,14 +867,16 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
   st.feasible = true;
   bool feas = true;
   for (int t = 0; t < N; ++t) {
+    if (t + 1 < N) issue(t + 1, (t + 1) & 1);
+    const double *sg = stage + (t & 1) * blk;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - Xn[(size_t)t * NS + i];
+    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - sg[i];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {  // u' = u + alpha_pr k + K dx (no clamp) (:1650-1651)
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) acc += gK[((size_t)t * NC + i) * NS + j] * dxv[j];
-      u[i] = (Un[(size_t)t * NC + i] + alpha_pr * gk[(size_t)t * NC + i]) + acc;
+      for (int j = 0; j < NS; ++j) acc += sg[oK + i * NS + j] * dxv[j];
+      u[i] = (sg[oU + i] + alpha_pr * sg[ok_ + i]) + acc;
     }
     double acc_t = 0.0, lacc = 0.0;
     for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
@@ -789,15 +884,15 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       double a1 = 0.0, a2 = 0.0;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        a1 += gKs[e * NS + j] * dxv[j];
-        a2 += gKy[e * NS + j] * dxv[j];
+        a1 += sg[oKs + q * NS + j] * dxv[j];
+        a2 += sg[oKy + q * NS + j] * dxv[j];
       }
-      const double s0 = S0[e], y0 = Y0[e];
+      const double s0 = sg[oS + q], y0 = sg[oY + q];
       // No FMA contraction here: with alpha_pr at its fraction-to-boundary cap and dx = 0 (t = 0) the test below compares
       // s + alpha ds against (1 - tau) s, which are EQUAL in exact arithmetic — the reference's decision is then made by
       // the rounding of exactly these two operations (:1623-1630), so they are reproduced operation by operation.
-      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, gks[e])), a1);
-      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, gky[e])), a2);
+      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, sg[oks + q])), a1);
+      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, sg[oky + q])), a2);
       if (sn < __dmul_rn(1.0 - tau, s0) || yn < __dmul_rn(1.0 - tau, y0)) feas = false;
       if (!finite_d(sn) || !finite_d(yn)) feas = false;
       const double g = con_value(ic, q, NS, NC, x, u);  // (:1743-1748)
@@ -807,7 +902,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       lacc += log(fmax(sn, EPS_SLACK));
       st.maxys = fmax(st.maxys, yn * sn);
       st.minys = fmin(st.minys, yn * sn);
-      if (WRITE) {
+      if (WRITE && wr) {
         Sc[e] = sn;
         Yc[e] = yn;
         Gc[e] = g;
@@ -834,7 +929,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       }
       st.cost += sx + su;
     }
-    if (WRITE) {
+    if (WRITE && wr) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) Xc[(size_t)t * NS + i] = x[i];
 #pragma unroll
@@ -849,6 +944,8 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 #pragma unroll
     for (int i = 0; i < NC; ++i)
       if (!finite_d(u[i])) feas = false;
+    cp_async_wait_all();  // the next step's operands have landed; every lane is done with this step's buffer
+    __syncwarp();
   }
   {
     const double *ref = d.xref + (size_t)b * NS;
@@ -862,7 +959,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
     }
     st.cost += sx;
   }
-  if (WRITE) {
+  if (WRITE && wr) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
   }
@@ -878,11 +975,14 @@ template <int MODEL>
 __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
                                                                 int mode) {
   constexpr int LG = 16;
+  constexpr int NS_ = Model<MODEL>::NS, NC_ = Model<MODEL>::NC;
+  extern __shared__ double fw_smem[];
   const int lane = threadIdx.x & 31;
   const int grp = lane / LG, al = lane % LG;
   const int b = ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp;
   const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   if (!__any_sync(0xffffffffu, alive)) return;
+  double *stage = fw_smem + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, ic.d);
   const int bb = alive ? b : 0;
   const int na = c.num_alphas, D = ic.d;
   const int cur = d.cur[bb];
@@ -892,7 +992,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double tau = ic.nc == 0 ? 1.0 : fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);  // (:1585-1588)
   const double alpha_pr = fmin(alpha, ip.apm[bb]), alpha_du = fmin(alpha, ip.adm[bb]);
   TrialStats st;
-  ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st);
+  ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
   const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
   const double phi_new = st.cost - mu * st.logsum;  // computeBarrierMerit (:2850-2880)
   const double theta_new = st.theta;
@@ -936,9 +1036,9 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double th_new = __shfl_sync(0xffffffffu, theta_new, src), ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
   const double maxys = __shfl_sync(0xffffffffu, st.maxys, src), minys = __shfl_sync(0xffffffffu, st.minys, src);
   const double phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
-  if (alive && first >= 0 && al == 0) {  // pass 2: write the accepted trial
+  if (__any_sync(0xffffffffu, alive && first >= 0)) {  // pass 2: replay the accepted trial (lane 0 of the group writes)
     TrialStats s2;
-    ip_rollout<MODEL, true>(c, d, ic, ip, b, cur, a_pr, a_du, tau, mu, s2);
+    ip_rollout<MODEL, true>(c, d, ic, ip, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
   }
   if (!(alive && al == 0)) return;
   d.accepted[b] = first;
@@ -1048,7 +1148,15 @@ template <int MODEL>
 cudaError_t launch_ip_forward_model(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                     cudaStream_t st) {
   const int per_cta = kFwThreads / 16;
-  ip_forward_kernel<MODEL><<<(d.B + per_cta - 1) / per_cta, kFwThreads, 0, st>>>(c, d, ic, ip, mode);
+  const size_t shm = sizeof(double) * (size_t)per_cta * 2 * ip_fw_step_doubles(d.n, d.m, ic.d);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ip_forward_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (shm > 200 * 1024) return cudaErrorInvalidValue;
+  ip_forward_kernel<MODEL><<<(d.B + per_cta - 1) / per_cta, kFwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 
@@ -1059,21 +1167,21 @@ cudaError_t launch_ip_init_model(const Constants &c, const DeviceState &d, const
   return cudaGetLastError();
 }
 
-template <int G>
+template <int G, int NS, int NC>
 cudaError_t launch_ip_backward_g(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                  cudaStream_t st) {
   const int n = d.n, m = d.m;
   const int gpc = kBwThreads / G;
-  const size_t shm = sizeof(double) * ((size_t)n * n + m * m + ((n * n + m * m) & 1) +
+  const size_t shm = sizeof(double) * ((size_t)n * n + m * m + ((n * n + m * m) & 1) + ((ip_table_doubles(n, m, ic.d) + 1) & ~1) +
                                        (size_t)gpc * ip_group_doubles(n, m, ic.d, d.rec_stride));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ip_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ip_backward_kernel<G, NS, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_backward_kernel<G><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_backward_kernel<G, NS, NC><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 
@@ -1093,9 +1201,13 @@ cudaError_t launch_ip_initialize(const Constants &c, const DeviceState &d, const
 cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                cudaStream_t st) {
   // lanes per trajectory: the widest per-step loop has n*(n+m) entries
-  if (d.n * (d.n + d.m) <= 24) return launch_ip_backward_g<8>(c, d, ic, ip, mode, st);
-  if (d.n * (d.n + d.m) <= 64) return launch_ip_backward_g<16>(c, d, ic, ip, mode, st);
-  return launch_ip_backward_g<32>(c, d, ic, ip, mode, st);
+  if (d.n == 2 && d.m == 1) return launch_ip_backward_g<8, 2, 1>(c, d, ic, ip, mode, st);
+  if (d.n == 3 && d.m == 2) return launch_ip_backward_g<8, 3, 2>(c, d, ic, ip, mode, st);
+  if (d.n == 4 && d.m == 1) return launch_ip_backward_g<8, 4, 1>(c, d, ic, ip, mode, st);
+  if (d.n == 13 && d.m == 4) return launch_ip_backward_g<32, 13, 4>(c, d, ic, ip, mode, st);
+  if (d.n * (d.n + d.m) <= 24) return launch_ip_backward_g<8, 0, 0>(c, d, ic, ip, mode, st);
+  if (d.n * (d.n + d.m) <= 64) return launch_ip_backward_g<16, 0, 0>(c, d, ic, ip, mode, st);
+  return launch_ip_backward_g<32, 0, 0>(c, d, ic, ip, mode, st);
 }
 
 cudaError_t launch_ip_forward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,

@@ -22,6 +22,23 @@ def main():
     if "--nobox" in sys.argv:
         spec["lb"] = spec["ub"] = None
     opts = dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=K + 3)
+    if cfg.get("solver") == "ipddp":
+        s = cddp.BatchedIPDDP(spec, cddp.default_options(**opts), cddp.default_ipddp_options(**cfg.get("ipddp_options", {})),
+                              cfg["constraints"], B)
+        s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], cfg["ref_traj"])
+        s.initialize()
+        s.iterate(3)
+        s.enable_timing(True)
+        s.reset_timing()
+        s.iterate(K)
+        t = s.get_timing()
+        sc = s.get_scalars()
+        it = t.linearize_ms / t.linearize_launches + t.backward_ms / t.backward_launches + t.forward_ms / t.forward_launches
+        print(f"{name} IPDDP B={B} d={s.d}: linearize {t.linearize_ms / t.linearize_launches:.3f} ms  backward "
+              f"{t.backward_ms / t.backward_launches:.3f} ms  forward {t.forward_ms / t.forward_launches:.3f} ms  -> "
+              f"{B / it * 1e3:.3e} instance-iterations/s; running {int((sc['status'] == 0).sum())}/{B} mean cost {np.mean(sc['cost']):.4f}")
+        s.close()
+        return
     s = cddp.BatchedCLDDP(spec, cddp.default_options(**opts), B)
     if "--dense" in sys.argv:
         s.set_record_layout("dense")
