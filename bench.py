@@ -162,6 +162,58 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_ipddp(cddp, problems, device, with_cpu):
+    """Secondary workload (not the bench line): BASELINE config #4's path-constraint part — unicycle obstacle avoidance,
+    IPDDP, n=3 m=2 N=200, batch 2048 — device-resident throughput and per-kernel CUDA-event times, with the CPU oracle
+    beside it.  Convergence exits disabled (tolerance 0) for the timed iterations."""
+    import torch
+    B, K, W = 2048, 20, 3
+    cfg = problems.make_config("unicycle_obstacle", batch=B)
+    opts = cddp.default_options(**dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
+    s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(), cfg["constraints"], B, device=device)
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
+    s.initialize()
+    s.iterate(W)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    e0.record()
+    s.iterate(K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sc = s.get_scalars()
+    running = int((sc["status"] == 0).sum())
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
+    s.initialize()
+    s.iterate(W)
+    s.enable_timing(True)
+    s.reset_timing()
+    s.iterate(K)
+    t = s.get_timing()
+    out = {"workload": cfg["notes"], "solver": "IPDDP", "batch": B, "horizon": cfg["spec"]["horizon"], "dual_dim": s.d,
+           "value": running * K / (ms * 1e-3) if running == B else B * K / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / K,
+           "instances_running_all_iterations": running,
+           "kernel_ms_per_iteration": {"linearize": t.linearize_ms / max(t.linearize_launches, 1),
+                                       "backward": t.backward_ms / max(t.backward_launches, 1),
+                                       "forward": t.forward_ms / max(t.forward_launches, 1)}}
+    s.close()
+    if with_cpu:
+        import oracle_binding as ob
+        threads = ob.hardware_threads()
+        sample = 256
+        ccfg = problems.make_config("unicycle_obstacle", batch=sample)
+        P = ob.OracleProblem(ccfg["spec"])
+        oo = ob.make_options(**dict(ccfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
+        t0 = time.perf_counter()
+        r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(), ob.ConstraintSet(ccfg["constraints"]), ccfg["x0"], ccfg["xref"],
+                                 ccfg["U0"], None, nthreads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{sample} instances x {W + K} IPDDP iterations, {dt:.2f}s wall"}
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -378,6 +430,13 @@ def main():
                "sample": f"{sample} instances x {it_cpu} DDP iterations of the same workload, {dt:.1f}s wall, std::thread static partition",
                "note": "CPU restatement of the reference algorithm (Eigen/autodiff unavailable, reference not buildable here)"}
 
+    other = None
+    if rank == 0 and world == 1 and args.config == "quadrotor" and not args.no_cpu_baseline:
+        try:
+            other = {"ipddp_unicycle_obstacle": measure_ipddp(cddp, problems, local_rank, True)}
+        except Exception as e:  # secondary measurement: never take the bench line down with it
+            other = {"ipddp_unicycle_obstacle": {"error": repr(e)}}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -393,7 +452,7 @@ def main():
                        "line_search_alphas": solver.num_alphas},
             "batched_iterations_per_s": K / (ms * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": clocks, "all_costs_finite": finite,
+            "clocks": clocks, "all_costs_finite": finite, "other_workloads": other,
         }
         print(json.dumps(line), flush=True)
     solver.close()

@@ -24,7 +24,8 @@ LIB_PATH = os.path.join(_HERE, "libcddp_b200.so")
 MAX_N, MAX_M, MAX_ALPHAS = 16, 8, 32
 
 MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_UNICYCLE, MODEL_QUADROTOR, MODEL_LTI = range(5)
-MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4}
+MODEL_USER = 5
+MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4, "user": 5}
 EULER, HEUN, RK3, RK4 = range(4)
 INTEGRATORS = {"euler": 0, "heun": 1, "rk3": 2, "rk4": 3}
 
@@ -135,7 +136,8 @@ ABI_SYMBOLS = [
     "cddp_b200_mpc_advance", "cddp_b200_get_first_controls_async",
     "cddp_b200_ipddp_default_options", "cddp_b200_ipddp_create", "cddp_b200_ipddp_dual_dim",
     "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
-    "cddp_b200_ipddp_get_history",
+    "cddp_b200_ipddp_get_history", "cddp_b200_create_ex", "cddp_b200_ipddp_create_ex", "cddp_b200_compile_user_model",
+    "cddp_b200_last_compile_log",
 ]
 
 
@@ -205,6 +207,11 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_ipddp_default_options.argtypes = [C.POINTER(IpddpOptions)]
     lib.cddp_b200_ipddp_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(IpddpOptions), vp, C.c_int,
                                            C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cddp_b200_create_ex.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cddp_b200_ipddp_create_ex.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(IpddpOptions), vp, C.c_int,
+                                              C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cddp_b200_compile_user_model.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    lib.cddp_b200_last_compile_log.restype = C.c_char_p
     lib.cddp_b200_ipddp_dual_dim.argtypes = [vp, ip]
     lib.cddp_b200_ipddp_get_solution.argtypes = [vp, vp, vp, vp, vp]
     lib.cddp_b200_ipddp_get_gains.argtypes = [vp, vp, vp, vp, vp]
@@ -213,7 +220,7 @@ def load_library() -> C.CDLL:
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("cddp_b200_error_string", "cddp_b200_last_cuda_error", "cddp_b200_status_string",
-                        "cddp_b200_default_options", "cddp_b200_ipddp_default_options"):
+                        "cddp_b200_default_options", "cddp_b200_ipddp_default_options", "cddp_b200_last_compile_log"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -225,6 +232,8 @@ def _check(rc: int) -> None:
         msg = lib.cddp_b200_error_string(rc).decode()
         if rc in (3, 4):
             msg += " — " + lib.cddp_b200_last_cuda_error().decode()
+        if rc == 6:
+            msg += "\n" + lib.cddp_b200_last_compile_log().decode()
         raise CddpB200Error(rc, msg)
 
 
@@ -303,7 +312,9 @@ class BatchedCLDDP:
         self.opts = opts
         self.B, self.n, self.m, self.N = int(batch), self.pspec.n, self.pspec.m, self.pspec.N
         self.handle = C.c_void_p()
-        _check(self.lib.cddp_b200_create(C.byref(self.pspec.struct), C.byref(opts), self.B, device, C.byref(self.handle)))
+        src = spec.get("model_source")  # CUDA source of a user-defined dynamics model (model == "user")
+        _check(self.lib.cddp_b200_create_ex(C.byref(self.pspec.struct), C.byref(opts), src.encode() if src else None, self.B,
+                                            device, C.byref(self.handle)))
         self.num_alphas = len(build_alphas(opts))
         self._keep = []
 
@@ -542,8 +553,10 @@ class BatchedIPDDP(BatchedCLDDP):
         self.cset = constraints if isinstance(constraints, ConstraintSet) else ConstraintSet(constraints)
         self.B, self.n, self.m, self.N = int(batch), self.pspec.n, self.pspec.m, self.pspec.N
         self.handle = C.c_void_p()
-        _check(self.lib.cddp_b200_ipddp_create(C.byref(self.pspec.struct), C.byref(opts), C.byref(ipddp_opts), self.cset.array,
-                                               self.cset.nc, self.B, device, C.byref(self.handle)))
+        src = spec.get("model_source")
+        _check(self.lib.cddp_b200_ipddp_create_ex(C.byref(self.pspec.struct), C.byref(opts), C.byref(ipddp_opts), self.cset.array,
+                                                  self.cset.nc, src.encode() if src else None, self.B, device,
+                                                  C.byref(self.handle)))
         self.num_alphas = len(build_alphas(opts))
         d = C.c_int(0)
         _check(self.lib.cddp_b200_ipddp_dual_dim(self.handle, C.byref(d)))
@@ -578,6 +591,14 @@ class BatchedIPDDP(BatchedCLDDP):
         lens = np.empty(self.B, dtype=np.int32)
         _check(self.lib.cddp_b200_ipddp_get_history(self.handle, _ptr(h), _ptr(lens)))
         return h, lens
+
+
+def compile_user_model(source: str, n: int, m: int) -> int:
+    """cddp_b200_compile_user_model: NVRTC-compiles a user dynamics source for (n, m); needs no GPU.  Returns the cubin
+    size; raises CddpB200Error(code 6) with the compiler log on failure."""
+    sz = C.c_size_t(0)
+    _check(load_library().cddp_b200_compile_user_model(source.encode(), int(n), int(m), C.byref(sz)))
+    return sz.value
 
 
 def solve_host(spec: dict, opts: Options, x0, xref, X0, U0, ref_traj=None, device: int = 0) -> dict:

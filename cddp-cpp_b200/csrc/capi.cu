@@ -12,12 +12,14 @@
 #include <vector>
 
 #include "engine.h"
+#include "user_model_host.h"
 
 using namespace cddp_b200;
 
 namespace {
 
 thread_local std::string g_last_cuda_error;
+thread_local std::string g_last_compile_log;
 
 int cuda_fail(cudaError_t e, const char *what) {
   g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -61,6 +63,7 @@ struct cddp_b200_solver {
   std::vector<void *> allocs;
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
   int *didxA = nullptr, *didxB = nullptr;
+  UserKernels *user_kernels = nullptr;  // CDDP_B200_MODEL_USER: the NVRTC-compiled module
   int kind = 0;      // 0 = CLDDP, 1 = IPDDP
   IpConstants ic{};  // IPDDP: flattened constraint rows + options
   IpDevice ip{};     // IPDDP: duals, slacks, gains, per-instance barrier/filter state
@@ -113,7 +116,7 @@ struct DeviceGuard {
   }
 };
 
-int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch) {
+int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, bool has_user_source = false) {
   if (!p || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (batch < 1 || p->horizon < 1 || !(p->dt > 0.0)) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (p->n < 1 || p->n > CDDP_B200_MAX_N || p->m < 1 || p->m > CDDP_B200_MAX_M) return CDDP_B200_ERR_INVALID_ARGUMENT;
@@ -126,6 +129,7 @@ int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch) 
     case CDDP_B200_MODEL_UNICYCLE: if (p->n != 3 || p->m != 2) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
     case CDDP_B200_MODEL_QUADROTOR: if (p->n != 13 || p->m != 4) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
     case CDDP_B200_MODEL_LTI: if (!p->lti_A || !p->lti_B) return CDDP_B200_ERR_INVALID_ARGUMENT; break;
+    case CDDP_B200_MODEL_USER: if (!has_user_source) return CDDP_B200_ERR_UNSUPPORTED_MODEL; break;  // no source, no device dynamics
     default: return CDDP_B200_ERR_UNSUPPORTED_MODEL;
   }
   if (o->max_iterations < 0 || o->ls_max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
@@ -282,6 +286,7 @@ const char *cddp_b200_error_string(int err) {
     case CDDP_B200_ERR_CUDA: return "CUDA error (see cddp_b200_last_cuda_error)";
     case CDDP_B200_ERR_OUT_OF_MEMORY: return "out of device memory";
     case CDDP_B200_ERR_STATE: return "invalid call order";
+    case CDDP_B200_ERR_USER_MODEL: return "the user-supplied dynamics source did not compile (see cddp_b200_last_compile_log)";
     default: return "unknown error";
   }
 }
@@ -337,12 +342,25 @@ int cddp_b200_build_alphas(const cddp_b200_options *opts, double *alphas, int ca
   return 0;
 }
 
-int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, int device,
-                     cddp_b200_solver **out) {
+const char *cddp_b200_last_compile_log(void) { return g_last_compile_log.c_str(); }
+
+int cddp_b200_compile_user_model(const char *model_source, int n, int m, size_t *cubin_bytes) {
+  if (!model_source || n < 1 || n > CDDP_B200_MAX_N || m < 1 || m > CDDP_B200_MAX_M) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  g_last_compile_log.clear();
+  return user_model_compile_only(model_source, n, m, g_last_compile_log, cubin_bytes);
+}
+
+int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, int device, cddp_b200_solver **out) {
+  return cddp_b200_create_ex(p, o, nullptr, batch, device, out);
+}
+
+int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, const char *model_source, int batch, int device,
+                        cddp_b200_solver **out) {
   if (!out) return CDDP_B200_ERR_INVALID_ARGUMENT;
   *out = nullptr;
-  int r = validate(p, o, batch);
+  int r = validate(p, o, batch, model_source != nullptr);
   if (r) return r;
+  if (model_source && p->model != CDDP_B200_MODEL_USER) return CDDP_B200_ERR_INVALID_ARGUMENT;
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return cuda_fail(cudaErrorInvalidDevice, "device index");
@@ -432,6 +450,17 @@ int cddp_b200_create(const cddp_b200_problem *p, const cddp_b200_options *o, int
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
   if (e != cudaSuccess) { cddp_b200_destroy(s); return cuda_fail(e, "solver setup"); }
+  d.user = nullptr;
+  if (model_source) {  // compile the model-dependent kernels around the user's dynamics and load them on this device
+    g_last_compile_log.clear();
+    r = user_model_build(model_source, n, m, c.cost_diag != 0, &s->user_kernels, g_last_compile_log);
+    if (r) {
+      if (r == CDDP_B200_ERR_CUDA) g_last_cuda_error = g_last_compile_log;
+      cddp_b200_destroy(s);
+      return r;
+    }
+    d.user = s->user_kernels;
+  }
   *out = s;
   return 0;
 }
@@ -441,6 +470,7 @@ int cddp_b200_destroy(cddp_b200_solver *s) {
   DeviceGuard g(s->device);
   cudaDeviceSynchronize();
   for (void *p : s->allocs) cudaFree(p);
+  if (s->user_kernels) user_model_destroy(s->user_kernels);
   if (s->scratch) cudaFree(s->scratch);
   if (s->h_running) cudaFreeHost(s->h_running);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -843,6 +873,12 @@ void cddp_b200_ipddp_default_options(cddp_b200_ipddp_options *io) { /* options.h
 
 int cddp_b200_ipddp_create(const cddp_b200_problem *p, const cddp_b200_options *o, const cddp_b200_ipddp_options *io,
                            const cddp_b200_constraint *cs, int nc, int batch, int device, cddp_b200_solver **out) {
+  return cddp_b200_ipddp_create_ex(p, o, io, cs, nc, nullptr, batch, device, out);
+}
+
+int cddp_b200_ipddp_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, const cddp_b200_ipddp_options *io,
+                              const cddp_b200_constraint *cs, int nc, const char *model_source, int batch, int device,
+                              cddp_b200_solver **out) {
   if (!out) return CDDP_B200_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (!p || !o || !io || nc < 0 || (nc > 0 && !cs)) return CDDP_B200_ERR_INVALID_ARGUMENT;
@@ -873,7 +909,7 @@ int cddp_b200_ipddp_create(const cddp_b200_problem *p, const cddp_b200_options *
   pc.has_control_box = 0;  // IPDDP never clamps (ipddp_solver.cpp:1650-1651); a ControlConstraint is a constraint row pair
   pc.lb = pc.ub = nullptr;
   cddp_b200_solver *s = nullptr;
-  int r = cddp_b200_create(&pc, o, batch, device, &s);
+  int r = cddp_b200_create_ex(&pc, o, model_source, batch, device, &s);
   if (r) return r;
   DeviceGuard g(device);
   s->kind = 1;

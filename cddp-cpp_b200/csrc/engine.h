@@ -1,6 +1,8 @@
 // Internal (non-ABI) definitions shared by the kernels and the C-ABI layer.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 #include "../../include/cddp_b200.h"
 #include "models.cuh"
@@ -58,6 +60,7 @@ struct DeviceState {
   int *history_len;
   int history_cap;
   int *num_running;  // device counter
+  void *user;        // HOST pointer (never dereferenced on the device): NVRTC-compiled kernels of a CDDP_B200_MODEL_USER handle
 };
 
 // batch-shared constants, passed by value to kernels (fits the 4 KB parameter space comfortably)
@@ -112,6 +115,7 @@ struct IpDevice {
 enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };
 enum ForwardMode { FW_EVALUATE = 0 /* do not apply */, FW_ITERATE = 1 };
 
+#ifndef __CUDACC_RTC__
 // kernel launchers (one per translation unit)
 cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st);
 cudaError_t launch_initialize(const Constants &c, const DeviceState &d, cudaStream_t st);
@@ -133,5 +137,7 @@ cudaError_t launch_ip_forward(const Constants &c, const DeviceState &d, const Ip
                               cudaStream_t st);
 cudaError_t launch_gather_current(const Constants &c, const DeviceState &d, double *X, double *U, int which,
                                   cudaStream_t st);
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace cddp_b200

@@ -1,0 +1,537 @@
+// Model-dependent IPDDP kernels (cold-start initialisation, forward rollout / filter line search / bookkeeping) and the
+// device helpers they share with the model-independent backward sweep (ipddp.cu, which holds the reference citations).
+// Header-only so that the SAME kernels are compiled ahead of time for the built-in models (ipddp.cu) and at run time by
+// NVRTC for a user-supplied model (user_model_host.cu).
+#pragma once
+#include "kernel_common.cuh"
+
+namespace cddp_b200 {
+namespace kern {
+
+constexpr double kSlackInteriorOffset = 1e-4;  // ipddp_solver.cpp:35-38
+constexpr double EPS_SLACK = 1e-10;
+constexpr double MAX_BARRIER_RATIO = 1e6;
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ double clip_pos(double num, double den) { return clampd(num / den, 0.0, MAX_BARRIER_RATIO); }
+__device__ __forceinline__ double clip_signed(double num, double den) {
+  return clampd(num / den, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+}
+__device__ __forceinline__ bool finite_d(double v) { return fabs(v) < pos_inf(); }
+
+// g_r(x,u) = constraint.evaluate(x,u) - getUpperBound() for row r of the stacked set (ipddp_solver.cpp:2273-2278)
+__device__ __forceinline__ double con_value(const IpConstants &ic, int r, int n, int m, const double *x, const double *u) {
+  const int ty = ic.row_type[r];
+  if (ty == IP_ROW_BALL) {  // constraint.hpp:326-343
+    const int bd = ic.row_bdim[r];
+    const double sc = ic.scale[r], rad = ic.off[r];
+    double sq = 0.0;
+    for (int i = 0; i < bd; ++i) {
+      const double df = x[i] - ic.Gx[r * n + i];
+      sq += df * df;
+    }
+    return -(sc * sq) - (-(rad * rad) * sc);
+  }
+  double s = 0.0;
+  if (ty == IP_ROW_STATE) {
+    for (int j = 0; j < n; ++j) s += ic.Gx[r * n + j] * x[j];
+  } else {
+    for (int j = 0; j < m; ++j) s += ic.Gu[r * m + j] * u[j];
+  }
+  return s - ic.off[r];
+}
+
+// asynchronous global -> shared copies (LDGSTS): the next timestep's operands are fetched while the current one is
+// being processed, so that the chain of N dependent timesteps pays HBM/L2 latency once, not N times
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------- filter
+__device__ __forceinline__ bool dominates(double m1, double t1, double m2, double t2) { return m1 <= m2 && t1 <= t2; }
+
+// detail::acceptFilterEntry (interior_point_utils.cpp:81-97); f = [cap][2] (merit, theta)
+__device__ void filter_accept(double *f, int &cnt, double merit, double theta) {
+  for (int i = 0; i < cnt; ++i)
+    if (dominates(f[2 * i], f[2 * i + 1], merit, theta)) return;
+  int w = 0;
+  for (int i = 0; i < cnt; ++i)
+    if (!dominates(merit, theta, f[2 * i], f[2 * i + 1])) {
+      f[2 * w] = f[2 * i];
+      f[2 * w + 1] = f[2 * i + 1];
+      ++w;
+    }
+  cnt = w;
+  if (cnt < IP_FILTER_CAP) {
+    f[2 * cnt] = merit;
+    f[2 * cnt + 1] = theta;
+    ++cnt;
+  }
+}
+// detail::pruneFilterToBestPoints (interior_point_utils.cpp:116-141)
+__device__ void filter_prune(double *f, int &cnt) {
+  if (cnt == 0) return;
+  double bvm = f[0], bvt = f[1], bmm = f[0], bmt = f[1];
+  for (int i = 0; i < cnt; ++i) {
+    if (f[2 * i + 1] < bvt) { bvm = f[2 * i]; bvt = f[2 * i + 1]; }
+    if (f[2 * i] < bmm) { bmm = f[2 * i]; bmt = f[2 * i + 1]; }
+  }
+  f[0] = bvm; f[1] = bvt;
+  cnt = 1;
+  if (fabs(bmt - bvt) > 1e-12 || fabs(bmm - bvm) > 1e-12) { f[2] = bmm; f[3] = bmt; cnt = 2; }
+}
+
+__device__ void ip_record_history(const DeviceState &d, const IpDevice &ip, int b) {
+  // recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp_solver.cpp:2084-2088)
+  if (!d.history) return;
+  const int hl = d.history_len[b];
+  if (hl >= d.history_cap) return;
+  double *h = d.history + ((size_t)b * d.history_cap + hl) * IP_HISTORY_COLS;
+  h[0] = d.cost[b]; h[1] = ip.merit[b]; h[2] = d.alpha[b]; h[3] = ip.alpha_du[b]; h[4] = d.inf_du[b];
+  h[5] = ip.inf_pr[b]; h[6] = ip.inf_comp[b]; h[7] = d.reg[b]; h[8] = ip.mu[b];
+  d.history_len[b] = hl + 1;
+}
+
+// ---------------------------------------------------------------------------------------------- initialize
+// One thread per instance: cold start (ipddp_solver.cpp:818-913).
+template <int MODEL>
+__global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const int N = d.N, D = ic.d;
+  const int cur = d.cur[b];
+  double *X = d.X[cur] + (size_t)b * (N + 1) * NS;
+  const double *U = d.U[cur] + (size_t)b * N * NC;
+  double *G = ip.G[cur] + (size_t)b * N * D, *S = ip.S[cur] + (size_t)b * N * D, *Y = ip.Y[cur] + (size_t)b * N * D;
+  const double mu = ic.nc == 0 ? fmax(c.opt.tolerance / 10.0, ic.io.mu_min_value) : ic.io.mu_initial;  // :884-887
+  double x[NS], xn[NS], u[NC];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+  double J = 0.0, logsum = 0.0, theta = 0.0, maxr = 0.0, maxys = -pos_inf(), minys = pos_inf();
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) X[(size_t)t * NS + i] = x[i];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) u[i] = U[(size_t)t * NC + i];
+    {  // running cost (objective.cpp:80-92)
+      const double *ref = ref_ptr(d, b, t);
+      double sx = 0.0, su = 0.0;
+      for (int j = 0; j < NS; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < NS; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * NS + j]);
+        sx += r * (x[j] - ref[j]);
+      }
+      for (int j = 0; j < NC; ++j) {
+        double r = 0.0;
+        for (int i = 0; i < NC; ++i) r += u[i] * (0.5 * c.Rdt2[i * NC + j]);
+        su += r * u[j];
+      }
+      J += sx + su;
+    }
+    double acc = 0.0, lacc = 0.0;
+    for (int r = 0; r < D; ++r) {  // :2447-2466
+      const double g = con_value(ic, r, NS, NC, x, u);
+      const double s = fmax(ic.io.slack_var_init_scale, -g + kSlackInteriorOffset);
+      const double y = (mu * ic.io.dual_var_init_scale) / fmax(s, EPS_SLACK);
+      G[(size_t)t * D + r] = g;
+      S[(size_t)t * D + r] = s;
+      Y[(size_t)t * D + r] = y;
+      const double res = g + s;
+      acc += ic.io.theta_norm_l2 ? res * res : fabs(res);
+      maxr = fmax(maxr, fabs(res));
+      lacc += log(fmax(s, EPS_SLACK));
+      maxys = fmax(maxys, y * s);
+      minys = fmin(minys, y * s);
+    }
+    theta += acc;
+    logsum += lacc;
+    discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = xn[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i) X[(size_t)N * NS + i] = x[i];
+  {
+    const double *ref = d.xref + (size_t)b * NS;
+    double sx = 0.0;
+    for (int j = 0; j < NS; ++j) {
+      double r = 0.0;
+      for (int i = 0; i < NS; ++i) r += (x[i] - ref[i]) * (0.5 * c.Qf2[i * NS + j]);
+      sx += r * (x[j] - ref[j]);
+    }
+    J += sx;
+  }
+  if (ic.io.theta_norm_l2) theta = sqrt(theta);
+  theta = fmax(theta, maxr);
+  d.cost[b] = J;
+  d.reg[b] = c.opt.reg_initial_value;
+  d.alpha[b] = 1.0;
+  ip.alpha_du[b] = 1.0;
+  ip.mu[b] = mu;
+  ip.step_norm[b] = 0.0;
+  ip.inf_pr[b] = maxr;  // resetBarrierFilter (:2484-2517)
+  ip.inf_comp[b] = D ? fmax(maxys - mu, mu - minys) : 0.0;
+  ip.merit[b] = J - mu * logsum;
+  ip.logsum[b] = logsum;
+  ip.filter_theta[b] = fmax(theta, 1e-8);
+  ip.filter_size[b] = 0;
+  ip.apm[b] = 1.0;
+  ip.adm[b] = 1.0;
+  d.inf_du[b] = 0.0;
+  d.dV[2 * b] = 0.0;
+  d.dV[2 * b + 1] = 0.0;
+  d.status[b] = CDDP_B200_STATUS_RUNNING;
+  d.iter[b] = 0;
+  d.lin_valid[b] = 0;
+  d.bw_ok[b] = 0;
+  d.accepted[b] = -1;
+  if (d.history) {
+    d.history_len[b] = 0;
+    ip_record_history(d, ip, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward pass
+constexpr int kFwThreads = 64;
+
+struct TrialStats {
+  double cost, logsum, theta, inf_pr, maxys, minys;
+  bool feasible;
+};
+
+// One rollout of IPDDPSolver::forwardPass (:1597-1751) for step sizes (alpha_pr, alpha_du), executed by ALL lanes of a
+// 16-lane group in lock-step (one alpha per lane in pass 1, the accepted alpha replicated in pass 2).  The per-timestep
+// operands x_nom | u_nom | k | K | S | Y | k_s | k_y | K_s | K_y are shared by the group's lanes: they are staged through a
+// double-buffered shared-memory block with asynchronous copies one timestep ahead.  WRITE && wr: store the trial
+// trajectory, slacks, duals and constraint values into the candidate buffers.
+__host__ __device__ inline int ip_fw_step_doubles(int n, int m, int D) {
+  return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1;
+}
+
+template <int MODEL, bool WRITE>
+__device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
+                                           int b, int cur, double alpha_pr, double alpha_du, double tau, double mu,
+                                           TrialStats &st, double *stage, int al, bool wr) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC, LG = 16;
+  const int N = d.N, D = ic.d;
+  const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
+  const double *gK = d.K + (size_t)b * N * NC * NS, *gk = d.kff + (size_t)b * N * NC;
+  const double *S0 = ip.S[cur] + (size_t)b * N * D, *Y0 = ip.Y[cur] + (size_t)b * N * D;
+  const double *gks = ip.ks + (size_t)b * N * D, *gky = ip.ky + (size_t)b * N * D;
+  const double *gKs = ip.Ks + (size_t)b * N * D * NS, *gKy = ip.Ky + (size_t)b * N * D * NS;
+  double *Xc = d.X[cur ^ 1] + (size_t)b * (N + 1) * NS, *Uc = d.U[cur ^ 1] + (size_t)b * N * NC;
+  double *Sc = ip.S[cur ^ 1] + (size_t)b * N * D, *Yc = ip.Y[cur ^ 1] + (size_t)b * N * D, *Gc = ip.G[cur ^ 1] + (size_t)b * N * D;
+  const bool l2 = ic.io.theta_norm_l2 != 0;
+  const int blk = ip_fw_step_doubles(NS, NC, D);
+  const int oU = NS, ok_ = oU + NC, oK = ok_ + NC, oS = oK + NC * NS, oY = oS + D, oks = oY + D, oky = oks + D, oKs = oky + D,
+            oKy = oKs + D * NS;
+  auto issue = [&](int tt, int x) {
+    double *dst = stage + x * blk;
+    for (int i = al; i < NS; i += LG) cp_async8(dst + i, Xn + (size_t)tt * NS + i);
+    for (int i = al; i < NC; i += LG) {
+      cp_async8(dst + oU + i, Un + (size_t)tt * NC + i);
+      cp_async8(dst + ok_ + i, gk + (size_t)tt * NC + i);
+    }
+    for (int i = al; i < NC * NS; i += LG) cp_async8(dst + oK + i, gK + (size_t)tt * NC * NS + i);
+    for (int i = al; i < D; i += LG) {
+      cp_async8(dst + oS + i, S0 + (size_t)tt * D + i);
+      cp_async8(dst + oY + i, Y0 + (size_t)tt * D + i);
+      cp_async8(dst + oks + i, gks + (size_t)tt * D + i);
+      cp_async8(dst + oky + i, gky + (size_t)tt * D + i);
+    }
+    for (int i = al; i < D * NS; i += LG) {
+      cp_async8(dst + oKs + i, gKs + (size_t)tt * D * NS + i);
+      cp_async8(dst + oKy + i, gKy + (size_t)tt * D * NS + i);
+    }
+  };
+  issue(0, 0);
+  cp_async_wait_all();
+  __syncwarp();
+  double x[NS], xn[NS], u[NC], dxv[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+  st.cost = 0.0; st.logsum = 0.0; st.theta = 0.0; st.inf_pr = 0.0; st.maxys = -pos_inf(); st.minys = pos_inf();
+  st.feasible = true;
+  bool feas = true;
+  for (int t = 0; t < N; ++t) {
+    if (t + 1 < N) issue(t + 1, (t + 1) & 1);
+    const double *sg = stage + (t & 1) * blk;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - sg[i];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {  // u' = u + alpha_pr k + K dx (no clamp) (:1650-1651)
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) acc += sg[oK + i * NS + j] * dxv[j];
+      u[i] = (sg[oU + i] + alpha_pr * sg[ok_ + i]) + acc;
+    }
+    double acc_t = 0.0, lacc = 0.0;
+    for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
+      const size_t e = (size_t)t * D + q;
+      double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        a1 += sg[oKs + q * NS + j] * dxv[j];
+        a2 += sg[oKy + q * NS + j] * dxv[j];
+      }
+      const double s0 = sg[oS + q], y0 = sg[oY + q];
+      // No FMA contraction here: with alpha_pr at its fraction-to-boundary cap and dx = 0 (t = 0) the test below compares
+      // s + alpha ds against (1 - tau) s, which are EQUAL in exact arithmetic — the reference's decision is then made by
+      // the rounding of exactly these two operations (:1623-1630), so they are reproduced operation by operation.
+      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, sg[oks + q])), a1);
+      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, sg[oky + q])), a2);
+      if (sn < __dmul_rn(1.0 - tau, s0) || yn < __dmul_rn(1.0 - tau, y0)) feas = false;
+      if (!finite_d(sn) || !finite_d(yn)) feas = false;
+      const double g = con_value(ic, q, NS, NC, x, u);  // (:1743-1748)
+      const double res = g + sn;
+      acc_t += l2 ? res * res : fabs(res);
+      st.inf_pr = fmax(st.inf_pr, fabs(res));
+      lacc += log(fmax(sn, EPS_SLACK));
+      st.maxys = fmax(st.maxys, yn * sn);
+      st.minys = fmin(st.minys, yn * sn);
+      if (WRITE && wr) {
+        Sc[e] = sn;
+        Yc[e] = yn;
+        Gc[e] = g;
+      }
+    }
+    st.theta += acc_t;
+    st.logsum += lacc;
+    {  // running cost (:1741)
+      const double *ref = ref_ptr(d, b, t);
+      double sx = 0.0, su = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        double rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * NS + j]);
+        sx += rr * (x[j] - ref[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        double rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) rr += u[i] * (0.5 * c.Rdt2[i * NC + j]);
+        su += rr * u[j];
+      }
+      st.cost += sx + su;
+    }
+    if (WRITE && wr) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) Xc[(size_t)t * NS + i] = x[i];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) Uc[(size_t)t * NC + i] = u[i];
+    }
+    discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);  // (:1652-1654)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      x[i] = xn[i];
+      if (!finite_d(xn[i])) feas = false;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (!finite_d(u[i])) feas = false;
+    cp_async_wait_all();  // the next step's operands have landed; every lane is done with this step's buffer
+    __syncwarp();
+  }
+  {
+    const double *ref = d.xref + (size_t)b * NS;
+    double sx = 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double rr = 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qf2[i * NS + j]);
+      sx += rr * (x[j] - ref[j]);
+    }
+    st.cost += sx;
+  }
+  if (WRITE && wr) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
+  }
+  if (l2) st.theta = sqrt(st.theta);
+  st.theta = fmax(st.theta, st.inf_pr);
+  st.feasible = feas;
+}
+
+// One lane per alpha, 16 lanes per trajectory.  pass 1: every lane rolls its alpha out and applies the acceptance test;
+// the first accepted alpha (sequential semantics, cddp_solver_base.cpp:255-263) is replayed once (pass 2, all lanes of
+// the group in lock-step, lane 0 writing the candidate buffers); lane 0 then runs the per-instance bookkeeping.
+template <int MODEL>
+__global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
+                                                                int mode) {
+  constexpr int LG = 16;
+  constexpr int NS_ = Model<MODEL>::NS, NC_ = Model<MODEL>::NC;
+  extern __shared__ double fw_smem[];
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LG, al = lane % LG;
+  const int b = ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp;
+  const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+  if (!__any_sync(0xffffffffu, alive)) return;
+  double *stage = fw_smem + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, ic.d);
+  const int bb = alive ? b : 0;
+  const int na = c.num_alphas, D = ic.d;
+  const int cur = d.cur[bb];
+  const double mu = ip.mu[bb];
+  const bool active = alive && al < na;
+  const double alpha = c.alphas[al < na ? al : na - 1];
+  const double tau = ic.nc == 0 ? 1.0 : fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);  // (:1585-1588)
+  const double alpha_pr = fmin(alpha, ip.apm[bb]), alpha_du = fmin(alpha, ip.adm[bb]);
+  TrialStats st;
+  ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
+  const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
+  const double phi_new = st.cost - mu * st.logsum;  // computeBarrierMerit (:2850-2880)
+  const double theta_new = st.theta;
+  const double inf_comp_new = D ? fmax(st.maxys - mu, mu - st.minys) : 0.0;
+  bool accept = false;
+  if (st.feasible && finite_d(phi_new) && finite_d(theta_new) && finite_d(st.inf_pr) && finite_d(inf_comp_new)) {
+    if (ic.nc == 0) {  // (:1787-1794)
+      const double dJ = cost_old - st.cost;
+      const double expected = -alpha_pr * (d.dV[2 * bb] + 0.5 * alpha_pr * d.dV[2 * bb + 1]);
+      const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
+      accept = ratio > 1e-6;
+    } else {  // filter acceptance (:1796-1839)
+      const double expected_improvement = alpha_pr * d.dV[2 * bb];
+      const int fs = ip.filter_size[bb];
+      const double cv_old = fs ? ip.filter[((size_t)bb * IP_FILTER_CAP + (fs - 1)) * 2 + 1] : 0.0;
+      const double high_ref = fs ? cv_old : ip.filter_theta[bb];
+      if (theta_new > ic.io.max_violation_threshold) {
+        accept = theta_new < (1 - ic.io.violation_acceptance_threshold) * high_ref;
+      } else if (fmax(theta_new, cv_old) < ic.io.min_violation_for_armijo_check && expected_improvement < 0) {
+        accept = phi_new < merit_old + c.opt.armijo_constant * expected_improvement;
+      } else {
+        accept = phi_new < merit_old - ic.io.merit_acceptance_threshold * theta_new ||
+                 theta_new < (1 - ic.io.violation_acceptance_threshold) * cv_old;
+      }
+    }
+  }
+  const bool success = active && accept;
+  unsigned ballot = __ballot_sync(0xffffffffu, success);
+  ballot = (ballot >> (grp * LG)) & 0xffffu;
+  const int first = ballot ? (__ffs(ballot) - 1) : -1;
+  if (alive && al < na) {
+    double *ls = ip.ls_stats + ((size_t)b * CDDP_B200_MAX_ALPHAS + al) * 4;
+    ls[0] = success ? 1.0 : 0.0;
+    ls[1] = st.cost;
+    ls[2] = phi_new;
+    ls[3] = theta_new;
+  }
+  const int src = grp * LG + (first >= 0 ? first : 0);
+  const double a_pr = __shfl_sync(0xffffffffu, alpha_pr, src), a_du = __shfl_sync(0xffffffffu, alpha_du, src);
+  const double cost_new = __shfl_sync(0xffffffffu, st.cost, src), logsum_new = __shfl_sync(0xffffffffu, st.logsum, src);
+  const double th_new = __shfl_sync(0xffffffffu, theta_new, src), ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
+  const double maxys = __shfl_sync(0xffffffffu, st.maxys, src), minys = __shfl_sync(0xffffffffu, st.minys, src);
+  const double phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
+  if (__any_sync(0xffffffffu, alive && first >= 0)) {  // pass 2: replay the accepted trial (lane 0 of the group writes)
+    TrialStats s2;
+    ip_rollout<MODEL, true>(c, d, ic, ip, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
+  }
+  if (!(alive && al == 0)) return;
+  d.accepted[b] = first;
+  if (mode != FW_ITERATE) return;
+  double reg = d.reg[b];
+  int status = CDDP_B200_STATUS_RUNNING;
+  const bool no_barrier = ic.nc == 0;
+  const double inf_du = d.inf_du[b];
+  if (first >= 0) {
+    const double dJ = cost_old - cost_new;  // cddp_solver_base.cpp:130
+    // applyForwardPassResult (:1878-1951)
+    d.cost[b] = cost_new;
+    d.alpha[b] = a_pr;
+    ip.alpha_du[b] = a_du;
+    d.cur[b] = cur ^ 1;
+    d.lin_valid[b] = 0;
+    double inf_pr = ipr_new;
+    double inf_comp = D ? fmax(maxys - mu, mu - minys) : 0.0;
+    const double phi = phi_acc;
+    // updateBarrierParameters(context, true) (:2548-2660)
+    double mu_new = mu;
+    if (!no_barrier) {
+      if (ic.io.barrier_strategy == CDDP_B200_BARRIER_ADAPTIVE) {
+        const double kkt = fmax(fmax(inf_pr, inf_du), inf_comp);
+        const double threshold = fmax(ic.io.mu_update_factor * mu, 2.0 * mu);
+        if (kkt <= threshold) {
+          double factor = ic.io.mu_update_factor;
+          if (mu > 1e-20) {
+            const double ratio = kkt / fmax(mu, 1e-20);
+            if (ratio < 0.01) factor = 0.1 * ic.io.mu_update_factor;
+            else if (ratio < 0.1) factor = 0.3 * ic.io.mu_update_factor;
+            else if (ratio < 0.5) factor = 0.6 * ic.io.mu_update_factor;
+          }
+          const double linear = factor * mu;
+          const double superlinear = pow(mu, ic.io.mu_update_power);
+          mu_new = fmax(fmin(linear, superlinear), fmax(ic.io.mu_min_value, c.opt.tolerance / 100.0));
+        }
+      } else {
+        const double kkt = fmax(fmax(inf_pr, inf_du * ic.io.barrier_update_dual_weight), inf_comp);
+        if (kkt <= ic.io.mu_kappa_epsilon * mu) {
+          const double linear = ic.io.mu_update_factor * mu;
+          const double superlinear = pow(mu, ic.io.mu_update_power);
+          mu_new = fmax(ic.io.mu_min_value, fmin(linear, superlinear));
+        }
+      }
+    }
+    const double filter_theta = fmax(th_new, 1e-8);
+    double *f = ip.filter + (size_t)b * IP_FILTER_CAP * 2;
+    int fs = ip.filter_size[b];
+    if ((mu_new < mu) && (mu_new > 0.0)) {
+      fs = 0;
+    } else {
+      filter_accept(f, fs, phi, filter_theta);
+      if (fs > ic.io.max_filter_size) filter_prune(f, fs);
+    }
+    ip.filter_size[b] = fs;
+    inf_comp = D ? fmax(maxys - mu_new, mu_new - minys) : 0.0;
+    ip.mu[b] = mu_new;
+    ip.inf_pr[b] = inf_pr;
+    ip.inf_comp[b] = inf_comp;
+    ip.merit[b] = cost_new - mu_new * logsum_new;
+    ip.logsum[b] = logsum_new;
+    ip.filter_theta[b] = filter_theta;
+    ip_record_history(d, ip, b);                                     // cddp_solver_base.cpp:133-135
+    reg = fmax(reg / c.opt.reg_update_factor, c.opt.reg_min_value);  // decreaseRegularization
+    const int iter = d.iter[b];
+    const double step_norm = ip.step_norm[b];
+    // checkConvergence (:1953-2025)
+    if (no_barrier) {
+      if (inf_pr < c.opt.tolerance && inf_du < c.opt.tolerance) {
+        status = CDDP_B200_STATUS_OPTIMAL;
+      } else if (c.opt.acceptable_tolerance > 0.0) {
+        const double sq = sqrt(c.opt.acceptable_tolerance);
+        bool acc = inf_pr < sq && inf_du < sq && iter > 50;
+        if (dJ > 0.0) acc = acc || (dJ < c.opt.acceptable_tolerance && iter > 50 && inf_pr < sq && inf_du < sq);
+        if (acc) status = CDDP_B200_STATUS_ACCEPTABLE;
+      }
+    } else {
+      const double tol = fmax(c.opt.tolerance, ic.io.barrier_tol_mult * mu_new);
+      if (inf_pr < tol && inf_du < tol && inf_comp < tol && step_norm < c.opt.tolerance * 10.0) {
+        status = CDDP_B200_STATUS_OPTIMAL;
+      } else if (c.opt.acceptable_tolerance > 0.0) {
+        const double at = sqrt(c.opt.acceptable_tolerance);
+        const double bat = fmax(ic.io.mu_min_value * 100.0, c.opt.tolerance / 10.0);
+        const bool kkt = inf_pr < at && inf_du < at && inf_comp < at;
+        const bool done = mu_new <= bat;
+        bool acc = kkt && done && iter > 10 && fabs(dJ) < c.opt.acceptable_tolerance;
+        acc = acc || (kkt && done && iter >= 1 && step_norm < c.opt.tolerance * 10.0 && inf_pr < 1e-4);
+        if (acc) status = CDDP_B200_STATUS_ACCEPTABLE;
+      }
+    }
+  } else {  // handleForwardPassFailure (:2037-2082)
+    reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+    if (reg >= c.opt.reg_max_value) {
+      const double base = sqrt(fmax(c.opt.acceptable_tolerance, c.opt.tolerance));
+      const double at = no_barrier ? base : fmax(base, ic.io.barrier_tol_mult * mu);
+      const bool acc = c.opt.acceptable_tolerance > 0.0 && ip.inf_pr[b] < at && inf_du < at &&
+                       (no_barrier || ip.inf_comp[b] < at);
+      status = acc ? CDDP_B200_STATUS_ACCEPTABLE : CDDP_B200_STATUS_REG_LIMIT;
+    }
+  }
+  d.reg[b] = reg;
+  if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+}
+
+}  // namespace kern
+}  // namespace cddp_b200

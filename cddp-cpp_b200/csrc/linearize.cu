@@ -6,115 +6,16 @@
 //              and the terminal gradient V_x(N) = 2 Qf (x_N - ref) (objective.cpp:122-126).
 //  initialize: initializeProblemIfNecessary + CLDDPSolver::initialize cold start
 //              (cddp_core.cpp:272-306, clddp_solver.cpp:68-74, cddp_solver_base.cpp:416-424).
-#include <type_traits>
-
 #include "engine.h"
+#include "kernels_linearize.cuh"
+#include "user_model_host.h"
 
 namespace cddp_b200 {
 
 namespace {
 
-__device__ __forceinline__ const double *ref_ptr(const DeviceState &d, int b, int t) {
-  // objective.cpp:84-88: per-index reference if a reference trajectory was given
-  return d.ref_traj ? d.ref_traj + ((size_t)b * (d.N + 1) + t) * d.n : d.xref + (size_t)b * d.n;
-}
-
-template <int B_, int E_, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-  if constexpr (B_ < E_) {
-    f(std::integral_constant<int, B_>{});
-    static_for<B_ + 1, E_>(f);
-  }
-}
-
-// One lane per (instance, t); one warp per chunk of 32 consecutive timesteps of ONE instance.  PAT = DensePattern
-// (RECORDS_DENSE) or ModelPattern<MODEL> (RECORDS_STRUCTURED): only entries inside the pattern are stored; the
-// analytic Jacobians are identically zero outside it.  The 32 records of a chunk are contiguous in HBM, so each
-// lane builds its record in a (bank-conflict-free, odd-stride) shared-memory row and the warp then streams the
-// whole chunk out with fully coalesced stores.  v1 had every thread write its own 832..1936-byte record directly
-// (32 scattered 8-byte stores per instruction): 0.34 ms for 341 MB = 1 TB/s.
-template <int MODEL, class PAT>
-__global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState d, int force, int warps_per_cta) {
-  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
-  using L = RecordLayout<NS, NC, PAT>;
-  constexpr int RS = L::stride, PS = RS | 1;  // padded row stride (odd => conflict-free per-lane rows)
-  extern __shared__ double lin_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= warps_per_cta) return;
-  const int N = d.N;
-  const int chunks = (N + 1 + 31) / 32;
-  const long long wid = (long long)blockIdx.x * warps_per_cta + warp;
-  if (wid >= (long long)d.B * chunks) return;
-  const int b = (int)(wid / chunks), t0 = (int)(wid % chunks) * 32, t = t0 + lane;
-  if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;  // warp-uniform
-  double *row = lin_smem + ((size_t)warp * 32 + lane) * PS;
-  const int cur = d.cur[b];
-  if (t <= N) {
-    const double *xp = d.X[cur] + ((size_t)b * (N + 1) + t) * NS;
-    double x[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) x[i] = xp[i];
-    if (t == N) {
-      const double *ref = d.xref + (size_t)b * NS;  // terminal cost always uses reference_state_ (objective.cpp:96)
-      double e[NS];
-#pragma unroll
-      for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
-      for (int i = 0; i < NS; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS; ++j) s += c.Qf2[i * NS + j] * e[j];
-        d.vterm[(size_t)b * NS + i] = s;
-      }
-    } else {
-      const double *up = d.U[cur] + ((size_t)b * N + t) * NC;
-      double u[NC];
-#pragma unroll
-      for (int i = 0; i < NC; ++i) u[i] = up[i];
-      double Fx[NS * NS], Fu[NS * NC];
-      Model<MODEL>::jac(c.mp, x, u, Fx, Fu);
-      static_for<0, NS>([&](auto lc) {
-        constexpr int l = decltype(lc)::value;
-        static_for<0, NS>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          if constexpr (PAT::a(l, j)) row[L::idxA(l, j)] = c.dt * Fx[l * NS + j] + (l == j ? 1.0 : 0.0);
-        });
-        if constexpr (PAT::brow(l)) {
-          static_for<0, NC>([&](auto ac) {
-            constexpr int a = decltype(ac)::value;
-            row[L::idxB(l, a)] = c.dt * Fu[l * NC + a];
-          });
-        }
-      });
-      const double *ref = ref_ptr(d, b, t);
-      double e[NS];
-#pragma unroll
-      for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
-      for (int i = 0; i < NS; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
-        row[L::offLx + i] = s;
-      }
-      for (int i = 0; i < NC; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
-        row[L::offLu + i] = s;
-      }
-#pragma unroll
-      for (int i = 0; i < NC; ++i) row[L::offU + i] = u[i];
-      if (L::count < RS) row[L::count] = 0.0;  // pad
-    }
-  }
-  __syncwarp();
-  const int nrec = min(32, N - t0);  // records in this chunk (t < N)
-  if (nrec > 0) {
-    double *dst = d.rec + ((size_t)b * N + t0) * RS;
-    const double *src = lin_smem + (size_t)warp * 32 * PS;
-    const int total = nrec * RS;
-    for (int e = lane; e < total; e += 32) dst[e] = src[(e / RS) * PS + (e % RS)];
-  }
-}
+using kern::linearize_kernel;
+using kern::ref_ptr;
 
 // LTI: runtime dimensions; Fx = (A_d - I)/dt, Fu = B_d/dt (lti_system.cpp:78-92) then the solver's
 // A = I + dt*Fx, B = dt*Fu — reproduced literally so that roundoff matches the reference's path.
@@ -355,6 +256,7 @@ cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool forc
       linearize_lti_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(c, d, force);
       return cudaGetLastError();
     }
+    case CDDP_B200_MODEL_USER: return launch_user_linearize(c, d, force, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -13,7 +13,9 @@
 // The reference obtains cartpole/quadrotor Jacobians by forward-mode AD; here they are derived by
 // hand (no AD on the device) and parity-checked against the oracle's dual-number Jacobians.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 #include "../../include/cddp_b200.h"
 
@@ -142,6 +144,7 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
       J.Iinv[i] = P.p[16 + i];
     }
   }
+#ifndef __CUDACC_RTC__
   // host-side: 3x3 inverse by cofactors, stored in p[16..24]; p[25] = 1/mass
   __host__ static void prepare(ModelParams &P) {
     const double *I = P.p + 1;
@@ -155,6 +158,7 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
     o[6] = c20 * id; o[7] = c21 * id; o[8] = c22 * id;
     P.p[25] = 1.0 / P.p[0];
   }
+#endif
 
   __device__ __forceinline__ static void f(const ModelParams &P, const double *x, const double *u, double *xd) {
     const double L = P.p[10], gravity = 9.81;

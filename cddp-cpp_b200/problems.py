@@ -70,7 +70,8 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
         "unicycle": _cfg_unicycle, "lti": _cfg_lti, "quadrotor_fig8": _cfg_quadrotor_fig8,
         "unicycle_obstacle": _cfg_unicycle_obstacle, "cartpole_ipddp": _cfg_cartpole_ipddp,
         "pendulum_ipddp": _cfg_pendulum_ipddp, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
-        "quadrotor_ipddp": _cfg_quadrotor_ipddp,
+        "quadrotor_ipddp": _cfg_quadrotor_ipddp, "bicycle_user": _cfg_bicycle_user, "bicycle_user_ipddp": _cfg_bicycle_user_ipddp,
+        "chain7_user": _cfg_chain7_user,
     }
     if name not in builders:
         raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
@@ -333,6 +334,96 @@ def _cfg_quadrotor_ipddp(batch, horizon, seed_offset):
                constraints=[dict(type="control_box", lb=[0.0] * 4, ub=[5.0] * 4)],
                notes="quadrotor point-to-point, IPDDP + control box 0..5 (examples/cddp_quadrotor_point.cpp:23-98)")
     return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# User-model plugin workloads: spec["model"] = "user" with spec["model_source"] = CUDA source of the dynamics
+# (include/cddp_b200.h, cddp_b200_create_ex); spec["oracle_model"] names the oracle's native twin of the same model.
+# ---------------------------------------------------------------------------------------------
+BICYCLE_SOURCE = """
+// Bicycle (src/dynamics_model/bicycle.cpp:29-47): state (x, y, theta, v), control (a, delta); p[0] = wheelbase
+template <class T>
+__device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot) {
+  xdot[0] = x[3] * cos(x[2]);
+  xdot[1] = x[3] * sin(x[2]);
+  xdot[2] = (x[3] / p[0]) * tan(u[1]);
+  xdot[3] = u[0];
+}
+"""
+
+CHAIN7_SOURCE = """
+// 7-joint chain (NOT a reference model; stands in for BASELINE config #5's 7-DOF manipulator): gravity, viscous friction,
+// nearest-neighbour elastic coupling.  state (q[7], qdot[7]), control tau[7]; p = g, c, k, I_1..I_7
+template <class T>
+__device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot) {
+  const double g = p[0], c = p[1], k = p[2];
+  for (int i = 0; i < 7; ++i) {
+    xdot[i] = x[7 + i];
+    T acc = u[i] - g * sin(x[i]) - c * x[7 + i];
+    if (i > 0) acc = acc - k * sin(x[i] - x[i - 1]);
+    if (i < 6) acc = acc - k * sin(x[i] - x[i + 1]);
+    xdot[7 + i] = acc / p[3 + i];
+  }
+}
+"""
+
+
+def _cfg_bicycle_user(batch, horizon, seed_offset):
+    """The reference's Bicycle model (src/dynamics_model/bicycle.cpp) supplied through the user-model plugin; CLDDP with a
+    control box (acceleration, steering), parking-style point-to-point problem."""
+    B = batch or 4
+    N = horizon or 100
+    dt = 0.05
+    rng = np.random.default_rng(SEED_BASE + 21 + seed_offset)
+    spec = dict(model="user", oracle_model="bicycle", model_source=BICYCLE_SOURCE, n=4, m=2, horizon=N, dt=dt, integrator="rk4",
+                params=[2.0], Q=_diag([0.0, 0.0, 0.0, 0.01]), R=_diag([0.1, 0.5]), Qf=_diag([100.0, 100.0, 50.0, 10.0]),
+                lb=[-2.0, -0.6], ub=[2.0, 0.6])
+    options = dict(max_iterations=60, tolerance=1e-5, acceptable_tolerance=1e-7, reg_initial_value=1e-5)
+    x0 = np.zeros((B, 4))
+    xref = np.tile(np.array([4.0, 3.0, math.pi / 2.0, 0.0]), (B, 1))
+    if B > 1:
+        xref[1:, 0:2] += 0.3 * rng.standard_normal((B - 1, 2))
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    U0 = np.zeros((B, N, 2))
+    U0[:, :, 0] = 0.2
+    return dict(name="bicycle_user", config_id=21, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="bicycle (reference model bicycle.cpp) through the user-model plugin, n=4 m=2 N=100, CLDDP + control box")
+
+
+def _cfg_bicycle_user_ipddp(batch, horizon, seed_offset):
+    """Same plugin model under IPDDP with a control box and a circular obstacle on the path."""
+    cfg = _cfg_bicycle_user(batch, horizon, seed_offset)
+    spec = dict(cfg["spec"], lb=None, ub=None)
+    cfg.update(name="bicycle_user_ipddp", config_id=22, solver="ipddp", spec=spec, X0=None, ipddp_options={},
+               options=dict(max_iterations=60, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-4),
+               constraints=[dict(type="control_box", lb=[-2.0, -0.6], ub=[2.0, 0.6]), dict(type="ball", center=[3.0, 1.2], radius=0.5)],
+               notes="bicycle through the user-model plugin, IPDDP, control box + ball obstacle")
+    return cfg
+
+
+def _cfg_chain7_user(batch, horizon, seed_offset):
+    """BASELINE config #5 stand-in: n=14, m=7, N=150, control box, CLDDP (the reference's manipulator example is CLDDP +
+    box, examples/cddp_manipulator.cpp:23-70; cost pattern Q = diag(1 x7, 0.1 x7), R = 0.1 I, Qf = 100 Q from the same
+    file).  The 7-DOF model itself does not exist in the reference: it is a plugin model of this build."""
+    B = batch or 4
+    N = horizon or 150
+    dt = 0.01
+    rng = np.random.default_rng(SEED_BASE + 5 + seed_offset)
+    inertia = [1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4]
+    qw = [1.0] * 7 + [0.1] * 7
+    spec = dict(model="user", oracle_model="chain7", model_source=CHAIN7_SOURCE, n=14, m=7, horizon=N, dt=dt, integrator="rk4",
+                params=[9.81, 0.5, 4.0] + inertia, Q=_diag(qw), R=0.1 * np.eye(7), Qf=100.0 * _diag(qw),
+                lb=[-50.0] * 7, ub=[50.0] * 7)
+    options = dict(max_iterations=60, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-5)
+    x0 = np.zeros((B, 14))
+    xref = np.zeros((B, 14))
+    xref[:, :7] = np.array([0.8, -0.6, 0.5, -0.4, 0.3, -0.2, 0.1])
+    if B > 1:
+        xref[1:, :7] += 0.1 * rng.standard_normal((B - 1, 7))
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=1)
+    U0 = np.zeros((B, N, 7))
+    return dict(name="chain7_user", config_id=5, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="7-joint chain (plugin model; stands in for BASELINE config #5) n=14 m=7 N=150, CLDDP + control box +-50")
 
 
 def shard(cfg: dict, rank: int, world: int) -> dict:

@@ -23,6 +23,10 @@
 #ifndef CDDP_B200_H
 #define CDDP_B200_H
 
+#ifndef __CUDACC_RTC__
+#include <stddef.h>
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -45,7 +49,8 @@ enum {
   CDDP_B200_ERR_UNSUPPORTED_MODEL = 2, /* host-only DynamicalSystem: no device dynamics (no CPU fallback) */
   CDDP_B200_ERR_CUDA = 3,              /* CUDA runtime error / no device; see cddp_b200_last_cuda_error */
   CDDP_B200_ERR_OUT_OF_MEMORY = 4,
-  CDDP_B200_ERR_STATE = 5              /* call order violated (e.g. backward before linearize) */
+  CDDP_B200_ERR_STATE = 5,             /* call order violated (e.g. backward before linearize) */
+  CDDP_B200_ERR_USER_MODEL = 6         /* the user-supplied dynamics source failed to compile; see cddp_b200_last_compile_log */
 };
 
 /* Device-resident dynamics models (src/dynamics_model/<name>.cpp).  model_params layout:
@@ -54,13 +59,15 @@ enum {
  *   UNICYCLE  : (none)                                                  (unicycle.cpp:24-26)
  *   QUADROTOR : mass, inertia 3x3 row-major (9), arm_length             (quadrotor.cpp:25-31)
  *   LTI       : (none) — discrete A_d, B_d passed in lti_A, lti_B       (lti_system.cpp:71-92)
+ *   USER      : free — passed to the user's device function as `p`      (see cddp_b200_create_ex)
  */
 enum {
   CDDP_B200_MODEL_PENDULUM = 0,
   CDDP_B200_MODEL_CARTPOLE = 1,
   CDDP_B200_MODEL_UNICYCLE = 2,
   CDDP_B200_MODEL_QUADROTOR = 3,
-  CDDP_B200_MODEL_LTI = 4
+  CDDP_B200_MODEL_LTI = 4,
+  CDDP_B200_MODEL_USER = 5 /* dynamics supplied as CUDA source, compiled at create time (cddp_b200_create_ex) */
 };
 
 /* DynamicalSystem integration_type (dynamical_system.cpp:67-83) */
@@ -205,6 +212,30 @@ CDDP_B200_API int cddp_b200_build_alphas(const cddp_b200_options *opts, double *
 CDDP_B200_API int cddp_b200_create(const cddp_b200_problem *problem, const cddp_b200_options *opts, int batch, int device,
                      cddp_b200_solver **out);
 CDDP_B200_API int cddp_b200_destroy(cddp_b200_solver *s);
+/* ---- user-defined dynamics: the device counterpart of subclassing cddp::DynamicalSystem
+ * (include/cddp-cpp/cddp_core/dynamical_system.hpp:33-152).  The reference's virtuals (getContinuousDynamics,
+ * getContinuousDynamicsAutodiff, getStateJacobian, ...) are host-only Eigen calls that cannot run inside a kernel, so a
+ * plugin model hands over CUDA C++ source instead: problem->model = CDDP_B200_MODEL_USER, any n <= CDDP_B200_MAX_N,
+ * m <= CDDP_B200_MAX_M, and `model_source` defining at global scope
+ *
+ *     template <class T>
+ *     __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot);   // p = model_params
+ *
+ * — ONE text, instantiated with T = double for the rollouts (getContinuousDynamics) and with a forward-mode dual number
+ * for the Jacobians, which is how the reference itself obtains them (autodiff of getContinuousDynamicsAutodiff,
+ * src/cddp_core/dynamical_system.cpp:102-133).  Optionally `#define CDDP_USER_HAS_JACOBIAN` and
+ *     __device__ void cddp_user_jacobian(const double *x, const double *u, const double *p, double *Fx, double *Fu);
+ * (row-major continuous-time Jacobians [n][n], [n][m]; = overriding getStateJacobian / getControlJacobian).
+ * The source is compiled for sm_100a with NVRTC together with the engine's own rollout / linearisation kernels (the same
+ * kernel text the built-in models use); integrators, costs, line search, constraints are the engine's.  A source that
+ * does not compile is CDDP_B200_ERR_USER_MODEL with the compiler output in cddp_b200_last_compile_log().
+ * model_source == NULL makes both _ex entry points identical to the plain ones. ---- */
+CDDP_B200_API int cddp_b200_create_ex(const cddp_b200_problem *problem, const cddp_b200_options *opts, const char *model_source,
+                                      int batch, int device, cddp_b200_solver **out);
+/* compile only — needs libnvrtc but no GPU/driver: validates a model source for dimensions (n, m) */
+CDDP_B200_API int cddp_b200_compile_user_model(const char *model_source, int n, int m, size_t *cubin_bytes);
+CDDP_B200_API const char *cddp_b200_last_compile_log(void);
+
 /* kernels are launched on this cudaStream_t (default: the legacy default stream) */
 CDDP_B200_API int cddp_b200_set_stream(cddp_b200_solver *s, void *cuda_stream);
 /* CDDP::setOptions (cddp_core.cpp:109-113): rebuilds the alpha schedule */
@@ -308,6 +339,11 @@ CDDP_B200_API void cddp_b200_ipddp_default_options(cddp_b200_ipddp_options *opts
 CDDP_B200_API int cddp_b200_ipddp_create(const cddp_b200_problem *problem, const cddp_b200_options *opts,
                                          const cddp_b200_ipddp_options *ipddp_opts, const cddp_b200_constraint *constraints,
                                          int num_constraints, int batch, int device, cddp_b200_solver **out);
+/* same with a user-defined dynamics model (see cddp_b200_create_ex) */
+CDDP_B200_API int cddp_b200_ipddp_create_ex(const cddp_b200_problem *problem, const cddp_b200_options *opts,
+                                            const cddp_b200_ipddp_options *ipddp_opts, const cddp_b200_constraint *constraints,
+                                            int num_constraints, const char *model_source, int batch, int device,
+                                            cddp_b200_solver **out);
 /* total dual dimension d of the handle's constraint set (getTotalDualDim, ipddp_solver.cpp:2134-2143); 0 for CLDDP handles */
 CDDP_B200_API int cddp_b200_ipddp_dual_dim(cddp_b200_solver *s, int *d);
 /* CDDPSolution interior-point fields (cddp_core.hpp:54-103; populateSolverSpecificSolution, ipddp_solver.cpp:2090-2097) and

@@ -112,11 +112,20 @@ inline Dual cos(const Dual &a) {
   for (int i = 0; i < a.nd; ++i) r.d[i] = s * a.d[i];
   return r;
 }
+inline Dual tan(const Dual &a) {
+  Dual r;
+  r.nd = a.nd;
+  r.v = std::tan(a.v);
+  const double c = 1.0 + r.v * r.v;
+  for (int i = 0; i < a.nd; ++i) r.d[i] = c * a.d[i];
+  return r;
+}
 inline double val(double a) { return a; }
 inline double val(const Dual &a) { return a.v; }
 using std::cos;
 using std::sin;
 using std::sqrt;
+using std::tan;
 
 /* ------------------------------------------------------------------------------------------
  * Model dynamics, templated on the scalar so the same text serves f and its AD Jacobian.
@@ -201,6 +210,31 @@ void cartpole_f(const double *P, const T *x, const T *u, T *xd, bool jac) {
 }
 
 /* pendulum.cpp:29-43.  params: length, mass, damping */
+/* bicycle.cpp:29-47 (double) / :49-64 (dual): state (x, y, theta, v), control (a, delta); params: wheelbase */
+template <typename T>
+void bicycle_f(const double *P, const T *x, const T *u, T *xd) {
+  xd[0] = x[3] * cos(x[2]);
+  xd[1] = x[3] * sin(x[2]);
+  xd[2] = (x[3] / P[0]) * tan(u[1]);
+  xd[3] = u[0];
+}
+
+/* NOT a reference model: a 7-joint chain with gravity, viscous friction and nearest-neighbour elastic coupling,
+ * q_i'' = (tau_i - g_i sin q_i - c q_i' - k (sin(q_i - q_{i-1}) + sin(q_i - q_{i+1}))) / I_i, state (q, q'), n = 14, m = 7.
+ * It stands in for BASELINE config #5's "7-DOF manipulator" (no such model exists in the reference) and
+ * exercises the user-model plugin at n = 14, m = 7.  params: g, c, k, I_1..I_7. */
+template <typename T>
+void chain7_f(const double *P, const T *x, const T *u, T *xd) {
+  const double g = P[0], c = P[1], k = P[2];
+  for (int i = 0; i < 7; ++i) {
+    xd[i] = x[7 + i];
+    T acc = u[i] - g * sin(x[i]) - c * x[7 + i];
+    if (i > 0) acc = acc - k * sin(x[i] - x[i - 1]);
+    if (i < 6) acc = acc - k * sin(x[i] - x[i + 1]);
+    xd[7 + i] = acc / P[3 + i];
+  }
+}
+
 void pendulum_f(const double *P, const double *x, const double *u, double *xd) {
   const double length = P[0], mass = P[1], damping = P[2], gravity = 9.81;
   const double inertia = mass * length * length;
@@ -276,6 +310,8 @@ void continuous_dynamics(const oracle_problem *p, const double *x, const double 
     case ORACLE_CARTPOLE: cartpole_f<double>(p->model_params, x, u, xd, false); break;
     case ORACLE_UNICYCLE: unicycle_f(x, u, xd); break;
     case ORACLE_QUADROTOR: quadrotor_f<double>(p->model_params, x, u, xd); break;
+    case ORACLE_BICYCLE: bicycle_f<double>(p->model_params, x, u, xd); break;
+    case ORACLE_CHAIN7: chain7_f<double>(p->model_params, x, u, xd); break;
     case ORACLE_LTI: {
       /* base-class fallback dynamical_system.cpp:85-98: (x_next - x)/dt */
       double xn[MAXN];
@@ -319,6 +355,8 @@ void jacobians(const oracle_problem *p, const double *x, const double *u, double
       break;
     }
     case ORACLE_CARTPOLE:
+    case ORACLE_BICYCLE: /* analytic in the reference (bicycle.cpp:66-113) = the derivative of the same expressions */
+    case ORACLE_CHAIN7:
     case ORACLE_QUADROTOR: { /* autodiff::jacobian: cartpole.cpp:95-103, quadrotor.cpp:116-140 */
       const int nd = n + m;
       Dual xs[MAXN], us[MAXM], xd[MAXN];
@@ -333,6 +371,10 @@ void jacobians(const oracle_problem *p, const double *x, const double *u, double
       for (int i = 0; i < n; ++i) xd[i] = dconst(0.0, nd);
       if (p->model == ORACLE_CARTPOLE)
         cartpole_f<Dual>(P, xs, us, xd, true);
+      else if (p->model == ORACLE_BICYCLE)
+        bicycle_f<Dual>(P, xs, us, xd);
+      else if (p->model == ORACLE_CHAIN7)
+        chain7_f<Dual>(P, xs, us, xd);
       else
         quadrotor_f<Dual>(P, xs, us, xd);
       for (int i = 0; i < n; ++i) {

@@ -114,13 +114,26 @@ def f_quadrotor(p, x, u, jac=False):  # quadrotor.cpp:33-96
     return out
 
 
-MODELS = {"pendulum": f_pendulum, "cartpole": f_cartpole, "unicycle": f_unicycle, "quadrotor": f_quadrotor}
+def f_bicycle(p, x, u, jac=False):  # bicycle.cpp:29-47; params: wheelbase
+    return np.array([x[3] * np.cos(x[2]), x[3] * np.sin(x[2]), (x[3] / p[0]) * np.tan(u[1]), u[0] + 0 * x[0]])
+
+
+def f_chain7(p, x, u, jac=False):  # test plugin model (not in the reference), see oracle/cddp_oracle.cpp chain7_f
+    g, c, k, inertia = p[0], p[1], p[2], np.asarray(p[3:10])
+    q, qd = x[:7], x[7:]
+    acc = u - g * np.sin(q) - c * qd
+    acc = acc - k * np.concatenate([[0.0], np.sin(q[1:] - q[:-1])]) - k * np.concatenate([np.sin(q[:-1] - q[1:]), [0.0]])
+    return np.concatenate([qd, acc / inertia])
+
+
+MODELS = {"pendulum": f_pendulum, "cartpole": f_cartpole, "unicycle": f_unicycle, "quadrotor": f_quadrotor,
+          "bicycle": f_bicycle, "chain7": f_chain7}
 
 
 class Problem:
     def __init__(self, spec):
         self.spec = spec
-        self.model = spec["model"]
+        self.model = spec.get("oracle_model", spec["model"])
         self.n, self.m, self.N = int(spec["n"]), int(spec["m"]), int(spec["horizon"])
         self.dt = float(spec["dt"])
         self.integrator = spec.get("integrator", "rk4")

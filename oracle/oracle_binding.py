@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4}
+MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4, "bicycle": 5, "chain7": 6}
 INTEGRATORS = {"euler": 0, "heun": 1, "rk3": 2, "rk4": 3}
 STATUS_STRINGS = {0: "Running", 1: "OptimalSolutionFound", 2: "AcceptableSolutionFound", 3: "MaxIterationsReached",
                   4: "RegularizationLimitReached_NotConverged", 5: "MaxCpuTimeReached"}
@@ -121,7 +121,7 @@ class OracleProblem:
         self.n, self.m, self.N = n, m, int(spec["horizon"])
         self._keep = {}
         p = Problem()
-        model = spec["model"]
+        model = spec.get("oracle_model", spec["model"])  # user-plugin workloads name the oracle's native twin of the model
         p.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
         p.n, p.m, p.horizon, p.dt = n, m, self.N, float(spec["dt"])
         integ = spec.get("integrator", "rk4")
