@@ -201,7 +201,7 @@ def measure_ipddp(cddp, problems, device, with_cpu):
     if with_cpu:
         import oracle_binding as ob
         threads = ob.hardware_threads()
-        sample = 256
+        sample = 2048
         ccfg = problems.make_config("unicycle_obstacle", batch=sample)
         P = ob.OracleProblem(ccfg["spec"])
         oo = ob.make_options(**dict(ccfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))

@@ -120,10 +120,14 @@ enum class SolverType { CLDDP, LogDDP, IPDDP, MSIPDDP };  // cddp_core.hpp:43-48
 // [ADDITION to the reference surface] what a DynamicalSystem must provide to run inside the sm_100a kernels.
 // The reference's virtuals are host-only Eigen calls; a model that cannot fill this is rejected by the B200
 // solver with std::runtime_error (no CPU fallback).  model = CDDP_B200_MODEL_* (include/cddp_b200.h).
+// A user-defined DynamicalSystem runs on the device by returning model = CDDP_B200_MODEL_USER and `source` = CUDA C++
+// defining `template <class T> __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot)`
+// (include/cddp_b200.h, cddp_b200_create_ex): the device twin of its getContinuousDynamics / getContinuousDynamicsAutodiff.
 struct DeviceModelDescriptor {
   int model = -1;
   double params[16] = {0};
   std::vector<double> lti_A, lti_B;  // row-major, LTI only
+  std::string source;                // CDDP_B200_MODEL_USER only
 };
 
 class DynamicalSystem {  // dynamical_system.hpp:33-152

@@ -15,6 +15,7 @@ struct Shared {  // the batch-shared part of a problem, in C-ABI form
   cddp_b200_problem p{};
   cddp_b200_options o{};
   std::vector<double> Q, R, Qf, lb, ub, ltiA, ltiB;
+  std::string source;  // user-defined dynamics (CDDP_B200_MODEL_USER)
   bool has_ref_traj = false;
 };
 
@@ -55,6 +56,9 @@ void describe(CDDP &ctx, Shared &s) {
   std::memcpy(s.p.model_params, dm.params, sizeof(dm.params));
   s.ltiA = dm.lti_A;
   s.ltiB = dm.lti_B;
+  s.source = dm.source;
+  if (dm.model == CDDP_B200_MODEL_USER && dm.source.empty())
+    throw std::runtime_error("B200: a CDDP_B200_MODEL_USER DynamicalSystem must return its device source from getDeviceModel()");
   // QuadraticObjective scales by ITS OWN timestep (objective.cpp:38-39); the C ABI scales by the problem timestep
   const double ratio = obj->getTimestep() / ctx.getTimestep();
   flatten(obj->unscaledQ() * ratio, s.Q);
@@ -106,7 +110,7 @@ bool same_shared(const Shared &a, const Shared &b) {
   return a.p.model == b.p.model && a.p.n == b.p.n && a.p.m == b.p.m && a.p.horizon == b.p.horizon && a.p.dt == b.p.dt &&
          a.p.integrator == b.p.integrator && a.p.has_control_box == b.p.has_control_box &&
          std::memcmp(a.p.model_params, b.p.model_params, sizeof(a.p.model_params)) == 0 && a.Q == b.Q && a.R == b.R && a.Qf == b.Qf &&
-         a.lb == b.lb && a.ub == b.ub && a.ltiA == b.ltiA && a.ltiB == b.ltiB && a.has_ref_traj == b.has_ref_traj &&
+         a.lb == b.lb && a.ub == b.ub && a.ltiA == b.ltiA && a.ltiB == b.ltiB && a.source == b.source && a.has_ref_traj == b.has_ref_traj &&
          std::memcmp(&a.o, &b.o, sizeof(a.o)) == 0;
 }
 
@@ -114,6 +118,7 @@ void check(int rc, const char *what) {
   if (rc == CDDP_B200_OK) return;
   std::string msg = std::string("B200 CLDDP: ") + what + ": " + cddp_b200_error_string(rc);
   if (rc == CDDP_B200_ERR_CUDA || rc == CDDP_B200_ERR_OUT_OF_MEMORY) msg += std::string(" — ") + cddp_b200_last_cuda_error();
+  if (rc == CDDP_B200_ERR_USER_MODEL) msg += std::string("\n") + cddp_b200_last_compile_log();
   throw std::runtime_error(msg);
 }
 
@@ -162,7 +167,7 @@ std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, int de
   std::vector<int> hist_len;
 
   cddp_b200_solver *h = nullptr;
-  check(cddp_b200_create(&sh.p, &sh.o, B, device, &h), "create");
+  check(cddp_b200_create_ex(&sh.p, &sh.o, sh.source.empty() ? nullptr : sh.source.c_str(), B, device, &h), "create");
   struct Guard {
     cddp_b200_solver *h;
     ~Guard() { cddp_b200_destroy(h); }
@@ -368,7 +373,8 @@ std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, i
   std::vector<double> hist;
   std::vector<int> hist_len;
   cddp_b200_solver *h = nullptr;
-  check(cddp_b200_ipddp_create(&sh.p, &sh.o, &ish.io, cs.empty() ? nullptr : cs.data(), (int)cs.size(), B, device, &h), "ipddp_create");
+  check(cddp_b200_ipddp_create_ex(&sh.p, &sh.o, &ish.io, cs.empty() ? nullptr : cs.data(), (int)cs.size(),
+                                  sh.source.empty() ? nullptr : sh.source.c_str(), B, device, &h), "ipddp_create");
   struct Guard {
     cddp_b200_solver *h;
     ~Guard() { cddp_b200_destroy(h); }

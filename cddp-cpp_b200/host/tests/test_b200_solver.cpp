@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "cddp_b200/b200_solver.hpp"
+#include "../../../include/cddp_b200.h"  // CDDP_B200_MODEL_USER
 #include "cddp_oracle.h"
 #include "check.hpp"
 
@@ -245,6 +246,86 @@ void SolveUnicycleObstacleIPDDP() {
   }
   CHECK(threw);
 }
+
+// A user-defined DynamicalSystem — the reference's Bicycle (src/dynamics_model/bicycle.cpp:29-47), which is NOT one of the
+// engine's built-in models — plugged in the way a cddp-cpp user would: subclass, host dynamics for the host-side API, plus
+// getDeviceModel() returning the CUDA twin of getContinuousDynamics.  Solved through the registry; oracle parity against
+// the oracle's native Bicycle.
+class UserBicycle : public DynamicalSystem {
+ public:
+  UserBicycle(double dt, double wheelbase, std::string integ) : DynamicalSystem(4, 2, dt, std::move(integ)), wheelbase_(wheelbase) {}
+  Eigen::VectorXd getContinuousDynamics(const Eigen::VectorXd &x, const Eigen::VectorXd &u, double) const override {
+    Eigen::VectorXd xd(4);
+    xd[0] = x[3] * std::cos(x[2]);
+    xd[1] = x[3] * std::sin(x[2]);
+    xd[2] = (x[3] / wheelbase_) * std::tan(u[1]);
+    xd[3] = u[0];
+    return xd;
+  }
+  bool getDeviceModel(DeviceModelDescriptor &d) const override {
+    d.model = CDDP_B200_MODEL_USER;
+    d.params[0] = wheelbase_;
+    d.source =
+        "template <class T> __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xd) {\n"
+        "  xd[0] = x[3] * cos(x[2]); xd[1] = x[3] * sin(x[2]); xd[2] = (x[3] / p[0]) * tan(u[1]); xd[3] = u[0];\n}\n";
+    return true;
+  }
+
+ private:
+  double wheelbase_;
+};
+
+void SolveUserDefinedBicycle() {
+  const int N = 80;
+  const double dt = 0.05;
+  CDDPOptions o;
+  o.max_iterations = 60; o.tolerance = 1e-5; o.acceptable_tolerance = 1e-7; o.regularization.initial_value = 1e-5; o.verbose = false;
+  const auto x0 = vec({0.0, 0.0, 0.0, 0.0}), goal = vec({4.0, 3.0, M_PI / 2.0, 0.0});
+  const Eigen::MatrixXd Q = diag({0, 0, 0, 0.01}), R = diag({0.1, 0.5}), Qf = diag({100, 100, 50, 10});
+  CDDP c(x0, goal, N, dt, std::make_unique<UserBicycle>(dt, 2.0, "rk4"),
+         std::make_unique<QuadraticObjective>(Q, R, Qf, goal, std::vector<Eigen::VectorXd>(), dt), o);
+  c.addPathConstraint("ControlConstraint", std::make_unique<ControlConstraint>(vec({-2.0, -0.6}), vec({2.0, 0.6})));
+  std::vector<Eigen::VectorXd> X((size_t)N + 1, x0), U((size_t)N, vec({0.2, 0.0}));
+  c.setInitialTrajectory(X, U);
+  CDDPSolution s = c.solve("CLDDP");
+  CHECK(s.status_message == "OptimalSolutionFound" || s.status_message == "AcceptableSolutionFound");
+  const double Qa[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.01}, Ra[4] = {0.1, 0, 0, 0.5},
+               Qfa[16] = {100, 0, 0, 0, 0, 100, 0, 0, 0, 0, 50, 0, 0, 0, 0, 10}, lb[2] = {-2.0, -0.6}, ub[2] = {2.0, 0.6};
+  oracle_problem p{};
+  p.model = ORACLE_BICYCLE; p.n = 4; p.m = 2; p.horizon = N; p.dt = dt; p.integrator = ORACLE_RK4; p.has_control_box = 1;
+  p.model_params[0] = 2.0; p.Q = Qa; p.R = Ra; p.Qf = Qfa; p.lb = lb; p.ub = ub;
+  oracle_options oo;
+  oracle_default_options(&oo);
+  oo.max_iterations = 60; oo.tolerance = 1e-5; oo.acceptable_tolerance = 1e-7; oo.reg_initial_value = 1e-5;
+  std::vector<double> Xo((size_t)(N + 1) * 4, 0.0), Uo((size_t)N * 2, 0.0), Ko((size_t)N * 8), ko((size_t)N * 2);
+  for (int t = 0; t < N; ++t) Uo[(size_t)t * 2] = 0.2;
+  const double x0a[4] = {0, 0, 0, 0}, xr[4] = {4.0, 3.0, M_PI / 2.0, 0.0};
+  oracle_result res;
+  oracle_solve(&p, &oo, x0a, xr, nullptr, Xo.data(), Uo.data(), Ko.data(), ko.data(), &res, nullptr);
+  CHECK(res.iterations == s.iterations_completed);
+  CHECK(std::fabs(res.final_objective - s.final_objective) <= 1e-6 * std::fabs(res.final_objective));
+  std::printf("  user-defined bicycle: %d iterations, %s, J=%.9f (oracle %.9f)\n", s.iterations_completed, s.status_message.c_str(),
+              s.final_objective, res.final_objective);
+  // a source that does not compile is a setup error carrying the compiler log
+  class Broken : public UserBicycle {
+   public:
+    using UserBicycle::UserBicycle;
+    bool getDeviceModel(DeviceModelDescriptor &d) const override {
+      d.model = CDDP_B200_MODEL_USER;
+      d.source = "template <class T> __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xd) { xd[0] = oops; }";
+      return true;
+    }
+  };
+  CDDP c2(x0, goal, N, dt, std::make_unique<Broken>(dt, 2.0, "rk4"),
+          std::make_unique<QuadraticObjective>(Q, R, Qf, goal, std::vector<Eigen::VectorXd>(), dt), o);
+  bool threw = false;
+  try {
+    c2.solve("CLDDP");
+  } catch (const std::runtime_error &e) {
+    threw = std::string(e.what()).find("oops") != std::string::npos;
+  }
+  CHECK(threw);
+}
 }  // namespace
 
 int main() {
@@ -252,5 +333,6 @@ int main() {
   RUN(SolvePendulum);
   RUN(SolveQuadrotorBatch);
   RUN(SolveUnicycleObstacleIPDDP);
+  RUN(SolveUserDefinedBicycle);
   return finish();
 }

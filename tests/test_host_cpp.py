@@ -39,4 +39,4 @@ def test_host_library_links_only_the_c_abi():
 @pytest.mark.gpu
 def test_plugin_route_and_batched_facade_on_gpu():
     out = _run("test_b200_solver")
-    assert "SolvePendulum" in out and "SolveQuadrotorBatch" in out and "SolveUnicycleObstacleIPDDP" in out
+    assert "SolvePendulum" in out and "SolveQuadrotorBatch" in out and "SolveUnicycleObstacleIPDDP" in out and "SolveUserDefinedBicycle" in out
