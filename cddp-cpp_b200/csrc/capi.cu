@@ -869,6 +869,9 @@ void cddp_b200_ipddp_default_options(cddp_b200_ipddp_options *io) { /* options.h
   io->theta_norm_l2 = 0;
   io->max_filter_size = 5;
   io->barrier_strategy = CDDP_B200_BARRIER_ADAPTIVE;
+  io->jacobian_regularization_value = 1e-8;
+  io->jacobian_regularization_exponent = 0.25;
+  io->terminal_equality = 0;
 }
 
 int cddp_b200_ipddp_create(const cddp_b200_problem *p, const cddp_b200_options *o, const cddp_b200_ipddp_options *io,
@@ -968,6 +971,10 @@ int cddp_b200_ipddp_create_ex(const cddp_b200_problem *p, const cddp_b200_option
   AL(ip.mu, B); AL(ip.merit, B); AL(ip.logsum, B); AL(ip.filter_theta, B); AL(ip.inf_pr, B); AL(ip.inf_comp, B);
   AL(ip.step_norm, B); AL(ip.alpha_du, B); AL(ip.apm, B); AL(ip.adm, B);
   AL(ip.filter, B * IP_FILTER_CAP * 2); AL(ip.filter_size, B); AL(ip.ls_stats, B * CDDP_B200_MAX_ALPHAS * 4);
+  AL(ip.lamT, B * n); AL(ip.dlamT, B * n); AL(ip.lamh, B);
+  if (io->terminal_equality) {  // scratch of the one-sweep / (n+1)-column terminal-equality solve (ipddp_teq.cu)
+    AL(ip.kvar, B * (n + 1) * N * m); AL(ip.pvar, B * (n + 1) * (N + 1) * n); AL(ip.rvar, B * N * m);
+  }
 #undef AL
   cudaError_t e = cudaMemcpy(drt, rt.data(), Dd * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dbd, bd.data(), Dd * sizeof(int), cudaMemcpyHostToDevice);
@@ -976,13 +983,16 @@ int cddp_b200_ipddp_create_ex(const cddp_b200_problem *p, const cddp_b200_option
   if (e == cudaSuccess) e = cudaMemcpy(doff, off.data(), Dd * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dsc, sc.data(), Dd * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(ip.filter_size, 0, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ip.lamT, 0, B * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.dlamT, 0, B * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ip.lamh, 0, B * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(ip.ls_stats, 0, B * CDDP_B200_MAX_ALPHAS * 4 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(ip.ky, 0, B * N * Dd * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(ip.ks, 0, B * N * Dd * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(ip.Ky, 0, B * N * Dd * n * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(ip.Ks, 0, B * N * Dd * n * sizeof(double));
   if (e != cudaSuccess) { cddp_b200_destroy(s); return cuda_fail(e, "ipddp setup"); }
-  s->ic.d = D; s->ic.nc = nc;
+  s->ic.d = D; s->ic.nc = nc; s->ic.teq = io->terminal_equality ? 1 : 0;
   s->ic.row_type = drt; s->ic.row_bdim = dbd; s->ic.Gx = dGx; s->ic.Gu = dGu; s->ic.off = doff; s->ic.scale = dsc;
   s->ic.io = *io;
   if ((r = apply_layout(s, RECORDS_DENSE))) { cddp_b200_destroy(s); return r; }

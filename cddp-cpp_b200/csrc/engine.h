@@ -92,6 +92,7 @@ constexpr int IP_MAX_DUAL = 48;
 struct IpConstants {
   int d;   // total dual dimension (rows)
   int nc;  // number of constraints in the set (0 = unconstrained branch)
+  int teq; // TerminalEqualityConstraint on the reference state (terminal-equality branch of the backward pass)
   const int *row_type;   // device [d]
   const int *row_bdim;   // device [d]  ball: dimension of the centre
   const double *Gx;      // device [d][n]  STATE rows: dg/dx; BALL rows: centre in the first bdim entries
@@ -110,6 +111,12 @@ struct IpDevice {
   double *filter;    // [B][IP_FILTER_CAP][2] (merit, theta)
   int *filter_size;  // [B]
   double *ls_stats;  // [B][CDDP_B200_MAX_ALPHAS][4] success, cost, merit, theta of every line-search candidate
+  // terminal equality (ipddp_teq.cu)
+  double *lamT, *dlamT;  // [B][n] Lambda_T_eq_, dLambda_T_eq_
+  double *lamh;          // [B] Lambda_T_eq_ . h_T of the nominal trajectory (the merit's multiplier term)
+  double *kvar;          // [B][n+1][N][m]   feed-forward of the p+1 sequential-LQR variants
+  double *pvar;          // [B][n+1][N+1][n] costate of the variants
+  double *rvar;          // [B][N][m]        condensed control gradient r_t
 };
 
 enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };
@@ -135,6 +142,8 @@ cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const I
                                cudaStream_t st);
 cudaError_t launch_ip_forward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                               cudaStream_t st);
+cudaError_t launch_ip_backward_teq(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                                   cudaStream_t st);
 cudaError_t launch_gather_current(const Constants &c, const DeviceState &d, double *X, double *U, int which,
                                   cudaStream_t st);
 

@@ -28,6 +28,7 @@
 // factorisation it does not reject indefinite matrices and the reference relies on that (:1431-1435).
 #include "engine.h"
 #include "kernels_ipddp.cuh"
+#include "ldlt_small.cuh"
 #include "user_model_host.h"
 
 namespace cddp_b200 {
@@ -35,79 +36,6 @@ namespace cddp_b200 {
 namespace {
 
 using namespace kern;
-
-// Eigen 3.4.0 LDLT (lower, diagonal pivoting), ldlt_inplace<Lower>::unblocked — executed by ONE lane on the m x m
-// matrix in shared memory.  a: in = matrix, out = L strictly below the diagonal and D on it; tr: transpositions.
-// Returns info() == Success.
-__device__ bool ldlt_small(double *a, int *tr, int n) {
-  bool ok = true, found_zero_pivot = false;
-  for (int k = 0; k < n; ++k) {
-    int big = k;
-    double best = fabs(a[k * n + k]);
-    for (int i = k + 1; i < n; ++i)
-      if (fabs(a[i * n + i]) > best) {
-        best = fabs(a[i * n + i]);
-        big = i;
-      }
-    tr[k] = big;
-    if (big != k) {
-      const int s = n - big - 1;
-      for (int j = 0; j < k; ++j) { const double t = a[k * n + j]; a[k * n + j] = a[big * n + j]; a[big * n + j] = t; }
-      for (int i = 0; i < s; ++i) {
-        const double t = a[(big + 1 + i) * n + k];
-        a[(big + 1 + i) * n + k] = a[(big + 1 + i) * n + big];
-        a[(big + 1 + i) * n + big] = t;
-      }
-      { const double t = a[k * n + k]; a[k * n + k] = a[big * n + big]; a[big * n + big] = t; }
-      for (int i = k + 1; i < big; ++i) { const double t = a[i * n + k]; a[i * n + k] = a[big * n + i]; a[big * n + i] = t; }
-    }
-    const int rs = n - k - 1;
-    if (k > 0) {
-      double temp[CDDP_B200_MAX_M];
-      for (int j = 0; j < k; ++j) temp[j] = a[j * n + j] * a[k * n + j];
-      double s = 0.0;
-      for (int j = 0; j < k; ++j) s += a[k * n + j] * temp[j];
-      a[k * n + k] -= s;
-      for (int i = 0; i < rs; ++i) {
-        double s2 = 0.0;
-        for (int j = 0; j < k; ++j) s2 += a[(k + 1 + i) * n + j] * temp[j];
-        a[(k + 1 + i) * n + k] -= s2;
-      }
-    }
-    const double akk = a[k * n + k];
-    const bool valid = fabs(akk) > 0.0;
-    if (k == 0 && !valid) {
-      for (int j = 0; j < n; ++j) tr[j] = j;
-      return ok;
-    }
-    if (rs > 0 && valid) {
-      for (int i = 0; i < rs; ++i) a[(k + 1 + i) * n + k] /= akk;
-    } else if (rs > 0) {
-      for (int i = 0; i < rs; ++i)
-        if (a[(k + 1 + i) * n + k] != 0.0) ok = false;
-    }
-    if (found_zero_pivot && valid) ok = false;
-    else if (!valid) found_zero_pivot = true;
-  }
-  return ok;
-}
-
-// LDLT::solve for one right-hand side held in b[0..n) with stride `st`
-__device__ void ldlt_solve(const double *a, const int *tr, int n, double *b, int st) {
-  for (int k = 0; k < n; ++k)
-    if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < i; ++j) b[i * st] -= a[i * n + j] * b[j * st];
-  const double tol = 2.2250738585072014e-308;  // numeric_limits<double>::min()
-  for (int i = 0; i < n; ++i) {
-    if (fabs(a[i * n + i]) > tol) b[i * st] /= a[i * n + i];
-    else b[i * st] = 0.0;
-  }
-  for (int i = n - 1; i >= 0; --i)
-    for (int j = i + 1; j < n; ++j) b[i * st] -= a[j * n + i] * b[j * st];
-  for (int k = n - 1; k >= 0; --k)
-    if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
-}
 
 // ---------------------------------------------------------------------------------------------- backward sweep
 // A group of G lanes owns one trajectory; its dense blocks live in the group's slice of shared memory and the lanes
@@ -675,6 +603,7 @@ cudaError_t launch_ip_initialize(const Constants &c, const DeviceState &d, const
 
 cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                cudaStream_t st) {
+  if (ic.teq) return launch_ip_backward_teq(c, d, ic, ip, mode, st);  // terminal-equality branch (ipddp_teq.cu)
   // lanes per trajectory: the widest per-step loop has n*(n+m) entries
   if (d.n == 2 && d.m == 1) return launch_ip_backward_g<8, 2, 1>(c, d, ic, ip, mode, st);
   if (d.n == 3 && d.m == 2) return launch_ip_backward_g<8, 3, 2>(c, d, ic, ip, mode, st);

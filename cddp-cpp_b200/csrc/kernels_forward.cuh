@@ -41,7 +41,7 @@ __device__ __forceinline__ int select_alpha(bool success, double J, int al, int 
 }
 
 // per-instance bookkeeping after the line search (lane 0 only)
-__device__ void finish_line_search(const Constants &c, const DeviceState &d, int b, int mode, int first, double Jacc) {
+__device__ inline void finish_line_search(const Constants &c, const DeviceState &d, int b, int mode, int first, double Jacc) {
   d.accepted[b] = first;
   if (mode != FW_ITERATE) return;
   double reg = d.reg[b];

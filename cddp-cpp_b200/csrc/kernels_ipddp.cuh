@@ -52,7 +52,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ bool dominates(double m1, double t1, double m2, double t2) { return m1 <= m2 && t1 <= t2; }
 
 // detail::acceptFilterEntry (interior_point_utils.cpp:81-97); f = [cap][2] (merit, theta)
-__device__ void filter_accept(double *f, int &cnt, double merit, double theta) {
+__device__ inline void filter_accept(double *f, int &cnt, double merit, double theta) {
   for (int i = 0; i < cnt; ++i)
     if (dominates(f[2 * i], f[2 * i + 1], merit, theta)) return;
   int w = 0;
@@ -70,7 +70,7 @@ __device__ void filter_accept(double *f, int &cnt, double merit, double theta) {
   }
 }
 // detail::pruneFilterToBestPoints (interior_point_utils.cpp:116-141)
-__device__ void filter_prune(double *f, int &cnt) {
+__device__ inline void filter_prune(double *f, int &cnt) {
   if (cnt == 0) return;
   double bvm = f[0], bvt = f[1], bmm = f[0], bmt = f[1];
   for (int i = 0; i < cnt; ++i) {
@@ -82,7 +82,7 @@ __device__ void filter_prune(double *f, int &cnt) {
   if (fabs(bmt - bvt) > 1e-12 || fabs(bmm - bvm) > 1e-12) { f[2] = bmm; f[3] = bmt; cnt = 2; }
 }
 
-__device__ void ip_record_history(const DeviceState &d, const IpDevice &ip, int b) {
+__device__ inline void ip_record_history(const DeviceState &d, const IpDevice &ip, int b) {
   // recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp_solver.cpp:2084-2088)
   if (!d.history) return;
   const int hl = d.history_len[b];
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
   double *X = d.X[cur] + (size_t)b * (N + 1) * NS;
   const double *U = d.U[cur] + (size_t)b * N * NC;
   double *G = ip.G[cur] + (size_t)b * N * D, *S = ip.S[cur] + (size_t)b * N * D, *Y = ip.Y[cur] + (size_t)b * N * D;
-  const double mu = ic.nc == 0 ? fmax(c.opt.tolerance / 10.0, ic.io.mu_min_value) : ic.io.mu_initial;  // :884-887
+  const double mu = (ic.nc == 0 && !ic.teq) ? fmax(c.opt.tolerance / 10.0, ic.io.mu_min_value) : ic.io.mu_initial;  // :884-887
   double x[NS], xn[NS], u[NC];
 #pragma unroll
   for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
@@ -163,6 +163,20 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
     }
     J += sx;
   }
+  if (ic.teq) {  // terminal equality residual h = x_N - xref enters theta and inf_pr (:2833-2845, :2930-2935); Lambda_T_eq_ = 0
+    const double *ref = d.xref + (size_t)b * NS;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const double h = x[i] - ref[i];
+      acc += ic.io.theta_norm_l2 ? h * h : fabs(h);
+      maxr = fmax(maxr, fabs(h));
+      ip.lamT[(size_t)b * NS + i] = 0.0;
+      ip.dlamT[(size_t)b * NS + i] = 0.0;
+    }
+    theta += acc;
+    ip.lamh[b] = 0.0;
+  }
   if (ic.io.theta_norm_l2) theta = sqrt(theta);
   theta = fmax(theta, maxr);
   d.cost[b] = J;
@@ -177,6 +191,11 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
   ip.logsum[b] = logsum;
   ip.filter_theta[b] = fmax(theta, 1e-8);
   ip.filter_size[b] = 0;
+  if (ic.teq) {  // resetBarrierFilter seeds the filter when a terminal constraint is present (:2513-2516)
+    ip.filter[(size_t)b * IP_FILTER_CAP * 2] = J - mu * logsum;
+    ip.filter[(size_t)b * IP_FILTER_CAP * 2 + 1] = fmax(theta, 1e-8);
+    ip.filter_size[b] = 1;
+  }
   ip.apm[b] = 1.0;
   ip.adm[b] = 1.0;
   d.inf_du[b] = 0.0;
@@ -198,6 +217,7 @@ constexpr int kFwThreads = 64;
 
 struct TrialStats {
   double cost, logsum, theta, inf_pr, maxys, minys;
+  double lamh;  // Lambda_T_eq_new . h_T_new (terminal equality only)
   bool feasible;
 };
 
@@ -352,6 +372,23 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 #pragma unroll
     for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
   }
+  st.lamh = 0.0;
+  if (ic.teq) {  // Lambda_T_eq_new = Lambda_T_eq_ + alpha_pr dLambda_T_eq_ (:1716-1723); h_T_new = x_N - xref (:1756-1760)
+    const double *ref = d.xref + (size_t)b * NS;
+    double acc = 0.0, dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const double h = x[i] - ref[i];
+      const double ln = ip.lamT[(size_t)b * NS + i] + alpha_pr * ip.dlamT[(size_t)b * NS + i];
+      if (!finite_d(ln)) feas = false;
+      acc += l2 ? h * h : fabs(h);
+      st.inf_pr = fmax(st.inf_pr, fabs(h));
+      dot += ln * h;
+      if (WRITE && wr) ip.lamT[(size_t)b * NS + i] = ln;
+    }
+    st.theta += acc;
+    st.lamh = dot;
+  }
   if (l2) st.theta = sqrt(st.theta);
   st.theta = fmax(st.theta, st.inf_pr);
   st.feasible = feas;
@@ -383,12 +420,12 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   TrialStats st;
   ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
   const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
-  const double phi_new = st.cost - mu * st.logsum;  // computeBarrierMerit (:2850-2880)
+  const double phi_new = (st.cost - mu * st.logsum) + st.lamh;  // computeBarrierMerit (:2850-2880)
   const double theta_new = st.theta;
   const double inf_comp_new = D ? fmax(st.maxys - mu, mu - st.minys) : 0.0;
   bool accept = false;
   if (st.feasible && finite_d(phi_new) && finite_d(theta_new) && finite_d(st.inf_pr) && finite_d(inf_comp_new)) {
-    if (ic.nc == 0) {  // (:1787-1794)
+    if (ic.nc == 0 && !ic.teq) {  // (:1785-1794)
       const double dJ = cost_old - st.cost;
       const double expected = -alpha_pr * (d.dV[2 * bb] + 0.5 * alpha_pr * d.dV[2 * bb + 1]);
       const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
@@ -425,6 +462,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double th_new = __shfl_sync(0xffffffffu, theta_new, src), ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
   const double maxys = __shfl_sync(0xffffffffu, st.maxys, src), minys = __shfl_sync(0xffffffffu, st.minys, src);
   const double phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
+  const double lamh_new = __shfl_sync(0xffffffffu, st.lamh, src);
   if (__any_sync(0xffffffffu, alive && first >= 0)) {  // pass 2: replay the accepted trial (lane 0 of the group writes)
     TrialStats s2;
     ip_rollout<MODEL, true>(c, d, ic, ip, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
@@ -479,6 +517,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
     int fs = ip.filter_size[b];
     if ((mu_new < mu) && (mu_new > 0.0)) {
       fs = 0;
+      if (ic.teq) filter_accept(f, fs, phi, filter_theta);  // (:2633-2636)
     } else {
       filter_accept(f, fs, phi, filter_theta);
       if (fs > ic.io.max_filter_size) filter_prune(f, fs);
@@ -488,7 +527,8 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
     ip.mu[b] = mu_new;
     ip.inf_pr[b] = inf_pr;
     ip.inf_comp[b] = inf_comp;
-    ip.merit[b] = cost_new - mu_new * logsum_new;
+    ip.merit[b] = (cost_new - mu_new * logsum_new) + lamh_new;
+    ip.lamh[b] = lamh_new;
     ip.logsum[b] = logsum_new;
     ip.filter_theta[b] = filter_theta;
     ip_record_history(d, ip, b);                                     // cddp_solver_base.cpp:133-135
@@ -521,6 +561,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
     }
   } else {  // handleForwardPassFailure (:2037-2082)
     reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+    if (!no_barrier && ic.teq) reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);  // (:2047-2051)
     if (reg >= c.opt.reg_max_value) {
       const double base = sqrt(fmax(c.opt.acceptable_tolerance, c.opt.tolerance));
       const double at = no_barrier ? base : fmax(base, ic.io.barrier_tol_mult * mu);

@@ -71,7 +71,8 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
         "unicycle_obstacle": _cfg_unicycle_obstacle, "cartpole_ipddp": _cfg_cartpole_ipddp,
         "pendulum_ipddp": _cfg_pendulum_ipddp, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
         "quadrotor_ipddp": _cfg_quadrotor_ipddp, "bicycle_user": _cfg_bicycle_user, "bicycle_user_ipddp": _cfg_bicycle_user_ipddp,
-        "chain7_user": _cfg_chain7_user,
+        "chain7_user": _cfg_chain7_user, "unicycle_obstacle_teq": _cfg_unicycle_obstacle_teq,
+        "unicycle_teq": _cfg_unicycle_teq, "cartpole_teq": _cfg_cartpole_teq,
     }
     if name not in builders:
         raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
@@ -272,6 +273,33 @@ def _cfg_unicycle_obstacle(batch, horizon, seed_offset):
     return dict(name="unicycle_obstacle", config_id=4, solver="ipddp", spec=spec, options=options, constraints=constraints,
                 ipddp_options={}, x0=x0, xref=xref, X0=None, U0=U0, ref_traj=None,
                 notes="unicycle obstacle avoidance n=3 m=2 N=200, IPDDP, control box + ball (python_portfolio_lib.py:374-473)")
+
+
+def _cfg_unicycle_obstacle_teq(batch, horizon, seed_offset):
+    """BASELINE config #4 in full: the obstacle-avoidance problem above PLUS TerminalEqualityConstraint(goal)
+    (addTerminalConstraint pattern of tests/cddp_core/test_ipddp_solver.cpp:1417-1419), i.e. path-inequality +
+    terminal-equality, IPDDP, n=3 m=2 N=200."""
+    cfg = _cfg_unicycle_obstacle(batch, horizon, seed_offset)
+    cfg.update(name="unicycle_obstacle_teq", config_id=4, ipddp_options=dict(terminal_equality=1),
+               notes="unicycle obstacle avoidance n=3 m=2 N=200, IPDDP, control box + ball + terminal equality (BASELINE config #4)")
+    return cfg
+
+
+def _cfg_unicycle_teq(batch, horizon, seed_offset):
+    """Terminal equality only (no path constraints): IPDDPTest.SolveWithTerminalEqualityOnly pattern
+    (test_ipddp_solver.cpp:1580-1637) on the unicycle."""
+    cfg = _cfg_unicycle_obstacle(batch, horizon or 100, seed_offset)
+    cfg.update(name="unicycle_teq", config_id=15, constraints=[], ipddp_options=dict(terminal_equality=1),
+               notes="unicycle, IPDDP with a terminal equality constraint only")
+    return cfg
+
+
+def _cfg_cartpole_teq(batch, horizon, seed_offset):
+    """Cartpole swing-up (rk4, n=4, m=1) with control box + terminal equality."""
+    cfg = _cfg_cartpole_ipddp(batch, horizon, seed_offset)
+    cfg.update(name="cartpole_teq", config_id=16, constraints=[dict(type="control_box", lb=[-5.0], ub=[5.0])],
+               ipddp_options=dict(terminal_equality=1), notes="cartpole swing-up, IPDDP, control box + terminal equality")
+    return cfg
 
 
 def _cfg_unicycle_ipddp_free(batch, horizon, seed_offset):

@@ -175,10 +175,14 @@ typedef struct {
   double violation_acceptance_threshold; /* 1e-6 */
   double max_violation_threshold;        /* 1e4 */
   double min_violation_for_armijo_check; /* 1e-7 */
+  double jacobian_regularization_value;    /* ipddp 1e-8: reduced-system floor of the terminal-equality solve (options.hpp:181-184) */
+  double jacobian_regularization_exponent; /* 0.25 */
   int theta_norm_l2;                     /* theta_norm: 0 = "l1" (default), 1 = "l2" */
   int max_filter_size;                   /* 5 (at most 7) */
   int barrier_strategy;                  /* CDDP_B200_BARRIER_ADAPTIVE */
-  int reserved;
+  int terminal_equality;                 /* 1 = addTerminalConstraint("TerminalEqualityConstraint", TerminalEqualityConstraint(
+                                            reference state)) (terminal_constraint.hpp:61-117): h(x_N) = x_N - xref[b] = 0, solved by
+                                            the terminal-equality branch (ipddp_solver.cpp:1120-1353, :484-639) */
 } cddp_b200_ipddp_options;
 
 /* CUDA-event timings accumulated since the last cddp_b200_reset_timing(); one launch of each
@@ -330,8 +334,8 @@ CDDP_B200_API int cddp_b200_get_forward(cddp_b200_solver *s, double *costs, int 
 
 /* ---- IPDDP handle: replaces B x { CDDP::addPathConstraint(...); CDDP::solve("IPDDP") } (cddp_core.cpp:156-161,
  * :235-270; IPDDPSolver, src/cddp_core/ipddp_solver.cpp).  Scope: cold start (options.warm_start = false),
- * use_ilqr = true, path inequality constraints of the four kinds above, no terminal constraints, built-in models
- * except LTI; problem->has_control_box is ignored (a ControlConstraint is an entry of `constraints`).  The handle is
+ * use_ilqr = true, path inequality constraints of the four kinds above, optionally a TerminalEqualityConstraint on the
+ * reference state (ipddp_opts->terminal_equality; no terminal INequalities), built-in models except LTI; problem->has_control_box is ignored (a ControlConstraint is an entry of `constraints`).  The handle is
  * driven by the same entry points as a CLDDP handle: cddp_b200_set_instances (X0 is ignored: IPDDP re-rolls the
  * state trajectory out from the given controls, ipddp_solver.cpp:876-882), cddp_b200_initialize / _linearize /
  * _backward_pass / _forward_pass / _iterate / _solve, cddp_b200_get_solution (inf_du = unscaled max |Q_u|). ---- */

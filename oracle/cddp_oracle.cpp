@@ -479,6 +479,39 @@ double min_eigenvalue_sym(const double *M, int n) {
   return mn;
 }
 
+/* all eigenvalues of a symmetric matrix (cyclic Jacobi), used for the singular values of a small square matrix:
+ * sigma_i = sqrt(eig_i(A^T A)) stands in for Eigen::JacobiSVD(A).singularValues() (ipddp_solver.cpp:557-560) */
+void eigenvalues_sym(const double *M, int n, double *ev) {
+  double a[MAXM * MAXM];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i * n + j] = 0.5 * (M[i * n + j] + M[j * n + i]);
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
+    if (off < 1e-300) break;
+    for (int p_ = 0; p_ < n; ++p_)
+      for (int q = p_ + 1; q < n; ++q) {
+        const double apq = a[p_ * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * n + q] - a[p_ * n + p_]) / (2.0 * apq);
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = a[k * n + p_], akq = a[k * n + q];
+          a[k * n + p_] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = a[p_ * n + k], aqk = a[q * n + k];
+          a[p_ * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) ev[i] = a[i * n + i];
+}
+
 /* MatrixXd::inverse() for a dynamic matrix = PartialPivLU().inverse() (clddp_solver.cpp:143). */
 void inverse_lu(const double *M, int n, double *Inv) {
   double a[MAXM * MAXM];
@@ -1267,9 +1300,13 @@ struct IpState {
   double inf_pr = 0, inf_du = 0, inf_comp = 0, step_norm = 0, reg = 0, alpha_pr = 1, alpha_du = 1;
   double dV[2] = {0, 0};
   std::vector<FilterPt> filter;
+  /* TerminalEqualityConstraint(target = reference state): h(x_N) = x_N - xref, Jacobian I (terminal_constraint.hpp:61-117) */
+  bool teq = false;
+  std::vector<double> lamT, dlamT; /* Lambda_T_eq_, dLambda_T_eq_ */
+  std::vector<double> kvar, pvar;  /* k / p of the p+1 sequential-LQR variants */
 };
 
-double ip_theta(const IpState &s, const double *G, const double *S) { /* computeTheta :2778-2848 */
+double ip_theta(const IpState &s, const double *G, const double *S, const double *hT = nullptr) { /* computeTheta :2778-2848 */
   const bool l2 = s.io->theta_norm_l2 != 0;
   double total = 0.0, max_entry = 0.0;
   for (int c = 0, o = 0; c < s.nc; ++c) { /* per constraint, per t, as the reference's map-of-trajectories loops */
@@ -1286,10 +1323,19 @@ double ip_theta(const IpState &s, const double *G, const double *S) { /* compute
     }
     o += dim;
   }
+  if (hT) { /* :2833-2845 */
+    double acc = 0.0, mx = 0.0;
+    for (int i = 0; i < s.n; ++i) {
+      acc += l2 ? hT[i] * hT[i] : std::fabs(hT[i]);
+      mx = std::max(mx, std::fabs(hT[i]));
+    }
+    total += acc;
+    max_entry = std::max(max_entry, mx);
+  }
   const double th = l2 ? std::sqrt(total) : total;
   return std::max(th, max_entry);
 }
-double ip_merit(const IpState &s, const double *S, double cost) { /* computeBarrierMerit :2850-2880 */
+double ip_merit(const IpState &s, const double *S, double cost, const double *lamT = nullptr, const double *hT = nullptr) { /* computeBarrierMerit :2850-2880 */
   double merit = cost;
   for (int c = 0, o = 0; c < s.nc; ++c) {
     const int dim = constraint_dim(s.p, s.cs[c]);
@@ -1300,25 +1346,39 @@ double ip_merit(const IpState &s, const double *S, double cost) { /* computeBarr
     }
     o += dim;
   }
+  if (lamT && hT) { /* :2872-2878 */
+    double dot = 0.0;
+    for (int i = 0; i < s.n; ++i) dot += lamT[i] * hT[i];
+    merit += dot;
+  }
   return merit;
 }
 void ip_primal_comp(const IpState &s, const double *G, const double *S, const double *Y, double mu, double *inf_pr,
-                    double *inf_comp) { /* computePrimalAndComplementarity :2882-2937 */
+                    double *inf_comp, const double *hT = nullptr) { /* computePrimalAndComplementarity :2882-2937 */
   double ip = 0.0, ic = 0.0;
   for (size_t i = 0; i < (size_t)s.N * s.d; ++i) {
     ip = std::max(ip, std::fabs(G[i] + S[i]));
     ic = std::max(ic, std::fabs(Y[i] * S[i] - mu));
   }
+  if (hT)
+    for (int i = 0; i < s.n; ++i) ip = std::max(ip, std::fabs(hT[i]));
   *inf_pr = ip;
   *inf_comp = ic;
 }
+inline void ip_terminal_residual(const IpState &s, const double *X, double *hT) { /* evaluateTerminalEqualityResidual :150-176 */
+  for (int i = 0; i < s.n; ++i) hT[i] = X[(size_t)s.N * s.n + i] - s.xref[i];
+}
 void ip_reset_filter(IpState &s) { /* resetBarrierFilter :2484-2517 */
-  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp);
-  s.merit = ip_merit(s, s.S.data(), s.cost);
+  double hT[MAXN];
+  if (s.teq) ip_terminal_residual(s, s.X.data(), hT);
+  const double *h = s.teq ? hT : nullptr;
+  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp, h);
+  s.merit = ip_merit(s, s.S.data(), s.cost, s.teq ? s.lamT.data() : nullptr, h);
   s.phi = s.merit;
-  s.filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data()), 1e-8);
+  s.filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data(), h), 1e-8);
   s.theta = std::max(s.filter_theta, std::max(s.io->theta_0_floor, 1e-8));
   s.filter.clear();
+  if (s.teq) accept_filter_entry(s.filter, s.phi, s.filter_theta); /* :2513-2516 */
 }
 
 void ip_initialize(IpState &s, const double *U0) { /* IPDDPSolver::initialize cold start :818-913 */
@@ -1336,7 +1396,10 @@ void ip_initialize(IpState &s, const double *U0) { /* IPDDPSolver::initialize co
   std::memcpy(s.X.data(), s.x0, sizeof(double) * n);
   for (int t = 0; t < N; ++t) /* :876-882 rollout of the given controls */
     discrete_dynamics(s.p, &s.X[(size_t)t * n], &s.U[(size_t)t * m], t * s.p->dt, &s.X[(size_t)(t + 1) * n]);
-  s.mu = s.nc == 0 ? std::max(s.o->tolerance / 10.0, s.io->mu_min_value) : s.io->mu_initial; /* :884-887 */
+  s.teq = s.io->terminal_equality != 0;
+  s.lamT.assign(n, 0.0);
+  s.dlamT.assign(n, 0.0);
+  s.mu = (s.nc == 0 && !s.teq) ? std::max(s.o->tolerance / 10.0, s.io->mu_min_value) : s.io->mu_initial; /* :884-887 */
   s.reg = s.o->reg_initial_value;
   s.step_norm = 0.0;
   s.alpha_pr = 1.0;
@@ -1355,6 +1418,379 @@ void ip_initialize(IpState &s, const double *U0) { /* IPDDPSolver::initialize co
   ip_reset_filter(s);
   s.inf_du = 0.0;
   s.dV[0] = s.dV[1] = 0.0;
+}
+
+/* solveSequentialLQR (ipddp_solver.cpp:411-482) for ONE right-hand side: Q,q (N+1), R,r,M (N), d = 0.  K [N][m][n] and
+ * P [N+1][n][n] do not depend on q/r, but the reference recomputes them per variant; so does this restatement. */
+bool sequential_lqr(int n, int m, int N, const std::vector<double> &Q, const std::vector<double> &q, const std::vector<double> &R,
+                    const std::vector<double> &r, const std::vector<double> &M, const std::vector<double> &A,
+                    const std::vector<double> &B, std::vector<double> &K, std::vector<double> &k, std::vector<double> &P,
+                    std::vector<double> &pp) {
+  K.assign((size_t)N * m * n, 0.0);
+  k.assign((size_t)N * m, 0.0);
+  P.assign((size_t)(N + 1) * n * n, 0.0);
+  pp.assign((size_t)(N + 1) * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) P[(size_t)N * n * n + i * n + j] = 0.5 * (Q[(size_t)N * n * n + i * n + j] + Q[(size_t)N * n * n + j * n + i]);
+    pp[(size_t)N * n + i] = q[(size_t)N * n + i];
+  }
+  LDLT ldlt;
+  for (int t = N - 1; t >= 0; --t) {
+    const double *Pn = &P[(size_t)(t + 1) * n * n], *pn = &pp[(size_t)(t + 1) * n];
+    const double *At = &A[(size_t)t * n * n], *Bt = &B[(size_t)t * n * m];
+    const double *Qt = &Q[(size_t)t * n * n], *Rt = &R[(size_t)t * m * m], *Mt = &M[(size_t)t * n * m];
+    double BtP[MAXM * MAXN], Quu[MAXM * MAXM], Qux[MAXM * MAXN], Qx[MAXN], Qu[MAXM];
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int l = 0; l < n; ++l) a += Bt[l * m + i] * Pn[l * n + j];
+        BtP[i * n + j] = a;
+      }
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) {
+        double a1 = 0.0, a2 = 0.0; /* BtP B and B^T P^T B */
+        for (int l = 0; l < n; ++l) a1 += BtP[i * n + l] * Bt[l * m + j];
+        for (int l = 0; l < n; ++l) {
+          double c = 0.0;
+          for (int q2 = 0; q2 < n; ++q2) c += Bt[q2 * m + i] * Pn[l * n + q2];
+          a2 += c * Bt[l * m + j];
+        }
+        Quu[i * m + j] = 0.5 * (((Rt[i * m + j] + a1) + Rt[j * m + i]) + a2);
+      }
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int l = 0; l < n; ++l) a += BtP[i * n + l] * At[l * n + j];
+        Qux[i * n + j] = a + Mt[j * m + i];
+      }
+    for (int i = 0; i < n; ++i) { /* drift = p_next (d = 0) */
+      double a = 0.0;
+      for (int l = 0; l < n; ++l) a += At[l * n + i] * pn[l];
+      Qx[i] = q[(size_t)t * n + i] + a;
+    }
+    for (int i = 0; i < m; ++i) {
+      double a = 0.0;
+      for (int l = 0; l < n; ++l) a += Bt[l * m + i] * pn[l];
+      Qu[i] = r[(size_t)t * m + i] + a;
+    }
+    ldlt.compute(Quu, m);
+    if (!ldlt.ok) return false;
+    double *Kt = &K[(size_t)t * m * n], *kt = &k[(size_t)t * m];
+    double col[MAXM];
+    for (int j = 0; j < n; ++j) {
+      for (int i = 0; i < m; ++i) col[i] = Qux[i * n + j];
+      ldlt.solve_inplace(col);
+      for (int i = 0; i < m; ++i) Kt[i * n + j] = -col[i];
+    }
+    for (int i = 0; i < m; ++i) col[i] = Qu[i];
+    ldlt.solve_inplace(col);
+    for (int i = 0; i < m; ++i) kt[i] = -col[i];
+    double APA[MAXN * MAXN], PA[MAXN * MAXN], QuuK[MAXM * MAXN], Quuk[MAXM];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int l = 0; l < n; ++l) a += Pn[i * n + l] * At[l * n + j];
+        PA[i * n + j] = a;
+      }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int l = 0; l < n; ++l) a += At[l * n + i] * PA[l * n + j];
+        APA[i * n + j] = a;
+      }
+    for (int i = 0; i < m; ++i) {
+      for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int l = 0; l < m; ++l) a += Quu[i * m + l] * Kt[l * n + j];
+        QuuK[i * n + j] = a;
+      }
+      double a = 0.0;
+      for (int l = 0; l < m; ++l) a += Quu[i * m + l] * kt[l];
+      Quuk[i] = a;
+    }
+    double Pt[MAXN * MAXN];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) { /* P = Q + A^T P A + Q_xu K + K^T Q_ux + K^T Q_uu K */
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int l = 0; l < m; ++l) {
+          a1 += Qux[l * n + i] * Kt[l * n + j];
+          a2 += Kt[l * n + i] * Qux[l * n + j];
+          a3 += Kt[l * n + i] * QuuK[l * n + j];
+        }
+        Pt[i * n + j] = (((Qt[i * n + j] + APA[i * n + j]) + a1) + a2) + a3;
+      }
+    bool finite = true;
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j < n; ++j) {
+        const double v = 0.5 * (Pt[i * n + j] + Pt[j * n + i]);
+        P[(size_t)t * n * n + i * n + j] = v;
+        finite = finite && std::isfinite(v);
+      }
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0; /* p = Q_x + Q_xu k + K^T Q_u + K^T Q_uu k */
+      for (int l = 0; l < m; ++l) {
+        a1 += Qux[l * n + i] * kt[l];
+        a2 += Kt[l * n + i] * Qu[l];
+        a3 += Kt[l * n + i] * Quuk[l];
+      }
+      pp[(size_t)t * n + i] = ((Qx[i] + a1) + a2) + a3;
+      finite = finite && std::isfinite(pp[(size_t)t * n + i]);
+    }
+    for (int i = 0; i < m * n; ++i) finite = finite && std::isfinite(Kt[i]);
+    for (int i = 0; i < m; ++i) finite = finite && std::isfinite(kt[i]);
+    if (!finite) return false;
+  }
+  return true;
+}
+
+/* IPDDPSolver::backwardPass, terminal-equality branch (:1120-1353) with solveTerminalEqualityLQR (:484-639); H_T = I,
+ * b_T = -h_T, dx0 = 0, d = 0. */
+bool ip_backward_teq(IpState &s, const double *Vx, const double *Vxx) {
+  const int n = s.n, m = s.m, N = s.N, d = s.d, pd = s.n;
+  const oracle_problem *p = s.p;
+  const double dt = p->dt;
+  std::vector<double> Q((size_t)(N + 1) * n * n, 0.0), q((size_t)(N + 1) * n, 0.0), R((size_t)N * m * m, 0.0), r((size_t)N * m, 0.0),
+      M((size_t)N * n * m, 0.0);
+  for (int i = 0; i < n * n; ++i) Q[(size_t)N * n * n + i] = Vxx[i];
+  for (int i = 0; i < n; ++i) q[(size_t)N * n + i] = Vx[i];
+  double hT[MAXN];
+  ip_terminal_residual(s, s.X.data(), hT);
+  double inf_pr = 0.0, inf_comp = 0.0, inf_du = 0.0, step_norm = 0.0;
+  for (int i = 0; i < n; ++i) inf_pr = std::max(inf_pr, std::fabs(hT[i])); /* :1041 */
+  std::vector<double> Gx((size_t)std::max(d, 1) * n), Gu((size_t)std::max(d, 1) * m);
+  std::vector<double> YSall((size_t)N * std::max(d, 1)), rhat_all((size_t)N * std::max(d, 1)), prim_all((size_t)N * std::max(d, 1)),
+      ssafe_all((size_t)N * std::max(d, 1));
+  for (int t = 0; t < N; ++t) {
+    const double *x = &s.X[(size_t)t * n], *u = &s.U[(size_t)t * m];
+    const double *ref = ref_at(p, s.xref, s.ref_traj, t);
+    double *Qt = &Q[(size_t)t * n * n], *qt = &q[(size_t)t * n], *Rt = &R[(size_t)t * m * m], *rt = &r[(size_t)t * m], *Mt = &M[(size_t)t * n * m];
+    for (int i = 0; i < n; ++i) {
+      double lx = 0.0;
+      for (int j = 0; j < n; ++j) lx += (2.0 * (p->Q[i * n + j] * dt)) * (x[j] - ref[j]);
+      qt[i] = lx;
+      for (int j = 0; j < n; ++j) Qt[i * n + j] = 0.5 * (2.0 * (p->Q[i * n + j] * dt) + 2.0 * (p->Q[j * n + i] * dt)); /* :1149 */
+    }
+    for (int i = 0; i < m; ++i) {
+      double lu = 0.0;
+      for (int j = 0; j < m; ++j) lu += (2.0 * (p->R[i * m + j] * dt)) * u[j];
+      rt[i] = lu;
+      for (int j = 0; j < m; ++j) Rt[i * m + j] = 0.5 * (2.0 * (p->R[i * m + j] * dt) + 2.0 * (p->R[j * m + i] * dt));
+    }
+    if (d) { /* :1181-1252 */
+      const double *y = &s.Y[(size_t)t * d], *sl = &s.S[(size_t)t * d], *g = &s.G[(size_t)t * d];
+      constraint_jacobians(p, s.cs, s.nc, x, Gx.data(), Gu.data());
+      double w[MAXDUAL];
+      double *YS = &YSall[(size_t)t * d], *rh = &rhat_all[(size_t)t * d], *pr = &prim_all[(size_t)t * d], *sf = &ssafe_all[(size_t)t * d];
+      for (int i = 0; i < d; ++i) {
+        sf[i] = std::max(sl[i], std::max(s.mu * 1e-3, EPS_SLACK));
+        YS[i] = clip_pos(y[i], sf[i]);
+        pr[i] = g[i] + sl[i];
+        const double comp = y[i] * sl[i] - s.mu;
+        rh[i] = y[i] * pr[i] - comp;
+        w[i] = y[i] + clip_signed(rh[i], sf[i]);
+        inf_pr = std::max(inf_pr, std::fabs(pr[i]));
+        inf_comp = std::max(inf_comp, std::fabs(comp));
+      }
+      for (int i = 0; i < n; ++i) {
+        double a = 0.0;
+        for (int k2 = 0; k2 < d; ++k2) a += Gx[k2 * n + i] * w[k2];
+        qt[i] += a;
+      }
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0;
+        for (int k2 = 0; k2 < d; ++k2) a += Gu[k2 * m + i] * w[k2];
+        rt[i] += a;
+      }
+      double Qn[MAXN * MAXN], Rn[MAXM * MAXM];
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double a = 0.0;
+          for (int k2 = 0; k2 < d; ++k2) a += Gx[k2 * n + i] * (YS[k2] * Gx[k2 * n + j]);
+          Qn[i * n + j] = Qt[i * n + j] + a;
+        }
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) { /* M += (Q_yu^T YSinv Q_yx)^T */
+          double a = 0.0;
+          for (int k2 = 0; k2 < d; ++k2) a += Gu[k2 * m + j] * (YS[k2] * Gx[k2 * n + i]);
+          Mt[i * m + j] += a;
+        }
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+          double a = 0.0;
+          for (int k2 = 0; k2 < d; ++k2) a += Gu[k2 * m + i] * (YS[k2] * Gu[k2 * m + j]);
+          Rn[i * m + j] = Rt[i * m + j] + a;
+        }
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Qt[i * n + j] = 0.5 * (Qn[i * n + j] + Qn[j * n + i]);
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) Rt[i * m + j] = 0.5 * (Rn[i * m + j] + Rn[j * m + i]);
+    }
+    for (int i = 0; i < m; ++i) Rt[i * m + i] += s.reg; /* :1254 */
+  }
+  /* solveTerminalEqualityLQR */
+  std::vector<double> qb = q;
+  for (int i = 0; i < n; ++i) qb[(size_t)N * n + i] += s.lamT[i]; /* H_T^T lambda_prev, H_T = I (:520-526) */
+  std::vector<std::vector<double>> Kv(pd + 1), kv(pd + 1), Pv(pd + 1), pv(pd + 1);
+  std::vector<double> xT((size_t)(pd + 1) * n, 0.0);
+  for (int v = 0; v <= pd; ++v) {
+    std::vector<double> qv = qb;
+    if (v > 0) qv[(size_t)N * n + (v - 1)] += 1.0; /* H_T.row(v-1)^T */
+    if (!sequential_lqr(n, m, N, Q, qv, R, r, M, s.A, s.B, Kv[v], kv[v], Pv[v], pv[v])) return false;
+    double dx[MAXN], dxn[MAXN], du[MAXM];
+    for (int i = 0; i < n; ++i) dx[i] = 0.0;
+    for (int t = 0; t < N; ++t) { /* rolloutLinearPolicy (:368-392) */
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0;
+        for (int j = 0; j < n; ++j) a += Kv[v][((size_t)t * m + i) * n + j] * dx[j];
+        du[i] = kv[v][(size_t)t * m + i] + a;
+      }
+      for (int i = 0; i < n; ++i) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) a1 += s.A[(size_t)t * n * n + i * n + j] * dx[j];
+        for (int j = 0; j < m; ++j) a2 += s.B[(size_t)t * n * m + i * m + j] * du[j];
+        dxn[i] = (a1 + a2) + 0.0;
+      }
+      for (int i = 0; i < n; ++i) dx[i] = dxn[i];
+    }
+    for (int i = 0; i < n; ++i) xT[(size_t)v * n + i] = dx[i];
+  }
+  double As[MAXN * MAXN], rhs[MAXN], AtA[MAXN * MAXN], Atb[MAXN];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < pd; ++j) As[i * pd + j] = xT[(size_t)(j + 1) * n + i] - xT[i]; /* A_small = H_T S_mat = S_mat */
+    rhs[i] = -hT[i] - xT[i];                                                              /* b_T - H_T xT_0 */
+  }
+  double trace = 0.0;
+  for (int i = 0; i < pd; ++i) {
+    for (int j = 0; j < pd; ++j) {
+      double a = 0.0;
+      for (int l = 0; l < n; ++l) a += As[l * pd + i] * As[l * pd + j];
+      AtA[i * pd + j] = a;
+    }
+    double a = 0.0;
+    for (int l = 0; l < n; ++l) a += As[l * pd + i] * rhs[l];
+    Atb[i] = a;
+    trace += AtA[i * pd + i];
+  }
+  const double trace_term = trace > 1.0 ? trace / std::max(pd, 1) : 1.0;
+  const double base_floor = std::max(1e-10, s.io->jacobian_regularization_value * std::pow(std::max(s.mu, 0.0), s.io->jacobian_regularization_exponent));
+  const double regq = std::max(base_floor, 1e-6 * trace_term);
+  double ev[MAXN];
+  eigenvalues_sym(AtA, pd, ev);
+  double smax = 0.0, smin = std::numeric_limits<double>::infinity();
+  for (int i = 0; i < pd; ++i) {
+    const double sg = std::sqrt(std::max(ev[i], 0.0));
+    smax = std::max(smax, sg);
+    smin = std::min(smin, sg);
+  }
+  const double svd_reg = std::max(1e-8 * smax - smin, 0.0);
+  const double reg_base = std::max(regq, svd_reg);
+  double rn = 0.0;
+  for (int i = 0; i < n; ++i) rn += rhs[i] * rhs[i];
+  const double cap = 100.0 * (1.0 + std::sqrt(rn));
+  const double scales[5] = {1.0, 10.0, 100.0, 1e3, 1e4};
+  double best[MAXN], best_res = std::numeric_limits<double>::infinity();
+  bool found = false;
+  for (int i = 0; i < pd; ++i) best[i] = 0.0;
+  LDLT ldlt;
+  for (int si = 0; si < 5; ++si) {
+    const double reg_i = std::max(reg_base * scales[si], 1e-12);
+    double sh[MAXN * MAXN], lam[MAXN];
+    for (int i = 0; i < pd * pd; ++i) sh[i] = AtA[i];
+    for (int i = 0; i < pd; ++i) sh[i * pd + i] += reg_i;
+    ldlt.compute(sh, pd);
+    if (!ldlt.ok) continue;
+    for (int i = 0; i < pd; ++i) lam[i] = Atb[i];
+    ldlt.solve_inplace(lam);
+    bool fin = true;
+    double ln = 0.0;
+    for (int i = 0; i < pd; ++i) {
+      fin = fin && std::isfinite(lam[i]);
+      ln += lam[i] * lam[i];
+    }
+    if (!fin) continue;
+    ln = std::sqrt(ln);
+    if (ln > cap)
+      for (int i = 0; i < pd; ++i) lam[i] *= cap / std::max(ln, 1e-12);
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0;
+      for (int j = 0; j < pd; ++j) a += As[i * pd + j] * lam[j];
+      res += (a - rhs[i]) * (a - rhs[i]);
+    }
+    res = std::sqrt(res);
+    if (!std::isfinite(res)) continue;
+    if (!found || res < best_res) {
+      for (int i = 0; i < pd; ++i) best[i] = lam[i];
+      best_res = res;
+      found = true;
+    }
+  }
+  s.Ku = Kv[0];
+  s.ku = kv[0];
+  std::vector<double> pout = pv[0];
+  for (int v = 0; v < pd; ++v) {
+    const double coeff = best[v];
+    for (size_t i = 0; i < s.ku.size(); ++i) s.ku[i] += coeff * (kv[v + 1][i] - kv[0][i]);
+    for (size_t i = 0; i < pout.size(); ++i) pout[i] += coeff * (pv[v + 1][i] - pv[0][i]);
+  }
+  for (int i = 0; i < pd; ++i) s.dlamT[i] = best[i]; /* dLambda_T_eq_ = lambda_delta (:1267) */
+  for (int t = 0; t < N; ++t) { /* :1268-1274 */
+    for (int i = 0; i < m; ++i) {
+      double a = 0.0;
+      for (int l = 0; l < n; ++l) a += s.B[(size_t)t * n * m + l * m + i] * pout[(size_t)(t + 1) * n + l];
+      inf_du = std::max(inf_du, std::fabs(r[(size_t)t * m + i] + a));
+      step_norm = std::max(step_norm, std::fabs(s.ku[(size_t)t * m + i]));
+    }
+  }
+  /* rolloutLinearPolicy with the final gains + slack / dual gains (:1276-1320) */
+  {
+    double dx[MAXN], dxn[MAXN], du[MAXM];
+    for (int i = 0; i < n; ++i) dx[i] = 0.0;
+    for (int t = 0; t < N; ++t) {
+      const double *x = &s.X[(size_t)t * n];
+      const double *Ku = &s.Ku[(size_t)t * m * n], *ku = &s.ku[(size_t)t * m];
+      if (d) {
+        constraint_jacobians(p, s.cs, s.nc, x, Gx.data(), Gu.data());
+        const double *y = &s.Y[(size_t)t * d];
+        const double *YS = &YSall[(size_t)t * d], *rh = &rhat_all[(size_t)t * d], *pr = &prim_all[(size_t)t * d], *sf = &ssafe_all[(size_t)t * d];
+        for (int k2 = 0; k2 < d; ++k2) {
+          double temp = 0.0;
+          for (int i = 0; i < m; ++i) temp += Gu[k2 * m + i] * ku[i];
+          const size_t e = (size_t)t * d + k2;
+          s.ky[e] = clip_signed(rh[k2] + y[k2] * temp, sf[k2]);
+          s.ks[e] = -pr[k2] - temp;
+          double a1 = 0.0, a2 = 0.0;
+          for (int j = 0; j < n; ++j) {
+            double gk = 0.0;
+            for (int i = 0; i < m; ++i) gk += Gu[k2 * m + i] * Ku[i * n + j];
+            const double qq = Gx[k2 * n + j] + gk;
+            s.Ky[e * n + j] = clampd(YS[k2] * qq, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+            s.Ks[e * n + j] = -Gx[k2 * n + j] - gk;
+            a1 += s.Ks[e * n + j] * dx[j];
+            a2 += s.Ky[e * n + j] * dx[j];
+          }
+          s.dS[e] = s.ks[e] + a1;
+          s.dY[e] = clampd(s.ky[e] + a2, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+        }
+      }
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0;
+        for (int j = 0; j < n; ++j) a += Ku[i * n + j] * dx[j];
+        du[i] = ku[i] + a;
+      }
+      for (int i = 0; i < n; ++i) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) a1 += s.A[(size_t)t * n * n + i * n + j] * dx[j];
+        for (int j = 0; j < m; ++j) a2 += s.B[(size_t)t * n * m + i * m + j] * du[j];
+        dxn[i] = (a1 + a2) + 0.0;
+      }
+      for (int i = 0; i < n; ++i) dx[i] = dxn[i];
+    }
+  }
+  s.inf_pr = inf_pr;
+  s.inf_du = inf_du;
+  s.inf_comp = inf_comp;
+  s.step_norm = step_norm;
+  return true;
 }
 
 /* IPDDPSolver::backwardPass (:960-1569), branches 1 and 3 */
@@ -1387,6 +1823,7 @@ bool ip_backward(IpState &s) {
       for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * (2.0 * p->Qf[i * n + j] + 2.0 * p->Qf[j * n + i]); /* :990 */
   }
   s.dV[0] = s.dV[1] = 0.0;
+  if (s.teq) return ip_backward_teq(s, Vx, Vxx); /* :1120-1353; dV_ stays zero on this branch */
   double inf_du = 0.0, inf_pr = 0.0, inf_comp = 0.0, step_norm = 0.0;
   std::vector<double> Gx((size_t)std::max(d, 1) * n), Gu((size_t)std::max(d, 1) * m);
   double Qx[MAXN], Qu[MAXM], Qxx[MAXN * MAXN], Qux[MAXM * MAXN], Quu[MAXM * MAXM], Qr[MAXM * MAXM];
@@ -1628,7 +2065,7 @@ struct IpTrial {
    * in exact arithmetic, so the reference's own decision is then made by roundoff; tests use the smallest margin of a
    * solve to tell roundoff-decided instances from robust ones. */
   double margin = 0;
-  std::vector<double> X, U, Y, S, G;
+  std::vector<double> X, U, Y, S, G, lamT;
 };
 
 /* IPDDPSolver::forwardPass (:1571-1876) */
@@ -1720,15 +2157,25 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
     if (d) eval_constraints(p, s.cs, s.nc, &r.X[(size_t)t * n], &r.U[(size_t)t * m], &r.G[(size_t)t * d]);
   }
   cost_new += terminal_cost(p, &r.X[(size_t)N * n], s.xref);
-  const double phi_new = ip_merit(s, r.S.data(), cost_new);
-  const double theta_new = ip_theta(s, r.G.data(), r.S.data());
+  double hTn[MAXN];
+  r.lamT = s.lamT;
+  if (s.teq) { /* :1716-1723, :1756-1760 */
+    for (int i = 0; i < n; ++i) {
+      r.lamT[i] = s.lamT[i] + alpha_pr * s.dlamT[i];
+      if (!std::isfinite(r.lamT[i])) return;
+    }
+    ip_terminal_residual(s, r.X.data(), hTn);
+  }
+  const double *hn = s.teq ? hTn : nullptr;
+  const double phi_new = ip_merit(s, r.S.data(), cost_new, s.teq ? r.lamT.data() : nullptr, hn);
+  const double theta_new = ip_theta(s, r.G.data(), r.S.data(), hn);
   double ipn = 0.0, icn = 0.0;
-  ip_primal_comp(s, r.G.data(), r.S.data(), r.Y.data(), s.mu, &ipn, &icn);
+  ip_primal_comp(s, r.G.data(), r.S.data(), r.Y.data(), s.mu, &ipn, &icn, hn);
   if (!std::isfinite(phi_new) || !std::isfinite(theta_new) || !std::isfinite(ipn) || !std::isfinite(icn)) return;
   bool accept = false;
   double acc_margin = 1.0;
   auto rm = [](double a, double b) { return std::fabs(a - b) / std::max(std::max(std::fabs(a), std::fabs(b)), 1e-300); };
-  if (s.nc == 0) { /* :1787-1794: hard-coded 1e-6 */
+  if (s.nc == 0 && !s.teq) { /* :1785-1794: hard-coded 1e-6 */
     const double dJ = s.cost - cost_new;
     const double expected = -alpha_pr * (s.dV[0] + 0.5 * alpha_pr * s.dV[1]);
     const double ratio = expected > 0.0 ? dJ / expected : std::copysign(1.0, dJ);
@@ -1795,16 +2242,20 @@ void ip_update_barrier(IpState &s) { /* updateBarrierParameters(context, true) (
       s.mu = std::max(s.io->mu_min_value, std::min(linear, superlinear));
     }
   }
-  const double filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data()), 1e-8);
+  double hT[MAXN];
+  if (s.teq) ip_terminal_residual(s, s.X.data(), hT);
+  const double *h = s.teq ? hT : nullptr;
+  const double filter_theta = std::max(ip_theta(s, s.G.data(), s.S.data(), h), 1e-8);
   const bool reset_filter = (s.mu < mu_old) && (s.mu > 0.0);
   if (reset_filter) {
     s.filter.clear();
+    if (s.teq) accept_filter_entry(s.filter, s.phi, filter_theta); /* :2633-2636 */
   } else {
     accept_filter_entry(s.filter, s.phi, filter_theta);
     if ((int)s.filter.size() > s.io->max_filter_size) prune_filter(s.filter);
   }
-  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp);
-  s.merit = ip_merit(s, s.S.data(), s.cost);
+  ip_primal_comp(s, s.G.data(), s.S.data(), s.Y.data(), s.mu, &s.inf_pr, &s.inf_comp, h);
+  s.merit = ip_merit(s, s.S.data(), s.cost, s.teq ? s.lamT.data() : nullptr, h);
   s.phi = s.merit;
   s.filter_theta = filter_theta;
   s.theta = std::max(filter_theta, std::max(s.io->theta_0_floor, 1e-8));
@@ -1880,7 +2331,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
       /* applyForwardPassResult (:1878-1951) */
       s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
       s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
-      s.Y = trial.Y; s.S = trial.S; s.G = trial.G;
+      s.Y = trial.Y; s.S = trial.S; s.G = trial.G; s.lamT = trial.lamT;
       s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
       s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
       ip_update_barrier(s);
@@ -1920,6 +2371,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
       }
     } else { /* handleForwardPassFailure (:2037-2082) */
       s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+      if (!no_barrier && s.teq) s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value); /* :2047-2051 */
       if (s.reg >= o->reg_max_value) {
         const double base = std::sqrt(std::max(o->acceptable_tolerance, o->tolerance));
         const double at = no_barrier ? base : std::max(base, io->barrier_tol_mult * s.mu);
@@ -2116,6 +2568,9 @@ void oracle_ipddp_default_options(oracle_ipddp_options *io) { /* options.hpp:75-
   io->theta_norm_l2 = 0;
   io->max_filter_size = 5;
   io->barrier_strategy = ORACLE_BARRIER_ADAPTIVE;
+  io->jacobian_regularization_value = 1e-8;
+  io->jacobian_regularization_exponent = 0.25;
+  io->terminal_equality = 0;
 }
 
 int oracle_total_dual_dim(const oracle_problem *p, const oracle_constraint *cs, int nc) { return total_dual_dim(p, cs, nc); }
@@ -2179,13 +2634,14 @@ void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const 
     if (fp) {
       s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
       s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
-      s.Y = trial.Y; s.S = trial.S; s.G = trial.G;
+      s.Y = trial.Y; s.S = trial.S; s.G = trial.G; s.lamT = trial.lamT;
       s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
       s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
       ip_update_barrier(s);
       s.reg = std::max(s.reg / o->reg_update_factor, o->reg_min_value);
     } else {
       s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+      if (s.nc != 0 && s.teq) s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
     }
   }
   auto cp = [](double *dst, const std::vector<double> &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(double) * v.size()); };

@@ -193,10 +193,12 @@ typedef struct {
   double violation_acceptance_threshold; /* 1e-6 */
   double max_violation_threshold;        /* 1e4 */
   double min_violation_for_armijo_check; /* 1e-7 */
+  double jacobian_regularization_value;    /* ipddp 1e-8  (terminal-equality reduced system, options.hpp:181-184) */
+  double jacobian_regularization_exponent; /* 0.25 */
   int theta_norm_l2;                     /* 0 = "l1" */
   int max_filter_size;                   /* 5 */
   int barrier_strategy;                  /* ADAPTIVE */
-  int reserved;
+  int terminal_equality;                 /* 1: addTerminalConstraint(TerminalEqualityConstraint(reference state)) */
 } oracle_ipddp_options;
 
 typedef struct {

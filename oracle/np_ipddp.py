@@ -10,7 +10,9 @@ src/cddp_core/ipddp_solver.cpp @ f71fa80, with different numerical routes:
   * barrier merit / theta: summed constraint-major over dictionaries of trajectories, as the reference's std::map code
     does (:2778-2880); the C++ oracle does the same, the CUDA path sums time-major.
 
-Scope: cold start, use_ilqr = true, path inequality constraints (control/state box, ball, linear), no terminal constraints.
+Scope: cold start, use_ilqr = true, path inequality constraints (control/state box, ball, linear), optional
+TerminalEqualityConstraint on the reference state (ipddp_solver.cpp:1120-1353, :484-639; singular values by numpy.linalg.svd,
+the reduced systems by numpy.linalg.solve).
 PARITY STATUS: "parity unpinned" — the reference binary cannot be built in this image.
 """
 from __future__ import annotations
@@ -28,6 +30,7 @@ IP_DEFAULTS = dict(  # options.hpp:75-104, :148-186
     mu_kappa_epsilon=10.0, theta_0_floor=1.0, mu_initial=1.0, mu_min_value=1e-10, mu_update_factor=0.5, mu_update_power=1.2,
     min_fraction_to_boundary=0.99, merit_acceptance_threshold=1e-6, violation_acceptance_threshold=1e-6,
     max_violation_threshold=1e4, min_violation_for_armijo_check=1e-7, theta_norm_l2=0, max_filter_size=5, barrier_strategy=0,
+    jacobian_regularization_value=1e-8, jacobian_regularization_exponent=0.25, terminal_equality=0,
 )
 NAMES = {"control_box": "ControlConstraint", "state_box": "StateConstraint", "ball": "BallConstraint", "linear": "LinearConstraint"}
 
@@ -98,7 +101,9 @@ def _setup(spec, opts, ipopts, constraints, x0, xref, U0):
     s.X[0] = s.x0
     for t in range(N):
         s.X[t + 1] = P.step(s.X[t], s.U[t])
-    s.mu = max(s.o["tolerance"] / 10.0, s.io["mu_min_value"]) if not s.cons else s.io["mu_initial"]
+    s.teq = bool(s.io["terminal_equality"])
+    s.lamT, s.dlamT = np.zeros(P.n), np.zeros(P.n)
+    s.mu = max(s.o["tolerance"] / 10.0, s.io["mu_min_value"]) if (not s.cons and not s.teq) else s.io["mu_initial"]
     s.reg, s.step_norm, s.alpha_pr, s.alpha_du = s.o["reg_initial_value"], 0.0, 1.0, 1.0
     s.G = [np.array([c.g(s.X[t], s.U[t]) for t in range(N)]) for c in s.cons]
     s.S = [np.maximum(s.io["slack_var_init_scale"], -g + K_SLACK_OFFSET) for g in s.G]  # :2447-2466
@@ -110,39 +115,52 @@ def _setup(spec, opts, ipopts, constraints, x0, xref, U0):
     return s
 
 
-def _theta(s, G, S):  # computeTheta :2778-2848
+def _theta(s, G, S, hT=None):  # computeTheta :2778-2848
     total = mx = 0.0
     for g, sl in zip(G, S):
         for t in range(len(g)):
             r = g[t] + sl[t]
             total += float(r @ r) if s.io["theta_norm_l2"] else float(np.abs(r).sum())
             mx = max(mx, float(np.abs(r).max()))
+    if hT is not None:
+        total += float(hT @ hT) if s.io["theta_norm_l2"] else float(np.abs(hT).sum())
+        mx = max(mx, float(np.abs(hT).max()))
     th = math.sqrt(total) if s.io["theta_norm_l2"] else total
     return max(th, mx)
 
 
-def _merit(s, S, cost, mu=None):  # computeBarrierMerit :2850-2880
-    mu = s.mu if mu is None else mu
+def _merit(s, S, cost, lamT=None, hT=None):  # computeBarrierMerit :2850-2880
     merit = cost
     for sl in S:
         for t in range(len(sl)):
-            merit -= mu * float(np.log(np.maximum(sl[t], EPS_SLACK)).sum())
+            merit -= s.mu * float(np.log(np.maximum(sl[t], EPS_SLACK)).sum())
+    if lamT is not None and hT is not None:
+        merit += float(lamT @ hT)
     return merit
 
 
-def _primal_comp(s, G, S, Y, mu):  # :2882-2937
+def _primal_comp(s, G, S, Y, mu, hT=None):  # :2882-2937
     ip = ic = 0.0
     for g, sl, y in zip(G, S, Y):
         ip = max(ip, float(np.abs(g + sl).max()))
         ic = max(ic, float(np.abs(y * sl - mu).max()))
+    if hT is not None:
+        ip = max(ip, float(np.abs(hT).max()))
     return ip, ic
 
 
+def _hT(s, X):
+    return (X[s.P.N] - s.xref) if s.teq else None
+
+
 def _reset_filter(s):  # resetBarrierFilter :2484-2517
-    s.inf_pr, s.inf_comp = _primal_comp(s, s.G, s.S, s.Y, s.mu)
-    s.merit = s.phi = _merit(s, s.S, s.cost)
-    s.filter_theta = max(_theta(s, s.G, s.S), 1e-8)
+    h = _hT(s, s.X)
+    s.inf_pr, s.inf_comp = _primal_comp(s, s.G, s.S, s.Y, s.mu, h)
+    s.merit = s.phi = _merit(s, s.S, s.cost, s.lamT if s.teq else None, h)
+    s.filter_theta = max(_theta(s, s.G, s.S, h), 1e-8)
     s.filter = []
+    if s.teq:
+        _accept_filter(s.filter, s.phi, s.filter_theta)
 
 
 def _backward(s):
@@ -158,6 +176,8 @@ def _backward(s):
     Vxx = 2.0 * P.Qf
     Vxx = 0.5 * (Vxx + Vxx.T)
     d = sum(c.dim for c in s.cons)
+    if s.teq:
+        return _backward_teq(s, Vx, Vxx, d)
     s.ku, s.Ku = np.zeros((N, m)), np.zeros((N, m, n))
     s.ky, s.Ky, s.ks, s.Ks = np.zeros((N, d)), np.zeros((N, d, n)), np.zeros((N, d)), np.zeros((N, d, n))
     dV = np.zeros(2)
@@ -230,6 +250,124 @@ def _backward(s):
     return True
 
 
+def _seq_lqr(Q, q, R, r, M, A, B):
+    """solveSequentialLQR (:411-482), d = 0."""
+    N = len(R)
+    n, m = Q[0].shape[0], R[0].shape[0]
+    K, k = np.zeros((N, m, n)), np.zeros((N, m))
+    P, p = [None] * (N + 1), [None] * (N + 1)
+    P[N], p[N] = 0.5 * (Q[N] + Q[N].T), q[N]
+    for t in range(N - 1, -1, -1):
+        BtP = B[t].T @ P[t + 1]
+        Q_uu = 0.5 * (R[t] + BtP @ B[t] + R[t].T + B[t].T @ P[t + 1].T @ B[t])
+        Q_ux = BtP @ A[t] + M[t].T
+        Q_x = q[t] + A[t].T @ p[t + 1]
+        Q_u = r[t] + B[t].T @ p[t + 1]
+        K[t] = -np.linalg.solve(Q_uu, Q_ux)
+        k[t] = -np.linalg.solve(Q_uu, Q_u)
+        Pt = Q[t] + A[t].T @ P[t + 1] @ A[t] + Q_ux.T @ K[t] + K[t].T @ Q_ux + K[t].T @ Q_uu @ K[t]
+        P[t] = 0.5 * (Pt + Pt.T)
+        p[t] = Q_x + Q_ux.T @ k[t] + K[t].T @ Q_u + K[t].T @ Q_uu @ k[t]
+    return K, k, P, np.array(p)
+
+
+def _backward_teq(s, Vx, Vxx, d):
+    """Terminal-equality branch (:1120-1353) + solveTerminalEqualityLQR (:484-639); H_T = I, b_T = -h_T."""
+    P, N, n, m = s.P, s.P.N, s.P.n, s.P.m
+    A, B = s.A, s.B
+    hT = s.X[N] - s.xref
+    inf_pr, inf_comp = float(np.abs(hT).max()), 0.0
+    Q, q, R, r, M = [None] * (N + 1), [None] * (N + 1), [None] * N, [None] * N, [None] * N
+    Q[N], q[N] = Vxx, Vx
+    models = []
+    for t in range(N):
+        x, u = s.X[t], s.U[t]
+        Q[t] = 0.5 * (2.0 * P.Qs + (2.0 * P.Qs).T)
+        q[t] = 2.0 * P.Qs @ (x - s.xref)
+        R[t] = 0.5 * (2.0 * P.Rs + (2.0 * P.Rs).T)
+        r[t] = 2.0 * P.Rs @ u
+        M[t] = np.zeros((n, m))
+        if s.cons:
+            y = np.concatenate([Y[t] for Y in s.Y])
+            sl = np.concatenate([S[t] for S in s.S])
+            g = np.concatenate([G[t] for G in s.G])
+            jac = [c.jac(x, u) for c in s.cons]
+            Q_yx, Q_yu = np.vstack([j[0] for j in jac]), np.vstack([j[1] for j in jac])
+            s_safe = np.maximum(sl, max(s.mu * 1e-3, EPS_SLACK))
+            YSinv = np.diag(_clip(y / s_safe, 0.0, MAX_RATIO))
+            primal, comp = g + sl, y * sl - s.mu
+            rhat = y * primal - comp
+            Sir = _clip(rhat / s_safe, -MAX_RATIO, MAX_RATIO)
+            q[t] = q[t] + Q_yx.T @ (y + Sir)
+            r[t] = r[t] + Q_yu.T @ (y + Sir)
+            Q[t] = Q[t] + Q_yx.T @ YSinv @ Q_yx
+            M[t] = M[t] + (Q_yu.T @ YSinv @ Q_yx).T
+            R[t] = R[t] + Q_yu.T @ YSinv @ Q_yu
+            Q[t], R[t] = 0.5 * (Q[t] + Q[t].T), 0.5 * (R[t] + R[t].T)
+            models.append((y, s_safe, Q_yx, Q_yu, YSinv, primal, rhat))
+            inf_pr = max(inf_pr, float(np.abs(primal).max()))
+            inf_comp = max(inf_comp, float(np.abs(comp).max()))
+        R[t] = R[t] + s.reg * np.eye(m)
+    qb = [v.copy() for v in q]
+    qb[N] = qb[N] + s.lamT
+    var, xT = [], []
+    for i in range(n + 1):
+        qv = [v.copy() for v in qb]
+        if i > 0:
+            qv[N][i - 1] += 1.0
+        K, k, Pm, pm = _seq_lqr(Q, qv, R, r, M, A, B)
+        dx = np.zeros(n)
+        for t in range(N):
+            dx = A[t] @ dx + B[t] @ (k[t] + K[t] @ dx)
+        var.append((K, k, pm))
+        xT.append(dx)
+    S_mat = np.column_stack([xT[i + 1] - xT[0] for i in range(n)])
+    rhs = -hT - xT[0]
+    AtA, Atb = S_mat.T @ S_mat, S_mat.T @ rhs
+    trace_term = AtA.trace() / max(n, 1) if AtA.trace() > 1.0 else 1.0
+    base_floor = max(1e-10, s.io["jacobian_regularization_value"] * max(s.mu, 0.0) ** s.io["jacobian_regularization_exponent"])
+    reg = max(base_floor, 1e-6 * trace_term)
+    sv = np.linalg.svd(S_mat, compute_uv=False)
+    reg_base = max(reg, max(1e-8 * sv.max() - sv.min(), 0.0))
+    cap = 100.0 * (1.0 + np.linalg.norm(rhs))
+    best, best_res, found = np.zeros(n), math.inf, False
+    for scale in (1.0, 10.0, 100.0, 1e3, 1e4):
+        lam = np.linalg.solve(AtA + max(reg_base * scale, 1e-12) * np.eye(n), Atb)
+        if not np.isfinite(lam).all():
+            continue
+        ln = np.linalg.norm(lam)
+        if ln > cap:
+            lam = lam * (cap / max(ln, 1e-12))
+        res = np.linalg.norm(S_mat @ lam - rhs)
+        if not found or res < best_res:
+            best, best_res, found = lam, res, True
+    s.Ku, s.ku = var[0][0], var[0][1].copy()
+    pout = var[0][2].copy()
+    for i in range(n):
+        s.ku += best[i] * (var[i + 1][1] - var[0][1])
+        pout += best[i] * (var[i + 1][2] - var[0][2])
+    s.dlamT = best
+    s.inf_du = max(float(np.abs(r[t] + B[t].T @ pout[t + 1]).max()) for t in range(N))
+    s.step_norm = float(np.abs(s.ku).max())
+    s.ky, s.Ky, s.ks, s.Ks = np.zeros((N, d)), np.zeros((N, d, n)), np.zeros((N, d)), np.zeros((N, d, n))
+    s.dS, s.dY = np.zeros((N, d)), np.zeros((N, d))
+    dx = np.zeros(n)
+    for t in range(N):
+        if s.cons:
+            y, s_safe, Q_yx, Q_yu, YSinv, primal, rhat = models[t]
+            temp = Q_yu @ s.ku[t]
+            s.ky[t] = _clip((rhat + y * temp) / s_safe, -MAX_RATIO, MAX_RATIO)
+            s.Ky[t] = _clip(YSinv @ (Q_yx + Q_yu @ s.Ku[t]), -MAX_RATIO, MAX_RATIO)
+            s.ks[t] = -primal - temp
+            s.Ks[t] = -Q_yx - Q_yu @ s.Ku[t]
+            s.dS[t] = s.ks[t] + s.Ks[t] @ dx
+            s.dY[t] = _clip(s.ky[t] + s.Ky[t] @ dx, -MAX_RATIO, MAX_RATIO)
+        dx = A[t] @ dx + B[t] @ (s.ku[t] + s.Ku[t] @ dx)
+    s.inf_pr, s.inf_comp = inf_pr, inf_comp
+    s.dV = np.zeros(2)
+    return True
+
+
 def _max_steps(s):  # computeMaxStepSizes :2939-2988
     if not s.cons:
         return 1.0, 1.0
@@ -274,12 +412,14 @@ def _forward(s, alpha):
             return None
     cost = P.trajectory_cost(X, U, s.xref)
     Gn = [np.array([c.g(X[t], U[t]) for t in range(N)]) for c in s.cons]
-    phi = _merit(s, Sn, cost)
-    theta = _theta(s, Gn, Sn)
-    ip, ic = _primal_comp(s, Gn, Sn, Yn, s.mu)
+    lam_new = s.lamT + a_pr * s.dlamT if s.teq else s.lamT
+    h_new = _hT(s, X)
+    phi = _merit(s, Sn, cost, lam_new if s.teq else None, h_new)
+    theta = _theta(s, Gn, Sn, h_new)
+    ip, ic = _primal_comp(s, Gn, Sn, Yn, s.mu, h_new)
     if not all(map(math.isfinite, (phi, theta, ip, ic))):
         return None
-    if not s.cons:  # :1787-1794
+    if not s.cons and not s.teq:  # :1785-1794
         dJ = s.cost - cost
         expected = -a_pr * (s.dV[0] + 0.5 * a_pr * s.dV[1])
         ratio = dJ / expected if expected > 0.0 else math.copysign(1.0, dJ)
@@ -298,7 +438,8 @@ def _forward(s, alpha):
                   theta < (1 - io["violation_acceptance_threshold"]) * cv_old)
     if not ok:
         return None
-    return dict(X=X, U=U, S=Sn, Y=Yn, G=Gn, cost=cost, merit=phi, theta=theta, inf_pr=ip, inf_comp=ic, a_pr=a_pr, a_du=a_du)
+    return dict(X=X, U=U, S=Sn, Y=Yn, G=Gn, cost=cost, merit=phi, theta=theta, inf_pr=ip, inf_comp=ic, a_pr=a_pr, a_du=a_du,
+                lamT=lam_new)
 
 
 def _accept_filter(f, merit, theta):  # interior_point_utils.cpp:81-97
@@ -322,7 +463,7 @@ def _apply(s, r):
     """applyForwardPassResult (:1878-1951) + updateBarrierParameters(true) (:2548-2660)."""
     s.X, s.U, s.cost, s.merit = r["X"], r["U"], r["cost"], r["merit"]
     s.alpha_pr, s.alpha_du = r["a_pr"], r["a_du"]
-    s.S, s.Y, s.G = r["S"], r["Y"], r["G"]
+    s.S, s.Y, s.G, s.lamT = r["S"], r["Y"], r["G"], r["lamT"]
     s.inf_pr, s.inf_comp, s.phi, s.filter_theta = r["inf_pr"], r["inf_comp"], r["merit"], r["theta"]
     io, mu_old = s.io, s.mu
     if s.cons:
@@ -343,15 +484,18 @@ def _apply(s, r):
             kkt = max(s.inf_pr, s.inf_du * io["barrier_update_dual_weight"], s.inf_comp)
             if kkt <= io["mu_kappa_epsilon"] * s.mu:
                 s.mu = max(io["mu_min_value"], min(io["mu_update_factor"] * s.mu, s.mu ** io["mu_update_power"]))
-    filter_theta = max(_theta(s, s.G, s.S), 1e-8)
+    h = _hT(s, s.X)
+    filter_theta = max(_theta(s, s.G, s.S, h), 1e-8)
     if s.mu < mu_old and s.mu > 0.0:
         s.filter = []
+        if s.teq:
+            _accept_filter(s.filter, s.phi, filter_theta)
     else:
         _accept_filter(s.filter, s.phi, filter_theta)
         if len(s.filter) > io["max_filter_size"]:
             _prune(s.filter)
-    s.inf_pr, s.inf_comp = _primal_comp(s, s.G, s.S, s.Y, s.mu)
-    s.merit = s.phi = _merit(s, s.S, s.cost)
+    s.inf_pr, s.inf_comp = _primal_comp(s, s.G, s.S, s.Y, s.mu, h)
+    s.merit = s.phi = _merit(s, s.S, s.cost, s.lamT if s.teq else None, h)
     s.filter_theta = filter_theta
 
 
@@ -360,7 +504,8 @@ def _flat(s):
     apm, adm = _max_steps(s)
     return dict(X=s.X, U=s.U, Y=cat(s.Y), S=cat(s.S), G=cat(s.G), ku=s.ku, Ku=s.Ku, ky=s.ky, Ky=s.Ky, ks=s.ks, Ks=s.Ks,
                 mu=s.mu, cost=s.cost, merit=s.merit, inf_pr=s.inf_pr, inf_du=s.inf_du, inf_comp=s.inf_comp,
-                step_norm=s.step_norm, reg=s.reg, dV0=s.dV[0], dV1=s.dV[1], alpha_pr_max=apm, alpha_du_max=adm)
+                step_norm=s.step_norm, reg=s.reg, dV0=s.dV[0], dV1=s.dV[1], alpha_pr_max=apm, alpha_du_max=adm,
+                lamT=s.lamT, dlamT=s.dlamT)
 
 
 def probe(spec, opts, ipopts, constraints, x0, xref, U0, iters):
@@ -377,6 +522,8 @@ def probe(spec, opts, ipopts, constraints, x0, xref, U0, iters):
             s.reg = max(s.reg / s.o["reg_update_factor"], s.o["reg_min_value"])
         else:
             s.reg = min(s.reg * s.o["reg_update_factor"], s.o["reg_max_value"])
+            if s.cons and s.teq:
+                s.reg = min(s.reg * s.o["reg_update_factor"], s.o["reg_max_value"])
     return _flat(s)
 
 
@@ -437,6 +584,8 @@ def solve(spec, opts, ipopts, constraints, x0, xref, U0):
                         break
         else:  # handleForwardPassFailure :2037-2082
             s.reg = min(s.reg * o["reg_update_factor"], o["reg_max_value"])
+            if not no_barrier and s.teq:
+                s.reg = min(s.reg * o["reg_update_factor"], o["reg_max_value"])
             if s.reg >= o["reg_max_value"]:
                 base = math.sqrt(max(o["acceptable_tolerance"], o["tolerance"]))
                 at = base if no_barrier else max(base, io["barrier_tol_mult"] * s.mu)

@@ -300,8 +300,9 @@ class IpddpOptions(C.Structure):
         "dual_var_init_scale", "slack_var_init_scale", "barrier_tol_mult", "barrier_update_dual_weight",
         "mu_kappa_epsilon", "theta_0_floor", "mu_initial", "mu_min_value", "mu_update_factor", "mu_update_power",
         "min_fraction_to_boundary", "merit_acceptance_threshold", "violation_acceptance_threshold",
-        "max_violation_threshold", "min_violation_for_armijo_check")] + [
-        ("theta_norm_l2", C.c_int), ("max_filter_size", C.c_int), ("barrier_strategy", C.c_int), ("reserved", C.c_int)]
+        "max_violation_threshold", "min_violation_for_armijo_check", "jacobian_regularization_value",
+        "jacobian_regularization_exponent")] + [
+        ("theta_norm_l2", C.c_int), ("max_filter_size", C.c_int), ("barrier_strategy", C.c_int), ("terminal_equality", C.c_int)]
 
 
 class IpddpResult(C.Structure):

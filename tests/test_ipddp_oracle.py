@@ -10,7 +10,8 @@ import pytest
 
 from conftest import rel_err
 
-IPDDP_CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "cartpole_ipddp", "quadrotor_ipddp"]
+IPDDP_CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "cartpole_ipddp", "quadrotor_ipddp",
+                 "unicycle_obstacle_teq", "unicycle_teq", "cartpole_teq"]
 
 
 def _prob(ob, n, m, model="unicycle"):
@@ -90,10 +91,12 @@ def test_solution_properties(ob, problems, name):
     controls, the reported cost is the cost of the returned trajectory, and the barrier parameter never grows."""
     B = 3
     cfg = problems.make_config(name, batch=B)
-    P, oo, oi = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"]), ob.make_ipddp_options()
+    P, oo, oi = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"]), ob.make_ipddp_options(**cfg.get("ipddp_options", {}))
     cs = ob.ConstraintSet(cfg["constraints"])
     for b in range(B):
         r = ob.ipddp_solve(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], history=True)
+        if cfg.get("ipddp_options", {}).get("terminal_equality") and r["status"] in (1, 2):
+            assert np.abs(r["X"][-1] - cfg["xref"][b]).max() < 1e-3  # TerminalEqualityConstraint: x_N = goal
         X, U = r["X"], r["U"]
         for t in range(0, P.N, 7):
             assert rel_err(ob.discrete_dynamics(P, X[t], U[t], t * cfg["spec"]["dt"]), X[t + 1]) < 1e-12
@@ -117,19 +120,20 @@ def test_oracle_vs_numpy_restatement(ob, problems, name):
     on instances whose line-search decisions are not roundoff-decided."""
     np_ipddp = pytest.importorskip("np_ipddp")
     B = 2
-    cfg = problems.make_config(name, batch=B, horizon=40 if name != "unicycle_obstacle" else 60)
-    P, oo, oi = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"]), ob.make_ipddp_options()
+    cfg = problems.make_config(name, batch=B, horizon=40 if not name.startswith("unicycle_obstacle") else 60)
+    ipo = cfg.get("ipddp_options", {})
+    P, oo, oi = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"]), ob.make_ipddp_options(**ipo)
     cs = ob.ConstraintSet(cfg["constraints"])
     for b in range(B):
         for iters in (0, 2):
             r = ob.ipddp_probe(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], iters)
-            q = np_ipddp.probe(cfg["spec"], cfg["options"], {}, cs.constraints, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], iters)
+            q = np_ipddp.probe(cfg["spec"], cfg["options"], ipo, cs.constraints, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], iters)
             for key in ("X", "U", "Y", "S", "G", "ku", "Ku", "ky", "Ky", "ks", "Ks"):
                 assert rel_err(r[key], q[key]) < 1e-7, (name, b, iters, key)
             for key in ("mu", "cost", "merit", "inf_du", "step_norm", "dV0", "dV1", "alpha_pr_max", "alpha_du_max"):
                 assert abs(r[key] - q[key]) <= 1e-7 * max(abs(q[key]), 1e-12), (name, b, iters, key, r[key], q[key])
         r = ob.ipddp_solve(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b])
         if r["decision_margin"] > 1e-6:
-            q = np_ipddp.solve(cfg["spec"], cfg["options"], {}, cs.constraints, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b])
+            q = np_ipddp.solve(cfg["spec"], cfg["options"], ipo, cs.constraints, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b])
             assert q["iterations"] == r["iterations"] and q["status"] == r["status"]
             assert abs(q["cost"] - r["cost"]) <= 1e-6 * abs(r["cost"])
