@@ -163,17 +163,18 @@ def run_reference(args, rank, world):
 
 
 def measure_ipddp(cddp, problems, device, with_cpu):
-    """Secondary workload (not the bench line): BASELINE config #4's path-constraint part — unicycle obstacle avoidance,
-    IPDDP, n=3 m=2 N=200, batch 2048 — device-resident throughput and per-kernel CUDA-event times, with the CPU oracle
-    beside it.  Convergence exits disabled (tolerance 0) for the timed iterations."""
+    """Secondary workload (not the bench line): BASELINE config #4 — unicycle obstacle avoidance, IPDDP, path-inequality
+    (control box + ball) + terminal-equality, n=3 m=2 N=200, batch 2048 — device-resident throughput and per-kernel
+    CUDA-event times, with the CPU oracle beside it.  Convergence exits disabled (tolerance 0) for the timed iterations."""
     import torch
     B, K, W = 2048, 20, 3
-    cfg = problems.make_config("unicycle_obstacle", batch=B)
+    cfg = problems.make_config("unicycle_obstacle_teq", batch=B)
     opts = cddp.default_options(**dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
-    s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(), cfg["constraints"], B, device=device)
+    s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(**cfg["ipddp_options"]), cfg["constraints"], B, device=device)
     s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
     s.initialize()
     s.iterate(W)
+    it0 = int(s.get_scalars()["iterations"].sum())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -184,6 +185,7 @@ def measure_ipddp(cddp, problems, device, with_cpu):
     ms = e0.elapsed_time(e1)
     sc = s.get_scalars()
     running = int((sc["status"] == 0).sum())
+    done = int(sc["iterations"].sum()) - it0  # instance-iterations actually performed in the timed region
     s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
     s.initialize()
     s.iterate(W)
@@ -192,7 +194,7 @@ def measure_ipddp(cddp, problems, device, with_cpu):
     s.iterate(K)
     t = s.get_timing()
     out = {"workload": cfg["notes"], "solver": "IPDDP", "batch": B, "horizon": cfg["spec"]["horizon"], "dual_dim": s.d,
-           "value": running * K / (ms * 1e-3) if running == B else B * K / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / K,
+           "value": done / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / K, "instance_iterations_timed": done,
            "instances_running_all_iterations": running,
            "kernel_ms_per_iteration": {"linearize": t.linearize_ms / max(t.linearize_launches, 1),
                                        "backward": t.backward_ms / max(t.backward_launches, 1),
@@ -202,11 +204,11 @@ def measure_ipddp(cddp, problems, device, with_cpu):
         import oracle_binding as ob
         threads = ob.hardware_threads()
         sample = 2048
-        ccfg = problems.make_config("unicycle_obstacle", batch=sample)
+        ccfg = problems.make_config("unicycle_obstacle_teq", batch=sample)
         P = ob.OracleProblem(ccfg["spec"])
         oo = ob.make_options(**dict(ccfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
         t0 = time.perf_counter()
-        r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(), ob.ConstraintSet(ccfg["constraints"]), ccfg["x0"], ccfg["xref"],
+        r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(**ccfg["ipddp_options"]), ob.ConstraintSet(ccfg["constraints"]), ccfg["x0"], ccfg["xref"],
                                  ccfg["U0"], None, nthreads=threads)
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
@@ -433,9 +435,9 @@ def main():
     other = None
     if rank == 0 and world == 1 and args.config == "quadrotor" and not args.no_cpu_baseline:
         try:
-            other = {"ipddp_unicycle_obstacle": measure_ipddp(cddp, problems, local_rank, True)}
+            other = {"ipddp_config4_unicycle_obstacle_teq": measure_ipddp(cddp, problems, local_rank, True)}
         except Exception as e:  # secondary measurement: never take the bench line down with it
-            other = {"ipddp_unicycle_obstacle": {"error": repr(e)}}
+            other = {"ipddp_config4_unicycle_obstacle_teq": {"error": repr(e)}}
 
     if rank == 0:
         line = {

@@ -86,6 +86,8 @@ struct IPDDPAlgorithmOptions {  // options.hpp:148-186 (the members the cold-sta
   int max_filter_size = 5;
   double theta_0_floor = 1.0;
   bool warmstart_repair = false;
+  double jacobian_regularization_value = 1e-8;
+  double jacobian_regularization_exponent = 0.25;
   SolverSpecificBarrierOptions barrier;
 };
 struct CDDPOptions {  // options.hpp:208-251

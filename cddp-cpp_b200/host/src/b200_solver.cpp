@@ -261,8 +261,22 @@ void describe_ipddp(CDDP &ctx, IpShared &s) {
   const CDDPOptions &o = ctx.getOptions();
   if (o.warm_start) throw std::runtime_error("B200 IPDDP: options.warm_start is not supported by the device path");
   if (!o.use_ilqr) throw std::runtime_error("B200 IPDDP: use_ilqr = false (second-order dynamics terms) is not supported by the device path");
-  if (!ctx.getTerminalConstraintSet().empty())
-    throw std::runtime_error("B200 IPDDP: terminal constraints are not supported by the device path");
+  // terminal constraints: one TerminalEqualityConstraint whose target is the objective's reference state runs on the device
+  // (terminal-equality branch, ipddp_solver.cpp:1120-1353); anything else is a setup error
+  bool terminal_equality = false;
+  for (const auto &kv : ctx.getTerminalConstraintSet()) {
+    const auto *te = dynamic_cast<const TerminalEqualityConstraint *>(kv.second.get());
+    if (!te || terminal_equality)
+      throw std::runtime_error("B200 IPDDP: terminal constraint '" + kv.first + "' is not supported by the device path (supported: "
+                               "a single TerminalEqualityConstraint on the reference state)");
+    const Eigen::VectorXd ref = ctx.getObjective().getReferenceState();
+    if (te->getTargetState().size() != ref.size())
+      throw std::runtime_error("B200 IPDDP: TerminalEqualityConstraint target has the wrong dimension");
+    for (long i = 0; i < ref.size(); ++i)
+      if (te->getTargetState()[i] != ref[i])
+        throw std::runtime_error("B200 IPDDP: the device path supports a TerminalEqualityConstraint only on the objective's reference state");
+    terminal_equality = true;
+  }
   if (o.ipddp.check_state_stationarity || o.ipddp.warmstart_repair)
     throw std::runtime_error("B200 IPDDP: check_state_stationarity / warmstart_repair are not supported by the device path");
   cddp_b200_ipddp_default_options(&s.io);
@@ -283,6 +297,9 @@ void describe_ipddp(CDDP &ctx, IpShared &s) {
   s.io.min_violation_for_armijo_check = o.filter.min_violation_for_armijo_check;
   s.io.theta_norm_l2 = o.ipddp.theta_norm == "l2" ? 1 : 0;
   s.io.max_filter_size = o.ipddp.max_filter_size;
+  s.io.jacobian_regularization_value = o.ipddp.jacobian_regularization_value;
+  s.io.jacobian_regularization_exponent = o.ipddp.jacobian_regularization_exponent;
+  s.io.terminal_equality = terminal_equality ? 1 : 0;
   s.io.barrier_strategy = o.ipddp.barrier.strategy == BarrierStrategy::ADAPTIVE ? CDDP_B200_BARRIER_ADAPTIVE
                           : o.ipddp.barrier.strategy == BarrierStrategy::MONOTONIC ? CDDP_B200_BARRIER_MONOTONIC : CDDP_B200_BARRIER_IPOPT;
   const int n = ctx.getStateDim();

@@ -236,11 +236,35 @@ void SolveUnicycleObstacleIPDDP() {
   CHECK(worst < 1e-6);
   std::printf("  unicycle obstacle IPDDP: %d iterations, %s, J=%.9f, mu=%.3e, min distance %.4f; batch of %d: worst cost rel err vs oracle %.2e\n",
               s0.iterations_completed, s0.status_message.c_str(), s0.final_objective, s0.final_barrier_mu, mind, B, worst);
-  // setup errors: terminal constraints / unsupported constraint classes are exceptions, never a CPU fallback
+  // BASELINE config #4 in full: + TerminalEqualityConstraint(goal) (test_ipddp_solver.cpp:1417-1419 pattern) -> terminal-equality branch
+  {
+    std::vector<Eigen::VectorXd> X((size_t)N + 1, batch[0]->getInitialState()), U((size_t)N, vec({0.0, 0.0}));
+    batch[0]->setInitialTrajectory(X, U);
+    const Eigen::VectorXd goal = batch[0]->getObjective().getReferenceState();
+    batch[0]->addTerminalConstraint("TerminalEqualityConstraint", std::make_unique<TerminalEqualityConstraint>(goal));
+    CDDPSolution st = batch[0]->solve("IPDDP");
+    CHECK(st.status_message == "OptimalSolutionFound" || st.status_message == "AcceptableSolutionFound");
+    double term = 0.0;
+    for (int i = 0; i < 3; ++i) term = std::max(term, std::fabs(st.state_trajectory.back()[i] - goal[i]));
+    CHECK(term < 1e-4);
+    oracle_ipddp_options oit = oi;
+    oit.terminal_equality = 1;
+    std::vector<double> Xo((size_t)(N + 1) * 3), Uo((size_t)N * 2, 0.0), Ko((size_t)N * 6);
+    const double x0a[3] = {0, 0, 0}, xr[3] = {goal[0], goal[1], goal[2]};
+    oracle_ipddp_result res;
+    oracle_ipddp_solve(&p, &oo, &oit, cs, 2, x0a, xr, nullptr, Xo.data(), Uo.data(), Ko.data(), nullptr, nullptr, &res, nullptr);
+    if (res.decision_margin > 1e-9) {
+      CHECK(res.iterations == st.iterations_completed);
+      CHECK(std::fabs(res.final_objective - st.final_objective) <= 1e-6 * std::fabs(res.final_objective));
+    }
+    std::printf("  + terminal equality: %d iterations, %s, J=%.9f (oracle %.9f), |x_N - goal| = %.2e\n", st.iterations_completed,
+                st.status_message.c_str(), st.final_objective, res.final_objective, term);
+  }
+  // setup errors: a terminal equality on another target / unsupported constraint classes are exceptions, never a CPU fallback
   bool threw = false;
-  batch[0]->addTerminalConstraint("TerminalEqualityConstraint", std::make_unique<TerminalEqualityConstraint>(vec({2.0, 2.0, 0.0})));
+  batch[1]->addTerminalConstraint("TerminalEqualityConstraint", std::make_unique<TerminalEqualityConstraint>(vec({9.0, 9.0, 0.0})));
   try {
-    batch[0]->solve("IPDDP");
+    batch[1]->solve("IPDDP");
   } catch (const std::runtime_error &) {
     threw = true;
   }
