@@ -446,9 +446,25 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
     }
   }
   const bool success = active && accept;
-  unsigned ballot = __ballot_sync(0xffffffffu, success);
-  ballot = (ballot >> (grp * LG)) & 0xffffu;
-  const int first = ballot ? (__ffs(ballot) - 1) : -1;
+  int first;
+  if (!c.opt.enable_parallel) {  // sequential rule: the first accepted alpha (cddp_solver_base.cpp:255-263)
+    unsigned ballot = __ballot_sync(0xffffffffu, success);
+    ballot = (ballot >> (grp * LG)) & 0xffffu;
+    first = ballot ? (__ffs(ballot) - 1) : -1;
+  } else {  // enable_parallel: the accepted alpha with the strictly lowest merit, ties to the earlier one (:264-285)
+    double pm = success ? phi_new : pos_inf();
+    int idx = (success && phi_new < pos_inf()) ? al : 64;
+#pragma unroll
+    for (int o = LG / 2; o > 0; o >>= 1) {
+      const double po = __shfl_xor_sync(0xffffffffu, pm, o);
+      const int io = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (po < pm || (po == pm && io < idx)) {
+        pm = po;
+        idx = io;
+      }
+    }
+    first = idx < 64 ? idx : -1;
+  }
   if (alive && al < na) {
     double *ls = ip.ls_stats + ((size_t)b * CDDP_B200_MAX_ALPHAS + al) * 4;
     ls[0] = success ? 1.0 : 0.0;

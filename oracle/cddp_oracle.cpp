@@ -2317,13 +2317,27 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
         break;
       }
     }
-    bool fp = false; /* performForwardPass, sequential (cddp_solver_base.cpp:255-263) */
-    for (int ai = 0; ai < na; ++ai) {
-      ip_forward(s, alphas[ai], trial);
-      min_margin = std::min(min_margin, trial.margin);
-      if (trial.success) {
-        fp = true;
-        break;
+    bool fp = false; /* performForwardPass: sequential = first success (cddp_solver_base.cpp:255-263) */
+    if (!o->enable_parallel) {
+      for (int ai = 0; ai < na; ++ai) {
+        ip_forward(s, alphas[ai], trial);
+        min_margin = std::min(min_margin, trial.margin);
+        if (trial.success) {
+          fp = true;
+          break;
+        }
+      }
+    } else { /* enable_parallel: the success with the strictly lowest merit, scanning in alpha order (:264-285) */
+      IpTrial cand;
+      double best_merit = std::numeric_limits<double>::infinity();
+      for (int ai = 0; ai < na; ++ai) {
+        ip_forward(s, alphas[ai], cand);
+        min_margin = std::min(min_margin, cand.margin);
+        if (cand.success && cand.merit < best_merit) {
+          best_merit = cand.merit;
+          trial = cand;
+          fp = true;
+        }
       }
     }
     if (fp) {

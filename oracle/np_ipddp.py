@@ -547,10 +547,16 @@ def solve(spec, opts, ipopts, constraints, x0, xref, U0):
             status = npo.OPTIMAL
             break
         r = None
-        for a in alphas:  # first success wins, cddp_solver_base.cpp:255-263
-            r = _forward(s, a)
-            if r is not None:
-                break
+        if not o["enable_parallel"]:
+            for a in alphas:  # first success wins, cddp_solver_base.cpp:255-263
+                r = _forward(s, a)
+                if r is not None:
+                    break
+        else:  # lowest merit among the successes, scanning in alpha order (:264-285)
+            for a in alphas:
+                c = _forward(s, a)
+                if c is not None and (r is None or c["merit"] < r["merit"]):
+                    r = c
         if r is not None:
             dJ = s.cost - r["cost"]
             _apply(s, r)

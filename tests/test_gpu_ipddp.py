@@ -165,6 +165,25 @@ def test_full_size_config4_properties(cddp, ob, problems, name):
     assert (np.abs(g2["cost"][robust] - o["cost"][robust]) <= COST_TOL * np.abs(o["cost"][robust])).all()
 
 
+def test_enable_parallel_selects_lowest_merit(cddp, ob, problems):
+    """options.enable_parallel: the accepted alpha with the lowest barrier merit wins (cddp_solver_base.cpp:264-285) instead
+    of the first accepted one — whole solves against the oracle run with the same option."""
+    B = 8
+    cfg = problems.make_config("unicycle_obstacle", batch=B, horizon=80)
+    s, opts = make(cddp, cfg, B, enable_parallel=1, max_iterations=40)
+    P, oo, oi, cs = oracle_of(ob, cfg, opts)
+    s.solve()
+    g = s.get_solution(want_K=False)
+    o = ob.ipddp_solve_batch(P, oo, oi, cs, cfg["x0"], cfg["xref"], cfg["U0"], nthreads=4)
+    robust = robust_mask(ob, P, oo, oi, cs, cfg, o)
+    assert robust.sum() >= 3
+    assert (g["iterations"][robust] == o["iterations"][robust]).all()
+    assert (np.abs(g["cost"][robust] - o["cost"][robust]) <= COST_TOL * np.abs(o["cost"][robust])).all()
+    seq = ob.ipddp_solve_batch(P, ob.make_options(**dict(opts, enable_parallel=0)), oi, cs, cfg["x0"], cfg["xref"], cfg["U0"], nthreads=4)
+    assert (np.abs(seq["cost"] - o["cost"]) > 1e-9 * np.abs(o["cost"])).any(), "the two selection rules must differ somewhere"
+    s.close()
+
+
 def test_errors_and_scope(cddp, problems):
     """Setup errors are error codes (the C++ shim turns them into std::runtime_error): LTI is not supported by the IPDDP
     handle, more than 16 line-search alphas, an unknown constraint kind."""
