@@ -663,8 +663,27 @@ inline double qp_value(const double *x, const double *H, const double *g, int n)
   return 0.5 * a + b;
 }
 
+/* test/profiling instrumentation: histogram of (iterations, line-search trials, factorizations) per BoxQP call */
+struct QpStats {
+  bool on = false;
+  long long iters[32] = {0}, trials[64] = {0}, facts[16] = {0}, calls = 0;
+};
+QpStats g_qp_stats;
+
 void boxqp_solve(const oracle_options *o, int n, const double *H, const double *g, const double *lower,
                  const double *upper, const double *x0, BoxQPOut *r) {
+  int dbg_trials = 0;
+  struct StatGuard {
+    BoxQPOut *r;
+    int *trials;
+    ~StatGuard() {
+      if (!g_qp_stats.on) return;
+      g_qp_stats.calls++;
+      g_qp_stats.iters[std::min(r->iterations, 31)]++;
+      g_qp_stats.trials[std::min(*trials, 63)]++;
+      g_qp_stats.facts[std::min(r->factorizations, 15)]++;
+    }
+  } stat_guard{r, &dbg_trials};
   r->status = ORACLE_QP_MAX_ITER_EXCEEDED;
   r->iterations = 0;
   r->factorizations = 0;
@@ -768,6 +787,7 @@ void boxqp_solve(const oracle_options *o, int n, const double *H, const double *
     bool ls_ok = false;
     double xn[MAXM];
     while (step > o->qp_min_step_size) {
+      ++dbg_trials;
       for (int i = 0; i < n; ++i) xn[i] = std::min(std::max(r->x[i] + step * search[i], lower[i]), upper[i]);
       const double vn = qp_value(xn, H, g, n);
       if ((vn - value) <= o->qp_armijo_constant * step * sdotg) {
@@ -2682,6 +2702,16 @@ void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const 
     scalars[10] = clampd(apm, 0.0, 1.0); scalars[11] = clampd(adm, 0.0, 1.0); scalars[12] = s.filter_theta;
     scalars[13] = s.theta; scalars[14] = (double)s.filter.size(); scalars[15] = ok ? 1.0 : 0.0;
   }
+}
+
+/* profiling aid (single-threaded use): enable/reset and read the BoxQP histograms */
+void oracle_debug_qp_stats(int enable, long long *iters32, long long *trials64, long long *facts16, long long *calls) {
+  if (iters32) std::memcpy(iters32, g_qp_stats.iters, sizeof(g_qp_stats.iters));
+  if (trials64) std::memcpy(trials64, g_qp_stats.trials, sizeof(g_qp_stats.trials));
+  if (facts16) std::memcpy(facts16, g_qp_stats.facts, sizeof(g_qp_stats.facts));
+  if (calls) *calls = g_qp_stats.calls;
+  g_qp_stats = QpStats();
+  g_qp_stats.on = enable != 0;
 }
 
 int oracle_hardware_threads(void) {

@@ -243,6 +243,7 @@ void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const 
                         dV0, dV1, alpha_pr_max, alpha_du_max, filter_theta, theta, filter_size, bw_ok */,
                         double *trial_costs /* [num_alphas][4]: success, cost, merit, theta of every alpha */);
 
+void oracle_debug_qp_stats(int enable, long long *iters32, long long *trials64, long long *facts16, long long *calls);
 int oracle_hardware_threads(void);
 const char *oracle_status_string(int status);
 
