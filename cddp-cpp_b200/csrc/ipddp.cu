@@ -69,11 +69,11 @@ __host__ __device__ inline int ip_table_doubles(int n, int m, int D) {  // const
 
 // NS, NC: compile-time state / control dimensions (0 = runtime): with constants the inner products unroll and the
 // index arithmetic (idx / n, idx % n) strength-reduces — about half of the generic kernel's instruction stream.
-template <int G, int NS, int NC>
+template <int G, int NS, int NC, int DC = 0>
 __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
                                                                  int mode) {
   extern __shared__ double smem[];
-  const int n = NS ? NS : d.n, m = NC ? NC : d.m, N = d.N, rs = d.rec_stride, D = ic.d;
+  const int n = NS ? NS : d.n, m = NC ? NC : d.m, N = d.N, rs = d.rec_stride, D = DC ? DC : ic.d;
   constexpr int GPC = kBwThreads / G;  // groups per CTA
   double *sQ = smem;
   double *sR = sQ + n * n;
@@ -546,20 +546,28 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   }
 }
 
-template <int MODEL>
-cudaError_t launch_ip_forward_model(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
-                                    cudaStream_t st) {
+template <int MODEL, int DC>
+cudaError_t launch_ip_forward_d(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                                cudaStream_t st) {
   const int per_cta = kFwThreads / 16;
-  const size_t shm = sizeof(double) * (size_t)per_cta * 2 * ip_fw_step_doubles(d.n, d.m, ic.d);
+  const size_t shm = sizeof(double) * (size_t)ip_fw_smem_doubles(d.n, d.m, ic.d);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ip_forward_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ip_forward_kernel<MODEL, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_forward_kernel<MODEL><<<(d.B + per_cta - 1) / per_cta, kFwThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_forward_kernel<MODEL, DC><<<(d.B + per_cta - 1) / per_cta, kFwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t launch_ip_forward_model(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
+                                    cudaStream_t st) {
+  // compile-time dual dimension for the BASELINE config #4 constraint set (control box 2m = 4 + ball 1)
+  if (MODEL == CDDP_B200_MODEL_UNICYCLE && ic.d == 5) return launch_ip_forward_d<MODEL, 5>(c, d, ic, ip, mode, st);
+  return launch_ip_forward_d<MODEL, 0>(c, d, ic, ip, mode, st);
 }
 
 template <int MODEL>
@@ -569,7 +577,7 @@ cudaError_t launch_ip_init_model(const Constants &c, const DeviceState &d, const
   return cudaGetLastError();
 }
 
-template <int G, int NS, int NC>
+template <int G, int NS, int NC, int DC = 0>
 cudaError_t launch_ip_backward_g(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                  cudaStream_t st) {
   const int n = d.n, m = d.m;
@@ -578,12 +586,12 @@ cudaError_t launch_ip_backward_g(const Constants &c, const DeviceState &d, const
                                        (size_t)gpc * ip_group_doubles(n, m, ic.d, d.rec_stride));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ip_backward_kernel<G, NS, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ip_backward_kernel<G, NS, NC, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_backward_kernel<G, NS, NC><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_backward_kernel<G, NS, NC, DC><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 
@@ -606,7 +614,8 @@ cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const I
   if (ic.teq) return launch_ip_backward_teq(c, d, ic, ip, mode, st);  // terminal-equality branch (ipddp_teq.cu)
   // lanes per trajectory: the widest per-step loop has n*(n+m) entries
   if (d.n == 2 && d.m == 1) return launch_ip_backward_g<8, 2, 1>(c, d, ic, ip, mode, st);
-  if (d.n == 3 && d.m == 2) return launch_ip_backward_g<8, 3, 2>(c, d, ic, ip, mode, st);
+  if (d.n == 3 && d.m == 2 && ic.d == 5) return launch_ip_backward_g<16, 3, 2, 5>(c, d, ic, ip, mode, st);
+  if (d.n == 3 && d.m == 2) return launch_ip_backward_g<16, 3, 2>(c, d, ic, ip, mode, st);
   if (d.n == 4 && d.m == 1) return launch_ip_backward_g<8, 4, 1>(c, d, ic, ip, mode, st);
   if (d.n == 13 && d.m == 4) return launch_ip_backward_g<32, 13, 4>(c, d, ic, ip, mode, st);
   if (d.n * (d.n + d.m) <= 24) return launch_ip_backward_g<8, 0, 0>(c, d, ic, ip, mode, st);

@@ -47,10 +47,10 @@ __host__ __device__ inline int teq_group_doubles(int n, int m, int D, int rs) {
   return (c + 1) & ~1;
 }
 
-template <int G, int NS, int NC>
+template <int G, int NS, int NC, int DC = 0>
 __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip, int mode) {
   extern __shared__ double smem[];
-  const int n = NS ? NS : d.n, m = NC ? NC : d.m, N = d.N, rs = d.rec_stride, D = ic.d;
+  const int n = NS ? NS : d.n, m = NC ? NC : d.m, N = d.N, rs = d.rec_stride, D = DC ? DC : ic.d;
   const int nv = n + 1, nc2 = 2 * n + 1;
   constexpr int GPC = kTeqThreads / G;
   double *sQ = smem;
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
   }
 }
 
-template <int G, int NS, int NC>
+template <int G, int NS, int NC, int DC = 0>
 cudaError_t launch_teq_g(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode, cudaStream_t st) {
   const int n = d.n, m = d.m, D = ic.d;
   const int gpc = kTeqThreads / G;
@@ -702,12 +702,12 @@ cudaError_t launch_teq_g(const Constants &c, const DeviceState &d, const IpConst
   const size_t shm = sizeof(double) * ((size_t)n * n + m * m + ((n * n + m * m) & 1) + tab + (size_t)gpc * teq_group_doubles(n, m, D, d.rec_stride));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ip_backward_teq_kernel<G, NS, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ip_backward_teq_kernel<G, NS, NC, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_backward_teq_kernel<G, NS, NC><<<(d.B + gpc - 1) / gpc, kTeqThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_backward_teq_kernel<G, NS, NC, DC><<<(d.B + gpc - 1) / gpc, kTeqThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 
@@ -716,6 +716,7 @@ cudaError_t launch_teq_g(const Constants &c, const DeviceState &d, const IpConst
 cudaError_t launch_ip_backward_teq(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                    cudaStream_t st) {
   if (d.n == 2 && d.m == 1) return launch_teq_g<8, 2, 1>(c, d, ic, ip, mode, st);
+  if (d.n == 3 && d.m == 2 && ic.d == 5) return launch_teq_g<16, 3, 2, 5>(c, d, ic, ip, mode, st);  // BASELINE config #4
   if (d.n == 3 && d.m == 2) return launch_teq_g<16, 3, 2>(c, d, ic, ip, mode, st);
   if (d.n == 4 && d.m == 1) return launch_teq_g<16, 4, 1>(c, d, ic, ip, mode, st);
   if (d.n * d.n <= 64) return launch_teq_g<16, 0, 0>(c, d, ic, ip, mode, st);

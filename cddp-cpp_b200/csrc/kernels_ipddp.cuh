@@ -19,27 +19,67 @@ __device__ __forceinline__ double clip_signed(double num, double den) {
 }
 __device__ __forceinline__ bool finite_d(double v) { return fabs(v) < pos_inf(); }
 
+// the flattened constraint rows (IpConstants) wherever they currently live: global memory, or a CTA's shared-memory copy
+struct ConTable {
+  const double *Gx, *Gu, *off, *scale;
+  const int *type, *bdim;
+};
+__device__ __forceinline__ ConTable con_table_global(const IpConstants &ic) {
+  return ConTable{ic.Gx, ic.Gu, ic.off, ic.scale, ic.row_type, ic.row_bdim};
+}
+__host__ __device__ inline int con_table_doubles(int n, int m, int D) { return (D * n + D * m + 3 * D + 1) & ~1; }
+// copies the table into shared memory (all threads of the CTA; caller synchronises)
+__device__ __forceinline__ ConTable con_table_stage(const IpConstants &ic, double *dst, int n, int m, int D) {
+  double *tGx = dst, *tGu = tGx + D * n, *tOff = tGu + D * m, *tScale = tOff + D;
+  int *tType = reinterpret_cast<int *>(tScale + D), *tBdim = tType + D;
+  for (int i = threadIdx.x; i < D * n; i += blockDim.x) tGx[i] = ic.Gx[i];
+  for (int i = threadIdx.x; i < D * m; i += blockDim.x) tGu[i] = ic.Gu[i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    tOff[i] = ic.off[i];
+    tScale[i] = ic.scale[i];
+    tType[i] = ic.row_type[i];
+    tBdim[i] = ic.row_bdim[i];
+  }
+  return ConTable{tGx, tGu, tOff, tScale, tType, tBdim};
+}
+
 // g_r(x,u) = constraint.evaluate(x,u) - getUpperBound() for row r of the stacked set (ipddp_solver.cpp:2273-2278)
-__device__ __forceinline__ double con_value(const IpConstants &ic, int r, int n, int m, const double *x, const double *u) {
-  const int ty = ic.row_type[r];
+__device__ __forceinline__ double con_value(const ConTable &ct, int r, int n, int m, const double *x, const double *u) {
+  const int ty = ct.type[r];
   if (ty == IP_ROW_BALL) {  // constraint.hpp:326-343
-    const int bd = ic.row_bdim[r];
-    const double sc = ic.scale[r], rad = ic.off[r];
+    const int bd = ct.bdim[r];
+    const double sc = ct.scale[r], rad = ct.off[r];
     double sq = 0.0;
     for (int i = 0; i < bd; ++i) {
-      const double df = x[i] - ic.Gx[r * n + i];
+      const double df = x[i] - ct.Gx[r * n + i];
       sq += df * df;
     }
     return -(sc * sq) - (-(rad * rad) * sc);
   }
   double s = 0.0;
   if (ty == IP_ROW_STATE) {
-    for (int j = 0; j < n; ++j) s += ic.Gx[r * n + j] * x[j];
+    for (int j = 0; j < n; ++j) s += ct.Gx[r * n + j] * x[j];
   } else {
-    for (int j = 0; j < m; ++j) s += ic.Gu[r * m + j] * u[j];
+    for (int j = 0; j < m; ++j) s += ct.Gu[r * m + j] * u[j];
   }
-  return s - ic.off[r];
+  return s - ct.off[r];
 }
+
+// sum_i log(s_i) accumulated as ONE logarithm: the slacks are multiplied in mantissa / exponent form (frexp keeps the running
+// product in [0.5, 1), the binary exponents add up exactly) and log(mantissa) + exponent * ln 2 is taken once per rollout.
+// An FP64 log is a ~60-instruction dependent sequence and the barrier merit needs one per constraint row per timestep
+// (computeBarrierMerit, ipddp_solver.cpp:2850-2880); the product form differs from the reference's sum of logs by the
+// rounding of the multiplications (~1e-16 relative per factor).
+struct LogProduct {
+  double mant = 1.0;
+  long long expo = 0;
+  __device__ __forceinline__ void mul(double v) {
+    int e;
+    mant = frexp(mant * v, &e);  // v > 0 (slacks are floored at EPS_SLACK): mant stays in [0.5, 1)
+    expo += e;
+  }
+  __device__ __forceinline__ double log_value() const { return log(mant) + (double)expo * 0.693147180559945309417232121458; }
+};
 
 // asynchronous global -> shared copies (LDGSTS): the next timestep's operands are fetched while the current one is
 // being processed, so that the chain of N dependent timesteps pays HBM/L2 latency once, not N times
@@ -106,10 +146,12 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
   const double *U = d.U[cur] + (size_t)b * N * NC;
   double *G = ip.G[cur] + (size_t)b * N * D, *S = ip.S[cur] + (size_t)b * N * D, *Y = ip.Y[cur] + (size_t)b * N * D;
   const double mu = (ic.nc == 0 && !ic.teq) ? fmax(c.opt.tolerance / 10.0, ic.io.mu_min_value) : ic.io.mu_initial;  // :884-887
+  const ConTable ctab = con_table_global(ic);
   double x[NS], xn[NS], u[NC];
 #pragma unroll
   for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
-  double J = 0.0, logsum = 0.0, theta = 0.0, maxr = 0.0, maxys = -pos_inf(), minys = pos_inf();
+  double J = 0.0, theta = 0.0, maxr = 0.0, maxys = -pos_inf(), minys = pos_inf();
+  LogProduct lprod;
   for (int t = 0; t < N; ++t) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) X[(size_t)t * NS + i] = x[i];
@@ -130,9 +172,9 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
       }
       J += sx + su;
     }
-    double acc = 0.0, lacc = 0.0;
+    double acc = 0.0;
     for (int r = 0; r < D; ++r) {  // :2447-2466
-      const double g = con_value(ic, r, NS, NC, x, u);
+      const double g = con_value(ctab, r, NS, NC, x, u);
       const double s = fmax(ic.io.slack_var_init_scale, -g + kSlackInteriorOffset);
       const double y = (mu * ic.io.dual_var_init_scale) / fmax(s, EPS_SLACK);
       G[(size_t)t * D + r] = g;
@@ -141,18 +183,18 @@ __global__ void __launch_bounds__(64) ip_initialize_kernel(Constants c, DeviceSt
       const double res = g + s;
       acc += ic.io.theta_norm_l2 ? res * res : fabs(res);
       maxr = fmax(maxr, fabs(res));
-      lacc += log(fmax(s, EPS_SLACK));
+      lprod.mul(fmax(s, EPS_SLACK));
       maxys = fmax(maxys, y * s);
       minys = fmin(minys, y * s);
     }
     theta += acc;
-    logsum += lacc;
     discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);
 #pragma unroll
     for (int i = 0; i < NS; ++i) x[i] = xn[i];
   }
 #pragma unroll
   for (int i = 0; i < NS; ++i) X[(size_t)N * NS + i] = x[i];
+  const double logsum = lprod.log_value();
   {
     const double *ref = d.xref + (size_t)b * NS;
     double sx = 0.0;
@@ -230,12 +272,12 @@ __host__ __device__ inline int ip_fw_step_doubles(int n, int m, int D) {
   return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1;
 }
 
-template <int MODEL, bool WRITE>
+template <int MODEL, bool WRITE, int DC>
 __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
-                                           int b, int cur, double alpha_pr, double alpha_du, double tau, double mu,
-                                           TrialStats &st, double *stage, int al, bool wr) {
+                                           const ConTable &ctab, int b, int cur, double alpha_pr, double alpha_du, double tau,
+                                           double mu, TrialStats &st, double *stage, int al, bool wr) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC, LG = 16;
-  const int N = d.N, D = ic.d;
+  const int N = d.N, D = DC ? DC : ic.d;
   const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
   const double *gK = d.K + (size_t)b * N * NC * NS, *gk = d.kff + (size_t)b * N * NC;
   const double *S0 = ip.S[cur] + (size_t)b * N * D, *Y0 = ip.Y[cur] + (size_t)b * N * D;
@@ -273,6 +315,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 #pragma unroll
   for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
   st.cost = 0.0; st.logsum = 0.0; st.theta = 0.0; st.inf_pr = 0.0; st.maxys = -pos_inf(); st.minys = pos_inf();
+  LogProduct lprod;
   st.feasible = true;
   bool feas = true;
   for (int t = 0; t < N; ++t) {
@@ -287,7 +330,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       for (int j = 0; j < NS; ++j) acc += sg[oK + i * NS + j] * dxv[j];
       u[i] = (sg[oU + i] + alpha_pr * sg[ok_ + i]) + acc;
     }
-    double acc_t = 0.0, lacc = 0.0;
+    double acc_t = 0.0;
     for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
       const size_t e = (size_t)t * D + q;
       double a1 = 0.0, a2 = 0.0;
@@ -304,11 +347,11 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, sg[oky + q])), a2);
       if (sn < __dmul_rn(1.0 - tau, s0) || yn < __dmul_rn(1.0 - tau, y0)) feas = false;
       if (!finite_d(sn) || !finite_d(yn)) feas = false;
-      const double g = con_value(ic, q, NS, NC, x, u);  // (:1743-1748)
+      const double g = con_value(ctab, q, NS, NC, x, u);  // (:1743-1748)
       const double res = g + sn;
       acc_t += l2 ? res * res : fabs(res);
       st.inf_pr = fmax(st.inf_pr, fabs(res));
-      lacc += log(fmax(sn, EPS_SLACK));
+      lprod.mul(fmax(sn, EPS_SLACK));
       st.maxys = fmax(st.maxys, yn * sn);
       st.minys = fmin(st.minys, yn * sn);
       if (WRITE && wr) {
@@ -318,7 +361,6 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       }
     }
     st.theta += acc_t;
-    st.logsum += lacc;
     {  // running cost (:1741)
       const double *ref = ref_ptr(d, b, t);
       double sx = 0.0, su = 0.0;
@@ -372,6 +414,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 #pragma unroll
     for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
   }
+  st.logsum = lprod.log_value();
   st.lamh = 0.0;
   if (ic.teq) {  // Lambda_T_eq_new = Lambda_T_eq_ + alpha_pr dLambda_T_eq_ (:1716-1723); h_T_new = x_N - xref (:1756-1760)
     const double *ref = d.xref + (size_t)b * NS;
@@ -397,20 +440,28 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 // One lane per alpha, 16 lanes per trajectory.  pass 1: every lane rolls its alpha out and applies the acceptance test;
 // the first accepted alpha (sequential semantics, cddp_solver_base.cpp:255-263) is replayed once (pass 2, all lanes of
 // the group in lock-step, lane 0 writing the candidate buffers); lane 0 then runs the per-instance bookkeeping.
-template <int MODEL>
+// DC: compile-time total dual dimension (0 = runtime) — the per-row loops of the rollout unroll.
+__host__ __device__ inline int ip_fw_smem_doubles(int n, int m, int D) {
+  return con_table_doubles(n, m, D) + (kFwThreads / 16) * 2 * ip_fw_step_doubles(n, m, D);
+}
+
+template <int MODEL, int DC = 0>
 __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, DeviceState d, IpConstants ic, IpDevice ip,
                                                                 int mode) {
   constexpr int LG = 16;
   constexpr int NS_ = Model<MODEL>::NS, NC_ = Model<MODEL>::NC;
   extern __shared__ double fw_smem[];
+  const int Dd = DC ? DC : ic.d;
+  const ConTable ctab = con_table_stage(ic, fw_smem, NS_, NC_, Dd);  // constraint rows: one shared-memory copy per CTA
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int grp = lane / LG, al = lane % LG;
   const int b = ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp;
   const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   if (!__any_sync(0xffffffffu, alive)) return;
-  double *stage = fw_smem + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, ic.d);
+  double *stage = fw_smem + con_table_doubles(NS_, NC_, Dd) + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, Dd);
   const int bb = alive ? b : 0;
-  const int na = c.num_alphas, D = ic.d;
+  const int na = c.num_alphas, D = Dd;
   const int cur = d.cur[bb];
   const double mu = ip.mu[bb];
   const bool active = alive && al < na;
@@ -418,7 +469,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double tau = ic.nc == 0 ? 1.0 : fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);  // (:1585-1588)
   const double alpha_pr = fmin(alpha, ip.apm[bb]), alpha_du = fmin(alpha, ip.adm[bb]);
   TrialStats st;
-  ip_rollout<MODEL, false>(c, d, ic, ip, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
+  ip_rollout<MODEL, false, DC>(c, d, ic, ip, ctab, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
   const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
   const double phi_new = (st.cost - mu * st.logsum) + st.lamh;  // computeBarrierMerit (:2850-2880)
   const double theta_new = st.theta;
@@ -481,7 +532,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double lamh_new = __shfl_sync(0xffffffffu, st.lamh, src);
   if (__any_sync(0xffffffffu, alive && first >= 0)) {  // pass 2: replay the accepted trial (lane 0 of the group writes)
     TrialStats s2;
-    ip_rollout<MODEL, true>(c, d, ic, ip, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
+    ip_rollout<MODEL, true, DC>(c, d, ic, ip, ctab, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
   }
   if (!(alive && al == 0)) return;
   d.accepted[b] = first;

@@ -119,7 +119,7 @@ std::string name_expr(int k, bool diag) {
     case K_FWD16: return std::string("cddp_b200::kern::forward_kernel<CDDP_B200_MODEL_USER, 16, ") + d + ">";
     case K_FWD32: return std::string("cddp_b200::kern::forward_kernel<CDDP_B200_MODEL_USER, 32, ") + d + ">";
     case K_IPINIT: return "cddp_b200::kern::ip_initialize_kernel<CDDP_B200_MODEL_USER>";
-    default: return "cddp_b200::kern::ip_forward_kernel<CDDP_B200_MODEL_USER>";
+    default: return "cddp_b200::kern::ip_forward_kernel<CDDP_B200_MODEL_USER, 0>";
   }
 }
 
@@ -289,7 +289,8 @@ cudaError_t launch_user_ip_forward(const Constants &c, const DeviceState &d, con
   UserKernels *uk = static_cast<UserKernels *>(d.user);
   const int per_cta = 64 / 16;  // kern::kFwThreads / LG
   const int step = (d.n + 2 * d.m + d.m * d.n + 4 * ic.d + 2 * ic.d * d.n + 1) & ~1;  // kern::ip_fw_step_doubles
-  const size_t shm = sizeof(double) * (size_t)per_cta * 2 * step;
+  const int table = (ic.d * d.n + ic.d * d.m + 3 * ic.d + 1) & ~1;                     // kern::con_table_doubles
+  const size_t shm = sizeof(double) * ((size_t)table + (size_t)per_cta * 2 * step);   // kern::ip_fw_smem_doubles
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
   void *params[] = {(void *)&c, (void *)&d, (void *)&ic, (void *)&ip, &mode};
   return launch(uk, K_IPFWD, (unsigned)((d.B + per_cta - 1) / per_cta), 64, shm, st, params);
