@@ -1007,17 +1007,17 @@ int cddp_b200_ipddp_dual_dim(cddp_b200_solver *s, int *d) {
 }
 
 namespace {
-// gather a [B][N][d(*n)] double-buffered array of the CURRENT nominal into contiguous scratch: done on the host side of
-// the copy by reading both buffers and selecting per instance (cur is tiny)
+// a [B][N][d] double-buffered array of the CURRENT nominal (cur[b] selects the buffer): gathered on the device into the
+// scratch buffer, then one device-to-host copy
 int download_current(cddp_b200_solver *s, double *dst, double *const buf[2], size_t per_instance) {
   if (!dst) return 0;
-  const size_t B = s->d.B;
-  std::vector<int> cur(B);
-  CU(cudaMemcpyAsync(cur.data(), s->d.cur, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  for (size_t b = 0; b < B; ++b)
-    CU(cudaMemcpyAsync(dst + b * per_instance, buf[cur[b]] + b * per_instance, per_instance * sizeof(double),
-                       cudaMemcpyDeviceToHost, s->stream));
+  const size_t bytes = (size_t)s->d.B * per_instance * sizeof(double);
+  int r = s->ensure_scratch(bytes);
+  if (r) return r;
+  CU(launch_gather_by_cur(s->d, buf[0], buf[1], per_instance, s->scratch, s->stream));
+  s->timing.other_launches++;
+  CU(cudaMemcpyAsync(dst, s->scratch, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // the scratch buffer is reused by the next call
   return 0;
 }
 }  // namespace

@@ -131,6 +131,8 @@ cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, c
 cudaError_t launch_finalize(const Constants &c, const DeviceState &d, int final_status, cudaStream_t st);
 cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st);
 cudaError_t launch_shift(const DeviceState &d, int k, cudaStream_t st);
+cudaError_t launch_gather_by_cur(const DeviceState &d, const double *buf0, const double *buf1, size_t per_instance, double *out,
+                                 cudaStream_t st);
 cudaError_t launch_first_controls(const DeviceState &d, double *u0, cudaStream_t st);
 cudaError_t launch_unpack_linearization(const Constants &c, const DeviceState &d, double *A, double *Bm,
                                         cudaStream_t st);

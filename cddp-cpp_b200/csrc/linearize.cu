@@ -175,6 +175,13 @@ __global__ void gather_current_kernel(DeviceState d, double *X, double *U, int w
     for (size_t i = threadIdx.x; i < nu; i += blockDim.x) U[b * nu + i] = d.U[buf][b * nu + i];
 }
 
+// gather a double-buffered per-instance array (IPDDP duals / slacks / constraint values) of the CURRENT nominal
+__global__ void gather_by_cur_kernel(DeviceState d, const double *buf0, const double *buf1, size_t per_instance, double *out) {
+  const int b = blockIdx.x;
+  const double *src = (d.cur[b] ? buf1 : buf0) + (size_t)b * per_instance;
+  for (size_t i = threadIdx.x; i < per_instance; i += blockDim.x) out[(size_t)b * per_instance + i] = src[i];
+}
+
 // Receding-horizon shift of the nominal trajectory (MPC warm start): X[t] <- X[t+k], U[t] <- U[t+k]; the tail repeats the
 // last control and the last state.  Written into the candidate buffer, then the buffers are swapped.
 __global__ void shift_kernel(DeviceState d, int k) {
@@ -208,6 +215,12 @@ __global__ void first_controls_kernel(DeviceState d, double *u0) {
 }
 
 }  // namespace
+
+cudaError_t launch_gather_by_cur(const DeviceState &d, const double *buf0, const double *buf1, size_t per_instance, double *out,
+                                 cudaStream_t st) {
+  gather_by_cur_kernel<<<d.B, 128, 0, st>>>(d, buf0, buf1, per_instance, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_shift(const DeviceState &d, int k, cudaStream_t st) {
   shift_kernel<<<d.B, 128, 0, st>>>(d, k);

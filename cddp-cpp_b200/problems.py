@@ -72,7 +72,7 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
         "pendulum_ipddp": _cfg_pendulum_ipddp, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
         "quadrotor_ipddp": _cfg_quadrotor_ipddp, "bicycle_user": _cfg_bicycle_user, "bicycle_user_ipddp": _cfg_bicycle_user_ipddp,
         "chain7_user": _cfg_chain7_user, "unicycle_obstacle_teq": _cfg_unicycle_obstacle_teq,
-        "unicycle_teq": _cfg_unicycle_teq, "cartpole_teq": _cfg_cartpole_teq,
+        "unicycle_teq": _cfg_unicycle_teq, "cartpole_teq": _cfg_cartpole_teq, "chain7_user_ipddp": _cfg_chain7_user_ipddp,
     }
     if name not in builders:
         raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
@@ -452,6 +452,20 @@ def _cfg_chain7_user(batch, horizon, seed_offset):
     U0 = np.zeros((B, N, 7))
     return dict(name="chain7_user", config_id=5, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
                 notes="7-joint chain (plugin model; stands in for BASELINE config #5) n=14 m=7 N=150, CLDDP + control box +-50")
+
+
+def _cfg_chain7_user_ipddp(batch, horizon, seed_offset):
+    """BASELINE config #5 as worded ("7-DOF manipulator n=14 m=7 N=150, mixed constraints"): the plugin chain model under IPDDP
+    with MIXED path constraints — torque box (ControlConstraint, 14 rows) + joint-angle / joint-rate box (StateConstraint,
+    28 rows): d = 42."""
+    cfg = _cfg_chain7_user(batch, horizon, seed_offset)
+    spec = dict(cfg["spec"], lb=None, ub=None)
+    cfg.update(name="chain7_user_ipddp", config_id=5, solver="ipddp", spec=spec, X0=None, ipddp_options={},
+               options=dict(max_iterations=60, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-5),
+               constraints=[dict(type="control_box", lb=[-50.0] * 7, ub=[50.0] * 7),
+                            dict(type="state_box", lb=[-1.0] * 7 + [-3.0] * 7, ub=[1.0] * 7 + [3.0] * 7)],
+               notes="7-joint chain (plugin model; BASELINE config #5 stand-in) n=14 m=7 N=150, IPDDP, torque box + joint/rate box (d=42)")
+    return cfg
 
 
 def shard(cfg: dict, rank: int, world: int) -> dict:

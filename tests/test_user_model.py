@@ -143,3 +143,37 @@ def test_plugin_ipddp_parity(cddp, ob, problems):
     dist = np.hypot(g["X"][:, :, 0] - 3.0, g["X"][:, :, 1] - 1.2)
     assert (dist.min(axis=1) > 0.5 - 5e-2).all()
     s.close()
+
+
+@pytest.mark.gpu
+def test_config5_standin_mixed_constraints_ipddp(cddp, ob, problems):
+    """BASELINE config #5 as worded (n=14, m=7, N=150, mixed constraints): the 7-joint plugin model under IPDDP with a torque
+    box and a joint / rate box (d = 42).  First backward pass against the oracle; whole solves are held to validity
+    properties (the state-box rows at t = 0 make every line search roundoff-decided, see tests/test_gpu_ipddp.py)."""
+    B = 4
+    cfg = problems.make_config("chain7_user_ipddp", batch=B, horizon=150)
+    s = cddp.BatchedIPDDP(cfg["spec"], cddp.default_options(**cfg["options"]), cddp.default_ipddp_options(), cfg["constraints"], B)
+    assert s.d == 42
+    P, oo, oi, cs = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"]), ob.make_ipddp_options(), ob.ConstraintSet(cfg["constraints"])
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"])
+    s.initialize()
+    s.linearize()
+    s.backward_pass()
+    sol, ips, gains, kff = s.get_solution(), s.get_ipddp_solution(), s.get_ipddp_gains(), s.get_feedforward()
+    for b in range(B):
+        r = ob.ipddp_probe(P, oo, oi, cs, cfg["x0"][b], cfg["xref"][b], cfg["U0"][b], 0)
+        for key, val in (("X", sol["X"][b]), ("S", ips["S"][b]), ("Y", ips["Y"][b]), ("G", ips["G"][b]), ("ku", kff[b]), ("Ku", sol["K"][b]),
+                         ("ky", gains["ky"][b]), ("Ky", gains["Ky"][b]), ("ks", gains["ks"][b]), ("Ks", gains["Ks"][b])):
+            assert rel_err(val, r[key]) < 1e-9, (b, key)
+        assert abs(ips["alpha_pr_max"][b] - r["alpha_pr_max"]) <= 1e-9 * r["alpha_pr_max"]
+        assert abs(sol["inf_du"][b] - r["inf_du"]) <= 1e-9 * r["inf_du"]
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"])
+    s.solve()
+    g, gi = s.get_solution(want_K=False), s.get_ipddp_solution()
+    assert np.isfinite(g["cost"]).all() and (gi["S"] > 0).all() and (gi["Y"] > 0).all()
+    conv = np.isin(g["status"], (1, 2))
+    assert conv.any()
+    assert (np.abs(g["U"][conv]) <= 50.0 + 1e-6).all() and (np.abs(g["X"][conv][:, :-1, :7]) <= 1.0 + 1e-4).all()
+    for b in range(B):
+        assert abs(ob.trajectory_cost(P, g["X"][b], g["U"][b], cfg["xref"][b]) - g["cost"][b]) <= 1e-10 * abs(g["cost"][b])
+    s.close()
