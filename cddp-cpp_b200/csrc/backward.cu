@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) backward_kernel(Constants c
             hi[i] = c.ub[i] - un[i];
             kk[i] = gk[(size_t)t * m + i];  // warm start x0 = k_u_[t]
           }
-        const int qs = SmallMat<MC>::boxqp(c.opt, m, H, g, lo, hi, kk, free_mask, L);
+        const int qs = SmallMat<MC>::boxqp(c.opt, m, H, g, lo, hi, kk, free_mask, L, true);
         if (qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT) {
           ok = false;
           break;

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
                 hi[a] = c.ub[a] - un;
                 kk[a] = S[Cfg::oKprev + a];
               }
-              const int qs = SmallMat<MC>::boxqp(c.opt, NC, H, g, lo, hi, kk, free_mask, Lf);
+              const int qs = SmallMat<MC>::boxqp(c.opt, NC, H, g, lo, hi, kk, free_mask, Lf, true);
               good = !(qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT);
               if (good && c.opt.qp_max_iterations <= 0) SmallMat<MC>::masked_cholesky(NC, H, free_mask, Lf);
             } else {
@@ -559,10 +559,8 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
 #pragma unroll
             for (int col = 0; col < MC; ++col) {
               double e[MC];
-#pragma unroll
-              for (int a = 0; a < MC; ++a) e[a] = (a == col) ? 1.0 : 0.0;
               const bool fc = (free_mask >> col) & 1u;
-              if (fc) SmallMat<MC>::chol_solve(NC, Lf, e);
+              SmallMat<MC>::chol_inverse_column(NC, Lf, col, e);
 #pragma unroll
               for (int a = 0; a < MC; ++a) {
                 const double hv = (fc && ((free_mask >> a) & 1u)) ? e[a] : 0.0;

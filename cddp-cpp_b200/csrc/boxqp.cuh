@@ -14,6 +14,9 @@
 //     (clamped rows/columns replaced by identity), which factors exactly the free block without a
 //     gather/scatter and keeps every lane on fixed-size m x m code.
 //   * MatrixXd::inverse() then multiply -> Cholesky solve.
+//   * The factor keeps 1/l_jj on its diagonal (rsqrt of the pivot) and the substitutions multiply by it: an FP64
+//     division is a ~17-instruction dependent sequence and a 7 x 7 inverse from the factor used to spend 112 of
+//     them per timestep on the sweep's critical path.
 // Every lane of the warp executes this code redundantly on identical data (one problem per warp,
 // so there is no intra-warp divergence); results live in registers of all lanes.
 #pragma once
@@ -29,7 +32,8 @@ enum {
 // M = compile-time capacity, m = runtime size (== M for specialised kernels)
 template <int M>
 struct SmallMat {
-  // Cholesky of the masked matrix; returns false if a pivot is not > 0 (also for NaN).
+  // Cholesky of the masked matrix; returns false if a pivot is not > 0 (also for NaN).  L holds the strict lower
+  // triangle of the factor and, ON THE DIAGONAL, the reciprocals 1/l_jj.
   __device__ __forceinline__ static bool masked_cholesky(int m, const double *H, unsigned free_mask, double *L) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -40,9 +44,8 @@ struct SmallMat {
         for (int k = 0; k < M; ++k)
           if (k < j) s -= L[j * M + k] * L[j * M + k];
         if (!(s > 0.0)) return false;
-        const double ljj = sqrt(s);
-        L[j * M + j] = ljj;
-        const double inv = 1.0 / ljj;
+        const double inv = rsqrt(s);
+        L[j * M + j] = inv;
 #pragma unroll
         for (int i = 0; i < M; ++i) {
           if (i > j && i < m) {
@@ -68,7 +71,7 @@ struct SmallMat {
 #pragma unroll
         for (int k = 0; k < M; ++k)
           if (k < i) s -= L[i * M + k] * b[k];
-        b[i] = s / L[i * M + i];
+        b[i] = s * L[i * M + i];
       }
     }
 #pragma unroll
@@ -79,7 +82,37 @@ struct SmallMat {
 #pragma unroll
         for (int k = 0; k < M; ++k)
           if (k > i && k < m) s -= L[k * M + i] * b[k];
-        b[i] = s / L[i * M + i];
+        b[i] = s * L[i * M + i];
+      }
+    }
+  }
+
+  // column `col` of (L L^T)^-1: the same substitutions with b = e_col, skipping the leading zeros of the forward pass
+  // (call with a compile-time col from an unrolled loop)
+  __device__ __forceinline__ static void chol_inverse_column(int m, const double *L, int col, double *b) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (i < col || i >= m) {
+        b[i] = 0.0;
+      } else if (i == col) {
+        b[i] = L[i * M + i];
+      } else {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+          if (k >= col && k < i) s -= L[i * M + k] * b[k];
+        b[i] = s * L[i * M + i];
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < M; ++ii) {
+      const int i = M - 1 - ii;
+      if (i < m) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+          if (k > i && k < m) s -= L[k * M + i] * b[k];
+        b[i] = s * L[i * M + i];
       }
     }
   }
@@ -101,9 +134,10 @@ struct SmallMat {
   }
 
   // BoxQPSolver::solve.  x: in = warm start x0 (boxqp.cpp:184-187, x0 always supplied by CLDDP),
-  // out = solution.  free_mask/L: final free set and its (masked) Cholesky factor.
+  // out = solution.  free_mask/L: final free set and its (masked) Cholesky factor.  L_is_full: on entry L already
+  // holds the factor of the unmasked H (the caller's PD test), which is what iteration 0 needs when nothing is clamped.
   __device__ static int boxqp(const cddp_b200_options &o, int m, const double *H, const double *g, const double *lo,
-                              const double *hi, double *x, unsigned &free_mask, double *L) {
+                              const double *hi, double *x, unsigned &free_mask, double *L, bool L_is_full = false) {
     const unsigned all = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
     int status = QP_MAX_ITER_EXCEEDED;
 #pragma unroll
@@ -113,6 +147,7 @@ struct SmallMat {
     free_mask = all;
     double value = qp_value(m, H, g, x);
     double old_value = __longlong_as_double(0x7ff0000000000000LL);
+    const double gtol2 = o.qp_min_gradient_norm * o.qp_min_gradient_norm;
     for (int iter = 0; iter < o.qp_max_iterations; ++iter) {
       if (iter > 0 && fabs(old_value - value) < o.qp_min_relative_improvement * fabs(old_value)) {
         status = QP_SUCCESS;
@@ -141,7 +176,7 @@ struct SmallMat {
         status = QP_ALL_CLAMPED;
         break;
       }
-      if (iter == 0 || clamped != old_clamped) {
+      if ((iter == 0 && !(L_is_full && clamped == 0u)) || (iter > 0 && clamped != old_clamped)) {
         if (!masked_cholesky(m, H, free_mask, L)) {
           status = QP_HESSIAN_NOT_PD;
           break;
@@ -151,7 +186,7 @@ struct SmallMat {
 #pragma unroll
       for (int i = 0; i < M; ++i)
         if (i < m && ((free_mask >> i) & 1u)) gn += grad[i] * grad[i];
-      if (sqrt(gn) < o.qp_min_gradient_norm) {
+      if (gn < gtol2) {  // sqrt(gn) < min_gradient_norm
         status = QP_SUCCESS;
         break;
       }
@@ -180,14 +215,14 @@ struct SmallMat {
         status = QP_NO_DESCENT;
         break;
       }
-      double step = 1.0;
+      double step = 1.0, vn = 0.0;
       bool ls_ok = false;
       double xn[M];
       while (step > o.qp_min_step_size) {
 #pragma unroll
         for (int i = 0; i < M; ++i)
           if (i < m) xn[i] = fmin(fmax(x[i] + step * search[i], lo[i]), hi[i]);
-        const double vn = qp_value(m, H, g, xn);
+        vn = qp_value(m, H, g, xn);
         if ((vn - value) <= o.qp_armijo_constant * step * sdotg) {
           ls_ok = true;
           break;
