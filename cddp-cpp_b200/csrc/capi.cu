@@ -432,7 +432,7 @@ int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, 
   AL(d.K, B * N * m * n); AL(d.kff, B * N * m);
   AL(d.x0, B * n); AL(d.xref, B * n);
   d.ref_traj = nullptr;
-  AL(d.cur, B); AL(d.status, B); AL(d.iter, B); AL(d.lin_valid, B); AL(d.bw_ok, B); AL(d.accepted, B);
+  AL(d.cur, B); AL(d.status, B); AL(d.iter, B); AL(d.lin_valid, B); AL(d.bw_ok, B); AL(d.accepted, B); AL(d.fw_done, B);
   AL(d.reg, B); AL(d.cost, B); AL(d.alpha, B); AL(d.inf_du, B); AL(d.dV, 2 * B);
   AL(d.ls_cost, B * CDDP_B200_MAX_ALPHAS);
   AL(d.Vx0, B * n); AL(d.Vxx0, B * n * n);
@@ -443,6 +443,7 @@ int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, 
 #undef AL
   e = cudaMemset(d.cur, 0, B * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d.status, 0, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d.fw_done, 0, B * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d.K, 0, B * N * m * n * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(d.kff, 0, B * N * m * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(d.ls_cost, 0, B * CDDP_B200_MAX_ALPHAS * sizeof(double));

@@ -47,6 +47,7 @@ struct DeviceState {
   int *lin_valid;  // rec matches the nominal trajectory
   int *bw_ok;      // last backward sweep succeeded
   int *accepted;   // index of the accepted alpha in the last line search (-1 none)
+  int *fw_done;    // FW_ITERATE only: this forward call's line search was already settled by forward_first_kernel
   double *reg;     // regularization_
   double *cost;    // cost_
   double *alpha;   // alpha_pr_

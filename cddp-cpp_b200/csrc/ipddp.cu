@@ -45,7 +45,7 @@ constexpr int kBwThreads = 128;
 
 __host__ __device__ inline int ip_stage_doubles(int n, int m, int D, int rs) {
   const int sweep = rs + n + 3 * D;                          // record | x | y | s | g of one timestep
-  const int roll = rs + 4 * D + 2 * D * n + m * n + m;       // record | k_s k_y S Y | K_s K_y | K | k (linear rollout)
+  const int roll = rs + m * n + m;                           // record | K | k (linear rollout of dx)
   const int b = sweep > roll ? sweep : roll;
   return (b + 1) & ~1;
 }
@@ -64,7 +64,9 @@ __host__ __device__ inline int ip_group_doubles(int n, int m, int D, int rs) {
   return (c + 1) & ~1;
 }
 __host__ __device__ inline int ip_table_doubles(int n, int m, int D) {  // constraint table staged in shared memory
-  return D * n + D * m + 2 * D + D;  // Gx | Gu | off | scale | (row_type, row_bdim) packed as ints in D doubles
+  // Gx | Gu | off | scale | (row_type, row_bdim) packed as ints in D doubles | sparsity masks (64-bit each): rows per
+  // state column, rows per control column, controls per row
+  return D * n + D * m + 2 * D + D + (n + m + D);
 }
 
 // NS, NC: compile-time state / control dimensions (0 = runtime): with constants the inner products unroll and the
@@ -83,6 +85,15 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   double *tScale = tOff + D;
   int *tType = reinterpret_cast<int *>(tScale + D);
   int *tBdim = tType + D;
+  // Structural sparsity of the constraint Jacobians (batch-shared): every supported row touches EITHER the state
+  // (StateConstraint / LinearConstraint / BallConstraint rows, Q_yu row = 0) OR the control (ControlConstraint rows,
+  // Q_yx row = 0), and a box row has a single +-1.  The reference multiplies the dense d x n / d x m blocks
+  // (ipddp_solver.cpp:1427-1447, :1461-1497); here every sum over rows visits only the rows whose entry is
+  // structurally non-zero, in ascending row order — the same sum without its exact-zero terms.
+  static_assert(IP_MAX_DUAL <= 64, "row masks are 64-bit");
+  unsigned long long *mColX = reinterpret_cast<unsigned long long *>(tScale + 2 * D);  // [n] rows with Gx(q, j) != 0
+  unsigned long long *mColU = mColX + n;                                                // [m] rows with Gu(q, a) != 0
+  unsigned long long *mRowU = mColU + m;                                                // [D] controls with Gu(q, a) != 0
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) sQ[i] = c.Qdt2[i];
   for (int i = threadIdx.x; i < m * m; i += blockDim.x) sR[i] = c.Rdt2[i];
   for (int i = threadIdx.x; i < D * n; i += blockDim.x) tGx[i] = ic.Gx[i];
@@ -93,12 +104,54 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
     tType[i] = ic.row_type[i];
     tBdim[i] = ic.row_bdim[i];
   }
+  for (int j = threadIdx.x; j < n + m + D; j += blockDim.x) {
+    unsigned long long mk = 0ull;
+    if (j < n) {
+      for (int q = 0; q < D; ++q) {
+        const int ty = ic.row_type[q];
+        const bool nz = (ty == IP_ROW_STATE && ic.Gx[q * n + j] != 0.0) || (ty == IP_ROW_BALL && j < ic.row_bdim[q]);
+        if (nz) mk |= 1ull << q;
+      }
+      mColX[j] = mk;
+    } else if (j < n + m) {
+      const int a = j - n;
+      for (int q = 0; q < D; ++q)
+        if (ic.row_type[q] == IP_ROW_CONTROL && ic.Gu[q * m + a] != 0.0) mk |= 1ull << q;
+      mColU[a] = mk;
+    } else {
+      const int q = j - n - m;
+      for (int a = 0; a < m; ++a)
+        if (ic.row_type[q] == IP_ROW_CONTROL && ic.Gu[q * m + a] != 0.0) mk |= 1ull << a;
+      mRowU[q] = mk;
+    }
+  }
   __syncthreads();
+  // sum over the rows (or controls) in a mask, ascending; with a compile-time dual dimension the dense unrolled loop
+  // over all `cnt` indices is kept (tiny d: the loop overhead of the sparse walk would cost more than the zeros)
+  auto for_bits = [&](unsigned long long mk, int cnt, auto &&f) {
+    if constexpr (DC != 0) {
+      for (int q = 0; q < cnt; ++q) f(q);
+    } else {
+      unsigned lo = (unsigned)mk, hi = (unsigned)(mk >> 32);  // two 32-bit walks: a 64-bit find-first-set is emulated
+      while (lo) {
+        const int q = __ffs((int)lo) - 1;
+        lo &= lo - 1;
+        f(q);
+      }
+      while (hi) {
+        const int q = 31 + __ffs((int)hi);
+        hi &= hi - 1;
+        f(q);
+      }
+    }
+  };
   const int grp = threadIdx.x / G, r = threadIdx.x % G;
   const int b = blockIdx.x * GPC + grp;
   const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   const int bb = alive ? b : 0;
   const int blk = ip_stage_doubles(n, m, D, rs);
+  bool any_ball = false;
+  for (int q = 0; q < D; ++q) any_ball = any_ball || tType[q] == IP_ROW_BALL;
   double *w = tGx + ((ip_table_doubles(n, m, D) + 1) & ~1) + (size_t)grp * ip_group_doubles(n, m, D, rs);
   double *stg = w;  w += 2 * blk;
   double *V = w;    w += n * n;
@@ -163,6 +216,10 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       for (int i = r; i < n; i += G) vx[i] = d.vterm[(size_t)bb * n + i];
     }
     dV0 = dV1 = inf_du = inf_pr = inf_comp = step_norm = 0.0;
+    if (act) {  // constraint Jacobians (precomputeConstraintGradients :2145-2250): the state-independent rows
+      for (int i = r; i < D * n; i += G) Gx[i] = (tType[i / n] == IP_ROW_STATE) ? tGx[i] : 0.0;
+      for (int i = r; i < D * m; i += G) Gu[i] = (tType[i / m] == IP_ROW_CONTROL) ? tGu[i] : 0.0;
+    }
     if (act) issue_sweep(N - 1, 0);
     cp_async_wait_all();
     __syncwarp();
@@ -173,15 +230,12 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       const double *A = rec, *Bm = rec + n * n, *lx = rec + d.offLx, *lu = rec + d.offLu;
       if (act) {
         // constraint Jacobians of this step (precomputeConstraintGradients :2145-2250) and the barrier terms (:1413-1443)
-        for (int i = r; i < D * n; i += G) {
-          const int row = i / n, j = i - row * n;
-          const int ty = tType[row];
-          double v = 0.0;
-          if (ty == IP_ROW_STATE) v = tGx[i];
-          else if (ty == IP_ROW_BALL && j < tBdim[row]) v = -2.0 * tScale[row] * (xs[j] - tGx[i]);
-          Gx[i] = v;
+        if (any_ball) {  // only BallConstraint rows depend on x_t; the others were written once before the sweep
+          for (int i = r; i < D * n; i += G) {
+            const int row = i / n, j = i - row * n;
+            if (tType[row] == IP_ROW_BALL) Gx[i] = (j < tBdim[row]) ? -2.0 * tScale[row] * (xs[j] - tGx[i]) : 0.0;
+          }
         }
-        for (int i = r; i < D * m; i += G) Gu[i] = (tType[i / m] == IP_ROW_CONTROL) ? tGu[i] : 0.0;
         for (int i = r; i < D; i += G) {
           const double sf = fmax(ss[i], fmax(mu * 1e-3, EPS_SLACK));
           ssafe[i] = sf;
@@ -212,13 +266,13 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         for (int j = r; j < n + m; j += G) {
           if (j < n) {
             double gy = 0.0, av = 0.0;
-            for (int q = 0; q < D; ++q) gy += Gx[q * n + j] * ys[q];
+            for_bits(mColX[j], D, [&](int q) { gy += Gx[q * n + j] * ys[q]; });
             for (int l = 0; l < n; ++l) av += A[l * n + j] * vx[l];
             Qx[j] = D ? (lx[j] + gy) + av : lx[j] + av;
           } else {
             const int a = j - n;
             double gy = 0.0, bv = 0.0;
-            for (int q = 0; q < D; ++q) gy += Gu[q * m + a] * ys[q];
+            for_bits(mColU[a], D, [&](int q) { gy += Gu[q * m + a] * ys[q]; });
             for (int l = 0; l < n; ++l) bv += Bm[l * m + a] * vx[l];
             Qu[a] = D ? (lu[a] + gy) + bv : lu[a] + bv;
           }
@@ -249,16 +303,16 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
           if (idx < m * m) {
             const int i = idx / m, j = idx - i * m;
             double acc = 0.0;
-            for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]);
+            for_bits(mColU[i] & mColU[j], D, [&](int q) { acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]); });
             Qr[idx] = 0.5 * (Quu[i * m + j] + Quu[j * m + i]) + acc + (i == j ? reg : 0.0);
           } else {
             const int e = idx - m * m, i = e / nc1, j = e - i * nc1;
             double acc = 0.0;
             if (j == 0) {
-              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * Sir[q];
+              for_bits(mColU[i], D, [&](int q) { acc += Gu[q * m + i] * Sir[q]; });
               RHS[e] = D ? Qu[i] + acc : Qu[i];
             } else {
-              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gx[q * n + (j - 1)]);
+              for_bits(mColU[i] & mColX[j - 1], D, [&](int q) { acc += Gu[q * m + i] * (YS[q] * Gx[q * n + (j - 1)]); });
               RHS[e] = D ? Qux[i * n + (j - 1)] + acc : Qux[i * n + (j - 1)];
             }
           }
@@ -282,7 +336,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
           e -= m * n;
           if (e < n) {
             double acc = 0.0;
-            for (int q = 0; q < D; ++q) acc += Gx[q * n + e] * Sir[q];
+            for_bits(mColX[e], D, [&](int q) { acc += Gx[q * n + e] * Sir[q]; });
             if (D) Qx[e] += acc;
             continue;
           }
@@ -290,7 +344,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
           if (e < n * n) {
             const int i = e / n, j = e - i * n;
             double acc = 0.0;
-            for (int q = 0; q < D; ++q) acc += Gx[q * n + i] * (YS[q] * Gx[q * n + j]);
+            for_bits(mColX[i] & mColX[j], D, [&](int q) { acc += Gx[q * n + i] * (YS[q] * Gx[q * n + j]); });
             if (D) Qxx[e] += acc;
             continue;
           }
@@ -299,7 +353,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
             const int i = e / m, j = e - i * m;
             if (D) {
               double acc = 0.0;
-              for (int q = 0; q < D; ++q) acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]);
+              for_bits(mColU[i] & mColU[j], D, [&](int q) { acc += Gu[q * m + i] * (YS[q] * Gu[q * m + j]); });
               QK[e] = Quu[e] + acc;  // staged: Quu is still being read by other lanes' Qr (done above) — safe after sync
             } else {
               QK[e] = Qr[e];  // unconstrained branch: the symmetrised + regularised Q_uu enters V and dV (:1083-1084)
@@ -339,12 +393,12 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
           const int q = idx / nc1, j = idx - q * nc1;
           if (j == 0) {
             double temp = 0.0;
-            for (int i = 0; i < m; ++i) temp += Gu[q * m + i] * RHS[i * nc1];
+            for_bits(mRowU[q], m, [&](int i) { temp += Gu[q * m + i] * RHS[i * nc1]; });
             gky[(size_t)t * D + q] = clip_signed(rhat[q] + ys[q] * temp, ssafe[q]);
             gks[(size_t)t * D + q] = -prim[q] - temp;
           } else {
             double gkk = 0.0;
-            for (int i = 0; i < m; ++i) gkk += Gu[q * m + i] * RHS[i * nc1 + j];
+            for_bits(mRowU[q], m, [&](int i) { gkk += Gu[q * m + i] * RHS[i * nc1 + j]; });
             const double qq = Gx[q * n + (j - 1)] + gkk;
             gKy[((size_t)t * D + q) * n + (j - 1)] = clampd(YS[q] * qq, -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
             gKs[((size_t)t * D + q) * n + (j - 1)] = -Gx[q * n + (j - 1)] - gkk;
@@ -378,7 +432,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         }
         dV0 += d0;
         dV1 += 0.5 * d1;
-        for (int q = 0; q < D; ++q) {
+        for (int q = r; q < D; q += G) {  // this lane's rows; the group maximum is formed after the sweep
           inf_pr = fmax(inf_pr, fabs(prim[q]));
           inf_comp = fmax(inf_comp, fabs(ys[q] * ss[q] - mu));
         }
@@ -436,27 +490,28 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
     }
   }
 
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    inf_pr = fmax(inf_pr, __shfl_xor_sync(0xffffffffu, inf_pr, o));
+    inf_comp = fmax(inf_comp, __shfl_xor_sync(0xffffffffu, inf_comp, o));
+  }
   // linearised slack / dual steps and the fraction-to-boundary step caps: rolloutLinearPolicy from dx0 = 0 (:368-392),
   // dS = k_s + K_s dX, dY = clamp(k_y + K_y dX) (:1516-1538), computeMaxStepSizes (:2939-2988)
   double apm = 1.0, adm = 1.0;
   const bool roll = ok && D > 0;
   if (__any_sync(0xffffffffu, roll)) {
     const double tau_b = fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);
-    // staging block of the rollout: record | k_s | k_y | S | Y | K_s | K_y | K | k of one timestep
-    const int oKs = rs, oKy = oKs + D, oS = oKy + D, oY = oS + D, oKS = oY + D, oKY = oKS + D * n, oK = oKY + D * n, ok_ = oK + m * n;
+    // Phase 1 (sequential in t, tiny): dx_{t+1} = A dx_t + B (k + K dx_t), staged record | K | k one step ahead; every
+    // dx_t goes to a scratch row in HBM.  The scratch is the instance's CANDIDATE state buffer X[cur ^ 1]: nothing reads it
+    // between this sweep and the forward pass, which rewrites it.
+    // Phase 2 (parallel over (t, row), streaming): the slack / dual steps and their fraction-to-boundary caps.  K_s, K_y
+    // (2 d n doubles per timestep) are read straight from HBM by consecutive lanes instead of being staged per timestep —
+    // staging them made the group's shared-memory block 1.8x larger than the sweep itself needs.
+    const int oK = rs, ok_ = oK + m * n;
+    double *dxs = d.X[cur ^ 1] + (size_t)bb * (N + 1) * n;
     auto issue_roll = [&](int tt, int x) {
       double *dst = stg + x * blk;
       for (int i = r; i < rs; i += G) cp_async8(dst + i, grec + (size_t)tt * rs + i);
-      for (int i = r; i < D; i += G) {
-        cp_async8(dst + oKs + i, gks + (size_t)tt * D + i);
-        cp_async8(dst + oKy + i, gky + (size_t)tt * D + i);
-        cp_async8(dst + oS + i, gS + (size_t)tt * D + i);
-        cp_async8(dst + oY + i, gY + (size_t)tt * D + i);
-      }
-      for (int i = r; i < D * n; i += G) {
-        cp_async8(dst + oKS + i, gKs + (size_t)tt * D * n + i);
-        cp_async8(dst + oKY + i, gKy + (size_t)tt * D * n + i);
-      }
       for (int i = r; i < m * n; i += G) cp_async8(dst + oK + i, gK + (size_t)tt * m * n + i);
       for (int i = r; i < m; i += G) cp_async8(dst + ok_ + i, gk + (size_t)tt * m + i);
     };
@@ -472,17 +527,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       const double *st_ = stg + bi * blk;
       const double *A = st_, *Bm = st_ + n * n;
       if (roll) {
-        for (int q = r; q < D; q += G) {
-          double a1 = 0.0, a2 = 0.0;
-          for (int j = 0; j < n; ++j) {
-            a1 += st_[oKS + q * n + j] * dx[j];
-            a2 += st_[oKY + q * n + j] * dx[j];
-          }
-          const double ds = __dadd_rn(st_[oKs + q], a1);
-          const double dy = clampd(__dadd_rn(st_[oKy + q], a2), -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
-          if (ds < 0.0) apm = fmin(apm, __ddiv_rn(__dmul_rn(-tau_b, st_[oS + q]), ds));
-          if (dy < 0.0) adm = fmin(adm, __ddiv_rn(__dmul_rn(-tau_b, st_[oY + q]), dy));
-        }
+        for (int i = r; i < n; i += G) dxs[(size_t)t * n + i] = dx[i];
         for (int i = r; i < m; i += G) {
           double acc = 0.0;
           for (int j = 0; j < n; ++j) acc += st_[oK + i * n + j] * dx[j];
@@ -502,6 +547,21 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         for (int i = r; i < n; i += G) dx[i] = dxn[i];
       cp_async_wait_all();
       __syncwarp();
+    }
+    if (roll) {
+      for (int idx = r; idx < N * D; idx += G) {
+        const int t = idx / D;
+        const double *ksr = gKs + (size_t)idx * n, *kyr = gKy + (size_t)idx * n, *dxt = dxs + (size_t)t * n;
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = 0; j < n; ++j) {
+          a1 += ksr[j] * dxt[j];
+          a2 += kyr[j] * dxt[j];
+        }
+        const double ds = __dadd_rn(gks[idx], a1);
+        const double dy = clampd(__dadd_rn(gky[idx], a2), -MAX_BARRIER_RATIO, MAX_BARRIER_RATIO);
+        if (ds < 0.0) apm = fmin(apm, __ddiv_rn(__dmul_rn(-tau_b, gS[idx]), ds));
+        if (dy < 0.0) adm = fmin(adm, __ddiv_rn(__dmul_rn(-tau_b, gY[idx]), dy));
+      }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -618,6 +678,7 @@ cudaError_t launch_ip_backward(const Constants &c, const DeviceState &d, const I
   if (d.n == 3 && d.m == 2) return launch_ip_backward_g<16, 3, 2>(c, d, ic, ip, mode, st);
   if (d.n == 4 && d.m == 1) return launch_ip_backward_g<8, 4, 1>(c, d, ic, ip, mode, st);
   if (d.n == 13 && d.m == 4) return launch_ip_backward_g<32, 13, 4>(c, d, ic, ip, mode, st);
+  if (d.n == 14 && d.m == 7) return launch_ip_backward_g<32, 14, 7>(c, d, ic, ip, mode, st);
   if (d.n * (d.n + d.m) <= 24) return launch_ip_backward_g<8, 0, 0>(c, d, ic, ip, mode, st);
   if (d.n * (d.n + d.m) <= 64) return launch_ip_backward_g<16, 0, 0>(c, d, ic, ip, mode, st);
   return launch_ip_backward_g<32, 0, 0>(c, d, ic, ip, mode, st);

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   __syncthreads();
   const int grp = lane / LG, al = lane % LG;
   const int b = (blockIdx.x * kWarpsPerCta + warp) * TPW + grp;
-  const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+  const bool alive = b < d.B && !(mode == FW_ITERATE && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.fw_done[b]));
   if (!__any_sync(0xffffffffu, alive)) return;
   const int bb = alive ? b : 0;
 
@@ -265,6 +265,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
     }
   }
   if (alive && al == 0) finish_line_search(c, d, b, mode, first, Jacc);
+}
+
+// Speculative first step of the sequential line search (cddp_solver_base.cpp:255-263: the FIRST accepted alpha wins, so
+// when alphas_[0] is accepted the other candidates are never looked at).  One LANE per trajectory rolls alphas_[0] out,
+// writes the candidate trajectory and, if the Armijo test passes, settles the instance (fw_done = 1); forward_kernel
+// then runs only for the instances that are left.  Worth it when the rollout is throughput-bound (a user model with
+// transcendental-heavy dynamics at a large batch: 16 lock-step lanes per trajectory cost 16 rollouts, of which a
+// well-conditioned problem needs one); launched for CDDP_B200_MODEL_USER handles with enable_parallel = false.
+template <int MODEL, bool DIAG>
+__global__ void __launch_bounds__(64) forward_first_kernel(Constants c, DeviceState d, int mode) {
+  constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
+  constexpr int QN = DIAG ? NS : NS * NS, RN = DIAG ? NC : NC * NC;
+  __shared__ double sQ[QN], sR[RN], sQf[QN];
+  for (int i = threadIdx.x; i < QN; i += blockDim.x) {
+    const int src = DIAG ? i * NS + i : i;
+    sQ[i] = 0.5 * c.Qdt2[src];
+    sQf[i] = 0.5 * c.Qf2[src];
+  }
+  for (int i = threadIdx.x; i < RN; i += blockDim.x) sR[i] = 0.5 * c.Rdt2[DIAG ? i * NC + i : i];
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  d.fw_done[b] = 0;
+  if (d.status[b] != CDDP_B200_STATUS_RUNNING) return;
+  const int N = d.N, cur = d.cur[b];
+  const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS;
+  const double *Un = d.U[cur] + (size_t)b * N * NC;
+  double *Xc = d.X[cur ^ 1] + (size_t)b * (N + 1) * NS;
+  double *Uc = d.U[cur ^ 1] + (size_t)b * N * NC;
+  const double *gK = d.K + (size_t)b * N * NC * NS;
+  const double *gk = d.kff + (size_t)b * N * NC;
+  const double *xref = d.xref + (size_t)b * NS;
+  const double *rtraj = d.ref_traj ? d.ref_traj + (size_t)b * (N + 1) * NS : nullptr;
+  const double alpha = c.alphas[0];
+  double x[NS], u[NC], xn[NS], J = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+  for (int t = 0; t < N; ++t) {
+    // same arithmetic, in the same order, as forward_kernel's advance()
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) acc += gK[((size_t)t * NC + i) * NS + j] * (x[j] - Xn[(size_t)t * NS + j]);
+      u[i] = Un[(size_t)t * NC + i] + alpha * gk[(size_t)t * NC + i] + acc;
+    }
+    if (c.has_box) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) u[i] = fmin(fmax(u[i], c.lb[i]), c.ub[i]);
+    }
+    {
+      const double *ref = rtraj ? rtraj + (size_t)t * NS : xref;
+      double e[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
+      J += quad_form<NS, DIAG>(sQ, e) + quad_form<NC, DIAG>(sR, u);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Xc[(size_t)t * NS + i] = x[i];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) Uc[(size_t)t * NC + i] = u[i];
+    discrete_step<MODEL>(c.mp, c.integrator, c.dt, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = xn[i];
+  }
+  {
+    double e[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      Xc[(size_t)N * NS + i] = x[i];
+      e[i] = x[i] - xref[i];
+    }
+    J += quad_form<NS, DIAG>(sQf, e);
+  }
+  const double dJ = d.cost[b] - J;
+  const double expected = -alpha * (d.dV[2 * b] + 0.5 * alpha * d.dV[2 * b + 1]);
+  const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
+  d.ls_cost[(size_t)b * CDDP_B200_MAX_ALPHAS] = J;
+  if (ratio > c.opt.armijo_constant) {
+    finish_line_search(c, d, b, mode, 0, J);
+    d.fw_done[b] = 1;
+  }
 }
 
 }  // namespace kern

@@ -65,15 +65,21 @@ __device__ inline bool ldlt_small(double *a, int *tr, int n) {
 __device__ inline void ldlt_solve(const double *a, const int *tr, int n, double *b, int st) {
   for (int k = 0; k < n; ++k)
     if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < i; ++j) b[i * st] -= a[i * n + j] * b[j * st];
+  for (int i = 0; i < n; ++i) {  // running value in a register: the same subtractions in the same order, without a
+    double s = b[i * st];        // shared-memory store -> load round trip between them
+    for (int j = 0; j < i; ++j) s -= a[i * n + j] * b[j * st];
+    b[i * st] = s;
+  }
   const double tol = 2.2250738585072014e-308;  // numeric_limits<double>::min()
   for (int i = 0; i < n; ++i) {
     if (fabs(a[i * n + i]) > tol) b[i * st] /= a[i * n + i];
     else b[i * st] = 0.0;
   }
-  for (int i = n - 1; i >= 0; --i)
-    for (int j = i + 1; j < n; ++j) b[i * st] -= a[j * n + i] * b[j * st];
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i * st];
+    for (int j = i + 1; j < n; ++j) s -= a[j * n + i] * b[j * st];
+    b[i * st] = s;
+  }
   for (int k = n - 1; k >= 0; --k)
     if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
 }

@@ -27,58 +27,140 @@ namespace cddp_b200 {
 namespace ad {  // its own namespace: the math overloads below are found by argument-dependent lookup only, so that they never
                 // shadow ::sqrt / ::pow / ... for plain doubles inside the engine's kernels
 
-// forward-mode dual number, one tangent direction (stands in for autodiff::dual; first derivatives only: use_ilqr = true)
+// forward-mode dual number carrying CDDP_DUAL_WIDTH tangent directions at once (stands in for autodiff::dual; first
+// derivatives only: use_ilqr = true).  One direction per pass — what autodiff::jacobian does — re-evaluates every
+// sin/cos/exp of the model n+m times; W directions per pass evaluate them ceil((n+m)/W) times and pay only W
+// multiply-adds per operation for the tangents.  W = 3 keeps the live duals of a 14-state / 7-control model in registers.
+#ifndef CDDP_DUAL_WIDTH
+#define CDDP_DUAL_WIDTH 3
+#endif
 struct Dual {
-  double v, d;
-  __device__ Dual() : v(0.0), d(0.0) {}
-  __device__ Dual(double v_) : v(v_), d(0.0) {}
-  __device__ Dual(double v_, double d_) : v(v_), d(d_) {}
+  static constexpr int W = CDDP_DUAL_WIDTH;
+  double v, d[W];
+  __device__ Dual() : v(0.0) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) d[k] = 0.0;
+  }
+  __device__ Dual(double v_) : v(v_) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) d[k] = 0.0;
+  }
 };
-__device__ inline Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
-__device__ inline Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
-__device__ inline Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
-__device__ inline Dual operator+(Dual a) { return a; }
-__device__ inline Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
-__device__ inline Dual operator/(Dual a, Dual b) {
-  const double q = a.v / b.v;
-  return Dual(q, (a.d - q * b.d) / b.v);
+// f(a) with derivative fp: value fv, tangent fp * a.d
+__device__ __forceinline__ Dual chain(const Dual &a, double fv, double fp) {
+  Dual r;
+  r.v = fv;
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = fp * a.d[k];
+  return r;
 }
-__device__ inline Dual &operator+=(Dual &a, Dual b) { a = a + b; return a; }
-__device__ inline Dual &operator-=(Dual &a, Dual b) { a = a - b; return a; }
-__device__ inline Dual &operator*=(Dual &a, Dual b) { a = a * b; return a; }
-__device__ inline Dual &operator/=(Dual &a, Dual b) { a = a / b; return a; }
-__device__ inline bool operator<(Dual a, Dual b) { return a.v < b.v; }
-__device__ inline bool operator>(Dual a, Dual b) { return a.v > b.v; }
-__device__ inline bool operator<=(Dual a, Dual b) { return a.v <= b.v; }
-__device__ inline bool operator>=(Dual a, Dual b) { return a.v >= b.v; }
-__device__ inline Dual sin(Dual a) { return Dual(::sin(a.v), ::cos(a.v) * a.d); }
-__device__ inline Dual cos(Dual a) { return Dual(::cos(a.v), -::sin(a.v) * a.d); }
-__device__ inline Dual tan(Dual a) {
+__device__ inline Dual operator+(const Dual &a, const Dual &b) {
+  Dual r;
+  r.v = a.v + b.v;
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = a.d[k] + b.d[k];
+  return r;
+}
+__device__ inline Dual operator-(const Dual &a, const Dual &b) {
+  Dual r;
+  r.v = a.v - b.v;
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = a.d[k] - b.d[k];
+  return r;
+}
+__device__ inline Dual operator-(const Dual &a) { return chain(a, -a.v, -1.0); }
+__device__ inline Dual operator+(const Dual &a) { return a; }
+__device__ inline Dual operator*(const Dual &a, const Dual &b) {
+  Dual r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k];
+  return r;
+}
+__device__ inline Dual operator/(const Dual &a, const Dual &b) {
+  Dual r;
+  const double ib = 1.0 / b.v, q = a.v * ib;
+  r.v = a.v / b.v;
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = (a.d[k] - q * b.d[k]) * ib;
+  return r;
+}
+// mixed double / Dual arithmetic without promoting the scalar to a dual with W zero tangents
+__device__ inline Dual operator+(const Dual &a, double b) { Dual r = a; r.v += b; return r; }
+__device__ inline Dual operator+(double a, const Dual &b) { Dual r = b; r.v += a; return r; }
+__device__ inline Dual operator-(const Dual &a, double b) { Dual r = a; r.v -= b; return r; }
+__device__ inline Dual operator-(double a, const Dual &b) { return chain(b, a - b.v, -1.0); }
+__device__ inline Dual operator*(const Dual &a, double b) { return chain(a, a.v * b, b); }
+__device__ inline Dual operator*(double a, const Dual &b) { return chain(b, a * b.v, a); }
+__device__ inline Dual operator/(const Dual &a, double b) {
+  Dual r = chain(a, 0.0, 1.0 / b);
+  r.v = a.v / b;
+  return r;
+}
+__device__ inline Dual operator/(double a, const Dual &b) {
+  const double q = a / b.v;
+  return chain(b, q, -q / b.v);
+}
+__device__ inline Dual &operator+=(Dual &a, const Dual &b) { a = a + b; return a; }
+__device__ inline Dual &operator-=(Dual &a, const Dual &b) { a = a - b; return a; }
+__device__ inline Dual &operator*=(Dual &a, const Dual &b) { a = a * b; return a; }
+__device__ inline Dual &operator/=(Dual &a, const Dual &b) { a = a / b; return a; }
+__device__ inline Dual &operator+=(Dual &a, double b) { a.v += b; return a; }
+__device__ inline Dual &operator-=(Dual &a, double b) { a.v -= b; return a; }
+__device__ inline Dual &operator*=(Dual &a, double b) { a = a * b; return a; }
+__device__ inline Dual &operator/=(Dual &a, double b) { a = a / b; return a; }
+__device__ inline bool operator<(const Dual &a, const Dual &b) { return a.v < b.v; }
+__device__ inline bool operator>(const Dual &a, const Dual &b) { return a.v > b.v; }
+__device__ inline bool operator<=(const Dual &a, const Dual &b) { return a.v <= b.v; }
+__device__ inline bool operator>=(const Dual &a, const Dual &b) { return a.v >= b.v; }
+__device__ inline bool operator<(const Dual &a, double b) { return a.v < b; }
+__device__ inline bool operator>(const Dual &a, double b) { return a.v > b; }
+__device__ inline bool operator<=(const Dual &a, double b) { return a.v <= b; }
+__device__ inline bool operator>=(const Dual &a, double b) { return a.v >= b; }
+__device__ inline bool operator<(double a, const Dual &b) { return a < b.v; }
+__device__ inline bool operator>(double a, const Dual &b) { return a > b.v; }
+__device__ inline bool operator<=(double a, const Dual &b) { return a <= b.v; }
+__device__ inline bool operator>=(double a, const Dual &b) { return a >= b.v; }
+__device__ inline Dual sin(const Dual &a) {
+  double sn, cs;
+  ::sincos(a.v, &sn, &cs);
+  return chain(a, sn, cs);
+}
+__device__ inline Dual cos(const Dual &a) {
+  double sn, cs;
+  ::sincos(a.v, &sn, &cs);
+  return chain(a, cs, -sn);
+}
+__device__ inline Dual tan(const Dual &a) {
   const double t = ::tan(a.v);
-  return Dual(t, (1.0 + t * t) * a.d);
+  return chain(a, t, 1.0 + t * t);
 }
-__device__ inline Dual sqrt(Dual a) {
+__device__ inline Dual sqrt(const Dual &a) {
   const double r = ::sqrt(a.v);
-  return Dual(r, a.d / (2.0 * r));
+  return chain(a, r, 1.0 / (2.0 * r));
 }
-__device__ inline Dual exp(Dual a) {
+__device__ inline Dual exp(const Dual &a) {
   const double e = ::exp(a.v);
-  return Dual(e, e * a.d);
+  return chain(a, e, e);
 }
-__device__ inline Dual log(Dual a) { return Dual(::log(a.v), a.d / a.v); }
-__device__ inline Dual tanh(Dual a) {
+__device__ inline Dual log(const Dual &a) { return chain(a, ::log(a.v), 1.0 / a.v); }
+__device__ inline Dual tanh(const Dual &a) {
   const double t = ::tanh(a.v);
-  return Dual(t, (1.0 - t * t) * a.d);
+  return chain(a, t, 1.0 - t * t);
 }
-__device__ inline Dual atan(Dual a) { return Dual(::atan(a.v), a.d / (1.0 + a.v * a.v)); }
-__device__ inline Dual asin(Dual a) { return Dual(::asin(a.v), a.d / ::sqrt(1.0 - a.v * a.v)); }
-__device__ inline Dual acos(Dual a) { return Dual(::acos(a.v), -a.d / ::sqrt(1.0 - a.v * a.v)); }
-__device__ inline Dual atan2(Dual y, Dual x) {
-  const double r2 = x.v * x.v + y.v * y.v;
-  return Dual(::atan2(y.v, x.v), (x.v * y.d - y.v * x.d) / r2);
+__device__ inline Dual atan(const Dual &a) { return chain(a, ::atan(a.v), 1.0 / (1.0 + a.v * a.v)); }
+__device__ inline Dual asin(const Dual &a) { return chain(a, ::asin(a.v), 1.0 / ::sqrt(1.0 - a.v * a.v)); }
+__device__ inline Dual acos(const Dual &a) { return chain(a, ::acos(a.v), -1.0 / ::sqrt(1.0 - a.v * a.v)); }
+__device__ inline Dual atan2(const Dual &y, const Dual &x) {
+  const double ir2 = 1.0 / (x.v * x.v + y.v * y.v);
+  Dual r;
+  r.v = ::atan2(y.v, x.v);
+#pragma unroll
+  for (int k = 0; k < Dual::W; ++k) r.d[k] = (x.v * y.d[k] - y.v * x.d[k]) * ir2;
+  return r;
 }
-__device__ inline Dual pow(Dual a, double e) { return Dual(::pow(a.v, e), e * ::pow(a.v, e - 1.0) * a.d); }
-__device__ inline Dual fabs(Dual a) { return a.v < 0.0 ? -a : a; }
+__device__ inline Dual pow(const Dual &a, double e) { return chain(a, ::pow(a.v, e), e * ::pow(a.v, e - 1.0)); }
+__device__ inline Dual fabs(const Dual &a) { return a.v < 0.0 ? -a : a; }
 
 }  // namespace ad
 using ad::Dual;
@@ -105,21 +187,31 @@ struct Model<CDDP_B200_MODEL_USER> {
 #ifdef CDDP_USER_HAS_JACOBIAN
     cddp_user_jacobian(x, u, P.p, Fx, Fu);
 #else
-    Dual xs[NS], us[NC], xd[NS];
+    constexpr int W = Dual::W;
+#pragma unroll 1
+    for (int base = 0; base < NS + NC; base += W) {  // W tangent directions per pass (autodiff::jacobian, dynamical_system.cpp:102-133)
+      Dual xs[NS], us[NC], xd[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) xs[i] = Dual(x[i]);
+      for (int i = 0; i < NS; ++i) {
+        xs[i].v = x[i];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) us[i] = Dual(u[i]);
-    for (int dir = 0; dir < NS + NC; ++dir) {  // one tangent direction per pass (autodiff::jacobian, dynamical_system.cpp:102-133)
-      if (dir < NS) xs[dir].d = 1.0;
-      else us[dir - NS].d = 1.0;
+        for (int k = 0; k < W; ++k) xs[i].d[k] = (i == base + k) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        us[i].v = u[i];
+#pragma unroll
+        for (int k = 0; k < W; ++k) us[i].d[k] = (NS + i == base + k) ? 1.0 : 0.0;
+      }
       cddp_user_dynamics<Dual>(xs, us, P.p, xd);
-      if (dir < NS) {
-        xs[dir].d = 0.0;
-        for (int i = 0; i < NS; ++i) Fx[i * NS + dir] = xd[i].d;
-      } else {
-        us[dir - NS].d = 0.0;
-        for (int i = 0; i < NS; ++i) Fu[i * NC + (dir - NS)] = xd[i].d;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int dir = base + k;
+        if (dir < NS) {
+          for (int i = 0; i < NS; ++i) Fx[i * NS + dir] = xd[i].d[k];
+        } else if (dir < NS + NC) {
+          for (int i = 0; i < NS; ++i) Fu[i * NC + (dir - NS)] = xd[i].d[k];
+        }
       }
     }
 #endif

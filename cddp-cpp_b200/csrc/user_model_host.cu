@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -110,7 +112,7 @@ Driver *driver(std::string &err) {
   return &lib;
 }
 
-enum { K_LIN = 0, K_FWD16, K_FWD32, K_IPINIT, K_IPFWD, K_COUNT };
+enum { K_LIN = 0, K_FWD16, K_FWD32, K_FWD1, K_IPINIT, K_IPFWD, K_COUNT };
 
 std::string name_expr(int k, bool diag) {
   const char *d = diag ? "true" : "false";
@@ -118,6 +120,7 @@ std::string name_expr(int k, bool diag) {
     case K_LIN: return "cddp_b200::kern::linearize_kernel<CDDP_B200_MODEL_USER, cddp_b200::DensePattern>";
     case K_FWD16: return std::string("cddp_b200::kern::forward_kernel<CDDP_B200_MODEL_USER, 16, ") + d + ">";
     case K_FWD32: return std::string("cddp_b200::kern::forward_kernel<CDDP_B200_MODEL_USER, 32, ") + d + ">";
+    case K_FWD1: return std::string("cddp_b200::kern::forward_first_kernel<CDDP_B200_MODEL_USER, ") + d + ">";
     case K_IPINIT: return "cddp_b200::kern::ip_initialize_kernel<CDDP_B200_MODEL_USER>";
     default: return "cddp_b200::kern::ip_forward_kernel<CDDP_B200_MODEL_USER, 0>";
   }
@@ -181,6 +184,12 @@ static int compile_user_model(const char *source, int n, int m, bool diag, std::
   rt->GetCUBINSize(prog, &sz);
   cubin.resize(sz);
   rt->GetCUBIN(prog, cubin.data());
+  if (const char *dump = getenv("CDDP_B200_DUMP_CUBIN")) {  // developer aid: cuobjdump -res-usage / -sass on the JIT result
+    if (FILE *f = fopen(dump, "wb")) {
+      fwrite(cubin.data(), 1, cubin.size(), f);
+      fclose(f);
+    }
+  }
   for (int k = 0; k < K_COUNT; ++k) {
     const char *low = nullptr;
     if (rt->GetLoweredName(prog, names[k].c_str(), &low) != NVRTC_SUCCESS || !low) {
@@ -273,6 +282,10 @@ cudaError_t launch_user_forward(const Constants &c, const DeviceState &d, int mo
   if (!uk || (c.cost_diag != 0) != uk->diag) return cudaErrorInvalidValue;
   const int wpc = 2;  // kern::kWarpsPerCta
   void *params[] = {(void *)&c, (void *)&d, &mode};
+  if (mode == FW_ITERATE && !c.opt.enable_parallel) {  // speculative alphas_[0] first (kernels_forward.cuh)
+    cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.B + 63) / 64), 64, 0, st, params);
+    if (e != cudaSuccess) return e;
+  }
   if (c.num_alphas <= 16) return launch(uk, K_FWD16, (unsigned)((d.B + wpc * 2 - 1) / (wpc * 2)), wpc * 32, 0, st, params);
   return launch(uk, K_FWD32, (unsigned)((d.B + wpc - 1) / wpc), wpc * 32, 0, st, params);
 }
