@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
 // Speculative first step of the sequential line search (cddp_solver_base.cpp:255-263: the FIRST accepted alpha wins, so
 // when alphas_[0] is accepted the other candidates are never looked at).  One LANE per trajectory rolls alphas_[0] out,
 // writes the candidate trajectory and, if the Armijo test passes, settles the instance (fw_done = 1); forward_kernel
-// then runs only for the instances that are left.  Worth it when the rollout is throughput-bound (a user model with
+// then runs only for the instances that are left (same decisions, same trajectories: the candidate it would have picked is
+// the one written here).  Worth it when the rollout is throughput-bound (a user model with
 // transcendental-heavy dynamics at a large batch: 16 lock-step lanes per trajectory cost 16 rollouts, of which a
 // well-conditioned problem needs one); launched for CDDP_B200_MODEL_USER handles with enable_parallel = false.
 template <int MODEL, bool DIAG>
@@ -289,6 +290,9 @@ __global__ void __launch_bounds__(64) forward_first_kernel(Constants c, DeviceSt
   if (b >= d.B) return;
   d.fw_done[b] = 0;
   if (d.status[b] != CDDP_B200_STATUS_RUNNING) return;
+  // speculate only where it is likely to pay: the instance's previous line search accepted alphas_[0] (or this is its
+  // first iteration).  After a backtracked or failed line search the full kernel runs alone until alphas_[0] wins again.
+  if (!(d.iter[b] <= 1 || d.accepted[b] == 0)) return;
   const int N = d.N, cur = d.cur[b];
   const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS;
   const double *Un = d.U[cur] + (size_t)b * N * NC;

@@ -266,16 +266,25 @@ struct TrialStats {
 // One rollout of IPDDPSolver::forwardPass (:1597-1751) for step sizes (alpha_pr, alpha_du), executed by ALL lanes of a
 // 16-lane group in lock-step (one alpha per lane in pass 1, the accepted alpha replicated in pass 2).  The per-timestep
 // operands x_nom | u_nom | k | K | S | Y | k_s | k_y | K_s | K_y are shared by the group's lanes: they are staged through a
-// double-buffered shared-memory block with asynchronous copies one timestep ahead.  WRITE && wr: store the trial
+// double-buffered shared-memory block with asynchronous copies one timestep ahead.  wr: store the trial
 // trajectory, slacks, duals and constraint values into the candidate buffers.
 __host__ __device__ inline int ip_fw_step_doubles(int n, int m, int D) {
   return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1;
 }
 
-template <int MODEL, bool WRITE, int DC>
+//
+// segment = false (pass 1, warp-uniform): the whole horizon from x0, operands staged as above; with save_ck the state
+// entering every `seg`-step segment is saved to the line-search scratch (d.ckpt).  segment = true (pass 2): this lane
+// alone replays timesteps [t0, t1) of the accepted trial from the saved state `xstart`, reading its operands straight
+// from HBM (the lanes of the group are at different timesteps), and with wr writes that part of the candidate — 1/16 of a
+// rollout in latency instead of a second full one.  The flags are RUN-TIME values and the kernel calls this function
+// from ONE call site (a two-trip loop): both passes execute the same machine code, so the trajectory written by pass 2 is
+// bit-for-bit the one whose merit pass 1 judged (two template instantiations were seen to differ in FMA contraction).
+template <int MODEL, int DC>
 __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
                                            const ConTable &ctab, int b, int cur, double alpha_pr, double alpha_du, double tau,
-                                           double mu, TrialStats &st, double *stage, int al, bool wr) {
+                                           double mu, TrialStats &st, double *stage, int al, bool wr, bool save_ck,
+                                           bool segment, int t0, int t1, const double *xstart) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC, LG = 16;
   const int N = d.N, D = DC ? DC : ic.d;
   const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
@@ -308,27 +317,48 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       cp_async8(dst + oKy + i, gKy + (size_t)tt * D * NS + i);
     }
   };
-  issue(0, 0);
-  cp_async_wait_all();
-  __syncwarp();
+  if (!segment) {
+    issue(0, 0);
+    cp_async_wait_all();
+    __syncwarp();
+  }
   double x[NS], xn[NS], u[NC], dxv[NS];
+  {
+    const double *xs0 = segment ? xstart : d.x0 + (size_t)b * NS;
 #pragma unroll
-  for (int i = 0; i < NS; ++i) x[i] = d.x0[(size_t)b * NS + i];
+    for (int i = 0; i < NS; ++i) x[i] = xs0[i];
+  }
+  const int seg = (N + LG - 1) / LG;
+  double *ck = d.ckpt + ((size_t)b * LG + al) * LG * NS;  // this lane's saved states [LG][NS]
   st.cost = 0.0; st.logsum = 0.0; st.theta = 0.0; st.inf_pr = 0.0; st.maxys = -pos_inf(); st.minys = pos_inf();
   LogProduct lprod;
   st.feasible = true;
   bool feas = true;
-  for (int t = 0; t < N; ++t) {
-    if (t + 1 < N) issue(t + 1, (t + 1) & 1);
-    const double *sg = stage + (t & 1) * blk;
+  for (int t = t0; t < t1; ++t) {
+    const double *pX, *pU, *pk, *pK, *pS, *pY, *pks, *pky, *pKs, *pKy;
+    if (segment) {
+      pX = Xn + (size_t)t * NS; pU = Un + (size_t)t * NC; pk = gk + (size_t)t * NC; pK = gK + (size_t)t * NC * NS;
+      pS = S0 + (size_t)t * D; pY = Y0 + (size_t)t * D; pks = gks + (size_t)t * D; pky = gky + (size_t)t * D;
+      pKs = gKs + (size_t)t * D * NS; pKy = gKy + (size_t)t * D * NS;
+    } else {
+      if (t + 1 < N) issue(t + 1, (t + 1) & 1);
+      const double *sg = stage + (t & 1) * blk;
+      pX = sg; pU = sg + oU; pk = sg + ok_; pK = sg + oK; pS = sg + oS; pY = sg + oY; pks = sg + oks; pky = sg + oky;
+      pKs = sg + oKs; pKy = sg + oKy;
+      if (save_ck && t % seg == 0) {
+        double *dst = ck + (size_t)(t / seg) * NS;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - sg[i];
+        for (int i = 0; i < NS; ++i) dst[i] = x[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dxv[i] = x[i] - pX[i];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {  // u' = u + alpha_pr k + K dx (no clamp) (:1650-1651)
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) acc += sg[oK + i * NS + j] * dxv[j];
-      u[i] = (sg[oU + i] + alpha_pr * sg[ok_ + i]) + acc;
+      for (int j = 0; j < NS; ++j) acc += pK[i * NS + j] * dxv[j];
+      u[i] = (pU[i] + alpha_pr * pk[i]) + acc;
     }
     double acc_t = 0.0;
     for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
@@ -336,32 +366,34 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       double a1 = 0.0, a2 = 0.0;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        a1 += sg[oKs + q * NS + j] * dxv[j];
-        a2 += sg[oKy + q * NS + j] * dxv[j];
+        a1 += pKs[q * NS + j] * dxv[j];
+        a2 += pKy[q * NS + j] * dxv[j];
       }
-      const double s0 = sg[oS + q], y0 = sg[oY + q];
+      const double s0 = pS[q], y0 = pY[q];
       // No FMA contraction here: with alpha_pr at its fraction-to-boundary cap and dx = 0 (t = 0) the test below compares
       // s + alpha ds against (1 - tau) s, which are EQUAL in exact arithmetic — the reference's decision is then made by
       // the rounding of exactly these two operations (:1623-1630), so they are reproduced operation by operation.
-      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, sg[oks + q])), a1);
-      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, sg[oky + q])), a2);
+      const double sn = __dadd_rn(__dadd_rn(s0, __dmul_rn(alpha_pr, pks[q])), a1);
+      const double yn = __dadd_rn(__dadd_rn(y0, __dmul_rn(alpha_du, pky[q])), a2);
       if (sn < __dmul_rn(1.0 - tau, s0) || yn < __dmul_rn(1.0 - tau, y0)) feas = false;
       if (!finite_d(sn) || !finite_d(yn)) feas = false;
       const double g = con_value(ctab, q, NS, NC, x, u);  // (:1743-1748)
-      const double res = g + sn;
-      acc_t += l2 ? res * res : fabs(res);
-      st.inf_pr = fmax(st.inf_pr, fabs(res));
-      lprod.mul(fmax(sn, EPS_SLACK));
-      st.maxys = fmax(st.maxys, yn * sn);
-      st.minys = fmin(st.minys, yn * sn);
-      if (WRITE && wr) {
+      if (!segment) {  // the trial's statistics are those of pass 1
+        const double res = g + sn;
+        acc_t += l2 ? res * res : fabs(res);
+        st.inf_pr = fmax(st.inf_pr, fabs(res));
+        lprod.mul(fmax(sn, EPS_SLACK));
+        st.maxys = fmax(st.maxys, yn * sn);
+        st.minys = fmin(st.minys, yn * sn);
+      }
+      if (wr) {
         Sc[e] = sn;
         Yc[e] = yn;
         Gc[e] = g;
       }
     }
     st.theta += acc_t;
-    {  // running cost (:1741)
+    if (!segment) {  // running cost (:1741)
       const double *ref = ref_ptr(d, b, t);
       double sx = 0.0, su = 0.0;
 #pragma unroll
@@ -380,7 +412,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       }
       st.cost += sx + su;
     }
-    if (WRITE && wr) {
+    if (wr) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) Xc[(size_t)t * NS + i] = x[i];
 #pragma unroll
@@ -395,8 +427,17 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 #pragma unroll
     for (int i = 0; i < NC; ++i)
       if (!finite_d(u[i])) feas = false;
-    cp_async_wait_all();  // the next step's operands have landed; every lane is done with this step's buffer
-    __syncwarp();
+    if (!segment) {
+      cp_async_wait_all();  // the next step's operands have landed; every lane is done with this step's buffer
+      __syncwarp();
+    }
+  }
+  if (segment) {
+    if (wr && t1 == N) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
+    }
+    return;
   }
   {
     const double *ref = d.xref + (size_t)b * NS;
@@ -409,10 +450,6 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       sx += rr * (x[j] - ref[j]);
     }
     st.cost += sx;
-  }
-  if (WRITE && wr) {
-#pragma unroll
-    for (int i = 0; i < NS; ++i) Xc[(size_t)N * NS + i] = x[i];
   }
   st.logsum = lprod.log_value();
   st.lamh = 0.0;
@@ -427,7 +464,6 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       acc += l2 ? h * h : fabs(h);
       st.inf_pr = fmax(st.inf_pr, fabs(h));
       dot += ln * h;
-      if (WRITE && wr) ip.lamT[(size_t)b * NS + i] = ln;
     }
     st.theta += acc;
     st.lamh = dot;
@@ -469,70 +505,97 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double tau = ic.nc == 0 ? 1.0 : fmax(ic.io.min_fraction_to_boundary, 1.0 - mu);  // (:1585-1588)
   const double alpha_pr = fmin(alpha, ip.apm[bb]), alpha_du = fmin(alpha, ip.adm[bb]);
   TrialStats st;
-  ip_rollout<MODEL, false, DC>(c, d, ic, ip, ctab, bb, cur, alpha_pr, alpha_du, tau, mu, st, stage, al, false);
   const double cost_old = d.cost[bb], merit_old = ip.merit[bb];
-  const double phi_new = (st.cost - mu * st.logsum) + st.lamh;  // computeBarrierMerit (:2850-2880)
-  const double theta_new = st.theta;
-  const double inf_comp_new = D ? fmax(st.maxys - mu, mu - st.minys) : 0.0;
-  bool accept = false;
-  if (st.feasible && finite_d(phi_new) && finite_d(theta_new) && finite_d(st.inf_pr) && finite_d(inf_comp_new)) {
-    if (ic.nc == 0 && !ic.teq) {  // (:1785-1794)
-      const double dJ = cost_old - st.cost;
-      const double expected = -alpha_pr * (d.dV[2 * bb] + 0.5 * alpha_pr * d.dV[2 * bb + 1]);
-      const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
-      accept = ratio > 1e-6;
-    } else {  // filter acceptance (:1796-1839)
-      const double expected_improvement = alpha_pr * d.dV[2 * bb];
-      const int fs = ip.filter_size[bb];
-      const double cv_old = fs ? ip.filter[((size_t)bb * IP_FILTER_CAP + (fs - 1)) * 2 + 1] : 0.0;
-      const double high_ref = fs ? cv_old : ip.filter_theta[bb];
-      if (theta_new > ic.io.max_violation_threshold) {
-        accept = theta_new < (1 - ic.io.violation_acceptance_threshold) * high_ref;
-      } else if (fmax(theta_new, cv_old) < ic.io.min_violation_for_armijo_check && expected_improvement < 0) {
-        accept = phi_new < merit_old + c.opt.armijo_constant * expected_improvement;
-      } else {
-        accept = phi_new < merit_old - ic.io.merit_acceptance_threshold * theta_new ||
-                 theta_new < (1 - ic.io.violation_acceptance_threshold) * cv_old;
+  int first = -1;
+  double a_pr = 0.0, a_du = 0.0, cost_new = 0.0, logsum_new = 0.0, th_new = 0.0, ipr_new = 0.0, maxys = 0.0, minys = 0.0,
+         phi_acc = 0.0, lamh_new = 0.0;
+  // arguments of the rollout: pass 0 = this lane's alpha over the whole horizon, pass 1 = this lane's segment of the
+  // accepted trial (see ip_rollout: one call site, so both passes run the same machine code)
+  double r_apr = alpha_pr, r_adu = alpha_du;
+  bool r_run = true, r_wr = false, r_ck = alive, r_seg = false;
+  int r_t0 = 0, r_t1 = d.N;
+  const double *r_xs = nullptr;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (r_run) ip_rollout<MODEL, DC>(c, d, ic, ip, ctab, bb, cur, r_apr, r_adu, tau, mu, st, stage, al, r_wr, r_ck, r_seg, r_t0, r_t1, r_xs);
+    if (pass == 1) break;
+    const double phi_new = (st.cost - mu * st.logsum) + st.lamh;  // computeBarrierMerit (:2850-2880)
+    const double theta_new = st.theta;
+    const double inf_comp_new = D ? fmax(st.maxys - mu, mu - st.minys) : 0.0;
+    bool accept = false;
+    if (st.feasible && finite_d(phi_new) && finite_d(theta_new) && finite_d(st.inf_pr) && finite_d(inf_comp_new)) {
+      if (ic.nc == 0 && !ic.teq) {  // (:1785-1794)
+        const double dJ = cost_old - st.cost;
+        const double expected = -alpha_pr * (d.dV[2 * bb] + 0.5 * alpha_pr * d.dV[2 * bb + 1]);
+        const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
+        accept = ratio > 1e-6;
+      } else {  // filter acceptance (:1796-1839)
+        const double expected_improvement = alpha_pr * d.dV[2 * bb];
+        const int fs = ip.filter_size[bb];
+        const double cv_old = fs ? ip.filter[((size_t)bb * IP_FILTER_CAP + (fs - 1)) * 2 + 1] : 0.0;
+        const double high_ref = fs ? cv_old : ip.filter_theta[bb];
+        if (theta_new > ic.io.max_violation_threshold) {
+          accept = theta_new < (1 - ic.io.violation_acceptance_threshold) * high_ref;
+        } else if (fmax(theta_new, cv_old) < ic.io.min_violation_for_armijo_check && expected_improvement < 0) {
+          accept = phi_new < merit_old + c.opt.armijo_constant * expected_improvement;
+        } else {
+          accept = phi_new < merit_old - ic.io.merit_acceptance_threshold * theta_new ||
+                   theta_new < (1 - ic.io.violation_acceptance_threshold) * cv_old;
+        }
       }
     }
-  }
-  const bool success = active && accept;
-  int first;
-  if (!c.opt.enable_parallel) {  // sequential rule: the first accepted alpha (cddp_solver_base.cpp:255-263)
-    unsigned ballot = __ballot_sync(0xffffffffu, success);
-    ballot = (ballot >> (grp * LG)) & 0xffffu;
-    first = ballot ? (__ffs(ballot) - 1) : -1;
-  } else {  // enable_parallel: the accepted alpha with the strictly lowest merit, ties to the earlier one (:264-285)
-    double pm = success ? phi_new : pos_inf();
-    int idx = (success && phi_new < pos_inf()) ? al : 64;
+    const bool success = active && accept;
+    if (!c.opt.enable_parallel) {  // sequential rule: the first accepted alpha (cddp_solver_base.cpp:255-263)
+      unsigned ballot = __ballot_sync(0xffffffffu, success);
+      ballot = (ballot >> (grp * LG)) & 0xffffu;
+      first = ballot ? (__ffs(ballot) - 1) : -1;
+    } else {  // enable_parallel: the accepted alpha with the strictly lowest merit, ties to the earlier one (:264-285)
+      double pm = success ? phi_new : pos_inf();
+      int idx = (success && phi_new < pos_inf()) ? al : 64;
 #pragma unroll
-    for (int o = LG / 2; o > 0; o >>= 1) {
-      const double po = __shfl_xor_sync(0xffffffffu, pm, o);
-      const int io = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (po < pm || (po == pm && io < idx)) {
-        pm = po;
-        idx = io;
+      for (int o = LG / 2; o > 0; o >>= 1) {
+        const double po = __shfl_xor_sync(0xffffffffu, pm, o);
+        const int io = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (po < pm || (po == pm && io < idx)) {
+          pm = po;
+          idx = io;
+        }
       }
+      first = idx < 64 ? idx : -1;
     }
-    first = idx < 64 ? idx : -1;
+    if (alive && al < na) {
+      double *ls = ip.ls_stats + ((size_t)b * CDDP_B200_MAX_ALPHAS + al) * 4;
+      ls[0] = success ? 1.0 : 0.0;
+      ls[1] = st.cost;
+      ls[2] = phi_new;
+      ls[3] = theta_new;
+    }
+    const int src = grp * LG + (first >= 0 ? first : 0);
+    a_pr = __shfl_sync(0xffffffffu, alpha_pr, src);
+    a_du = __shfl_sync(0xffffffffu, alpha_du, src);
+    cost_new = __shfl_sync(0xffffffffu, st.cost, src);
+    logsum_new = __shfl_sync(0xffffffffu, st.logsum, src);
+    th_new = __shfl_sync(0xffffffffu, theta_new, src);
+    ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
+    maxys = __shfl_sync(0xffffffffu, st.maxys, src);
+    minys = __shfl_sync(0xffffffffu, st.minys, src);
+    phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
+    lamh_new = __shfl_sync(0xffffffffu, st.lamh, src);
+    __syncwarp();  // pass 1's saved states are visible to the other lanes of the group
+    // pass 2: write the accepted trial, one segment of the horizon per lane
+    const int seg = (d.N + LG - 1) / LG;
+    r_apr = a_pr;
+    r_adu = a_du;
+    r_seg = true;
+    r_wr = true;
+    r_ck = false;
+    r_t0 = al * seg;
+    r_t1 = min(r_t0 + seg, d.N);
+    r_xs = d.ckpt + (((size_t)bb * LG + (first >= 0 ? first : 0)) * LG + al) * NS_;
+    r_run = alive && first >= 0 && r_t0 < d.N;
   }
-  if (alive && al < na) {
-    double *ls = ip.ls_stats + ((size_t)b * CDDP_B200_MAX_ALPHAS + al) * 4;
-    ls[0] = success ? 1.0 : 0.0;
-    ls[1] = st.cost;
-    ls[2] = phi_new;
-    ls[3] = theta_new;
-  }
-  const int src = grp * LG + (first >= 0 ? first : 0);
-  const double a_pr = __shfl_sync(0xffffffffu, alpha_pr, src), a_du = __shfl_sync(0xffffffffu, alpha_du, src);
-  const double cost_new = __shfl_sync(0xffffffffu, st.cost, src), logsum_new = __shfl_sync(0xffffffffu, st.logsum, src);
-  const double th_new = __shfl_sync(0xffffffffu, theta_new, src), ipr_new = __shfl_sync(0xffffffffu, st.inf_pr, src);
-  const double maxys = __shfl_sync(0xffffffffu, st.maxys, src), minys = __shfl_sync(0xffffffffu, st.minys, src);
-  const double phi_acc = __shfl_sync(0xffffffffu, phi_new, src);
-  const double lamh_new = __shfl_sync(0xffffffffu, st.lamh, src);
-  if (__any_sync(0xffffffffu, alive && first >= 0)) {  // pass 2: replay the accepted trial (lane 0 of the group writes)
-    TrialStats s2;
-    ip_rollout<MODEL, true, DC>(c, d, ic, ip, ctab, bb, cur, a_pr, a_du, tau, mu, s2, stage, al, alive && first >= 0 && al == 0);
+  if (alive && first >= 0 && ic.teq && al == 0) {  // Lambda_T_eq_ += alpha_pr dLambda_T_eq_ (:1716-1723)
+    for (int i = 0; i < NS_; ++i) ip.lamT[(size_t)b * NS_ + i] = ip.lamT[(size_t)b * NS_ + i] + a_pr * ip.dlamT[(size_t)b * NS_ + i];
   }
   if (!(alive && al == 0)) return;
   d.accepted[b] = first;

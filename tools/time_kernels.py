@@ -1,5 +1,6 @@
 """Developer script: CUDA-event timings of the three kernels for a workload variant.
-usage: python tools/time_kernels.py [config] [batch] [--nobox] [--dense] [--iters K]"""
+usage: python tools/time_kernels.py [config] [batch] [--nobox] [--dense] [--iters K] [--cold]
+--cold: time the FIRST K iterations of the solve (default: iterations 4..K+3, after 3 untimed ones)"""
 import importlib
 import os
 import sys
@@ -27,7 +28,8 @@ def main():
                               cfg["constraints"], B)
         s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], cfg["ref_traj"])
         s.initialize()
-        s.iterate(3)
+        if "--cold" not in sys.argv:
+            s.iterate(3)
         s.enable_timing(True)
         s.reset_timing()
         s.iterate(K)
@@ -44,7 +46,8 @@ def main():
         s.set_record_layout("dense")
     s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"], cfg["ref_traj"])
     s.initialize()
-    s.iterate(3)
+    if "--cold" not in sys.argv:
+        s.iterate(3)
     s.enable_timing(True)
     s.reset_timing()
     s.iterate(K)
