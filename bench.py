@@ -216,6 +216,70 @@ def measure_ipddp(cddp, problems, device, with_cpu):
     return out
 
 
+def measure_user_solve(cddp, problems, device, name, B, cpu_sample, with_cpu):
+    """Secondary workload (not the bench line): the BASELINE config #5 stand-in — a 7-joint chain supplied through the
+    user-model plugin (CUDA source compiled by NVRTC at create time), n=14 m=7 N=150.  Measured as what a caller runs: ONE
+    solve() of the whole batch to the workload's own tolerances (instances stop when they converge), instance-iterations
+    actually performed / device time; the CPU oracle runs the same solves on a sample."""
+    import torch
+    cfg = problems.make_config(name, batch=B)
+    ip = cfg.get("solver") == "ipddp"
+    opts = cddp.default_options(**cfg["options"])
+    if ip:
+        s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(**cfg.get("ipddp_options", {})), cfg["constraints"], B,
+                              device=device)
+    else:
+        s = cddp.BatchedCLDDP(cfg["spec"], opts, B, device=device)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def load():
+        s.set_instances(cfg["x0"], cfg["xref"], None if ip else cfg["X0"], cfg["U0"], cfg["ref_traj"])
+        s.initialize()
+
+    load()
+    s.solve()  # untimed: first launches of the JIT-compiled module
+    torch.cuda.synchronize()
+    load()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.solve()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sc = s.get_scalars()
+    done = int(sc["iterations"].sum())
+    load()
+    s.enable_timing(True)
+    s.reset_timing()
+    s.solve()
+    t = s.get_timing()
+    out = {"workload": cfg["notes"], "solver": "IPDDP" if ip else "CLDDP", "batch": B, "horizon": cfg["spec"]["horizon"],
+           "value": done / (ms * 1e-3), "unit": UNIT, "solve_ms": ms, "instance_iterations": done,
+           "mean_iterations": done / B, "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sc["status"], return_counts=True))},
+           "mean_cost": float(np.mean(sc["cost"])),
+           "kernel_ms_total": {"linearize": t.linearize_ms, "backward": t.backward_ms, "forward": t.forward_ms},
+           "kernel_launches": {"linearize": t.linearize_launches, "backward": t.backward_launches, "forward": t.forward_launches}}
+    if ip:
+        out["dual_dim"] = s.d
+    s.close()
+    if with_cpu:
+        import oracle_binding as ob
+        threads = ob.hardware_threads()
+        ccfg = problems.make_config(name, batch=cpu_sample)
+        P = ob.OracleProblem(ccfg["spec"])
+        oo = ob.make_options(**ccfg["options"])
+        t0 = time.perf_counter()
+        if ip:
+            r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(**ccfg.get("ipddp_options", {})), ob.ConstraintSet(ccfg["constraints"]),
+                                     ccfg["x0"], ccfg["xref"], ccfg["U0"], None, nthreads=threads)
+        else:
+            r = ob.solve_batch(P, oo, ccfg["x0"], ccfg["xref"], ccfg["X0"], ccfg["U0"], ccfg["ref_traj"], nthreads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{cpu_sample} instances solved to tolerance, {dt:.2f}s wall"}
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -434,10 +498,16 @@ def main():
 
     other = None
     if rank == 0 and world == 1 and args.config == "quadrotor" and not args.no_cpu_baseline:
-        try:
-            other = {"ipddp_config4_unicycle_obstacle_teq": measure_ipddp(cddp, problems, local_rank, True)}
-        except Exception as e:  # secondary measurement: never take the bench line down with it
-            other = {"ipddp_config4_unicycle_obstacle_teq": {"error": repr(e)}}
+        other = {}
+        for key, fn in (("ipddp_config4_unicycle_obstacle_teq", lambda: measure_ipddp(cddp, problems, local_rank, True)),
+                        ("clddp_config5_standin_chain7_user_model",
+                         lambda: measure_user_solve(cddp, problems, local_rank, "chain7_user", 8192, 1024, True)),
+                        ("ipddp_config5_standin_chain7_user_model",
+                         lambda: measure_user_solve(cddp, problems, local_rank, "chain7_user_ipddp", 8192, 256, True))):
+            try:
+                other[key] = fn()
+            except Exception as e:  # secondary measurement: never take the bench line down with it
+                other[key] = {"error": repr(e)}
 
     if rank == 0:
         line = {

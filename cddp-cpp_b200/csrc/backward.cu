@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) backward_kernel(Constants c
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) sQ[i] = c.Qdt2[i];
   for (int i = threadIdx.x; i < m * m; i += blockDim.x) sR[i] = c.Rdt2[i];
   __syncthreads();
-  const int b = blockIdx.x * kWarpsPerCta + warp;
+  const int b = slot_instance(d, blockIdx.x * kWarpsPerCta + warp);
   if (b >= d.B) return;
   if (mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING) return;
 
@@ -334,7 +334,7 @@ cudaError_t launch_t(const Constants &c, const DeviceState &d, int mode, cudaStr
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int blocks = (d.B + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int blocks = (d.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
   backward_kernel<NS, NC><<<blocks, kWarpsPerCta * 32, shm, st>>>(c, d, mode);
   return cudaGetLastError();
 }

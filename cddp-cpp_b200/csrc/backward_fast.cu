@@ -126,7 +126,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     // =========================================================== matrix warps
     const int hw = lane / G, r = lane % G;  // hw: which of the warp's TPW trajectories, r: lane within the group
     const int q = warp * TPW + hw;
-    const int b = blockIdx.x * T + q;
+    const int b = slot_instance(d, blockIdx.x * T + q);
     double *S = traj0 + q * ST;
     const volatile double *Sv = S;  // for broadcast reads (see phase A1)
     // rows owned by this lane: row[s] = r + G*s.  row < NS: a row of V_xx; row == NS: V_x^T; row > NS: idle slot
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     // =========================================================== QP warp: lane q <-> trajectory q
     constexpr int MC = NC;
     const int q = lane;
-    const int b = blockIdx.x * T + q;
+    const int b = slot_instance(d, blockIdx.x * T + (q < T ? q : 0));
     const bool alive = q < T && b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
     const double *S = traj0 + (q < T ? q : T - 1) * ST;
     double *Sw = traj0 + (q < T ? q : T - 1) * ST;
@@ -662,7 +662,7 @@ cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cud
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int blocks = (d.B + Cfg::T - 1) / Cfg::T;
+  const int blocks = (d.n_slots + Cfg::T - 1) / Cfg::T;
   sweep_kernel<NS, NC, PAT, W, MINB><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
   return cudaGetLastError();
 }

@@ -63,12 +63,13 @@ struct cddp_b200_solver {
   std::vector<void *> allocs;
   double *dQdt2 = nullptr, *dRdt2 = nullptr, *dQf2 = nullptr, *dltiA = nullptr, *dltiB = nullptr;
   int *didxA = nullptr, *didxB = nullptr;
+  int *order_buf = nullptr;  // work list of the running instances (solve(), see DeviceState::order)
   UserKernels *user_kernels = nullptr;  // CDDP_B200_MODEL_USER: the NVRTC-compiled module
   int kind = 0;      // 0 = CLDDP, 1 = IPDDP
   IpConstants ic{};  // IPDDP: flattened constraint rows + options
   IpDevice ip{};     // IPDDP: duals, slacks, gains, per-instance barrier/filter state
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
-  int poll_interval = -1;  // -1: widening stride (default); 0: never poll (fully asynchronous solve); k > 0: every k iterations
+  int poll_interval = -1;  // -1: automatic (default: every iteration for heavy batches, else a widening stride); 0: never poll (fully asynchronous solve); k > 0: every k iterations
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;
@@ -384,6 +385,7 @@ int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, 
     c.ub[i] = (p->has_control_box && i < m) ? p->ub[i] : INFINITY;
   }
   d.B = batch; d.n = n; d.m = m; d.N = N;
+  d.order = nullptr; d.n_slots = batch;
   c.q_diag = 1;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j)
@@ -432,7 +434,7 @@ int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, 
   AL(d.K, B * N * m * n); AL(d.kff, B * N * m);
   AL(d.x0, B * n); AL(d.xref, B * n);
   d.ref_traj = nullptr;
-  AL(d.cur, B); AL(d.status, B); AL(d.iter, B); AL(d.lin_valid, B); AL(d.bw_ok, B); AL(d.accepted, B); AL(d.fw_done, B);
+  AL(d.cur, B); AL(d.status, B); AL(d.iter, B); AL(d.lin_valid, B); AL(d.bw_ok, B); AL(d.accepted, B); AL(d.fw_done, B); AL(s->order_buf, B);
   AL(d.reg, B); AL(d.cost, B); AL(d.alpha, B); AL(d.inf_du, B); AL(d.dV, 2 * B);
   AL(d.ls_cost, B * CDDP_B200_MAX_ALPHAS);
   AL(d.Vx0, B * n); AL(d.Vxx0, B * n * n);
@@ -537,6 +539,8 @@ int cddp_b200_initialize(cddp_b200_solver *s) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (!s->have_instances) return CDDP_B200_ERR_STATE;
   DeviceGuard g(s->device);
+  s->d.order = nullptr;  // every instance runs again
+  s->d.n_slots = s->d.B;
   if (s->kind == 1) CU(launch_ip_initialize(s->c, s->d, s->ic, s->ip, s->stream));
   else CU(launch_initialize(s->c, s->d, s->stream));
   s->timing.other_launches++;
@@ -588,7 +592,11 @@ int cddp_b200_solve(cddp_b200_solver *s) {
   // poll the running counter with a widening stride: cheap for short solves, rare for long ones.  With
   // poll_interval == 0 the solve is enqueued without any host synchronisation (finished instances are masked on
   // the device, so running the remaining launches is correct, just not free).
-  int next_poll = s->poll_interval > 0 ? s->poll_interval : 4;
+  // A poll is one small kernel + one stream synchronisation (~20 us): for a batch whose iteration takes a millisecond or
+  // more it is taken every iteration from the second on, so that the work list (DeviceState::order) shrinks as soon as
+  // instances finish; small batches keep the widening stride.
+  const bool heavy = (long long)s->d.B * s->d.N >= 32768;
+  int next_poll = s->poll_interval > 0 ? s->poll_interval : (heavy ? 2 : 4);
   for (int it = 0; it < max_it; ++it) {
     if (s->c.opt.max_cpu_time > 0.0) {  // cddp_solver_base.cpp:77-90 (wall clock, checked per batched iteration)
       CU(cudaStreamSynchronize(s->stream));
@@ -600,12 +608,21 @@ int cddp_b200_solve(cddp_b200_solver *s) {
     }
     if ((r = one_iteration(s))) return r;
     if (s->poll_interval != 0 && it + 1 == next_poll && it + 1 < max_it) {
+      // count the running instances and compact them into the work list: the launches that follow cover only those
       int running = 0;
-      if ((r = read_running(s, &running))) return r;
+      CU(launch_compact_running(s->d, s->order_buf, s->stream));
+      s->timing.other_launches++;
+      CU(cudaMemcpyAsync(s->h_running, s->d.num_running, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+      running = *s->h_running;
       if (running == 0) break;
-      next_poll += s->poll_interval > 0 ? s->poll_interval : ((next_poll < 16) ? 4 : 8);
+      s->d.order = s->order_buf;
+      s->d.n_slots = running;
+      next_poll += s->poll_interval > 0 ? s->poll_interval : (heavy ? 1 : ((next_poll < 16) ? 4 : 8));
     }
   }
+  s->d.order = nullptr;  // single-step entry points and the next solve address the whole batch
+  s->d.n_slots = s->d.B;
   CU(launch_finalize(s->c, s->d, final_status, s->stream));
   s->timing.other_launches++;
   return 0;

@@ -48,6 +48,11 @@ struct DeviceState {
   int *bw_ok;      // last backward sweep succeeded
   int *accepted;   // index of the accepted alpha in the last line search (-1 none)
   int *fw_done;    // FW_ITERATE only: this forward call's line search was already settled by forward_first_kernel
+  // Work list of the per-iteration kernels: slot s of a launch works on instance order[s] (identity when order is null);
+  // n_slots <= B slots are launched.  solve() compacts the still-running instances into the list whenever it polls the
+  // running counter, so a batch whose instances converge at different iterations stops paying for the finished ones.
+  const int *order;
+  int n_slots;
   double *reg;     // regularization_
   double *cost;    // cost_
   double *alpha;   // alpha_pr_
@@ -63,6 +68,13 @@ struct DeviceState {
   int *num_running;  // device counter
   void *user;        // HOST pointer (never dereferenced on the device): NVRTC-compiled kernels of a CDDP_B200_MODEL_USER handle
 };
+
+#ifdef __CUDACC__
+// instance handled by work-list slot `slot` (d.B = none)
+__device__ __forceinline__ int slot_instance(const DeviceState &d, int slot) {
+  return slot < d.n_slots ? (d.order ? d.order[slot] : slot) : d.B;
+}
+#endif
 
 // batch-shared constants, passed by value to kernels (fits the 4 KB parameter space comfortably)
 struct Constants {
@@ -131,6 +143,7 @@ cudaError_t launch_backward(const Constants &c, const DeviceState &d, int mode, 
 cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
 cudaError_t launch_finalize(const Constants &c, const DeviceState &d, int final_status, cudaStream_t st);
 cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st);
+cudaError_t launch_compact_running(const DeviceState &d, int *order, cudaStream_t st);
 cudaError_t launch_shift(const DeviceState &d, int k, cudaStream_t st);
 cudaError_t launch_gather_by_cur(const DeviceState &d, const double *buf0, const double *buf1, size_t per_instance, double *out,
                                  cudaStream_t st);

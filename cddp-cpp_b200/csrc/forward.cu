@@ -28,7 +28,7 @@ using namespace kern;
 __global__ void __launch_bounds__(kWarpsPerCta * 32) forward_lti_kernel(Constants c, DeviceState d, int mode) {
   constexpr int MS = CDDP_B200_MAX_N, MC = CDDP_B200_MAX_M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kWarpsPerCta + warp;
+  const int b = slot_instance(d, blockIdx.x * kWarpsPerCta + warp);
   if (b >= d.B) return;
   if (mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING) return;
   const int n = d.n, m = d.m, N = d.N, na = c.num_alphas;
@@ -115,11 +115,11 @@ cudaError_t launch_forward_model(const Constants &c, const DeviceState &d, int m
   const int threads = kWarpsPerCta * 32;
   const bool diag = c.cost_diag != 0;
   if (c.num_alphas <= 16) {
-    const int blocks = (d.B + kWarpsPerCta * 2 - 1) / (kWarpsPerCta * 2);
+    const int blocks = (d.n_slots + kWarpsPerCta * 2 - 1) / (kWarpsPerCta * 2);
     if (diag) forward_kernel<MODEL, 16, true><<<blocks, threads, 0, st>>>(c, d, mode);
     else forward_kernel<MODEL, 16, false><<<blocks, threads, 0, st>>>(c, d, mode);
   } else {
-    const int blocks = (d.B + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int blocks = (d.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
     if (diag) forward_kernel<MODEL, 32, true><<<blocks, threads, 0, st>>>(c, d, mode);
     else forward_kernel<MODEL, 32, false><<<blocks, threads, 0, st>>>(c, d, mode);
   }
@@ -133,7 +133,7 @@ cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, c
     case CDDP_B200_MODEL_UNICYCLE: return launch_forward_model<CDDP_B200_MODEL_UNICYCLE>(c, d, mode, st);
     case CDDP_B200_MODEL_QUADROTOR: return launch_forward_model<CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
     case CDDP_B200_MODEL_LTI: {
-      const int blocks = (d.B + kWarpsPerCta - 1) / kWarpsPerCta;
+      const int blocks = (d.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
       forward_lti_kernel<<<blocks, kWarpsPerCta * 32, 0, st>>>(c, d, mode);
       return cudaGetLastError();
     }

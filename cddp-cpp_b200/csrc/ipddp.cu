@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
     }
   };
   const int grp = threadIdx.x / G, r = threadIdx.x % G;
-  const int b = blockIdx.x * GPC + grp;
+  const int b = slot_instance(d, blockIdx.x * GPC + grp);
   const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   const int bb = alive ? b : 0;
   const int blk = ip_stage_doubles(n, m, D, rs);
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
       if (act) {
         for (int i = r; i < m * m; i += G) Quu[i] = QK[i];
         if (r == 0) {
-          const bool good = ldlt_small(Qr, tr, m);  // Eigen::LDLT(Q_uu_reg) (:1431)
+          const bool good = ldlt_small_t<NC>(Qr, tr, m);  // Eigen::LDLT(Q_uu_reg) (:1431)
           tr[CDDP_B200_MAX_M] = good ? 1 : 0;
         }
       }
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         fail = tr[CDDP_B200_MAX_M] == 0;  // ldlt.info() != Success -> backward pass fails (:1432-1435)
         if (!fail) {
           for (int col = r; col < nc1; col += G) {  // kK = -ldlt.solve(bigRHS) (:1449)
-            ldlt_solve(Qr, tr, m, RHS + col, nc1);
+            ldlt_solve_t<NC>(Qr, tr, m, RHS + col, nc1);
             for (int i = 0; i < m; ++i) RHS[i * nc1 + col] = -RHS[i * nc1 + col];
           }
         }
@@ -618,7 +618,7 @@ cudaError_t launch_ip_forward_d(const Constants &c, const DeviceState &d, const 
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_forward_kernel<MODEL, DC><<<(d.B + per_cta - 1) / per_cta, kFwThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_forward_kernel<MODEL, DC><<<(d.n_slots + per_cta - 1) / per_cta, kFwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 
@@ -651,7 +651,7 @@ cudaError_t launch_ip_backward_g(const Constants &c, const DeviceState &d, const
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_backward_kernel<G, NS, NC, DC><<<(d.B + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_backward_kernel<G, NS, NC, DC><<<(d.n_slots + gpc - 1) / gpc, kBwThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
   }
   __syncthreads();
   const int grp = threadIdx.x / G, r = threadIdx.x % G;
-  const int b = blockIdx.x * GPC + grp;
+  const int b = slot_instance(d, blockIdx.x * GPC + grp);
   const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   const int bb = alive ? b : 0;
   const int blk = teq_stage_doubles(n, m, D, rs);
@@ -314,13 +314,13 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
       }
       __syncwarp();
       bool fail = false;
-      if (act && r == 0) tr[CDDP_B200_MAX_N] = ldlt_small(Qf, tr, m) ? 1 : 0;  // Eigen::LDLT(Q_uu) (:457-461)
+      if (act && r == 0) tr[CDDP_B200_MAX_N] = ldlt_small_t<NC>(Qf, tr, m) ? 1 : 0;  // Eigen::LDLT(Q_uu) (:457-461)
       __syncwarp();
       if (act) {
         fail = tr[CDDP_B200_MAX_N] == 0;
         if (!fail)
           for (int col = r; col < nc2; col += G) {  // K = -solve(Q_ux), k_v = -solve(Q_u_v) (:463-464)
-            ldlt_solve(Qf, tr, m, RHS + col, nc2);
+            ldlt_solve_t<NC>(Qf, tr, m, RHS + col, nc2);
             for (int i = 0; i < m; ++i) RHS[i * nc2 + col] = -RHS[i * nc2 + col];
           }
       }
@@ -707,7 +707,7 @@ cudaError_t launch_teq_g(const Constants &c, const DeviceState &d, const IpConst
     configured = true;
   }
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
-  ip_backward_teq_kernel<G, NS, NC, DC><<<(d.B + gpc - 1) / gpc, kTeqThreads, shm, st>>>(c, d, ic, ip, mode);
+  ip_backward_teq_kernel<G, NS, NC, DC><<<(d.n_slots + gpc - 1) / gpc, kTeqThreads, shm, st>>>(c, d, ic, ip, mode);
   return cudaGetLastError();
 }
 

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   for (int i = threadIdx.x; i < RN; i += blockDim.x) sR[i] = 0.5 * c.Rdt2[DIAG ? i * NC + i : i];
   __syncthreads();
   const int grp = lane / LG, al = lane % LG;
-  const int b = (blockIdx.x * kWarpsPerCta + warp) * TPW + grp;
+  const int b = slot_instance(d, (blockIdx.x * kWarpsPerCta + warp) * TPW + grp);
   const bool alive = b < d.B && !(mode == FW_ITERATE && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.fw_done[b]));
   if (!__any_sync(0xffffffffu, alive)) return;
   const int bb = alive ? b : 0;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(64) forward_first_kernel(Constants c, DeviceSt
   }
   for (int i = threadIdx.x; i < RN; i += blockDim.x) sR[i] = 0.5 * c.Rdt2[DIAG ? i * NC + i : i];
   __syncthreads();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = slot_instance(d, blockIdx.x * blockDim.x + threadIdx.x);
   if (b >= d.B) return;
   d.fw_done[b] = 0;
   if (d.status[b] != CDDP_B200_STATUS_RUNNING) return;

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int grp = lane / LG, al = lane % LG;
-  const int b = ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp;
+  const int b = slot_instance(d, ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp);
   const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   if (!__any_sync(0xffffffffu, alive)) return;
   double *stage = fw_smem + con_table_doubles(NS_, NC_, Dd) + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, Dd);

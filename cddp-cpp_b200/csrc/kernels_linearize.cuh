@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState
   const int N = d.N;
   const int chunks = (N + 1 + 31) / 32;
   const long long wid = (long long)blockIdx.x * warps_per_cta + warp;
-  if (wid >= (long long)d.B * chunks) return;
-  const int b = (int)(wid / chunks), t0 = (int)(wid % chunks) * 32, t = t0 + lane;
+  if (wid >= (long long)d.n_slots * chunks) return;
+  const int b = slot_instance(d, (int)(wid / chunks)), t0 = (int)(wid % chunks) * 32, t = t0 + lane;
   if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;  // warp-uniform
   double *row = lin_smem + ((size_t)warp * 32 + lane) * PS;
   const int cur = d.cur[b];

@@ -8,7 +8,10 @@ namespace kern {
 // Eigen 3.4.0 LDLT (lower, diagonal pivoting), ldlt_inplace<Lower>::unblocked — executed by ONE lane on the m x m
 // matrix in shared memory.  a: in = matrix, out = L strictly below the diagonal and D on it; tr: transpositions.
 // Returns info() == Success.
-__device__ inline bool ldlt_small(double *a, int *tr, int n) {
+// NN: compile-time size (0 = the run-time n_rt): with a constant size the loops unroll and the addressing is immediate.
+template <int NN>
+__device__ __forceinline__ bool ldlt_small_t(double *a, int *tr, int n_rt) {
+  const int n = NN ? NN : n_rt;
   bool ok = true, found_zero_pivot = false;
   for (int k = 0; k < n; ++k) {
     int big = k;
@@ -32,7 +35,7 @@ __device__ inline bool ldlt_small(double *a, int *tr, int n) {
     }
     const int rs = n - k - 1;
     if (k > 0) {
-      double temp[CDDP_B200_MAX_N];  // capacity: also used for the n x n terminal-multiplier system
+      double temp[NN ? NN : CDDP_B200_MAX_N];  // capacity: also used for the n x n terminal-multiplier system
       for (int j = 0; j < k; ++j) temp[j] = a[j * n + j] * a[k * n + j];
       double s = 0.0;
       for (int j = 0; j < k; ++j) s += a[k * n + j] * temp[j];
@@ -61,8 +64,12 @@ __device__ inline bool ldlt_small(double *a, int *tr, int n) {
   return ok;
 }
 
+__device__ inline bool ldlt_small(double *a, int *tr, int n) { return ldlt_small_t<0>(a, tr, n); }
+
 // LDLT::solve for one right-hand side held in b[0..n) with stride `st`
-__device__ inline void ldlt_solve(const double *a, const int *tr, int n, double *b, int st) {
+template <int NN>
+__device__ __forceinline__ void ldlt_solve_t(const double *a, const int *tr, int n_rt, double *b, int st) {
+  const int n = NN ? NN : n_rt;
   for (int k = 0; k < n; ++k)
     if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
   for (int i = 0; i < n; ++i) {  // running value in a register: the same subtractions in the same order, without a
@@ -83,6 +90,7 @@ __device__ inline void ldlt_solve(const double *a, const int *tr, int n, double 
   for (int k = n - 1; k >= 0; --k)
     if (tr[k] != k) { const double t = b[k * st]; b[k * st] = b[tr[k] * st]; b[tr[k] * st] = t; }
 }
+__device__ inline void ldlt_solve(const double *a, const int *tr, int n, double *b, int st) { ldlt_solve_t<0>(a, tr, n, b, st); }
 
 }  // namespace kern
 }  // namespace cddp_b200

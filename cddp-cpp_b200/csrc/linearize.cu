@@ -143,6 +143,28 @@ __global__ void count_running_kernel(DeviceState d) {
   if ((threadIdx.x & 31) == 0 && mask) atomicAdd(d.num_running, __popc(mask));
 }
 
+// Stable compaction of the running instances into `order` (one CTA: every thread owns a contiguous chunk of the batch,
+// block-wide exclusive scan of the chunk counts); also writes the count to d.num_running.
+__global__ void __launch_bounds__(1024) compact_running_kernel(DeviceState d, int *order) {
+  __shared__ int part[1024];
+  const int chunk = (d.B + 1023) / 1024;
+  const int lo = min(threadIdx.x * chunk, d.B), hi = min(lo + chunk, d.B);
+  int cnt = 0;
+  for (int b = lo; b < hi; ++b) cnt += d.status[b] == CDDP_B200_STATUS_RUNNING;
+  part[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int pos = part[threadIdx.x] - cnt;
+  for (int b = lo; b < hi; ++b)
+    if (d.status[b] == CDDP_B200_STATUS_RUNNING) order[pos++] = b;
+  if (threadIdx.x == 1023) *d.num_running = part[1023];
+}
+
 __global__ void unpack_lin_kernel(DeviceState d, double *A, double *Bm) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)d.B * d.N) return;
@@ -245,7 +267,7 @@ cudaError_t launch_linearize_model(const Constants &c, const DeviceState &d, boo
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const long long warps = (long long)d.B * ((d.N + 1 + 31) / 32);
+  const long long warps = (long long)d.n_slots * ((d.N + 1 + 31) / 32);
   const int blocks = (int)((warps + wpc - 1) / wpc);
   linearize_kernel<MODEL, PAT><<<blocks, 128, per_warp * wpc, stream>>>(c, d, force ? 1 : 0, wpc);
   return cudaGetLastError();
@@ -290,6 +312,11 @@ cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(d.num_running, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   count_running_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_running(const DeviceState &d, int *order, cudaStream_t st) {
+  compact_running_kernel<<<1, 1024, 0, st>>>(d, order);
   return cudaGetLastError();
 }
 

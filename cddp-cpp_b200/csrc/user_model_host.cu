@@ -270,7 +270,7 @@ cudaError_t launch_user_linearize(const Constants &c, const DeviceState &d, bool
   const int stride = (n * n + n * m + n + 2 * m + 1) & ~1, PS = stride | 1;  // RecordLayout<n, m, DensePattern>::stride
   const size_t per_warp = sizeof(double) * 32 * PS;
   int wpc = (per_warp * 4 <= 100 * 1024) ? 4 : ((per_warp * 2 <= 200 * 1024) ? 2 : 1);
-  const long long warps = (long long)d.B * ((d.N + 1 + 31) / 32);
+  const long long warps = (long long)d.n_slots * ((d.N + 1 + 31) / 32);
   const unsigned blocks = (unsigned)((warps + wpc - 1) / wpc);
   int f = force ? 1 : 0;
   void *params[] = {(void *)&c, (void *)&d, &f, &wpc};
@@ -283,11 +283,11 @@ cudaError_t launch_user_forward(const Constants &c, const DeviceState &d, int mo
   const int wpc = 2;  // kern::kWarpsPerCta
   void *params[] = {(void *)&c, (void *)&d, &mode};
   if (mode == FW_ITERATE && !c.opt.enable_parallel) {  // speculative alphas_[0] first (kernels_forward.cuh)
-    cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.B + 63) / 64), 64, 0, st, params);
+    cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.n_slots + 63) / 64), 64, 0, st, params);
     if (e != cudaSuccess) return e;
   }
-  if (c.num_alphas <= 16) return launch(uk, K_FWD16, (unsigned)((d.B + wpc * 2 - 1) / (wpc * 2)), wpc * 32, 0, st, params);
-  return launch(uk, K_FWD32, (unsigned)((d.B + wpc - 1) / wpc), wpc * 32, 0, st, params);
+  if (c.num_alphas <= 16) return launch(uk, K_FWD16, (unsigned)((d.n_slots + wpc * 2 - 1) / (wpc * 2)), wpc * 32, 0, st, params);
+  return launch(uk, K_FWD32, (unsigned)((d.n_slots + wpc - 1) / wpc), wpc * 32, 0, st, params);
 }
 
 cudaError_t launch_user_ip_initialize(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
@@ -306,7 +306,7 @@ cudaError_t launch_user_ip_forward(const Constants &c, const DeviceState &d, con
   const size_t shm = sizeof(double) * ((size_t)table + (size_t)per_cta * 2 * step);   // kern::ip_fw_smem_doubles
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
   void *params[] = {(void *)&c, (void *)&d, (void *)&ic, (void *)&ip, &mode};
-  return launch(uk, K_IPFWD, (unsigned)((d.B + per_cta - 1) / per_cta), 64, shm, st, params);
+  return launch(uk, K_IPFWD, (unsigned)((d.n_slots + per_cta - 1) / per_cta), 64, shm, st, params);
 }
 
 }  // namespace cddp_b200

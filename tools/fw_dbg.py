@@ -7,12 +7,12 @@ cddp = importlib.import_module("cddp-cpp_b200")
 problems = importlib.import_module("cddp-cpp_b200.problems")
 name, B = sys.argv[1], int(sys.argv[2])
 cfg = problems.make_config(name, batch=B)
-opts = dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=20)
+opts = dict(cfg["options"], max_iterations=30) if "--tol" in sys.argv else dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=20)
 s = cddp.BatchedCLDDP(dict(cfg["spec"]), cddp.default_options(**opts), B)
 s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"], cfg["ref_traj"])
 s.initialize()
 s.enable_timing(True)
-for it in range(10):
+for it in range(int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 10):
     s.reset_timing()
     s.iterate(1)
     t = s.get_timing()
