@@ -195,3 +195,20 @@ def test_errors_and_scope(cddp, problems):
     lti = problems.make_config("lti", batch=2)
     with pytest.raises(cddp.CddpB200Error):
         cddp.BatchedIPDDP(lti["spec"], cddp.default_options(), cddp.default_ipddp_options(), [], 2)
+
+
+def test_work_list_compaction_changes_nothing(cddp, problems):
+    """Same as the CLDDP test: polling + compaction every iteration vs a fully enqueued solve, bit-identical results."""
+    B = 96
+    cfg = problems.make_config("unicycle_obstacle", batch=B, horizon=60)
+    out = []
+    for interval in (1, 0):
+        s, _ = make(cddp, cfg, B, max_iterations=60)
+        s.set_poll_interval(interval)
+        s.solve()
+        out.append(s.get_solution())
+        s.close()
+    its = out[0]["iterations"]
+    assert its.min() < its.max()
+    for key in ("X", "U", "cost", "iterations", "status"):
+        assert np.array_equal(out[0][key], out[1][key]), key

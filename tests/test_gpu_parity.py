@@ -470,3 +470,24 @@ def test_random_trajectories_per_step_parity(cddp, ob, problems, name):
                     first = ai
             assert fw["accepted"][b] == first
         s.close()
+
+
+@pytest.mark.parametrize("name", ["cartpole", "quadrotor"])
+def test_work_list_compaction_changes_nothing(cddp, problems, name):
+    """solve() compacts the running instances into a work list at every poll (DeviceState::order); instances are
+    independent, so polling every iteration, the default stride and never polling must give bit-identical results
+    on a batch whose instances converge at different iterations."""
+    B = 200
+    cfg = problems.make_config(name, batch=B)
+    out = []
+    for interval in (1, -1, 0):
+        s, _ = make(cddp, cfg, B, max_iterations=40)
+        s.set_poll_interval(interval)
+        s.solve()
+        out.append(s.get_solution())
+        s.close()
+    its = out[0]["iterations"]
+    assert its.min() < its.max(), "the batch must be heterogeneous for this test to mean anything"
+    for o in out[1:]:
+        for key in ("X", "U", "K", "cost", "iterations", "status"):
+            assert np.array_equal(out[0][key], o[key]), key
