@@ -200,10 +200,10 @@ def test_errors_and_scope(cddp, problems):
 def test_work_list_compaction_changes_nothing(cddp, problems):
     """Same as the CLDDP test: polling + compaction every iteration vs a fully enqueued solve, bit-identical results."""
     B = 96
-    cfg = problems.make_config("unicycle_obstacle", batch=B, horizon=60)
+    cfg = problems.make_config("pendulum_ipddp", batch=B)
     out = []
     for interval in (1, 0):
-        s, _ = make(cddp, cfg, B, max_iterations=60)
+        s, _ = make(cddp, cfg, B, max_iterations=100)
         s.set_poll_interval(interval)
         s.solve()
         out.append(s.get_solution())

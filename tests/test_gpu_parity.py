@@ -472,7 +472,7 @@ def test_random_trajectories_per_step_parity(cddp, ob, problems, name):
         s.close()
 
 
-@pytest.mark.parametrize("name", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("name", ["cartpole", "unicycle"])
 def test_work_list_compaction_changes_nothing(cddp, problems, name):
     """solve() compacts the running instances into a work list at every poll (DeviceState::order); instances are
     independent, so polling every iteration, the default stride and never polling must give bit-identical results
