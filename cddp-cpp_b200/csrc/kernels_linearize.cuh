@@ -14,14 +14,20 @@ namespace kern {
 // One lane per (instance, t); one warp per chunk of 32 consecutive timesteps of ONE instance.  PAT = DensePattern
 // (RECORDS_DENSE) or ModelPattern<MODEL> (RECORDS_STRUCTURED): only entries inside the pattern are stored; the
 // analytic Jacobians are identically zero outside it.  The 32 records of a chunk are contiguous in HBM, so each
-// lane builds its record in a (bank-conflict-free, odd-stride) shared-memory row and the warp then streams the
-// whole chunk out with fully coalesced stores.  v1 had every thread write its own 832..1936-byte record directly
-// (32 scattered 8-byte stores per instruction): 0.34 ms for 341 MB = 1 TB/s.
+// lane puts its record into a (bank-conflict-free, odd-stride) shared-memory row and the warp then streams the
+// chunk out with coalesced stores.  v1 had every thread write its own 832..1936-byte record directly (32 scattered
+// 8-byte stores per instruction): 0.34 ms for 341 MB = 1 TB/s.
+// The record goes through shared memory in PARTS slices of at most 56 doubles: staging whole records (26.9 KB per warp
+// for the quadrotor, 82.7 KB for a dense n = 14 model) left 6 resp. 2 warps per SM, and the kernel is bound by the
+// latency of its loads and of the FP64 chain that forms the Jacobians, not by the stores.
+__host__ __device__ constexpr int lin_parts(int rs) { return (rs + 55) / 56; }
+__host__ __device__ constexpr int lin_part_width(int rs) { return (rs + lin_parts(rs) - 1) / lin_parts(rs); }
+
 template <int MODEL, class PAT>
-__global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState d, int force, int warps_per_cta) {
+__global__ void __launch_bounds__(128, 3) linearize_kernel(Constants c, DeviceState d, int force, int warps_per_cta) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
   using L = RecordLayout<NS, NC, PAT>;
-  constexpr int RS = L::stride, PS = RS | 1;  // padded row stride (odd => conflict-free per-lane rows)
+  constexpr int RS = L::stride, PARTS = lin_parts(RS), H = lin_part_width(RS), PSH = H | 1;  // odd row stride
   extern __shared__ double lin_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= warps_per_cta) return;
@@ -31,8 +37,10 @@ __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState
   if (wid >= (long long)d.n_slots * chunks) return;
   const int b = slot_instance(d, (int)(wid / chunks)), t0 = (int)(wid % chunks) * 32, t = t0 + lane;
   if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;  // warp-uniform
-  double *row = lin_smem + ((size_t)warp * 32 + lane) * PS;
+  double *row = lin_smem + ((size_t)warp * 32 + lane) * PSH;
   const int cur = d.cur[b];
+  const bool rec = t < N;
+  double Fx[NS * NS], Fu[NS * NC], lxv[NS], luv[NC], u[NC];
   if (t <= N) {
     const double *xp = d.X[cur] + ((size_t)b * (N + 1) + t) * NS;
     double x[NS];
@@ -51,53 +59,68 @@ __global__ void __launch_bounds__(128) linearize_kernel(Constants c, DeviceState
       }
     } else {
       const double *up = d.U[cur] + ((size_t)b * N + t) * NC;
-      double u[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) u[i] = up[i];
-      double Fx[NS * NS], Fu[NS * NC];
       Model<MODEL>::jac(c.mp, x, u, Fx, Fu);
-      static_for<0, NS>([&](auto lc) {
-        constexpr int l = decltype(lc)::value;
-        static_for<0, NS>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          if constexpr (PAT::a(l, j)) row[L::idxA(l, j)] = c.dt * Fx[l * NS + j] + (l == j ? 1.0 : 0.0);
-        });
-        if constexpr (PAT::brow(l)) {
-          static_for<0, NC>([&](auto ac) {
-            constexpr int a = decltype(ac)::value;
-            row[L::idxB(l, a)] = c.dt * Fu[l * NC + a];
-          });
-        }
-      });
       const double *ref = ref_ptr(d, b, t);
       double e[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
+#pragma unroll
       for (int i = 0; i < NS; ++i) {
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
-        row[L::offLx + i] = s;
+        lxv[i] = s;
       }
+#pragma unroll
       for (int i = 0; i < NC; ++i) {
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
-        row[L::offLu + i] = s;
+        luv[i] = s;
       }
-#pragma unroll
-      for (int i = 0; i < NC; ++i) row[L::offU + i] = u[i];
-      if (L::count < RS) row[L::count] = 0.0;  // pad
     }
   }
-  __syncwarp();
   const int nrec = min(32, N - t0);  // records in this chunk (t < N)
-  if (nrec > 0) {
-    double *dst = d.rec + ((size_t)b * N + t0) * RS;
-    const double *src = lin_smem + (size_t)warp * 32 * PS;
-    const int total = nrec * RS;
-    for (int e = lane; e < total; e += 32) dst[e] = src[(e / RS) * PS + (e % RS)];
-  }
+  double *dst = d.rec + ((size_t)b * N + (nrec > 0 ? t0 : 0)) * RS;
+  const double *src = lin_smem + (size_t)warp * 32 * PSH;
+  static_for<0, PARTS>([&](auto pc) {
+    constexpr int part = decltype(pc)::value, lo = part * H;
+    if (rec) {  // this lane's entries lo .. lo + H of its record
+      static_for<0, NS>([&](auto lc) {
+        constexpr int l = decltype(lc)::value;
+        static_for<0, NS>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          if constexpr (PAT::a(l, j)) {
+            if constexpr (L::idxA(l, j) / H == part) row[L::idxA(l, j) - lo] = c.dt * Fx[l * NS + j] + (l == j ? 1.0 : 0.0);
+          }
+        });
+        if constexpr (PAT::brow(l)) {
+          static_for<0, NC>([&](auto ac) {
+            constexpr int a = decltype(ac)::value;
+            if constexpr (L::idxB(l, a) / H == part) row[L::idxB(l, a) - lo] = c.dt * Fu[l * NC + a];
+          });
+        }
+        if constexpr ((L::offLx + l) / H == part) row[L::offLx + l - lo] = lxv[l];
+      });
+      static_for<0, NC>([&](auto ac) {
+        constexpr int a = decltype(ac)::value;
+        if constexpr ((L::offLu + a) / H == part) row[L::offLu + a - lo] = luv[a];
+        if constexpr ((L::offU + a) / H == part) row[L::offU + a - lo] = u[a];
+      });
+      if constexpr (L::count < RS && L::count / H == part) row[L::count - lo] = 0.0;  // pad
+    }
+    __syncwarp();
+    if (nrec > 0) {
+      const int total = nrec * H;
+      for (int e = lane; e < total; e += 32) {
+        const int r = e / H, k = e - r * H;
+        if (lo + k < RS) dst[(size_t)r * RS + lo + k] = src[r * PSH + k];
+      }
+    }
+    __syncwarp();
+  });
 }
 
 }  // namespace kern

@@ -258,9 +258,9 @@ template <int MODEL, class PAT>
 cudaError_t launch_linearize_model(const Constants &c, const DeviceState &d, bool force, cudaStream_t stream) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
   using L = RecordLayout<NS, NC, PAT>;
-  constexpr int PS = L::stride | 1;
-  constexpr size_t per_warp = sizeof(double) * 32 * PS;
-  constexpr int wpc = (per_warp * 4 <= 100 * 1024) ? 4 : ((per_warp * 2 <= 200 * 1024) ? 2 : 1);
+  constexpr int PSH = kern::lin_part_width(L::stride) | 1;
+  constexpr size_t per_warp = sizeof(double) * 32 * PSH;
+  constexpr int wpc = 4;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(linearize_kernel<MODEL, PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpc));

@@ -267,9 +267,10 @@ static cudaError_t launch(UserKernels *uk, int k, unsigned blocks, unsigned thre
 cudaError_t launch_user_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st) {
   UserKernels *uk = static_cast<UserKernels *>(d.user);
   const int n = d.n, m = d.m;
-  const int stride = (n * n + n * m + n + 2 * m + 1) & ~1, PS = stride | 1;  // RecordLayout<n, m, DensePattern>::stride
-  const size_t per_warp = sizeof(double) * 32 * PS;
-  int wpc = (per_warp * 4 <= 100 * 1024) ? 4 : ((per_warp * 2 <= 200 * 1024) ? 2 : 1);
+  const int stride = (n * n + n * m + n + 2 * m + 1) & ~1;  // RecordLayout<n, m, DensePattern>::stride
+  const int parts = (stride + 55) / 56, PSH = ((stride + parts - 1) / parts) | 1;  // kern::lin_parts / lin_part_width
+  const size_t per_warp = sizeof(double) * 32 * PSH;
+  int wpc = 4;
   const long long warps = (long long)d.n_slots * ((d.N + 1 + 31) / 32);
   const unsigned blocks = (unsigned)((warps + wpc - 1) / wpc);
   int f = force ? 1 : 0;
