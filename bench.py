@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--config", default="quadrotor")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's batch)")
     ap.add_argument("--iters-per-call", type=int, default=10, help="DDP iterations per e2e solve call")
-    ap.add_argument("--e2e-calls", type=int, default=6)
+    ap.add_argument("--e2e-calls", type=int, default=24)
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -406,6 +406,7 @@ def main():
         class Lane:
             def __init__(self, slv, strm):
                 self.s, self.stream = slv, strm
+                self.solved = torch.cuda.Event()  # recorded after the last kernel of this lane's solve
                 slv.set_stream(strm.cuda_stream)
                 slv.set_options(cddp.default_options(**throughput_options(cfg, ipc)))
                 self.hin = {k: pin(cfg[k]) for k in ("x0", "xref", "X0", "U0")}
@@ -417,12 +418,18 @@ def main():
                              "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
                              "status": torch.empty(B, dtype=torch.int32).pin_memory()}
 
-            def enqueue(self, blocking):
+            def enqueue(self, blocking, after=None):
                 h, hin, hout = self.s.handle, self.hin, self.hout
                 cddp._check(lib.cddp_b200_set_instances(h, hin["x0"].data_ptr(), hin["xref"].data_ptr(),
                                                         self.hrt.data_ptr() if self.hrt is not None else None,
                                                         hin["X0"].data_ptr(), hin["U0"].data_ptr()))
+                # The two lanes overlap COPIES with kernels, not kernels with kernels: this lane's solve starts when the
+                # other lane's solve has finished.  Interleaved, every sweep launch (one 255-register CTA per SM) has to
+                # wait for whole SMs to drain of the other lane's CTAs, which cost 10 % of the pipelined throughput.
+                if after is not None:
+                    self.stream.wait_event(after)
                 cddp._check(lib.cddp_b200_solve(h))
+                self.solved.record(self.stream)
                 get = lib.cddp_b200_get_solution if blocking else lib.cddp_b200_get_solution_async
                 cddp._check(get(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr(), hout["cost"].data_ptr(),
                                 hout["iters"].data_ptr(), hout["status"].data_ptr(), None, None, None))
@@ -444,24 +451,29 @@ def main():
             lane0.enqueue(True)
         barrier()
         dt_serial = time.perf_counter() - t0
-        # (b) pipelined: two handles, asynchronous calls
-        solver2 = cddp.BatchedCLDDP(spec, cddp.default_options(**throughput_options(cfg, ipc)), B, device=local_rank)
-        lane1 = Lane(solver2, torch.cuda.Stream())
-        lanes = [lane0, lane1]
+        # (b) pipelined: three handles, asynchronous calls.  The link is the narrow part (57 MB up + 227 MB down per call,
+        # ~10 ms of PCIe time against 11.7 ms of kernels): with two lanes the upload of call k+1 could only be enqueued
+        # once the download of call k-1 had finished (same lane), and the two copies ran back to back; the third lane
+        # lets call k+1's upload run against call k-1's download (full duplex, two copy engines).
+        extra = [cddp.BatchedCLDDP(spec, cddp.default_options(**throughput_options(cfg, ipc)), B, device=local_rank) for _ in range(2)]
+        lanes = [lane0] + [Lane(sv, torch.cuda.Stream()) for sv in extra]
+        NL = len(lanes)
         for ln in lanes:
             ln.s.set_poll_interval(0)
             ln.enqueue(False)
             ln.wait()
         barrier()
         t0 = time.perf_counter()
-        inflight = [False, False]
+        inflight = [False] * NL
         for k in range(calls):
-            i = k & 1
+            i = k % NL
             if inflight[i]:
                 lanes[i].wait()
-            lanes[i].enqueue(False)
+            prev = (i - 1) % NL
+            lanes[i].enqueue(False, after=lanes[prev].solved if inflight[prev] else None)
             inflight[i] = True
-        for i in (0, 1):
+        for j in range(NL):
+            i = (calls + j) % NL  # oldest first
             if inflight[i]:
                 lanes[i].wait()
         barrier()
@@ -474,8 +486,10 @@ def main():
                "iterations_per_call": ipc, "calls": calls, "ms_per_call": 1e3 * dt / calls,
                "serial_value": world * B * ipc * calls / dt_serial, "serial_ms_per_call": 1e3 * dt_serial / calls,
                "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution[_async] on pinned host buffers; "
-                      "value = two handles double-buffered on two CUDA streams, serial_value = one handle, blocking calls"}
-        solver2.close()
+                      "value = three handles used in rotation on three CUDA streams (copies overlap the other lanes' kernels, "
+                      "kernels of different lanes are serialised by an event), serial_value = one handle, blocking calls"}
+        for sv in extra:
+            sv.close()
         solver.set_stream(stream.cuda_stream)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
