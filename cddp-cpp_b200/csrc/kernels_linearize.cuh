@@ -66,19 +66,26 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(Constants c, DeviceSt
       double e[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) e[i] = x[i] - ref[i];
+      if (c.cost_diag) {  // Q, R diagonal (every shipped workload): the products with the exact-zero entries are skipped
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        double s = 0.0;
+        for (int i = 0; i < NS; ++i) lxv[i] = 0.0 + c.Qdt2[i * NS + i] * e[i];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
-        lxv[i] = s;
-      }
+        for (int i = 0; i < NC; ++i) luv[i] = 0.0 + c.Rdt2[i * NC + i] * u[i];
+      } else {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        double s = 0.0;
+        for (int i = 0; i < NS; ++i) {
+          double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
-        luv[i] = s;
+          for (int j = 0; j < NS; ++j) s += c.Qdt2[i * NS + j] * e[j];
+          lxv[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) s += c.Rdt2[i * NC + j] * u[j];
+          luv[i] = s;
+        }
       }
     }
   }
@@ -112,11 +119,12 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(Constants c, DeviceSt
       if constexpr (L::count < RS && L::count / H == part) row[L::count - lo] = 0.0;  // pad
     }
     __syncwarp();
-    if (nrec > 0) {
-      const int total = nrec * H;
-      for (int e = lane; e < total; e += 32) {
-        const int r = e / H, k = e - r * H;
-        if (lo + k < RS) dst[(size_t)r * RS + lo + k] = src[r * PSH + k];
+    // lane -> fixed columns k = lane, lane + 32 of the slice, loop over the records: 256-byte runs, no index division
+#pragma unroll
+    for (int k0 = 0; k0 < H; k0 += 32) {
+      const int k = k0 + lane;
+      if (k < H && lo + k < RS) {
+        for (int r = 0; r < nrec; ++r) dst[(size_t)r * RS + lo + k] = src[r * PSH + k];
       }
     }
     __syncwarp();
