@@ -142,7 +142,7 @@ struct SmallMat {
     int status = QP_MAX_ITER_EXCEEDED;
 #pragma unroll
     for (int i = 0; i < M; ++i)
-      if (i < m) x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+      if (i < m) x[i] = clamp_box(x[i], lo[i], hi[i]);
     unsigned clamped = 0u;
     free_mask = all;
     double value = qp_value(m, H, g, x);
@@ -221,7 +221,7 @@ struct SmallMat {
       while (step > o.qp_min_step_size) {
 #pragma unroll
         for (int i = 0; i < M; ++i)
-          if (i < m) xn[i] = fmin(fmax(x[i] + step * search[i], lo[i]), hi[i]);
+          if (i < m) xn[i] = clamp_box(x[i] + step * search[i], lo[i], hi[i]);
         vn = qp_value(m, H, g, xn);
         if ((vn - value) <= o.qp_armijo_constant * step * sdotg) {
           ls_ok = true;

@@ -195,7 +195,7 @@ struct SmallQP {
     constexpr unsigned all = (1u << M) - 1u;
     int status = QP_MAX_ITER_EXCEEDED;
 #pragma unroll
-    for (int i = 0; i < M; ++i) x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+    for (int i = 0; i < M; ++i) x[i] = clamp_box(x[i], lo[i], hi[i]);
     auto matvec_value = [&](const double *z, double *Hz) {  // 0.5 z^T H z + g^T z  (boxqp.cpp:235-239)
       double a = 0.0, bb = 0.0;
 #pragma unroll
@@ -275,7 +275,7 @@ struct SmallQP {
       double xn[M], Hxn[M];
       while (step > o.qp_min_step_size) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) xn[i] = fmin(fmax(x[i] + step * search[i], lo[i]), hi[i]);
+        for (int i = 0; i < M; ++i) xn[i] = clamp_box(x[i] + step * search[i], lo[i], hi[i]);
         vn = matvec_value(xn, Hxn);
         if ((vn - value_) <= o.qp_armijo_constant * step * sdotg) {
           ls_ok = true;

@@ -70,6 +70,14 @@ struct DeviceState {
 };
 
 #ifdef __CUDACC__
+// std::min(std::max(v, lo), hi) as the reference writes it (boxqp.cpp:241-250; Eigen's cwiseMax / cwiseMin in
+// ControlConstraint::clamp, constraint.hpp:225-228): (v < lo) ? lo : v, then (hi < v) ? hi : v.  Two compares and two
+// 64-bit selects; CUDA's fmax / fmin add NaN canonicalisation and come to 15 instructions per clamp, which made the
+// projection the most expensive part of a BoxQP line-search trial on the sweep's critical path.
+__device__ __forceinline__ double clamp_box(double v, double lo, double hi) {
+  v = (v < lo) ? lo : v;
+  return (hi < v) ? hi : v;
+}
 // instance handled by work-list slot `slot` (d.B = none)
 __device__ __forceinline__ int slot_instance(const DeviceState &d, int slot) {
   return slot < d.n_slots ? (d.order ? d.order[slot] : slot) : d.B;

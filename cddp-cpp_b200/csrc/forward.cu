@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) forward_lti_kernel(Constant
         u[i] = Un[(size_t)t * m + i] + alpha * gk[(size_t)t * m + i] + acc;
       }
       if (c.has_box)
-        for (int i = 0; i < m; ++i) u[i] = fmin(fmax(u[i], c.lb[i]), c.ub[i]);
+        for (int i = 0; i < m; ++i) u[i] = clamp_box(u[i], c.lb[i], c.ub[i]);
       const double *ref = rtraj ? rtraj + (size_t)t * n : xref;
       double sx = 0.0, su = 0.0;
       for (int j = 0; j < n; ++j) {

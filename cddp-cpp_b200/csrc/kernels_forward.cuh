@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
     }
     if (c.has_box) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) u[i] = fmin(fmax(u[i], c.lb[i]), c.ub[i]);  // clamp (:235-238)
+      for (int i = 0; i < NC; ++i) u[i] = clamp_box(u[i], c.lb[i], c.ub[i]);  // clamp (:235-238)
     }
     {  // running cost (e^T Q_) e + (u^T R_) u  (:240-241)
       const double *ref = rtraj ? rtraj + (size_t)t * NS : xref;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(64) forward_first_kernel(Constants c, DeviceSt
     }
     if (c.has_box) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) u[i] = fmin(fmax(u[i], c.lb[i]), c.ub[i]);
+      for (int i = 0; i < NC; ++i) u[i] = clamp_box(u[i], c.lb[i], c.ub[i]);
     }
     {
       const double *ref = rtraj ? rtraj + (size_t)t * NS : xref;
