@@ -584,13 +584,13 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
             const double sq = fma(-reg, kk[a], Hk[a]);  // (Q_uu k)_a = (Q_uu_reg k)_a - reg k_a
             d0 = fma(g[a], kk[a], d0);
             d1 = fma(kk[a], sq, d1);
-            linf = fmax(linf, fabs(g[a]));
+            linf = max_ref(linf, fabs(g[a]));
             Sw[Cfg::oW + a] = sq + g[a];
             Sw[Cfg::oKk + a] = kk[a];
           }
           dV0 += d0;
           dV1 += 0.5 * d1;
-          Qu_err = fmax(Qu_err, linf);  // (:195)
+          Qu_err = max_ref(Qu_err, linf);  // (:195)
           *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_OK;
           if (--qt < 0) {
             run = false;

@@ -78,6 +78,9 @@ __device__ __forceinline__ double clamp_box(double v, double lo, double hi) {
   v = (v < lo) ? lo : v;
   return (hi < v) ? hi : v;
 }
+// std::max / std::min as compare-select (same reason): (a < b) ? b : a and (b < a) ? b : a
+__device__ __forceinline__ double max_ref(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double min_ref(double a, double b) { return (b < a) ? b : a; }
 // instance handled by work-list slot `slot` (d.B = none)
 __device__ __forceinline__ int slot_instance(const DeviceState &d, int slot) {
   return slot < d.n_slots ? (d.order ? d.order[slot] : slot) : d.B;

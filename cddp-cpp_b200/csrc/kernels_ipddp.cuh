@@ -381,10 +381,10 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       if (!segment) {  // the trial's statistics are those of pass 1
         const double res = g + sn;
         acc_t += l2 ? res * res : fabs(res);
-        st.inf_pr = fmax(st.inf_pr, fabs(res));
-        lprod.mul(fmax(sn, EPS_SLACK));
-        st.maxys = fmax(st.maxys, yn * sn);
-        st.minys = fmin(st.minys, yn * sn);
+        st.inf_pr = max_ref(st.inf_pr, fabs(res));
+        lprod.mul(max_ref(sn, EPS_SLACK));
+        st.maxys = max_ref(st.maxys, yn * sn);
+        st.minys = min_ref(st.minys, yn * sn);
       }
       if (wr) {
         Sc[e] = sn;
