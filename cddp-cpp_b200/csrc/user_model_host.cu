@@ -286,6 +286,11 @@ cudaError_t launch_user_forward(const Constants &c, const DeviceState &d, int mo
   if (mode == FW_ITERATE && !c.opt.enable_parallel) {  // speculative alphas_[0] first (kernels_forward.cuh)
     cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.n_slots + 63) / 64), 64, 0, st, params);
     if (e != cudaSuccess) return e;
+  } else if (mode == FW_ITERATE) {
+    // options can change on a live handle (cddp_b200_set_options): flags left by an earlier speculative pass must not
+    // mask instances from the full line search
+    cudaError_t e = cudaMemsetAsync(d.fw_done, 0, (size_t)d.B * sizeof(int), st);
+    if (e != cudaSuccess) return e;
   }
   if (c.num_alphas <= 16) return launch(uk, K_FWD16, (unsigned)((d.n_slots + wpc * 2 - 1) / (wpc * 2)), wpc * 32, 0, st, params);
   return launch(uk, K_FWD32, (unsigned)((d.n_slots + wpc - 1) / wpc), wpc * 32, 0, st, params);
