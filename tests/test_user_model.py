@@ -114,6 +114,39 @@ def test_plugin_clddp_parity(cddp, ob, problems, name):
 
 
 @pytest.mark.gpu
+def test_speculative_first_alpha_and_option_switch(cddp, ob, problems):
+    """User models try alphas_[0] on one lane per instance before the 16-wide line search (sequential rule only).  (1) Per
+    iteration, the accepted step and the cost must be those of the oracle's sequential line search.  (2) Switching a live
+    handle to enable_parallel (full line search alone) must not be masked by flags the speculative pass left behind."""
+    B = 6
+    cfg = problems.make_config("bicycle_user", batch=B, horizon=60)
+    opts = dict(cfg["options"], max_iterations=30)
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+    s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), B)
+    s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+    s.enable_history(True)
+    s.initialize()
+    s.iterate(4)
+    h, lens = s.get_history()
+    for b in range(B):
+        o = ob.solve(P, ob.make_options(**dict(opts, max_iterations=4)), cfg["x0"][b], cfg["xref"][b], cfg["X0"][b], cfg["U0"][b],
+                     history=True)
+        n = min(lens[b], o["history"].shape[0])
+        assert n >= 2
+        assert rel_err(h[b, :n, :2], o["history"][:n, :2]) < 1e-7  # accepted cost and alpha per iteration
+    mid = s.get_solution()
+    # (2) continue with enable_parallel on the SAME handle: every instance (all still far from converged) must keep moving
+    assert (mid["status"] == 0).all()
+    s.set_options(cddp.default_options(**dict(opts, enable_parallel=1)))
+    s.iterate(3)
+    a = s.get_solution()
+    s.close()
+    for b in range(B):
+        assert not np.array_equal(a["X"][b], mid["X"][b]), b
+        assert a["cost"][b] < mid["cost"][b]
+
+
+@pytest.mark.gpu
 def test_plugin_ipddp_parity(cddp, ob, problems):
     B = 4
     cfg = problems.make_config("bicycle_user_ipddp", batch=B, horizon=60)
