@@ -11,10 +11,10 @@
 #include <nvrtc.h>
 
 #include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -136,8 +136,44 @@ struct UserKernels {
 };
 
 // Compiles the translation unit; on success `cubin` holds the sm_100a image and `lowered` the mangled kernel names.
+static int compile_user_model_uncached(const char *source, int n, int m, bool diag, std::vector<char> &cubin,
+                                       std::string lowered[K_COUNT], std::string &log);
+
+// Process-wide cache of compiled images keyed by (n, m, cost form, source text): a solver handle per MPC loop / per stream /
+// per solver type of the same model then pays the NVRTC compile (4 .. 19 s) once.
+namespace {
+struct CompiledImage {
+  std::vector<char> cubin;
+  std::string lowered[K_COUNT];
+};
+std::mutex g_cache_mutex;
+std::map<std::string, CompiledImage> g_image_cache;
+}  // namespace
+
 static int compile_user_model(const char *source, int n, int m, bool diag, std::vector<char> &cubin, std::string lowered[K_COUNT],
                               std::string &log) {
+  const std::string key = std::to_string(n) + "/" + std::to_string(m) + "/" + (diag ? "d" : "f") + "/" + source;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    auto it = g_image_cache.find(key);
+    if (it != g_image_cache.end()) {
+      cubin = it->second.cubin;
+      for (int k = 0; k < K_COUNT; ++k) lowered[k] = it->second.lowered[k];
+      return 0;
+    }
+  }
+  const int r = compile_user_model_uncached(source, n, m, diag, cubin, lowered, log);
+  if (r == 0) {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    CompiledImage &img = g_image_cache[key];
+    img.cubin = cubin;
+    for (int k = 0; k < K_COUNT; ++k) img.lowered[k] = lowered[k];
+  }
+  return r;
+}
+
+static int compile_user_model_uncached(const char *source, int n, int m, bool diag, std::vector<char> &cubin,
+                                       std::string lowered[K_COUNT], std::string &log) {
   std::string err;
   Nvrtc *rt = nvrtc(err);
   if (!rt) {
