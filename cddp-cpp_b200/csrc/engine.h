@@ -69,6 +69,20 @@ struct DeviceState {
   void *user;        // HOST pointer (never dereferenced on the device): NVRTC-compiled kernels of a CDDP_B200_MODEL_USER handle
 };
 
+// linearize_kernel stages a record of `rs` doubles through shared memory in lin_parts(rs) slices of lin_part_width(rs)
+// doubles (kernels_linearize.cuh); shared by the kernel and by the host launchers that size its shared memory.
+#ifdef __CUDACC__
+#define CDDP_B200_HD __host__ __device__
+#else
+#define CDDP_B200_HD
+#endif
+CDDP_B200_HD constexpr int lin_parts(int rs) { return (rs + 55) / 56; }
+CDDP_B200_HD constexpr int lin_part_width(int rs) { return (rs + lin_parts(rs) - 1) / lin_parts(rs); }
+// shared-memory geometry of ip_forward_kernel (kernels_ipddp.cuh): the constraint table staged once per CTA, and one
+// timestep's operands x | u | k | K | S | Y | k_s | k_y | K_s | K_y of a trajectory
+CDDP_B200_HD constexpr int con_table_doubles(int n, int m, int D) { return (D * n + D * m + 3 * D + 1) & ~1; }
+CDDP_B200_HD constexpr int ip_fw_step_doubles(int n, int m, int D) { return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1; }
+
 #ifdef __CUDACC__
 // std::min(std::max(v, lo), hi) as the reference writes it (boxqp.cpp:241-250; Eigen's cwiseMax / cwiseMin in
 // ControlConstraint::clamp, constraint.hpp:225-228): (v < lo) ? lo : v, then (hi < v) ? hi : v.  Two compares and two

@@ -27,7 +27,7 @@ struct ConTable {
 __device__ __forceinline__ ConTable con_table_global(const IpConstants &ic) {
   return ConTable{ic.Gx, ic.Gu, ic.off, ic.scale, ic.row_type, ic.row_bdim};
 }
-__host__ __device__ inline int con_table_doubles(int n, int m, int D) { return (D * n + D * m + 3 * D + 1) & ~1; }
+// (con_table_doubles / ip_fw_step_doubles live in engine.h: the host launchers size the shared memory with them)
 // copies the table into shared memory (all threads of the CTA; caller synchronises)
 __device__ __forceinline__ ConTable con_table_stage(const IpConstants &ic, double *dst, int n, int m, int D) {
   double *tGx = dst, *tGu = tGx + D * n, *tOff = tGu + D * m, *tScale = tOff + D;
@@ -268,9 +268,6 @@ struct TrialStats {
 // operands x_nom | u_nom | k | K | S | Y | k_s | k_y | K_s | K_y are shared by the group's lanes: they are staged through a
 // double-buffered shared-memory block with asynchronous copies one timestep ahead.  wr: store the trial
 // trajectory, slacks, duals and constraint values into the candidate buffers.
-__host__ __device__ inline int ip_fw_step_doubles(int n, int m, int D) {
-  return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1;
-}
 
 //
 // segment = false (pass 1, warp-uniform): the whole horizon from x0, operands staged as above; with save_ck the state

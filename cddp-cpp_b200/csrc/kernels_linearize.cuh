@@ -20,8 +20,7 @@ namespace kern {
 // The record goes through shared memory in PARTS slices of at most 56 doubles: staging whole records (26.9 KB per warp
 // for the quadrotor, 82.7 KB for a dense n = 14 model) left 6 resp. 2 warps per SM, and the kernel is bound by the
 // latency of its loads and of the FP64 chain that forms the Jacobians, not by the stores.
-__host__ __device__ constexpr int lin_parts(int rs) { return (rs + 55) / 56; }
-__host__ __device__ constexpr int lin_part_width(int rs) { return (rs + lin_parts(rs) - 1) / lin_parts(rs); }
+// (lin_parts / lin_part_width live in engine.h: the host launchers size the shared memory with them)
 
 template <int MODEL, class PAT>
 __global__ void __launch_bounds__(128, 3) linearize_kernel(Constants c, DeviceState d, int force, int warps_per_cta) {

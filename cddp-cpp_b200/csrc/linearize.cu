@@ -258,7 +258,7 @@ template <int MODEL, class PAT>
 cudaError_t launch_linearize_model(const Constants &c, const DeviceState &d, bool force, cudaStream_t stream) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
   using L = RecordLayout<NS, NC, PAT>;
-  constexpr int PSH = kern::lin_part_width(L::stride) | 1;
+  constexpr int PSH = lin_part_width(L::stride) | 1;
   constexpr size_t per_warp = sizeof(double) * 32 * PSH;
   constexpr int wpc = 4;
   static bool configured = false;

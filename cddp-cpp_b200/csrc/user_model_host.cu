@@ -304,7 +304,7 @@ cudaError_t launch_user_linearize(const Constants &c, const DeviceState &d, bool
   UserKernels *uk = static_cast<UserKernels *>(d.user);
   const int n = d.n, m = d.m;
   const int stride = (n * n + n * m + n + 2 * m + 1) & ~1;  // RecordLayout<n, m, DensePattern>::stride
-  const int parts = (stride + 55) / 56, PSH = ((stride + parts - 1) / parts) | 1;  // kern::lin_parts / lin_part_width
+  const int PSH = lin_part_width(stride) | 1;
   const size_t per_warp = sizeof(double) * 32 * PSH;
   int wpc = 4;
   const long long warps = (long long)d.n_slots * ((d.N + 1 + 31) / 32);
@@ -343,8 +343,7 @@ cudaError_t launch_user_ip_forward(const Constants &c, const DeviceState &d, con
                                    cudaStream_t st) {
   UserKernels *uk = static_cast<UserKernels *>(d.user);
   const int per_cta = 64 / 16;  // kern::kFwThreads / LG
-  const int step = (d.n + 2 * d.m + d.m * d.n + 4 * ic.d + 2 * ic.d * d.n + 1) & ~1;  // kern::ip_fw_step_doubles
-  const int table = (ic.d * d.n + ic.d * d.m + 3 * ic.d + 1) & ~1;                     // kern::con_table_doubles
+  const int step = ip_fw_step_doubles(d.n, d.m, ic.d), table = con_table_doubles(d.n, d.m, ic.d);
   const size_t shm = sizeof(double) * ((size_t)table + (size_t)per_cta * 2 * step);   // kern::ip_fw_smem_doubles
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
   void *params[] = {(void *)&c, (void *)&d, (void *)&ic, (void *)&ip, &mode};
