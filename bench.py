@@ -394,9 +394,9 @@ def main():
 
     # ---- leg 3: end to end through the C ABI with pinned HOST buffers, the way a serving loop calls it ----
     # Every call uploads its inputs (x0, xref, X0, U0) host->device and downloads its full solution (X, U, K, cost,
-    # iterations, status) device->host inside the timed region.  Two solver handles on two CUDA streams are used
-    # alternately (double buffering across calls: call k+1's upload + solve overlaps call k's download), each with
-    # its own pinned buffers; "serial" is the same measurement on ONE handle with a blocking call sequence.
+    # iterations, status) device->host inside the timed region.  Three solver handles on three CUDA streams are used in
+    # rotation (call k+1's upload and call k-1's download overlap call k's kernels), each with its own pinned buffers;
+    # "serial" is the same measurement on ONE handle with a blocking call sequence.
     e2e = None
     if not args.no_e2e:
         ipc = args.iters_per_call

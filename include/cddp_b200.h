@@ -296,7 +296,7 @@ CDDP_B200_API int cddp_b200_get_solution(cddp_b200_solver *s, double *X, double 
  * cddp_b200_set_poll_interval(s, 0) cddp_b200_solve only ENQUEUES work on the solver's stream (no host
  * synchronisation; instances that finish early are masked on the device), and cddp_b200_get_solution_async enqueues
  * the device-to-host copies without waiting — call cddp_b200_synchronize before reading the host buffers.  Host
- * buffers must be pinned and stay valid until then.  Two handles on two streams give a double-buffered pipeline in
+ * buffers must be pinned and stay valid until then.  Two or three handles on their own streams give a pipeline in
  * which call k+1's upload + solve overlaps call k's download.  interval -1 = automatic (every iteration from the second
  * on when batch x horizon >= 32768, else at iterations 4, 8, 12, 16, 24, ...), k > 0 = poll every k iterations.  At every
  * poll the still-running instances are compacted into the work list of the per-iteration kernels, so the launches that
