@@ -82,6 +82,8 @@ CDDP_B200_HD constexpr int lin_part_width(int rs) { return (rs + lin_parts(rs) -
 // timestep's operands x | u | k | K | S | Y | k_s | k_y | K_s | K_y of a trajectory
 CDDP_B200_HD constexpr int con_table_doubles(int n, int m, int D) { return (D * n + D * m + 3 * D + 1) & ~1; }
 CDDP_B200_HD constexpr int ip_fw_step_doubles(int n, int m, int D) { return (n + 2 * m + m * n + 4 * D + 2 * D * n + 1) & ~1; }
+// ... preceded by the halved cost matrices Q dt | R dt | Qf (the rollout's running / terminal cost, read every timestep)
+CDDP_B200_HD constexpr int ip_fw_cost_doubles(int n, int m) { return (2 * n * n + m * m + 1) & ~1; }
 
 #ifdef __CUDACC__
 // std::min(std::max(v, lo), hi) as the reference writes it (boxqp.cpp:241-250; Eigen's cwiseMax / cwiseMin in

@@ -281,7 +281,8 @@ template <int MODEL, int DC>
 __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip,
                                            const ConTable &ctab, int b, int cur, double alpha_pr, double alpha_du, double tau,
                                            double mu, TrialStats &st, double *stage, int al, bool wr, bool save_ck,
-                                           bool segment, int t0, int t1, const double *xstart) {
+                                           bool segment, int t0, int t1, const double *xstart, const double *sQh,
+                                           const double *sRh, const double *sQfh) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC, LG = 16;
   const int N = d.N, D = DC ? DC : ic.d;
   const double *Xn = d.X[cur] + (size_t)b * (N + 1) * NS, *Un = d.U[cur] + (size_t)b * N * NC;
@@ -397,14 +398,14 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       for (int j = 0; j < NS; ++j) {
         double rr = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qdt2[i * NS + j]);
+        for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * sQh[i * NS + j];  // 0.5 * (2 Q dt), staged once per CTA
         sx += rr * (x[j] - ref[j]);
       }
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         double rr = 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) rr += u[i] * (0.5 * c.Rdt2[i * NC + j]);
+        for (int i = 0; i < NC; ++i) rr += u[i] * sRh[i * NC + j];
         su += rr * u[j];
       }
       st.cost += sx + su;
@@ -443,7 +444,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
     for (int j = 0; j < NS; ++j) {
       double rr = 0.0;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * (0.5 * c.Qf2[i * NS + j]);
+      for (int i = 0; i < NS; ++i) rr += (x[i] - ref[i]) * sQfh[i * NS + j];
       sx += rr * (x[j] - ref[j]);
     }
     st.cost += sx;
@@ -475,7 +476,7 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
 // the group in lock-step, lane 0 writing the candidate buffers); lane 0 then runs the per-instance bookkeeping.
 // DC: compile-time total dual dimension (0 = runtime) — the per-row loops of the rollout unroll.
 __host__ __device__ inline int ip_fw_smem_doubles(int n, int m, int D) {
-  return con_table_doubles(n, m, D) + (kFwThreads / 16) * 2 * ip_fw_step_doubles(n, m, D);
+  return ip_fw_cost_doubles(n, m) + con_table_doubles(n, m, D) + (kFwThreads / 16) * 2 * ip_fw_step_doubles(n, m, D);
 }
 
 template <int MODEL, int DC = 0>
@@ -485,14 +486,22 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   constexpr int NS_ = Model<MODEL>::NS, NC_ = Model<MODEL>::NC;
   extern __shared__ double fw_smem[];
   const int Dd = DC ? DC : ic.d;
-  const ConTable ctab = con_table_stage(ic, fw_smem, NS_, NC_, Dd);  // constraint rows: one shared-memory copy per CTA
+  // shared memory: halved cost matrices | constraint table | per-group staging blocks
+  double *sQh = fw_smem, *sRh = sQh + NS_ * NS_, *sQfh = sRh + NC_ * NC_;
+  for (int i = threadIdx.x; i < NS_ * NS_; i += blockDim.x) {
+    sQh[i] = 0.5 * c.Qdt2[i];
+    sQfh[i] = 0.5 * c.Qf2[i];
+  }
+  for (int i = threadIdx.x; i < NC_ * NC_; i += blockDim.x) sRh[i] = 0.5 * c.Rdt2[i];
+  double *tab_smem = fw_smem + ip_fw_cost_doubles(NS_, NC_);
+  const ConTable ctab = con_table_stage(ic, tab_smem, NS_, NC_, Dd);  // constraint rows: one shared-memory copy per CTA
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int grp = lane / LG, al = lane % LG;
   const int b = slot_instance(d, ((blockIdx.x * kFwThreads + threadIdx.x) >> 5) * 2 + grp);
   const bool alive = b < d.B && !(mode == FW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
   if (!__any_sync(0xffffffffu, alive)) return;
-  double *stage = fw_smem + con_table_doubles(NS_, NC_, Dd) + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, Dd);
+  double *stage = tab_smem + con_table_doubles(NS_, NC_, Dd) + (size_t)(threadIdx.x / LG) * 2 * ip_fw_step_doubles(NS_, NC_, Dd);
   const int bb = alive ? b : 0;
   const int na = c.num_alphas, D = Dd;
   const int cur = d.cur[bb];
@@ -514,7 +523,9 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   const double *r_xs = nullptr;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-    if (r_run) ip_rollout<MODEL, DC>(c, d, ic, ip, ctab, bb, cur, r_apr, r_adu, tau, mu, st, stage, al, r_wr, r_ck, r_seg, r_t0, r_t1, r_xs);
+    if (r_run)
+      ip_rollout<MODEL, DC>(c, d, ic, ip, ctab, bb, cur, r_apr, r_adu, tau, mu, st, stage, al, r_wr, r_ck, r_seg, r_t0, r_t1, r_xs, sQh,
+                            sRh, sQfh);
     if (pass == 1) break;
     const double phi_new = (st.cost - mu * st.logsum) + st.lamh;  // computeBarrierMerit (:2850-2880)
     const double theta_new = st.theta;

@@ -344,7 +344,7 @@ cudaError_t launch_user_ip_forward(const Constants &c, const DeviceState &d, con
   UserKernels *uk = static_cast<UserKernels *>(d.user);
   const int per_cta = 64 / 16;  // kern::kFwThreads / LG
   const int step = ip_fw_step_doubles(d.n, d.m, ic.d), table = con_table_doubles(d.n, d.m, ic.d);
-  const size_t shm = sizeof(double) * ((size_t)table + (size_t)per_cta * 2 * step);   // kern::ip_fw_smem_doubles
+  const size_t shm = sizeof(double) * ((size_t)ip_fw_cost_doubles(d.n, d.m) + table + (size_t)per_cta * 2 * step);  // kern::ip_fw_smem_doubles
   if (shm > 200 * 1024) return cudaErrorInvalidValue;
   void *params[] = {(void *)&c, (void *)&d, (void *)&ic, (void *)&ip, &mode};
   return launch(uk, K_IPFWD, (unsigned)((d.n_slots + per_cta - 1) / per_cta), 64, shm, st, params);
