@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   constexpr int QN = DIAG ? NS : NS * NS, RN = DIAG ? NC : NC * NC;
   __shared__ double sQ[QN], sR[RN], sQf[QN];
   __shared__ double stage[kWarpsPerCta][TPW][2][STEPP];
+  __shared__ double sref[kWarpsPerCta][TPW][NS];  // the instance's reference state (read every timestep by every lane)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < QN; i += blockDim.x) {
     const int src = DIAG ? i * NS + i : i;
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   double *Uc = d.U[cur ^ 1] + (size_t)bb * N * NC;
   const double *gK = d.K + (size_t)bb * N * NC * NS;
   const double *gk = d.kff + (size_t)bb * N * NC;
-  const double *xref = d.xref + (size_t)bb * NS;
+  for (int i = al; i < NS; i += LG) sref[warp][grp][i] = d.xref[(size_t)bb * NS + i];
+  __syncwarp();
+  const double *xref = sref[warp][grp];
   const double *rtraj = d.ref_traj ? d.ref_traj + (size_t)bb * (N + 1) * NS : nullptr;
   double *ck = d.ckpt + ((size_t)bb * LG + al) * LG * NS;  // this lane's saved states [LG][NS]
   double(*st)[STEPP] = stage[warp][grp];
