@@ -138,7 +138,7 @@ ABI_SYMBOLS = [
     "cddp_b200_ipddp_default_options", "cddp_b200_ipddp_create", "cddp_b200_ipddp_dual_dim",
     "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
     "cddp_b200_ipddp_get_history", "cddp_b200_create_ex", "cddp_b200_ipddp_create_ex", "cddp_b200_compile_user_model",
-    "cddp_b200_last_compile_log",
+    "cddp_b200_last_compile_log", "cddp_b200_enable_trace", "cddp_b200_get_trace",
 ]
 
 
@@ -443,6 +443,17 @@ class BatchedCLDDP:
         return h, lens
 
     # ---- white box ----
+    def enable_trace(self, enable: bool = True):
+        _check(self.lib.cddp_b200_enable_trace(self.handle, int(enable)))
+
+    def get_trace(self) -> np.ndarray:
+        """[B][max_iterations] decision codes (cddp_b200_get_trace)."""
+        cap = C.c_int(0)
+        tr = np.zeros((self.B, max(int(self.opts.max_iterations), 1)), dtype=np.int32)
+        _check(self.lib.cddp_b200_get_trace(self.handle, C.c_void_p(tr.ctypes.data), C.byref(cap)))
+        assert cap.value == tr.shape[1], (cap.value, tr.shape)
+        return tr
+
     def get_feedforward(self) -> np.ndarray:
         k = np.empty((self.B, self.N, self.m))
         _check(self.lib.cddp_b200_get_feedforward(self.handle, _ptr(k)))

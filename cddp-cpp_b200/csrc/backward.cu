@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) backward_kernel(Constants c
 
   bool ok = false;
   double dV0 = 0.0, dV1 = 0.0, inf_du = 0.0;
-  int status = CDDP_B200_STATUS_RUNNING;
+  int status = CDDP_B200_STATUS_RUNNING, failures = 0;
 
   while (true) {
     // ---- one sweep at regularisation `reg` ----
@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) backward_kernel(Constants c
     if (mode == BW_SINGLE) break;
     // backward failure: increaseRegularization + limit test (cddp_solver_base.cpp:95-109)
     reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+    ++failures;
     if (reg >= c.opt.reg_max_value) {
       status = CDDP_B200_STATUS_REG_LIMIT;
       break;
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) backward_kernel(Constants c
         }
       }
       if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+      trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
     }
   }
 }

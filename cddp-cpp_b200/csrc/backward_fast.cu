@@ -474,7 +474,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     double reg = alive ? d.reg[b] : 0.0;
     if (alive && mode == BW_ITERATE) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
     double dV0 = 0.0, dV1 = 0.0, Qu_err = 0.0;
-    int qt = N - 1, status = CDDP_B200_STATUS_RUNNING;
+    int qt = N - 1, status = CDDP_B200_STATUS_RUNNING, failures = 0;
     bool run = alive, ok = false;
     constexpr unsigned all = (1u << NC) - 1u;
     while (true) {
@@ -602,6 +602,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         } else {
           // increaseRegularization + limit test (cddp_solver_base.cpp:95-109, cddp_core.cpp:308-326)
           reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+          ++failures;
           if (reg >= c.opt.reg_max_value) {
             status = CDDP_B200_STATUS_REG_LIMIT;
             *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_FAIL;
@@ -645,6 +646,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
           }
         }
         if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+        trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
       }
     }
   }

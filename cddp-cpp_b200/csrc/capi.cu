@@ -77,6 +77,8 @@ struct cddp_b200_solver {
   bool timing_enabled = false;
   cddp_b200_timing timing{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *history_buf = nullptr;  // the allocation behind d.history (which is null while history is disabled)
+  int *trace_buf = nullptr;       // same for d.trace
   // scratch for host-pointer setters / getters
   double *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -117,6 +119,13 @@ struct DeviceGuard {
   }
 };
 
+// option checks shared by create and cddp_b200_set_options; kind 1 = IPDDP (one lane per alpha, 16 lanes per trajectory)
+int validate_options(const cddp_b200_options &o, int kind) {
+  if (o.max_iterations < 0 || o.ls_max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (count_alphas(o) > (kind == 1 ? 16 : CDDP_B200_MAX_ALPHAS)) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  return 0;
+}
+
 int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, bool has_user_source = false) {
   if (!p || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
   if (batch < 1 || p->horizon < 1 || !(p->dt > 0.0)) return CDDP_B200_ERR_INVALID_ARGUMENT;
@@ -133,9 +142,7 @@ int validate(const cddp_b200_problem *p, const cddp_b200_options *o, int batch, 
     case CDDP_B200_MODEL_USER: if (!has_user_source) return CDDP_B200_ERR_UNSUPPORTED_MODEL; break;  // no source, no device dynamics
     default: return CDDP_B200_ERR_UNSUPPORTED_MODEL;
   }
-  if (o->max_iterations < 0 || o->ls_max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
-  if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS) return CDDP_B200_ERR_INVALID_ARGUMENT;
-  return 0;
+  return validate_options(*o, 0);
 }
 
 void set_options(cddp_b200_solver *s, const cddp_b200_options &o) {
@@ -442,6 +449,7 @@ int cddp_b200_create_ex(const cddp_b200_problem *p, const cddp_b200_options *o, 
   AL(d.ckpt, B * s->ckpt_lg * s->ckpt_lg * n);
   AL(d.num_running, 1);
   d.history = nullptr; d.history_len = nullptr; d.history_cap = 0;
+  d.trace = nullptr; d.trace_cap = 0;
 #undef AL
   e = cudaMemset(d.cur, 0, B * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d.status, 0, B * sizeof(int));
@@ -490,8 +498,9 @@ int cddp_b200_set_stream(cddp_b200_solver *s, void *stream) {
 
 int cddp_b200_set_options(cddp_b200_solver *s, const cddp_b200_options *o) {
   if (!s || !o) return CDDP_B200_ERR_INVALID_ARGUMENT;
-  if (count_alphas(*o) > CDDP_B200_MAX_ALPHAS || o->max_iterations < 0) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (int r = validate_options(*o, s->kind)) return r;
   if (s->d.history && o->max_iterations + 1 > s->d.history_cap) return CDDP_B200_ERR_STATE;
+  if (s->d.trace && o->max_iterations > s->d.trace_cap) return CDDP_B200_ERR_STATE;
   if (count_alphas(*o) > 16 && s->ckpt_lg < 32) {  // more than 16 alphas: one trajectory per warp, bigger scratch
     DeviceGuard g(s->device);
     double *p = nullptr;
@@ -589,6 +598,13 @@ int cddp_b200_solve(cddp_b200_solver *s) {
   const auto t0 = std::chrono::steady_clock::now();
   const int max_it = s->c.opt.max_iterations;
   int final_status = CDDP_B200_STATUS_MAX_ITERATIONS;
+  struct WorkListReset {  // single-step entry points and the next solve address the whole batch, also after an error return
+    cddp_b200_solver *s;
+    ~WorkListReset() {
+      s->d.order = nullptr;
+      s->d.n_slots = s->d.B;
+    }
+  } work_list_reset{s};
   // poll the running counter with a widening stride: cheap for short solves, rare for long ones.  With
   // poll_interval == 0 the solve is enqueued without any host synchronisation (finished instances are masked on
   // the device, so running the remaining launches is correct, just not free).
@@ -727,21 +743,54 @@ int cddp_b200_enable_history(cddp_b200_solver *s, int enable) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
   DeviceGuard g(s->device);
   if (!enable) {
-    s->d.history = nullptr;
+    s->d.history = nullptr;  // the buffer stays allocated (history_buf) for a later re-enable
     return 0;
   }
   const int cap = s->c.opt.max_iterations + 1;
-  if (!s->d.history_len || cap > s->d.history_cap) {
+  if (!s->history_buf || cap > s->d.history_cap) {
     double *h = nullptr;
     int *l = nullptr;
     int r;
     if ((r = s->alloc(&h, (size_t)s->d.B * cap * (s->kind == 1 ? IP_HISTORY_COLS : 4)))) return r;
     if ((r = s->alloc(&l, (size_t)s->d.B))) return r;
-    s->d.history = h;
+    s->history_buf = h;
     s->d.history_len = l;
     s->d.history_cap = cap;
     CU(cudaMemset(l, 0, (size_t)s->d.B * sizeof(int)));
   }
+  s->d.history = s->history_buf;
+  return 0;
+}
+
+int cddp_b200_enable_trace(cddp_b200_solver *s, int enable) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (s->kind == 1) return CDDP_B200_ERR_INVALID_ARGUMENT;  // CLDDP handles only
+  DeviceGuard g(s->device);
+  if (!enable) {
+    s->d.trace = nullptr;
+    return 0;
+  }
+  const int cap = s->c.opt.max_iterations > 0 ? s->c.opt.max_iterations : 1;
+  if (!s->trace_buf || cap > s->d.trace_cap) {
+    int *t = nullptr;
+    int r;
+    if ((r = s->alloc(&t, (size_t)s->d.B * cap))) return r;
+    s->trace_buf = t;
+    s->d.trace_cap = cap;
+  }
+  CU(cudaMemsetAsync(s->trace_buf, 0, (size_t)s->d.B * s->d.trace_cap * sizeof(int), s->stream));
+  s->d.trace = s->trace_buf;
+  return 0;
+}
+
+int cddp_b200_get_trace(cddp_b200_solver *s, int *trace, int *cap) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  if (!s->d.trace) return CDDP_B200_ERR_STATE;
+  DeviceGuard g(s->device);
+  if (cap) *cap = s->d.trace_cap;
+  int r;
+  if ((r = download(s, trace, s->d.trace, (size_t)s->d.B * s->d.trace_cap * sizeof(int)))) return r;
+  CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
 

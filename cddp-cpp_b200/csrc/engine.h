@@ -65,6 +65,11 @@ struct DeviceState {
   double *history; // [B][max_iterations+1][4] or nullptr
   int *history_len;
   int history_cap;
+  // decision trace (test / audit instrumentation, cddp_b200_enable_trace): one int per entry of the main loop,
+  // (backward failures << 8) | code, code = 1 + index of the accepted alpha, 0 = line search failed,
+  // 0xff = early convergence exit, 0xfe = regularisation limit in the backward retry
+  int *trace;  // [B][trace_cap] or nullptr
+  int trace_cap;
   int *num_running;  // device counter
   void *user;        // HOST pointer (never dereferenced on the device): NVRTC-compiled kernels of a CDDP_B200_MODEL_USER handle
 };
@@ -97,6 +102,14 @@ __device__ __forceinline__ double clamp_box(double v, double lo, double hi) {
 // std::max / std::min as compare-select (same reason): (a < b) ? b : a and (b < a) ? b : a
 __device__ __forceinline__ double max_ref(double a, double b) { return (a < b) ? b : a; }
 __device__ __forceinline__ double min_ref(double a, double b) { return (b < a) ? b : a; }
+// decision trace: the sweep stores (failures << 8) | code for iteration `iter` (1-based), the line search adds its code
+__device__ __forceinline__ void trace_backward(const DeviceState &d, int b, int iter, int failures, int code) {
+  if (d.trace && iter >= 1 && iter <= d.trace_cap) d.trace[(size_t)b * d.trace_cap + iter - 1] = (failures << 8) | code;
+}
+__device__ __forceinline__ void trace_line_search(const DeviceState &d, int b, int accepted) {
+  const int iter = d.iter[b];
+  if (d.trace && accepted >= 0 && iter >= 1 && iter <= d.trace_cap) d.trace[(size_t)b * d.trace_cap + iter - 1] |= 1 + accepted;
+}
 // instance handled by work-list slot `slot` (d.B = none)
 __device__ __forceinline__ int slot_instance(const DeviceState &d, int slot) {
   return slot < d.n_slots ? (d.order ? d.order[slot] : slot) : d.B;

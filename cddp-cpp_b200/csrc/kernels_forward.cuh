@@ -44,6 +44,7 @@ __device__ __forceinline__ int select_alpha(bool success, double J, int al, int 
 __device__ inline void finish_line_search(const Constants &c, const DeviceState &d, int b, int mode, int first, double Jacc) {
   d.accepted[b] = first;
   if (mode != FW_ITERATE) return;
+  trace_line_search(d, b, first);
   double reg = d.reg[b];
   int status = CDDP_B200_STATUS_RUNNING;
   if (first >= 0) {

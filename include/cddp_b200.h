@@ -319,6 +319,14 @@ CDDP_B200_API int cddp_b200_get_first_controls_async(cddp_b200_solver *s, double
  * {objective, step_length_primal, dual_infeasibility, regularization}; lens [B] */
 CDDP_B200_API int cddp_b200_enable_history(cddp_b200_solver *s, int enable);
 CDDP_B200_API int cddp_b200_get_history(cddp_b200_solver *s, double *history, int *lens);
+/* Decision trace (audit / parity instrumentation, no reference counterpart; CLDDP handles).  One int per entry of the
+ * main loop of CDDPSolverBase::solve (cddp_solver_base.cpp:74) and instance, [B][cap], cap = max_iterations at enable
+ * time: (backward-pass failures of this iteration << 8) | code, code = 1 + index of the accepted alpha
+ * (performForwardPass, :248-263), 0 = no alpha accepted (handleForwardPassFailure, :206-218), 0xff = early convergence
+ * exit (clddp_solver.cpp:206-213), 0xfe = regularisation limit during the backward retry (:95-109).  The parity tests
+ * feed it to the CPU oracle, which then follows the same decision sequence. */
+CDDP_B200_API int cddp_b200_enable_trace(cddp_b200_solver *s, int enable);
+CDDP_B200_API int cddp_b200_get_trace(cddp_b200_solver *s, int *trace, int *cap);
 
 /* ---- white-box access for parity tests (the reference's tests use a friend shim the same way,
  * tests/cddp_core/test_ipddp_solver.cpp:30-134) ---- */

@@ -1026,7 +1026,7 @@ int backward_pass(const oracle_problem *p, const oracle_options *o, const double
 /* CLDDPSolver::forwardPass (clddp_solver.cpp:215-262) */
 int forward_pass(const oracle_problem *p, const oracle_options *o, const double *x0, const double *X, const double *U,
                  const double *xref, const double *ref_traj, const double *K, const double *k, const double *dV,
-                 double cost, double alpha, double *Xn, double *Un, double *Jn) {
+                 double cost, double alpha, double *Xn, double *Un, double *Jn, double *ratio_out = nullptr) {
   const int n = p->n, m = p->m, N = p->horizon;
   std::memcpy(Xn, x0, sizeof(double) * n); /* :224 */
   double J = 0.0;
@@ -1050,6 +1050,7 @@ int forward_pass(const oracle_problem *p, const oracle_options *o, const double 
   const double expected = -alpha * (dV[0] + 0.5 * alpha * dV[1]);
   const double ratio = expected > 0.0 ? dJ / expected : std::copysign(1.0, dJ);
   *Jn = J;
+  if (ratio_out) *ratio_out = ratio;
   return ratio > o->armijo_constant ? 1 : 0;
 }
 
@@ -1069,9 +1070,30 @@ int build_alphas(const oracle_options *o, double *alphas) { /* cddp_context_util
 }
 
 /* CDDP::solve("CLDDP"): cddp_core.cpp:235-306 + clddp_solver.cpp:28-75 + cddp_solver_base.cpp:29-186 */
+struct Replay;
+void solve_one_replay(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
+                      const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
+                      double *history, const Replay &rp, oracle_replay_report *rep);
+
+/* Decision trace (test instrumentation, no reference counterpart): one int per entry of the main loop,
+ * (backward failures in this iteration << 8) | code, code = ORACLE_TRACE_* or 1 + index of the accepted alpha.
+ * With `replay` the solve FOLLOWS a recorded decision sequence instead of taking its own accept / reject / converged
+ * decisions (all arithmetic is still the oracle's); `rep` then reports where its own verdict would have differed
+ * and by how much it missed the threshold. */
+struct Replay {
+  const int *trace;
+  int iterations;
+  int status;
+};
+
 void solve_one(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
                const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
-               double *history) {
+               double *history, int *trace_out = nullptr, const Replay *replay = nullptr,
+               oracle_replay_report *rep = nullptr) {
+  if (replay) {
+    solve_one_replay(p, o, x0, xref, ref_traj, X, U, K, k, res, history, *replay, rep);
+    return;
+  }
   const int n = p->n, m = p->m, N = p->horizon;
   double alphas[ORACLE_MAX_ALPHAS];
   const int na = build_alphas(o, alphas);
@@ -1111,10 +1133,12 @@ void solve_one(const oracle_problem *p, const oracle_options *o, const double *x
       }
     }
     bool backward_ok = false; /* :93-111 */
+    int bw_fail = 0;
     while (!backward_ok) {
       backward_ok = backward_pass(p, o, nullptr, nullptr, X, U, xref, ref_traj, reg, K, k, dV, &inf_du, nullptr,
                                   nullptr, nullptr) != 0;
       if (!backward_ok) {
+        ++bw_fail;
         reg = std::min(reg * o->reg_update_factor, o->reg_max_value); /* cddp_core.cpp:308-314 */
         if (reg >= o->reg_max_value) {
           status = ORACLE_REG_LIMIT;
@@ -1122,20 +1146,24 @@ void solve_one(const oracle_problem *p, const oracle_options *o, const double *x
         }
       }
     }
+    if (trace_out) trace_out[iter - 1] = (bw_fail << 8) | (backward_ok ? ORACLE_TRACE_LS_FAILED : ORACLE_TRACE_BW_LIMIT);
     if (!backward_ok) break;
     if (inf_du < o->tolerance) { /* clddp_solver.cpp:206-213 */
       status = ORACLE_OPTIMAL;
       converged = true;
       record();
+      if (trace_out) trace_out[iter - 1] = (bw_fail << 8) | ORACLE_TRACE_EARLY_EXIT;
       break;
     }
     bool fp_success = false; /* cddp_solver_base.cpp:255-263: first success wins */
     double Jn = 0.0, a_acc = 0.0;
+    int a_idx = -1;
     if (!o->enable_parallel) {
       for (int ai = 0; ai < na; ++ai) {
         if (forward_pass(p, o, x0, X, U, xref, ref_traj, K, k, dV, cost, alphas[ai], Xn.data(), Un.data(), &Jn)) {
           fp_success = true;
           a_acc = alphas[ai];
+          a_idx = ai;
           break;
         }
       }
@@ -1149,12 +1177,14 @@ void solve_one(const oracle_problem *p, const oracle_options *o, const double *x
           best = Jt;
           fp_success = true;
           a_acc = alphas[ai];
+          a_idx = ai;
           Jn = Jt;
           Xn = Xt;
           Un = Ut;
         }
       }
     }
+    if (trace_out && fp_success) trace_out[iter - 1] = (bw_fail << 8) | (1 + a_idx);
     if (fp_success) { /* :129-139 */
       const double dJ = cost - Jn;
       std::memcpy(X, Xn.data(), sizeof(double) * (N + 1) * n);
@@ -1189,6 +1219,190 @@ void solve_one(const oracle_problem *p, const oracle_options *o, const double *x
   res->reserved = 0;
 }
 
+/* ONE entry of the main loop of CDDPSolverBase::solve (cddp_solver_base.cpp:74-170) from a given solver state —
+ * test instrumentation: the same statements as the loop body of solve_one, with two additions.
+ *   (1) `follow` >= 0: a recorded decision ((backward failures << 8) | code, see cddp_oracle.h) and, in
+ *       `follow_status`, the recorded status after this iteration (ORACLE_RUNNING = the solve went on).  Every `if`
+ *       on a line-search / convergence / backward-failure verdict then takes the RECORDED branch; all arithmetic is
+ *       still the oracle's.
+ *   (2) own verdicts are always evaluated; where one differs from the recorded branch, rep counts it and keeps the
+ *       largest MARGIN: how far the tested quantity was from its threshold, measured in the units in which roundoff
+ *       enters it — |dJ - c*expected| / |cost| for the Armijo test (clddp_solver.cpp:251-257), the same for
+ *       0 < dJ < acceptable_tolerance (:272-275), |inf_du - tol| / tol for the inf_du tests (:206-213, :268-271).
+ * Returns the decision taken in *code_out and the status after the iteration in *status_out. */
+struct IterState {
+  double *X, *U, *K, *k;
+  double reg, cost, alpha_pr, inf_du;
+  double dV[2];
+};
+
+void iterate_once(const oracle_problem *p, const oracle_options *o, const double *alphas, int na, const double *x0,
+                  const double *xref, const double *ref_traj, IterState &st, int follow, int follow_status,
+                  int *code_out, int *status_out, double *reg_used_out, oracle_replay_report &R, std::vector<double> &Xn,
+                  std::vector<double> &Un, std::vector<double> &Xt, std::vector<double> &Ut) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  const bool rec = follow >= 0;
+  const int rcode = rec ? (follow & 0xff) : 0, rfail = rec ? (follow >> 8) : 0;
+  auto margin = [&](double dist, double scale) {
+    ++R.n_disagree;
+    const double mg = std::fabs(dist) / std::max(std::fabs(scale), 1e-300);
+    if (!(mg <= R.max_margin)) R.max_margin = mg; /* NaN sticks */
+  };
+  *status_out = ORACLE_RUNNING;
+  *reg_used_out = st.reg;
+  /* backward pass with regularisation retry (:93-111) */
+  bool ok = false;
+  int bw_fail = 0;
+  while (true) {
+    if (rec && bw_fail == rfail && rcode == ORACLE_TRACE_BW_LIMIT) break;
+    ok = backward_pass(p, o, nullptr, nullptr, st.X, st.U, xref, ref_traj, st.reg, st.K, st.k, st.dV, &st.inf_du, nullptr,
+                       nullptr, nullptr) != 0;
+    if (rec) {
+      if (bw_fail < rfail) {
+        if (ok) ++R.n_backward_disagree; /* recorded: failure; own: success */
+        ok = false;
+      } else if (!ok) {
+        ++R.n_backward_disagree; /* recorded: success; own: failure -> the sequence cannot be followed */
+        R.infeasible = 1;
+        break;
+      }
+    }
+    if (ok) break;
+    ++bw_fail;
+    st.reg = std::min(st.reg * o->reg_update_factor, o->reg_max_value); /* cddp_core.cpp:308-314 */
+    if (!rec && st.reg >= o->reg_max_value) break;
+  }
+  if (!ok) {
+    *code_out = (bw_fail << 8) | ORACLE_TRACE_BW_LIMIT;
+    *status_out = ORACLE_REG_LIMIT;
+    return;
+  }
+  *reg_used_out = st.reg; /* the regularisation of the successful sweep (what recordIterationHistory sees) */
+  const bool own_early = st.inf_du < o->tolerance; /* clddp_solver.cpp:206-213 */
+  const bool early = rec ? rcode == ORACLE_TRACE_EARLY_EXIT : own_early;
+  if (own_early != early) margin(st.inf_du - o->tolerance, o->tolerance);
+  if (early) {
+    *code_out = (bw_fail << 8) | ORACLE_TRACE_EARLY_EXIT;
+    *status_out = ORACLE_OPTIMAL;
+    return;
+  }
+  /* line search (cddp_solver_base.cpp:255-285) */
+  int acc = -1;
+  double Jn = 0.0;
+  auto armijo_distance = [&](double Jt, double alpha) { /* distance of dJ to the acceptance threshold */
+    const double dJ = st.cost - Jt, expected = -alpha * (st.dV[0] + 0.5 * alpha * st.dV[1]);
+    return expected > 0.0 ? dJ - o->armijo_constant * expected : dJ;
+  };
+  if (!o->enable_parallel) {
+    const int racc = rcode - 1;
+    const int upto = rec ? (racc >= 0 ? racc : na - 1) : na - 1;
+    for (int ai = 0; ai <= upto; ++ai) {
+      double Jt = 0.0;
+      const bool s = forward_pass(p, o, x0, st.X, st.U, xref, ref_traj, st.K, st.k, st.dV, st.cost, alphas[ai], Xt.data(),
+                                  Ut.data(), &Jt) != 0;
+      const bool take = rec ? ai == racc : s;
+      if (s != take) margin(armijo_distance(Jt, alphas[ai]), st.cost);
+      if (take) {
+        acc = ai;
+        Jn = Jt;
+        Xn.swap(Xt);
+        Un.swap(Ut);
+        break;
+      }
+    }
+  } else { /* lowest cost among the accepted candidates (:264-285) */
+    double best = std::numeric_limits<double>::infinity();
+    int own = -1;
+    const int racc = rcode - 1;
+    for (int ai = 0; ai < na; ++ai) {
+      double Jt = 0.0;
+      const bool s = forward_pass(p, o, x0, st.X, st.U, xref, ref_traj, st.K, st.k, st.dV, st.cost, alphas[ai], Xt.data(),
+                                  Ut.data(), &Jt) != 0;
+      if (s && Jt < best) {
+        best = Jt;
+        own = ai;
+      }
+      if (rec ? ai == racc : (own == ai)) {
+        acc = ai;
+        Jn = Jt;
+        Xn.swap(Xt);
+        Un.swap(Ut);
+      }
+    }
+    if (rec && own != racc) margin(racc >= 0 && own >= 0 ? Jn - best : st.cost, st.cost);
+  }
+  *code_out = (bw_fail << 8) | (acc >= 0 ? 1 + acc : ORACLE_TRACE_LS_FAILED);
+  if (acc >= 0) { /* :129-139 */
+    const double dJ = st.cost - Jn;
+    std::memcpy(st.X, Xn.data(), sizeof(double) * (N + 1) * n);
+    std::memcpy(st.U, Un.data(), sizeof(double) * N * m);
+    st.cost = Jn;
+    st.alpha_pr = alphas[acc];
+    st.reg = std::max(st.reg / o->reg_update_factor, o->reg_min_value); /* cddp_core.cpp:316-322 */
+    const bool own_opt = st.inf_du < o->tolerance; /* clddp_solver.cpp:264-277 */
+    const bool own_acc = !own_opt && dJ > 0.0 && dJ < o->acceptable_tolerance;
+    const bool r_opt = rec ? follow_status == ORACLE_OPTIMAL : own_opt;
+    const bool r_acc = rec ? follow_status == ORACLE_ACCEPTABLE : own_acc;
+    if (own_opt != r_opt) margin(st.inf_du - o->tolerance, o->tolerance);
+    else if (own_acc != r_acc)
+      margin(std::min(std::fabs(dJ), std::fabs(dJ - o->acceptable_tolerance)), st.cost);
+    if (r_opt) *status_out = ORACLE_OPTIMAL;
+    else if (r_acc) *status_out = ORACLE_ACCEPTABLE;
+  } else { /* handleForwardPassFailure, cddp_solver_base.cpp:206-218 */
+    st.reg = std::min(st.reg * o->reg_update_factor, o->reg_max_value);
+    if (rec ? follow_status == ORACLE_REG_LIMIT : st.reg >= o->reg_max_value) *status_out = ORACLE_REG_LIMIT;
+  }
+}
+
+/* CDDP::solve("CLDDP") driven by a recorded decision sequence: initialisation as solve_one, then iterate_once per
+ * recorded entry. */
+void solve_one_replay(const oracle_problem *p, const oracle_options *o, const double *x0, const double *xref,
+                      const double *ref_traj, double *X, double *U, double *K, double *k, oracle_result *res,
+                      double *history, const Replay &rp, oracle_replay_report *rep) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  std::memcpy(X, x0, sizeof(double) * n);
+  std::fill(K, K + (size_t)N * m * n, 0.0);
+  std::fill(k, k + (size_t)N * m, 0.0);
+  IterState st{X, U, K, k, o->reg_initial_value, 0.0, o->ls_initial_step_size, std::numeric_limits<double>::infinity(), {0.0, 0.0}};
+  st.cost = trajectory_cost(p, X, U, xref, ref_traj);
+  std::vector<double> Xn((size_t)(N + 1) * n), Un((size_t)N * m), Xt((size_t)(N + 1) * n), Ut((size_t)N * m);
+  oracle_replay_report R;
+  std::memset(&R, 0, sizeof(R));
+  int hl = 0;
+  auto record = [&](double reg) {
+    if (history) {
+      history[hl * 4 + 0] = st.cost;
+      history[hl * 4 + 1] = st.alpha_pr;
+      history[hl * 4 + 2] = st.inf_du;
+      history[hl * 4 + 3] = reg;
+      ++hl;
+    }
+  };
+  record(st.reg);
+  int iter = 0;
+  while (iter < rp.iterations && !R.infeasible) {
+    ++iter;
+    const bool last = iter == rp.iterations;
+    if (last && rp.status == ORACLE_MAX_CPU_TIME) break;
+    int code = 0, status = 0;
+    double reg_used = st.reg;
+    iterate_once(p, o, alphas, na, x0, xref, ref_traj, st, rp.trace[iter - 1], last ? rp.status : ORACLE_RUNNING, &code,
+                 &status, &reg_used, R, Xn, Un, Xt, Ut);
+    const int c = code & 0xff;
+    if (c == ORACLE_TRACE_EARLY_EXIT || (c >= 1 && c < ORACLE_TRACE_BW_LIMIT)) record(reg_used); /* :116-118, :132-135 */
+  }
+  res->final_objective = st.cost;
+  res->final_step_length = st.alpha_pr;
+  res->final_regularization = st.reg;
+  res->inf_du = st.inf_du;
+  res->iterations = iter;
+  res->status = rp.status;
+  res->history_len = hl;
+  res->reserved = 0;
+  if (rep) *rep = R;
+}
 
 /* ==========================================================================================
  * IPDDP (src/cddp_core/ipddp_solver.cpp) — cold start (options.warm_start = false), use_ilqr = true
@@ -2562,15 +2776,69 @@ void oracle_solve(const oracle_problem *p, const oracle_options *o, const double
 void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
                         const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
                         oracle_result *res) {
+  oracle_solve_batch_traced(p, o, batch, nthreads, x0, xref, ref_traj, X, U, K, k, res, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, nullptr);
+}
+
+void oracle_solve_batch_traced(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                               const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                               oracle_result *res, double *history, int *trace_out, const int *replay_trace,
+                               const int *replay_iterations, const int *replay_status, oracle_replay_report *rep) {
   const int n = p->n, m = p->m, N = p->horizon;
+  const size_t hstride = (size_t)(o->max_iterations + 1) * 4, tstride = (size_t)(o->max_iterations > 0 ? o->max_iterations : 1);
   if (nthreads < 1) nthreads = 1;
   if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
   auto work = [&](int tid) {
     const int lo = (int)((long long)batch * tid / nthreads), hi = (int)((long long)batch * (tid + 1) / nthreads);
     for (int b = lo; b < hi; ++b) {
+      Replay rp{nullptr, 0, 0};
+      if (replay_trace) rp = Replay{replay_trace + (size_t)b * tstride, replay_iterations[b], replay_status[b]};
       solve_one(p, o, x0 + (size_t)b * n, xref + (size_t)b * n,
                 ref_traj ? ref_traj + (size_t)b * (N + 1) * n : nullptr, X + (size_t)b * (N + 1) * n,
-                U + (size_t)b * N * m, K + (size_t)b * N * m * n, k + (size_t)b * N * m, res + b, nullptr);
+                U + (size_t)b * N * m, K + (size_t)b * N * m * n, k + (size_t)b * N * m, res + b,
+                history ? history + (size_t)b * hstride : nullptr, trace_out ? trace_out + (size_t)b * tstride : nullptr,
+                replay_trace ? &rp : nullptr, rep ? rep + b : nullptr);
+    }
+  };
+  if (nthreads == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+  for (auto &t : th) t.join();
+}
+
+void oracle_iterate_batch(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                          const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                          double *reg, double *cost, double *alpha, double *inf_du, double *dV, const int *follow,
+                          const int *follow_status, int *code, int *status, oracle_replay_report *rep) {
+  const int n = p->n, m = p->m, N = p->horizon;
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
+  auto work = [&](int tid) {
+    const int lo = (int)((long long)batch * tid / nthreads), hi = (int)((long long)batch * (tid + 1) / nthreads);
+    std::vector<double> Xn((size_t)(N + 1) * n), Un((size_t)N * m), Xt((size_t)(N + 1) * n), Ut((size_t)N * m);
+    for (int b = lo; b < hi; ++b) {
+      IterState st{X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, K + (size_t)b * N * m * n, k + (size_t)b * N * m,
+                   reg[b], cost[b], alpha[b], inf_du[b], {0.0, 0.0}};
+      oracle_replay_report R;
+      std::memset(&R, 0, sizeof(R));
+      double reg_used = 0.0;
+      iterate_once(p, o, alphas, na, x0 + (size_t)b * n, xref + (size_t)b * n,
+                   ref_traj ? ref_traj + (size_t)b * (N + 1) * n : nullptr, st, follow ? follow[b] : -1,
+                   follow_status ? follow_status[b] : ORACLE_RUNNING, code + b, status + b, &reg_used, R, Xn, Un, Xt, Ut);
+      reg[b] = st.reg;
+      cost[b] = st.cost;
+      alpha[b] = st.alpha_pr;
+      inf_du[b] = st.inf_du;
+      if (dV) {
+        dV[2 * b] = st.dV[0];
+        dV[2 * b + 1] = st.dV[1];
+      }
+      if (rep) rep[b] = R;
     }
   };
   if (nthreads == 1) {

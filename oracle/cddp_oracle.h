@@ -154,6 +154,41 @@ void oracle_solve_batch(const oracle_problem *p, const oracle_options *o, int ba
                         const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
                         oracle_result *res);
 
+/* Decision trace / decision replay (test instrumentation; DESIGN.md "Parity procedure").
+ * trace: [B][max_iterations] ints, one per entry of the main loop (cddp_solver_base.cpp:74):
+ *   (backward-pass failures in this iteration << 8) | code,
+ *   code = 1 + index of the accepted alpha, or one of ORACLE_TRACE_*.
+ * oracle_solve_batch_traced with replay_trace == NULL runs the normal solve and (trace_out != NULL) records its
+ * decisions.  With replay_trace / replay_iterations / replay_status (e.g. downloaded from the CUDA path) the oracle's
+ * arithmetic FOLLOWS those decisions instead of taking its own: accept / reject of every line-search candidate
+ * (clddp_solver.cpp:251-257), backward failure + regularisation bump (cddp_solver_base.cpp:93-111), early and late
+ * convergence (clddp_solver.cpp:206-213,264-277).  rep[b] says how often its own verdict differed and the largest
+ * relative distance to the decision threshold among those decisions.  history: [B][max_iterations+1][4] or NULL. */
+enum { ORACLE_TRACE_LS_FAILED = 0, ORACLE_TRACE_EARLY_EXIT = 0xff, ORACLE_TRACE_BW_LIMIT = 0xfe };
+typedef struct {
+  int n_disagree;          /* threshold decisions (Armijo ratio, inf_du < tolerance, dJ < acceptable_tolerance) */
+  int n_backward_disagree; /* backward-pass success / failure verdicts */
+  int infeasible;          /* the recorded sequence could not be followed (own backward pass failed where it must succeed) */
+  int reserved;
+  double max_margin;       /* max over the n_disagree decisions of the distance to the threshold, in the units roundoff
+                              enters the test: |dJ - c expected| / |cost| (Armijo), |inf_du - tol| / tol */
+} oracle_replay_report;
+
+void oracle_solve_batch_traced(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                               const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                               oracle_result *res, double *history, int *trace_out, const int *replay_trace,
+                               const int *replay_iterations, const int *replay_status, oracle_replay_report *rep);
+
+/* ONE entry of the main loop (cddp_solver_base.cpp:74-170) for every instance of a batch, from a caller-supplied solver
+ * state: X, U (nominal trajectory), k (BoxQP warm start k_u_), reg, cost, alpha, inf_du are in/out, K and dV out.
+ * follow == NULL: the oracle takes its own decisions and reports them in code[b] (trace encoding) and status[b]
+ * (ORACLE_RUNNING = not terminated).  follow / follow_status != NULL: it follows those decisions and rep[b] reports
+ * how its own verdicts differed.  The lock-step parity tests feed it the CUDA path's state before every iteration. */
+void oracle_iterate_batch(const oracle_problem *p, const oracle_options *o, int batch, int nthreads, const double *x0,
+                          const double *xref, const double *ref_traj, double *X, double *U, double *K, double *k,
+                          double *reg, double *cost, double *alpha, double *inf_du, double *dV, const int *follow,
+                          const int *follow_status, int *code, int *status, oracle_replay_report *rep);
+
 /* ---------------------------------------------------------------------------------------------
  * IPDDP (src/cddp_core/ipddp_solver.cpp): cold start, use_ilqr = true, path inequality constraints, no
  * terminal constraints.  Same parity status as above ("parity unpinned").

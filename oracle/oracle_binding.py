@@ -277,6 +277,76 @@ def solve_batch(P, opts, x0, xref, X0, U0, ref_traj=None, nthreads=1):
                 status=np.array([r.status for r in res], dtype=np.int32))
 
 
+class ReplayReport(C.Structure):
+    _fields_ = [("n_disagree", C.c_int), ("n_backward_disagree", C.c_int), ("infeasible", C.c_int), ("reserved", C.c_int),
+                ("max_margin", C.c_double)]
+
+
+TRACE_LS_FAILED, TRACE_EARLY_EXIT, TRACE_BW_LIMIT = 0, 0xFF, 0xFE
+
+
+def solve_batch_traced(P, opts, x0, xref, X0, U0, ref_traj=None, nthreads=1, replay=None, history=True):
+    """oracle_solve_batch_traced.  replay=None: normal solve, the decision trace comes back as out["trace"]
+    ([B][max_iterations] int32).  replay=dict(trace=..., iterations=..., status=...): the oracle follows that decision
+    sequence (e.g. the CUDA path's); out["replay"] holds the per-instance disagreement report."""
+    x0, xref = _f64(x0), _f64(xref)
+    B = x0.shape[0]
+    X, U = _f64(X0).copy(), _f64(U0).copy()
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K, k = np.zeros((B, P.N, P.m, P.n)), np.zeros((B, P.N, P.m))
+    res = (Result * B)()
+    mi = max(int(opts.max_iterations), 1)
+    hist = np.zeros((B, opts.max_iterations + 1, 4)) if history else None
+    trace = np.zeros((B, mi), dtype=np.int32)
+    rep = (ReplayReport * B)()
+    if replay is None:
+        load().oracle_solve_batch_traced(P.ref, C.byref(opts), B, int(nthreads), _p(x0), _p(xref), _p(rt), _p(X), _p(U), _p(K),
+                                         _p(k), res, _p(hist), _p(trace), None, None, None, None)
+    else:
+        rtrace = np.ascontiguousarray(replay["trace"], dtype=np.int32)
+        assert rtrace.shape == (B, mi), (rtrace.shape, (B, mi))
+        rit = np.ascontiguousarray(replay["iterations"], dtype=np.int32)
+        rst = np.ascontiguousarray(replay["status"], dtype=np.int32)
+        load().oracle_solve_batch_traced(P.ref, C.byref(opts), B, int(nthreads), _p(x0), _p(xref), _p(rt), _p(X), _p(U), _p(K),
+                                         _p(k), res, _p(hist), None, _p(rtrace), _p(rit), _p(rst), rep)
+        trace = rtrace
+    out = dict(X=X, U=U, K=K, k=k, cost=np.array([r.final_objective for r in res]),
+               alpha=np.array([r.final_step_length for r in res]), reg=np.array([r.final_regularization for r in res]),
+               inf_du=np.array([r.inf_du for r in res]), iterations=np.array([r.iterations for r in res], dtype=np.int32),
+               status=np.array([r.status for r in res], dtype=np.int32), trace=trace,
+               history_len=np.array([r.history_len for r in res], dtype=np.int32))
+    if history:
+        out["history"] = hist
+    if replay is not None:
+        out["replay"] = dict(n_disagree=np.array([r.n_disagree for r in rep]),
+                             n_backward_disagree=np.array([r.n_backward_disagree for r in rep]),
+                             infeasible=np.array([r.infeasible for r in rep]),
+                             max_margin=np.array([r.max_margin for r in rep]))
+    return out
+
+
+def iterate_batch(P, opts, x0, xref, X, U, k, reg, cost, alpha, inf_du, ref_traj=None, nthreads=1, follow=None,
+                  follow_status=None):
+    """oracle_iterate_batch: one main-loop entry per instance from the given solver state (arrays are copied)."""
+    x0, xref = _f64(x0), _f64(xref)
+    B = x0.shape[0]
+    X, U, k = _f64(X).copy(), _f64(U).copy(), _f64(k).copy()
+    reg, cost, alpha, inf_du = (_f64(a).copy() for a in (reg, cost, alpha, inf_du))
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    K = np.zeros((B, P.N, P.m, P.n))
+    dV = np.zeros((B, 2))
+    code, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    rep = (ReplayReport * B)()
+    fo = None if follow is None else np.ascontiguousarray(follow, dtype=np.int32)
+    fs = None if follow_status is None else np.ascontiguousarray(follow_status, dtype=np.int32)
+    load().oracle_iterate_batch(P.ref, C.byref(opts), B, int(nthreads), _p(x0), _p(xref), _p(rt), _p(X), _p(U), _p(K), _p(k),
+                                _p(reg), _p(cost), _p(alpha), _p(inf_du), _p(dV), _p(fo), _p(fs), _p(code), _p(status), rep)
+    return dict(X=X, U=U, K=K, k=k, reg=reg, cost=cost, alpha=alpha, inf_du=inf_du, dV=dV, code=code, status=status,
+                n_disagree=np.array([r.n_disagree for r in rep]),
+                n_backward_disagree=np.array([r.n_backward_disagree for r in rep]),
+                infeasible=np.array([r.infeasible for r in rep]), max_margin=np.array([r.max_margin for r in rep]))
+
+
 def hardware_threads() -> int:
     return int(load().oracle_hardware_threads())
 
