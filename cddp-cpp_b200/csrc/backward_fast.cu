@@ -100,9 +100,17 @@ struct SweepCfg {
   static constexpr int oNrm = oW + ev(NC);                // sum_t ||V_x||_1 (matrix lane NS -> QP lane, at the end of the sweep)
   static constexpr int oCtrl = oNrm + 2;                  // int state
   static constexpr int oBar = oCtrl + 2;                  // 2 x uint64 mbarrier
-  static constexpr int raw = oBar + 2;
-  static constexpr int ST = raw + ((2 - raw % 4) + 4) % 4;  // == 2 (mod 4): even (16-byte aligned records) and the
-                                                            // blocks of neighbouring trajectories start in different banks
+  static constexpr int oKst = oBar + 2;                   // [2][NC] BoxQP warm start k_u_[t], staged with the record (TMA)
+  static constexpr bool kStaged = (NC * 8) % 16 == 0;     // cp.async.bulk moves multiples of 16 bytes
+  static constexpr int raw = oKst + (kStaged ? 2 * NC : 0);
+  // Stride between the blocks of neighbouring trajectories, in doubles (even: records stay 16-byte aligned).
+  // Four trajectories per warp (G = 8): stride == 4 (mod 16).  A broadcast read then touches the four 8-byte banks
+  // 0, 4, 8, 12 (+ offset) — one wavefront — and a row / transposed access (8 consecutive doubles per trajectory)
+  // covers every bank exactly twice — two wavefronts, the minimum for 256 bytes.  The former stride == 2 (mod 4)
+  // made such accesses 4-way conflicts (ncu: 80.0 M shared wavefronts against 59.7 M ideal).
+  // Eight trajectories per warp (G = 4): stride == 2 (mod 16), distinct banks for the eight broadcast addresses.
+  static constexpr int want = (G == 8) ? 4 : 2;
+  static constexpr int ST = raw + ((want - raw % 16) + 16) % 16;
   static constexpr int constDoubles = ((NS * NS + NC * NC) + 1) & ~1;
   static constexpr size_t smemBytes = sizeof(double) * (size_t)(constDoubles + T * ST);
   static constexpr int threads = (W + 1) * 32;
@@ -162,8 +170,11 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
 
     auto issue = [&](int tt, int x) {
       if (r == 0) {
-        mbar_expect_tx(&bar[x], RS * 8);
+        mbar_expect_tx(&bar[x], RS * 8 + (Cfg::kStaged ? NC * 8 : 0));
         bulk_g2s(S + Cfg::oRec + x * RS, grec + (size_t)tt * RS, RS * 8, &bar[x]);
+        // the BoxQP warm start of step tt rides on the same mbarrier: as a plain load issued in phase A2 it shared a
+        // scoreboard with the first record reads and stalled them for an HBM round trip (ncu: 1.5 k samples on one DFMA)
+        if constexpr (Cfg::kStaged) bulk_g2s(S + Cfg::oKst + x * NC, gk + (size_t)tt * NC, NC * 8, &bar[x]);
       }
       if (x) pend1 = true; else pend0 = true;
     };
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
       t = N - 1;
       buf = 0;
       nrm = 0.0;
-      kprev = (r < NC) ? gk[(size_t)(N - 1) * NC + r] : 0.0;
+      if constexpr (!Cfg::kStaged) kprev = (r < NC) ? gk[(size_t)(N - 1) * NC + r] : 0.0;
     };
 
     __syncthreads();  // mbarriers initialised, sQ/sR loaded
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         if (run && r < NC) {
           S[Cfg::oQu + r] = rc[L::offLu + r] + S[Cfg::oPB + NS * NC + r];
           S[Cfg::oU + r] = rc[L::offU + r];
-          S[Cfg::oKprev + r] = kprev;
+          S[Cfg::oKprev + r] = Cfg::kStaged ? S[Cfg::oKst + buf * NC + r] : kprev;
         }
       }
       if (!__syncthreads_or(run ? 1 : 0)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
@@ -259,7 +270,8 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         // ------------------------------------------------------------ phase A2 (in the shadow of the QP warp)
         // BoxQP warm start of the NEXT step, k_u_[t-1] (clddp_solver.cpp:149): an HBM-latency load, issued here so
         // that it is off the critical path (phase A1 used to stall on it)
-        if (run && r < NC && t > 0) kprev = gk[(size_t)(t - 1) * NC + r];
+        if constexpr (!Cfg::kStaged)
+          if (run && r < NC && t > 0) kprev = gk[(size_t)(t - 1) * NC + r];
         // TMA staging, also in the shadow: record t-1 (other buffer) was issued one step ago -> wait for it now.
         // Record t-2 is issued into THIS step's buffer once phase A2 has finished reading it (end of this block).
         if (run && t > 0) wait_buf(buf ^ 1);
@@ -418,12 +430,15 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
             S[Cfg::oVx + row[sl]] = vxn[sl];
           }
         __syncwarp();
+        // V is assigned in EVERY lane — also those whose step failed: they restart from init_sweep or stop and never read
+        // it again — so that the old value function is dead once phase A2 has formed P_A.  Assigned under `if (okh)` it
+        // stayed live through the second half of A2 and all of C (2*R*NS registers; the kernel spilled at 255).
+#pragma unroll
+        for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+          for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); the V_x slot takes the new V_x^T
+            V[sl][j] = isrow[sl] ? 0.5 * (Vn[sl][j] + S[Cfg::oPA + j * NS + rr[sl]]) : Sv[Cfg::oVx + j];
         if (okh) {
-#pragma unroll
-          for (int sl = 0; sl < R; ++sl)
-#pragma unroll
-            for (int j = 0; j < NS; ++j)  // V_xx = (V' + V'^T)/2 (:192); the V_x slot takes the new V_x^T
-              V[sl][j] = isrow[sl] ? 0.5 * (Vn[sl][j] + S[Cfg::oPA + j * NS + rr[sl]]) : Sv[Cfg::oVx + j];
           // gains to HBM last: a store keeps its address/data registers busy until the LSU has read them, which
           // stalled the value update when the stores sat in front of it
 #pragma unroll

@@ -70,6 +70,7 @@ struct cddp_b200_solver {
   IpDevice ip{};     // IPDDP: duals, slacks, gains, per-instance barrier/filter state
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
   int poll_interval = -1;  // -1: automatic (default: every iteration for heavy batches, else a widening stride); 0: never poll (fully asynchronous solve); k > 0: every k iterations
+  int ls_window = 1;      // windowed line search (cddp_b200_set_line_search_window)
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;
@@ -149,6 +150,7 @@ void set_options(cddp_b200_solver *s, const cddp_b200_options &o) {
   s->c.opt = o;
   s->c.num_alphas = build_alphas(o, s->c.alphas, CDDP_B200_MAX_ALPHAS);
   s->d.num_alphas = s->c.num_alphas;
+  s->c.ls_window = s->ls_window;
 }
 
 // Selects the record layout (records.cuh): allocates the record buffer of that layout on first use and
@@ -736,6 +738,13 @@ int cddp_b200_get_first_controls_async(cddp_b200_solver *s, double *u0, double *
 int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval) {
   if (!s || interval < -1) return CDDP_B200_ERR_INVALID_ARGUMENT;
   s->poll_interval = interval;
+  return 0;
+}
+
+int cddp_b200_set_line_search_window(cddp_b200_solver *s, int enable) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->ls_window = enable ? 1 : 0;
+  s->c.ls_window = s->ls_window;
   return 0;
 }
 

@@ -129,6 +129,7 @@ struct Constants {
   double lb[CDDP_B200_MAX_M], ub[CDDP_B200_MAX_M];
   double alphas[CDDP_B200_MAX_ALPHAS];
   int num_alphas;
+  int ls_window;  // windowed line search (kernels_forward.cuh): first 8 candidates at 8 lanes per trajectory, then the rest
   cddp_b200_options opt;
 };
 

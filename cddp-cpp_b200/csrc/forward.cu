@@ -115,6 +115,13 @@ cudaError_t launch_forward_model(const Constants &c, const DeviceState &d, int m
   const int threads = kWarpsPerCta * 32;
   const bool diag = c.cost_diag != 0;
   if (c.num_alphas <= 16) {
+    if (mode == FW_ITERATE && c.num_alphas > 8 && !c.opt.enable_parallel && c.ls_window) {
+      // windowed line search (kernels_forward.cuh): the first 8 candidates with 8 lanes per trajectory, then the full
+      // width for the instances none of them settled
+      const int wblocks = (d.n_slots + kWarpsPerCta * 4 - 1) / (kWarpsPerCta * 4);
+      if (diag) forward_kernel<MODEL, 8, true, true><<<wblocks, threads, 0, st>>>(c, d, mode);
+      else forward_kernel<MODEL, 8, false, true><<<wblocks, threads, 0, st>>>(c, d, mode);
+    }
     const int blocks = (d.n_slots + kWarpsPerCta * 2 - 1) / (kWarpsPerCta * 2);
     if (diag) forward_kernel<MODEL, 16, true><<<blocks, threads, 0, st>>>(c, d, mode);
     else forward_kernel<MODEL, 16, false><<<blocks, threads, 0, st>>>(c, d, mode);

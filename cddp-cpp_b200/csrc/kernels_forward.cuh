@@ -103,8 +103,15 @@ __device__ __forceinline__ double quad_form(const double *M, const double *e) {
 //   pass 2: the LG lanes re-run the accepted alpha's rollout in parallel, one `seg`-step segment each, from
 //           the saved states, and write the candidate trajectory (1/LG of a rollout in latency instead of
 //           a full sequential replay).
-template <int MODEL, int LG, bool DIAG>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kernel(Constants c, DeviceState d, int mode) {
+//
+// WINDOW (sequential rule only, FW_ITERATE): the kernel looks at the first LG candidates alphas_[0..LG-1] of a longer
+// list.  The first accepted alpha wins (cddp_solver_base.cpp:255-263), so if one of them passes the Armijo test the
+// remaining candidates are never looked at and the instance is settled here (fw_done = 1); otherwise it is left
+// untouched (fw_done = 0) for the full-width launch that follows.  Same decisions, same trajectories; a bang-bang
+// workload whose accepted index is 3..6 (the headline quadrotor batch: alphas_[0] is accepted in 0 % of the
+// instance-iterations, index <= 7 in all of them) pays 8 rollouts per trajectory instead of 16.
+template <int MODEL, int LG, bool DIAG, bool WINDOW = false>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LG == 8 ? 4 : kMinCtasPerSm) forward_kernel(Constants c, DeviceState d, int mode) {
   constexpr int NS = Model<MODEL>::NS, NC = Model<MODEL>::NC;
   constexpr int STEP = NS + 2 * NC + NC * NS;  // x_nom | u_nom | k | K
   constexpr int STEPP = (STEP + 1) & ~1;
@@ -124,11 +131,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   __syncthreads();
   const int grp = lane / LG, al = lane % LG;
   const int b = slot_instance(d, (blockIdx.x * kWarpsPerCta + warp) * TPW + grp);
-  const bool alive = b < d.B && !(mode == FW_ITERATE && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.fw_done[b]));
+  // (a WINDOW launch is the first of its iteration: it ignores, then rewrites, the flags of the previous one)
+  const bool alive = b < d.B && !(mode == FW_ITERATE && (d.status[b] != CDDP_B200_STATUS_RUNNING || (!WINDOW && d.fw_done[b])));
+  // the full-width launch consumes the flags: nothing stale is left for a later launch with other options
+  if (!WINDOW && mode == FW_ITERATE && b < d.B && al == 0 && d.fw_done[b]) d.fw_done[b] = 0;
   if (!__any_sync(0xffffffffu, alive)) return;
   const int bb = alive ? b : 0;
 
-  const int N = d.N, na = c.num_alphas;
+  const int N = d.N, na = WINDOW ? min(c.num_alphas, LG) : c.num_alphas;
   const int seg = (N + LG - 1) / LG;
   const int cur = d.cur[bb];
   const double *Xn = d.X[cur] + (size_t)bb * (N + 1) * NS;
@@ -228,8 +238,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
   const double expected = -alpha * (d.dV[2 * bb] + 0.5 * alpha * d.dV[2 * bb + 1]);
   const double ratio = expected > 0.0 ? dJ / expected : copysign(1.0, dJ);
   const bool success = alive && active && (ratio > c.opt.armijo_constant);
-  const int first = select_alpha<LG>(success, J, al, grp, c.opt.enable_parallel);
+  const int first = select_alpha<LG>(success, J, al, grp, WINDOW ? 0 : c.opt.enable_parallel);
   if (alive && active) d.ls_cost[(size_t)b * CDDP_B200_MAX_ALPHAS + al] = J;
+  if (WINDOW) {
+    if (alive && al == 0) d.fw_done[b] = first >= 0 ? 1 : 0;
+    if (!__any_sync(0xffffffffu, alive && first >= 0)) return;
+  }
   const double Jacc = __shfl_sync(0xffffffffu, J, grp * LG + (first >= 0 ? first : 0));
 
   // ---------------- pass 2: write the accepted rollout, one segment per lane ----------------
@@ -268,7 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) forward_kern
       }
     }
   }
-  if (alive && al == 0) finish_line_search(c, d, b, mode, first, Jacc);
+  if (alive && al == 0 && !(WINDOW && first < 0)) finish_line_search(c, d, b, mode, first, Jacc);
 }
 
 // Speculative first step of the sequential line search (cddp_solver_base.cpp:255-263: the FIRST accepted alpha wins, so

@@ -491,3 +491,26 @@ def test_work_list_compaction_changes_nothing(cddp, problems, name):
     for o in out[1:]:
         for key in ("X", "U", "K", "cost", "iterations", "status"):
             assert np.array_equal(out[0][key], o[key]), key
+
+
+@pytest.mark.parametrize("name,B,N", [("quadrotor", 70, 60), ("unicycle", 33, None), ("pendulum", 9, 120)])
+def test_windowed_line_search_changes_nothing(cddp, problems, name, B, N):
+    """cddp_b200_set_line_search_window: the first 8 candidates at 8 lanes per trajectory + the full width for the
+    rest must take the same decisions and write the same trajectories as the single full-width launch (first
+    accepted alpha wins, cddp_solver_base.cpp:255-263).  Includes instances whose accepted index is >= 8 (pendulum:
+    deep backtracking) and line-search failures."""
+    cfg = problems.make_config(name, batch=B, horizon=N)
+    out = []
+    for window in (True, False):
+        s, _ = make(cddp, cfg, B, max_iterations=25, ls_max_iterations=15)
+        s.set_line_search_window(window)
+        s.enable_trace(True)
+        s.solve()
+        r = s.get_solution()
+        r["trace"] = s.get_trace()
+        out.append(r)
+        s.close()
+    for key in ("X", "U", "K", "cost", "iterations", "status", "alpha", "reg", "trace"):
+        assert np.array_equal(out[0][key], out[1][key]), key
+    acc = (out[0]["trace"] & 0xFF)
+    print(f"\n[window {name}] accepted-index histogram (0 = failed, k = index k-1): {np.bincount(acc[acc < 0xF0].ravel(), minlength=17).tolist()}")
