@@ -20,8 +20,11 @@
 //   * Records are staged global->shared by TMA bulk copies (cp.async.bulk + mbarrier), double-buffered
 //     one timestep ahead, issued by one lane per trajectory.
 #include <cstdint>
+#include <cstdlib>
+#include <string>
 #include <type_traits>
 
+#include "boxqp_quad.cuh"
 #include "boxqp_small.cuh"
 #include "engine.h"
 #include "records.cuh"
@@ -72,13 +75,21 @@ constexpr int rows_per_lane(int ns) { return ns + 1 <= 8 ? 1 : 2; }
 
 enum { CTRL_OK = 1, CTRL_RESTART = 2, CTRL_FAIL = 3 };
 
-template <int NS, int NC, class PAT, int W>
+// QPQ = false: W matrix warps + ONE QP warp, one trajectory per QP lane, CTA-wide barriers (any n, m).
+// QPQ = true (m = 4, 4 trajectories per matrix warp): W = 8 matrix warps + FOUR QP warps, four lanes per trajectory
+// (boxqp_quad.cuh).  The CTA is four independent SETS of two matrix warps and one QP warp (8 trajectories) that meet at
+// their own named barriers, so a slow subproblem holds up 8 trajectories instead of 28, and the warps re-divide the
+// register file with setmaxnreg (sm_90+): 12 warps are launched at 168 registers, the matrix warps grow to kMatrixRegs
+// and the QP warps shrink to kQpRegs (8*32*216 + 4*32*72 = 384*168).
+template <int NS, int NC, class PAT, int W, bool QPQ = false>
 struct SweepCfg {
   using L = RecordLayout<NS, NC, PAT>;
   static constexpr int G = group_size(NS);
   static constexpr int R = rows_per_lane(NS);
   static constexpr int TPW = 32 / G;  // trajectories per warp
-  static constexpr int T = W * TPW;   // trajectories per CTA (one QP-warp lane each)
+  static constexpr int T = W * TPW;   // trajectories per CTA
+  static constexpr int QW = QPQ ? W / 2 : 1;  // QP warps
+  static constexpr int kMatrixRegs = 216, kQpRegs = 72;
   static constexpr int RS = L::stride;
   // per-trajectory shared-memory block (offsets in doubles).  Every field starts on an even offset (16 bytes): nvcc
   // merges stores/loads of neighbouring doubles into 128-bit accesses and has been seen (compute-sanitizer, pendulum
@@ -98,7 +109,8 @@ struct SweepCfg {
   static constexpr int oHinv = oKk + ev(NC);              // [NC][NC] Ht = inverse of the free block of Q_uu_reg, clamped rows/cols 0
   static constexpr int oW = oHinv + ev(NC * NC);          // [NC] w = Q_uu k + Q_u
   static constexpr int oNrm = oW + ev(NC);                // sum_t ||V_x||_1 (matrix lane NS -> QP lane, at the end of the sweep)
-  static constexpr int oCtrl = oNrm + 2;                  // int state
+  static constexpr int oAcc = oNrm + 2;                   // QPQ: dV0, dV1, Qu_err accumulated here (the QP lanes run at 72 registers)
+  static constexpr int oCtrl = oAcc + 4;                  // int state
   static constexpr int oBar = oCtrl + 2;                  // 2 x uint64 mbarrier
   static constexpr int oKst = oBar + 2;                   // [2][NC] BoxQP warm start k_u_[t], staged with the record (TMA)
   static constexpr bool kStaged = (NC * 8) % 16 == 0;     // cp.async.bulk moves multiples of 16 bytes
@@ -113,12 +125,65 @@ struct SweepCfg {
   static constexpr int ST = raw + ((want - raw % 16) + 16) % 16;
   static constexpr int constDoubles = ((NS * NS + NC * NC) + 1) & ~1;
   static constexpr size_t smemBytes = sizeof(double) * (size_t)(constDoubles + T * ST);
-  static constexpr int threads = (W + 1) * 32;
+  static constexpr int threads = (W + QW) * 32;
 };
 
-template <int NS, int NC, class PAT, int W, int MINB>
-__global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
-  using Cfg = SweepCfg<NS, NC, PAT, W>;
+// set-level barriers of the QPQ layout: ids 1 + 2*set (reduces "any trajectory of the set still running") and 2 + 2*set
+__device__ __forceinline__ bool set_barrier_or(int id, int count, bool p) {
+  unsigned r;
+  asm volatile(
+      "{\n\t.reg .pred pi, po;\n\tsetp.ne.u32 pi, %1, 0;\n\tbarrier.cta.red.or.pred po, %2, %3, pi;\n\tselp.u32 %0, 1, 0, po;\n\t}"
+      : "=r"(r)
+      : "r"(p ? 1u : 0u), "r"(id), "r"(count)
+      : "memory");
+  return r != 0u;
+}
+__device__ __forceinline__ void set_barrier(int id, int count) {
+  asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// End of a trajectory's sweep (one lane per trajectory): inf_du scaling (clddp_solver.cpp:194-201), early convergence
+// (:206-213), history (cddp_solver_base.cpp:116-118), state written back for the line search.
+template <int NS>
+__device__ __forceinline__ void sweep_epilogue(const Constants &c, const DeviceState &d, int mode, int b, bool ok, double norm_Vx,
+                                               int N, double reg, double dV0, double dV1, double Qu_err, int status,
+                                               int failures) {
+  double inf_du = 0.0;
+  if (ok) {  // norm_Vx: accumulated by the lane that holds V_x
+    double sf = c.opt.termination_scaling_max_factor;  // (:197-201)
+    sf = fmax(sf, norm_Vx / (double)(N * NS)) / sf;
+    inf_du = Qu_err / sf;
+    d.dV[2 * b] = dV0;
+    d.dV[2 * b + 1] = dV1;
+    d.inf_du[b] = inf_du;
+  }
+  d.bw_ok[b] = ok ? 1 : 0;
+  d.lin_valid[b] = 1;
+  if (mode == BW_ITERATE) {
+    d.reg[b] = reg;
+    if (ok && inf_du < c.opt.tolerance) {  // checkEarlyConvergence, clddp_solver.cpp:206-213
+      status = CDDP_B200_STATUS_OPTIMAL;
+      if (d.history) {  // recordIterationHistory, cddp_solver_base.cpp:116-118
+        const int hl = d.history_len[b];
+        if (hl < d.history_cap) {
+          double *h = d.history + ((size_t)b * d.history_cap + hl) * 4;
+          h[0] = d.cost[b];
+          h[1] = d.alpha[b];
+          h[2] = inf_du;
+          h[3] = reg;
+          d.history_len[b] = hl + 1;
+        }
+      }
+    }
+    if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+    trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
+  }
+}
+
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false>
+__global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
+  static_assert(!QPQ || (NC == 4 && Cfg::TPW == 4 && W % 2 == 0), "quad QP: m = 4, sets of two matrix warps");
   using L = typename Cfg::L;
   constexpr int G = Cfg::G, R = Cfg::R, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
   extern __shared__ __align__(16) double smem[];
@@ -130,8 +195,19 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
   for (int i = threadIdx.x; i < NS * NS; i += blockDim.x) sQ[i] = c.Qdt2[i];
   for (int i = threadIdx.x; i < NC * NC; i += blockDim.x) sR[i] = c.Rdt2[i];
 
+  // barriers: CTA-wide (id 0) or, with QPQ, the set's own pair over its 96 threads
+  const int set = QPQ ? (warp < W ? warp >> 1 : warp - W) : 0;
+  auto barrier_any = [&](bool p) -> bool {
+    if constexpr (QPQ) return set_barrier_or(1 + 2 * set, 96, p);
+    else return __syncthreads_or(p ? 1 : 0) != 0;
+  };
+  auto barrier_all = [&]() {
+    if constexpr (QPQ) set_barrier(2 + 2 * set, 96);
+    else __syncthreads();
+  };
   if (warp < W) {
     // =========================================================== matrix warps
+    if constexpr (QPQ) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kMatrixRegs));
     const int hw = lane / G, r = lane % G;  // hw: which of the warp's TPW trajectories, r: lane within the group
     const int q = warp * TPW + hw;
     const int b = slot_instance(d, blockIdx.x * T + q);
@@ -265,7 +341,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
           S[Cfg::oKprev + r] = Cfg::kStaged ? S[Cfg::oKst + buf * NC + r] : kprev;
         }
       }
-      if (!__syncthreads_or(run ? 1 : 0)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
+      if (!barrier_any(run)) break;  // barrier 1: Q_uu/Q_u visible to the QP warp
       if (wrun) {
         // ------------------------------------------------------------ phase A2 (in the shadow of the QP warp)
         // BoxQP warm start of the NEXT step, k_u_[t-1] (clddp_solver.cpp:149): an HBM-latency load, issued here so
@@ -353,7 +429,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         __syncwarp();  // every lane of the group is done reading this step's record
         if (run && t > 1) issue(t - 2, buf);
       }
-      __syncthreads();  // barrier 2: k, Ht, w, state visible to the matrix warps (and Q_ux to the other lanes)
+      barrier_all();  // barrier 2: k, Ht, w, state visible to the matrix warps (and Q_ux to the other lanes)
       if (wrun) {
         // ------------------------------------------------------------ phase C (critical path): value update
         const int st = run ? *reinterpret_cast<volatile int *>(S + Cfg::oCtrl) : 0;
@@ -477,6 +553,101 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
         __syncwarp();  // all reads of the transpose buffer done before the next step overwrites it
       }
     }
+  } else if constexpr (QPQ) {
+    // =========================================================== QP warps, four lanes per trajectory (boxqp_quad.cuh)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kQpRegs));
+    const int i = lane & 3, qb = lane & 28;
+    const int q = set * 8 + (lane >> 2);
+    const int b = slot_instance(d, blockIdx.x * T + q);
+    const bool alive = b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
+    double *Sw = traj0 + q * ST;
+    const volatile double *S = Sw;
+    __syncthreads();
+    double reg = alive ? d.reg[b] : 0.0;
+    if (alive && mode == BW_ITERATE && i == 0) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
+    if (i < 3) Sw[Cfg::oAcc + i] = 0.0;  // dV0, dV1, Qu_err
+    int qt = N - 1, status = CDDP_B200_STATUS_RUNNING, failures = 0;
+    bool run = alive, ok = false;
+    while (true) {
+      if (!barrier_any(run)) break;
+      {
+        // Q_uu_reg (:130-131): this lane's row in original order, from the upper-triangle entries
+        double Ho[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Ho[j] = S[Cfg::oQuu + (i < j ? i * 4 + j : j * 4 + i)] + (j == i ? reg : 0.0);
+        const double g = S[Cfg::oQu + i];
+        double kk = 0.0, Hk = 0.0, inv[4];
+        unsigned fm = 15u;
+        bool good;
+        if (c.has_box) {  // (:147-159)
+          const double un = S[Cfg::oU + i];
+          kk = S[Cfg::oKprev + i];
+          // (lane-dependent index into a kernel-parameter array would make the compiler copy the array to local memory)
+          const double lbi = i == 0 ? c.lb[0] : (i == 1 ? c.lb[1] : (i == 2 ? c.lb[2] : c.lb[3]));
+          const double ubi = i == 0 ? c.ub[0] : (i == 1 ? c.ub[1] : (i == 2 ? c.ub[2] : c.ub[3]));
+          const int qs = QuadQP::solve_box(c.opt, run, S + Cfg::oQuu, reg, Ho, g, lbi - un, ubi - un, kk, Hk, fm, inv, i, qb);
+          good = !(qs == QP_HESSIAN_NOT_PD || qs == QP_NO_DESCENT);
+        } else {  // k = -H^-1 Q_u (:142-144)
+          good = QuadQP::inverse_row(S + Cfg::oQuu, reg, 15u, i, qb, inv);
+          double v4[4];
+          QuadQP::gather_rot(g, qb, i, v4);
+          double sacc = 0.0;
+#pragma unroll
+          for (int bc = 0; bc < 4; ++bc) sacc = fma(inv[bc], v4[bc], sacc);
+          kk = -sacc;
+          QuadQP::gather(kk, qb, v4);
+          sacc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sacc = fma(Ho[j], v4[j], sacc);
+          Hk = sacc;
+        }
+        // dV += (Q_u.k, 0.5 k^T Q_uu k), unregularised Q_uu (:184-186); all lanes take part in the quad sums
+        const double sq = fma(-reg, kk, Hk);  // (Q_uu k)_i = (Q_uu_reg k)_i - reg k_i
+        const double d0 = QuadQP::quad_sum(g * kk), d1 = QuadQP::quad_sum(kk * sq), linf = QuadQP::quad_max(fabs(g));
+        if (run) {
+          if (good) {
+            const bool fi = (fm >> i) & 1u;
+#pragma unroll
+            for (int bc = 0; bc < 4; ++bc) {  // inverse of the free block, clamped rows / columns zero (:161-178)
+              const int j = (i + bc) & 3;
+              Sw[Cfg::oHinv + i * 4 + j] = (fi && ((fm >> j) & 1u)) ? inv[bc] : 0.0;
+            }
+            Sw[Cfg::oW + i] = sq + g;
+            Sw[Cfg::oKk + i] = kk;
+            // lane 0: dV0 += d0, lane 1: dV1 += 0.5 d1, lane 2: Qu_err = max(Qu_err, linf) (:184-186, :195)
+            if (i < 3) {
+              const double acc = S[Cfg::oAcc + i];
+              Sw[Cfg::oAcc + i] = i == 0 ? acc + d0 : (i == 1 ? acc + 0.5 * d1 : max_ref(acc, linf));
+            }
+            if (i == 0) *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_OK;
+            if (--qt < 0) {
+              run = false;
+              ok = true;
+            }
+          } else if (mode == BW_SINGLE) {
+            if (i == 0) *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_FAIL;
+            run = false;
+          } else {
+            // increaseRegularization + limit test (cddp_solver_base.cpp:95-109, cddp_core.cpp:308-326)
+            reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+            ++failures;
+            if (reg >= c.opt.reg_max_value) {
+              status = CDDP_B200_STATUS_REG_LIMIT;
+              if (i == 0) *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_FAIL;
+              run = false;
+            } else {
+              if (i == 0) *reinterpret_cast<volatile int *>(Sw + Cfg::oCtrl) = CTRL_RESTART;
+              if (i < 3) Sw[Cfg::oAcc + i] = 0.0;
+              qt = N - 1;
+            }
+          }
+        }
+      }
+      barrier_all();
+    }
+    __syncwarp();
+    if (alive && i == 0)
+      sweep_epilogue<NS>(c, d, mode, b, ok, S[Cfg::oNrm], N, reg, S[Cfg::oAcc], S[Cfg::oAcc + 1], S[Cfg::oAcc + 2], status, failures);
   } else {
     // =========================================================== QP warp: lane q <-> trajectory q
     constexpr int MC = NC;
@@ -493,7 +664,7 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
     bool run = alive, ok = false;
     constexpr unsigned all = (1u << NC) - 1u;
     while (true) {
-      if (!__syncthreads_or(run ? 1 : 0)) break;
+      if (!barrier_any(run)) break;
       if (run) {
         double H[MC * MC], g[MC], kk[MC], Hk[MC];
 #pragma unroll
@@ -629,68 +800,52 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB) sweep_kernel(Constants c, 
           }
         }
       }
-      __syncthreads();
+      barrier_all();
     }
-    if (alive) {
-      double inf_du = 0.0;
-      if (ok) {
-        const double norm_Vx = S[Cfg::oNrm];  // accumulated by the lane that holds V_x
-        double sf = c.opt.termination_scaling_max_factor;               // (:197-201)
-        sf = fmax(sf, norm_Vx / (double)(N * NS)) / sf;
-        inf_du = Qu_err / sf;
-        d.dV[2 * b] = dV0;
-        d.dV[2 * b + 1] = dV1;
-        d.inf_du[b] = inf_du;
-      }
-      d.bw_ok[b] = ok ? 1 : 0;
-      d.lin_valid[b] = 1;
-      if (mode == BW_ITERATE) {
-        d.reg[b] = reg;
-        if (ok && inf_du < c.opt.tolerance) {  // checkEarlyConvergence, clddp_solver.cpp:206-213
-          status = CDDP_B200_STATUS_OPTIMAL;
-          if (d.history) {  // recordIterationHistory, cddp_solver_base.cpp:116-118
-            const int hl = d.history_len[b];
-            if (hl < d.history_cap) {
-              double *h = d.history + ((size_t)b * d.history_cap + hl) * 4;
-              h[0] = d.cost[b];
-              h[1] = d.alpha[b];
-              h[2] = inf_du;
-              h[3] = reg;
-              d.history_len[b] = hl + 1;
-            }
-          }
-        }
-        if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
-        trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
-      }
-    }
+    if (alive) sweep_epilogue<NS>(c, d, mode, b, ok, S[Cfg::oNrm], N, reg, dV0, dV1, Qu_err, status, failures);
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false>
 cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
-  using Cfg = SweepCfg<NS, NC, PAT, W>;
-  static_assert(Cfg::T <= 32, "one QP-warp lane per trajectory");
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
+  static_assert(QPQ || Cfg::T <= 32, "one QP-warp lane per trajectory");
   static_assert(NS + 1 <= Cfg::G * Cfg::R, "V_x rides as an extra row");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int blocks = (d.n_slots + Cfg::T - 1) / Cfg::T;
-  sweep_kernel<NS, NC, PAT, W, MINB><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
+  sweep_kernel<NS, NC, PAT, W, MINB, QPQ><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
   return cudaGetLastError();
 }
 
 }  // namespace
 
+// Developer switch (A-B timing only): CDDP_B200_SWEEP_VARIANT=quad selects the 12-warp layout for m = 4 (SweepCfg::QPQ:
+// four QP warps, four lanes per trajectory, set-level barriers, setmaxnreg).  It passes the same parity tests but is
+// SLOWER on B200 (0.815 ms against 0.571 ms for the headline batch, profiles/r02_sweep_quad_qp.txt): the quad-parallel
+// BoxQP is a chain of shuffle round trips (1 575 warp-instructions per step at 7.3 cycles each against 1 900 at 3.5 for
+// the one-lane-per-trajectory QP warp), and eight matrix warps per SM run 9 % slower than seven.  Default: one QP warp.
+static int sweep_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("CDDP_B200_SWEEP_VARIANT");
+    return (e && std::string(e) == "quad") ? 0 : 1;
+  }();
+  return v;
+}
+
 cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int mode, cudaStream_t st, bool *handled) {
   *handled = true;
   const int n = d.n, m = d.m;
   if (d.layout == RECORDS_STRUCTURED) {
-    if (c.model == CDDP_B200_MODEL_QUADROTOR) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
+    if (c.model == CDDP_B200_MODEL_QUADROTOR) {
+      if (sweep_variant() == 0) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 8, 1, true>(c, d, mode, st);
+      return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
+    }
     if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
     if (c.model == CDDP_B200_MODEL_UNICYCLE) return launch_sweep<3, 2, ModelPattern<CDDP_B200_MODEL_UNICYCLE>, 4, 4>(c, d, mode, st);
   } else {
@@ -699,7 +854,10 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
     if (n == 4 && m == 1) return launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 4 && m == 2) return launch_sweep<4, 2, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 6 && m == 3) return launch_sweep<6, 3, DensePattern, 7, 2>(c, d, mode, st);
-    if (n == 13 && m == 4) return launch_sweep<13, 4, DensePattern, 7, 1>(c, d, mode, st);
+    if (n == 13 && m == 4) {
+      if (sweep_variant() == 0) return launch_sweep<13, 4, DensePattern, 8, 1, true>(c, d, mode, st);
+      return launch_sweep<13, 4, DensePattern, 7, 1>(c, d, mode, st);
+    }
     if (n == 14 && m == 7) return launch_sweep<14, 7, DensePattern, 5, 1>(c, d, mode, st);
   }
   *handled = false;
