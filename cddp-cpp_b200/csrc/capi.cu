@@ -70,7 +70,7 @@ struct cddp_b200_solver {
   IpDevice ip{};     // IPDDP: duals, slacks, gains, per-instance barrier/filter state
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
   int poll_interval = -1;  // -1: automatic (default: every iteration for heavy batches, else a widening stride); 0: never poll (fully asynchronous solve); k > 0: every k iterations
-  int ls_window = 1;      // windowed line search (cddp_b200_set_line_search_window)
+  int ls_window = 0;      // windowed line search (cddp_b200_set_line_search_window); off: measured slower on B200
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
   bool initialized = false;

@@ -280,7 +280,9 @@ class Constraint {  // constraint.hpp:31-138 (the members CLDDP and the facade u
 
 class ControlConstraint : public Constraint {  // constraint.hpp:144-251 (BoxConstraint<Control>)
  public:
-  ControlConstraint(const Eigen::VectorXd &lower_bound, const Eigen::VectorXd &upper_bound);
+  // scale_factor multiplies evaluate(), the IP upper bound and the Jacobians (constraint.hpp:147-218); the raw bounds
+  // and clamp() — what CLDDP's BoxQP uses — are unscaled
+  ControlConstraint(const Eigen::VectorXd &lower_bound, const Eigen::VectorXd &upper_bound, double scale_factor = 1.0);
   explicit ControlConstraint(const Eigen::VectorXd &upper_bound);  // symmetric: lower = -upper
   int getDualDim() const override { return 2 * (int)upper_bound_.size(); }
   Eigen::VectorXd evaluate(const Eigen::VectorXd &state, const Eigen::VectorXd &control, int index = 0) const override;  // [-u; u]
@@ -289,9 +291,11 @@ class ControlConstraint : public Constraint {  // constraint.hpp:144-251 (BoxCon
   const Eigen::VectorXd &rawLowerBound() const { return lower_bound_; }  // :222
   const Eigen::VectorXd &rawUpperBound() const { return upper_bound_; }  // :223
   Eigen::VectorXd clamp(const Eigen::VectorXd &v) const;                 // :225-228
+  double getScaleFactor() const { return scale_factor_; }
 
  private:
   Eigen::VectorXd lower_bound_, upper_bound_;
+  double scale_factor_ = 1.0;
 };
 
 class StateConstraint : public Constraint {  // constraint.hpp:144-251 (BoxConstraint<State>)

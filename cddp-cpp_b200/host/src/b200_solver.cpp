@@ -310,6 +310,7 @@ void describe_ipddp(CDDP &ctx, IpShared &s) {
     if (auto *cc = dynamic_cast<const ControlConstraint *>(base)) {
       c.type = CDDP_B200_CON_CONTROL_BOX;
       c.rows = (int)cc->rawLowerBound().size();
+      c.scale = cc->getScaleFactor();
       c.p0.assign(cc->rawLowerBound().data(), cc->rawLowerBound().data() + c.rows);
       c.p1.assign(cc->rawUpperBound().data(), cc->rawUpperBound().data() + c.rows);
     } else if (auto *sc = dynamic_cast<const StateConstraint *>(base)) {

@@ -281,19 +281,22 @@ Eigen::VectorXd QuadraticObjective::getFinalCostGradient(const Eigen::VectorXd &
 Eigen::MatrixXd QuadraticObjective::getFinalCostHessian(const Eigen::VectorXd &) const { return Qf_ * 2.0; }
 
 // ------------------------------------------------------------------------------------------------ ControlConstraint
-ControlConstraint::ControlConstraint(const Eigen::VectorXd &lower_bound, const Eigen::VectorXd &upper_bound)
-    : Constraint("ControlConstraint"), lower_bound_(lower_bound), upper_bound_(upper_bound) {}
+ControlConstraint::ControlConstraint(const Eigen::VectorXd &lower_bound, const Eigen::VectorXd &upper_bound, double scale_factor)
+    : Constraint("ControlConstraint"), lower_bound_(lower_bound), upper_bound_(upper_bound), scale_factor_(scale_factor) {}
 ControlConstraint::ControlConstraint(const Eigen::VectorXd &upper_bound)
     : Constraint("ControlConstraint"), lower_bound_(upper_bound * -1.0), upper_bound_(upper_bound) {}
 Eigen::VectorXd ControlConstraint::evaluate(const Eigen::VectorXd &, const Eigen::VectorXd &u, int) const {
   Eigen::VectorXd g(2 * u.size());
-  for (long i = 0; i < u.size(); ++i) { g[i] = -u[i]; g[u.size() + i] = u[i]; }
+  for (long i = 0; i < u.size(); ++i) { g[i] = -u[i] * scale_factor_; g[u.size() + i] = u[i] * scale_factor_; }  // (:163-172)
   return g;
 }
 Eigen::VectorXd ControlConstraint::getLowerBound() const { return Eigen::VectorXd::Constant(2 * upper_bound_.size(), -std::numeric_limits<double>::infinity()); }
 Eigen::VectorXd ControlConstraint::getUpperBound() const {
   Eigen::VectorXd r(2 * upper_bound_.size());
-  for (long i = 0; i < upper_bound_.size(); ++i) { r[i] = -lower_bound_[i]; r[upper_bound_.size() + i] = upper_bound_[i]; }
+  for (long i = 0; i < upper_bound_.size(); ++i) {  // [-lb; ub] * scale (:156-159)
+    r[i] = -lower_bound_[i] * scale_factor_;
+    r[upper_bound_.size() + i] = upper_bound_[i] * scale_factor_;
+  }
   return r;
 }
 Eigen::VectorXd ControlConstraint::clamp(const Eigen::VectorXd &v) const {

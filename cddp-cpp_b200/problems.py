@@ -69,7 +69,7 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
         "pendulum": _cfg_pendulum, "cartpole": _cfg_cartpole, "quadrotor": _cfg_quadrotor,
         "unicycle": _cfg_unicycle, "lti": _cfg_lti, "quadrotor_fig8": _cfg_quadrotor_fig8,
         "unicycle_obstacle": _cfg_unicycle_obstacle, "cartpole_ipddp": _cfg_cartpole_ipddp,
-        "pendulum_ipddp": _cfg_pendulum_ipddp, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
+        "pendulum_ipddp": _cfg_pendulum_ipddp, "pendulum_ipddp_scaled": _cfg_pendulum_ipddp_scaled, "unicycle_ipddp_free": _cfg_unicycle_ipddp_free,
         "quadrotor_ipddp": _cfg_quadrotor_ipddp, "bicycle_user": _cfg_bicycle_user, "bicycle_user_ipddp": _cfg_bicycle_user_ipddp,
         "chain7_user": _cfg_chain7_user, "unicycle_obstacle_teq": _cfg_unicycle_obstacle_teq,
         "unicycle_teq": _cfg_unicycle_teq, "cartpole_teq": _cfg_cartpole_teq, "chain7_user_ipddp": _cfg_chain7_user_ipddp,
@@ -309,6 +309,16 @@ def _cfg_unicycle_ipddp_free(batch, horizon, seed_offset):
     return cfg
 
 
+def _cfg_pendulum_ipddp_scaled(batch, horizon, seed_offset):
+    """pendulum_ipddp with ControlConstraint(lb, ub, scale_factor = 0.25): the scale multiplies evaluate(), the IP upper
+    bound and the Jacobians (constraint.hpp:147-218), so slack / dual initialisation, theta and the barrier schedule
+    differ from the unscaled problem."""
+    cfg = _cfg_pendulum_ipddp(batch, horizon, seed_offset)
+    cfg["constraints"] = [dict(type="control_box", lb=[-20.0], ub=[20.0], scale=0.25)]
+    cfg["name"] = "pendulum_ipddp_scaled"
+    return cfg
+
+
 def _cfg_pendulum_ipddp(batch, horizon, seed_offset):
     """examples/cddp_pendulum.cpp:27-67: Pendulum(dt=0.02, l=0.5, m=1, b=0.01) N=100, control box +-20, IPDDP."""
     B = batch or 1
@@ -366,7 +376,7 @@ def _cfg_quadrotor_ipddp(batch, horizon, seed_offset):
 
 # ---------------------------------------------------------------------------------------------
 # User-model plugin workloads: spec["model"] = "user" with spec["model_source"] = CUDA source of the dynamics
-# (include/cddp_b200.h, cddp_b200_create_ex); spec["oracle_model"] names the oracle's native twin of the same model.
+# (include/cddp_b200.h, cddp_b200_create_ex); spec["twin_model"] names the CPU checker's native implementation of the same model.
 # ---------------------------------------------------------------------------------------------
 BICYCLE_SOURCE = """
 // Bicycle (src/dynamics_model/bicycle.cpp:29-47): state (x, y, theta, v), control (a, delta); p[0] = wheelbase
@@ -403,7 +413,7 @@ def _cfg_bicycle_user(batch, horizon, seed_offset):
     N = horizon or 100
     dt = 0.05
     rng = np.random.default_rng(SEED_BASE + 21 + seed_offset)
-    spec = dict(model="user", oracle_model="bicycle", model_source=BICYCLE_SOURCE, n=4, m=2, horizon=N, dt=dt, integrator="rk4",
+    spec = dict(model="user", twin_model="bicycle", model_source=BICYCLE_SOURCE, n=4, m=2, horizon=N, dt=dt, integrator="rk4",
                 params=[2.0], Q=_diag([0.0, 0.0, 0.0, 0.01]), R=_diag([0.1, 0.5]), Qf=_diag([100.0, 100.0, 50.0, 10.0]),
                 lb=[-2.0, -0.6], ub=[2.0, 0.6])
     options = dict(max_iterations=60, tolerance=1e-5, acceptable_tolerance=1e-7, reg_initial_value=1e-5)
@@ -439,7 +449,7 @@ def _cfg_chain7_user(batch, horizon, seed_offset):
     rng = np.random.default_rng(SEED_BASE + 5 + seed_offset)
     inertia = [1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4]
     qw = [1.0] * 7 + [0.1] * 7
-    spec = dict(model="user", oracle_model="chain7", model_source=CHAIN7_SOURCE, n=14, m=7, horizon=N, dt=dt, integrator="rk4",
+    spec = dict(model="user", twin_model="chain7", model_source=CHAIN7_SOURCE, n=14, m=7, horizon=N, dt=dt, integrator="rk4",
                 params=[9.81, 0.5, 4.0] + inertia, Q=_diag(qw), R=0.1 * np.eye(7), Qf=100.0 * _diag(qw),
                 lb=[-50.0] * 7, ub=[50.0] * 7)
     options = dict(max_iterations=60, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-5)

@@ -133,7 +133,7 @@ MODELS = {"pendulum": f_pendulum, "cartpole": f_cartpole, "unicycle": f_unicycle
 class Problem:
     def __init__(self, spec):
         self.spec = spec
-        self.model = spec.get("oracle_model", spec["model"])
+        self.model = spec.get("twin_model", spec["model"])
         self.n, self.m, self.N = int(spec["n"]), int(spec["m"]), int(spec["horizon"])
         self.dt = float(spec["dt"])
         self.integrator = spec.get("integrator", "rk4")

@@ -121,7 +121,7 @@ class OracleProblem:
         self.n, self.m, self.N = n, m, int(spec["horizon"])
         self._keep = {}
         p = Problem()
-        model = spec.get("oracle_model", spec["model"])  # user-plugin workloads name the oracle's native twin of the model
+        model = spec.get("twin_model", spec["model"])  # user-plugin workloads name the oracle's native twin of the model
         p.model = MODEL_IDS[model] if isinstance(model, str) else int(model)
         p.n, p.m, p.horizon, p.dt = n, m, self.N, float(spec["dt"])
         integ = spec.get("integrator", "rk4")

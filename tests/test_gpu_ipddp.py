@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 STEP_TOL = 1e-9
 COST_TOL = 1e-6
 ROBUST_MARGIN = 1e-9
-CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "cartpole_ipddp", "quadrotor_ipddp",
+CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "pendulum_ipddp_scaled", "cartpole_ipddp", "quadrotor_ipddp",
            "unicycle_obstacle_teq", "unicycle_teq", "cartpole_teq"]  # *_teq: TerminalEqualityConstraint(goal) (terminal-equality branch)
 
 
@@ -101,7 +101,7 @@ def test_whole_solve(cddp, ob, problems, name):
     h, hl = s.get_history()
     o = ob.ipddp_solve_batch(P, oo, oi, cs, cfg["x0"], cfg["xref"], cfg["U0"], cfg["ref_traj"], nthreads=4)
     robust = robust_mask(ob, P, oo, oi, cs, cfg, o)
-    if name in ("unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "unicycle_obstacle_teq", "unicycle_teq"):
+    if name in ("unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "pendulum_ipddp_scaled", "unicycle_obstacle_teq", "unicycle_teq"):
         assert robust.sum() >= B // 2, "workload expected to be mostly roundoff-robust"
     for b in range(B):
         assert np.isfinite(g["cost"][b]) and np.isfinite(g["X"][b]).all()

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import rel_err
 
-IPDDP_CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "cartpole_ipddp", "quadrotor_ipddp",
+IPDDP_CONFIGS = ["unicycle_obstacle", "unicycle_ipddp_free", "pendulum_ipddp", "pendulum_ipddp_scaled", "cartpole_ipddp", "quadrotor_ipddp",
                  "unicycle_obstacle_teq", "unicycle_teq", "cartpole_teq"]
 
 
