@@ -35,6 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONFIG5_CLDDP, CONFIG5_IPDDP = "chain7_user", "chain7_user_ipddp"  # BASELINE config #5 workloads (user-model plugin)
 METRIC = "DDP iterations/sec (instance-iterations: backward sweep + forward line search per problem instance)"
 UNIT = "instance-iterations/s"
 
@@ -52,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads (configs 1, 2, 4, 5)")
     return ap.parse_args()
 
 
@@ -116,6 +118,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def default_batch(config):
+    return {"quadrotor": 4096, "cartpole": 1024, "pendulum": 1, "unicycle_obstacle_teq": 2048}.get(config, 1024)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the pinned host buffers it first-touches) to the CPUs NVML reports as local to
+    GPU `index`, so that every rank's host<->device copies stay on its GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def throughput_options(cfg, max_iterations):
     o = dict(cfg["options"])
     o.update(tolerance=0.0, acceptable_tolerance=0.0, max_iterations=max_iterations)
@@ -130,9 +153,13 @@ def run_reference(args, rank, world):
     import oracle_binding as ob
     problems = importlib.import_module("cddp-cpp_b200.problems")
     threads = ob.hardware_threads()
-    sample = args.cpu_sample or max(threads * 4, 32)
+    # the SAME workload as the GPU arm's rank 0: its per-GPU batch (4096 instances at config 3), not a small sample.  One
+    # step = iters_per_call DDP iterations of that whole batch (~2-3 s of host work on 16 cores).
+    sample = args.cpu_sample or args.batch or default_batch(args.config)
     iters = args.iters_per_call
     cfg = problems.make_config(args.config, batch=sample)
+    if cfg.get("solver") == "ipddp" or cfg["spec"]["model"] == "user":
+        raise SystemExit("bench.py --impl reference: the CPU arm times the CLDDP headline configs")
     P = ob.OracleProblem(cfg["spec"])
     oo = ob.make_options(**throughput_options(cfg, iters))
     times, done = [], 0
@@ -151,7 +178,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["notes"], "n": spec["n"], "m": spec["m"], "horizon": spec["horizon"],
-                   "sample_instances": sample, "iterations_per_step": iters,
+                   "batch_per_gpu": sample, "global_batch": sample, "sample_instances": sample, "iterations_per_step": iters,
+                   "convergence_exits": "disabled (tolerance=0) so every instance does every iteration",
                    "note": "CPU restatement of the reference algorithm (oracle/); the reference itself cannot be built "
                            "here (Eigen 3.4 / autodiff are network FetchContent deps)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
@@ -162,107 +190,171 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_ipddp(cddp, problems, device, with_cpu):
-    """Secondary workload (not the bench line): BASELINE config #4 — unicycle obstacle avoidance, IPDDP, path-inequality
-    (control box + ball) + terminal-equality, n=3 m=2 N=200, batch 2048 — device-resident throughput and per-kernel
-    CUDA-event times, with the CPU oracle beside it.  Convergence exits disabled (tolerance 0) for the timed iterations."""
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
     import torch
-    B, K, W = 2048, 20, 3
-    cfg = problems.make_config("unicycle_obstacle_teq", batch=B)
-    opts = cddp.default_options(**dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
-    s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(**cfg["ipddp_options"]), cfg["constraints"], B, device=device)
-    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(v, world):
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def rank_barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def make_solver(cddp, cfg, opts, B, device):
+    if cfg.get("solver") == "ipddp":
+        return cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(**cfg.get("ipddp_options", {})), cfg["constraints"], B,
+                                 device=device)
+    return cddp.BatchedCLDDP(cfg["spec"], opts, B, device=device)
+
+
+def load_instances(s, cfg):
+    ip = cfg.get("solver") == "ipddp"
+    s.set_instances(cfg["x0"], cfg["xref"], None if ip else cfg["X0"], cfg["U0"], cfg["ref_traj"])
     s.initialize()
+
+
+def measure_iterations(cddp, problems, device, name, global_batch, rank, world, with_cpu, K=20, W=3, peak=None):
+    """Secondary workload, fixed number of batched iterations with the convergence exits disabled (the headline protocol):
+    `global_batch` instances split contiguously over `world` ranks (strong scaling), device-resident inputs, time = max
+    over ranks of the CUDA-event time of K iterations; per-kernel CUDA-event times from a second pass; for IPDDP the
+    backward sweep's algorithmic-HBM roofline; the CPU oracle beside it on rank 0 (single-GPU runs only)."""
+    import torch
+    sharding = importlib.import_module("cddp-cpp_b200.sharding")
+    lo, hi = sharding.shard_bounds(global_batch, rank, world)
+    B = hi - lo
+    full = problems.make_config(name, batch=global_batch)
+    cfg = dict(full)
+    for k in ("x0", "xref", "X0", "U0", "ref_traj"):
+        cfg[k] = None if full[k] is None else full[k][lo:hi]
+    ip = cfg.get("solver") == "ipddp"
+    opts = cddp.default_options(**dict(cfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
+    s = make_solver(cddp, cfg, opts, B, device)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    load_instances(s, cfg)
     s.iterate(W)
     it0 = int(s.get_scalars()["iterations"].sum())
-    torch.cuda.synchronize()
+    rank_barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.set_stream(torch.cuda.current_stream().cuda_stream)
     e0.record()
     s.iterate(K)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    rank_barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
     sc = s.get_scalars()
-    running = int((sc["status"] == 0).sum())
-    done = int(sc["iterations"].sum()) - it0  # instance-iterations actually performed in the timed region
-    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], None)
-    s.initialize()
+    done = sum_over_ranks(int(sc["iterations"].sum()) - it0, world)  # instance-iterations actually performed while timed
+    running = sum_over_ranks(int((sc["status"] == 0).sum()), world)
+    load_instances(s, cfg)
     s.iterate(W)
     s.enable_timing(True)
     s.reset_timing()
     s.iterate(K)
     t = s.get_timing()
-    out = {"workload": cfg["notes"], "solver": "IPDDP", "batch": B, "horizon": cfg["spec"]["horizon"], "dual_dim": s.d,
-           "value": done / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / K, "instance_iterations_timed": done,
-           "instances_running_all_iterations": running,
-           "kernel_ms_per_iteration": {"linearize": t.linearize_ms / max(t.linearize_launches, 1),
-                                       "backward": t.backward_ms / max(t.backward_launches, 1),
-                                       "forward": t.forward_ms / max(t.forward_launches, 1)}}
+    spec = cfg["spec"]
+    n, m, N = spec["n"], spec["m"], spec["horizon"]
+    kms = {"linearize": t.linearize_ms / max(t.linearize_launches, 1), "backward": t.backward_ms / max(t.backward_launches, 1),
+           "forward": t.forward_ms / max(t.forward_launches, 1)}
+    out = {"workload": cfg["notes"], "solver": "IPDDP" if ip else "CLDDP", "global_batch": global_batch, "n_gpus": world,
+           "batch_per_gpu": B, "horizon": N, "scaling": "strong" if world > 1 else "single GPU",
+           "value": done / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / K, "us_per_iteration": 1e3 * ms / K,
+           "instance_iterations_timed": int(done), "instances_running_all_iterations": int(running),
+           "kernel_ms_per_iteration": kms}
+    # backward-sweep roofline in the north star's accounting (SURVEY 8d): CLDDP rows 8(n^2+2nm+n+3m) B per step; IPDDP adds
+    # the reads of y, s, g (3d) and the writes of k_y, K_y, k_s, K_s (2(d + dn))
+    per_step = 8.0 * (n * n + 2 * n * m + n + 3 * m)
+    if ip:
+        d = s.d
+        out["dual_dim"] = d
+        per_step += 8.0 * (3 * d + 2 * (d + d * n))
+    if peak:
+        alg = per_step * N * B
+        ach = alg / (kms["backward"] * 1e-3) / 1e9
+        out["roofline"] = {"kernel": "ip_backward" if ip else "backward_sweep", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                           "frac": ach / peak, "algorithmic_bytes_per_step": per_step, "algorithmic_bytes_per_launch": alg,
+                           "ms_per_launch": kms["backward"]}
     s.close()
-    if with_cpu:
+    if with_cpu and rank == 0 and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_binding as ob
         threads = ob.hardware_threads()
-        sample = 2048
-        ccfg = problems.make_config("unicycle_obstacle_teq", batch=sample)
-        P = ob.OracleProblem(ccfg["spec"])
-        oo = ob.make_options(**dict(ccfg["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
+        P = ob.OracleProblem(full["spec"])
+        oo = ob.make_options(**dict(full["options"], tolerance=0.0, acceptable_tolerance=0.0, max_iterations=W + K))
         t0 = time.perf_counter()
-        r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(**ccfg["ipddp_options"]), ob.ConstraintSet(ccfg["constraints"]), ccfg["x0"], ccfg["xref"],
-                                 ccfg["U0"], None, nthreads=threads)
+        if ip:
+            r = ob.ipddp_solve_batch(P, oo, ob.make_ipddp_options(**full["ipddp_options"]), ob.ConstraintSet(full["constraints"]), full["x0"],
+                                     full["xref"], full["U0"], None, nthreads=threads)
+        else:
+            r = ob.solve_batch(P, oo, full["x0"], full["xref"], full["X0"], full["U0"], full["ref_traj"], nthreads=threads)
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{sample} instances x {W + K} IPDDP iterations, {dt:.2f}s wall"}
+                               "sample": f"{global_batch} instances x {W + K} iterations, {dt:.2f}s wall"}
     return out
 
 
-def measure_user_solve(cddp, problems, device, name, B, cpu_sample, with_cpu):
-    """Secondary workload (not the bench line): the BASELINE config #5 stand-in — a 7-joint chain supplied through the
-    user-model plugin (CUDA source compiled by NVRTC at create time), n=14 m=7 N=150.  Measured as what a caller runs: ONE
-    solve() of the whole batch to the workload's own tolerances (instances stop when they converge), instance-iterations
-    actually performed / device time; the CPU oracle runs the same solves on a sample."""
+def measure_solve(cddp, problems, device, name, global_batch, rank, world, cpu_sample, with_cpu):
+    """Secondary workload measured as what a caller runs: ONE solve() of the whole batch to the workload's own tolerances
+    (instances stop when they converge), `global_batch` instances split over `world` ranks; instance-iterations actually
+    performed / max-over-ranks device time; the CPU oracle runs the same solves on a sample (rank 0, single-GPU runs)."""
     import torch
-    cfg = problems.make_config(name, batch=B)
+    sharding = importlib.import_module("cddp-cpp_b200.sharding")
+    lo, hi = sharding.shard_bounds(global_batch, rank, world)
+    B = hi - lo
+    full = problems.make_config(name, batch=global_batch)
+    cfg = dict(full)
+    for k in ("x0", "xref", "X0", "U0", "ref_traj"):
+        cfg[k] = None if full[k] is None else full[k][lo:hi]
     ip = cfg.get("solver") == "ipddp"
-    opts = cddp.default_options(**cfg["options"])
-    if ip:
-        s = cddp.BatchedIPDDP(cfg["spec"], opts, cddp.default_ipddp_options(**cfg.get("ipddp_options", {})), cfg["constraints"], B,
-                              device=device)
-    else:
-        s = cddp.BatchedCLDDP(cfg["spec"], opts, B, device=device)
+    s = make_solver(cddp, cfg, cddp.default_options(**cfg["options"]), B, device)
     s.set_stream(torch.cuda.current_stream().cuda_stream)
-
-    def load():
-        s.set_instances(cfg["x0"], cfg["xref"], None if ip else cfg["X0"], cfg["U0"], cfg["ref_traj"])
-        s.initialize()
-
-    load()
-    s.solve()  # untimed: first launches of the JIT-compiled module
+    load_instances(s, cfg)
+    s.solve()  # untimed: first launches (of the JIT-compiled module for a user model)
     torch.cuda.synchronize()
-    load()
+    load_instances(s, cfg)
+    rank_barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     s.solve()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    rank_barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
     sc = s.get_scalars()
-    done = int(sc["iterations"].sum())
-    load()
+    done = sum_over_ranks(int(sc["iterations"].sum()), world)
+    load_instances(s, cfg)
     s.enable_timing(True)
     s.reset_timing()
     s.solve()
     t = s.get_timing()
-    out = {"workload": cfg["notes"], "solver": "IPDDP" if ip else "CLDDP", "batch": B, "horizon": cfg["spec"]["horizon"],
-           "value": done / (ms * 1e-3), "unit": UNIT, "solve_ms": ms, "instance_iterations": done,
-           "mean_iterations": done / B, "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sc["status"], return_counts=True))},
-           "mean_cost": float(np.mean(sc["cost"])),
-           "kernel_ms_total": {"linearize": t.linearize_ms, "backward": t.backward_ms, "forward": t.forward_ms},
-           "kernel_launches": {"linearize": t.linearize_launches, "backward": t.backward_launches, "forward": t.forward_launches}}
+    out = {"workload": cfg["notes"], "solver": "IPDDP" if ip else "CLDDP", "global_batch": global_batch, "n_gpus": world,
+           "batch_per_gpu": B, "horizon": cfg["spec"]["horizon"], "scaling": "strong" if world > 1 else "single GPU",
+           "value": done / (ms * 1e-3), "unit": UNIT, "solve_ms": ms, "instance_iterations": int(done),
+           "mean_iterations": done / global_batch,
+           "status_counts_rank0": {int(k): int(v) for k, v in zip(*np.unique(sc["status"], return_counts=True))},
+           "mean_cost_rank0": float(np.mean(sc["cost"])),
+           "kernel_ms_total_rank0": {"linearize": t.linearize_ms, "backward": t.backward_ms, "forward": t.forward_ms},
+           "kernel_launches_rank0": {"linearize": t.linearize_launches, "backward": t.backward_launches, "forward": t.forward_launches,
+                                     "other": t.other_launches}}
     if ip:
         out["dual_dim"] = s.d
     s.close()
-    if with_cpu:
+    if with_cpu and rank == 0 and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_binding as ob
         threads = ob.hardware_threads()
         ccfg = problems.make_config(name, batch=cpu_sample)
@@ -275,8 +367,8 @@ def measure_user_solve(cddp, problems, device, name, B, cpu_sample, with_cpu):
         else:
             r = ob.solve_batch(P, oo, ccfg["x0"], ccfg["xref"], ccfg["X0"], ccfg["U0"], ccfg["ref_traj"], nthreads=threads)
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{cpu_sample} instances solved to tolerance, {dt:.2f}s wall"}
+        out["cpu_baseline"] = {"value": float(r["iterations"].sum()) / dt, "unit": UNIT, "cores": min(threads, cpu_sample), "kind": "port",
+                               "sample": f"{cpu_sample} instance(s) solved to tolerance, {dt:.3f}s wall"}
     return out
 
 
@@ -295,6 +387,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -304,7 +397,7 @@ def main():
 
     # ---- workload: BASELINE config #3 per GPU (weak scaling: the batch shards with no exchange) ----
     base = problems.make_config(args.config, batch=1)
-    per_gpu = args.batch or {"quadrotor": 4096, "cartpole": 1024, "pendulum": 1}.get(args.config, 1024)
+    per_gpu = args.batch or default_batch(args.config)
     cfg = problems.make_config(args.config, batch=per_gpu, seed_offset=1000 * rank)
     spec = cfg["spec"]
     n, m, N, B = spec["n"], spec["m"], spec["horizon"], per_gpu
@@ -404,6 +497,8 @@ def main():
         lib = solver.lib
 
         class Lane:
+            with_gains = False  # payload of the download: trajectories + scalars, or the full CDDPSolution incl. K_u_
+
             def __init__(self, slv, strm):
                 self.s, self.stream = slv, strm
                 self.solved = torch.cuda.Event()  # recorded after the last kernel of this lane's solve
@@ -431,8 +526,8 @@ def main():
                 cddp._check(lib.cddp_b200_solve(h))
                 self.solved.record(self.stream)
                 get = lib.cddp_b200_get_solution if blocking else lib.cddp_b200_get_solution_async
-                cddp._check(get(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr(), hout["cost"].data_ptr(),
-                                hout["iters"].data_ptr(), hout["status"].data_ptr(), None, None, None))
+                cddp._check(get(h, hout["X"].data_ptr(), hout["U"].data_ptr(), hout["K"].data_ptr() if Lane.with_gains else None,
+                                hout["cost"].data_ptr(), hout["iters"].data_ptr(), hout["status"].data_ptr(), None, None, None))
 
             def wait(self):
                 self.s.synchronize()
@@ -441,53 +536,76 @@ def main():
 
         lane0 = Lane(solver, torch.cuda.Stream())
         h2d = sum(v.numel() * v.element_size() for v in lane0.hin.values()) + (lane0.hrt.numel() * 8 if lane0.hrt is not None else 0)
-        d2h = sum(v.numel() * v.element_size() for v in lane0.hout.values())
+        d2h_full = sum(v.numel() * v.element_size() for v in lane0.hout.values())
+        d2h = d2h_full - lane0.hout["K"].numel() * 8
         calls = max(args.e2e_calls, 2)
-        # (a) serial: one handle, blocking calls
-        lane0.enqueue(True)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(calls):
-            lane0.enqueue(True)
-        barrier()
-        dt_serial = time.perf_counter() - t0
-        # (b) pipelined: three handles, asynchronous calls.  The link is the narrow part (57 MB up + 227 MB down per call,
-        # ~10 ms of PCIe time against 11.7 ms of kernels): with two lanes the upload of call k+1 could only be enqueued
-        # once the download of call k-1 had finished (same lane), and the two copies ran back to back; the third lane
-        # lets call k+1's upload run against call k-1's download (full duplex, two copy engines).
         extra = [cddp.BatchedCLDDP(spec, cddp.default_options(**throughput_options(cfg, ipc)), B, device=local_rank) for _ in range(2)]
         lanes = [lane0] + [Lane(sv, torch.cuda.Stream()) for sv in extra]
         NL = len(lanes)
-        for ln in lanes:
-            ln.s.set_poll_interval(0)
-            ln.enqueue(False)
-            ln.wait()
-        barrier()
-        t0 = time.perf_counter()
-        inflight = [False] * NL
-        for k in range(calls):
-            i = k % NL
-            if inflight[i]:
-                lanes[i].wait()
-            prev = (i - 1) % NL
-            lanes[i].enqueue(False, after=lanes[prev].solved if inflight[prev] else None)
-            inflight[i] = True
-        for j in range(NL):
-            i = (calls + j) % NL  # oldest first
-            if inflight[i]:
-                lanes[i].wait()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt, dt_serial], device="cuda", dtype=torch.float64)
+
+        def serial():  # one handle, blocking calls
+            lane0.s.set_poll_interval(-1)
+            lane0.enqueue(True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                lane0.enqueue(True)
+            barrier()
+            return time.perf_counter() - t0
+
+        def pipelined():
+            # three handles, asynchronous calls: call k+1's upload runs against call k-1's download (full duplex, two copy
+            # engines) and both against call k's kernels
+            for ln in lanes:
+                ln.s.set_poll_interval(0)
+                ln.enqueue(False)
+                ln.wait()
+            barrier()
+            t0 = time.perf_counter()
+            inflight = [False] * NL
+            for k in range(calls):
+                i = k % NL
+                if inflight[i]:
+                    lanes[i].wait()
+                prev = (i - 1) % NL
+                lanes[i].enqueue(False, after=lanes[prev].solved if inflight[prev] else None)
+                inflight[i] = True
+            for j in range(NL):
+                i = (calls + j) % NL  # oldest first
+                if inflight[i]:
+                    lanes[i].wait()
+            barrier()
+            return time.perf_counter() - t0
+
+        def over_ranks(*ts):
+            if world == 1:
+                return ts
+            t = torch.tensor(list(ts), device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, dt_serial = float(t[0].item()), float(t[1].item())
+            return tuple(float(v) for v in t)
+
+        # payload 1 (e2e.value): what a serving / MPC caller reads back every call — the optimised trajectories X, U and the
+        # per-instance cost / iterations / status.  payload 2 (with_gains_*): the whole CDDPSolution of the reference
+        # including the feedback gains K_u_ (cddp_core.hpp:54-103), 3x the bytes; both through the same entry points.
+        Lane.with_gains = False
+        dt_serial = serial()
+        dt = pipelined()
+        Lane.with_gains = True
+        dt_full = pipelined()
+        Lane.with_gains = False
+        dt, dt_serial, dt_full = over_ranks(dt, dt_serial, dt_full)
         e2e = {"value": world * B * ipc * calls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "iterations_per_call": ipc, "calls": calls, "ms_per_call": 1e3 * dt / calls,
                "serial_value": world * B * ipc * calls / dt_serial, "serial_ms_per_call": 1e3 * dt_serial / calls,
-               "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution[_async] on pinned host buffers; "
-                      "value = three handles used in rotation on three CUDA streams (copies overlap the other lanes' kernels, "
-                      "kernels of different lanes are serialised by an event), serial_value = one handle, blocking calls"}
+               "with_gains_value": world * B * ipc * calls / dt_full, "with_gains_ms_per_call": 1e3 * dt_full / calls,
+               "with_gains_d2h_bytes_per_step": int(d2h_full),
+               "host_link_GBps_per_gpu": {"payload": (h2d + d2h) * calls / dt / 1e9, "with_gains": (h2d + d2h_full) * calls / dt_full / 1e9},
+               "numa_local_cpus": numa_cpus,
+               "api": "cddp_b200_set_instances + cddp_b200_solve + cddp_b200_get_solution[_async] on pinned host buffers allocated "
+                      "on the GPU's NUMA node; value = X, U, cost, iterations, status downloaded every call (K pointer NULL), "
+                      "with_gains_value = the same calls downloading the feedback gains K too; three handles used in rotation "
+                      "on three CUDA streams (copies overlap the other lanes' kernels, kernels of different lanes are serialised "
+                      "by an event); serial_value = one handle, blocking calls"}
         for sv in extra:
             sv.close()
         solver.set_stream(stream.cuda_stream)
@@ -510,14 +628,23 @@ def main():
                "sample": f"{sample} instances x {it_cpu} DDP iterations of the same workload, {dt:.1f}s wall, std::thread static partition",
                "note": "CPU restatement of the reference algorithm (Eigen/autodiff unavailable, reference not buildable here)"}
 
+    # ---- the other BASELINE.json configs, each on the GPU count it is stated for (all ranks take part: strong scaling) ----
     other = None
-    if rank == 0 and world == 1 and args.config == "quadrotor" and not args.no_cpu_baseline:
+    if args.config == "quadrotor" and not args.no_other:
+        peak_gbs = float(peaks["hbm_gbs"])
+        with_cpu = not args.no_cpu_baseline
+        jobs = []
+        if world == 1:
+            jobs += [("clddp_config1_pendulum_single_trajectory", lambda: measure_solve(cddp, problems, local_rank, "pendulum", 1, rank, world, 1, with_cpu)),
+                     ("clddp_config2_cartpole_batch1024", lambda: measure_iterations(cddp, problems, local_rank, "cartpole", 1024, rank, world, with_cpu, peak=peak_gbs)),
+                     ("clddp_config2_cartpole_batch1024_solve", lambda: measure_solve(cddp, problems, local_rank, "cartpole", 1024, rank, world, 1024, with_cpu))]
+        if world in (1, 4):
+            jobs += [("ipddp_config4_unicycle_obstacle_teq_batch2048", lambda: measure_iterations(cddp, problems, local_rank, "unicycle_obstacle_teq", 2048, rank, world, with_cpu, peak=peak_gbs))]
+        if world in (1, 8):
+            jobs += [("clddp_config5_7dof_user_model_batch8192", lambda: measure_solve(cddp, problems, local_rank, CONFIG5_CLDDP, 8192, rank, world, 1024, with_cpu)),
+                     ("ipddp_config5_7dof_user_model_batch8192", lambda: measure_solve(cddp, problems, local_rank, CONFIG5_IPDDP, 8192, rank, world, 256, with_cpu))]
         other = {}
-        for key, fn in (("ipddp_config4_unicycle_obstacle_teq", lambda: measure_ipddp(cddp, problems, local_rank, True)),
-                        ("clddp_config5_standin_chain7_user_model",
-                         lambda: measure_user_solve(cddp, problems, local_rank, "chain7_user", 8192, 1024, True)),
-                        ("ipddp_config5_standin_chain7_user_model",
-                         lambda: measure_user_solve(cddp, problems, local_rank, "chain7_user_ipddp", 8192, 256, True))):
+        for key, fn in jobs:
             try:
                 other[key] = fn()
             except Exception as e:  # secondary measurement: never take the bench line down with it
