@@ -35,7 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CONFIG5_CLDDP, CONFIG5_IPDDP = "chain7_user", "chain7_user_ipddp"  # BASELINE config #5 workloads (user-model plugin)
+CONFIG5_CLDDP, CONFIG5_IPDDP = "manip7_user", "manip7_user_ipddp"  # BASELINE config #5 workloads (user-model plugin)
 METRIC = "DDP iterations/sec (instance-iterations: backward sweep + forward line search per problem instance)"
 UNIT = "instance-iterations/s"
 

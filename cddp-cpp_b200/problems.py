@@ -73,6 +73,7 @@ def make_config(name: str, batch: int | None = None, horizon: int | None = None,
         "quadrotor_ipddp": _cfg_quadrotor_ipddp, "bicycle_user": _cfg_bicycle_user, "bicycle_user_ipddp": _cfg_bicycle_user_ipddp,
         "chain7_user": _cfg_chain7_user, "unicycle_obstacle_teq": _cfg_unicycle_obstacle_teq,
         "unicycle_teq": _cfg_unicycle_teq, "cartpole_teq": _cfg_cartpole_teq, "chain7_user_ipddp": _cfg_chain7_user_ipddp,
+        "manip7_user": _cfg_manip7_user, "manip7_user_ipddp": _cfg_manip7_user_ipddp,
     }
     if name not in builders:
         raise KeyError(f"unknown config {name!r}; have {sorted(builders)}")
@@ -406,6 +407,84 @@ __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *x
 """
 
 
+MANIP7_SOURCE = """
+// 7-DOF serial manipulator, the n-joint generalisation of the reference's 3-DOF Manipulator (src/dynamics_model/
+// manipulator.cpp:29-51 dynamics, :174-208 mass matrix and gravity vector: point masses at the link ends, base joint about
+// the vertical, M_ij = (sum of the masses outboard of max(i,j)) l_i l_j cos(q_{i+1} + ... + q_j)), with the Coriolis /
+// centrifugal vector that belongs to that M(q) (Christoffel symbols) and viscous joint friction:
+//     M(q) qdd + h(q, qd) + G(q) + b qd = tau,   state (q[7], qd[7]), control tau[7]
+// p = g, b, m_0..m_6, l_0..l_6.  sigma_j = q_1 + ... + q_j (sigma_0 = 0), w_j = d/dt sigma_j:
+//     M_ij   = mu_max(i,j) l_i l_j cos(sigma_j - sigma_i),  mu_j = m_j + ... + m_6
+//     h_k    = sum_j Mdot_kj qd_j - 1/2 d/dq_k (qd^T M qd),  Mdot_ij = -S_ij (w_j - w_i),  S_ij = mu_j l_i l_j sin(sigma_j - sigma_i) (i < j)
+//              d/dq_k (qd^T M qd) = -2 sum_{i < k <= j} S_ij qd_i qd_j
+//     G_0 = 0,  G_k = -sum_{j >= k} mu_j g l_j cos(sigma_j)                     (manipulator.cpp:200-206)
+// qdd from an LDL^T factorisation of the 7 x 7 mass matrix (positive definite for positive masses and lengths).
+template <class T>
+__device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot) {
+  const double g = p[0], bv = p[1];
+  const double *mass = p + 2, *len = p + 9;
+  double mu[7];
+  mu[6] = mass[6];
+  for (int j = 5; j >= 0; --j) mu[j] = mu[j + 1] + mass[j];
+  T c[7], s[7], w[7];
+  {
+    T sg = x[0] * 0.0, sv = x[0] * 0.0;
+    for (int j = 0; j < 7; ++j) {
+      if (j > 0) {
+        sg = sg + x[j];
+        sv = sv + x[7 + j];
+      }
+      c[j] = cos(sg);
+      s[j] = sin(sg);
+      w[j] = sv;
+    }
+  }
+  T M[7][7], r[7];
+  for (int k = 0; k < 7; ++k) r[k] = u[k] - bv * x[7 + k];
+  for (int i = 0; i < 7; ++i) {
+    M[i][i] = x[0] * 0.0 + mu[i] * len[i] * len[i];
+    for (int j = i + 1; j < 7; ++j) {
+      const double a = mu[j] * len[i] * len[j];
+      M[i][j] = a * (c[i] * c[j] + s[i] * s[j]);
+      const T S = a * (s[j] * c[i] - c[j] * s[i]);
+      const T md = S * (w[j] - w[i]);  // = -Mdot_ij
+      r[i] = r[i] + md * x[7 + j];
+      r[j] = r[j] + md * x[7 + i];
+      const T P = S * (x[7 + i] * x[7 + j]);
+      for (int k = i + 1; k <= j; ++k) r[k] = r[k] - P;
+    }
+  }
+  {
+    T acc = x[0] * 0.0;  // -G_k = sum_{j >= k} mu_j g l_j cos(sigma_j), k >= 1
+    for (int k = 6; k >= 1; --k) {
+      acc = acc + (mu[k] * g * len[k]) * c[k];
+      r[k] = r[k] + acc;
+    }
+  }
+  // LDL^T in place (unit lower factor in the upper-triangle slots M[j][i], i > j; pivots on the diagonal)
+  for (int j = 0; j < 7; ++j) {
+    T d = M[j][j];
+    for (int k = 0; k < j; ++k) d = d - M[k][j] * M[k][j] * M[k][k];
+    M[j][j] = d;
+    for (int i = j + 1; i < 7; ++i) {
+      T v = M[j][i];
+      for (int k = 0; k < j; ++k) v = v - M[k][i] * M[k][j] * M[k][k];
+      M[j][i] = v / d;
+    }
+  }
+  for (int i = 0; i < 7; ++i)
+    for (int k = 0; k < i; ++k) r[i] = r[i] - M[k][i] * r[k];
+  for (int i = 0; i < 7; ++i) r[i] = r[i] / M[i][i];
+  for (int i = 6; i >= 0; --i)
+    for (int k = i + 1; k < 7; ++k) r[i] = r[i] - M[i][k] * r[k];
+  for (int i = 0; i < 7; ++i) {
+    xdot[i] = x[7 + i];
+    xdot[7 + i] = r[i];
+  }
+}
+"""
+
+
 def _cfg_bicycle_user(batch, horizon, seed_offset):
     """The reference's Bicycle model (src/dynamics_model/bicycle.cpp) supplied through the user-model plugin; CLDDP with a
     control box (acceleration, steering), parking-style point-to-point problem."""
@@ -462,6 +541,55 @@ def _cfg_chain7_user(batch, horizon, seed_offset):
     U0 = np.zeros((B, N, 7))
     return dict(name="chain7_user", config_id=5, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
                 notes="7-joint chain (plugin model; stands in for BASELINE config #5) n=14 m=7 N=150, CLDDP + control box +-50")
+
+
+MANIP7_PARAMS = [9.81, 0.05] + [1.0, 1.0, 1.0, 0.8, 0.6, 0.5, 0.4] + [0.3, 0.3, 0.25, 0.25, 0.2, 0.15, 0.1]  # g, b, masses, lengths
+
+
+def _cfg_manip7_user(batch, horizon, seed_offset):
+    """BASELINE config #5: 7-DOF manipulator n=14 m=7 N=150, control box, CLDDP.  Problem data patterned on the reference's
+    3-DOF example (examples/cddp_manipulator.cpp:23-70): dt = 0.01, torque box +-50, Q = diag(1 x7, 0.1 x7), R = 0.1 I,
+    Qf = 100 Q, max_iterations 80, line_search.max_iterations 20 -> capped at 16 candidates here; the nominal is the arm at
+    rest (see below) instead of the example's straight line.  The model is the 7-joint
+    generalisation of the reference's Manipulator (MANIP7_SOURCE), supplied through the user-model plugin; the reference
+    itself has only the 3-DOF model.  Per-instance goals are perturbed."""
+    B = batch or 4
+    N = horizon or 150
+    dt = 0.01
+    rng = np.random.default_rng(SEED_BASE + 5 + seed_offset)
+    qw = [1.0] * 7 + [0.1] * 7
+    spec = dict(model="user", twin_model="manip7", model_source=MANIP7_SOURCE, n=14, m=7, horizon=N, dt=dt, integrator="rk4",
+                params=MANIP7_PARAMS, Q=_diag(qw), R=0.1 * np.eye(7), Qf=100.0 * _diag(qw), lb=[-50.0] * 7, ub=[50.0] * 7)
+    options = dict(max_iterations=80, ls_max_iterations=16)
+    x0 = np.zeros((B, 14))
+    x0[:, 1] = -math.pi / 2.0  # arm hanging: sigma_j = -pi/2 for every j >= 1
+    xref = np.zeros((B, 14))
+    xref[:, :7] = np.array([math.pi / 2, -math.pi / 6, -math.pi / 3, math.pi / 4, -math.pi / 4, math.pi / 6, 0.0])
+    if B > 1:
+        xref[1:, :7] += 0.1 * rng.standard_normal((B - 1, 7))
+    # the hanging arm at rest is an equilibrium of the model, so X0 = x0 repeated with U0 = 0 is a dynamically consistent
+    # nominal.  (The example's straight-line X0 with U0 = 0 is not: CLDDP takes the cost of the GIVEN trajectory as its
+    # starting point, clddp_solver.cpp:62-66, no rollout can match the cost of a path that reaches the goal for free, every
+    # line search fails and the solve ends at the regularisation limit with the nominal unchanged.)
+    X0 = np.repeat(x0[:, None, :], N + 1, axis=0 + 1)
+    U0 = np.zeros((B, N, 7))
+    return dict(name="manip7_user", config_id=5, spec=spec, options=options, x0=x0, xref=xref, X0=X0, U0=U0, ref_traj=None,
+                notes="7-DOF manipulator (plugin model: M(q) qdd + h(q,qd) + G(q) + b qd = tau, the 7-joint generalisation of "
+                      "src/dynamics_model/manipulator.cpp) n=14 m=7 N=150, CLDDP + torque box +-50")
+
+
+def _cfg_manip7_user_ipddp(batch, horizon, seed_offset):
+    """BASELINE config #5 as worded ("7-DOF manipulator n=14 m=7 N=150, mixed constraints"): the same model under IPDDP
+    with MIXED path constraints — torque box (ControlConstraint, 14 rows) + joint-angle / joint-rate box (StateConstraint,
+    28 rows): d = 42."""
+    cfg = _cfg_manip7_user(batch, horizon, seed_offset)
+    spec = dict(cfg["spec"], lb=None, ub=None)
+    cfg.update(name="manip7_user_ipddp", config_id=5, solver="ipddp", spec=spec, X0=None, ipddp_options={},
+               options=dict(max_iterations=80, tolerance=1e-4, acceptable_tolerance=1e-6, reg_initial_value=1e-5),
+               constraints=[dict(type="control_box", lb=[-50.0] * 7, ub=[50.0] * 7),
+                            dict(type="state_box", lb=[-3.3] * 7 + [-8.0] * 7, ub=[3.3] * 7 + [8.0] * 7)],
+               notes="7-DOF manipulator (plugin model) n=14 m=7 N=150, IPDDP, torque box + joint/rate box (d=42)")
+    return cfg
 
 
 def _cfg_chain7_user_ipddp(batch, horizon, seed_offset):

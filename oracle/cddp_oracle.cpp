@@ -235,6 +235,69 @@ void chain7_f(const double *P, const T *x, const T *u, T *xd) {
   }
 }
 
+/* 7-DOF serial manipulator: the n-joint generalisation of the reference's 3-DOF Manipulator (manipulator.cpp:29-51,
+ * :174-208 — point masses at the link ends, base joint about the vertical, M_ij = mu_max(i,j) l_i l_j cos(q_{i+1}+...+q_j),
+ * G_k = -sum_{j>=k} mu_j g l_j cos(q_1+...+q_j)) with the Coriolis / centrifugal vector of that M(q) and viscous friction:
+ * M(q) qdd + h(q,qd) + G(q) + b qd = tau.  The native twin of the plugin model MANIP7_SOURCE (cddp-cpp_b200/problems.py);
+ * BASELINE config #5.  params: g, b, m_0..m_6, l_0..l_6.  Written independently of the plugin text: explicit h_k sums,
+ * Gaussian elimination with the mass matrix kept whole. */
+template <typename T>
+void manip7_f(const double *P, const T *x, const T *u, T *xd) {
+  const double g = P[0], bv = P[1];
+  const double *mass = P + 2, *len = P + 9;
+  double mu[7];
+  for (int j = 0; j < 7; ++j) {
+    mu[j] = 0.0;
+    for (int k = j; k < 7; ++k) mu[j] += mass[k];
+  }
+  const T zero = x[0] * 0.0;
+  T sig[7], w[7];
+  sig[0] = zero;
+  w[0] = zero;
+  for (int j = 1; j < 7; ++j) {
+    sig[j] = sig[j - 1] + x[j];
+    w[j] = w[j - 1] + x[7 + j];
+  }
+  T M[7][7], S[7][7], rhs[7];
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 7; ++j) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      const double a = mu[hi] * len[lo] * len[hi];
+      M[i][j] = a * cos(sig[hi] - sig[lo]);
+      S[i][j] = a * sin(sig[hi] - sig[lo]); /* symmetric: S_ij = S_ji = a sin(sigma_hi - sigma_lo) */
+    }
+  for (int k = 0; k < 7; ++k) {
+    T h = zero; /* h_k = sum_j Mdot_kj qd_j - 1/2 d/dq_k (qd^T M qd) */
+    for (int j = 0; j < 7; ++j) {
+      if (j == k) continue;
+      const int lo = k < j ? k : j, hi = k < j ? j : k;
+      h = h - S[k][j] * (w[hi] - w[lo]) * x[7 + j];
+    }
+    for (int i = 0; i < k; ++i)
+      for (int j = k; j < 7; ++j) h = h + S[i][j] * x[7 + i] * x[7 + j];
+    T G = zero;
+    if (k >= 1)
+      for (int j = k; j < 7; ++j) G = G - (mu[j] * g * len[j]) * cos(sig[j]);
+    rhs[k] = u[k] - h - G - bv * x[7 + k];
+  }
+  /* qdd = M^-1 rhs: Gaussian elimination without pivoting (M is symmetric positive definite) */
+  for (int c = 0; c < 7; ++c)
+    for (int r = c + 1; r < 7; ++r) {
+      const T f = M[r][c] / M[c][c];
+      for (int k = c; k < 7; ++k) M[r][k] = M[r][k] - f * M[c][k];
+      rhs[r] = rhs[r] - f * rhs[c];
+    }
+  for (int r = 6; r >= 0; --r) {
+    T acc = rhs[r];
+    for (int k = r + 1; k < 7; ++k) acc = acc - M[r][k] * rhs[k];
+    rhs[r] = acc / M[r][r];
+  }
+  for (int i = 0; i < 7; ++i) {
+    xd[i] = x[7 + i];
+    xd[7 + i] = rhs[i];
+  }
+}
+
 void pendulum_f(const double *P, const double *x, const double *u, double *xd) {
   const double length = P[0], mass = P[1], damping = P[2], gravity = 9.81;
   const double inertia = mass * length * length;
@@ -312,6 +375,7 @@ void continuous_dynamics(const oracle_problem *p, const double *x, const double 
     case ORACLE_QUADROTOR: quadrotor_f<double>(p->model_params, x, u, xd); break;
     case ORACLE_BICYCLE: bicycle_f<double>(p->model_params, x, u, xd); break;
     case ORACLE_CHAIN7: chain7_f<double>(p->model_params, x, u, xd); break;
+    case ORACLE_MANIP7: manip7_f<double>(p->model_params, x, u, xd); break;
     case ORACLE_LTI: {
       /* base-class fallback dynamical_system.cpp:85-98: (x_next - x)/dt */
       double xn[MAXN];
@@ -357,6 +421,7 @@ void jacobians(const oracle_problem *p, const double *x, const double *u, double
     case ORACLE_CARTPOLE:
     case ORACLE_BICYCLE: /* analytic in the reference (bicycle.cpp:66-113) = the derivative of the same expressions */
     case ORACLE_CHAIN7:
+    case ORACLE_MANIP7:
     case ORACLE_QUADROTOR: { /* autodiff::jacobian: cartpole.cpp:95-103, quadrotor.cpp:116-140 */
       const int nd = n + m;
       Dual xs[MAXN], us[MAXM], xd[MAXN];
@@ -375,6 +440,8 @@ void jacobians(const oracle_problem *p, const double *x, const double *u, double
         bicycle_f<Dual>(P, xs, us, xd);
       else if (p->model == ORACLE_CHAIN7)
         chain7_f<Dual>(P, xs, us, xd);
+      else if (p->model == ORACLE_MANIP7)
+        manip7_f<Dual>(P, xs, us, xd);
       else
         quadrotor_f<Dual>(P, xs, us, xd);
       for (int i = 0; i < n; ++i) {

@@ -29,7 +29,8 @@ extern "C" {
 
 /* model ids (src/dynamics_model/<name>.cpp) */
 enum { ORACLE_PENDULUM = 0, ORACLE_CARTPOLE = 1, ORACLE_UNICYCLE = 2, ORACLE_QUADROTOR = 3, ORACLE_LTI = 4,
-       ORACLE_BICYCLE = 5 /* bicycle.cpp */, ORACLE_CHAIN7 = 6 /* test plugin model, not in the reference */ };
+       ORACLE_BICYCLE = 5 /* bicycle.cpp */, ORACLE_CHAIN7 = 6 /* test plugin model, not in the reference */,
+       ORACLE_MANIP7 = 7 /* 7-DOF generalisation of manipulator.cpp (BASELINE config #5) */ };
 /* integrators (src/cddp_core/dynamical_system.cpp:28-83) */
 enum { ORACLE_EULER = 0, ORACLE_HEUN = 1, ORACLE_RK3 = 2, ORACLE_RK4 = 3 };
 /* BoxQP status (include/cddp-cpp/cddp_core/boxqp.hpp:47-55) */

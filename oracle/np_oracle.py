@@ -126,8 +126,31 @@ def f_chain7(p, x, u, jac=False):  # test plugin model (not in the reference), s
     return np.concatenate([qd, acc / inertia])
 
 
+def f_manip7(p, x, u, jac=False):
+    """7-DOF manipulator (BASELINE config #5), matrix form: M(q) qdd + h(q,qd) + G(q) + b qd = tau with
+    M_ij = mu_max(i,j) l_i l_j cos(sigma_i - sigma_j), h from the Christoffel symbols of M, see oracle/cddp_oracle.cpp manip7_f.
+    Third, independent statement: h is formed from dM/dq_k tensors."""
+    g, bv = p[0], p[1]
+    mass, ln = np.asarray(p[2:9], float), np.asarray(p[9:16], float)
+    q, qd = x[:7], x[7:]
+    mu = np.cumsum(mass[::-1])[::-1]
+    T = np.tril(np.ones((7, 7)))
+    T[:, 0] = 0.0  # sigma_j = q_1 + ... + q_j
+    sig = T @ q
+    A = np.array([[mu[max(i, j)] * ln[i] * ln[j] for j in range(7)] for i in range(7)])
+    D = sig[:, None] - sig[None, :]
+    M = A * np.cos(D)
+    # dM/dq_k = -A sin(D) * (dsig_i/dq_k - dsig_j/dq_k)
+    dM = [-(A * np.sin(D)) * (T[:, k][:, None] - T[:, k][None, :]) for k in range(7)]
+    Mdot = sum(dM[k] * qd[k] for k in range(7))
+    h = Mdot @ qd - 0.5 * np.array([qd @ dM[k] @ qd for k in range(7)])
+    Gv = np.array([0.0 if k == 0 else -np.sum(mu[k:] * g * ln[k:] * np.cos(sig[k:])) for k in range(7)], dtype=M.dtype)
+    qdd = np.linalg.solve(M, u - h - Gv - bv * qd)
+    return np.concatenate([qd, qdd])
+
+
 MODELS = {"pendulum": f_pendulum, "cartpole": f_cartpole, "unicycle": f_unicycle, "quadrotor": f_quadrotor,
-          "bicycle": f_bicycle, "chain7": f_chain7}
+          "bicycle": f_bicycle, "chain7": f_chain7, "manip7": f_manip7}
 
 
 class Problem:

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4, "bicycle": 5, "chain7": 6}
+MODEL_IDS = {"pendulum": 0, "cartpole": 1, "unicycle": 2, "quadrotor": 3, "lti": 4, "bicycle": 5, "chain7": 6, "manip7": 7}
 INTEGRATORS = {"euler": 0, "heun": 1, "rk3": 2, "rk4": 3}
 STATUS_STRINGS = {0: "Running", 1: "OptimalSolutionFound", 2: "AcceptableSolutionFound", 3: "MaxIterationsReached",
                   4: "RegularizationLimitReached_NotConverged", 5: "MaxCpuTimeReached"}

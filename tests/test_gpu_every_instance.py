@@ -23,7 +23,10 @@ STEP_COST_TOL = 1e-8  # one iteration from an identical state
 MARGIN_TOL = 1e-9   # a decision on which the two disagree must be this close to its threshold
 
 # name, batch, max_iterations of the lock-step run (None = the config's own)
-FULL = [("pendulum", 1, None), ("cartpole", 1024, None), ("quadrotor", 4096, None)]
+# config 5 (7-DOF manipulator through the user-model plugin, CLDDP + torque box): 512 instances of the 8192 (the oracle
+# needs ~40 ms per instance-iteration-batch on the host; every one of the 512 is checked at every iteration, including the
+# ones that end at the regularisation limit — their status must be the oracle's)
+FULL = [("pendulum", 1, None), ("cartpole", 1024, None), ("quadrotor", 4096, None), ("manip7_user", 512, None)]
 
 
 def snapshot(s):
