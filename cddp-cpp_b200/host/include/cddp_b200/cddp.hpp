@@ -457,8 +457,6 @@ class CDDP {  // cddp_core.hpp:212-442, cddp_core.cpp
   const CDDPOptions &getOptions() const { return options_; }
   const std::map<std::string, std::unique_ptr<Constraint>> &getConstraintSet() const { return path_constraint_set_; }
   const std::map<std::string, std::unique_ptr<Constraint>> &getTerminalConstraintSet() const { return terminal_constraint_set_; }
-  bool hasSystem() const { return (bool)system_; }
-  bool hasObjective() const { return (bool)objective_; }
 
   void setDynamicalSystem(std::unique_ptr<DynamicalSystem> system);
   void setInitialState(const Eigen::VectorXd &initial_state);
@@ -509,13 +507,11 @@ class CDDP {  // cddp_core.hpp:212-442, cddp_core.cpp
   void decreaseRegularization();
   bool isRegularizationLimitReached() const;
 
-  // cddp_core.cpp:272-306; public here because external solvers on the batched path need it too
-  void initializeProblemIfNecessary();
-
  protected:
   virtual std::unique_ptr<ISolverAlgorithm> createSolver(const std::string &solver_type);
 
  private:
+  void initializeProblemIfNecessary();  // cddp_core.cpp:272-306 (private in the reference too, cddp_core.hpp:441)
   std::unique_ptr<DynamicalSystem> system_;
   std::unique_ptr<Objective> objective_;
   std::map<std::string, std::unique_ptr<Constraint>> path_constraint_set_;

@@ -33,11 +33,26 @@ void flatten(const Eigen::MatrixXd &M, std::vector<double> &out) {
     for (long j = 0; j < M.cols(); ++j) out[(size_t)(i * M.cols() + j)] = M(i, j);
 }
 
+// The effect of CDDP::initializeProblemIfNecessary (private, cddp_core.cpp:272-306) that the batched facade needs, through
+// the PUBLIC members of the reference class only (X_, U_ are public fields, cddp_core.hpp:323-326): size the nominal
+// trajectory if the caller gave none, and pin its first state to the initial state.
+void ensure_trajectory(CDDP &c, int n, int m, int N) {
+  auto fits = [](const std::vector<Eigen::VectorXd> &v, int len, int dim) {
+    if ((int)v.size() != len) return false;
+    for (const auto &e : v)
+      if ((int)e.size() != dim) return false;
+    return true;
+  };
+  if (!fits(c.X_, N + 1, n)) c.X_.assign((size_t)(N + 1), Eigen::VectorXd::Zero(n));
+  if (!fits(c.U_, N, m)) c.U_.assign((size_t)N, Eigen::VectorXd::Zero(m));
+  c.X_[0] = c.getInitialState();
+}
+
 // Reads one CDDP into the shared C-ABI description; throws std::runtime_error for anything the device path
 // cannot run (there is no CPU fallback to hand it to).
 void describe(CDDP &ctx, Shared &s) {
-  if (!ctx.hasSystem()) throw std::runtime_error("Dynamical system must be set before solving.");
-  if (!ctx.hasObjective()) throw std::runtime_error("Objective function must be set before solving.");
+  // (a missing system / objective is rejected by CDDP::solve before a plugin is called, cddp_core.cpp:277-282; solveBatch
+  // documents complete problems as its precondition — the reference has no public "is it set" query)
   const DynamicalSystem &sys = ctx.getSystem();
   DeviceModelDescriptor dm;
   if (!sys.getDeviceModel(dm))
@@ -143,7 +158,7 @@ std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, int de
   if (sh.has_ref_traj) rt.resize((size_t)B * (N + 1) * n);
   for (int b = 0; b < B; ++b) {
     CDDP &c = *problems[b];
-    c.initializeProblemIfNecessary();  // sizes X_/U_, X_[0] = x0, cost = inf, reg = initial (cddp_core.cpp:272-306)
+    ensure_trajectory(c, n, m, N);
     const Eigen::VectorXd ref = c.getObjective().getReferenceState();
     if ((int)ref.size() != n) throw std::runtime_error("B200 CLDDP: reference state has the wrong dimension");
     for (int i = 0; i < n; ++i) {
@@ -375,7 +390,7 @@ std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, i
   std::vector<double> x0((size_t)B * n), xref((size_t)B * n), X((size_t)B * (N + 1) * n), U((size_t)B * N * m);
   for (int b = 0; b < B; ++b) {
     CDDP &c = *problems[b];
-    c.initializeProblemIfNecessary();
+    ensure_trajectory(c, n, m, N);
     const Eigen::VectorXd ref = c.getObjective().getReferenceState();
     if ((int)ref.size() != n) throw std::runtime_error("B200 IPDDP: reference state has the wrong dimension");
     for (int i = 0; i < n; ++i) {

@@ -514,3 +514,29 @@ def test_windowed_line_search_changes_nothing(cddp, problems, name, B, N):
         assert np.array_equal(out[0][key], out[1][key]), key
     acc = (out[0]["trace"] & 0xFF)
     print(f"\n[window {name}] accepted-index histogram (0 = failed, k = index k-1): {np.bincount(acc[acc < 0xF0].ravel(), minlength=17).tolist()}")
+
+
+def test_max_cpu_time_stops_the_solve(cddp, problems):
+    """options.max_cpu_time (cddp_solver_base.cpp:77-90): the wall clock is checked before every batched iteration; when
+    it has run out the instances still running end with MaxCpuTimeReached (status 5) after the iterations completed so
+    far, with the trajectory of their last accepted step; instances that had already converged keep their status."""
+    B = 512
+    cfg = problems.make_config("quadrotor", batch=B)
+    s, _ = make(cddp, cfg, B, max_iterations=100000, max_cpu_time=0.05, tolerance=0.0, acceptable_tolerance=0.0)
+    s.solve()
+    r = s.get_solution(want_K=False)
+    assert (r["status"] == 5).all(), np.bincount(r["status"])
+    assert (r["iterations"] >= 1).all() and (r["iterations"] < 100000).all() and len(set(r["iterations"].tolist())) == 1
+    assert np.isfinite(r["cost"]).all()
+    s.close()
+    assert cddp.status_string(5) == "MaxCpuTimeReached"
+    # a generous limit changes nothing
+    a, _ = make(cddp, cfg, B, max_iterations=6, max_cpu_time=1e6)
+    b, _ = make(cddp, cfg, B, max_iterations=6)
+    a.solve()
+    b.solve()
+    ra, rb = a.get_solution(want_K=False), b.get_solution(want_K=False)
+    np.testing.assert_array_equal(ra["cost"], rb["cost"])
+    np.testing.assert_array_equal(ra["status"], rb["status"])
+    a.close()
+    b.close()
