@@ -50,5 +50,14 @@ void registerSolvers(int device = 0);
 // strings, never exceptions (cddp_solver_base.cpp:69,82,162).
 std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, int device = 0);
 
+// The same facade over SEVERAL devices of one node: the batch is cut into contiguous shards of
+// ceil(B / G) problems, shard g goes to devices[g] (an entry may repeat), every shard is driven by its own host thread
+// with its own C-ABI handle and CUDA stream, and nothing is exchanged between devices — the instances share only
+// read-only constants, which every handle uploads for itself.  Solutions come back in problem order.  An exception on
+// any shard is rethrown after all threads have joined.  availableDevices() = {0, ..., cudaGetDeviceCount() - 1}.
+std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, const std::vector<int> &devices);
+std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, const std::vector<int> &devices);
+std::vector<int> availableDevices();
+
 }  // namespace b200
 }  // namespace cddp

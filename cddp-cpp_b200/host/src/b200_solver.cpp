@@ -2,6 +2,8 @@
 #include "cddp_b200/b200_solver.hpp"
 
 #include <chrono>
+#include <exception>
+#include <thread>
 #include <cstring>
 
 #include "../../../include/cddp_b200.h"
@@ -245,6 +247,68 @@ std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, int de
     c.regularization_ = s.final_regularization;
   }
   return out;
+}
+
+// ------------------------------------------------------------------------------------------------ several devices
+namespace {
+template <class SolveOne>
+std::vector<CDDPSolution> solve_sharded(const std::vector<CDDP *> &problems, const std::vector<int> &devices, SolveOne solve_one) {
+  if (devices.empty()) throw std::runtime_error("B200: solveBatch needs at least one device");
+  const size_t B = problems.size(), G = devices.size();
+  if (B == 0) return {};
+  const size_t per = (B + G - 1) / G;  // B_g = ceil(B / G), trailing shards may be short or empty
+  std::vector<std::vector<CDDPSolution>> parts(G);
+  std::vector<std::exception_ptr> errors(G);
+  std::vector<std::thread> threads;
+  for (size_t g = 0; g < G; ++g) {
+    const size_t lo = std::min(g * per, B), hi = std::min((g + 1) * per, B);
+    if (lo == hi) continue;
+    threads.emplace_back([&, g, lo, hi]() {
+      try {
+        std::vector<CDDP *> shard(problems.begin() + (long)lo, problems.begin() + (long)hi);
+        parts[g] = solve_one(shard, devices[g]);
+      } catch (...) {
+        errors[g] = std::current_exception();
+      }
+    });
+  }
+  for (auto &t : threads) t.join();
+  for (auto &e : errors)
+    if (e) std::rethrow_exception(e);
+  std::vector<CDDPSolution> out;
+  out.reserve(B);
+  for (auto &p : parts)
+    for (auto &sol : p) out.push_back(std::move(sol));
+  return out;
+}
+}  // namespace
+
+std::vector<CDDPSolution> solveBatch(const std::vector<CDDP *> &problems, const std::vector<int> &devices) {
+  if (!problems.empty()) {  // structural identity across shards (each shard checks its own members against its first)
+    Shared first;
+    describe(*problems[0], first);
+    const size_t per = (problems.size() + devices.size() - 1) / std::max<size_t>(devices.size(), 1);
+    for (size_t lo = per; lo < problems.size(); lo += per) {
+      Shared other;
+      describe(*problems[lo], other);
+      if (!same_shared(first, other))
+        throw std::runtime_error("B200 CLDDP: solveBatch needs structurally identical problems; instance " + std::to_string(lo) +
+                                 " differs from instance 0");
+    }
+  }
+  return solve_sharded(problems, devices, [](const std::vector<CDDP *> &shard, int dev) { return solveBatch(shard, dev); });
+}
+
+std::vector<CDDPSolution> solveBatchIPDDP(const std::vector<CDDP *> &problems, const std::vector<int> &devices) {
+  return solve_sharded(problems, devices, [](const std::vector<CDDP *> &shard, int dev) { return solveBatchIPDDP(shard, dev); });
+}
+
+std::vector<int> availableDevices() {
+  int count = 0;
+  if (cddp_b200_device_count(&count) != CDDP_B200_OK) count = 0;
+  std::vector<int> d((size_t)std::max(count, 0));
+  for (int i = 0; i < count; ++i) d[(size_t)i] = i;
+  return d;
 }
 
 void CLDDPSolver::initialize(CDDP &context) {

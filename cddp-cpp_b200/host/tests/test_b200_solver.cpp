@@ -152,6 +152,26 @@ void SolveQuadrotorBatch() {
   }
   CHECK(worst < 1e-6);
   std::printf("  quadrotor batch of %d: worst final-cost rel err vs oracle %.2e\n", B, worst);
+  // multi-device entry point: the batch cut into shards, one host thread + handle per shard.  Every available device is
+  // used (a one-GPU box runs three shards on device 0); results must be bitwise those of the single-handle call,
+  // in problem order.
+  std::vector<int> devs = b200::availableDevices();
+  CHECK(!devs.empty());
+  if (devs.size() == 1) devs = {0, 0, 0};
+  for (int b = 0; b < B; ++b) {  // the first call left its solution in the contexts: back to the original nominal
+    std::vector<Eigen::VectorXd> X((size_t)N + 1, batch[(size_t)b]->getInitialState()), U((size_t)N, Eigen::VectorXd::Constant(4, hover));
+    batch[(size_t)b]->setInitialTrajectory(X, U);
+  }
+  auto sharded = b200::solveBatch(batch, devs);
+  CHECK(sharded.size() == (size_t)B);
+  for (int b = 0; b < B; ++b) {
+    CHECK(sharded[(size_t)b].final_objective == sols[(size_t)b].final_objective);
+    CHECK(sharded[(size_t)b].iterations_completed == sols[(size_t)b].iterations_completed);
+    CHECK((sharded[(size_t)b].control_trajectory[3] - sols[(size_t)b].control_trajectory[3]).norm() == 0.0);
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 13; ++j) CHECK(sharded[(size_t)b].feedback_gains[7](i, j) == sols[(size_t)b].feedback_gains[7](i, j));
+  }
+  std::printf("  multi-device solveBatch over %zu shard(s): identical to the single-device call\n", devs.size());
   // mismatched batch is a setup error (exception), not an outcome
   CDDPOptions o2 = o;
   o2.max_iterations = 3;
