@@ -136,7 +136,7 @@ ABI_SYMBOLS = [
     "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_set_line_search_window", "cddp_b200_get_solution_async",
     "cddp_b200_mpc_advance", "cddp_b200_get_first_controls_async",
     "cddp_b200_ipddp_default_options", "cddp_b200_ipddp_create", "cddp_b200_ipddp_dual_dim",
-    "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
+    "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_iteration_state", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
     "cddp_b200_ipddp_get_history", "cddp_b200_create_ex", "cddp_b200_ipddp_create_ex", "cddp_b200_compile_user_model",
     "cddp_b200_last_compile_log", "cddp_b200_enable_trace", "cddp_b200_get_trace",
 ]
@@ -217,6 +217,7 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_ipddp_dual_dim.argtypes = [vp, ip]
     lib.cddp_b200_ipddp_get_solution.argtypes = [vp, vp, vp, vp, vp]
     lib.cddp_b200_ipddp_get_gains.argtypes = [vp, vp, vp, vp, vp]
+    lib.cddp_b200_ipddp_get_iteration_state.argtypes = [vp, vp, vp, vp, vp]
     lib.cddp_b200_ipddp_get_line_search.argtypes = [vp, vp]
     lib.cddp_b200_ipddp_get_history.argtypes = [vp, vp, vp]
     for name in ABI_SYMBOLS:
@@ -588,6 +589,16 @@ class BatchedIPDDP(BatchedCLDDP):
                                                      _ptr(sc)))
         for i, k in enumerate(("mu", "merit", "inf_pr", "inf_comp", "step_norm", "alpha_du", "alpha_pr_max", "alpha_du_max")):
             out[k] = sc[:, i].copy()
+        return out
+
+    def get_iteration_state(self) -> dict:
+        """cddp_b200_ipddp_get_iteration_state: Lambda_T, filter points, filter size, {filter_theta, logsum, lamh}."""
+        B = self.B
+        out = {"lamT": np.zeros((B, self.n)), "filter": np.zeros((B, 8, 2)), "filter_size": np.zeros(B, dtype=np.int32)}
+        sc = np.zeros((B, 3))
+        _check(self.lib.cddp_b200_ipddp_get_iteration_state(self.handle, _ptr(out["lamT"]), _ptr(out["filter"]),
+                                                            C.c_void_p(out["filter_size"].ctypes.data), _ptr(sc)))
+        out["filter_theta"], out["logsum"], out["lamh"] = sc[:, 0].copy(), sc[:, 1].copy(), sc[:, 2].copy()
         return out
 
     def get_ipddp_gains(self) -> dict:

@@ -773,7 +773,6 @@ int cddp_b200_enable_history(cddp_b200_solver *s, int enable) {
 
 int cddp_b200_enable_trace(cddp_b200_solver *s, int enable) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
-  if (s->kind == 1) return CDDP_B200_ERR_INVALID_ARGUMENT;  // CLDDP handles only
   DeviceGuard g(s->device);
   if (!enable) {
     s->d.trace = nullptr;
@@ -1116,6 +1115,38 @@ int cddp_b200_ipddp_get_solution(cddp_b200_solver *s, double *Y, double *S, doub
     CU(cudaStreamSynchronize(s->stream));
     for (size_t b = 0; b < B; ++b)
       for (int k = 0; k < 8; ++k) scalars[b * 8 + k] = tmp[k * B + b];
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int cddp_b200_ipddp_get_iteration_state(cddp_b200_solver *s, double *lamT, double *filter, int *filter_size, double *scalars) {
+  if (!s || s->kind != 1) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(s->device);
+  const size_t B = s->d.B, n = s->d.n;
+  int r;
+  if (lamT) {
+    if (s->ic.teq) {
+      if ((r = download(s, lamT, s->ip.lamT, B * n * sizeof(double)))) return r;
+    } else {
+      std::memset(lamT, 0, B * n * sizeof(double));
+    }
+  }
+  if ((r = download(s, filter, s->ip.filter, B * IP_FILTER_CAP * 2 * sizeof(double)))) return r;
+  if ((r = download(s, filter_size, s->ip.filter_size, B * sizeof(int)))) return r;
+  if (scalars) {
+    std::vector<double> tmp(3 * B);
+    double *src[3] = {s->ip.filter_theta, s->ip.logsum, s->ip.lamh};
+    for (int k = 0; k < 3; ++k) {
+      if (!src[k]) {
+        std::fill(tmp.begin() + k * B, tmp.begin() + (k + 1) * B, 0.0);
+        continue;
+      }
+      if ((r = download(s, tmp.data() + k * B, src[k], B * sizeof(double)))) return r;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    for (size_t b = 0; b < B; ++b)
+      for (int k = 0; k < 3; ++k) scalars[b * 3 + k] = tmp[k * B + b];
   }
   CU(cudaStreamSynchronize(s->stream));
   return 0;

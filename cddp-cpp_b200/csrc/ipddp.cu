@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
   if (alive && mode == BW_ITERATE && r == 0) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
   int status = CDDP_B200_STATUS_RUNNING;
   bool need = alive, ok = false;
+  int failures = 0;  // backward-pass failures of this iteration (decision trace)
   double dV0 = 0.0, dV1 = 0.0, inf_du = 0.0, inf_pr = 0.0, inf_comp = 0.0, step_norm = 0.0;
 
   while (__any_sync(0xffffffffu, need)) {
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         need = false;
       } else {  // increaseRegularization + limit test (cddp_solver_base.cpp:95-109, cddp_core.cpp:308-326)
         reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+        ++failures;
         if (reg >= c.opt.reg_max_value) {
           status = CDDP_B200_STATUS_REG_LIMIT;
           need = false;
@@ -602,6 +604,7 @@ __global__ void __launch_bounds__(kBwThreads) ip_backward_kernel(Constants c, De
         }
       }
       if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+      trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
     }
   }
 }

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
   if (alive && mode == BW_ITERATE && r == 0) d.iter[b] += 1;
   int status = CDDP_B200_STATUS_RUNNING;
   bool need = alive, ok = false;
+  int failures = 0;  // backward-pass failures of this iteration (decision trace)
   double inf_du = 0.0, inf_pr = 0.0, inf_comp = 0.0, step_norm = 0.0, apm = 1.0, adm = 1.0;
 
   auto issue_sweep = [&](int tt, int x) {
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
         need = false;
       } else {  // regularisation retry (cddp_solver_base.cpp:93-111, cddp_core.cpp:308-326)
         reg = fmin(reg * c.opt.reg_update_factor, c.opt.reg_max_value);
+        ++failures;
         if (reg >= c.opt.reg_max_value) {
           status = CDDP_B200_STATUS_REG_LIMIT;
           need = false;
@@ -690,6 +692,7 @@ __global__ void __launch_bounds__(kTeqThreads) ip_backward_teq_kernel(Constants 
         }
       }
       if (status != CDDP_B200_STATUS_RUNNING) d.status[b] = status;
+      trace_backward(d, b, d.iter[b], failures, status == CDDP_B200_STATUS_OPTIMAL ? 0xff : status == CDDP_B200_STATUS_REG_LIMIT ? 0xfe : 0);
     }
   }
 }

@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(kFwThreads) ip_forward_kernel(Constants c, Dev
   if (!(alive && al == 0)) return;
   d.accepted[b] = first;
   if (mode != FW_ITERATE) return;
+  trace_line_search(d, b, first);
   double reg = d.reg[b];
   int status = CDDP_B200_STATUS_RUNNING;
   const bool no_barrier = ic.nc == 0;

@@ -326,7 +326,7 @@ CDDP_B200_API int cddp_b200_get_first_controls_async(cddp_b200_solver *s, double
  * {objective, step_length_primal, dual_infeasibility, regularization}; lens [B] */
 CDDP_B200_API int cddp_b200_enable_history(cddp_b200_solver *s, int enable);
 CDDP_B200_API int cddp_b200_get_history(cddp_b200_solver *s, double *history, int *lens);
-/* Decision trace (audit / parity instrumentation, no reference counterpart; CLDDP handles).  One int per entry of the
+/* Decision trace (audit / parity instrumentation, no reference counterpart; CLDDP and IPDDP handles).  One int per entry of the
  * main loop of CDDPSolverBase::solve (cddp_solver_base.cpp:74) and instance, [B][cap], cap = max_iterations at enable
  * time: (backward-pass failures of this iteration << 8) | code, code = 1 + index of the accepted alpha
  * (performForwardPass, :248-263), 0 = no alpha accepted (handleForwardPassFailure, :206-218), 0xff = early convergence
@@ -373,6 +373,10 @@ CDDP_B200_API int cddp_b200_ipddp_dual_dim(cddp_b200_solver *s, int *d);
 CDDP_B200_API int cddp_b200_ipddp_get_solution(cddp_b200_solver *s, double *Y, double *S, double *G, double *scalars);
 /* white box: slack/dual gains of the last backward pass, k_y,k_s [B][N][d], K_y,K_s [B][N][d][n]; line-search table
  * [B][num_alphas][4] = accepted?, cost, barrier merit, theta of every alpha of the last forward pass */
+/* white box (parity tests): what IPDDPSolver carries from one iteration to the next besides the trajectories —
+ * Lambda_T_eq_ [B][n] (zeros without a terminal equality), the filter points [B][8][2] (merit, theta) and their count [B]
+ * (ipddp_solver.hpp filter_), scalars [B][3] = {filter theta of the nominal, sum log s of the nominal, Lambda_T . h_T} */
+CDDP_B200_API int cddp_b200_ipddp_get_iteration_state(cddp_b200_solver *s, double *lamT, double *filter, int *filter_size, double *scalars);
 CDDP_B200_API int cddp_b200_ipddp_get_gains(cddp_b200_solver *s, double *ky, double *Ky, double *ks, double *Ks);
 CDDP_B200_API int cddp_b200_ipddp_get_line_search(cddp_b200_solver *s, double *table);
 /* History with interior-point columns: [B][max_iterations+1][9] = objective, merit, alpha_pr, alpha_du, inf_du, inf_pr,

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -2562,6 +2563,167 @@ void ip_update_barrier(IpState &s) { /* updateBarrierParameters(context, true) (
   s.theta = std::max(filter_theta, std::max(s.io->theta_0_floor, 1e-8));
 }
 
+/* ONE entry of the main loop of CDDPSolverBase::solve (cddp_solver_base.cpp:74-170) with the IPDDP hooks, on the solver
+ * state `s`.  follow < 0: the oracle takes its own decisions (this IS the loop body of ipddp_solve_one).  follow >= 0
+ * (test instrumentation, see iterate_once above): a recorded decision ((backward failures << 8) | code) and the recorded
+ * status after the iteration; every branch on a backward-failure / line-search / convergence verdict takes the RECORDED
+ * side while all arithmetic stays the oracle's, and R reports where its own verdict differed and how close to its
+ * threshold the tested quantity was (the line-search margin is the trial's own accept/reject margin).
+ * Returns the decision in *code_out, the status after the iteration in *status_out (ORACLE_RUNNING = goes on). */
+void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int follow, int follow_status, int *code_out,
+                     int *status_out, double *min_margin, oracle_replay_report &R, const std::function<void()> &record) {
+  const oracle_options *o = s.o;
+  const oracle_ipddp_options *io = s.io;
+  const bool no_barrier = s.nc == 0;
+  const bool rec = follow >= 0;
+  const int rcode = rec ? (follow & 0xff) : 0, rfail = rec ? (follow >> 8) : 0;
+  auto note = [&](double mg) {
+    ++R.n_disagree;
+    if (!(mg <= R.max_margin)) R.max_margin = mg;
+  };
+  auto near = [](double a, double b) { return std::fabs(a - b) / std::max(std::max(std::fabs(a), std::fabs(b)), 1e-300); };
+  *status_out = ORACLE_RUNNING;
+  bool backward_ok = false; /* cddp_solver_base.cpp:93-111 */
+  int bw_fail = 0;
+  while (true) {
+    if (rec && bw_fail == rfail && rcode == ORACLE_TRACE_BW_LIMIT) break;
+    backward_ok = ip_backward(s);
+    if (rec) {
+      if (bw_fail < rfail) {
+        if (backward_ok) ++R.n_backward_disagree;
+        backward_ok = false;
+      } else if (!backward_ok) {
+        ++R.n_backward_disagree;
+        R.infeasible = 1;
+        break;
+      }
+    }
+    if (backward_ok) break;
+    ++bw_fail;
+    s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+    if (!rec && s.reg >= o->reg_max_value) break;
+  }
+  if (!backward_ok) {
+    *code_out = (bw_fail << 8) | ORACLE_TRACE_BW_LIMIT;
+    *status_out = ORACLE_REG_LIMIT;
+    return;
+  }
+  { /* checkEarlyConvergence (:925-958) */
+    bool own;
+    double mg;
+    if (no_barrier) {
+      own = s.inf_pr < o->tolerance && s.inf_du < o->tolerance;
+      mg = std::min(near(s.inf_pr, o->tolerance), near(s.inf_du, o->tolerance));
+    } else {
+      const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
+      own = s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol && std::fabs(s.alpha_pr) * s.step_norm < o->tolerance * 10.0;
+      mg = std::min(std::min(near(s.inf_pr, tol), near(s.inf_du, tol)),
+                    std::min(near(s.inf_comp, tol), near(std::fabs(s.alpha_pr) * s.step_norm, o->tolerance * 10.0)));
+    }
+    const bool early = rec ? rcode == ORACLE_TRACE_EARLY_EXIT : own;
+    if (own != early) note(mg);
+    if (early) {
+      record();
+      *code_out = (bw_fail << 8) | ORACLE_TRACE_EARLY_EXIT;
+      *status_out = ORACLE_OPTIMAL;
+      return;
+    }
+  }
+  IpTrial trial, cand;
+  bool fp = false; /* performForwardPass: sequential = first success (cddp_solver_base.cpp:255-263) */
+  int acc = -1;
+  const int racc = rcode - 1;
+  if (!o->enable_parallel) {
+    const int upto = rec ? (racc >= 0 ? racc : na - 1) : na - 1;
+    for (int ai = 0; ai <= upto; ++ai) {
+      ip_forward(s, alphas[ai], trial);
+      *min_margin = std::min(*min_margin, trial.margin);
+      const bool take = rec ? ai == racc : trial.success;
+      if (trial.success != take) note(trial.margin);
+      if (take) {
+        fp = true;
+        acc = ai;
+        break;
+      }
+    }
+  } else { /* enable_parallel: the success with the strictly lowest merit, scanning in alpha order (:264-285) */
+    double best_merit = std::numeric_limits<double>::infinity();
+    int own = -1;
+    for (int ai = 0; ai < na; ++ai) {
+      ip_forward(s, alphas[ai], cand);
+      *min_margin = std::min(*min_margin, cand.margin);
+      if (cand.success && cand.merit < best_merit) {
+        best_merit = cand.merit;
+        own = ai;
+        if (!rec) trial = cand;
+      }
+      if (rec && ai == racc) trial = cand;
+    }
+    acc = rec ? racc : own;
+    fp = acc >= 0;
+    if (rec && own != racc) note(racc >= 0 && own >= 0 ? near(trial.merit, best_merit) : 1.0);
+  }
+  *code_out = (bw_fail << 8) | (fp ? 1 + acc : ORACLE_TRACE_LS_FAILED);
+  if (fp) {
+    const double dJ = s.cost - trial.cost;
+    /* applyForwardPassResult (:1878-1951) */
+    s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
+    s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
+    s.Y = trial.Y; s.S = trial.S; s.G = trial.G; s.lamT = trial.lamT;
+    s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
+    s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
+    ip_update_barrier(s);
+    record();
+    s.reg = std::max(s.reg / o->reg_update_factor, o->reg_min_value);
+    /* checkConvergence (:1953-2025) */
+    int own = ORACLE_RUNNING;
+    double mg = 1.0;
+    if (no_barrier) {
+      mg = std::min(near(s.inf_pr, o->tolerance), near(s.inf_du, o->tolerance));
+      if (s.inf_pr < o->tolerance && s.inf_du < o->tolerance) {
+        own = ORACLE_OPTIMAL;
+      } else if (o->acceptable_tolerance > 0.0) {
+        const double sq = std::sqrt(o->acceptable_tolerance);
+        bool a = s.inf_pr < sq && s.inf_du < sq && iter > 50;
+        if (dJ > 0.0) a = a || (dJ < o->acceptable_tolerance && iter > 50 && s.inf_pr < sq && s.inf_du < sq);
+        if (a) own = ORACLE_ACCEPTABLE;
+        mg = std::min(mg, std::min(near(s.inf_pr, sq), near(s.inf_du, sq)));
+      }
+    } else {
+      const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
+      mg = std::min(std::min(near(s.inf_pr, tol), near(s.inf_du, tol)), std::min(near(s.inf_comp, tol), near(s.step_norm, o->tolerance * 10.0)));
+      if (s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol && s.step_norm < o->tolerance * 10.0) {
+        own = ORACLE_OPTIMAL;
+      } else if (o->acceptable_tolerance > 0.0) {
+        const double at = std::sqrt(o->acceptable_tolerance);
+        const double bat = std::max(io->mu_min_value * 100.0, o->tolerance / 10.0);
+        const bool kkt = s.inf_pr < at && s.inf_du < at && s.inf_comp < at;
+        const bool done = s.mu <= bat;
+        bool a = kkt && done && iter > 10 && std::fabs(dJ) < o->acceptable_tolerance;
+        a = a || (kkt && done && iter >= 1 && s.step_norm < o->tolerance * 10.0 && s.inf_pr < 1e-4);
+        if (a) own = ORACLE_ACCEPTABLE;
+        mg = std::min(mg, std::min(std::min(near(s.inf_pr, at), near(s.inf_du, at)), std::min(near(s.inf_comp, at), near(s.mu, bat))));
+        mg = std::min(mg, std::min(near(std::fabs(dJ), o->acceptable_tolerance), near(s.inf_pr, 1e-4)));
+      }
+    }
+    const int taken = rec ? ((follow_status == ORACLE_OPTIMAL || follow_status == ORACLE_ACCEPTABLE) ? follow_status : ORACLE_RUNNING) : own;
+    if (taken != own) note(mg);
+    *status_out = taken;
+  } else { /* handleForwardPassFailure (:2037-2082) */
+    s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
+    if (!no_barrier && s.teq) s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value); /* :2047-2051 */
+    if (s.reg >= o->reg_max_value) {
+      const double base = std::sqrt(std::max(o->acceptable_tolerance, o->tolerance));
+      const double at = no_barrier ? base : std::max(base, io->barrier_tol_mult * s.mu);
+      const bool a = o->acceptable_tolerance > 0.0 && s.inf_pr < at && s.inf_du < at && (no_barrier || s.inf_comp < at);
+      const int own = a ? ORACLE_ACCEPTABLE : ORACLE_REG_LIMIT;
+      const int taken = rec && (follow_status == ORACLE_ACCEPTABLE || follow_status == ORACLE_REG_LIMIT) ? follow_status : own;
+      if (taken != own) note(std::min(std::min(near(s.inf_pr, at), near(s.inf_du, at)), near(s.inf_comp, at)));
+      *status_out = taken;
+    }
+  }
+}
+
 /* CDDP::solve("IPDDP"): CDDPSolverBase::solve (cddp_solver_base.cpp:29-186) with the IPDDP hooks */
 void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
                      const oracle_constraint *cs, int nc, const double *x0, const double *xref, const double *ref_traj,
@@ -2575,7 +2737,7 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
   const int na = build_alphas(o, alphas);
   ip_initialize(s, U);
   int hl = 0;
-  auto record = [&]() { /* recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp :2084-2088) */
+  std::function<void()> record = [&]() { /* recordIterationHistory (cddp_solver_base.cpp:220-232 + ipddp :2084-2088) */
     if (!history) return;
     double *h = history + (size_t)hl * ORACLE_IPDDP_HISTORY_COLS;
     h[0] = s.cost; h[1] = s.merit; h[2] = s.alpha_pr; h[3] = s.alpha_du; h[4] = s.inf_du;
@@ -2584,118 +2746,17 @@ void ipddp_solve_one(const oracle_problem *p, const oracle_options *o, const ora
   };
   record();
   int iter = 0, status = ORACLE_MAX_ITERATIONS;
-  bool converged = false;
-  const bool no_barrier = nc == 0;
-  IpTrial trial;
   double min_margin = 1.0;
+  oracle_replay_report R;
+  std::memset(&R, 0, sizeof(R));
   while (iter < o->max_iterations) {
     ++iter;
-    bool backward_ok = false;
-    while (!backward_ok) {
-      backward_ok = ip_backward(s);
-      if (!backward_ok) {
-        s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
-        if (s.reg >= o->reg_max_value) {
-          status = ORACLE_REG_LIMIT;
-          break;
-        }
-      }
+    int code = 0, st = ORACLE_RUNNING;
+    ip_iterate_once(s, iter, alphas, na, -1, ORACLE_RUNNING, &code, &st, &min_margin, R, record);
+    if (st != ORACLE_RUNNING) {
+      status = st;
+      break;
     }
-    if (!backward_ok) break;
-    { /* checkEarlyConvergence (:925-958) */
-      bool early;
-      if (no_barrier) {
-        early = s.inf_pr < o->tolerance && s.inf_du < o->tolerance;
-      } else {
-        const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
-        early = s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol &&
-                std::fabs(s.alpha_pr) * s.step_norm < o->tolerance * 10.0;
-      }
-      if (early) {
-        status = ORACLE_OPTIMAL;
-        converged = true;
-        record();
-        break;
-      }
-    }
-    bool fp = false; /* performForwardPass: sequential = first success (cddp_solver_base.cpp:255-263) */
-    if (!o->enable_parallel) {
-      for (int ai = 0; ai < na; ++ai) {
-        ip_forward(s, alphas[ai], trial);
-        min_margin = std::min(min_margin, trial.margin);
-        if (trial.success) {
-          fp = true;
-          break;
-        }
-      }
-    } else { /* enable_parallel: the success with the strictly lowest merit, scanning in alpha order (:264-285) */
-      IpTrial cand;
-      double best_merit = std::numeric_limits<double>::infinity();
-      for (int ai = 0; ai < na; ++ai) {
-        ip_forward(s, alphas[ai], cand);
-        min_margin = std::min(min_margin, cand.margin);
-        if (cand.success && cand.merit < best_merit) {
-          best_merit = cand.merit;
-          trial = cand;
-          fp = true;
-        }
-      }
-    }
-    if (fp) {
-      const double dJ = s.cost - trial.cost;
-      /* applyForwardPassResult (:1878-1951) */
-      s.X = trial.X; s.U = trial.U; s.cost = trial.cost; s.merit = trial.merit;
-      s.alpha_pr = trial.alpha_pr; s.alpha_du = trial.alpha_du;
-      s.Y = trial.Y; s.S = trial.S; s.G = trial.G; s.lamT = trial.lamT;
-      s.inf_pr = trial.inf_pr; s.inf_comp = trial.inf_comp;
-      s.phi = trial.merit; s.filter_theta = trial.theta; s.theta = trial.theta;
-      ip_update_barrier(s);
-      record();
-      s.reg = std::max(s.reg / o->reg_update_factor, o->reg_min_value);
-      /* checkConvergence (:1953-2025) */
-      if (no_barrier) {
-        if (s.inf_pr < o->tolerance && s.inf_du < o->tolerance) {
-          status = ORACLE_OPTIMAL;
-          converged = true;
-        } else if (o->acceptable_tolerance > 0.0) {
-          const double sq = std::sqrt(o->acceptable_tolerance);
-          bool acc = s.inf_pr < sq && s.inf_du < sq && iter > 50;
-          if (dJ > 0.0) acc = acc || (dJ < o->acceptable_tolerance && iter > 50 && s.inf_pr < sq && s.inf_du < sq);
-          if (acc) {
-            status = ORACLE_ACCEPTABLE;
-            converged = true;
-          }
-        }
-      } else {
-        const double tol = std::max(o->tolerance, io->barrier_tol_mult * s.mu);
-        if (s.inf_pr < tol && s.inf_du < tol && s.inf_comp < tol && s.step_norm < o->tolerance * 10.0) {
-          status = ORACLE_OPTIMAL;
-          converged = true;
-        } else if (o->acceptable_tolerance > 0.0) {
-          const double at = std::sqrt(o->acceptable_tolerance);
-          const double bat = std::max(io->mu_min_value * 100.0, o->tolerance / 10.0);
-          const bool kkt = s.inf_pr < at && s.inf_du < at && s.inf_comp < at;
-          const bool done = s.mu <= bat;
-          bool acc = kkt && done && iter > 10 && std::fabs(dJ) < o->acceptable_tolerance;
-          acc = acc || (kkt && done && iter >= 1 && s.step_norm < o->tolerance * 10.0 && s.inf_pr < 1e-4);
-          if (acc) {
-            status = ORACLE_ACCEPTABLE;
-            converged = true;
-          }
-        }
-      }
-    } else { /* handleForwardPassFailure (:2037-2082) */
-      s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
-      if (!no_barrier && s.teq) s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value); /* :2047-2051 */
-      if (s.reg >= o->reg_max_value) {
-        const double base = std::sqrt(std::max(o->acceptable_tolerance, o->tolerance));
-        const double at = no_barrier ? base : std::max(base, io->barrier_tol_mult * s.mu);
-        const bool acc = o->acceptable_tolerance > 0.0 && s.inf_pr < at && s.inf_du < at && (no_barrier || s.inf_comp < at);
-        status = acc ? ORACLE_ACCEPTABLE : ORACLE_REG_LIMIT;
-        break;
-      }
-    }
-    if (converged) break;
   }
   std::memcpy(X, s.X.data(), sizeof(double) * s.X.size());
   std::memcpy(U, s.U.data(), sizeof(double) * s.U.size());
@@ -3037,6 +3098,80 @@ void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const 
     scalars[10] = clampd(apm, 0.0, 1.0); scalars[11] = clampd(adm, 0.0, 1.0); scalars[12] = s.filter_theta;
     scalars[13] = s.theta; scalars[14] = (double)s.filter.size(); scalars[15] = ok ? 1.0 : 0.0;
   }
+}
+
+/* ONE IPDDP main-loop entry per instance from a caller-supplied solver state (lock-step parity tests).  In / out, per
+ * instance: X [N+1][n], U [N][m], Y, S, G [N][d], lamT [n], filter [8][2] (merit, theta) + filter_size, scalars [12] =
+ * {mu, cost, merit, filter_theta, inf_pr, inf_comp, reg, alpha_pr, alpha_du, step_norm, inf_du, iteration index (1-based, in)}.
+ * follow / follow_status == NULL: own decisions. */
+void oracle_ipddp_iterate_batch(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                                const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0, const double *xref,
+                                const double *ref_traj, double *X, double *U, double *Y, double *S, double *G, double *lamT,
+                                double *filter, int *filter_size, double *scalars, const int *follow, const int *follow_status,
+                                int *code, int *status, oracle_replay_report *rep) {
+  const int n = p->n, m = p->m, N = p->horizon, d = total_dual_dim(p, cs, nc);
+  double alphas[ORACLE_MAX_ALPHAS];
+  const int na = build_alphas(o, alphas);
+  auto work = [&](int lo, int hi) {
+    for (int b = lo; b < hi; ++b) {
+      IpState s;
+      s.p = p; s.o = o; s.io = io; s.cs = cs; s.nc = nc;
+      s.n = n; s.m = m; s.N = N; s.d = d;
+      s.x0 = x0 + (size_t)b * n; s.xref = xref + (size_t)b * n;
+      s.ref_traj = ref_traj ? ref_traj + (size_t)b * (N + 1) * n : nullptr;
+      ip_initialize(s, U + (size_t)b * N * m); /* sizes every array and sets the flags; the state proper is overwritten below */
+      double *sc = scalars + (size_t)b * 12;
+      s.X.assign(X + (size_t)b * (N + 1) * n, X + (size_t)(b + 1) * (N + 1) * n);
+      s.U.assign(U + (size_t)b * N * m, U + (size_t)(b + 1) * N * m);
+      if (d) {
+        s.Y.assign(Y + (size_t)b * N * d, Y + (size_t)(b + 1) * N * d);
+        s.S.assign(S + (size_t)b * N * d, S + (size_t)(b + 1) * N * d);
+        s.G.assign(G + (size_t)b * N * d, G + (size_t)(b + 1) * N * d);
+      }
+      if (s.teq) s.lamT.assign(lamT + (size_t)b * n, lamT + (size_t)(b + 1) * n);
+      s.filter.clear();
+      for (int k = 0; k < filter_size[b]; ++k) {
+        FilterPt fpnt;
+        fpnt.merit = filter[((size_t)b * 8 + k) * 2];
+        fpnt.theta = filter[((size_t)b * 8 + k) * 2 + 1];
+        s.filter.push_back(fpnt);
+      }
+      s.mu = sc[0]; s.cost = sc[1]; s.merit = sc[2]; s.phi = sc[2]; s.filter_theta = sc[3];
+      s.theta = std::max(s.filter_theta, std::max(io->theta_0_floor, 1e-8));
+      s.inf_pr = sc[4]; s.inf_comp = sc[5]; s.reg = sc[6]; s.alpha_pr = sc[7]; s.alpha_du = sc[8]; s.step_norm = sc[9]; s.inf_du = sc[10];
+      const int iter = (int)sc[11];
+      oracle_replay_report R;
+      std::memset(&R, 0, sizeof(R));
+      double mm = 1.0;
+      std::function<void()> norecord = []() {};
+      ip_iterate_once(s, iter, alphas, na, follow ? follow[b] : -1, follow_status ? follow_status[b] : ORACLE_RUNNING, &code[b], &status[b],
+                      &mm, R, norecord);
+      std::memcpy(X + (size_t)b * (N + 1) * n, s.X.data(), sizeof(double) * (N + 1) * n);
+      std::memcpy(U + (size_t)b * N * m, s.U.data(), sizeof(double) * N * m);
+      if (d) {
+        std::memcpy(Y + (size_t)b * N * d, s.Y.data(), sizeof(double) * N * d);
+        std::memcpy(S + (size_t)b * N * d, s.S.data(), sizeof(double) * N * d);
+        std::memcpy(G + (size_t)b * N * d, s.G.data(), sizeof(double) * N * d);
+      }
+      if (s.teq) std::memcpy(lamT + (size_t)b * n, s.lamT.data(), sizeof(double) * n);
+      filter_size[b] = (int)s.filter.size();
+      for (int k = 0; k < (int)s.filter.size() && k < 8; ++k) {
+        filter[((size_t)b * 8 + k) * 2] = s.filter[k].merit;
+        filter[((size_t)b * 8 + k) * 2 + 1] = s.filter[k].theta;
+      }
+      sc[0] = s.mu; sc[1] = s.cost; sc[2] = s.merit; sc[3] = s.filter_theta; sc[4] = s.inf_pr; sc[5] = s.inf_comp; sc[6] = s.reg;
+      sc[7] = s.alpha_pr; sc[8] = s.alpha_du; sc[9] = s.step_norm; sc[10] = s.inf_du;
+      if (rep) rep[b] = R;
+    }
+  };
+  const int nt = std::max(1, std::min(nthreads, batch));
+  std::vector<std::thread> th;
+  const int per = (batch + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int lo = t * per, hi = std::min(batch, (t + 1) * per);
+    if (lo < hi) th.emplace_back(work, lo, hi);
+  }
+  for (auto &t : th) t.join();
 }
 
 /* profiling aid (single-threaded use): enable/reset and read the BoxQP histograms */

@@ -271,6 +271,13 @@ void oracle_ipddp_solve_batch(const oracle_problem *p, const oracle_options *o, 
 /* white-box single steps for per-step parity: state in/out through flat arrays.
  * oracle_ipddp_step runs initialize + `iters` full iterations and then ONE backward pass, returning every
  * intermediate the CUDA path exposes. */
+/* ONE IPDDP main-loop entry per instance from a caller-supplied solver state (see cddp_oracle.cpp); follow / follow_status
+ * as for oracle_iterate_batch. */
+void oracle_ipddp_iterate_batch(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
+                                const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0, const double *xref,
+                                const double *ref_traj, double *X, double *U, double *Y, double *S, double *G, double *lamT,
+                                double *filter, int *filter_size, double *scalars, const int *follow, const int *follow_status,
+                                int *code, int *status, oracle_replay_report *rep);
 void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
                         const oracle_constraint *cs, int nc, const double *x0, const double *xref,
                         const double *ref_traj, const double *U0, int iters, double *X, double *U, double *Y, double *S,

@@ -479,6 +479,41 @@ def ipddp_solve_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_tra
                 status=f("status", np.int32))
 
 
+IP_STATE_SCALARS = ("mu", "cost", "merit", "filter_theta", "inf_pr", "inf_comp", "reg", "alpha_pr", "alpha_du", "step_norm",
+                    "inf_du", "iter")
+
+
+def ipddp_iterate_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, state, ref_traj=None, nthreads=1, follow=None,
+                        follow_status=None):
+    """oracle_ipddp_iterate_batch: ONE IPDDP main-loop entry per instance from the solver state `state` =
+    dict(X, U, Y, S, G, lamT, filter [B][8][2], filter_size [B], + the IP_STATE_SCALARS as [B] arrays; "iter" = the 1-based
+    index of the iteration about to run).  Arrays are copied; the state after the iteration comes back in the same form
+    plus code / status / the disagreement report."""
+    x0, xref = _f64(x0), _f64(xref)
+    B = x0.shape[0]
+    d = cset.dual_dim(P.n, P.m)
+    X, U = _f64(state["X"]).copy(), _f64(state["U"]).copy()
+    Y, S, G = (_f64(state[k]).copy().reshape(B, P.N, d) if d else np.zeros((B, P.N, 1)) for k in ("Y", "S", "G"))
+    lamT = _f64(state["lamT"]).copy() if state.get("lamT") is not None else np.zeros((B, P.n))
+    filt = _f64(state["filter"]).copy()
+    fsz = np.ascontiguousarray(state["filter_size"], dtype=np.int32).copy()
+    sc = np.ascontiguousarray(np.stack([np.asarray(state[k], dtype=np.float64) for k in IP_STATE_SCALARS], axis=1))
+    rt = _f64(ref_traj) if ref_traj is not None else None
+    code, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    rep = (ReplayReport * B)()
+    fo = None if follow is None else np.ascontiguousarray(follow, dtype=np.int32)
+    fs = None if follow_status is None else np.ascontiguousarray(follow_status, dtype=np.int32)
+    load().oracle_ipddp_iterate_batch(P.ref, C.byref(opts), C.byref(iopts), cset.array, cset.nc, B, int(nthreads), _p(x0), _p(xref),
+                                      _p(rt), _p(X), _p(U), _p(Y), _p(S), _p(G), _p(lamT), _p(filt), _p(fsz), _p(sc), _p(fo), _p(fs),
+                                      _p(code), _p(status), rep)
+    out = dict(X=X, U=U, Y=Y[:, :, :d], S=S[:, :, :d], G=G[:, :, :d], lamT=lamT, filter=filt, filter_size=fsz, code=code, status=status,
+               n_disagree=np.array([r.n_disagree for r in rep]), n_backward_disagree=np.array([r.n_backward_disagree for r in rep]),
+               infeasible=np.array([r.infeasible for r in rep]), max_margin=np.array([r.max_margin for r in rep]))
+    for i, k in enumerate(IP_STATE_SCALARS):
+        out[k] = sc[:, i].copy()
+    return out
+
+
 def ipddp_probe(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, iters, ref_traj=None):
     """initialize + `iters` full iterations + ONE backward pass; returns every intermediate (white box)."""
     x0, xref, U0 = _f64(x0), _f64(xref), _f64(U0)

@@ -138,3 +138,72 @@ def test_whole_solve_decision_replay_every_instance(cddp, ob, problems, name, B)
     # and 242 of 256 cartpole instances within 1e-6).  The 100 % statement is the lock-step test
     # above; here the bulk must agree and the count is reported.
     assert np.nanmean(relc < COST_TOL) >= 0.9, f"{name}: only {(relc < COST_TOL).sum()}/{B} replayed instances within 1e-6"
+
+
+def ip_snapshot(s):
+    r = s.get_solution(want_K=False)
+    r.update(s.get_ipddp_solution())
+    r.update(s.get_iteration_state())
+    return r
+
+
+@pytest.mark.parametrize("name,B", [("unicycle_obstacle_teq", 2048), ("unicycle_obstacle", 2048), ("pendulum_ipddp", 64)])
+def test_ipddp_lockstep_every_instance_every_iteration(cddp, ob, problems, name, B):
+    """BASELINE config #4 (unicycle obstacle avoidance, IPDDP, path inequalities + terminal equality, N = 200) at its full
+    batch, in lock step: before every batched iteration the CUDA path's IPDDP state — trajectories, duals, slacks,
+    constraint values, terminal multiplier, barrier parameter, merit, filter, regularisation, step lengths — is downloaded,
+    the oracle runs ONE main-loop entry of IPDDPSolver from it on EVERY running instance following the recorded decision
+    (accepted alpha, backward retries, convergence exit), and the two states must agree afterwards.  Decisions on which
+    the oracle's own verdict differs must be within roundoff of their threshold — this includes the fraction-to-boundary
+    test at t = 0 that the reference itself decides by roundoff."""
+    cfg = problems.make_config(name, batch=B)
+    opts = dict(cfg["options"])
+    s = cddp.BatchedIPDDP(cfg["spec"], cddp.default_options(**opts), cddp.default_ipddp_options(**cfg.get("ipddp_options", {})),
+                          cfg["constraints"], B)
+    s.set_instances(cfg["x0"], cfg["xref"], None, cfg["U0"], cfg["ref_traj"])
+    s.enable_trace(True)
+    s.initialize()
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
+    oi, cs = ob.make_ipddp_options(**cfg.get("ipddp_options", {})), ob.ConstraintSet(cfg["constraints"])
+    nt = ob.hardware_threads()
+    worst = dict(cost=0.0, X=0.0, U=0.0, S=0.0, Y=0.0, mu=0.0, merit=0.0)
+    n_checked = n_disagree = 0
+    max_margin = 0.0
+    pre = ip_snapshot(s)
+    for it in range(opts["max_iterations"]):
+        run = np.flatnonzero(pre["status"] == 0)
+        if run.size == 0:
+            break
+        s.iterate(1)
+        post = ip_snapshot(s)
+        code = s.get_trace()[run, it]
+        state = {k: pre[k][run] for k in ("X", "U", "Y", "S", "G", "lamT", "filter", "filter_size", "mu", "cost", "merit", "filter_theta",
+                                          "inf_pr", "inf_comp", "reg", "alpha_du", "step_norm", "inf_du")}
+        state["alpha_pr"] = pre["alpha"][run]
+        state["iter"] = np.full(run.size, float(it + 1))
+        o = ob.ipddp_iterate_batch(P, oo, oi, cs, cfg["x0"][run], cfg["xref"][run], state, ref_traj=sub(cfg["ref_traj"], run), nthreads=nt,
+                                   follow=code, follow_status=post["status"][run])
+        assert (o["infeasible"] == 0).all(), f"{name} it {it}: the oracle's backward pass failed where the CUDA path's succeeded"
+        assert (o["n_backward_disagree"] == 0).all(), f"{name} it {it}: backward success / failure verdicts differ"
+        n_checked += run.size
+        n_disagree += int(o["n_disagree"].sum())
+        if o["n_disagree"].any():
+            max_margin = max(max_margin, float(o["max_margin"][o["n_disagree"] > 0].max()))
+        for key, tol in (("cost", 1e-8), ("mu", 1e-12), ("merit", 1e-7)):
+            e = np.abs(post[key][run] - o[key]) / np.maximum(np.abs(o[key]), 1e-300)
+            worst[key] = max(worst[key], float(e.max()))
+            assert e.max() < tol, f"{name} it {it}: {key} differs on instance {run[e.argmax()]}: {e.max():.2e}"
+        np.testing.assert_array_equal(post["reg"][run], o["reg"])
+        np.testing.assert_array_equal(post["alpha"][run], o["alpha_pr"])
+        np.testing.assert_array_equal(post["filter_size"][run], o["filter_size"])
+        for key, tol in (("X", 1e-7), ("U", 1e-7), ("S", 1e-6), ("Y", 1e-6)):
+            if post[key][run].size:
+                ee = inst_rel_err(post[key][run], o[key])
+                worst[key] = max(worst[key], float(ee.max()))
+                assert ee.max() < tol, f"{name} it {it} instance {run[ee.argmax()]}: {key} differs by {ee.max():.2e}"
+        pre = post
+    assert max_margin < 1e-7, f"{name}: a decision differed {max_margin:.2e} away from its threshold"
+    print(f"\n[IPDDP lock-step {name} B={B}] instance-iterations checked {n_checked} (100 % of the running instances, every "
+          f"iteration); decisions where the oracle's own verdict differed: {n_disagree} (max margin {max_margin:.2e}); worst rel err "
+          + " ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    s.close()
