@@ -2371,12 +2371,17 @@ struct IpTrial {
 };
 
 /* IPDDPSolver::forwardPass (:1571-1876) */
-void ip_forward(const IpState &s, double alpha, IpTrial &r) {
+/* force (decision-following instrumentation): a fraction-to-boundary violation is noted (own verdict = reject, margin =
+ * that violation's) but the trial is still evaluated to the end, so that a caller following a RECORDED acceptance gets the
+ * complete candidate; without it the function returns at the first violation as the reference does (:1623-1630). */
+void ip_forward(const IpState &s, double alpha, IpTrial &r, bool force = false) {
   const int n = s.n, m = s.m, N = s.N, d = s.d;
   const oracle_problem *p = s.p;
   r.success = false;
   r.margin = 1.0;
   double feas_margin = 1.0;
+  bool own_reject = false;
+  double reject_margin = 1.0;
   /* computeMaxStepSizes (:2939-2988) */
   const double tau_b = std::max(s.io->min_fraction_to_boundary, 1.0 - s.mu);
   double apm = 1.0, adm = 1.0;
@@ -2433,7 +2438,10 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
           /* rejected: the decision is as robust as this violation (the scan below looks for a clearer one) */
           double best = std::max(sn[i] < smin ? ms : 0.0, yn[i] < ymin ? my : 0.0);
           r.margin = best;
-          return;
+          if (!force) return;
+          if (!own_reject) reject_margin = best;
+          own_reject = true;
+          continue;
         }
         feas_margin = std::min(feas_margin, std::min(ms, my));
       }
@@ -2506,8 +2514,9 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r) {
     }
   }
   r.margin = accept ? std::min(feas_margin, acc_margin) : acc_margin;
-  if (!accept) return;
-  r.success = true;
+  if (own_reject) r.margin = reject_margin;
+  if (!accept && !force) return;
+  r.success = accept && !own_reject;
   r.cost = cost_new;
   r.merit = phi_new;
   r.theta = theta_new;
@@ -2636,7 +2645,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
   if (!o->enable_parallel) {
     const int upto = rec ? (racc >= 0 ? racc : na - 1) : na - 1;
     for (int ai = 0; ai <= upto; ++ai) {
-      ip_forward(s, alphas[ai], trial);
+      ip_forward(s, alphas[ai], trial, rec && ai == racc);
       *min_margin = std::min(*min_margin, trial.margin);
       const bool take = rec ? ai == racc : trial.success;
       if (trial.success != take) note(trial.margin);
@@ -2650,7 +2659,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
     double best_merit = std::numeric_limits<double>::infinity();
     int own = -1;
     for (int ai = 0; ai < na; ++ai) {
-      ip_forward(s, alphas[ai], cand);
+      ip_forward(s, alphas[ai], cand, rec && ai == racc);
       *min_margin = std::min(*min_margin, cand.margin);
       if (cand.success && cand.merit < best_merit) {
         best_merit = cand.merit;
