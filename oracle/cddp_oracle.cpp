@@ -2579,6 +2579,8 @@ void ip_update_barrier(IpState &s) { /* updateBarrierParameters(context, true) (
  * side while all arithmetic stays the oracle's, and R reports where its own verdict differed and how close to its
  * threshold the tested quantity was (the line-search margin is the trial's own accept/reject margin).
  * Returns the decision in *code_out, the status after the iteration in *status_out (ORACLE_RUNNING = goes on). */
+thread_local double *g_ip_trial_table = nullptr; /* debug: [na][6] success, cost, merit, theta, margin, alpha_pr of every evaluated candidate */
+
 void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int follow, int follow_status, int *code_out,
                      int *status_out, double *min_margin, oracle_replay_report &R, const std::function<void()> &record) {
   const oracle_options *o = s.o;
@@ -2586,9 +2588,12 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
   const bool no_barrier = s.nc == 0;
   const bool rec = follow >= 0;
   const int rcode = rec ? (follow & 0xff) : 0, rfail = rec ? (follow >> 8) : 0;
-  auto note = [&](double mg) {
+  auto note = [&](double mg, int kind = 0) { /* kind (reserved): 1 early exit, 2 line search, 3 convergence, 4 failure status */
     ++R.n_disagree;
-    if (!(mg <= R.max_margin)) R.max_margin = mg;
+    if (!(mg <= R.max_margin)) {
+      R.max_margin = mg;
+      R.reserved = kind;
+    }
   };
   auto near = [](double a, double b) { return std::fabs(a - b) / std::max(std::max(std::fabs(a), std::fabs(b)), 1e-300); };
   *status_out = ORACLE_RUNNING;
@@ -2630,7 +2635,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
                     std::min(near(s.inf_comp, tol), near(std::fabs(s.alpha_pr) * s.step_norm, o->tolerance * 10.0)));
     }
     const bool early = rec ? rcode == ORACLE_TRACE_EARLY_EXIT : own;
-    if (own != early) note(mg);
+    if (own != early) note(mg, 1);
     if (early) {
       record();
       *code_out = (bw_fail << 8) | ORACLE_TRACE_EARLY_EXIT;
@@ -2647,8 +2652,13 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
     for (int ai = 0; ai <= upto; ++ai) {
       ip_forward(s, alphas[ai], trial, rec && ai == racc);
       *min_margin = std::min(*min_margin, trial.margin);
+      if (g_ip_trial_table) {
+        double *row = g_ip_trial_table + (size_t)ai * 6;
+        row[0] = trial.success ? 1.0 : 0.0; row[1] = trial.cost; row[2] = trial.merit; row[3] = trial.theta; row[4] = trial.margin;
+        row[5] = trial.alpha_pr;
+      }
       const bool take = rec ? ai == racc : trial.success;
-      if (trial.success != take) note(trial.margin);
+      if (trial.success != take) note(trial.margin, 2 + 16 * ai);
       if (take) {
         fp = true;
         acc = ai;
@@ -2670,7 +2680,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
     }
     acc = rec ? racc : own;
     fp = acc >= 0;
-    if (rec && own != racc) note(racc >= 0 && own >= 0 ? near(trial.merit, best_merit) : 1.0);
+    if (rec && own != racc) note(racc >= 0 && own >= 0 ? near(trial.merit, best_merit) : 1.0, 2);
   }
   *code_out = (bw_fail << 8) | (fp ? 1 + acc : ORACLE_TRACE_LS_FAILED);
   if (fp) {
@@ -2716,7 +2726,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
       }
     }
     const int taken = rec ? ((follow_status == ORACLE_OPTIMAL || follow_status == ORACLE_ACCEPTABLE) ? follow_status : ORACLE_RUNNING) : own;
-    if (taken != own) note(mg);
+    if (taken != own) note(mg, 3);
     *status_out = taken;
   } else { /* handleForwardPassFailure (:2037-2082) */
     s.reg = std::min(s.reg * o->reg_update_factor, o->reg_max_value);
@@ -2727,7 +2737,7 @@ void ip_iterate_once(IpState &s, int iter, const double *alphas, int na, int fol
       const bool a = o->acceptable_tolerance > 0.0 && s.inf_pr < at && s.inf_du < at && (no_barrier || s.inf_comp < at);
       const int own = a ? ORACLE_ACCEPTABLE : ORACLE_REG_LIMIT;
       const int taken = rec && (follow_status == ORACLE_ACCEPTABLE || follow_status == ORACLE_REG_LIMIT) ? follow_status : own;
-      if (taken != own) note(std::min(std::min(near(s.inf_pr, at), near(s.inf_du, at)), near(s.inf_comp, at)));
+      if (taken != own) note(std::min(std::min(near(s.inf_pr, at), near(s.inf_du, at)), near(s.inf_comp, at)), 4);
       *status_out = taken;
     }
   }
@@ -3117,7 +3127,7 @@ void oracle_ipddp_iterate_batch(const oracle_problem *p, const oracle_options *o
                                 const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0, const double *xref,
                                 const double *ref_traj, double *X, double *U, double *Y, double *S, double *G, double *lamT,
                                 double *filter, int *filter_size, double *scalars, const int *follow, const int *follow_status,
-                                int *code, int *status, oracle_replay_report *rep) {
+                                int *code, int *status, oracle_replay_report *rep, double *trial_table) {
   const int n = p->n, m = p->m, N = p->horizon, d = total_dual_dim(p, cs, nc);
   double alphas[ORACLE_MAX_ALPHAS];
   const int na = build_alphas(o, alphas);
@@ -3153,8 +3163,10 @@ void oracle_ipddp_iterate_batch(const oracle_problem *p, const oracle_options *o
       std::memset(&R, 0, sizeof(R));
       double mm = 1.0;
       std::function<void()> norecord = []() {};
+      g_ip_trial_table = trial_table ? trial_table + (size_t)b * ORACLE_MAX_ALPHAS * 6 : nullptr;
       ip_iterate_once(s, iter, alphas, na, follow ? follow[b] : -1, follow_status ? follow_status[b] : ORACLE_RUNNING, &code[b], &status[b],
                       &mm, R, norecord);
+      g_ip_trial_table = nullptr;
       std::memcpy(X + (size_t)b * (N + 1) * n, s.X.data(), sizeof(double) * (N + 1) * n);
       std::memcpy(U + (size_t)b * N * m, s.U.data(), sizeof(double) * N * m);
       if (d) {

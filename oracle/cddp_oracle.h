@@ -277,7 +277,7 @@ void oracle_ipddp_iterate_batch(const oracle_problem *p, const oracle_options *o
                                 const oracle_constraint *cs, int nc, int batch, int nthreads, const double *x0, const double *xref,
                                 const double *ref_traj, double *X, double *U, double *Y, double *S, double *G, double *lamT,
                                 double *filter, int *filter_size, double *scalars, const int *follow, const int *follow_status,
-                                int *code, int *status, oracle_replay_report *rep);
+                                int *code, int *status, oracle_replay_report *rep, double *trial_table /* [B][ORACLE_MAX_ALPHAS][6] or NULL */);
 void oracle_ipddp_probe(const oracle_problem *p, const oracle_options *o, const oracle_ipddp_options *io,
                         const oracle_constraint *cs, int nc, const double *x0, const double *xref,
                         const double *ref_traj, const double *U0, int iters, double *X, double *U, double *Y, double *S,

@@ -479,6 +479,7 @@ def ipddp_solve_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, U0, ref_tra
                 status=f("status", np.int32))
 
 
+MAX_ALPHAS = 64
 IP_STATE_SCALARS = ("mu", "cost", "merit", "filter_theta", "inf_pr", "inf_comp", "reg", "alpha_pr", "alpha_du", "step_norm",
                     "inf_du", "iter")
 
@@ -503,12 +504,14 @@ def ipddp_iterate_batch(P, opts, iopts, cset: ConstraintSet, x0, xref, state, re
     rep = (ReplayReport * B)()
     fo = None if follow is None else np.ascontiguousarray(follow, dtype=np.int32)
     fs = None if follow_status is None else np.ascontiguousarray(follow_status, dtype=np.int32)
+    table = np.full((B, MAX_ALPHAS, 6), np.nan)
     load().oracle_ipddp_iterate_batch(P.ref, C.byref(opts), C.byref(iopts), cset.array, cset.nc, B, int(nthreads), _p(x0), _p(xref),
                                       _p(rt), _p(X), _p(U), _p(Y), _p(S), _p(G), _p(lamT), _p(filt), _p(fsz), _p(sc), _p(fo), _p(fs),
-                                      _p(code), _p(status), rep)
+                                      _p(code), _p(status), rep, _p(table))
     out = dict(X=X, U=U, Y=Y[:, :, :d], S=S[:, :, :d], G=G[:, :, :d], lamT=lamT, filter=filt, filter_size=fsz, code=code, status=status,
                n_disagree=np.array([r.n_disagree for r in rep]), n_backward_disagree=np.array([r.n_backward_disagree for r in rep]),
-               infeasible=np.array([r.infeasible for r in rep]), max_margin=np.array([r.max_margin for r in rep]))
+               infeasible=np.array([r.infeasible for r in rep]), max_margin=np.array([r.max_margin for r in rep]),
+               kind=np.array([r.reserved for r in rep]), trials=table)
     for i, k in enumerate(IP_STATE_SCALARS):
         out[k] = sc[:, i].copy()
     return out
