@@ -2418,7 +2418,7 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r, bool force = false) 
     for (int i = 0; i < n; ++i) dx[i] = xt[i] - s.X[(size_t)t * n + i];
     for (int c = 0, o = 0; c < s.nc; ++c) { /* :1620-1647, per constraint */
       const int dim = constraint_dim(p, s.cs[c]);
-      double sn[MAXDUAL], yn[MAXDUAL];
+      double sn[MAXDUAL], yn[MAXDUAL], sscale[MAXDUAL], yscale[MAXDUAL];
       for (int i = 0; i < dim; ++i) {
         const size_t q = (size_t)t * d + o + i;
         double a1 = 0.0, a2 = 0.0;
@@ -2428,12 +2428,23 @@ void ip_forward(const IpState &s, double alpha, IpTrial &r, bool force = false) 
         }
         sn[i] = (s.S[q] + alpha_pr * s.ks[q]) + a1;
         yn[i] = (s.Y[q] + alpha_du * s.ky[q]) + a2;
+        /* instrumentation: the magnitude roundoff is relative to — dx = x' - x carries the absolute roundoff of the rolled-out
+         * state (~eps |x|), which the gains K_s, K_y amplify; a threshold (1 - tau) s at the scale of a collapsed slack
+         * (1e-14) can be far below it */
+        double b1 = std::fabs(s.S[q]) + std::fabs(alpha_pr * s.ks[q]), b2 = std::fabs(s.Y[q]) + std::fabs(alpha_du * s.ky[q]);
+        for (int j = 0; j < n; ++j) {
+          const double xm = std::fabs(xt[j]) + std::fabs(s.X[(size_t)t * n + j]);
+          b1 += std::fabs(s.Ks[q * n + j]) * xm;
+          b2 += std::fabs(s.Ky[q * n + j]) * xm;
+        }
+        sscale[i] = b1;
+        yscale[i] = b2;
       }
       for (int i = 0; i < dim; ++i) {
         const size_t q = (size_t)t * d + o + i;
         const double smin = (1.0 - tau) * s.S[q], ymin = (1.0 - tau) * s.Y[q];
-        const double ms = std::fabs(sn[i] - smin) / std::max(std::fabs(smin), 1e-300);
-        const double my = std::fabs(yn[i] - ymin) / std::max(std::fabs(ymin), 1e-300);
+        const double ms = std::fabs(sn[i] - smin) / std::max(sscale[i], 1e-300);
+        const double my = std::fabs(yn[i] - ymin) / std::max(yscale[i], 1e-300);
         if (sn[i] < smin || yn[i] < ymin) {
           /* rejected: the decision is as robust as this violation (the scan below looks for a clearer one) */
           double best = std::max(sn[i] < smin ? ms : 0.0, yn[i] < ymin ? my : 0.0);
