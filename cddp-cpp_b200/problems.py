@@ -421,14 +421,18 @@ MANIP7_SOURCE = """
 // qdd from an LDL^T factorisation of the 7 x 7 mass matrix (positive definite for positive masses and lengths).
 template <class T>
 __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *xdot) {
+  // every loop has a constant trip count and is unrolled, so that c, s, w, r and the 28 entries of the upper triangle of M
+  // are addressed statically and live in registers (as run-time-indexed local arrays one RK4 step cost 60 us)
   const double g = p[0], bv = p[1];
   const double *mass = p + 2, *len = p + 9;
   double mu[7];
   mu[6] = mass[6];
+#pragma unroll
   for (int j = 5; j >= 0; --j) mu[j] = mu[j + 1] + mass[j];
   T c[7], s[7], w[7];
   {
     T sg = x[0] * 0.0, sv = x[0] * 0.0;
+#pragma unroll
     for (int j = 0; j < 7; ++j) {
       if (j > 0) {
         sg = sg + x[j];
@@ -440,9 +444,12 @@ __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *x
     }
   }
   T M[7][7], r[7];
+#pragma unroll
   for (int k = 0; k < 7; ++k) r[k] = u[k] - bv * x[7 + k];
+#pragma unroll
   for (int i = 0; i < 7; ++i) {
     M[i][i] = x[0] * 0.0 + mu[i] * len[i] * len[i];
+#pragma unroll
     for (int j = i + 1; j < 7; ++j) {
       const double a = mu[j] * len[i] * len[j];
       M[i][j] = a * (c[i] * c[j] + s[i] * s[j]);
@@ -451,32 +458,44 @@ __device__ void cddp_user_dynamics(const T *x, const T *u, const double *p, T *x
       r[i] = r[i] + md * x[7 + j];
       r[j] = r[j] + md * x[7 + i];
       const T P = S * (x[7 + i] * x[7 + j]);
+#pragma unroll
       for (int k = i + 1; k <= j; ++k) r[k] = r[k] - P;
     }
   }
   {
     T acc = x[0] * 0.0;  // -G_k = sum_{j >= k} mu_j g l_j cos(sigma_j), k >= 1
+#pragma unroll
     for (int k = 6; k >= 1; --k) {
       acc = acc + (mu[k] * g * len[k]) * c[k];
       r[k] = r[k] + acc;
     }
   }
   // LDL^T in place (unit lower factor in the upper-triangle slots M[j][i], i > j; pivots on the diagonal)
+#pragma unroll
   for (int j = 0; j < 7; ++j) {
     T d = M[j][j];
+#pragma unroll
     for (int k = 0; k < j; ++k) d = d - M[k][j] * M[k][j] * M[k][k];
     M[j][j] = d;
+#pragma unroll
     for (int i = j + 1; i < 7; ++i) {
       T v = M[j][i];
+#pragma unroll
       for (int k = 0; k < j; ++k) v = v - M[k][i] * M[k][j] * M[k][k];
       M[j][i] = v / d;
     }
   }
+#pragma unroll
   for (int i = 0; i < 7; ++i)
+#pragma unroll
     for (int k = 0; k < i; ++k) r[i] = r[i] - M[k][i] * r[k];
+#pragma unroll
   for (int i = 0; i < 7; ++i) r[i] = r[i] / M[i][i];
+#pragma unroll
   for (int i = 6; i >= 0; --i)
+#pragma unroll
     for (int k = i + 1; k < 7; ++k) r[i] = r[i] - M[i][k] * r[k];
+#pragma unroll
   for (int i = 0; i < 7; ++i) {
     xdot[i] = x[7 + i];
     xdot[7 + i] = r[i];

@@ -147,7 +147,8 @@ def ip_snapshot(s):
     return r
 
 
-@pytest.mark.parametrize("name,B", [("unicycle_obstacle_teq", 2048), ("unicycle_obstacle", 2048), ("pendulum_ipddp", 64)])
+@pytest.mark.parametrize("name,B", [("unicycle_obstacle_teq", 2048), ("unicycle_obstacle", 2048), ("pendulum_ipddp", 64),
+                                    ("manip7_user_ipddp", 48)])
 def test_ipddp_lockstep_every_instance_every_iteration(cddp, ob, problems, name, B):
     """BASELINE config #4 (unicycle obstacle avoidance, IPDDP, path inequalities + terminal equality, N = 200) at its full
     batch, in lock step: before every batched iteration the CUDA path's IPDDP state — trajectories, duals, slacks,
