@@ -158,13 +158,15 @@ struct SmallQP {
   // free block is the inverse of the free block of H; clamped rows/columns come back as identity rows — callers
   // mask their right-hand sides / results instead of paying 2*M*M selects here.  H must be symmetric-stored.
   __device__ __forceinline__ static bool masked_inverse_raw(const double *H, unsigned free_mask, double *Inv) {
-    double Hm[M * M];
+    double Hm[M * M];  // symmetric: the M (M + 1) / 2 distinct entries are selected once and mirrored
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
+      for (int j = i; j < M; ++j) {
         const bool f = ((free_mask >> i) & 1u) && ((free_mask >> j) & 1u);
-        Hm[i * M + j] = f ? H[i * M + j] : (i == j ? 1.0 : 0.0);
+        const double h = f ? H[i * M + j] : (i == j ? 1.0 : 0.0);
+        Hm[i * M + j] = h;
+        Hm[j * M + i] = h;
       }
     return SymInverse<M>::run(Hm, Inv);
   }
@@ -247,13 +249,14 @@ struct SmallQP {
         status = QP_SUCCESS;
         break;
       }
-      double rhs[M];
+      double rhs[M], xc[M];  // xc = x on the clamped entries, 0 elsewhere: g + sum over the clamped i of H[:, i] x_i (:128-146)
+#pragma unroll                //  as M unpredicated FMAs per row (adding H * 0 changes nothing)
+      for (int i = 0; i < M; ++i) xc[i] = ((clamped >> i) & 1u) ? x[i] : 0.0;
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         double s = g[j];
 #pragma unroll
-        for (int i = 0; i < M; ++i)
-          if ((clamped >> i) & 1u) s += H[j * M + i] * x[i];
+        for (int i = 0; i < M; ++i) s += H[j * M + i] * xc[i];
         rhs[j] = ((free_mask >> j) & 1u) ? s : 0.0;  // masked rhs: the identity rows of the raw inverse then contribute nothing
       }
       double search[M];
