@@ -319,7 +319,14 @@ cudaError_t launch_user_forward(const Constants &c, const DeviceState &d, int mo
   if (!uk || (c.cost_diag != 0) != uk->diag) return cudaErrorInvalidValue;
   const int wpc = 2;  // kern::kWarpsPerCta
   void *params[] = {(void *)&c, (void *)&d, &mode};
-  if (mode == FW_ITERATE && !c.opt.enable_parallel) {  // speculative alphas_[0] first (kernels_forward.cuh)
+  // The speculative alphas_[0] pass (kernels_forward.cuh) saves THROUGHPUT: one rollout instead of 16 for every instance
+  // it settles.  Its price is LATENCY: the full-width launch that follows starts after it and costs a whole rollout
+  // however few instances are left.  It pays only while the full line search is throughput-bound, i.e. while the 16-wide
+  // rollout of the work list oversubscribes the SMs (measured with the 7-DOF manipulator: 9.1 ms at 1024 instances and
+  // 11.4 ms at 8192 with the pass, one rollout = 4.4 ms); below that the full launch runs alone.
+  const bool speculate = c.speculate >= 0 ? c.speculate != 0
+                                          : (long long)d.n_slots * 16 > 32LL * 2048 * 4;  // > 4 resident warps per scheduler on 148 SMs
+  if (mode == FW_ITERATE && !c.opt.enable_parallel && speculate) {
     cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.n_slots + 63) / 64), 64, 0, st, params);
     if (e != cudaSuccess) return e;
   } else if (mode == FW_ITERATE) {

@@ -309,6 +309,10 @@ CDDP_B200_API int cddp_b200_set_poll_interval(cddp_b200_solver *s, int interval)
  * 0.418 ms): the rollout is bound by the latency of its 100 dependent RK4 steps, not by FP64 throughput, and half the
  * warps hide less of it.  Kept as an option for throughput-bound models. */
 CDDP_B200_API int cddp_b200_set_line_search_window(cddp_b200_solver *s, int enable);
+/* User-model handles, sequential rule: try alphas_[0] on one lane per instance before the 16-wide line search (same
+ * decisions and trajectories).  mode 1 = always, 0 = never, -1 (default) = only while the full search is throughput-bound
+ * (it saves 15 of 16 rollouts per settled instance but adds one rollout of latency). */
+CDDP_B200_API int cddp_b200_set_first_alpha_speculation(cddp_b200_solver *s, int mode);
 CDDP_B200_API int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
                                  int *iterations_completed, int *status, double *final_step_length,
                                  double *final_regularization, double *inf_du);

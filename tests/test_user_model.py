@@ -171,6 +171,7 @@ def test_speculative_first_alpha_and_option_switch(cddp, ob, problems):
     opts = dict(cfg["options"], max_iterations=30)
     P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**opts)
     s = cddp.BatchedCLDDP(cfg["spec"], cddp.default_options(**opts), B)
+    s.set_first_alpha_speculation(1)  # a batch this small would not speculate on its own (latency-bound)
     s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
     s.enable_history(True)
     s.initialize()
