@@ -322,10 +322,10 @@ cudaError_t launch_user_forward(const Constants &c, const DeviceState &d, int mo
   // The speculative alphas_[0] pass (kernels_forward.cuh) saves THROUGHPUT: one rollout instead of 16 for every instance
   // it settles.  Its price is LATENCY: the full-width launch that follows starts after it and costs a whole rollout
   // however few instances are left.  It pays only while the full line search is throughput-bound, i.e. while the 16-wide
-  // rollout of the work list oversubscribes the SMs (measured with the 7-DOF manipulator: 9.1 ms at 1024 instances and
-  // 11.4 ms at 8192 with the pass, one rollout = 4.4 ms); below that the full launch runs alone.
+  // rollout of the work list oversubscribes the SMs (measured with the 7-DOF manipulator: 9.1 -> 3.4 ms at 1024 instances
+  // without the pass, 12.6 -> 11.4 ms at 8192 with it); below that the full launch runs alone.
   const bool speculate = c.speculate >= 0 ? c.speculate != 0
-                                          : (long long)d.n_slots * 16 > 32LL * 2048 * 4;  // > 4 resident warps per scheduler on 148 SMs
+                                          : d.n_slots >= 8192;  // 16 lanes x 8192 = 4096 warps = 27 per SM: past the point where one more rollout of latency is cheaper
   if (mode == FW_ITERATE && !c.opt.enable_parallel && speculate) {
     cudaError_t e = launch(uk, K_FWD1, (unsigned)((d.n_slots + 63) / 64), 64, 0, st, params);
     if (e != cudaSuccess) return e;
