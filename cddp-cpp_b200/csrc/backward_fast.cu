@@ -81,7 +81,7 @@ enum { CTRL_OK = 1, CTRL_RESTART = 2, CTRL_FAIL = 3 };
 // their own named barriers, so a slow subproblem holds up 8 trajectories instead of 28, and the warps re-divide the
 // register file with setmaxnreg (sm_90+): 12 warps are launched at 168 registers, the matrix warps grow to kMatrixRegs
 // and the QP warps shrink to kQpRegs (8*32*216 + 4*32*72 = 384*168).
-template <int NS, int NC, class PAT, int W, bool QPQ = false>
+template <int NS, int NC, class PAT, int W, bool QPQ = false, int SMOD = -1>
 struct SweepCfg {
   using L = RecordLayout<NS, NC, PAT>;
   static constexpr int G = group_size(NS);
@@ -115,14 +115,17 @@ struct SweepCfg {
   static constexpr int oKst = oBar + 2;                   // [2][NC] BoxQP warm start k_u_[t], staged with the record (TMA)
   static constexpr bool kStaged = (NC * 8) % 16 == 0;     // cp.async.bulk moves multiples of 16 bytes
   static constexpr int raw = oKst + (kStaged ? 2 * NC : 0);
-  // Stride between the blocks of neighbouring trajectories, in doubles (even: records stay 16-byte aligned).
-  // Four trajectories per warp (G = 8): stride == 4 (mod 16).  A broadcast read then touches the four 8-byte banks
-  // 0, 4, 8, 12 (+ offset) — one wavefront — and a row / transposed access (8 consecutive doubles per trajectory)
-  // covers every bank exactly twice — two wavefronts, the minimum for 256 bytes.  The former stride == 2 (mod 4)
-  // made such accesses 4-way conflicts (ncu: 80.0 M shared wavefronts against 59.7 M ideal).
-  // Eight trajectories per warp (G = 4): stride == 2 (mod 16), distinct banks for the eight broadcast addresses.
-  static constexpr int want = (G == 8) ? 4 : 2;
-  static constexpr int ST = raw + ((want - raw % 16) + 16) % 16;
+  // Stride between the blocks of neighbouring trajectories, in doubles; even, so that the records stay 16-byte aligned
+  // for the bulk copies.  Which residue mod 16 (= mod the 32 four-byte banks) is best was MEASURED, not derived — the
+  // matrix warps' row / transposed accesses (8 consecutive doubles per trajectory, 4 trajectories per warp), their
+  // broadcast reads and the QP warp's accesses (lane q -> trajectory q: 28 addresses one stride apart) pull in different
+  // directions.  Headline launch, ncu shared wavefronts / bank conflicts per launch and sweep time (profiles/
+  // r02_sweep_stride.txt): residue 0: 192.7 M / 130.1 M, 0.785 ms; 2 and 14: 88.0 M / 25.6 M, 0.562 ms; 4 and 12: 90.3 M /
+  // 27.9 M, 0.563 ms; 8: 98.4 M / 36.0 M, 0.564 ms; **6 and 10: 82.3 M / 20.0 M, 0.552 ms**.  Four trajectories per warp use
+  // residue 6; eight (G = 4) keep "== 2 (mod 4)".
+  static constexpr int ST = (SMOD >= 0) ? raw + ((SMOD - raw % 16) + 16) % 16
+                            : (G == 8) ? raw + ((6 - raw % 16) + 16) % 16
+                                       : raw + ((2 - raw % 4) + 4) % 4;
   static constexpr int constDoubles = ((NS * NS + NC * NC) + 1) & ~1;
   static constexpr size_t smemBytes = sizeof(double) * (size_t)(constDoubles + T * ST);
   static constexpr int threads = (W + QW) * 32;
@@ -180,9 +183,9 @@ __device__ __forceinline__ void sweep_epilogue(const Constants &c, const DeviceS
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1>
 __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
-  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
   static_assert(!QPQ || (NC == 4 && Cfg::TPW == 4 && W % 2 == 0), "quad QP: m = 4, sets of two matrix warps");
   using L = typename Cfg::L;
   constexpr int G = Cfg::G, R = Cfg::R, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
@@ -806,20 +809,20 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1>
 cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
-  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
   static_assert(QPQ || Cfg::T <= 32, "one QP-warp lane per trajectory");
   static_assert(NS + 1 <= Cfg::G * Cfg::R, "V_x rides as an extra row");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int blocks = (d.n_slots + Cfg::T - 1) / Cfg::T;
-  sweep_kernel<NS, NC, PAT, W, MINB, QPQ><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
+  sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
   return cudaGetLastError();
 }
 
