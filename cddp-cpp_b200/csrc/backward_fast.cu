@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
 
     auto issue = [&](int tt, int x) {
       if (r == 0) {
+        // the buffer was last READ through the generic proxy (phases A1 / A2 of the step that used it, ordered before this
+        // point by the __syncwarp of the caller); the bulk copy WRITES it through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bar[x], RS * 8 + (Cfg::kStaged ? NC * 8 : 0));
         bulk_g2s(S + Cfg::oRec + x * RS, grec + (size_t)tt * RS, RS * 8, &bar[x]);
         // the BoxQP warm start of step tt rides on the same mbarrier: as a plain load issued in phase A2 it shared a
