@@ -27,7 +27,10 @@
 #include "boxqp_quad.cuh"
 #include "boxqp_small.cuh"
 #include "engine.h"
+#include "kernel_common.cuh"
+#include "models.cuh"
 #include "records.cuh"
+#include "static_for.cuh"
 
 namespace cddp_b200 {
 
@@ -183,7 +186,14 @@ __device__ __forceinline__ void sweep_epilogue(const Constants &c, const DeviceS
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1>
+// FMODEL >= 0 (one-QP-warp layout, a built-in model's structured records): FUSED LINEARISATION (SURVEY 8f N2,
+// clddp_solver.cpp:113-118 computes A, B inside the sweep's loop).  The QP warp is idle from barrier 2 to barrier 1 — while
+// the matrix warps run phases C and A1, 40 % of the step — and holds no matrix state, so its lane q forms ONE record of
+// trajectory q per step there (closed-form Jacobians of timestep lt = N-4, N-5, ... from x, u; the same statements as
+// linearize_kernel), four steps ahead of the sweep, and writes it to the trajectory's record buffer; the matrix warps
+// stage it through the same bulk copies as before.  The separate linearize launch (0.115 ms of the 1.06 ms iteration)
+// is then skipped by the iteration loop; white-box calls (BW_SINGLE) use the records they are given.
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1, int FMODEL = -1>
 __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
   using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
   static_assert(!QPQ || (NC == 4 && Cfg::TPW == 4 && W % 2 == 0), "quad QP: m = 4, sets of two matrix warps");
@@ -251,7 +261,10 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
       if (r == 0) {
         // the buffer was last READ through the generic proxy (phases A1 / A2 of the step that used it, ordered before this
         // point by the __syncwarp of the caller); the bulk copy WRITES it through the async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // (fused linearisation: the record itself was WRITTEN to global memory through the generic proxy by the QP warp, a
+        // CTA barrier ago, and is READ by the bulk copy through the async proxy)
+        if constexpr (FMODEL >= 0) asm volatile("fence.proxy.async;" ::: "memory");
+        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bar[x], RS * 8 + (Cfg::kStaged ? NC * 8 : 0));
         bulk_g2s(S + Cfg::oRec + x * RS, grec + (size_t)tt * RS, RS * 8, &bar[x]);
         // the BoxQP warm start of step tt rides on the same mbarrier: as a plain load issued in phase A2 it shared a
@@ -662,6 +675,99 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
     const bool alive = q < T && b < d.B && !(mode == BW_ITERATE && d.status[b] != CDDP_B200_STATUS_RUNNING);
     const double *S = traj0 + (q < T ? q : T - 1) * ST;
     double *Sw = traj0 + (q < T ? q : T - 1) * ST;
+    // ---- fused linearisation: this lane's trajectory, one record per step, three steps ahead of the sweep
+    const bool need_lin = FMODEL >= 0 && mode == BW_ITERATE && alive && !d.lin_valid[b];
+    int lt = N - 1;  // next timestep whose record is still to be formed
+    auto produce = [&](int tt) {
+      if constexpr (FMODEL >= 0) {
+        const int cur = d.cur[b];
+        const double *xp = d.X[cur] + ((size_t)b * (N + 1) + tt) * NS;
+        const double *up = d.U[cur] + ((size_t)b * N + tt) * NC;
+        double x[NS], u[NC], Fx[NS * NS], Fu[NS * NC], lxv[NS], luv[NC];
+#pragma unroll
+        for (int i2 = 0; i2 < NS; ++i2) x[i2] = xp[i2];
+#pragma unroll
+        for (int i2 = 0; i2 < NC; ++i2) u[i2] = up[i2];
+        Model<FMODEL>::jac(c.mp, x, u, Fx, Fu);
+        const double *ref = kern::ref_ptr(d, b, tt);
+        double e[NS];
+#pragma unroll
+        for (int i2 = 0; i2 < NS; ++i2) e[i2] = x[i2] - ref[i2];
+        if (c.cost_diag) {  // the statements of linearize_kernel (kernels_linearize.cuh), in its order
+#pragma unroll
+          for (int i2 = 0; i2 < NS; ++i2) lxv[i2] = 0.0 + c.Qdt2[i2 * NS + i2] * e[i2];
+#pragma unroll
+          for (int i2 = 0; i2 < NC; ++i2) luv[i2] = 0.0 + c.Rdt2[i2 * NC + i2] * u[i2];
+        } else {
+#pragma unroll
+          for (int i2 = 0; i2 < NS; ++i2) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j2 = 0; j2 < NS; ++j2) acc += c.Qdt2[i2 * NS + j2] * e[j2];
+            lxv[i2] = acc;
+          }
+#pragma unroll
+          for (int i2 = 0; i2 < NC; ++i2) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j2 = 0; j2 < NC; ++j2) acc += c.Rdt2[i2 * NC + j2] * u[j2];
+            luv[i2] = acc;
+          }
+        }
+        double rv[RS];  // the packed record, then 16-byte stores (a record is a 16-byte multiple, 16-byte aligned)
+#pragma unroll
+        for (int i2 = 0; i2 < RS; ++i2) rv[i2] = 0.0;
+        static_for<0, NS>([&](auto lc) {
+          constexpr int l = decltype(lc)::value;
+          static_for<0, NS>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (PAT::a(l, j)) rv[L::idxA(l, j)] = c.dt * Fx[l * NS + j] + (l == j ? 1.0 : 0.0);
+          });
+          if constexpr (PAT::brow(l)) {
+            static_for<0, NC>([&](auto ac) {
+              constexpr int a = decltype(ac)::value;
+              rv[L::idxB(l, a)] = c.dt * Fu[l * NC + a];
+            });
+          }
+          rv[L::offLx + l] = lxv[l];
+        });
+        static_for<0, NC>([&](auto ac) {
+          constexpr int a = decltype(ac)::value;
+          rv[L::offLu + a] = luv[a];
+          rv[L::offU + a] = u[a];
+        });
+        double2 *dst = reinterpret_cast<double2 *>(d.rec + ((size_t)b * N + tt) * RS);
+#pragma unroll
+        for (int i2 = 0; i2 < RS / 2; ++i2) dst[i2] = make_double2(rv[2 * i2], rv[2 * i2 + 1]);
+        if (tt > 0) {  // the next window's x, u (the timestep below): into L1 now, so that its loads do not start the window with an HBM round trip
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(xp - NS));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(xp - 1));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up - NC));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(up - 1));
+        }
+      }
+    };
+    if (need_lin) {
+      if constexpr (FMODEL >= 0) {
+        // terminal gradient V_x(N) = 2 Qf (x_N - ref) (objective.cpp:122-126), as linearize_kernel forms it
+        const double *xp = d.X[d.cur[b]] + ((size_t)b * (N + 1) + N) * NS;
+        const double *ref = d.xref + (size_t)b * NS;
+        double e[NS];
+#pragma unroll
+        for (int i2 = 0; i2 < NS; ++i2) e[i2] = xp[i2] - ref[i2];
+        for (int i2 = 0; i2 < NS; ++i2) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < NS; ++j2) acc += c.Qf2[i2 * NS + j2] * e[j2];
+          d.vterm[(size_t)b * NS + i2] = acc;
+        }
+      }
+      // records N-1, N-2 are staged right after the barrier below, N-3 during the first step: a record is always formed
+      // one whole step before the bulk copy that reads it is issued, so that the fence which pushes it to the L2
+      // (__threadfence at the top of the NEXT window) finds its stores long since acknowledged
+      for (int k2 = 0; k2 < 3 && lt >= 0; ++k2) produce(lt--);
+      __threadfence();
+    }
     __syncthreads();
     double reg = alive ? d.reg[b] : 0.0;
     if (alive && mode == BW_ITERATE) d.iter[b] += 1;  // ++iter, cddp_solver_base.cpp:75
@@ -670,6 +776,10 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
     bool run = alive, ok = false;
     constexpr unsigned all = (1u << NC) - 1u;
     while (true) {
+      if (need_lin) {  // the idle window: barrier 2 of the previous step ... barrier 1 of this one
+        __threadfence();  // the record of the PREVIOUS window is at the L2 before the barrier that lets a matrix lane copy it
+        if (lt >= 0) produce(lt--);
+      }
       if (!barrier_any(run)) break;
       if (run) {
         double H[MC * MC], g[MC], kk[MC], Hk[MC];
@@ -812,20 +922,20 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1, int FMODEL = -1>
 cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
   using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
   static_assert(QPQ || Cfg::T <= 32, "one QP-warp lane per trajectory");
   static_assert(NS + 1 <= Cfg::G * Cfg::R, "V_x rides as an extra row");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD, FMODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int blocks = (d.n_slots + Cfg::T - 1) / Cfg::T;
-  sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
+  sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD, FMODEL><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
   return cudaGetLastError();
 }
 
@@ -844,12 +954,33 @@ static int sweep_variant() {
   return v;
 }
 
+// Fused linearisation is OPT-IN (CDDP_B200_FUSED_LINEARIZE=1): it passes the same parity tests — the lock-step run of the
+// headline batch gives the same worst-case errors to the last digit — but it is SLOWER on B200.  Forming one quadrotor
+// record is ~750 dependent instructions for a single lane (~8 k cycles in the QP warp, which shares its scheduler's FP64
+// pipe with a matrix warp in its critical phase C); the idle window is 4.7 k.  Measured, headline batch: sweep 0.551 ->
+// 0.701 ms with the linearize launch (0.115 ms) gone: iteration 1.061 -> 1.114 ms (first version, fence and loads on
+// the window's critical path: 1.181 ms).
+static bool sweep_fused_enabled() {
+  static const bool v = [] {
+    const char *e = std::getenv("CDDP_B200_FUSED_LINEARIZE");
+    return e && std::string(e) == "1";
+  }();
+  return v;
+}
+
+// true if launch_backward(BW_ITERATE) forms the linearisation records itself (the iteration loop then skips linearize)
+bool backward_fuses_linearization(const Constants &c, const DeviceState &d) {
+  return d.layout == RECORDS_STRUCTURED && c.model == CDDP_B200_MODEL_QUADROTOR && sweep_variant() != 0 && sweep_fused_enabled();
+}
+
 cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int mode, cudaStream_t st, bool *handled) {
   *handled = true;
   const int n = d.n, m = d.m;
   if (d.layout == RECORDS_STRUCTURED) {
     if (c.model == CDDP_B200_MODEL_QUADROTOR) {
       if (sweep_variant() == 0) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 8, 1, true>(c, d, mode, st);
+      if (sweep_fused_enabled())
+        return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1, false, -1, CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
       return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     }
     if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);

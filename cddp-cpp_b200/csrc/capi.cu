@@ -230,7 +230,8 @@ int do_forward(cddp_b200_solver *s, int mode) {
 
 int one_iteration(cddp_b200_solver *s) {
   int r;
-  if ((r = do_linearize(s, false))) return r;
+  // CLDDP sweeps that form their own linearisation records (fused linearisation, backward_fast.cu) need no linearize launch
+  if (!(s->kind == 0 && backward_fuses_linearization(s->c, s->d)) && (r = do_linearize(s, false))) return r;
   if ((r = do_backward(s, BW_ITERATE))) return r;
   if ((r = do_forward(s, FW_ITERATE))) return r;
   return 0;

@@ -182,6 +182,7 @@ enum ForwardMode { FW_EVALUATE = 0 /* do not apply */, FW_ITERATE = 1 };
 cudaError_t launch_linearize(const Constants &c, const DeviceState &d, bool force, cudaStream_t st);
 cudaError_t launch_initialize(const Constants &c, const DeviceState &d, cudaStream_t st);
 cudaError_t launch_backward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
+bool backward_fuses_linearization(const Constants &c, const DeviceState &d);
 cudaError_t launch_forward(const Constants &c, const DeviceState &d, int mode, cudaStream_t st);
 cudaError_t launch_finalize(const Constants &c, const DeviceState &d, int final_status, cudaStream_t st);
 cudaError_t launch_count_running(const DeviceState &d, cudaStream_t st);

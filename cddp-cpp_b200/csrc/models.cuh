@@ -198,7 +198,7 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
   // Fx [13][13], Fu [13][4], row-major, fully written.
   __device__ __forceinline__ static void jac(const ModelParams &P, const double *x, const double *u, double *Fx,
                                              double *Fu) {
-    const double mass = P.p[0], L = P.p[10];
+    const double L = P.p[10];
     Inertia J;
     inertia(P, J);
 #pragma unroll
@@ -210,18 +210,20 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
     Fx[1 * 13 + 8] = 1.0;
     Fx[2 * 13 + 9] = 1.0;
     double qw = x[3], qx = x[4], qy = x[5], qz = x[6];
-    const double norm = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
-    const bool reg = norm > 1e-6;
+    // 1/|q| as rsqrt(|q|^2) and products instead of a square root and six divisions (each an FP64 division is a
+    // ~25-instruction dependent sequence; the Jacobian is a latency chain wherever it runs), as f() does
+    const double n2 = qw * qw + qx * qx + qy * qy + qz * qz;
+    const bool reg = n2 > 1e-12;  // |q| > 1e-6 (quadrotor.cpp:45-55)
     double inv_norm = 0.0;
     if (reg) {
-      inv_norm = 1.0 / norm;
-      qw /= norm; qx /= norm; qy /= norm; qz /= norm;
+      inv_norm = rsqrt(n2);
+      qw *= inv_norm; qx *= inv_norm; qy *= inv_norm; qz *= inv_norm;
     } else {
       qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0;
     }
     const double wx = x[10], wy = x[11], wz = x[12];
     const double thrust = u[0] + u[1] + u[2] + u[3];
-    const double tm = thrust / mass;
+    const double tm = thrust * P.p[25];  // p[25] = 1 / mass (prepare())
     // G = d(q_dot, v_dot)/d(qn): 7 rows x 4 cols
     double G[7][4] = {
         {0.0, -0.5 * wx, -0.5 * wy, -0.5 * wz},
@@ -268,7 +270,7 @@ struct Model<CDDP_B200_MODEL_QUADROTOR> {
         Fx[(10 + r) * 13 + 10 + c] =
             -(J.Iinv[r * 3 + 0] * D[0 * 3 + c] + J.Iinv[r * 3 + 1] * D[1 * 3 + c] + J.Iinv[r * 3 + 2] * D[2 * 3 + c]);
     // Fu: v_dot rows = r3/m for every rotor; omega_dot rows = Iinv * dtau/df
-    const double im = 1.0 / mass;
+    const double im = P.p[25];
     const double r3x = 2.0 * (qx * qz + qy * qw), r3y = 2.0 * (qy * qz - qx * qw), r3z = 1.0 - 2.0 * (qx * qx + qy * qy);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
