@@ -133,7 +133,7 @@ ABI_SYMBOLS = [
     "cddp_b200_get_linearization", "cddp_b200_set_linearization", "cddp_b200_get_sweep", "cddp_b200_get_forward",
     "cddp_b200_reset_timing", "cddp_b200_get_timing", "cddp_b200_enable_timing",
     "cddp_b200_backward_algorithmic_bytes", "cddp_b200_solve_host", "cddp_b200_set_record_layout",
-    "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_set_line_search_window", "cddp_b200_set_first_alpha_speculation", "cddp_b200_get_solution_async",
+    "cddp_b200_get_record_layout", "cddp_b200_set_poll_interval", "cddp_b200_set_line_search_window", "cddp_b200_set_first_alpha_speculation", "cddp_b200_set_fused_linearization", "cddp_b200_get_solution_async",
     "cddp_b200_mpc_advance", "cddp_b200_get_first_controls_async",
     "cddp_b200_ipddp_default_options", "cddp_b200_ipddp_create", "cddp_b200_ipddp_dual_dim",
     "cddp_b200_ipddp_get_solution", "cddp_b200_ipddp_get_iteration_state", "cddp_b200_ipddp_get_gains", "cddp_b200_ipddp_get_line_search",
@@ -190,6 +190,7 @@ def load_library() -> C.CDLL:
     lib.cddp_b200_set_poll_interval.argtypes = [vp, C.c_int]
     lib.cddp_b200_set_line_search_window.argtypes = [vp, C.c_int]
     lib.cddp_b200_set_first_alpha_speculation.argtypes = [vp, C.c_int]
+    lib.cddp_b200_set_fused_linearization.argtypes = [vp, C.c_int]
     lib.cddp_b200_mpc_advance.argtypes = [vp, C.c_int, vp, vp]
     lib.cddp_b200_get_first_controls_async.argtypes = [vp, vp, vp, vp]
     lib.cddp_b200_enable_history.argtypes = [vp, C.c_int]
@@ -376,6 +377,9 @@ class BatchedCLDDP:
 
     def set_line_search_window(self, enable: bool):
         _check(self.lib.cddp_b200_set_line_search_window(self.handle, int(enable)))
+
+    def set_fused_linearization(self, enable: bool):
+        _check(self.lib.cddp_b200_set_fused_linearization(self.handle, int(enable)))
 
     def set_first_alpha_speculation(self, mode: int):
         _check(self.lib.cddp_b200_set_first_alpha_speculation(self.handle, int(mode)))

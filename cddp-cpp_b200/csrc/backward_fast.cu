@@ -954,7 +954,7 @@ static int sweep_variant() {
   return v;
 }
 
-// Fused linearisation is OPT-IN (CDDP_B200_FUSED_LINEARIZE=1): it passes the same parity tests — the lock-step run of the
+// Fused linearisation is OPT-IN (cddp_b200_set_fused_linearization, or CDDP_B200_FUSED_LINEARIZE=1 for every handle): it passes the same parity tests — the lock-step run of the
 // headline batch gives the same worst-case errors to the last digit — but it is SLOWER on B200.  Forming one quadrotor
 // record is ~750 dependent instructions for a single lane (~8 k cycles in the QP warp, which shares its scheduler's FP64
 // pipe with a matrix warp in its critical phase C); the idle window is 4.7 k.  Measured, headline batch: sweep 0.551 ->
@@ -970,7 +970,8 @@ static bool sweep_fused_enabled() {
 
 // true if launch_backward(BW_ITERATE) forms the linearisation records itself (the iteration loop then skips linearize)
 bool backward_fuses_linearization(const Constants &c, const DeviceState &d) {
-  return d.layout == RECORDS_STRUCTURED && c.model == CDDP_B200_MODEL_QUADROTOR && sweep_variant() != 0 && sweep_fused_enabled();
+  return d.layout == RECORDS_STRUCTURED && c.model == CDDP_B200_MODEL_QUADROTOR && sweep_variant() != 0 &&
+         (c.fuse_lin || sweep_fused_enabled());
 }
 
 cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int mode, cudaStream_t st, bool *handled) {
@@ -979,7 +980,7 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
   if (d.layout == RECORDS_STRUCTURED) {
     if (c.model == CDDP_B200_MODEL_QUADROTOR) {
       if (sweep_variant() == 0) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 8, 1, true>(c, d, mode, st);
-      if (sweep_fused_enabled())
+      if (c.fuse_lin || sweep_fused_enabled())
         return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1, false, -1, CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
       return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     }

@@ -71,6 +71,7 @@ struct cddp_b200_solver {
   int ckpt_lg = 16;  // lanes per trajectory the line-search scratch was sized for
   int poll_interval = -1;  // -1: automatic (default: every iteration for heavy batches, else a widening stride); 0: never poll (fully asynchronous solve); k > 0: every k iterations
   int speculate = -1;     // cddp_b200_set_first_alpha_speculation
+  int fuse_lin = 0;       // cddp_b200_set_fused_linearization
   int ls_window = 0;      // windowed line search (cddp_b200_set_line_search_window); off: measured slower on B200
   double *rec_by_layout[2] = {nullptr, nullptr};  // record buffers are allocated lazily per layout
   int *h_running = nullptr;  // pinned
@@ -153,6 +154,7 @@ void set_options(cddp_b200_solver *s, const cddp_b200_options &o) {
   s->d.num_alphas = s->c.num_alphas;
   s->c.ls_window = s->ls_window;
   s->c.speculate = s->speculate;
+  s->c.fuse_lin = s->fuse_lin;
 }
 
 // Selects the record layout (records.cuh): allocates the record buffer of that layout on first use and
@@ -748,6 +750,13 @@ int cddp_b200_set_line_search_window(cddp_b200_solver *s, int enable) {
   if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
   s->ls_window = enable ? 1 : 0;
   s->c.ls_window = s->ls_window;
+  return 0;
+}
+
+int cddp_b200_set_fused_linearization(cddp_b200_solver *s, int enable) {
+  if (!s) return CDDP_B200_ERR_INVALID_ARGUMENT;
+  s->fuse_lin = enable ? 1 : 0;
+  s->c.fuse_lin = s->fuse_lin;
   return 0;
 }
 

@@ -130,6 +130,7 @@ struct Constants {
   double alphas[CDDP_B200_MAX_ALPHAS];
   int num_alphas;
   int ls_window;  // windowed line search (kernels_forward.cuh): first 8 candidates at 8 lanes per trajectory, then the rest
+  int fuse_lin;   // CLDDP, quadrotor structured records: the sweep's QP warp forms the linearisation records itself (opt-in)
   int speculate;  // user models: speculative alphas_[0] pass; -1 = automatic (only while the full search is throughput-bound)
   cddp_b200_options opt;
 };

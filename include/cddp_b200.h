@@ -313,6 +313,11 @@ CDDP_B200_API int cddp_b200_set_line_search_window(cddp_b200_solver *s, int enab
  * decisions and trajectories).  mode 1 = always, 0 = never, -1 (default) = only while the full search is throughput-bound
  * (it saves 15 of 16 rollouts per settled instance but adds one rollout of latency). */
 CDDP_B200_API int cddp_b200_set_first_alpha_speculation(cddp_b200_solver *s, int mode);
+/* Fused linearisation (default off; CLDDP, quadrotor, structured records): A = I + dt Fx, B = dt Fu are formed inside the
+ * backward sweep, as CLDDPSolver::backwardPass does (clddp_solver.cpp:113-118), by the sweep's otherwise idle QP warp, and
+ * cddp_b200_iterate / _solve skip the separate linearisation launch.  Results are identical; measured on B200 it is slower
+ * (iteration 1.061 -> 1.114 ms at the headline batch), hence opt-in. */
+CDDP_B200_API int cddp_b200_set_fused_linearization(cddp_b200_solver *s, int enable);
 CDDP_B200_API int cddp_b200_get_solution_async(cddp_b200_solver *s, double *X, double *U, double *K, double *final_objective,
                                  int *iterations_completed, int *status, double *final_step_length,
                                  double *final_regularization, double *inf_du);

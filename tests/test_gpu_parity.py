@@ -540,3 +540,25 @@ def test_max_cpu_time_stops_the_solve(cddp, problems):
     np.testing.assert_array_equal(ra["status"], rb["status"])
     a.close()
     b.close()
+
+
+def test_fused_linearization_changes_nothing(cddp, problems):
+    """cddp_b200_set_fused_linearization: A = I + dt Fx, B = dt Fu formed inside the sweep by its QP warp (as
+    clddp_solver.cpp:113-118 forms them inside backwardPass) instead of by the linearize launch — same records, hence
+    bitwise the same solve, including instances that restart their sweep (regularisation retry), failed line searches
+    (records reused) and a batch that is not a multiple of the CTA size."""
+    B = 61
+    cfg = problems.make_config("quadrotor", batch=B, horizon=57)
+    out = []
+    for fused in (True, False):
+        s, _ = make(cddp, cfg, B, max_iterations=30)
+        s.set_fused_linearization(fused)
+        s.enable_timing(True)
+        s.solve()
+        r = s.get_solution()
+        t = s.get_timing()
+        assert (t.linearize_launches == 0) == fused
+        out.append(r)
+        s.close()
+    for key in ("X", "U", "K", "cost", "iterations", "status", "alpha", "reg", "inf_du"):
+        assert np.array_equal(out[0][key], out[1][key]), key
