@@ -44,6 +44,8 @@ def main():
     s = cddp.BatchedCLDDP(spec, cddp.default_options(**opts), B)
     if "--dense" in sys.argv:
         s.set_record_layout("dense")
+    if "--fused" in sys.argv:
+        s.set_fused_linearization(int(sys.argv[sys.argv.index("--fused") + 1]))
     s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"], cfg["ref_traj"])
     s.initialize()
     if "--cold" not in sys.argv:
@@ -56,6 +58,8 @@ def main():
     lay, nb = s.get_record_layout()
     alg = s.backward_algorithmic_bytes()
     bw = t.backward_ms / t.backward_launches
+    if t.linearize_launches == 0:
+        t.linearize_launches = 1
     print(f"{name} B={B} box={'lb' in spec and spec['lb'] is not None} layout={lay} ({nb} B/record): "
           f"linearize {t.linearize_ms / t.linearize_launches:.3f} ms  backward {bw:.3f} ms ({alg / bw / 1e6 / 6539.2 * 100:.1f}% of HBM peak, algorithmic)  "
           f"forward {t.forward_ms / t.forward_launches:.3f} ms  mean cost {np.mean(sc['cost']):.4f} finite={np.isfinite(sc['cost']).all()}")
