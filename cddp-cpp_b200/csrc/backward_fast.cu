@@ -84,7 +84,7 @@ enum { CTRL_OK = 1, CTRL_RESTART = 2, CTRL_FAIL = 3 };
 // their own named barriers, so a slow subproblem holds up 8 trajectories instead of 28, and the warps re-divide the
 // register file with setmaxnreg (sm_90+): 12 warps are launched at 168 registers, the matrix warps grow to kMatrixRegs
 // and the QP warps shrink to kQpRegs (8*32*216 + 4*32*72 = 384*168).
-template <int NS, int NC, class PAT, int W, bool QPQ = false, int SMOD = -1>
+template <int NS, int NC, class PAT, int W, bool QPQ = false>
 struct SweepCfg {
   using L = RecordLayout<NS, NC, PAT>;
   static constexpr int G = group_size(NS);
@@ -126,9 +126,7 @@ struct SweepCfg {
   // r02_sweep_stride.txt): residue 0: 192.7 M / 130.1 M, 0.785 ms; 2 and 14: 88.0 M / 25.6 M, 0.562 ms; 4 and 12: 90.3 M /
   // 27.9 M, 0.563 ms; 8: 98.4 M / 36.0 M, 0.564 ms; **6 and 10: 82.3 M / 20.0 M, 0.552 ms**.  Four trajectories per warp use
   // residue 6; eight (G = 4) keep "== 2 (mod 4)".
-  static constexpr int ST = (SMOD >= 0) ? raw + ((SMOD - raw % 16) + 16) % 16
-                            : (G == 8) ? raw + ((6 - raw % 16) + 16) % 16
-                                       : raw + ((2 - raw % 4) + 4) % 4;
+  static constexpr int ST = (G == 8) ? raw + ((6 - raw % 16) + 16) % 16 : raw + ((2 - raw % 4) + 4) % 4;
   static constexpr int constDoubles = ((NS * NS + NC * NC) + 1) & ~1;
   static constexpr size_t smemBytes = sizeof(double) * (size_t)(constDoubles + T * ST);
   static constexpr int threads = (W + QW) * 32;
@@ -193,9 +191,9 @@ __device__ __forceinline__ void sweep_epilogue(const Constants &c, const DeviceS
 // linearize_kernel), four steps ahead of the sweep, and writes it to the trajectory's record buffer; the matrix warps
 // stage it through the same bulk copies as before.  The separate linearize launch (0.115 ms of the 1.06 ms iteration)
 // is then skipped by the iteration loop; white-box calls (BW_SINGLE) use the records they are given.
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1, int FMODEL = -1>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int FMODEL = -1>
 __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) sweep_kernel(Constants c, DeviceState d, int mode) {
-  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
   static_assert(!QPQ || (NC == 4 && Cfg::TPW == 4 && W % 2 == 0), "quad QP: m = 4, sets of two matrix warps");
   using L = typename Cfg::L;
   constexpr int G = Cfg::G, R = Cfg::R, TPW = Cfg::TPW, T = Cfg::T, RS = Cfg::RS, ST = Cfg::ST;
@@ -922,20 +920,20 @@ __global__ void __launch_bounds__(SweepCfg<NS, NC, PAT, W, QPQ>::threads, MINB) 
   }
 }
 
-template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int SMOD = -1, int FMODEL = -1>
+template <int NS, int NC, class PAT, int W, int MINB, bool QPQ = false, int FMODEL = -1>
 cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cudaStream_t st) {
-  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ, SMOD>;
+  using Cfg = SweepCfg<NS, NC, PAT, W, QPQ>;
   static_assert(QPQ || Cfg::T <= 32, "one QP-warp lane per trajectory");
   static_assert(NS + 1 <= Cfg::G * Cfg::R, "V_x rides as an extra row");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD, FMODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NS, NC, PAT, W, MINB, QPQ, FMODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int blocks = (d.n_slots + Cfg::T - 1) / Cfg::T;
-  sweep_kernel<NS, NC, PAT, W, MINB, QPQ, SMOD, FMODEL><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
+  sweep_kernel<NS, NC, PAT, W, MINB, QPQ, FMODEL><<<blocks, Cfg::threads, Cfg::smemBytes, st>>>(c, d, mode);
   return cudaGetLastError();
 }
 
@@ -946,12 +944,9 @@ cudaError_t launch_sweep(const Constants &c, const DeviceState &d, int mode, cud
 // SLOWER on B200 (0.815 ms against 0.571 ms for the headline batch, profiles/r02_sweep_quad_qp.txt): the quad-parallel
 // BoxQP is a chain of shuffle round trips (1 575 warp-instructions per step at 7.3 cycles each against 1 900 at 3.5 for
 // the one-lane-per-trajectory QP warp), and eight matrix warps per SM run 9 % slower than seven.  Default: one QP warp.
-static int sweep_variant() {
-  static const int v = [] {
-    const char *e = std::getenv("CDDP_B200_SWEEP_VARIANT");
-    return (e && std::string(e) == "quad") ? 0 : 1;
-  }();
-  return v;
+static int sweep_variant() {  // read at every launch (not cached): the parity test of the variant switches it per solve
+  const char *e = std::getenv("CDDP_B200_SWEEP_VARIANT");
+  return (e && std::string(e) == "quad") ? 0 : 1;
 }
 
 // Fused linearisation is OPT-IN (cddp_b200_set_fused_linearization, or CDDP_B200_FUSED_LINEARIZE=1 for every handle): it passes the same parity tests — the lock-step run of the
@@ -981,7 +976,7 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
     if (c.model == CDDP_B200_MODEL_QUADROTOR) {
       if (sweep_variant() == 0) return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 8, 1, true>(c, d, mode, st);
       if (c.fuse_lin || sweep_fused_enabled())
-        return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1, false, -1, CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
+        return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1, false, CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
       return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     }
     if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);

@@ -562,3 +562,32 @@ def test_fused_linearization_changes_nothing(cddp, problems):
         s.close()
     for key in ("X", "U", "K", "cost", "iterations", "status", "alpha", "reg", "inf_du"):
         assert np.array_equal(out[0][key], out[1][key]), key
+
+
+def test_quad_qp_sweep_variant_against_the_oracle(cddp, ob, problems, monkeypatch):
+    """The 12-warp warp-specialised sweep (four QP warps, four lanes per trajectory, set-level named barriers, setmaxnreg;
+    CDDP_B200_SWEEP_VARIANT=quad, measured slower and therefore not the default) stays covered: one sweep
+    against the oracle, and a whole solve against the default kernel — same decisions, costs to roundoff (its masked
+    inverse is a different cofactor expansion, so results are not bitwise those of the one-QP-warp kernel)."""
+    B = 37
+    cfg = problems.make_config("quadrotor", batch=B, horizon=45)
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"])
+    res = {}
+    for variant in ("quad", ""):
+        monkeypatch.setenv("CDDP_B200_SWEEP_VARIANT", variant)
+        s, opts = make(cddp, cfg, B, max_iterations=12)
+        s.initialize()
+        s.linearize()
+        s.backward_pass()
+        sw, K, k = s.get_sweep(), s.get_solution()["K"], s.get_feedforward()
+        for b in range(0, B, 6):
+            r = ob.backward_pass(P, oo, cfg["X0"][b], cfg["U0"][b], cfg["xref"][b], opts["reg_initial_value"])
+            assert r["ok"] and sw["ok"][b] == 1
+            assert rel_err(K[b], r["K"]) < STEP_TOL and rel_err(k[b], r["k"]) < STEP_TOL and rel_err(sw["dV"][b], r["dV"]) < STEP_TOL
+        s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        s.solve()
+        res[variant] = s.get_solution()
+        s.close()
+    np.testing.assert_array_equal(res["quad"]["iterations"], res[""]["iterations"])
+    np.testing.assert_array_equal(res["quad"]["alpha"], res[""]["alpha"])
+    assert np.max(np.abs(res["quad"]["cost"] - res[""]["cost"]) / np.abs(res[""]["cost"])) < 1e-9
