@@ -184,6 +184,8 @@ __device__ __forceinline__ void sweep_epilogue(const Constants &c, const DeviceS
   }
 }
 
+#include "sweep_inline.cuh"
+
 // FMODEL >= 0 (one-QP-warp layout, a built-in model's structured records): FUSED LINEARISATION (SURVEY 8f N2,
 // clddp_solver.cpp:113-118 computes A, B inside the sweep's loop).  The QP warp is idle from barrier 2 to barrier 1 — while
 // the matrix warps run phases C and A1, 40 % of the step — and holds no matrix state, so its lane q forms ONE record of
@@ -963,6 +965,12 @@ static bool sweep_fused_enabled() {
   return v;
 }
 
+// CDDP_B200_INLINE_SWEEP=0 restores the warp-specialised kernel for m = 1 (A-B timing; read per launch)
+static bool inline_sweep_enabled() {
+  const char *e = std::getenv("CDDP_B200_INLINE_SWEEP");
+  return !(e && std::string(e) == "0");
+}
+
 // true if launch_backward(BW_ITERATE) forms the linearisation records itself (the iteration loop then skips linearize)
 bool backward_fuses_linearization(const Constants &c, const DeviceState &d) {
   return d.layout == RECORDS_STRUCTURED && c.model == CDDP_B200_MODEL_QUADROTOR && sweep_variant() != 0 &&
@@ -979,12 +987,16 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
         return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1, false, CDDP_B200_MODEL_QUADROTOR>(c, d, mode, st);
       return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     }
-    if (c.model == CDDP_B200_MODEL_CARTPOLE) return launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
+    if (c.model == CDDP_B200_MODEL_CARTPOLE)  // one control: inline subproblem, no QP warp, no CTA barrier (sweep_inline.cuh)
+      return inline_sweep_enabled() ? launch_sweep_inline<4, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 2>(c, d, mode, st)
+                                    : launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
     if (c.model == CDDP_B200_MODEL_UNICYCLE) return launch_sweep<3, 2, ModelPattern<CDDP_B200_MODEL_UNICYCLE>, 4, 4>(c, d, mode, st);
   } else {
-    if (n == 2 && m == 1) return launch_sweep<2, 1, DensePattern, 4, 4>(c, d, mode, st);
+    if (n == 2 && m == 1)
+      return inline_sweep_enabled() ? launch_sweep_inline<2, DensePattern, 2>(c, d, mode, st) : launch_sweep<2, 1, DensePattern, 4, 4>(c, d, mode, st);
     if (n == 3 && m == 2) return launch_sweep<3, 2, DensePattern, 4, 4>(c, d, mode, st);
-    if (n == 4 && m == 1) return launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
+    if (n == 4 && m == 1)
+      return inline_sweep_enabled() ? launch_sweep_inline<4, DensePattern, 2>(c, d, mode, st) : launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 4 && m == 2) return launch_sweep<4, 2, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 6 && m == 3) return launch_sweep<6, 3, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 13 && m == 4) {
