@@ -965,10 +965,15 @@ static bool sweep_fused_enabled() {
   return v;
 }
 
-// CDDP_B200_INLINE_SWEEP=0 restores the warp-specialised kernel for m = 1 (A-B timing; read per launch)
-static bool inline_sweep_enabled() {
+// One-control models: the inline kernel (sweep_inline.cuh) where the subproblem is a division (no control box:
+// cartpole 1024 x 100 steps 0.116 -> 0.073 ms, 16384: 0.303 -> 0.226 ms), the warp-specialised kernel where it is the
+// BoxQP iteration, which the inline kernel would run redundantly on every lane and divergently across the trajectories of
+// a warp (pendulum 1 x 500 steps: 0.516 vs 0.588 ms; 4096: 0.572 vs 0.773 ms).  CDDP_B200_INLINE_SWEEP=0 / =1 forces
+// one of them (A-B timing and the both-kernels parity test; read per launch).
+static bool inline_sweep_enabled(const Constants &c) {
   const char *e = std::getenv("CDDP_B200_INLINE_SWEEP");
-  return !(e && std::string(e) == "0");
+  if (e && (e[0] == '0' || e[0] == '1') && e[1] == 0) return e[0] == '1';
+  return !c.has_box;
 }
 
 // true if launch_backward(BW_ITERATE) forms the linearisation records itself (the iteration loop then skips linearize)
@@ -988,15 +993,15 @@ cudaError_t launch_backward_fast(const Constants &c, const DeviceState &d, int m
       return launch_sweep<13, 4, ModelPattern<CDDP_B200_MODEL_QUADROTOR>, 7, 1>(c, d, mode, st);
     }
     if (c.model == CDDP_B200_MODEL_CARTPOLE)  // one control: inline subproblem, no QP warp, no CTA barrier (sweep_inline.cuh)
-      return inline_sweep_enabled() ? launch_sweep_inline<4, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 2>(c, d, mode, st)
+      return inline_sweep_enabled(c) ? launch_sweep_inline<4, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 2>(c, d, mode, st)
                                     : launch_sweep<4, 1, ModelPattern<CDDP_B200_MODEL_CARTPOLE>, 7, 2>(c, d, mode, st);
     if (c.model == CDDP_B200_MODEL_UNICYCLE) return launch_sweep<3, 2, ModelPattern<CDDP_B200_MODEL_UNICYCLE>, 4, 4>(c, d, mode, st);
   } else {
     if (n == 2 && m == 1)
-      return inline_sweep_enabled() ? launch_sweep_inline<2, DensePattern, 2>(c, d, mode, st) : launch_sweep<2, 1, DensePattern, 4, 4>(c, d, mode, st);
+      return inline_sweep_enabled(c) ? launch_sweep_inline<2, DensePattern, 2>(c, d, mode, st) : launch_sweep<2, 1, DensePattern, 4, 4>(c, d, mode, st);
     if (n == 3 && m == 2) return launch_sweep<3, 2, DensePattern, 4, 4>(c, d, mode, st);
     if (n == 4 && m == 1)
-      return inline_sweep_enabled() ? launch_sweep_inline<4, DensePattern, 2>(c, d, mode, st) : launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
+      return inline_sweep_enabled(c) ? launch_sweep_inline<4, DensePattern, 2>(c, d, mode, st) : launch_sweep<4, 1, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 4 && m == 2) return launch_sweep<4, 2, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 6 && m == 3) return launch_sweep<6, 3, DensePattern, 7, 2>(c, d, mode, st);
     if (n == 13 && m == 4) {

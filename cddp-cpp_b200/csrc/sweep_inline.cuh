@@ -99,14 +99,31 @@ __global__ void __launch_bounds__(W * 32) sweep_inline_kernel(Constants c, Devic
 
   while (__any_sync(0xffffffffu, run)) {
     const volatile double *rc = S + Cfg::oRec + buf * RS;
-    // ------------------------------------------------------------ P_B = V B, Q_uu, Q_u                       (:125,:128)
-    double PBr = 0.0;
+    // ------------------------------------------------------------ P_B = V B, P_A = V A                        (:124-125)
+    double PBr = 0.0, PAr[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) PAr[j] = 0.0;
     static_for<0, NS>([&](auto lc) {
       constexpr int l = decltype(lc)::value;
       if constexpr (PAT::brow(l)) PBr = fma(V[l], rc[L::idxB(l, 0)], PBr);
+      static_for<0, NS>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (PAT::a(l, j)) PAr[j] = fma(V[l], rc[L::idxA(l, j)], PAr[j]);
+      });
     });
-    if (has) S[Cfg::oPB + row] = PBr;
+    if (has) {
+      S[Cfg::oPB + row] = PBr;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) S[Cfg::oPA + row * NS + j] = PAr[j];
+    }
+    {
+      double l1 = 0.0;  // ||V_x||_1 of the value function entering this step (:194)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) l1 += fabs(V[j]);
+      nrm += isvx ? l1 : 0.0;
+    }
     __syncwarp();
+    // ------------------------------------------------------------ Q_uu, Q_u, Q_xx, Q_xu, Q_x                  (:126-128)
     double Quu = Rdt2;
     static_for<0, NS>([&](auto lc) {
       constexpr int l = decltype(lc)::value;
@@ -114,7 +131,28 @@ __global__ void __launch_bounds__(W * 32) sweep_inline_kernel(Constants c, Devic
     });
     const double Qu = rc[L::offLu] + Sv[Cfg::oPB + NS];
     const double un = rc[L::offU];
+    double col[NS], Qxx[NS], Qxu = 0.0;
+#pragma unroll
+    for (int l = 0; l < NS; ++l) col[l] = S[Cfg::oPA + l * NS + rr];
+    if (c.q_diag) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) Qxx[j] = (j == rr) ? qd : 0.0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) Qxx[j] = sQ[rr * NS + j];
+    }
+    static_for<0, NS>([&](auto lc) {
+      constexpr int l = decltype(lc)::value;
+      static_for<0, NS>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (PAT::a(l, j)) Qxx[j] = fma(col[l], rc[L::idxA(l, j)], Qxx[j]);
+      });
+      if constexpr (PAT::brow(l)) Qxu = fma(col[l], rc[L::idxB(l, 0)], Qxu);
+    });
+    const double Qx = rc[L::offLx + rr] + S[Cfg::oPA + NS * NS + rr];  // Q_x = l_x + A^T V_x
+    if (isrow) S[Cfg::oQux + row] = Qxu;
     // ------------------------------------------------------------ control-space subproblem, every lane   (:130-178)
+    // (after the loads above and with no barrier in between, so that its divide chain overlaps the Q_xx FMAs)
     double H[1], g[1], kk[1], Hk[1], Hinv[1];
     H[0] = Quu + reg;  // Q_uu_reg (:130-131)
     g[0] = Qu;
@@ -143,48 +181,6 @@ __global__ void __launch_bounds__(W * 32) sweep_inline_kernel(Constants c, Devic
     good = good && run;
     const double sq = fma(-reg, kk[0], Hk[0]);  // (Q_uu k) = (Q_uu_reg k) - reg k
     const double wq = sq + g[0];                // w = Q_uu k + Q_u
-    // ------------------------------------------------------------ P_A = V A, Q_xx, Q_xu, Q_x             (:124,:126-127)
-    double PAr[NS];
-#pragma unroll
-    for (int j = 0; j < NS; ++j) PAr[j] = 0.0;
-    static_for<0, NS>([&](auto lc) {
-      constexpr int l = decltype(lc)::value;
-      static_for<0, NS>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        if constexpr (PAT::a(l, j)) PAr[j] = fma(V[l], rc[L::idxA(l, j)], PAr[j]);
-      });
-    });
-    if (has) {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) S[Cfg::oPA + row * NS + j] = PAr[j];
-    }
-    {
-      double l1 = 0.0;  // ||V_x||_1 of the value function entering this step (:194)
-#pragma unroll
-      for (int j = 0; j < NS; ++j) l1 += fabs(V[j]);
-      nrm += isvx ? l1 : 0.0;
-    }
-    __syncwarp();
-    double col[NS], Qxx[NS], Qxu = 0.0;
-#pragma unroll
-    for (int l = 0; l < NS; ++l) col[l] = S[Cfg::oPA + l * NS + rr];
-    if (c.q_diag) {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) Qxx[j] = (j == rr) ? qd : 0.0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) Qxx[j] = sQ[rr * NS + j];
-    }
-    static_for<0, NS>([&](auto lc) {
-      constexpr int l = decltype(lc)::value;
-      static_for<0, NS>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        if constexpr (PAT::a(l, j)) Qxx[j] = fma(col[l], rc[L::idxA(l, j)], Qxx[j]);
-      });
-      if constexpr (PAT::brow(l)) Qxu = fma(col[l], rc[L::idxB(l, 0)], Qxu);
-    });
-    const double Qx = rc[L::offLx + rr] + S[Cfg::oPA + NS * NS + rr];  // Q_x = l_x + A^T V_x
-    if (isrow) S[Cfg::oQux + row] = Qxu;
     __syncwarp();  // Q_ux complete; every lane is done with this step's record
     // next step's record: the fetched one goes to the other buffer, the one after is requested
     if (run && t > 0) put(buf ^ 1);

@@ -591,3 +591,34 @@ def test_quad_qp_sweep_variant_against_the_oracle(cddp, ob, problems, monkeypatc
     np.testing.assert_array_equal(res["quad"]["iterations"], res[""]["iterations"])
     np.testing.assert_array_equal(res["quad"]["alpha"], res[""]["alpha"])
     assert np.max(np.abs(res["quad"]["cost"] - res[""]["cost"]) / np.abs(res[""]["cost"])) < 1e-9
+
+
+@pytest.mark.parametrize("name,B,box", [("cartpole", 37, False), ("cartpole", 21, True), ("pendulum", 19, True)])
+def test_one_control_sweep_kernels_agree_bitwise(cddp, ob, problems, monkeypatch, name, B, box):
+    """m = 1 has two sweep kernels: the inline one (scalar subproblem on every lane, no CTA barrier; default
+    without a control box) and the warp-specialised one (default with a box).  Both perform the reference's operations in
+    the same order, so a whole solve must agree BITWISE between them, and one sweep of each is held to the oracle."""
+    cfg = problems.make_config(name, batch=B, horizon=40)
+    if name == "cartpole" and box:
+        cfg["spec"] = dict(cfg["spec"], lb=[-4.0], ub=[4.0])
+    assert (cfg["spec"].get("lb") is not None) == box
+    P, oo = ob.OracleProblem(cfg["spec"]), ob.make_options(**cfg["options"])
+    res = {}
+    for inline in ("1", "0"):
+        monkeypatch.setenv("CDDP_B200_INLINE_SWEEP", inline)
+        s, opts = make(cddp, cfg, B, max_iterations=15)
+        s.initialize()
+        s.linearize()
+        s.backward_pass()
+        sw, K, k = s.get_sweep(), s.get_solution()["K"], s.get_feedforward()
+        for b in range(0, B, 5):
+            r = ob.backward_pass(P, oo, cfg["X0"][b], cfg["U0"][b], cfg["xref"][b], opts["reg_initial_value"])
+            assert bool(r["ok"]) == (sw["ok"][b] == 1)
+            if r["ok"]:
+                assert rel_err(K[b], r["K"]) < STEP_TOL and rel_err(k[b], r["k"]) < STEP_TOL and rel_err(sw["dV"][b], r["dV"]) < STEP_TOL
+        s.set_instances(cfg["x0"], cfg["xref"], cfg["X0"], cfg["U0"])
+        s.solve()
+        res[inline] = s.get_solution()
+        s.close()
+    for key in ("X", "U", "K", "cost", "iterations", "status", "alpha", "reg", "inf_du"):
+        assert np.array_equal(res["1"][key], res["0"][key]), key
