@@ -1068,6 +1068,7 @@ int cddp_b200_ipddp_create_ex(const cddp_b200_problem *p, const cddp_b200_option
   AL(ip.lamT, B * n); AL(ip.dlamT, B * n); AL(ip.lamh, B);
   if (io->terminal_equality) {  // scratch of the one-sweep / (n+1)-column terminal-equality solve (ipddp_teq.cu)
     AL(ip.kvar, B * (n + 1) * N * m); AL(ip.pvar, B * (n + 1) * (N + 1) * n); AL(ip.rvar, B * N * m);
+    if (teq_small_case(n, m, (int)Dd)) { AL(ip.stage, B * N * teq_stage_stride(n, m)); AL(ip.teq_ran, B); }
   }
 #undef AL
   cudaError_t e = cudaMemcpy(drt, rt.data(), Dd * sizeof(int), cudaMemcpyHostToDevice);

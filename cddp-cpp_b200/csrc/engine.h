@@ -158,6 +158,11 @@ struct IpConstants {
   cddp_b200_ipddp_options io;
 };
 
+// doubles per stage record of the small terminal-equality kernels: Q_t | R_t | M_t | q_t | r_t | two residual maxima
+inline int teq_stage_stride(int n, int m) { return (n * n + m * m + n * m + n + m + 2 + 1) & ~1; }
+// (n, m, dual dimension) for which launch_ip_backward_teq takes the register-resident kernels
+inline bool teq_small_case(int n, int m, int dd) { return n == 3 && m == 2 && dd == 5; }
+
 struct IpDevice {
   double *Y[2], *S[2], *G[2];  // [B][N][d] duals, slacks, constraint values; double-buffered like X/U (cur[b] selects)
   double *ky, *ks;             // [B][N][d]
@@ -173,6 +178,8 @@ struct IpDevice {
   double *kvar;          // [B][n+1][N][m]   feed-forward of the p+1 sequential-LQR variants
   double *pvar;          // [B][n+1][N+1][n] costate of the variants
   double *rvar;          // [B][N][m]        condensed control gradient r_t
+  double *stage;         // [B][N][teq_stage_stride(n,m)] condensed stage cost of the register-resident kernels (ipddp_teq_small.cuh)
+  int *teq_ran;          // [B] the sweep kernel ran and succeeded for this instance in the current launch sequence
 };
 
 enum BackwardMode { BW_SINGLE = 0 /* one sweep, no retry, no iteration bookkeeping */, BW_ITERATE = 1 };

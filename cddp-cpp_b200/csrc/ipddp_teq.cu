@@ -12,6 +12,9 @@
 #include "kernels_ipddp.cuh"
 #include "ldlt_small.cuh"
 
+#include <cstdlib>
+#include <string>
+
 namespace cddp_b200 {
 
 namespace {
@@ -19,6 +22,15 @@ namespace {
 using namespace kern;
 
 constexpr int kTeqThreads = 128;
+
+#include "ipddp_teq_small.cuh"
+
+// CDDP_B200_TEQ_KERNEL=shared keeps the shared-memory kernel where the register-resident one applies (A-B timing and the
+// both-kernels test; read per launch)
+static bool teq_reg_enabled() {
+  const char *e = std::getenv("CDDP_B200_TEQ_KERNEL");
+  return !(e && std::string(e) == "shared");
+}
 
 __host__ __device__ inline int teq_stage_doubles(int n, int m, int D, int rs) {
   const int sweep = rs + n + 3 * D;                                 // record | x | y | s | g
@@ -719,7 +731,9 @@ cudaError_t launch_teq_g(const Constants &c, const DeviceState &d, const IpConst
 cudaError_t launch_ip_backward_teq(const Constants &c, const DeviceState &d, const IpConstants &ic, const IpDevice &ip, int mode,
                                    cudaStream_t st) {
   if (d.n == 2 && d.m == 1) return launch_teq_g<8, 2, 1>(c, d, ic, ip, mode, st);
-  if (d.n == 3 && d.m == 2 && ic.d == 5) return launch_teq_g<16, 3, 2, 5>(c, d, ic, ip, mode, st);  // BASELINE config #4
+  static_assert(TeqStage<3, 2>::stride == 26, "engine.h teq_stage_stride");
+  if (teq_small_case(d.n, d.m, ic.d))  // BASELINE config #4
+    return teq_reg_enabled() ? launch_teq_reg<3, 2, 5>(c, d, ic, ip, mode, st) : launch_teq_g<16, 3, 2, 5>(c, d, ic, ip, mode, st);
   if (d.n == 3 && d.m == 2) return launch_teq_g<16, 3, 2>(c, d, ic, ip, mode, st);
   if (d.n == 4 && d.m == 1) return launch_teq_g<16, 4, 1>(c, d, ic, ip, mode, st);
   if (d.n * d.n <= 64) return launch_teq_g<16, 0, 0>(c, d, ic, ip, mode, st);
