@@ -232,3 +232,40 @@ def test_work_list_compaction_changes_nothing(cddp, problems):
     assert its.min() < its.max()
     for key in ("X", "U", "cost", "iterations", "status"):
         assert np.array_equal(out[0][key], out[1][key]), key
+
+
+def test_terminal_equality_kernels_agree(cddp, problems, monkeypatch):
+    """Config 4's backward pass has two implementations: the three-launch register-resident path (time-parallel
+    stage cost -> sweep with one lane per sequential-LQR variant -> time-parallel gains; the default at n = 3, m = 2, d = 5)
+    and the shared-memory kernel (CDDP_B200_TEQ_KERNEL=shared).  Same statements in the same order: after three iterations
+    every gain and every per-instance scalar agrees to roundoff; and the default path is bit-identical under work-list
+    compaction (its stage / gains kernels index the work list per (slot, t))."""
+    B = 37  # not a multiple of the 8 trajectories per warp of the sweep kernel
+    cfg = problems.make_config("unicycle_obstacle_teq", batch=B, horizon=70)
+    out = {}
+    for kern in ("reg", "shared"):
+        monkeypatch.setenv("CDDP_B200_TEQ_KERNEL", kern)
+        s, _ = make(cddp, cfg, B)
+        s.initialize()
+        s.iterate(3)
+        s.linearize()
+        s.backward_pass()
+        out[kern] = dict(s.get_ipddp_gains(), ku=s.get_feedforward(), Ku=s.get_solution()["K"], **{
+            k: s.get_ipddp_solution()[k] for k in ("alpha_pr_max", "alpha_du_max", "inf_pr", "inf_comp", "step_norm")},
+            inf_du=s.get_solution()["inf_du"], ok=s.get_sweep()["ok"])
+        s.close()
+    assert (out["reg"]["ok"] == 1).all() and (out["shared"]["ok"] == 1).all()
+    for key in out["reg"]:
+        a, b_ = np.asarray(out["reg"][key], dtype=float), np.asarray(out["shared"][key], dtype=float)
+        assert np.max(np.abs(a - b_) / np.maximum(np.abs(b_), 1e-12)) < 1e-9, key
+    monkeypatch.setenv("CDDP_B200_TEQ_KERNEL", "reg")
+    res = []
+    for interval in (1, 0):
+        s, _ = make(cddp, cfg, B, max_iterations=60)
+        s.set_poll_interval(interval)
+        s.solve()
+        res.append(dict(s.get_solution(), **s.get_ipddp_gains()))
+        s.close()
+    assert res[0]["iterations"].min() < res[0]["iterations"].max()
+    for key in ("X", "U", "K", "cost", "iterations", "status", "ky", "ks", "Ky", "Ks"):
+        assert np.array_equal(res[0][key], res[1][key]), key
