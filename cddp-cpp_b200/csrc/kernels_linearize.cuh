@@ -35,9 +35,11 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(Constants c, DeviceSt
   const long long wid = (long long)blockIdx.x * warps_per_cta + warp;
   if (wid >= (long long)d.n_slots * chunks) return;
   const int b = slot_instance(d, (int)(wid / chunks)), t0 = (int)(wid % chunks) * 32, t = t0 + lane;
-  if (!force && (d.status[b] != CDDP_B200_STATUS_RUNNING || d.lin_valid[b])) return;  // warp-uniform
+  // (the three per-instance words are requested together: with cur read after the early return the warp paid one more
+  // dependent memory round trip before its first operand load — half of the kernel's stall samples are these chains)
+  const int status = d.status[b], valid = d.lin_valid[b], cur = d.cur[b];
+  if (!force && (status != CDDP_B200_STATUS_RUNNING || valid)) return;  // warp-uniform
   double *row = lin_smem + ((size_t)warp * 32 + lane) * PSH;
-  const int cur = d.cur[b];
   const bool rec = t < N;
   double Fx[NS * NS], Fu[NS * NC], lxv[NS], luv[NC], u[NC];
   if (t <= N) {
