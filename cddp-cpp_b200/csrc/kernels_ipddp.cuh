@@ -359,6 +359,11 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
       u[i] = (pU[i] + alpha_pr * pk[i]) + acc;
     }
     double acc_t = 0.0;
+    // With a compile-time dual dimension the candidate slacks / duals / constraint values of the timestep are kept in
+    // registers and stored after the row loop: stored row by row (pass 2), every row's operand loads were ordered behind the
+    // previous row's stores — five dependent HBM round trips per replayed timestep instead of one.
+    double sv[DC ? DC : 1], yv[DC ? DC : 1], gv[DC ? DC : 1];
+#pragma unroll(DC ? DC : 1)
     for (int q = 0; q < D; ++q) {  // slack / dual trial step with the fraction-to-boundary test (:1620-1647)
       const size_t e = (size_t)t * D + q;
       double a1 = 0.0, a2 = 0.0;
@@ -384,10 +389,24 @@ __device__ __forceinline__ void ip_rollout(const Constants &c, const DeviceState
         st.maxys = max_ref(st.maxys, yn * sn);
         st.minys = min_ref(st.minys, yn * sn);
       }
-      if (wr) {
+      if constexpr (DC > 0) {
+        sv[q] = sn;
+        yv[q] = yn;
+        gv[q] = g;
+      } else if (wr) {
         Sc[e] = sn;
         Yc[e] = yn;
         Gc[e] = g;
+      }
+    }
+    if constexpr (DC > 0) {
+      if (wr) {
+#pragma unroll
+        for (int q = 0; q < DC; ++q) {
+          Sc[(size_t)t * DC + q] = sv[q];
+          Yc[(size_t)t * DC + q] = yv[q];
+          Gc[(size_t)t * DC + q] = gv[q];
+        }
       }
     }
     st.theta += acc_t;
