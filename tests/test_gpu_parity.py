@@ -593,12 +593,13 @@ def test_quad_qp_sweep_variant_against_the_oracle(cddp, ob, problems, monkeypatc
     assert np.max(np.abs(res["quad"]["cost"] - res[""]["cost"]) / np.abs(res[""]["cost"])) < 1e-9
 
 
-@pytest.mark.parametrize("name,B,box", [("cartpole", 37, False), ("cartpole", 21, True), ("pendulum", 19, True)])
-def test_one_control_sweep_kernels_agree_bitwise(cddp, ob, problems, monkeypatch, name, B, box):
+@pytest.mark.parametrize("name,B,box,N", [("cartpole", 37, False, 40), ("cartpole", 21, True, 40), ("pendulum", 19, True, 40),
+                                          ("cartpole", 3, False, 1), ("pendulum", 9, True, 2)])
+def test_one_control_sweep_kernels_agree_bitwise(cddp, ob, problems, monkeypatch, name, B, box, N):
     """m = 1 has two sweep kernels: the inline one (scalar subproblem on every lane, no CTA barrier; default
     without a control box) and the warp-specialised one (default with a box).  Both perform the reference's operations in
     the same order, so a whole solve must agree BITWISE between them, and one sweep of each is held to the oracle."""
-    cfg = problems.make_config(name, batch=B, horizon=40)
+    cfg = problems.make_config(name, batch=B, horizon=N)  # N = 1, 2: the record double buffer has nothing to prefetch
     if name == "cartpole" and box:
         cfg["spec"] = dict(cfg["spec"], lb=[-4.0], ub=[4.0])
     assert (cfg["spec"].get("lb") is not None) == box
