@@ -234,6 +234,30 @@ def test_work_list_compaction_changes_nothing(cddp, problems):
         assert np.array_equal(out[0][key], out[1][key]), key
 
 
+@pytest.mark.parametrize("N", [1, 2, 9])
+def test_terminal_equality_kernels_agree_at_short_horizons(cddp, problems, monkeypatch, N):
+    """Horizons below the depth of the rollout ring (8) and below the number of lanes of a trajectory (4): one backward pass from
+    the initial trajectory, register-resident path against the shared-memory kernel."""
+    B = 11
+    cfg = problems.make_config("unicycle_obstacle_teq", batch=B, horizon=N)
+    out = {}
+    for kern in ("reg", "shared"):
+        monkeypatch.setenv("CDDP_B200_TEQ_KERNEL", kern)
+        s, _ = make(cddp, cfg, B)
+        s.initialize()
+        s.linearize()
+        s.backward_pass()
+        out[kern] = dict(s.get_ipddp_gains(), ku=s.get_feedforward(), Ku=s.get_solution()["K"], **{
+            k: s.get_ipddp_solution()[k] for k in ("alpha_pr_max", "alpha_du_max", "inf_pr", "inf_comp", "step_norm")},
+            inf_du=s.get_solution()["inf_du"], ok=s.get_sweep()["ok"])
+        s.close()
+    assert np.array_equal(out["reg"]["ok"], out["shared"]["ok"]) and (out["reg"]["ok"] == 1).any()
+    good = out["reg"]["ok"] == 1
+    for key in out["reg"]:
+        a, b_ = np.asarray(out["reg"][key], dtype=float)[good], np.asarray(out["shared"][key], dtype=float)[good]
+        assert np.max(np.abs(a - b_) / np.maximum(np.abs(b_), 1e-12)) < 1e-9, key
+
+
 def test_terminal_equality_kernels_agree(cddp, problems, monkeypatch):
     """Config 4's backward pass has two implementations: the three-launch register-resident path (time-parallel
     stage cost -> sweep with one lane per sequential-LQR variant -> time-parallel gains; the default at n = 3, m = 2, d = 5)
