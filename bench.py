@@ -288,7 +288,16 @@ def measure_iterations(cddp, problems, device, name, global_batch, rank, world, 
         ach = alg / (kms["backward"] * 1e-3) / 1e9
         out["roofline"] = {"kernel": "ip_backward" if ip else "backward_sweep", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                            "frac": ach / peak, "algorithmic_bytes_per_step": per_step, "algorithmic_bytes_per_launch": alg,
-                           "ms_per_launch": kms["backward"]}
+                           "ms_per_launch": kms["backward"], "traffic": None}
+        tf = os.path.join(ROOT, "profiles", "ip_backward_traffic.json" if ip else "backward_traffic.json")
+        try:  # dram__bytes_read + dram__bytes_write of the backward pass from the committed ncu capture of this workload
+            with open(tf) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B and tj.get("config") == name:
+                out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                out["roofline"]["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
     s.close()
     if with_cpu and rank == 0 and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
